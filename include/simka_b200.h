@@ -1,0 +1,185 @@
+/*
+ * simka_b200.h -- C ABI of the B200-native Simka hot path (libsimka_b200.so).
+ *
+ * The reference (GATB/simka) has no in-process plugin ABI for this path: its seams are the
+ * simkaCount / simkaMerge process CLIs plus temp files, and the GATB-core C++ template
+ * interfaces.  This header is the boundary a reference maintainer binds to
+ * replace those stages in-process; every entry point names the reference code it replaces
+ * (paths relative to the reference root; GC/ = thirdparty/gatb-core/gatb-core/src/gatb/).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * SIMKA_ERR_* code and never throws; the caller owns all host buffers; the library owns all
+ * device memory; one context per GPU; a context is not thread-safe.  There is NO CPU fallback:
+ * if no CUDA device is usable, simka_gpu_create fails with SIMKA_ERR_CUDA.
+ */
+#ifndef SIMKA_B200_H
+#define SIMKA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMKA_OK 0
+#define SIMKA_ERR_INVALID (-1)   /* bad argument / call order                         */
+#define SIMKA_ERR_CUDA (-2)      /* CUDA runtime failure (see simka_gpu_last_error)   */
+#define SIMKA_ERR_OVERFLOW (-3)  /* an on-chip table overflowed (should never happen) */
+#define SIMKA_ERR_NOMEM (-4)
+#define SIMKA_ERR_IO (-5)
+
+typedef struct simka_ctx simka_ctx;
+
+/* Replaces the argv of simkaCount / simkaMerge (src/SimkaCount.cpp:80-98, src/SimkaMerge.cpp:1530-1544):
+ * -kmer-size, -nb-datasets, -abundance-min/-max, -simple-dist, -complex-dist. */
+typedef struct {
+    int32_t kmer_size;        /* 2..31 (span-32 k-mers, GC/kmer/impl/Model.hpp:100)                 */
+    int32_t nb_samples;       /* N, 1..65535                                                       */
+    int64_t abundance_min;    /* keep a k-mer of a sample iff min <= count <= max                  */
+    int64_t abundance_max;    /*   (src/minikc/MiniKC.hpp:56)                                       */
+    int32_t simple_dist;      /* chord / hellinger / kulczynski accumulators                       */
+    int32_t complex_dist;     /* whittaker / jensen-shannon / canberra accumulators                */
+    int32_t device;           /* CUDA device ordinal                                               */
+    int32_t shard_rank;       /* multi-GPU: this context keeps hash-buckets rank of shard_count    */
+    int32_t shard_count;      /*   (the reference's one-merge-process-per-partition split,         */
+                              /*    src/SimkaPotara.hpp:991-1058); 0 or 1 = no sharding            */
+    int32_t reserved;
+    uint64_t expected_kmers_per_sample; /* sizing hint for the merge granularity, 0 = derive       */
+} simka_params;
+
+/* Replaces the 4 lines of count_synchro/<id>.ok (src/SimkaCount.cpp:303-317,355-368). */
+typedef struct {
+    uint64_t nb_reads;
+    uint64_t nb_distinct;     /* distinct solid k-mers         */
+    uint64_t nb_kmers;        /* sum of solid abundances       */
+    uint64_t chord_n2;        /* sum of squared abundances     */
+} simka_sample_totals;
+
+/* Replaces SimkaStatistics (src/core/SimkaDistance.hpp:68-139).  Host arrays owned by the caller.
+ * sym = N(N+1)/2 entries, idx = j + (N-1) i - i(i-1)/2 for i<j; sq = N*N row-major.
+ * Arrays of a disabled distance family may be NULL. */
+typedef struct {
+    int32_t nb_samples, simple_dist, complex_dist, reserved;
+    uint64_t nb_distinct_kmers, nb_shared_kmers;  /* _nbDistinctKmers, _nbSharedKmers              */
+    simka_sample_totals *totals;                  /* [N]                                           */
+    uint64_t *distinct_shared;                    /* sym  _matrixNbDistinctSharedKmers             */
+    uint64_t *braycurtis_num;                     /* sym  _brayCurtisNumerator                     */
+    uint64_t *nb_shared;                          /* sq   _matrixNbSharedKmers                     */
+    uint64_t *chord_ninj;                         /* sq   _chord_NiNj (integer-valued)             */
+    uint64_t *hellinger;                          /* sq   _hellinger_SqrtNiNj                      */
+    uint64_t *kulczynski;                         /* sq   _kulczynski_minNiNj (upper triangle)     */
+    uint64_t *canberra;                           /* sq   _canberra                                */
+    uint64_t *whittaker;                          /* sq   _whittaker_minNiNj                       */
+    double *kullback_leibler;                     /* sq   _kullbackLeibler                         */
+} simka_stats_view;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+int simka_gpu_create(simka_ctx **ctx, const simka_params *params);
+void simka_gpu_destroy(simka_ctx *ctx);
+/* forget all samples and accumulators but keep the device work buffers (next run of the same shape) */
+int simka_gpu_reset(simka_ctx *ctx);
+const char *simka_gpu_last_error(const simka_ctx *ctx);
+/* pinned host buffers for the streaming path (cudaHostAlloc / cudaFreeHost) */
+int simka_gpu_host_alloc(void **ptr, size_t bytes);
+int simka_gpu_host_free(void *ptr);
+
+/* ---- stage 1: replaces `simkaCount` for one sample -----------------------------------------
+ * (src/SimkaCount.cpp:174-353 -> SortingCountAlgorithm, GC/kmer/impl/SortingCountAlgorithm.cpp:600-653,
+ *  -> SimkaCompressedProcessor::process, src/minikc/MiniKC.hpp:54-79)
+ *
+ * Reads of a sample arrive as a 2-bit packed base stream + a 1-bit/base "bad" mask:
+ *   base i of the stream lives in packed[i/32] at bits [62-2*(i%32), 63-2*(i%32)] (first base most
+ *   significant, code A=0 C=1 T=2 G=3 = (ascii>>1)&3, GC/tools/misc/api/Data.hpp:179);
+ *   bad[i/32] bit (31-i%32) is 1 for any char outside ACGTacgt and for the ONE separator position
+ *   that must follow every read; positions >= n_bases of the last word are bad.
+ * Both arrays must have n_words+1 entries (the last entry: packed 0, bad 0xFFFFFFFF).
+ * simka_pack_reads() below produces exactly this layout.  A sample may be pushed in several
+ * calls (k-mers never span two pushes).  The copy is asynchronous when the buffers are pinned;
+ * they must stay valid until simka_gpu_finish_sample(sample_id) returns.  Two samples may be in
+ * flight: pushing sample s+1 before finishing sample s overlaps its copy with the kernels of s. */
+int simka_gpu_push_reads(simka_ctx *ctx, int sample_id, const uint64_t *packed, const uint32_t *bad,
+                         uint64_t n_words, uint64_t n_reads);
+/* Same layout, but the buffers already live in device memory of this context's GPU (zero copy; they
+ * must stay valid and unchanged until simka_gpu_finish_sample returns). */
+int simka_gpu_push_reads_device(simka_ctx *ctx, int sample_id, const uint64_t *d_packed, const uint32_t *d_bad,
+                                uint64_t n_words, uint64_t n_reads);
+/* Same, from concatenated ASCII reads (read r = seqs[read_off[r] .. read_off[r+1])); the 2-bit
+ * packing runs on the GPU (replaces the per-char encode of GC/kmer/impl/Model.hpp:726-765). */
+int simka_gpu_push_ascii(simka_ctx *ctx, int sample_id, const char *seqs, const uint64_t *read_off,
+                         uint64_t n_reads);
+/* Counts the pushed reads of the sample: canonical k-mers, exact multiset count, abundance filter,
+ * per-sample totals.  The filtered (k-mer,count) list stays resident in HBM. */
+int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *out);
+
+/* parity hook: the sample's solid k-mers in increasing k-mer order with their counts, i.e. the
+ * decoded content of the solid/part_P/__p__I.gz files (src/SimkaCount.cpp:248-257).  Call with kmers=NULL to
+ * get the size.  Only this shard's k-mers are returned when sharded. */
+int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers, uint32_t *counts, uint64_t *n);
+
+/* ---- barrier between the stages: global per-sample totals -----------------------------------
+ * (SimkaStatistics ctor reads count_synchro/<id>.ok of ALL samples, src/core/SimkaDistance.cpp:116-151)
+ * Single GPU: nothing to do.  Sharded: all-reduce(sum) the three counters over the shards
+ * (nb_reads is per sample, not summed) and hand the global values back before the merge. */
+int simka_gpu_get_totals(simka_ctx *ctx, simka_sample_totals *out /* [N] */);
+int simka_gpu_set_totals(simka_ctx *ctx, const simka_sample_totals *in /* [N] */);
+
+/* ---- stage 2: replaces `simkaMerge` over all of this shard's buckets ---------------------------
+ * (src/SimkaMerge.cpp:1164-1326 k-way merge + insert gate, SimkaCountProcessorSimple::process /
+ *  updateDistance{Default,Simple,Complex}, src/core/SimkaAlgorithm.hpp:200-516) */
+int simka_gpu_merge_and_accumulate(simka_ctx *ctx);
+/* Accumulators of this shard; element-wise sum over shards == the reference's mainStats
+ * (src/SimkaPotara.hpp:1161-1174, src/core/SimkaDistance.cpp:156-213). */
+int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out);
+
+/* device-side time per kernel, in ms, summed over the samples since create/reset (CUDA events on
+ * the context's stream, recorded around each launch) */
+typedef struct {
+    float extract_count_ms, extract_scatter_ms; /* K1 canonical k-mer extraction: count pass, scatter pass   */
+    float part_count_ms, part_scatter_ms;       /* K2 level-2 partition: count pass, scatter pass            */
+    float bin_count_ms;                         /* K3 per-bin exact count + filter                            */
+    float compact_ms;                           /* survivors -> per-sample list                               */
+    float merge_ms;                             /* K4 merge + N x N accumulate (+ Whittaker one-sided)        */
+    float samples_ms;                           /* stage 1 total (first to last kernel of every sample)       */
+    float total_ms;                             /* samples_ms + merge_ms                                      */
+    uint64_t kmers_in;                          /* valid k-mer occurrences kept by this shard                 */
+    uint64_t entries;                           /* solid (sample,k-mer) entries after the abundance filter    */
+    uint64_t distinct_kmers;                    /* distinct solid k-mers over all samples                     */
+    uint64_t pairs;                             /* sample pairs enumerated by the accumulate kernel           */
+    uint64_t kernel_launches;
+} simka_timings;
+int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out);
+/* the CUDA stream all of this context's kernels run on (for external CUDA-event timing) */
+void *simka_gpu_stream(simka_ctx *ctx);
+
+/* ---- host helpers (no GPU needed) ---------------------------------------------------------------- */
+
+/* words needed for reads of the given total length (one separator per read + pad word) */
+uint64_t simka_pack_words(uint64_t total_bases, uint64_t n_reads);
+/* 2-bit pack + bad mask in the layout simka_gpu_push_reads expects; multi-threaded.
+ * packed/bad must hold simka_pack_words()+1 entries.  Returns the number of words used. */
+uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n_reads,
+                          uint64_t *packed, uint32_t *bad, int nthreads);
+
+/* Replaces SimkaDistance + SimkaStatistics::outputMatrix (src/core/SimkaDistance.cpp:603-649,920-1226).
+ * Matrix order = the reference's output order: 15 default, +3 if simple, +3 if complex. */
+int simka_nb_matrices(const simka_stats_view *stats);
+const char *simka_matrix_name(const simka_stats_view *stats, int m);
+int simka_distance_matrix(const simka_stats_view *stats, int m, float *out /* N*N */);
+/* CSV text of dumpMatrix (src/core/SimkaDistance.cpp:653-699).  Returns the byte count needed. */
+size_t simka_matrix_csv(const simka_stats_view *stats, int m, const char *const *ids, char *buf, size_t cap);
+/* writes <dir>/<name>.csv.gz for every matrix, like outputMatrix */
+int simka_write_matrices(const simka_stats_view *stats, const char *const *ids, const char *out_dir);
+
+/* ---- SimkaMin: replaces ComputeDistanceManager::computeDistance_unsynch over all pairs ------------
+ * (src/simkaMin/SimkaMinDistance.hpp:190-303).  hashes/counts: n sketches of s entries, ascending,
+ * zero hashes at the front are padding (loadSketches :521-586).  Outputs n*n float32 row-major. */
+int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *counts, uint32_t n,
+                          uint32_t s, float *jaccard, float *braycurtis, float *kernel_ms);
+
+const char *simka_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

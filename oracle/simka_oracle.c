@@ -707,24 +707,34 @@ size_t orc_matrix_csv(const orc_run *r, int m, const char *const *ids, char *buf
 static void simkamin_pair(const uint64_t *h1, const uint32_t *c1, size_t n1,
                           const uint64_t *h2, const uint32_t *c2, size_t n2, uint32_t sketch_size,
                           float *jac, float *bc) {
-    size_t i = 0, j = 0;
     uint64_t nb_shared_distinct = 0, nb_distinct = 0, nb_shared_kmers = 0, nb_kmers = 0;
-    while (nb_distinct < sketch_size && i < n1 && j < n2) {
-        if (h1[i] < h2[j]) { nb_kmers += c1[i]; i++; }
-        else if (h1[i] > h2[j]) { nb_kmers += c2[j]; j++; }
-        else {
-            nb_shared_distinct++;
-            nb_kmers += c1[i]; nb_kmers += c2[j];
-            nb_shared_kmers += c1[i] < c2[j] ? c1[i] : c2[j];
-            i++; j++;
+    /* sketchSize = min of the two (zero-stripped) sizes (:204); iterator = (next, isDone) (:73-101) */
+    uint64_t ss = n1 < n2 ? n1 : n2;
+    (void)sketch_size;
+    if (n1 > 0 && n2 > 0) {
+        size_t i = 0, j = 0; /* items already fetched from each side */
+        uint64_t k1 = h1[i], k2 = h2[j]; uint32_t a1 = c1[i], a2 = c2[j]; i++; j++;
+        while (nb_distinct < ss) {
+            if (k1 > k2) {
+                nb_distinct += 1; nb_kmers += a2;
+                if (j >= n2) break;
+                k2 = h2[j]; a2 = c2[j]; j++;
+            } else if (k1 < k2) {
+                nb_distinct += 1; nb_kmers += a1;
+                if (i >= n1) break;
+                k1 = h1[i]; a1 = c1[i]; i++;
+            } else {
+                nb_distinct += 1; nb_kmers += (uint64_t)a1 + a2;
+                nb_shared_distinct += 1; nb_shared_kmers += a1 < a2 ? a1 : a2;
+                if (j >= n2 || i >= n1) break;
+                k1 = h1[i]; a1 = c1[i]; i++;
+                k2 = h2[j]; a2 = c2[j]; j++;
+            }
         }
-        nb_distinct++;
     }
-    if (nb_distinct < sketch_size) {
-        if (i < n1) { while (nb_distinct < sketch_size && i < n1) { nb_kmers += c1[i]; i++; nb_distinct++; } }
-        if (j < n2) { while (nb_distinct < sketch_size && j < n2) { nb_kmers += c2[j]; j++; nb_distinct++; } }
-    }
+    if (nb_distinct == 0) *jac = 1; else
     *jac = (float)(1 - (long double)nb_shared_distinct / (long double)nb_distinct);
+    if (nb_kmers == 0) *bc = 1; else
     *bc = (float)(1 - (long double)(2 * nb_shared_kmers) / (long double)nb_kmers);
 }
 

@@ -1,0 +1,66 @@
+"""In-tree build of libsimka_b200.so (hand-written CUDA for sm_100a + the C++ host side).
+
+`python -m simka_b200.build` or simka_b200.build.build().  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+LIBDIR = ROOT / "lib"
+LIB = LIBDIR / "libsimka_b200.so"
+SIMKA_BIN = ROOT / "bin" / "simka"
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-diag-suppress", "128",
+    "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built (no CPU fallback exists)")
+
+
+def _stale(target: Path, sources) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(s).stat().st_mtime > t for s in sources)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    srcs = [CSRC / "simka_gpu.cu", CSRC / "simka_host.cpp"]
+    deps = srcs + [CSRC / "kmer_device.cuh", ROOT.parent / "include" / "simka_b200.h"]
+    LIBDIR.mkdir(exist_ok=True)
+    if force or _stale(LIB, deps):
+        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, srcs), "-lz"]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    cli = CSRC / "simka_main.cpp"
+    if cli.exists():
+        SIMKA_BIN.parent.mkdir(exist_ok=True)
+        cdeps = deps + [cli, CSRC / "bank.hpp"]
+        if force or _stale(SIMKA_BIN, cdeps) or _stale(SIMKA_BIN, [LIB]):
+            cmd = [_nvcc(), "-O2", "-std=c++17", "-o", str(SIMKA_BIN), str(cli), f"-L{LIBDIR}", "-lsimka_b200",
+                   "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib", "-lz", "-lpthread"]
+            subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,1502 @@
+// simka_gpu.cu -- sm_100a kernels and the C ABI of the Simka hot path (see include/simka_b200.h).
+//
+// Pipeline (one context per GPU, everything on one CUDA stream + one copy stream):
+//
+//   per sample  push_reads      H2D of the 2-bit packed base stream (+ 1 bit/base bad mask)
+//               K1 extract      canonical k-mer per start position -> invertible hash h -> L1 bucket
+//                               (count pass, scan, scatter pass through a shared-memory sorted tile)
+//               K2 partition    L1 bucket -> fine bins (count, scan, scatter), bins ~1K keys
+//               K3 bin count    one CTA per bin: shared-memory hash table, exact multiset count,
+//                               abundance filter, per-sample totals, survivors compacted
+//   all samples merge           one CTA per merge bin: gather the N per-sample segments, group equal
+//                               k-mers in a shared-memory table (= the N-wide abundance vector, stored
+//                               sparse), enumerate sample pairs, update the N x N accumulators
+//
+// What each stage replaces in the reference is cited at the kernels.  No host fallback exists.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/simka_b200.h"
+#include "kmer_device.cuh"
+
+using simka::Mix;
+
+typedef unsigned long long ull;
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            ctx->set_error(std::string(#call) + ": " + cudaGetErrorString(e_));            \
+            return SIMKA_ERR_CUDA;                                                        \
+        }                                                                                 \
+    } while (0)
+
+namespace {
+
+constexpr int BLOCK = 256;
+constexpr int L1_KPT = 32;                   // K1: one packed word (32 start positions) per thread
+constexpr int L1_TILE = BLOCK * L1_KPT;      // 8192 keys
+constexpr int L2_KPT = 16;
+constexpr int L2_TILE = BLOCK * L2_KPT;      // 4096 keys
+constexpr int MAX_B = 1024;                  // max buckets per partition level
+constexpr int BIN_TARGET = 512;              // average keys per fine bin
+constexpr int CNT_SLOTS = 2048;              // K3 hash table slots
+constexpr int CNT_SUBPASS_KEYS = 1024;       // keys per sub-pass when a bin is oversized
+constexpr int CHIST = 1024;                  // dense abundance histogram bins (complex distances)
+constexpr int MRG_SLOTS = 2048;              // merge hash table slots
+constexpr int MRG_CAP = 2048;                // merge: grouped entries held in shared memory
+constexpr int MRG_TARGET = 768;              // average entries per merge bin
+constexpr int MRG_MAXN = 8192;               // samples supported by the shared-memory prefix arrays
+constexpr uint64_t EMPTY = ~0ull;
+
+struct KParams {
+    Mix mix;
+    int k;
+    int shard_rank, shard_count;
+};
+
+__device__ __forceinline__ bool shard_keep(uint64_t h, const KParams &kp) {
+    if (kp.shard_count <= 1) return true;
+    uint32_t x = (uint32_t)(simka::hash2(h) >> 32);
+    return (int)(((uint64_t)x * (uint32_t)kp.shard_count) >> 32) == kp.shard_rank;
+}
+
+// exclusive scan of a shared array of n (<= MAX_B*?) u32 values by the whole block, in place.
+// Returns the total in *total (shared).  n need not be a multiple of the block size.
+__device__ void block_exclusive_scan(uint32_t *a, int n, uint32_t *warp_tmp /*[BLOCK/32+1]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (n + BLOCK - 1) / BLOCK;
+    const int beg = min(tid * per, n), end = min(beg + per, n);
+    uint32_t sum = 0;
+    for (int i = beg; i < end; i++) sum += a[i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) warp_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < BLOCK / 32 ? warp_tmp[lane] : 0, winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += v;
+        }
+        if (lane < BLOCK / 32) warp_tmp[lane] = winc - w;
+        if (lane == BLOCK / 32 - 1) warp_tmp[BLOCK / 32] = winc;
+    }
+    __syncthreads();
+    uint32_t run = warp_tmp[wid] + inc - sum;
+    for (int i = beg; i < end; i++) {
+        uint32_t v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// P0: ASCII -> 2-bit packed stream + bad mask (GPU-side packing for simka_gpu_push_ascii).
+// Stream position p = read_off[r] + r + o: one separator (bad) position after every read.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_pack_ascii(const char *__restrict__ seqs, const uint64_t *__restrict__ read_off,
+                                                      uint64_t n_reads, uint64_t n_words, uint64_t *__restrict__ packed,
+                                                      uint32_t *__restrict__ bad) {
+    uint64_t t = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (t > n_words) return;
+    if (t == n_words) { packed[t] = 0; bad[t] = 0xFFFFFFFFu; return; }
+    const uint64_t p0 = t * 32;
+    // largest r with read_off[r] + r <= p0
+    uint64_t lo = 0, hi = n_reads;  // invariant: start(lo) <= p0, start(hi) > p0 (start(n_reads) = total)
+    if (n_reads == 0 || read_off[n_reads] + n_reads <= p0) {
+        packed[t] = 0; bad[t] = 0xFFFFFFFFu; return;
+    }
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (read_off[mid] + mid <= p0) lo = mid; else hi = mid;
+    }
+    uint64_t r = lo;
+    uint64_t rbeg = read_off[r], rend = read_off[r + 1];
+    uint64_t o = p0 - (rbeg + r);  // offset inside read r (== len means separator)
+    uint64_t w = 0;
+    uint32_t b = 0;
+#pragma unroll 4
+    for (int j = 0; j < 32; j++) {
+        uint32_t code = 0, isbad = 1;
+        if (r < n_reads) {
+            if (rbeg + o < rend) {
+                unsigned char c = (unsigned char)seqs[rbeg + o];
+                code = (c >> 1) & 3u;
+                unsigned char u = c & 0xDF;  // upper-case
+                isbad = !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
+                o++;
+            } else {  // separator
+                r++;
+                if (r < n_reads) { rbeg = rend; rend = read_off[r + 1]; }
+                o = 0;
+            }
+        }
+        w = (w << 2) | code;
+        b = (b << 1) | isbad;
+    }
+    packed[t] = w;
+    bad[t] = b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: canonical k-mer extraction + level-1 bucket partition.
+// Replaces Kmer<span>::ModelCanonical::iterate (GC/kmer/impl/Model.hpp:726-765,858-884) and the
+// minimizer/partition step of FillPartitions (GC/kmer/impl/SortingCountAlgorithm.cpp:1048-1140).
+// Thread t owns packed word t = start positions 32t..32t+31; the 62-bit window slides through the
+// (word t, word t+1) register pair, the reverse strand is rolled alongside.
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(BLOCK, 2)
+k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t n_words, KParams kp, int b1_bits,
+          uint32_t *__restrict__ g_hist, const uint64_t *__restrict__ bucket_base, uint32_t *__restrict__ bucket_cursor,
+          uint64_t *__restrict__ keys_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);           // [MAX_B] counts, then tile-local starts
+    uint32_t *gbase = hist + MAX_B;                                    // [MAX_B] reserved global offsets
+    uint32_t *cnt = gbase + MAX_B;                                     // [MAX_B] counts copy
+    uint32_t *warp_tmp = cnt + MAX_B;                                  // [16]
+    uint64_t *sorted = reinterpret_cast<uint64_t *>(warp_tmp + 16);    // [L1_TILE] (scatter mode only)
+
+    const int tid = threadIdx.x;
+    const int nb = 1 << b1_bits;
+    const int W = kp.mix.bits;
+    const int k = kp.k;
+    for (int i = tid; i < nb; i += BLOCK) hist[i] = 0;
+    __syncthreads();
+
+    const uint64_t t = (uint64_t)blockIdx.x * BLOCK + tid;
+    uint64_t hi = 0, lo = 0, bm = ~0ull;
+    if (t < n_words) {
+        hi = seq[t];
+        lo = seq[t + 1];
+        bm = ((uint64_t)bad[t] << 32) | bad[t + 1];
+    }
+    uint64_t keys[L1_KPT];
+    uint32_t ranks[L1_KPT / 2];
+    uint32_t vmask = 0;
+    uint64_t rev = 0;
+    const int bshift = W - b1_bits;
+#pragma unroll
+    for (int j = 0; j < L1_KPT; j++) {
+        const uint64_t fwd = hi >> (64 - 2 * k);
+        const bool ok = ((bm << j) >> (64 - k)) == 0;
+        if (j == 0) rev = simka::revcomp(fwd, k);
+        else rev = (rev >> 2) | ((uint64_t)((fwd & 3) ^ 2) << (2 * k - 2));
+        const uint64_t canon = fwd < rev ? fwd : rev;
+        const uint64_t h = simka::mix_fwd(canon, kp.mix);
+        const bool keep = ok && shard_keep(h, kp);
+        keys[j] = h;
+        if (keep) {
+            vmask |= 1u << j;
+            uint32_t r = atomicAdd(&hist[(uint32_t)(h >> bshift)], 1u);
+            if (!COUNT_ONLY) {
+                if (j & 1) ranks[j >> 1] |= r << 16; else ranks[j >> 1] = r;
+            }
+        } else if (!COUNT_ONLY && !(j & 1)) {
+            ranks[j >> 1] = 0;
+        }
+        hi = (hi << 2) | (lo >> 62);
+        lo <<= 2;
+    }
+    __syncthreads();
+    if (COUNT_ONLY) {
+        for (int i = tid; i < nb; i += BLOCK) {
+            uint32_t c = hist[i];
+            if (c) atomicAdd(&g_hist[i], c);
+        }
+        return;
+    }
+    for (int i = tid; i < nb; i += BLOCK) {
+        uint32_t c = hist[i];
+        cnt[i] = c;
+        gbase[i] = c ? atomicAdd(&bucket_cursor[i], c) : 0;
+    }
+    __syncthreads();
+    block_exclusive_scan(hist, nb, warp_tmp);
+    const uint32_t total = warp_tmp[BLOCK / 32];
+#pragma unroll
+    for (int j = 0; j < L1_KPT; j++) {
+        if (vmask & (1u << j)) {
+            uint32_t r = (j & 1) ? (ranks[j >> 1] >> 16) : (ranks[j >> 1] & 0xFFFFu);
+            sorted[hist[(uint32_t)(keys[j] >> bshift)] + r] = keys[j];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < total; i += BLOCK) {
+        uint64_t h = sorted[i];
+        uint32_t b = (uint32_t)(h >> bshift);
+        keys_out[bucket_base[b] + gbase[b] + (i - hist[b])] = h;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------------------------
+
+// out[0..n] = exclusive scan of in[0..n-1] (u32 -> u64); single block, chunked.
+__global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n) {
+    __shared__ uint64_t warp_sum[33];
+    __shared__ uint64_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024) {
+        uint64_t i = base + tid;
+        uint64_t v = i < n ? in[i] : 0, inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        if (lane == 31) warp_sum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t w = warp_sum[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t u = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += u;
+            }
+            warp_sum[lane] = winc - w;
+            if (lane == 31) warp_sum[32] = winc;
+        }
+        __syncthreads();
+        if (i < n) out[i] = carry + warp_sum[wid] + inc - v;
+        __syncthreads();
+        if (tid == 0) carry += warp_sum[32];
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+// tiles[b] = ceil(count[b] / tile)
+__global__ void k_tiles_per_bucket(const uint32_t *__restrict__ count, uint32_t *__restrict__ tiles, int n, int tile) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tiles[i] = (count[i] + tile - 1) / tile;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: level-2 partition of an L1 bucket into fine bins (count pass / scatter pass).
+// Same role as the per-partition "read" phase of PartitionsByVectorCommand
+// (GC/kmer/impl/PartitionsCommand.cpp:1253-1378), which splits a partition into radix bins.
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT_ONLY>
+__global__ void __launch_bounds__(BLOCK)
+k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ bucket_base /*[B1+1]*/,
+             const uint64_t *__restrict__ tile_start /*[B1+1]*/, int b1_bits, int b2_bits, int W,
+             uint32_t *__restrict__ fine_hist, const uint64_t *__restrict__ fine_off, uint32_t *__restrict__ fine_cursor,
+             uint64_t *__restrict__ keys_out) {
+    __shared__ uint32_t hist[MAX_B], gbase[MAX_B], warp_tmp[16];
+    __shared__ __align__(16) uint64_t sorted[COUNT_ONLY ? 1 : L2_TILE];
+    __shared__ int s_bucket;
+    const int tid = threadIdx.x;
+    const int nb1 = 1 << b1_bits, nb2 = 1 << b2_bits;
+    if (tid == 0) {  // which L1 bucket does this tile belong to?
+        uint64_t tile = blockIdx.x;
+        int lo = 0, hi = nb1;  // tile_start[lo] <= tile < tile_start[hi]
+        if (tile >= tile_start[nb1]) s_bucket = -1;
+        else {
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (tile_start[mid] <= tile) lo = mid; else hi = mid; }
+            s_bucket = lo;
+        }
+    }
+    for (int i = tid; i < nb2; i += BLOCK) hist[i] = 0;
+    __syncthreads();
+    const int b1 = s_bucket;
+    if (b1 < 0) return;
+    const uint64_t bbeg = bucket_base[b1], bend = bucket_base[b1 + 1];
+    const uint64_t tbeg = bbeg + (blockIdx.x - tile_start[b1]) * (uint64_t)L2_TILE;
+    const int shift = W - b1_bits - b2_bits;
+    const uint32_t m2 = (uint32_t)nb2 - 1;
+
+    uint64_t keys[L2_KPT];
+    uint32_t ranks[L2_KPT / 2];
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int j = 0; j < L2_KPT; j++) {
+        uint64_t i = tbeg + (uint64_t)j * BLOCK + tid;
+        if (i < bend) {
+            uint64_t h = keys_in[i];
+            keys[j] = h;
+            vmask |= 1u << j;
+            uint32_t r = atomicAdd(&hist[(uint32_t)(h >> shift) & m2], 1u);
+            if (!COUNT_ONLY) { if (j & 1) ranks[j >> 1] |= r << 16; else ranks[j >> 1] = r; }
+        } else if (!COUNT_ONLY && !(j & 1)) ranks[j >> 1] = 0;
+    }
+    __syncthreads();
+    const uint32_t fbase = (uint32_t)b1 << b2_bits;
+    if (COUNT_ONLY) {
+        for (int i = tid; i < nb2; i += BLOCK) { uint32_t c = hist[i]; if (c) atomicAdd(&fine_hist[fbase + i], c); }
+        return;
+    }
+    for (int i = tid; i < nb2; i += BLOCK) { uint32_t c = hist[i]; gbase[i] = c ? atomicAdd(&fine_cursor[fbase + i], c) : 0; }
+    __syncthreads();
+    block_exclusive_scan(hist, nb2, warp_tmp);
+    const uint32_t total = warp_tmp[BLOCK / 32];
+#pragma unroll
+    for (int j = 0; j < L2_KPT; j++)
+        if (vmask & (1u << j)) {
+            uint32_t r = (j & 1) ? (ranks[j >> 1] >> 16) : (ranks[j >> 1] & 0xFFFFu);
+            sorted[hist[(uint32_t)(keys[j] >> shift) & m2] + r] = keys[j];
+        }
+    __syncthreads();
+    for (uint32_t i = tid; i < total; i += BLOCK) {
+        uint64_t h = sorted[i];
+        uint32_t b = (uint32_t)(h >> shift) & m2;
+        keys_out[fine_off[fbase + b] + gbase[b] + (i - hist[b])] = h;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: per-bin exact multiset count + abundance filter + per-sample totals.
+// Replaces the sort / run-length "dump" of PartitionsByVectorCommand
+// (GC/kmer/impl/PartitionsCommand.cpp:1390-1504,1600-1760) and SimkaCompressedProcessor::process
+// (src/minikc/MiniKC.hpp:54-79).  Equal keys meet in a shared-memory open-addressing table; order
+// inside a bin is irrelevant downstream (the merge regroups by key), so no sort is needed.
+// ---------------------------------------------------------------------------------------------
+struct CountOut {
+    uint64_t *stage_h;      // survivors are written at fine_off[bin] + i
+    uint32_t *stage_c;
+    uint32_t *surv;         // [nbins] survivor count per bin
+    ull *totals;            // [3] distinct, sum c, sum c^2
+    ull *chist;             // [CHIST] abundance histogram of this sample (complex only) or null
+    uint32_t *big_counts;   // overflow list for counts >= CHIST
+    uint32_t *big_sample;
+    uint32_t *big_n;
+    uint32_t big_cap;
+    int *error_flag;
+};
+
+__global__ void __launch_bounds__(BLOCK)
+k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine_off, int64_t amin, int64_t amax,
+            int sample, CountOut out) {
+    __shared__ uint64_t tk[CNT_SLOTS];
+    __shared__ uint32_t tc[CNT_SLOTS];
+    __shared__ uint32_t chist[CHIST];
+    __shared__ uint32_t s_cursor;
+    __shared__ ull s_tot[3];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t bin = blockIdx.x;
+    const uint64_t beg = fine_off[bin], end = fine_off[bin + 1];
+    const uint64_t n = end - beg;
+    if (tid == 0) { s_cursor = 0; s_tot[0] = s_tot[1] = s_tot[2] = 0; }
+    if (n == 0) { if (tid == 0) out.surv[bin] = 0; return; }
+    const bool want_hist = out.chist != nullptr;
+    if (want_hist) for (int i = tid; i < CHIST; i += BLOCK) chist[i] = 0;
+    uint32_t R = 1;
+    if (n > 3 * CNT_SUBPASS_KEYS / 2) { while ((uint64_t)R * CNT_SUBPASS_KEYS < n) R <<= 1; }
+    ull t_d = 0, t_s = 0, t_q = 0;
+    for (uint32_t r = 0; r < R; r++) {
+        for (int i = tid; i < CNT_SLOTS; i += BLOCK) { tk[i] = EMPTY; tc[i] = 0; }
+        __syncthreads();
+        for (uint64_t i = tid; i < n; i += BLOCK) {
+            const uint64_t h = keys[beg + i];
+            const uint64_t hh = simka::hash2(h);
+            if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
+            uint32_t slot = (uint32_t)(hh >> 40) & (CNT_SLOTS - 1);
+            int probes = 0;
+            for (;;) {
+                ull prev = atomicCAS(reinterpret_cast<ull *>(&tk[slot]), (ull)EMPTY, (ull)h);
+                if (prev == EMPTY || prev == h) { atomicAdd(&tc[slot], 1u); break; }
+                slot = (slot + 1) & (CNT_SLOTS - 1);
+                if (++probes >= CNT_SLOTS) { *out.error_flag = 1; break; }
+            }
+        }
+        __syncthreads();
+        for (int base = 0; base < CNT_SLOTS; base += BLOCK) {
+            const int slot = base + tid;
+            const uint64_t h = tk[slot];
+            const uint32_t c = tc[slot];
+            const bool keep = (h != EMPTY) && !((int64_t)c < amin || (int64_t)c > amax);
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            uint32_t wbase = 0;
+            if (lane == 0 && m) wbase = atomicAdd(&s_cursor, (uint32_t)__popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (keep) {
+                const uint64_t pos = beg + wbase + __popc(m & ((1u << lane) - 1));
+                out.stage_h[pos] = h;
+                out.stage_c[pos] = c;
+                t_d += 1;
+                t_s += c;
+                t_q += (ull)((double)c * (double)c);  // pow(count,2) -> u64, src/minikc/MiniKC.hpp:62
+                if (want_hist) {
+                    if (c < CHIST) atomicAdd(&chist[c], 1u);
+                    else {
+                        uint32_t q = atomicAdd(out.big_n, 1u);
+                        if (q < out.big_cap) { out.big_counts[q] = c; out.big_sample[q] = (uint32_t)sample; }
+                        else *out.error_flag = 2;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        t_d += __shfl_down_sync(0xffffffffu, t_d, d);
+        t_s += __shfl_down_sync(0xffffffffu, t_s, d);
+        t_q += __shfl_down_sync(0xffffffffu, t_q, d);
+    }
+    if (lane == 0 && t_d) { atomicAdd(&s_tot[0], t_d); atomicAdd(&s_tot[1], t_s); atomicAdd(&s_tot[2], t_q); }
+    __syncthreads();
+    if (tid == 0) {
+        out.surv[bin] = s_cursor;
+        if (s_tot[0]) { atomicAdd(&out.totals[0], s_tot[0]); atomicAdd(&out.totals[1], s_tot[1]); atomicAdd(&out.totals[2], s_tot[2]); }
+    }
+    if (want_hist)
+        for (int i = tid; i < CHIST; i += BLOCK) { uint32_t c = chist[i]; if (c) atomicAdd(&out.chist[i], (ull)c); }
+}
+
+// survivors staging -> exactly-sized per-sample list; one CTA per bin
+__global__ void __launch_bounds__(BLOCK)
+k_compact(const uint64_t *__restrict__ stage_h, const uint32_t *__restrict__ stage_c, const uint64_t *__restrict__ fine_off,
+          const uint64_t *__restrict__ out_off, uint64_t *__restrict__ eh, uint32_t *__restrict__ ec) {
+    const uint32_t bin = blockIdx.x;
+    const uint64_t src = fine_off[bin], dst = out_off[bin];
+    const uint32_t n = (uint32_t)(out_off[bin + 1] - dst);
+    for (uint32_t i = threadIdx.x; i < n; i += BLOCK) { eh[dst + i] = stage_h[src + i]; ec[dst + i] = stage_c[src + i]; }
+}
+
+// off_table[fr] = out_off[fr * (nbins / FG)], fr in [0, FG]
+__global__ void k_fill_offsets(const uint64_t *__restrict__ out_off, uint32_t *__restrict__ table, uint32_t fg, uint32_t bins_per_fr) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= fg) table[i] = (uint32_t)out_off[(uint64_t)i * bins_per_fr];
+}
+
+// h -> k-mer (parity hook)
+__global__ void k_unmix(const uint64_t *__restrict__ eh, uint64_t *__restrict__ out, uint64_t n, Mix mix) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = simka::mix_inv(eh[i], mix);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: multi-sample merge + N x N accumulator update.
+// Replaces the k-way merge of SimkaMergeAlgorithm::execute (src/SimkaMerge.cpp:1164-1264), the insert
+// gate (:1307-1326) and SimkaCountProcessorSimple::updateDistance{Default,Simple,Complex}
+// (src/core/SimkaAlgorithm.hpp:341-516).  One CTA per merge bin: the N per-sample segments of the bin
+// are grouped by k-mer in a shared-memory table (group = the non-zero entries of the reference's
+// abundancePerBank vector), then sample pairs of every group are enumerated flat over the threads.
+//
+// One-sided terms of the complex distances (pairs where exactly one of c_i,c_j is 0) are NOT
+// enumerated (that is O(N) per k-mer): Canberra and Jensen-Shannon get them in closed form from
+// nb_shared / the per-sample totals at read-out, Whittaker from the per-sample abundance histogram
+// (k_whittaker_onesided) minus the both-present corrections accumulated here.
+// ---------------------------------------------------------------------------------------------
+struct MergeArgs {
+    int n;                       // samples
+    int fg_bits, mg_bits;        // fine-range and merge-bin granularity (log2)
+    const uint64_t *const *eh;   // [n] per-sample hashed k-mers
+    const uint32_t *const *ec;   // [n] per-sample counts
+    const uint32_t *off;         // [n][FG+1]
+    const double *ntot;          // [n] global solid k-mer totals N_i as double
+    int simple, complex_;
+    ull *nb_shared, *distinct_shared, *braycurtis, *chord, *hellinger, *whittaker;
+    double *kl;
+    ull *scalars;                // [0] distinct k-mers, [1] shared k-mers, [2] pairs
+    int *error_flag;
+};
+
+__device__ __forceinline__ long long absint32_ext(uint64_t x) {  // abs((int)x) as the reference's int -> u64 add
+    int d = (int)(uint32_t)x;
+    d = (int)(d < 0 ? 0u - (unsigned)d : (unsigned)d);
+    return (long long)d;
+}
+
+__device__ __forceinline__ void accumulate_pair(const MergeArgs &a, int i, int j, uint32_t ci, uint32_t cj) {
+    // i < j
+    const size_t n = (size_t)a.n;
+    const size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
+    const size_t sym = (size_t)j + (n - 1) * i - ((size_t)i * (i - 1) / 2);
+    const uint32_t mn = ci < cj ? ci : cj;
+    atomicAdd(&a.nb_shared[ij], (ull)ci);
+    atomicAdd(&a.nb_shared[ji], (ull)cj);
+    atomicAdd(&a.distinct_shared[sym], 1ull);
+    atomicAdd(&a.braycurtis[sym], (ull)mn);
+    if (a.simple) {
+        const ull prod = (ull)ci * (ull)cj;
+        atomicAdd(&a.chord[ij], prod);
+        atomicAdd(&a.hellinger[ij], (ull)sqrt((double)prod));  // u64 += double truncates per increment
+    }
+    if (a.complex_) {
+        const double ai = (double)ci, aj = (double)cj, Ni = a.ntot[i], Nj = a.ntot[j];
+        const double yX = aj * Ni, xY = ai * Nj;
+        const double d1 = (ai / Ni) * log((2 * xY) / (xY + yX));
+        const double d2 = (aj / Nj) * log((2 * yX) / (xY + yX));
+        atomicAdd(&a.kl[ij], d1 + d2);
+        const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
+        const long long two = absint32_ext(wx - wy);
+        const long long sub = absint32_ext(wx) + absint32_ext(wy);  // their one-sided values, removed here
+        atomicAdd(&a.whittaker[ij], (ull)(two - sub));
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK)
+k_merge(MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *tk = reinterpret_cast<uint64_t *>(smem_raw);      // [MRG_SLOTS] table keys
+    uint32_t *gs = reinterpret_cast<uint32_t *>(tk + MRG_SLOTS); // [MRG_SLOTS] group size, then group start
+    uint32_t *pp = gs + MRG_SLOTS;                               // [MRG_SLOTS+1] fill cursors, then pair prefix
+    uint32_t *ge_c = pp + MRG_SLOTS + 1;                         // [MRG_CAP] grouped counts
+    uint32_t *s_start = ge_c + MRG_CAP;                          // [N]
+    uint32_t *s_pre = s_start + a.n;                             // [N+1]
+    uint16_t *gsz = reinterpret_cast<uint16_t *>(s_pre + a.n + 1); // [MRG_SLOTS] group size copy
+    uint16_t *ge_s = gsz + MRG_SLOTS;                            // [MRG_CAP] grouped sample ids
+    __shared__ uint32_t warp_tmp[16];
+    __shared__ uint32_t s_groups, s_shared;
+
+    const int tid = threadIdx.x;
+    const int N = a.n;
+    const uint32_t MG = 1u << a.mg_bits;
+    const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
+    const size_t ostride = ((size_t)1 << a.fg_bits) + 1;
+    ull loc_groups = 0, loc_shared = 0;
+
+    for (uint32_t mb = blockIdx.x; mb < MG; mb += gridDim.x) {
+        __syncthreads();
+        for (int s = tid; s < N; s += BLOCK) {
+            const uint32_t b0 = a.off[(size_t)s * ostride + (size_t)mb * q];
+            const uint32_t b1 = a.off[(size_t)s * ostride + (size_t)(mb + 1) * q];
+            s_start[s] = b0;
+            s_pre[s] = b1 - b0;
+        }
+        __syncthreads();
+        block_exclusive_scan(s_pre, N, warp_tmp);
+        const uint32_t n_e = warp_tmp[BLOCK / 32];
+        if (tid == 0) s_pre[N] = n_e;
+        __syncthreads();
+        if (n_e == 0) continue;
+        uint32_t R = 1;
+        if (n_e > MRG_CAP) { while ((uint64_t)R * (MRG_CAP / 2) < n_e) R <<= 1; }
+        for (uint32_t r = 0; r < R; r++) {
+            for (int i = tid; i < MRG_SLOTS; i += BLOCK) { tk[i] = EMPTY; gs[i] = 0; pp[i] = 0; }
+            if (tid == 0) { s_groups = 0; s_shared = 0; }
+            __syncthreads();
+            // phase 1: insert keys, count group sizes
+            for (uint32_t i = tid; i < n_e; i += BLOCK) {
+                int lo = 0, hi = N;  // s_pre[lo] <= i < s_pre[hi]
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const uint64_t h = a.eh[lo][s_start[lo] + (i - s_pre[lo])];
+                const uint64_t hh = simka::hash2(h);
+                if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
+                int probes = 0;
+                for (;;) {
+                    ull prev = atomicCAS(reinterpret_cast<ull *>(&tk[slot]), (ull)EMPTY, (ull)h);
+                    if (prev == EMPTY || prev == h) { atomicAdd(&gs[slot], 1u); break; }
+                    slot = (slot + 1) & (MRG_SLOTS - 1);
+                    if (++probes >= MRG_SLOTS) { *a.error_flag = 3; break; }
+                }
+            }
+            __syncthreads();
+            // phase 2: group statistics; only groups with >= 2 samples are materialised
+            uint32_t my_groups = 0, my_shared = 0;
+            for (int i = tid; i < MRG_SLOTS; i += BLOCK) {
+                const uint32_t g = gs[i];
+                gsz[i] = (uint16_t)g;
+                my_groups += g > 0;
+                my_shared += g > 1;
+                if (g < 2) gs[i] = 0;
+            }
+            if (my_groups) atomicAdd(&s_groups, my_groups);
+            if (my_shared) atomicAdd(&s_shared, my_shared);
+            __syncthreads();
+            block_exclusive_scan(gs, MRG_SLOTS, warp_tmp);
+            const uint32_t n_sub = warp_tmp[BLOCK / 32];
+            const uint32_t n_shared_groups = s_shared;
+            if (tid == 0) { loc_groups += s_groups; loc_shared += s_shared; }
+            __syncthreads();
+            if (n_sub > MRG_CAP) { if (tid == 0) *a.error_flag = 4; continue; }
+            if (n_shared_groups == 0) continue;  // nothing shared in this bin: no accumulator changes
+            // phase 3: scatter the entries of shared k-mers into their groups
+            for (uint32_t i = tid; i < n_e; i += BLOCK) {
+                int lo = 0, hi = N;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const size_t idx = s_start[lo] + (i - s_pre[lo]);
+                const uint64_t h = a.eh[lo][idx];
+                const uint64_t hh = simka::hash2(h);
+                if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
+                while (tk[slot] != h) slot = (slot + 1) & (MRG_SLOTS - 1);
+                if (gsz[slot] < 2) continue;  // private k-mer: contributes to no pair
+                const uint32_t pos = gs[slot] + atomicAdd(&pp[slot], 1u);
+                ge_s[pos] = (uint16_t)lo;
+                ge_c[pos] = a.ec[lo][idx];
+            }
+            __syncthreads();
+            for (int i = tid; i < MRG_SLOTS; i += BLOCK) { const uint32_t g = gsz[i]; pp[i] = g * (g - 1) / 2; }  // g=0 -> 0
+            __syncthreads();
+            block_exclusive_scan(pp, MRG_SLOTS, warp_tmp);
+            const uint32_t P = warp_tmp[BLOCK / 32];
+            if (tid == 0) pp[MRG_SLOTS] = P;
+            __syncthreads();
+            // phase 4: flat pair enumeration
+            for (uint32_t p = tid; p < P; p += BLOCK) {
+                int lo = 0, hi = MRG_SLOTS;  // pp[lo] <= p < pp[hi]
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pp[mid] <= p) lo = mid; else hi = mid; }
+                const uint32_t g = gsz[lo], l = p - pp[lo], base = gs[lo];
+                // row-major strict upper triangle of a g x g matrix: row x starts at x(2g-x-1)/2
+                const double tg = 2.0 * g - 1.0;
+                int x = (int)((tg - sqrt(tg * tg - 8.0 * (double)l)) * 0.5);
+                if (x < 0) x = 0;
+                while ((uint32_t)(x + 1) * (2 * g - (x + 1) - 1) / 2 <= l) x++;
+                while ((uint32_t)x * (2 * g - x - 1) / 2 > l) x--;
+                const uint32_t y = x + 1 + (l - (uint32_t)x * (2 * g - x - 1) / 2);
+                int si = ge_s[base + x], sj = ge_s[base + y];
+                uint32_t ci = ge_c[base + x], cj = ge_c[base + y];
+                if (si > sj) { int ts = si; si = sj; sj = ts; uint32_t tc = ci; ci = cj; cj = tc; }
+                accumulate_pair(a, si, sj, ci, cj);
+            }
+            if (tid == 0) atomicAdd(&a.scalars[2], (ull)P);
+        }
+    }
+    if (tid == 0 && (loc_groups | loc_shared)) {
+        atomicAdd(&a.scalars[0], loc_groups);
+        atomicAdd(&a.scalars[1], loc_shared);
+    }
+}
+
+// T[i][j] = sum over solid k-mers e of sample i of f((u64)(c_e * N_j)), f = abs((int)x): the value the
+// reference's Whittaker update adds for a k-mer present in i and absent from j
+// (src/core/SimkaAlgorithm.hpp:481,512).  Computed from the abundance histogram of sample i.
+__global__ void __launch_bounds__(BLOCK)
+k_whittaker_onesided(const ull *__restrict__ chist /*[n][CHIST]*/, const uint32_t *__restrict__ big_counts,
+                     const uint32_t *__restrict__ big_sample, uint32_t big_n, const double *__restrict__ ntot, int n,
+                     ull *__restrict__ T /*[n][n]*/) {
+    const int i = blockIdx.x;
+    for (int j = threadIdx.x; j < n; j += BLOCK) {
+        if (j == i) continue;
+        const double Nj = ntot[j];
+        ull acc = 0;
+        for (int c = 1; c < CHIST; c++) {
+            const ull m = chist[(size_t)i * CHIST + c];
+            if (m) acc += m * (ull)absint32_ext((uint64_t)((double)c * Nj));
+        }
+        for (uint32_t q = 0; q < big_n; q++)
+            if (big_sample[q] == (uint32_t)i) acc += (ull)absint32_ext((uint64_t)((double)big_counts[q] * Nj));
+        T[(size_t)i * n + j] = acc;
+    }
+}
+
+// whittaker[i][j] (i<j) += T[i][j] + T[j][i]
+__global__ void k_whittaker_fold(ull *__restrict__ whit, const ull *__restrict__ T, int n) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    int i = idx / n, j = idx % n;
+    if (i < j) whit[idx] += T[idx] + T[(size_t)j * n + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// SimkaMin: all-pairs bottom-s sketch comparison.
+// Replaces ComputeDistanceManager::computeDistance_unsynch (src/simkaMin/SimkaMinDistance.hpp:190-279).
+// One CTA per pair; the merged prefix that holds the s smallest distinct hashes of the union is
+// located with a merge-path binary search, then counted in parallel (hash intersections by
+// per-thread chunked two-pointer walks).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t *a, uint32_t n, uint64_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+k_simkamin_pair(const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ start,
+                uint32_t n, uint32_t s, ull *__restrict__ quad /*[pairs][4]: shared, distinct, sharedK, kmers*/) {
+    // pair index -> (i, j), i < j
+    const uint64_t p = blockIdx.x;
+    const double tn = 2.0 * n - 1.0;
+    int i = (int)((tn - sqrt(tn * tn - 8.0 * (double)p)) * 0.5);
+    if (i < 0) i = 0;
+    while ((uint64_t)(i + 1) * (2ull * n - (i + 1) - 1) / 2 <= p) i++;
+    while ((uint64_t)i * (2ull * n - i - 1) / 2 > p) i--;
+    const int j = i + 1 + (int)(p - (uint64_t)i * (2ull * n - i - 1) / 2);
+
+    const uint64_t *A = hashes + (size_t)i * s + start[i];
+    const uint64_t *B = hashes + (size_t)j * s + start[j];
+    const uint32_t *CA = counts + (size_t)i * s + start[i];
+    const uint32_t *CB = counts + (size_t)j * s + start[j];
+    const uint32_t na = s - start[i], nb = s - start[j];
+    const uint32_t S = min(na, nb);  // sketchSize = min of the two stripped sizes (:204)
+
+    __shared__ ull s_shared, s_sharedk, s_kmers;
+    __shared__ uint32_t s_ea, s_eb, s_distinct;
+    __shared__ uint32_t sh_cnt[BLOCK + 1];
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_shared = s_sharedk = s_kmers = 0; }
+
+    // The reference walk consumes the merged sequence in ascending order and stops once S distinct
+    // values were seen (a side can only run out at that same step, because the union rank of a
+    // side's last value is >= its length >= S).  So the consumed prefixes (ea, eb) hold exactly the
+    // S smallest distinct values of A u B.
+    // Phase A: per-thread chunks of A[0..min(na,S)) count their matches in B; the chunk prefix makes
+    // the union rank searchable at chunk granularity.
+    const uint32_t naE = min(na, S);
+    const uint32_t per = (naE + BLOCK - 1) / BLOCK;
+    const uint32_t a0 = min(naE, tid * per), a1 = min(naE, a0 + per);
+    uint32_t my_sh = 0;
+    if (a0 < a1) {
+        uint32_t b = lower_bound_u64(B, nb, A[a0]);
+        for (uint32_t x = a0; x < a1 && b < nb; x++) {
+            const uint64_t v = A[x];
+            while (b < nb && B[b] < v) b++;
+            if (b < nb && B[b] == v) my_sh++;
+        }
+    }
+    sh_cnt[tid] = my_sh;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int t = 0; t < BLOCK; t++) { uint32_t v = sh_cnt[t]; sh_cnt[t] = run; run += v; }
+        sh_cnt[BLOCK] = run;
+        // state after chunk t: x = end of chunk, y = #B smaller than the next A element
+        uint32_t x = 0, y = 0, d = 0;
+        for (int t = 0; t < BLOCK; t++) {
+            const uint32_t ca0 = min(naE, (uint32_t)t * per), ca1 = min(naE, ca0 + per);
+            if (ca0 >= ca1) break;
+            const uint32_t yb = (ca1 < na) ? lower_bound_u64(B, nb, A[ca1]) : nb;
+            const uint32_t dn = ca1 + yb - sh_cnt[t + 1];
+            if (dn >= S) break;  // the stop lies inside this chunk
+            x = ca1; y = yb; d = dn;
+        }
+        while (d < S && x < na && y < nb) {  // sequential refinement, at most one chunk long
+            const uint64_t va = A[x], vb = B[y];
+            x += va <= vb;
+            y += vb <= va;
+            d++;
+        }
+        // (unreachable for well-formed sketches: one side ran out before S distinct values)
+        s_ea = x; s_eb = y; s_distinct = d;
+    }
+    __syncthreads();
+    const uint32_t ea = s_ea, eb = s_eb;
+    // Phase B: sums over the consumed prefixes.
+    ull kmers = 0, shared = 0, sharedk = 0;
+    for (uint32_t x = tid; x < ea; x += BLOCK) kmers += CA[x];
+    for (uint32_t y = tid; y < eb; y += BLOCK) kmers += CB[y];
+    {
+        const uint32_t per2 = (ea + BLOCK - 1) / BLOCK;
+        const uint32_t c0 = min(ea, tid * per2), c1 = min(ea, c0 + per2);
+        if (c0 < c1) {
+            uint32_t b = lower_bound_u64(B, eb, A[c0]);
+            for (uint32_t x = c0; x < c1 && b < eb; x++) {
+                const uint64_t v = A[x];
+                while (b < eb && B[b] < v) b++;
+                if (b < eb && B[b] == v) { shared++; sharedk += min(CA[x], CB[b]); }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        kmers += __shfl_down_sync(0xffffffffu, kmers, d);
+        shared += __shfl_down_sync(0xffffffffu, shared, d);
+        sharedk += __shfl_down_sync(0xffffffffu, sharedk, d);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_kmers, kmers); atomicAdd(&s_shared, shared); atomicAdd(&s_sharedk, sharedk); }
+    __syncthreads();
+    if (tid == 0) {
+        quad[4 * p + 0] = s_shared;
+        quad[4 * p + 1] = s_distinct;
+        quad[4 * p + 2] = s_sharedk;
+        quad[4 * p + 3] = s_kmers;
+    }
+}
+
+__global__ void k_sketch_starts(const uint64_t *__restrict__ hashes, uint32_t n, uint32_t s, uint32_t *__restrict__ start) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t *h = hashes + (size_t)i * s;
+    uint32_t lo = 0, hi = s;  // first non-zero (zeros are a prefix: sketches are ascending)
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (h[mid] == 0) lo = mid + 1; else hi = mid; }
+    start[i] = lo;
+}
+
+}  // namespace
+
+// =============================================================================================
+// context
+// =============================================================================================
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// bump allocator for the per-sample solid k-mer lists (kept across simka_gpu_reset)
+struct Arena {
+    struct Chunk { char *p; size_t cap, used; };
+    std::vector<Chunk> chunks;
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (auto &c : chunks)
+            if (c.cap - c.used >= bytes) { void *r = c.p + c.used; c.used += bytes; return r; }
+        size_t cap = std::max<size_t>(bytes, (size_t)256 << 20);
+        void *p = nullptr;
+        if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+        chunks.push_back({(char *)p, cap, bytes});
+        return p;
+    }
+    void reset() { for (auto &c : chunks) c.used = 0; }
+    void release() { for (auto &c : chunks) cudaFree(c.p); chunks.clear(); }
+};
+
+struct SampleData {
+    uint64_t *eh = nullptr;   // hashed solid k-mers, grouped by fine range (arena memory)
+    uint32_t *ec = nullptr;
+    uint64_t n = 0;
+    uint32_t *off = nullptr;  // points into ctx->off_table
+    bool done = false;
+    simka_sample_totals local = {0, 0, 0, 0};
+};
+
+// input of one sample in flight; two slots so that the H2D copy of sample s+1 overlaps the kernels of s
+struct InSlot {
+    DevBuf packed, bad;
+    const uint64_t *ext_packed = nullptr;  // caller-owned device buffers (simka_gpu_push_reads_device)
+    const uint32_t *ext_bad = nullptr;
+    uint64_t words = 0, reads = 0;
+    int sample = -1;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+    bool consumed_valid = false;
+};
+
+enum { T_EXTRACT_COUNT = 0, T_EXTRACT_SCATTER, T_PART_COUNT, T_PART_SCATTER, T_BIN_COUNT, T_COMPACT, T_NSTAGE };
+
+struct simka_ctx {
+    simka_params prm;
+    KParams kp;
+    int W = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[2 * T_NSTAGE + 4] = {};
+    std::string err;
+    InSlot slots[2];
+    DevBuf d_ascii, d_roff;
+    // work buffers
+    DevBuf d_keysA, d_keysB, d_stage_c;
+    DevBuf d_hist1, d_base1, d_cursor1, d_tiles, d_tile_start, d_fine_hist, d_fine_off, d_fine_cursor, d_surv, d_out_off;
+    DevBuf d_small;  // totals[3] + error flag + big_n
+    // per-sample results
+    std::vector<SampleData> samples;
+    Arena arena;
+    int fg_bits = -1;    // fine-range granularity, fixed by the first sample
+    DevBuf d_off_table;  // [N][FG+1]
+    std::vector<simka_sample_totals> global_totals;
+    bool totals_overridden = false;
+    // complex-distance helpers
+    DevBuf d_chist, d_big_counts, d_big_sample;
+    uint32_t big_cap = 1u << 20;
+    // accumulators
+    DevBuf d_acc;  // one slab
+    bool merged = false;
+    size_t acc_bytes = 0;
+    ull *a_nb_shared = nullptr, *a_distinct = nullptr, *a_bc = nullptr, *a_chord = nullptr, *a_hell = nullptr, *a_whit = nullptr, *a_T = nullptr, *a_scalars = nullptr;
+    double *a_kl = nullptr, *a_ntot = nullptr;
+    DevBuf d_ptrs;
+    float stage_ms[T_NSTAGE] = {};
+    float sample_ms = 0, merge_ms = 0;
+    uint64_t kmers_in = 0, entries = 0;
+    uint64_t launches = 0;
+
+    void set_error(const std::string &s) { err = s; }
+};
+
+static size_t merge_smem_bytes(int n) {
+    return (size_t)MRG_SLOTS * 8 + (size_t)MRG_SLOTS * 4 + ((size_t)MRG_SLOTS + 1) * 4 + (size_t)MRG_CAP * 4 + ((size_t)2 * n + 1) * 4 +
+           (size_t)MRG_SLOTS * 2 + (size_t)MRG_CAP * 2 + 16;
+}
+// the reference expression for a k-mer present in x only (src/core/SimkaAlgorithm.hpp:450-453), evaluated
+// at run time so that the degenerate empty-sample case (N_y = 0 -> 0/0) yields the same NaN
+static double __attribute__((noinline)) onesided_kl_term(double c, double Nx, double Ny) {
+    volatile double yX = 0.0 * Nx, xY = c * Ny;
+    double xi = c / Nx;
+    return xi * log((2 * xY) / (xY + yX));
+}
+static int ilog2_ceil(uint64_t v) { int b = 0; while (((uint64_t)1 << b) < v) b++; return b; }
+
+static int reset_state(simka_ctx *ctx) {
+    for (auto &s : ctx->samples) s = SampleData();
+    ctx->arena.reset();
+    for (auto &sl : ctx->slots) { sl.sample = -1; sl.words = sl.reads = 0; sl.ext_packed = nullptr; sl.ext_bad = nullptr; }
+    ctx->global_totals.assign(ctx->prm.nb_samples, simka_sample_totals{0, 0, 0, 0});
+    ctx->totals_overridden = false;
+    ctx->merged = false;
+    ctx->fg_bits = -1;
+    for (float &f : ctx->stage_ms) f = 0;
+    ctx->sample_ms = ctx->merge_ms = 0;
+    ctx->kmers_in = ctx->entries = 0;
+    ctx->launches = 0;
+    if (ctx->prm.complex_dist) CK(cudaMemsetAsync(ctx->d_chist.p, 0, (size_t)ctx->prm.nb_samples * CHIST * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_small.p, 0, 64, ctx->stream));
+    return SIMKA_OK;
+}
+
+extern "C" {
+
+const char *simka_b200_version(void) { return "simka_b200 0.1 (sm_100a)"; }
+
+int simka_gpu_host_alloc(void **ptr, size_t bytes) { return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? SIMKA_OK : SIMKA_ERR_NOMEM; }
+int simka_gpu_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SIMKA_OK : SIMKA_ERR_CUDA; }
+
+int simka_gpu_create(simka_ctx **out, const simka_params *p) {
+    if (!out || !p) return SIMKA_ERR_INVALID;
+    *out = nullptr;
+    if (p->kmer_size < 2 || p->kmer_size > 31 || p->nb_samples < 1 || p->nb_samples > MRG_MAXN) return SIMKA_ERR_INVALID;
+    if (p->shard_count > 1 && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)) return SIMKA_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || p->device < 0 || p->device >= ndev) return SIMKA_ERR_CUDA;
+    if (cudaSetDevice(p->device) != cudaSuccess) return SIMKA_ERR_CUDA;
+    simka_ctx *ctx = new simka_ctx();
+    ctx->prm = *p;
+    ctx->kp.mix = simka::make_mix(p->kmer_size);
+    ctx->kp.k = p->kmer_size;
+    ctx->kp.shard_rank = p->shard_rank;
+    ctx->kp.shard_count = p->shard_count > 1 ? p->shard_count : 1;
+    ctx->W = 2 * p->kmer_size;
+    ctx->samples.resize(p->nb_samples);
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &sl : ctx->slots)
+        ok = ok && cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming) == cudaSuccess;
+    for (auto &e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(p->nb_samples)) == cudaSuccess;
+    ok = ok && ctx->d_small.reserve(64) == 0;
+    if (ok && p->complex_dist)
+        ok = ctx->d_chist.reserve((size_t)p->nb_samples * CHIST * 8) == 0 && ctx->d_big_counts.reserve((size_t)ctx->big_cap * 4) == 0 &&
+             ctx->d_big_sample.reserve((size_t)ctx->big_cap * 4) == 0;
+    if (ok) ok = reset_state(ctx) == SIMKA_OK;
+    if (!ok) { simka_gpu_destroy(ctx); return SIMKA_ERR_CUDA; }
+    *out = ctx;
+    return SIMKA_OK;
+}
+
+int simka_gpu_reset(simka_ctx *ctx) {
+    if (!ctx) return SIMKA_ERR_INVALID;
+    CK(cudaSetDevice(ctx->prm.device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return reset_state(ctx);
+}
+
+void simka_gpu_destroy(simka_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->prm.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    ctx->arena.release();
+    DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
+                      &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
+                      &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char *simka_gpu_last_error(const simka_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void *simka_gpu_stream(simka_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// grows a device buffer while keeping its first `keep` bytes
+static int grow_keep(simka_ctx *ctx, DevBuf &b, size_t bytes, size_t keep) {
+    if (bytes <= b.cap) return SIMKA_OK;
+    void *np = nullptr;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaMalloc(&np, want));
+    if (keep) { CK(cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, ctx->copy_stream)); CK(cudaStreamSynchronize(ctx->copy_stream)); }
+    if (b.p) cudaFree(b.p);
+    b.p = np; b.cap = want;
+    return SIMKA_OK;
+}
+
+static int find_slot(simka_ctx *ctx, int sample_id, InSlot **out) {
+    if (!ctx) return SIMKA_ERR_INVALID;
+    if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done) { ctx->set_error("bad sample id"); return SIMKA_ERR_INVALID; }
+    if (cudaSetDevice(ctx->prm.device) != cudaSuccess) return SIMKA_ERR_CUDA;
+    for (auto &sl : ctx->slots) if (sl.sample == sample_id) { *out = &sl; return SIMKA_OK; }
+    for (auto &sl : ctx->slots)
+        if (sl.sample < 0) {
+            sl.sample = sample_id; sl.words = sl.reads = 0; sl.ext_packed = nullptr; sl.ext_bad = nullptr;
+            // the kernels of the sample that used this slot before must have consumed it
+            if (sl.consumed_valid) CK(cudaStreamWaitEvent(ctx->copy_stream, sl.consumed, 0));
+            *out = &sl;
+            return SIMKA_OK;
+        }
+    ctx->set_error("at most two samples may be in flight: finish one first");
+    return SIMKA_ERR_INVALID;
+}
+
+int simka_gpu_push_reads(simka_ctx *ctx, int sample_id, const uint64_t *packed, const uint32_t *bad, uint64_t n_words, uint64_t n_reads) {
+    InSlot *sl = nullptr;
+    int rc = find_slot(ctx, sample_id, &sl);
+    if (rc) return rc;
+    if (sl->ext_packed) { ctx->set_error("sample already bound to device buffers"); return SIMKA_ERR_INVALID; }
+    sl->reads += n_reads;
+    if (n_words == 0) return SIMKA_OK;
+    const uint64_t w0 = sl->words;
+    rc = grow_keep(ctx, sl->packed, (w0 + n_words + 1) * 8, w0 * 8); if (rc) return rc;
+    rc = grow_keep(ctx, sl->bad, (w0 + n_words + 1) * 4, w0 * 4); if (rc) return rc;
+    CK(cudaMemcpyAsync(sl->packed.as<uint64_t>() + w0, packed, (n_words + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaMemcpyAsync(sl->bad.as<uint32_t>() + w0, bad, (n_words + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(sl->copied, ctx->copy_stream));
+    sl->words = w0 + n_words;
+    return SIMKA_OK;
+}
+
+int simka_gpu_push_reads_device(simka_ctx *ctx, int sample_id, const uint64_t *d_packed, const uint32_t *d_bad, uint64_t n_words, uint64_t n_reads) {
+    InSlot *sl = nullptr;
+    int rc = find_slot(ctx, sample_id, &sl);
+    if (rc) return rc;
+    if (sl->words) { ctx->set_error("sample already has host-pushed reads"); return SIMKA_ERR_INVALID; }
+    sl->ext_packed = d_packed; sl->ext_bad = d_bad;
+    sl->words = n_words; sl->reads = n_reads;
+    CK(cudaEventRecord(sl->copied, ctx->copy_stream));
+    return SIMKA_OK;
+}
+
+int simka_gpu_push_ascii(simka_ctx *ctx, int sample_id, const char *seqs, const uint64_t *read_off, uint64_t n_reads) {
+    InSlot *sl = nullptr;
+    int rc = find_slot(ctx, sample_id, &sl);
+    if (rc) return rc;
+    if (sl->ext_packed) { ctx->set_error("sample already bound to device buffers"); return SIMKA_ERR_INVALID; }
+    if (n_reads == 0) return SIMKA_OK;
+    const uint64_t total = read_off[n_reads] - read_off[0];
+    const uint64_t n_words = (total + n_reads + 31) / 32;
+    const uint64_t w0 = sl->words;
+    rc = grow_keep(ctx, sl->packed, (w0 + n_words + 1) * 8, w0 * 8); if (rc) return rc;
+    rc = grow_keep(ctx, sl->bad, (w0 + n_words + 1) * 4, w0 * 4); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->copy_stream));  // the ASCII staging buffers are shared between pushes
+    if (ctx->d_ascii.reserve(total + 16) || ctx->d_roff.reserve((n_reads + 1) * 8)) { ctx->set_error("out of device memory"); return SIMKA_ERR_NOMEM; }
+    std::vector<uint64_t> rel;  // offsets relative to the first read
+    const uint64_t *ro = read_off;
+    if (read_off[0] != 0) { rel.resize(n_reads + 1); for (uint64_t i = 0; i <= n_reads; i++) rel[i] = read_off[i] - read_off[0]; ro = rel.data(); }
+    CK(cudaMemcpyAsync(ctx->d_ascii.p, seqs + read_off[0], total, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaMemcpyAsync(ctx->d_roff.p, ro, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (!rel.empty()) CK(cudaStreamSynchronize(ctx->copy_stream));
+    const unsigned grid = (unsigned)((n_words + 1 + BLOCK - 1) / BLOCK);
+    k_pack_ascii<<<grid, BLOCK, 0, ctx->copy_stream>>>(ctx->d_ascii.as<char>(), ctx->d_roff.as<uint64_t>(), n_reads, n_words,
+                                                       sl->packed.as<uint64_t>() + w0, sl->bad.as<uint32_t>() + w0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(sl->copied, ctx->copy_stream));
+    sl->words = w0 + n_words;
+    sl->reads += n_reads;
+    return SIMKA_OK;
+}
+
+int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *out) {
+    if (!ctx) return SIMKA_ERR_INVALID;
+    if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done) { ctx->set_error("bad sample id"); return SIMKA_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->prm.device));
+    cudaStream_t st = ctx->stream;
+    SampleData &sd = ctx->samples[sample_id];
+    InSlot *sl = nullptr;
+    for (auto &s : ctx->slots) if (s.sample == sample_id) sl = &s;
+    const uint64_t n_words = sl ? sl->words : 0;
+    const uint64_t n_reads = sl ? sl->reads : 0;
+    const uint64_t n_pos = n_words * 32;
+    const int W = ctx->W;
+
+    // bin geometry (fixed per sample): nbins = 2^(b1+b2) fine bins of ~BIN_TARGET keys, >= fine ranges
+    if (ctx->fg_bits < 0) {
+        uint64_t per_sample = ctx->prm.expected_kmers_per_sample ? ctx->prm.expected_kmers_per_sample : n_pos;
+        uint64_t want = std::max<uint64_t>(1, (per_sample / 4) * (uint64_t)ctx->prm.nb_samples / MRG_TARGET);
+        int fg = ilog2_ceil(want);
+        fg = std::min(fg, std::min(W, 22));
+        while (fg > 0 && ((size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4) > ((size_t)2 << 30)) fg--;
+        ctx->fg_bits = fg;
+        const size_t tbl = (size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4;
+        if (ctx->d_off_table.reserve(tbl)) { ctx->set_error("out of device memory (offset table)"); return SIMKA_ERR_NOMEM; }
+        CK(cudaMemsetAsync(ctx->d_off_table.p, 0, tbl, st));
+    }
+    int bin_bits = std::max(ilog2_ceil(std::max<uint64_t>(1, n_pos / BIN_TARGET)), ctx->fg_bits);
+    bin_bits = std::min(bin_bits, std::min(W, 20));
+    bin_bits = std::max(bin_bits, ctx->fg_bits);
+    const int b1_bits = std::min(bin_bits, bin_bits > 16 ? 10 : 8);
+    const int b2_bits = bin_bits - b1_bits;
+    if (b2_bits > 10) { ctx->set_error("sample too large for the bin geometry"); return SIMKA_ERR_INVALID; }
+    const uint32_t nb1 = 1u << b1_bits, nbins = 1u << bin_bits;
+    const size_t fgn = ((size_t)1 << ctx->fg_bits) + 1;
+    sd.off = ctx->d_off_table.as<uint32_t>() + (size_t)sample_id * fgn;
+
+    ull *d_totals = ctx->d_small.as<ull>();  // [0..2]
+    int *d_error = reinterpret_cast<int *>(ctx->d_small.as<char>() + 32);
+    uint32_t *d_big_n = reinterpret_cast<uint32_t *>(ctx->d_small.as<char>() + 40);
+    uint64_t h_keys = 0, h_surv = 0;
+    ull h_tot[3] = {0, 0, 0};
+
+    if (n_words > 0) {
+        bool okm = !ctx->d_keysA.reserve(n_pos * 8) && !ctx->d_keysB.reserve(n_pos * 8) && !ctx->d_stage_c.reserve(n_pos * 4) &&
+                   !ctx->d_hist1.reserve(MAX_B * 4) && !ctx->d_base1.reserve((MAX_B + 1) * 8) && !ctx->d_cursor1.reserve(MAX_B * 4) &&
+                   !ctx->d_tiles.reserve(MAX_B * 4) && !ctx->d_tile_start.reserve((MAX_B + 1) * 8) &&
+                   !ctx->d_fine_hist.reserve((size_t)nbins * 4) && !ctx->d_fine_off.reserve(((size_t)nbins + 1) * 8) &&
+                   !ctx->d_fine_cursor.reserve((size_t)nbins * 4) && !ctx->d_surv.reserve((size_t)nbins * 4) &&
+                   !ctx->d_out_off.reserve(((size_t)nbins + 1) * 8);
+        if (!okm) { ctx->set_error("out of device memory (work buffers)"); return SIMKA_ERR_NOMEM; }
+        CK(cudaStreamWaitEvent(st, sl->copied, 0));
+        cudaEvent_t *ev = ctx->ev;
+        CK(cudaEventRecord(ev[2 * T_NSTAGE], st));  // sample start
+        CK(cudaMemsetAsync(d_totals, 0, 24, st));
+        CK(cudaMemsetAsync(ctx->d_hist1.p, 0, MAX_B * 4, st));
+        CK(cudaMemsetAsync(ctx->d_cursor1.p, 0, MAX_B * 4, st));
+        CK(cudaMemsetAsync(ctx->d_fine_hist.p, 0, (size_t)nbins * 4, st));
+        CK(cudaMemsetAsync(ctx->d_fine_cursor.p, 0, (size_t)nbins * 4, st));
+
+        const unsigned g1 = (unsigned)((n_words + BLOCK - 1) / BLOCK);
+        const uint64_t *seq = sl->ext_packed ? sl->ext_packed : sl->packed.as<uint64_t>();
+        const uint32_t *bad = sl->ext_bad ? sl->ext_bad : sl->bad.as<uint32_t>();
+        // K1 count / scan / scatter
+        CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
+        k_extract<true><<<g1, BLOCK, 3 * MAX_B * 4 + 64, st>>>(seq, bad, n_words, ctx->kp, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, nullptr);
+        CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT + 1], st));
+        k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_hist1.as<uint32_t>(), ctx->d_base1.as<uint64_t>(), nb1);
+        CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER], st));
+        k_extract<false><<<g1, BLOCK, 3 * MAX_B * 4 + 64 + L1_TILE * 8, st>>>(seq, bad, n_words, ctx->kp, b1_bits, nullptr, ctx->d_base1.as<uint64_t>(),
+                                                                           ctx->d_cursor1.as<uint32_t>(), ctx->d_keysA.as<uint64_t>());
+        CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER + 1], st));
+        CK(cudaEventRecord(sl->consumed, st));  // the input slot may be overwritten from here on
+        sl->consumed_valid = true;
+        // K2 tiles, count / scan / scatter
+        k_tiles_per_bucket<<<(nb1 + 255) / 256, 256, 0, st>>>(ctx->d_hist1.as<uint32_t>(), ctx->d_tiles.as<uint32_t>(), nb1, L2_TILE);
+        k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_tiles.as<uint32_t>(), ctx->d_tile_start.as<uint64_t>(), nb1);
+        const unsigned g2 = (unsigned)(n_pos / L2_TILE + nb1 + 1);  // upper bound on the number of tiles
+        CK(cudaEventRecord(ev[2 * T_PART_COUNT], st));
+        k_partition2<true><<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
+                                                 ctx->d_fine_hist.as<uint32_t>(), nullptr, nullptr, nullptr);
+        CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
+        k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), nbins);
+        CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
+        k_partition2<false><<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
+                                                  nullptr, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), ctx->d_keysB.as<uint64_t>());
+        CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
+        // K3 count
+        CountOut co;
+        co.stage_h = ctx->d_keysA.as<uint64_t>();
+        co.stage_c = ctx->d_stage_c.as<uint32_t>();
+        co.surv = ctx->d_surv.as<uint32_t>();
+        co.totals = d_totals;
+        co.chist = ctx->prm.complex_dist ? ctx->d_chist.as<ull>() + (size_t)sample_id * CHIST : nullptr;
+        co.big_counts = ctx->d_big_counts.as<uint32_t>();
+        co.big_sample = ctx->d_big_sample.as<uint32_t>();
+        co.big_n = d_big_n;
+        co.big_cap = ctx->big_cap;
+        co.error_flag = d_error;
+        CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
+        k_bin_count<<<nbins, BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), ctx->prm.abundance_min, ctx->prm.abundance_max, sample_id, co);
+        CK(cudaEventRecord(ev[2 * T_BIN_COUNT + 1], st));
+        k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins);
+        ctx->launches += 9;
+        CK(cudaGetLastError());
+        // the only host sync of the sample: sizes + totals
+        int h_err = 0;
+        CK(cudaMemcpyAsync(&h_surv, ctx->d_out_off.as<uint64_t>() + nbins, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_keys, ctx->d_fine_off.as<uint64_t>() + nbins, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_tot, d_totals, 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_err, d_error, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_err) { ctx->set_error("on-chip table overflow in k_bin_count (code " + std::to_string(h_err) + ")"); return SIMKA_ERR_OVERFLOW; }
+        if (h_surv >= (1ull << 32)) { ctx->set_error("more than 2^32 solid k-mers in one sample shard"); return SIMKA_ERR_INVALID; }
+        CK(cudaEventRecord(ev[2 * T_COMPACT], st));
+        if (h_surv > 0) {
+            sd.eh = (uint64_t *)ctx->arena.alloc(h_surv * 8);
+            sd.ec = (uint32_t *)ctx->arena.alloc(h_surv * 4);
+            if (!sd.eh || !sd.ec) { ctx->set_error("out of device memory (sample list)"); return SIMKA_ERR_NOMEM; }
+            k_compact<<<nbins, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(),
+                                              ctx->d_out_off.as<uint64_t>(), sd.eh, sd.ec);
+            ctx->launches++;
+        }
+        const uint32_t fg = 1u << ctx->fg_bits;
+        k_fill_offsets<<<(fg + 1 + 255) / 256, 256, 0, st>>>(ctx->d_out_off.as<uint64_t>(), sd.off, fg, nbins >> ctx->fg_bits);
+        ctx->launches++;
+        CK(cudaEventRecord(ev[2 * T_COMPACT + 1], st));
+        CK(cudaEventRecord(ev[2 * T_NSTAGE + 1], st));  // sample end
+        CK(cudaEventSynchronize(ev[2 * T_NSTAGE + 1]));
+        float ms = 0;
+        for (int t = 0; t < T_NSTAGE; t++) { cudaEventElapsedTime(&ms, ev[2 * t], ev[2 * t + 1]); ctx->stage_ms[t] += ms; }
+        cudaEventElapsedTime(&ms, ev[2 * T_NSTAGE], ev[2 * T_NSTAGE + 1]);
+        ctx->sample_ms += ms;
+    }
+    sd.n = h_surv;
+    sd.done = true;
+    sd.local.nb_reads = n_reads;
+    sd.local.nb_distinct = h_tot[0];
+    sd.local.nb_kmers = h_tot[1];
+    sd.local.chord_n2 = h_tot[2];
+    if (!ctx->totals_overridden) ctx->global_totals[sample_id] = sd.local;
+    ctx->kmers_in += h_keys;
+    ctx->entries += h_surv;
+    if (sl) { sl->sample = -1; sl->words = sl->reads = 0; sl->ext_packed = nullptr; sl->ext_bad = nullptr; }
+    if (out) *out = sd.local;
+    return SIMKA_OK;
+}
+
+int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers, uint32_t *counts, uint64_t *n) {
+    if (!ctx || !n || sample_id < 0 || sample_id >= ctx->prm.nb_samples || !ctx->samples[sample_id].done) return SIMKA_ERR_INVALID;
+    CK(cudaSetDevice(ctx->prm.device));
+    SampleData &sd = ctx->samples[sample_id];
+    if (!kmers || !counts) { *n = sd.n; return SIMKA_OK; }
+    if (*n < sd.n) { *n = sd.n; return SIMKA_ERR_INVALID; }
+    *n = sd.n;
+    if (sd.n == 0) return SIMKA_OK;
+    uint64_t *tmp = nullptr;
+    CK(cudaMalloc(&tmp, sd.n * 8));
+    k_unmix<<<(unsigned)((sd.n + 255) / 256), 256, 0, ctx->stream>>>(sd.eh, tmp, sd.n, ctx->kp.mix);
+    std::vector<uint64_t> hk(sd.n);
+    std::vector<uint32_t> hc(sd.n);
+    CK(cudaMemcpyAsync(hk.data(), tmp, sd.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hc.data(), sd.ec, sd.n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+    std::vector<uint64_t> order(sd.n);
+    for (uint64_t i = 0; i < sd.n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
+    for (uint64_t i = 0; i < sd.n; i++) { kmers[i] = hk[order[i]]; counts[i] = hc[order[i]]; }
+    return SIMKA_OK;
+}
+
+int simka_gpu_get_totals(simka_ctx *ctx, simka_sample_totals *out) {
+    if (!ctx || !out) return SIMKA_ERR_INVALID;
+    for (int s = 0; s < ctx->prm.nb_samples; s++) out[s] = ctx->samples[s].local;
+    return SIMKA_OK;
+}
+
+int simka_gpu_set_totals(simka_ctx *ctx, const simka_sample_totals *in) {
+    if (!ctx || !in) return SIMKA_ERR_INVALID;
+    for (int s = 0; s < ctx->prm.nb_samples; s++) ctx->global_totals[s] = in[s];
+    ctx->totals_overridden = true;
+    return SIMKA_OK;
+}
+
+int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
+    if (!ctx) return SIMKA_ERR_INVALID;
+    const int N = ctx->prm.nb_samples;
+    for (int s = 0; s < N; s++) if (!ctx->samples[s].done) { ctx->set_error("all samples must be finished before the merge"); return SIMKA_ERR_INVALID; }
+    if (ctx->merged) { ctx->set_error("merge already done"); return SIMKA_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->prm.device));
+    cudaStream_t st = ctx->stream;
+    const size_t nn = (size_t)N * N, ns = (size_t)N * (N + 1) / 2;
+    // slab: nb_shared nn | distinct ns | bc ns | chord nn | hell nn | whit nn | T nn | scalars 4 | kl nn (f64) | ntot N (f64)
+    const size_t words = nn + ns + ns + nn + nn + nn + nn + 4 + nn + N;
+    ctx->acc_bytes = words * 8;
+    if (ctx->d_acc.reserve(ctx->acc_bytes)) { ctx->set_error("out of device memory (accumulators)"); return SIMKA_ERR_NOMEM; }
+    cudaEvent_t e0 = ctx->ev[2 * T_NSTAGE + 2], e1 = ctx->ev[2 * T_NSTAGE + 3];
+    CK(cudaEventRecord(e0, st));
+    CK(cudaMemsetAsync(ctx->d_acc.p, 0, ctx->acc_bytes, st));
+    ull *p = ctx->d_acc.as<ull>();
+    ctx->a_nb_shared = p; p += nn;
+    ctx->a_distinct = p; p += ns;
+    ctx->a_bc = p; p += ns;
+    ctx->a_chord = p; p += nn;
+    ctx->a_hell = p; p += nn;
+    ctx->a_whit = p; p += nn;
+    ctx->a_T = p; p += nn;
+    ctx->a_scalars = p; p += 4;
+    ctx->a_kl = reinterpret_cast<double *>(p); p += nn;
+    ctx->a_ntot = reinterpret_cast<double *>(p);
+    std::vector<double> ntot(N);
+    uint64_t total_entries = 0;
+    for (int s = 0; s < N; s++) { ntot[s] = (double)ctx->global_totals[s].nb_kmers; total_entries += ctx->samples[s].n; }
+    CK(cudaMemcpyAsync(ctx->a_ntot, ntot.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    // pointer tables
+    std::vector<const void *> ptrs(2 * (size_t)N);
+    for (int s = 0; s < N; s++) { ptrs[s] = ctx->samples[s].eh; ptrs[N + s] = ctx->samples[s].ec; }
+    if (ctx->d_ptrs.reserve(ptrs.size() * sizeof(void *))) { ctx->set_error("out of device memory"); return SIMKA_ERR_NOMEM; }
+    CK(cudaMemcpyAsync(ctx->d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
+
+    int *d_error = reinterpret_cast<int *>(ctx->d_small.as<char>() + 32);
+    uint32_t *d_big_n = reinterpret_cast<uint32_t *>(ctx->d_small.as<char>() + 40);
+    uint32_t big_n = 0;
+    if (ctx->prm.complex_dist) CK(cudaMemcpyAsync(&big_n, d_big_n, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));  // host staging vectors are reused below / big_n needed
+    if (ctx->fg_bits >= 0 && total_entries > 0) {
+        int mg_bits = std::min(ctx->fg_bits, ilog2_ceil(std::max<uint64_t>(1, total_entries / MRG_TARGET)));
+        MergeArgs a;
+        a.n = N; a.fg_bits = ctx->fg_bits; a.mg_bits = mg_bits;
+        a.eh = reinterpret_cast<const uint64_t *const *>(ctx->d_ptrs.p);
+        a.ec = reinterpret_cast<const uint32_t *const *>(ctx->d_ptrs.as<const void *>() + N);
+        a.off = ctx->d_off_table.as<uint32_t>();
+        a.ntot = ctx->a_ntot;
+        a.simple = ctx->prm.simple_dist; a.complex_ = ctx->prm.complex_dist;
+        a.nb_shared = ctx->a_nb_shared; a.distinct_shared = ctx->a_distinct; a.braycurtis = ctx->a_bc;
+        a.chord = ctx->a_chord; a.hellinger = ctx->a_hell; a.whittaker = ctx->a_whit; a.kl = ctx->a_kl;
+        a.scalars = ctx->a_scalars; a.error_flag = d_error;
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->prm.device);
+        const uint32_t MG = 1u << mg_bits;
+        const unsigned grid = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * 8);
+        k_merge<<<grid, BLOCK, merge_smem_bytes(N), st>>>(a);
+        ctx->launches++;
+        if (ctx->prm.complex_dist) {
+            big_n = std::min(big_n, ctx->big_cap);
+            k_whittaker_onesided<<<N, BLOCK, 0, st>>>(ctx->d_chist.as<ull>(), ctx->d_big_counts.as<uint32_t>(), ctx->d_big_sample.as<uint32_t>(), big_n,
+                                                     ctx->a_ntot, N, ctx->a_T);
+            k_whittaker_fold<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(ctx->a_whit, ctx->a_T, N);
+            ctx->launches += 2;
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(e1, st));
+    int h_err = 0;
+    CK(cudaMemcpyAsync(&h_err, d_error, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_err) { ctx->set_error("on-chip table overflow in k_merge (code " + std::to_string(h_err) + ")"); return SIMKA_ERR_OVERFLOW; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ctx->merge_ms = ms;
+    ctx->merged = true;
+    return SIMKA_OK;
+}
+
+int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) {
+    if (!ctx || !out || !ctx->merged) { if (ctx) ctx->set_error("merge_and_accumulate has not run"); return SIMKA_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->prm.device));
+    const int N = ctx->prm.nb_samples;
+    const size_t nn = (size_t)N * N, ns = (size_t)N * (N + 1) / 2;
+    std::vector<ull> h(ctx->acc_bytes / 8);
+    CK(cudaMemcpyAsync(h.data(), ctx->d_acc.p, ctx->acc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const ull *nb_shared = h.data();
+    const ull *distinct = nb_shared + nn, *bc = distinct + ns, *chord = bc + ns, *hell = chord + nn, *whit = hell + nn;
+    const ull *scal = whit + nn + nn;
+    const double *kl = reinterpret_cast<const double *>(scal + 4);
+    out->nb_samples = N; out->simple_dist = ctx->prm.simple_dist; out->complex_dist = ctx->prm.complex_dist;
+    out->nb_distinct_kmers = scal[0];
+    out->nb_shared_kmers = scal[1];
+    if (out->totals) for (int s = 0; s < N; s++) out->totals[s] = ctx->global_totals[s];
+    if (out->distinct_shared) memcpy(out->distinct_shared, distinct, ns * 8);
+    if (out->braycurtis_num) memcpy(out->braycurtis_num, bc, ns * 8);
+    if (out->nb_shared) memcpy(out->nb_shared, nb_shared, nn * 8);
+    if (ctx->prm.simple_dist) {
+        if (out->chord_ninj) memcpy(out->chord_ninj, chord, nn * 8);
+        if (out->hellinger) memcpy(out->hellinger, hell, nn * 8);
+        if (out->kulczynski) {  // same increments as the Bray-Curtis numerator, stored in the upper triangle
+            memset(out->kulczynski, 0, nn * 8);
+            for (int i = 0; i < N; i++)
+                for (int j = i + 1; j < N; j++) out->kulczynski[(size_t)i * N + j] = bc[(size_t)j + (size_t)(N - 1) * i - ((size_t)i * (i - 1) / 2)];
+        }
+    }
+    if (ctx->prm.complex_dist) {
+        // one-sided closed forms use this shard's own counts so that shards still sum to the global value
+        if (out->whittaker) memcpy(out->whittaker, whit, nn * 8);
+        if (out->canberra) {
+            memset(out->canberra, 0, nn * 8);
+            for (int i = 0; i < N; i++)
+                for (int j = i + 1; j < N; j++) {
+                    const ull a = distinct[(size_t)j + (size_t)(N - 1) * i - ((size_t)i * (i - 1) / 2)];
+                    out->canberra[(size_t)i * N + j] = ctx->samples[i].local.nb_distinct + ctx->samples[j].local.nb_distinct - 2 * a;
+                }
+        }
+        if (out->kullback_leibler) {
+            const double ln2 = log(2.0);
+            for (size_t q = 0; q < nn; q++) out->kullback_leibler[q] = 0;
+            for (int i = 0; i < N; i++)
+                for (int j = i + 1; j < N; j++) {
+                    const size_t ij = (size_t)i * N + j, ji = (size_t)j * N + i;
+                    double v = kl[ij];
+                    const double Ni = (double)ctx->global_totals[i].nb_kmers, Nj = (double)ctx->global_totals[j].nb_kmers;
+                    // k-mers present in exactly one of the two samples: (c/N_x) * log(2 c N_y / (c N_y + 0)) each
+                    const ull only_i = ctx->samples[i].local.nb_kmers - nb_shared[ij];
+                    const ull only_j = ctx->samples[j].local.nb_kmers - nb_shared[ji];
+                    if (only_i) v += (Nj > 0) ? ln2 * ((double)only_i / Ni) : onesided_kl_term(1.0, Ni, Nj);
+                    if (only_j) v += (Ni > 0) ? ln2 * ((double)only_j / Nj) : onesided_kl_term(1.0, Nj, Ni);
+                    out->kullback_leibler[ij] = v;
+                }
+        }
+    }
+    return SIMKA_OK;
+}
+
+int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
+    if (!ctx || !out) return SIMKA_ERR_INVALID;
+    simka_timings t;
+    memset(&t, 0, sizeof t);
+    t.extract_count_ms = ctx->stage_ms[T_EXTRACT_COUNT];
+    t.extract_scatter_ms = ctx->stage_ms[T_EXTRACT_SCATTER];
+    t.part_count_ms = ctx->stage_ms[T_PART_COUNT];
+    t.part_scatter_ms = ctx->stage_ms[T_PART_SCATTER];
+    t.bin_count_ms = ctx->stage_ms[T_BIN_COUNT];
+    t.compact_ms = ctx->stage_ms[T_COMPACT];
+    t.merge_ms = ctx->merge_ms;
+    t.samples_ms = ctx->sample_ms;
+    t.total_ms = ctx->sample_ms + ctx->merge_ms;
+    t.kmers_in = ctx->kmers_in;
+    t.entries = ctx->entries;
+    t.kernel_launches = ctx->launches;
+    if (ctx->merged && ctx->a_scalars) {
+        ull sc[4];
+        if (cudaMemcpy(sc, ctx->a_scalars, 32, cudaMemcpyDeviceToHost) == cudaSuccess) { t.distinct_kmers = sc[0]; t.pairs = sc[2]; }
+    }
+    *out = t;
+    return SIMKA_OK;
+}
+
+int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *counts, uint32_t n, uint32_t s, float *jaccard,
+                          float *braycurtis, float *kernel_ms) {
+    if (!hashes || !counts || !jaccard || !braycurtis || n == 0 || s == 0) return SIMKA_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return SIMKA_ERR_CUDA;
+    uint64_t *dh = nullptr; uint32_t *dc = nullptr, *dstart = nullptr; ull *dq = nullptr;
+    const size_t ne = (size_t)n * s, nn = (size_t)n * n;
+    const uint64_t pairs = (uint64_t)n * (n - 1) / 2;
+    int rc = SIMKA_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<ull> hq(4 * pairs);
+    do {
+        if (cudaMalloc(&dh, ne * 8) || cudaMalloc(&dc, ne * 4) || cudaMalloc(&dstart, (size_t)n * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
+        if (cudaMemcpy(dh, hashes, ne * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc, counts, ne * 4, cudaMemcpyHostToDevice)) { rc = SIMKA_ERR_CUDA; break; }
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        k_sketch_starts<<<(n + 255) / 256, 256>>>(dh, n, s, dstart);
+        if (pairs) k_simkamin_pair<<<(unsigned)pairs, BLOCK>>>(dh, dc, dstart, n, s, dq);
+        cudaEventRecord(e1);
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
+        if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
+        if (pairs && cudaMemcpy(hq.data(), dq, pairs * 32, cudaMemcpyDeviceToHost)) { rc = SIMKA_ERR_CUDA; break; }
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(dh); cudaFree(dc); cudaFree(dstart); cudaFree(dq);
+    if (rc) return rc;
+    // final ratios exactly as the reference: long double division, stored as float (:244-259)
+    for (size_t q = 0; q < nn; q++) { jaccard[q] = 0; braycurtis[q] = 0; }
+    uint64_t p = 0;
+    for (uint32_t i = 0; i < n; i++)
+        for (uint32_t j = i + 1; j < n; j++, p++) {
+            const ull sh = hq[4 * p], di = hq[4 * p + 1], sk = hq[4 * p + 2], km = hq[4 * p + 3];
+            float ja = di == 0 ? 1.0f : (float)(1 - (long double)sh / (long double)di);
+            float b = km == 0 ? 1.0f : (float)(1 - (long double)(2 * sk) / (long double)km);
+            jaccard[(size_t)i * n + j] = jaccard[(size_t)j * n + i] = ja;
+            braycurtis[(size_t)i * n + j] = braycurtis[(size_t)j * n + i] = b;
+        }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// simka_host.cpp -- host-side pieces of the C ABI that need no GPU: read packing, the distance
+// closed forms and the CSV writer.  The distance formulas are the cold N^2 tail of the path
+// (SURVEY.md 3.4); they are evaluated on the host in the reference's own precision (long double
+// where it uses long double) so that the %f output is byte-identical.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/simka_b200.h"
+
+namespace {
+
+inline size_t sym_index(size_t n, size_t i, size_t j) { return j + (n - 1) * i - (i * (i - 1) / 2); }  // src/core/SimkaAlgorithm.hpp:364
+
+// ---- SimkaDistance (src/core/SimkaDistance.cpp:920-1226) -----------------------------------------
+struct Dist {
+    const simka_stats_view &s;
+    size_t n;
+    explicit Dist(const simka_stats_view &v) : s(v), n((size_t)v.nb_samples) {}
+    uint64_t D(size_t i) const { return s.totals[i].nb_distinct; }   // _nbSolidDistinctKmersPerBank
+    uint64_t NS(size_t i) const { return s.totals[i].nb_kmers; }     // _nbSolidKmersPerBank
+    uint64_t sq(const uint64_t *m, size_t i, size_t j) const { return m ? m[i * n + j] : 0; }
+    void abc(size_t i, size_t j, double &a, double &b, double &c) const {  // get_abc :920-926
+        uint64_t ua = s.distinct_shared[sym_index(n, i, j)];
+        a = (double)ua; b = (double)(D(i) - ua); c = (double)(D(j) - ua);
+    }
+    double ab_braycurtis(size_t i, size_t j) const {  // :928-939
+        double union_ = NS(i) + NS(j);
+        if (union_ == 0) return 1;
+        double inter = 2 * s.braycurtis_num[sym_index(n, i, j)];
+        return 1 - inter / union_;
+    }
+    double ab_chord(size_t i, size_t j) const {  // :942-959; _chord_sqrt_N2 = sqrt(u64) kept as long double (:132)
+        long double si = sqrt((double)s.totals[i].chord_n2), sj = sqrt((double)s.totals[j].chord_n2);
+        double den = si * sj;
+        if (den == 0) return sqrt(2);
+        long double ninj = (long double)sq(s.chord_ninj, i, j);
+        long double v = sqrtl(2 - 2 * ninj / den);
+        return (double)v;
+    }
+    double ab_hellinger(size_t i, size_t j) const {  // :962-972
+        double union_ = sqrt((double)NS(i)) * sqrt((double)NS(j));
+        if (union_ == 0) return sqrt(2);
+        double inter = 2 * sq(s.hellinger, i, j);
+        return sqrt(2 - (inter / union_));
+    }
+    double ab_whittaker(size_t i, size_t j) const {  // :988-998
+        long double union_ = NS(i) * NS(j);
+        if (union_ == 0) return 1;
+        long double inter = sq(s.whittaker, i, j);
+        double w = 0.5 * (inter / union_);
+        return w;
+    }
+    double ab_kl(size_t i, size_t j) const {  // :1001-1007
+        long double v = s.kullback_leibler ? (long double)s.kullback_leibler[i * n + j] : 0;
+        if (v == 0) return 1;
+        return sqrt(0.5 * v);
+    }
+    double ab_canberra(size_t i, size_t j) const {  // :1010-1021
+        double a, b, c; abc(i, j, a, b, c);
+        if ((a + b + c) == 0) return 1;
+        return (1 / (a + b + c)) * sq(s.canberra, i, j);
+    }
+    double ab_kulczynski(size_t i, size_t j) const {  // :1024-1038 ([j][i] is never written by the update)
+        if (NS(i) == 0 || NS(j) == 0) return 1;
+        long double n1 = (double)sq(s.kulczynski, i, j) / (double)NS(i);
+        long double n2 = (double)sq(s.kulczynski, j, i) / (double)NS(j);
+        double v = 1 - 0.5 * (n1 + n2);
+        return v;
+    }
+    double ab_jaccard_simka(size_t i, size_t j, bool sym) const {  // :1041-1065
+        double A1 = sq(s.nb_shared, i, j), B1 = sq(s.nb_shared, j, i), A0 = NS(i), B0 = NS(j);
+        double num = sym ? A1 + B1 : A1, den = sym ? A0 + B0 : A0;
+        if (den == 0) return 1;
+        return 1 - num / den;
+    }
+    double ab_ochiai(size_t i, size_t j) const {  // :1068-1078
+        double A1 = sq(s.nb_shared, i, j), B1 = sq(s.nb_shared, j, i), A0 = NS(i), B0 = NS(j);
+        if (A0 == 0 || B0 == 0) return 1;
+        return 1 - sqrt(A1 / A0) * sqrt(B1 / B0);
+    }
+    double ab_sorensen(size_t i, size_t j) const {  // :1081-1096
+        double A1 = sq(s.nb_shared, i, j), B1 = sq(s.nb_shared, j, i), A0 = NS(i), B0 = NS(j);
+        double num = 2 * A1 * B1, den = A0 * B1 + A1 * B0;
+        if (den == 0) return 1;
+        return 1 - num / den;
+    }
+    double ab_jaccard(size_t i, size_t j) const {  // :1099-1115
+        double A1 = sq(s.nb_shared, i, j), B1 = sq(s.nb_shared, j, i), A0 = NS(i), B0 = NS(j);
+        double num = A1 * B1, den = A0 * B1 + A1 * B0 - A1 * B1;
+        if (den == 0) return 1;
+        return 1 - num / den;
+    }
+    static double pa_chord(double a, double b, double c) {  // :1117-1127
+        double p1 = sqrt((a + b) * (a + c));
+        if (p1 == 0) return sqrt(2);
+        return sqrt(2 * (1 - a / p1));
+    }
+    static double pa_whittaker(double a, double b, double c) {  // :1129-1145
+        if (a + b == 0 || a + c == 0) return 1;
+        double p1 = b / (a + b), p2 = c / (a + c), p3 = a / (a + b), p4 = a / (a + c);
+        return 0.5 * (p1 + p2 + fabs(p3 - p4));
+    }
+    static double pa_kulczynski(double a, double b, double c) {  // :1156-1170
+        if (a + b == 0 || a + c == 0) return 1;
+        return 1 - 0.5 * (a / (a + b) + a / (a + c));
+    }
+    static double pa_braycurtis(double a, double b, double c) {  // :1172-1183
+        if ((2 * a + b + c) == 0) return 1;
+        return (b + c) / (2 * a + b + c);
+    }
+    static double pa_ochiai(double a, double b, double c) {  // :1188-1199 (float denominator)
+        float val = sqrt((a + b) * (a + c));
+        if (val == 0) return 1;
+        return 1 - (a / val);
+    }
+    static double pa_jaccard(double a, double b, double c) {  // :1201-1209
+        if ((a + b + c) == 0) return 1;
+        return (b + c) / (a + b + c);
+    }
+    double pa_jaccard_simka(size_t i, size_t j, size_t idx, bool sym) const {  // :1211-1226
+        double num = sym ? 2 * s.distinct_shared[idx] : s.distinct_shared[idx];
+        double den = sym ? D(i) + D(j) : D(i);
+        if (den == 0) return 1;
+        return 1 - num / den;
+    }
+};
+
+// order and names of outputMatrix (src/core/SimkaDistance.cpp:617-648)
+const char *const NAMES[21] = {
+    "mat_presenceAbsence_chord", "mat_presenceAbsence_whittaker", "mat_presenceAbsence_kulczynski",
+    "mat_presenceAbsence_braycurtis", "mat_presenceAbsence_jaccard", "mat_presenceAbsence_simka-jaccard",
+    "mat_presenceAbsence_simka-jaccard_asym", "mat_presenceAbsence_ochiai",
+    "mat_abundance_simka-jaccard", "mat_abundance_simka-jaccard_asym", "mat_abundance_ab-ochiai",
+    "mat_abundance_ab-sorensen", "mat_abundance_ab-jaccard", "mat_abundance_braycurtis", "mat_abundance_jaccard",
+    "mat_abundance_chord", "mat_abundance_hellinger", "mat_abundance_kulczynski",
+    "mat_abundance_whittaker", "mat_abundance_jensenshannon", "mat_abundance_canberra"};
+
+int matrix_id(const simka_stats_view *s, int m) {
+    if (m < 0) return -1;
+    if (m < 15) return m;
+    if (s->simple_dist) { if (m < 18) return m; m -= 3; }
+    if (s->complex_dist && m >= 15 && m < 18) return m + 3;
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int simka_nb_matrices(const simka_stats_view *s) { return s ? 15 + (s->simple_dist ? 3 : 0) + (s->complex_dist ? 3 : 0) : 0; }
+
+const char *simka_matrix_name(const simka_stats_view *s, int m) {
+    int id = s ? matrix_id(s, m) : -1;
+    return id < 0 ? nullptr : NAMES[id];
+}
+
+int simka_distance_matrix(const simka_stats_view *s, int m, float *out) {
+    if (!s || !out || !s->totals || !s->distinct_shared || !s->braycurtis_num || !s->nb_shared) return SIMKA_ERR_INVALID;
+    const int id = matrix_id(s, m);
+    if (id < 0) return SIMKA_ERR_INVALID;
+    Dist d(*s);
+    const size_t n = d.n;
+    memset(out, 0, n * n * sizeof(float));
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = i + 1; j < n; j++) {
+            double a, b, c; d.abc(i, j, a, b, c);
+            const size_t idx = sym_index(n, i, j);
+            double v = 0, w = 0; bool asym = false;
+            switch (id) {
+            case 0: v = Dist::pa_chord(a, b, c); break;
+            case 1: v = Dist::pa_whittaker(a, b, c); break;
+            case 2: v = Dist::pa_kulczynski(a, b, c); break;
+            case 3: v = Dist::pa_braycurtis(a, b, c); break;
+            case 4: v = Dist::pa_jaccard(a, b, c); break;
+            case 5: v = d.pa_jaccard_simka(i, j, idx, true); break;
+            case 6: v = d.pa_jaccard_simka(i, j, idx, false); w = d.pa_jaccard_simka(j, i, idx, false); asym = true; break;
+            case 7: v = Dist::pa_ochiai(a, b, c); break;
+            case 8: v = d.ab_jaccard_simka(i, j, true); break;
+            case 9: v = d.ab_jaccard_simka(i, j, false); w = d.ab_jaccard_simka(j, i, false); asym = true; break;
+            case 10: v = d.ab_ochiai(i, j); break;
+            case 11: v = d.ab_sorensen(i, j); break;
+            case 12: v = d.ab_jaccard(i, j); break;
+            case 13: case 14: v = d.ab_braycurtis(i, j); break;
+            case 15: v = d.ab_chord(i, j); break;
+            case 16: v = d.ab_hellinger(i, j); break;
+            case 17: v = d.ab_kulczynski(i, j); break;
+            case 18: v = d.ab_whittaker(i, j); break;
+            case 19: v = d.ab_kl(i, j); break;
+            case 20: v = d.ab_canberra(i, j); break;
+            }
+            out[i * n + j] = (float)v;
+            out[j * n + i] = asym ? (float)w : (float)v;
+        }
+    if (id == 14)  // computeJaccardDistanceFromBrayCurtis works on the float matrix (src/core/SimkaDistance.hpp:463-475)
+        for (size_t q = 0; q < n * n; q++) { double B = out[q]; double J = (2 * B) / (1 + B); out[q] = (float)J; }
+    return SIMKA_OK;
+}
+
+size_t simka_matrix_csv(const simka_stats_view *s, int m, const char *const *ids, char *buf, size_t cap) {
+    if (!s || !ids) return 0;
+    const size_t n = (size_t)s->nb_samples;
+    std::vector<float> mat(n * n);
+    if (simka_distance_matrix(s, m, mat.data()) != SIMKA_OK) return 0;
+    std::string str;
+    for (size_t i = 0; i < n; i++) { str += ";"; str += ids[i]; }
+    str += '\n';
+    char num[64];
+    for (size_t i = 0; i < n; i++) {
+        str += ids[i];
+        for (size_t j = 0; j < n; j++) { snprintf(num, sizeof num, ";%f", mat[i * n + j]); str += num; }
+        str += '\n';
+    }
+    if (buf && cap > str.size()) memcpy(buf, str.c_str(), str.size() + 1);
+    return str.size();
+}
+
+int simka_write_matrices(const simka_stats_view *s, const char *const *ids, const char *out_dir) {
+    if (!s || !ids || !out_dir) return SIMKA_ERR_INVALID;
+    const int nm = simka_nb_matrices(s);
+    for (int m = 0; m < nm; m++) {
+        size_t need = simka_matrix_csv(s, m, ids, nullptr, 0);
+        std::vector<char> buf(need + 1);
+        simka_matrix_csv(s, m, ids, buf.data(), need + 1);
+        std::string path = std::string(out_dir) + "/" + simka_matrix_name(s, m) + ".csv.gz";
+        gzFile f = gzopen(path.c_str(), "wb");
+        if (!f) return SIMKA_ERR_IO;
+        gzwrite(f, buf.data(), (unsigned)need);
+        gzclose(f);
+    }
+    return SIMKA_OK;
+}
+
+// ---- read packing ----------------------------------------------------------------------------------
+
+uint64_t simka_pack_words(uint64_t total_bases, uint64_t n_reads) { return (total_bases + n_reads + 31) / 32; }
+
+uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n_reads, uint64_t *packed, uint32_t *bad, int nthreads) {
+    const uint64_t base0 = n_reads ? read_off[0] : 0;
+    const uint64_t total = n_reads ? read_off[n_reads] - base0 : 0;
+    const uint64_t n_words = simka_pack_words(total, n_reads);
+    if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if ((uint64_t)nthreads > n_words / 4096 + 1) nthreads = (int)(n_words / 4096 + 1);
+    auto work = [&](uint64_t w0, uint64_t w1) {
+        // stream position p = (read_off[r]-base0) + r + o; find the read containing position 32*w0
+        const uint64_t p0 = w0 * 32;
+        uint64_t r = 0;
+        if (n_reads) {
+            uint64_t lo = 0, hi = n_reads;  // start(lo) <= p0 < start(hi)
+            if (total + n_reads <= p0) r = n_reads;
+            else {
+                while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (read_off[mid] - base0 + mid <= p0) lo = mid; else hi = mid; }
+                r = lo;
+            }
+        }
+        uint64_t rbeg = 0, rend = 0, o = 0;
+        if (r < n_reads) { rbeg = read_off[r]; rend = read_off[r + 1]; o = p0 - (rbeg - base0 + r); }
+        for (uint64_t w = w0; w < w1; w++) {
+            uint64_t v = 0; uint32_t b = 0;
+            for (int j = 0; j < 32; j++) {
+                uint32_t code = 0, isbad = 1;
+                if (r < n_reads) {
+                    if (rbeg + o < rend) {
+                        unsigned char c = (unsigned char)seqs[rbeg + o];
+                        code = (c >> 1) & 3u;  // GC/tools/misc/api/Data.hpp:179
+                        unsigned char u = c & 0xDF;
+                        isbad = !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
+                        o++;
+                    } else {  // separator after the read
+                        r++;
+                        if (r < n_reads) { rbeg = rend; rend = read_off[r + 1]; }
+                        o = 0;
+                    }
+                }
+                v = (v << 2) | code;
+                b = (b << 1) | isbad;
+            }
+            packed[w] = v;
+            bad[w] = b;
+        }
+    };
+    if (nthreads == 1) work(0, n_words);
+    else {
+        std::vector<std::thread> th;
+        const uint64_t per = (n_words + nthreads - 1) / nthreads;
+        for (int t = 0; t < nthreads; t++) {
+            uint64_t w0 = (uint64_t)t * per, w1 = std::min<uint64_t>(n_words, w0 + per);
+            if (w0 < w1) th.emplace_back(work, w0, w1);
+        }
+        for (auto &t : th) t.join();
+    }
+    packed[n_words] = 0;
+    bad[n_words] = 0xFFFFFFFFu;
+    return n_words;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import simka_b200
+from helpers import assert_stats_equal, nasty_samples, oracle_run, synthetic_samples
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def load_example(golden_dir):
+    spec = oracle.parse_simka_input(os.path.join(golden_dir, "example", "simka_input.txt"))
+    ids, samples = [], []
+    for ident, groups in spec:
+        ids.append(ident)
+        datas, offs, base = [], [np.zeros(1, np.uint64)], 0
+        for grp in groups:
+            for f in grp:
+                d, o = oracle.read_fastx(f)
+                datas.append(d)
+                offs.append(o[1:] + np.uint64(base))
+                base += len(d)
+        samples.append((np.concatenate(datas), np.concatenate(offs)))
+    return ids, samples
+
+
+@pytest.mark.parametrize("k", [21, 31])
+@pytest.mark.parametrize("t", [0, 2])
+def test_example_csv_byte_identical(golden_dir, k, t):
+    """The reference's own end-to-end golden test (tests/simple_test.py:93-119) through the GPU path."""
+    ids, samples = load_example(golden_dir)
+    st = simka_b200.run_samples(samples, k, abundance_min=t, simple_dist=True, complex_dist=True)
+    tdir = os.path.join(golden_dir, "truth", f"results_k{k}_t{t}")
+    checked = 0
+    for m, name in enumerate(st.matrix_names()):
+        path = os.path.join(tdir, name + ".csv")
+        if not os.path.exists(path):
+            continue  # mat_abundance_jaccard has no truth file in the reference either
+        assert st.csv(m, ids) == open(path).read(), name
+        checked += 1
+    assert checked == 20
+
+
+@pytest.mark.parametrize("k,amin", [(31, 2), (21, 1), (15, 2), (9, 0)])
+def test_synthetic_per_sample_counts_and_stats(k, amin):
+    samples = synthetic_samples(6, 3000)
+    run = oracle_run(samples, k, amin)
+    st, ctx = simka_b200.run_samples(samples, k, abundance_min=amin, keep_ctx=True)
+    for s in range(len(samples)):
+        km, ct = ctx.dump_sample_counts(s)
+        okm, oct_ = run.sample(s)
+        np.testing.assert_array_equal(km, okm)
+        np.testing.assert_array_equal(ct, oct_)
+    ctx.close()
+    assert_stats_equal(st, run)
+
+
+@pytest.mark.parametrize("ascii_path", [False, True])
+def test_nasty_inputs(ascii_path):
+    samples = nasty_samples()
+    for k, amin, amax in [(31, 0, 999999999), (21, 2, 999999999), (21, 1, 30)]:
+        run = oracle_run(samples, k, amin, amax)
+        st = simka_b200.run_samples(samples, k, abundance_min=amin, abundance_max=amax, ascii_path=ascii_path)
+        assert_stats_equal(st, run)
+        # duplicated sample -> distance exactly 0 in Bray-Curtis
+        assert st.matrix("mat_abundance_braycurtis")[1, 4] == 0.0
+
+
+@pytest.mark.parametrize("simple,complex_", [(False, False), (True, False), (False, True)])
+def test_distance_family_flags(simple, complex_):
+    samples = synthetic_samples(4, 1500)
+    run = oracle_run(samples, 25, 2, simple=simple, complex_=complex_)
+    st = simka_b200.run_samples(samples, 25, abundance_min=2, simple_dist=simple, complex_dist=complex_)
+    assert_stats_equal(st, run)
+
+
+def test_medium_size_larger_bins():
+    """Enough k-mers per sample for multi-tile buckets and thousands of bins."""
+    samples = synthetic_samples(5, 40000, n_genomes=32, genome_len=20000)
+    run = oracle_run(samples, 31, 2)
+    st = simka_b200.run_samples(samples, 31, abundance_min=2)
+    assert_stats_equal(st, run)
+
+
+def test_many_samples():
+    samples = synthetic_samples(40, 600, read_len=100, n_genomes=8, genome_len=3000)
+    run = oracle_run(samples, 21, 2)
+    st = simka_b200.run_samples(samples, 21, abundance_min=2)
+    assert_stats_equal(st, run)
+
+
+def test_shards_sum_to_whole():
+    """Multi-GPU semantics on one device: the accumulators of S shard contexts sum to the unsharded
+    run (the reference's per-partition stats sum, src/SimkaPotara.hpp:1161-1174)."""
+    samples = synthetic_samples(5, 2500)
+    run = oracle_run(samples, 31, 2)
+    S = 3
+    ctxs = [simka_b200.SimkaGpu(len(samples), 31, 2, simple_dist=True, complex_dist=True, shard_rank=r, shard_count=S)
+            for r in range(S)]
+    for c in ctxs:
+        for s, (seqs, off) in enumerate(samples):
+            p, b, nw = simka_b200.pack_reads(seqs, off)
+            c.push_reads(s, p, b, nw, len(off) - 1)
+            c.finish_sample(s)
+    tot = sum(c.get_totals() for c in ctxs)
+    tot[:, 0] = ctxs[0].get_totals()[:, 0]  # nb_reads is per sample, not summed
+    total = None
+    for c in ctxs:
+        c.set_totals(tot)
+        c.merge_and_accumulate()
+        st = c.stats()
+        if total is None:
+            total = st
+        else:
+            total += st
+        c.close()
+    assert_stats_equal(total, run)
+
+
+def test_simkamin_distance():
+    from simka_b200 import synth
+    hashes, counts = synth.make_sketches(12, 5000)
+    hashes[3, :700] = 0  # a short sketch: zero padding at the front
+    counts[3, :700] = 0
+    jac, bc, _ = simka_b200.simkamin_distance(hashes, counts)
+    ojac, obc = oracle.simkamin_distance(hashes, counts)
+    np.testing.assert_array_equal(jac, ojac)
+    np.testing.assert_array_equal(bc, obc)

@@ -1,0 +1,100 @@
+"""CPU tests: the oracle against every golden vector the reference's own tests hold for this path
+(SURVEY.md 8c).  These pin the oracle; the GPU tests then compare the CUDA path with it."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+# count_synchro/<id>.ok known answers of a reference run: reads distinct sum sum^2
+KNOWN_TOTALS = {
+    (31, 2): {"A": (99, 3840, 7920, 16560), "B": (102, 880, 1840, 3920), "C": (98, 240, 560, 1360),
+              "D": (146, 880, 2080, 6080), "E": (402, 7200, 32160, 188480)},
+    (31, 0): {"B": (102, 7200, 8160, 10240), "C": (98, 7520, 7840, 8640), "D": (146, 10480, 11680, 15680)},
+    (21, 2): {"A": (99, 4320, 8910, 18630), "B": (102, 990, 2070, 4410), "C": (98, 270, 630, 1530),
+              "D": (146, 990, 2340, 6840), "E": (402, 8100, 36180, 212040)},
+    (21, 0): {"B": (102, 8100, 9180, 11520), "C": (98, 8460, 8820, 9720), "D": (146, 11790, 13140, 17640)},
+}
+
+
+def test_kmer_model_known_answers():
+    """gatb-core test/unit/src/kmer/TestKmer.cpp:141-147,178-191"""
+    seq = b"CATTGATAGTGG"
+    km, va = oracle.direct_kmers(seq, 3)
+    assert km.tolist() == [18, 10, 43, 44, 50, 8, 35, 14, 59, 47] and va.all()
+    km, va = oracle.canonical_kmers(seq, 3)
+    assert km.tolist() == [11, 2, 16, 36, 9, 8, 24, 6, 17, 20] and va.all()
+
+
+def test_kmer_model_bad_chars():
+    """windows containing a non-ACGT char are invalid (Model.hpp:754-758); lower case is valid"""
+    km, va = oracle.canonical_kmers(b"ACGTNACGTAC", 4)
+    assert va.tolist() == [True, False, False, False, False, True, True, True]
+    a, _ = oracle.canonical_kmers(b"acgtacgt", 4)
+    b, _ = oracle.canonical_kmers(b"ACGTACGT", 4)
+    assert a.tolist() == b.tolist()
+    assert len(oracle.canonical_kmers(b"ACG", 4)[0]) == 0
+
+
+def test_revcomp_and_minimizer():
+    L = oracle.lib()
+    # AAAC -> GTTT ; code A=0 C=1 T=2 G=3
+    assert L.orc_revcomp(0b00000001, 4) == 0b11101010
+    # minimizer never exceeds the default 4^m-1 and is strand-independent
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        x = int(rng.integers(0, 2**62))
+        rc = L.orc_revcomp(x, 31)
+        m1, m2 = L.orc_minimizer(x, 31, 7), L.orc_minimizer(rc, 31, 7)
+        assert m1 == m2 and m1 <= 4**7 - 1
+
+
+@pytest.mark.parametrize("k", [21, 31])
+@pytest.mark.parametrize("t", [0, 2])
+def test_truth_matrices_byte_identical(golden_dir, k, t):
+    """reference tests/simple_test.py:93-119: 20 matrices per (k, abundance-min), byte compare"""
+    run, ids = oracle.run_from_input_file(os.path.join(golden_dir, "example", "simka_input.txt"), k, abundance_min=t)
+    run.merge()
+    assert ids == ["A", "B", "C", "D", "E"]
+    tdir = os.path.join(golden_dir, "truth", f"results_k{k}_t{t}")
+    names = run.matrix_names()
+    assert len(names) == 21
+    checked = 0
+    for m, name in enumerate(names):
+        path = os.path.join(tdir, name + ".csv")
+        if not os.path.exists(path):
+            assert name == "mat_abundance_jaccard"  # produced by the reference but it ships no truth file
+            continue
+        assert run.csv(m, ids) == open(path).read(), name
+        checked += 1
+    assert checked == 20
+    tot = run.all_totals()
+    for ident, exp in KNOWN_TOTALS[(k, t)].items():
+        assert tuple(int(x) for x in tot[ids.index(ident)]) == exp
+    # consequence of the u64 Canberra accumulator
+    np.testing.assert_array_equal(run.matrix("mat_abundance_canberra"), run.matrix("mat_presenceAbsence_jaccard"))
+
+
+def test_partition_independence(golden_dir):
+    """reference tests/simple_test.py:122-129: results must not depend on the resources / split"""
+    path = os.path.join(golden_dir, "example", "simka_input.txt")
+    a, ids = oracle.run_from_input_file(path, 21, abundance_min=0, nthreads=1)
+    b, _ = oracle.run_from_input_file(path, 21, abundance_min=0, nthreads=4)
+    a.merge(), b.merge()
+    for m in range(len(a.matrix_names())):
+        assert a.csv(m, ids) == b.csv(m, ids)
+
+
+def test_fastx_reader_variants(tmp_path):
+    """multi-line FASTA, FASTQ, gz, CRLF, empty lines: kseq rules of BankFasta.cpp:485-572"""
+    import gzip
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(b">r1 comment\nACGT\nACGT\n\n>r2\r\nTTTT\r\n>r3\n")
+    d, o = oracle.read_fastx(str(fa))
+    assert [bytes(d[o[i]:o[i + 1]]) for i in range(len(o) - 1)] == [b"ACGTACGT", b"TTTT", b""]
+    fq = tmp_path / "a.fq.gz"
+    with gzip.open(fq, "wb") as f:
+        f.write(b"@q1\nACGTN\n+\n@IIII\n@q2\nGG\nCC\n+q2\nII\nII\n")
+    d, o = oracle.read_fastx(str(fq))
+    assert [bytes(d[o[i]:o[i + 1]]) for i in range(len(o) - 1)] == [b"ACGTN", b"GGCC"]
