@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--kmer", type=int, default=31)
     ap.add_argument("--abundance-min", type=int, default=2)
-    ap.add_argument("--ref-reads", type=int, default=30_000, help="reads/sample of the bounded CPU sample")
+    ap.add_argument("--ref-reads", type=int, default=300_000, help="reads/sample of the bounded CPU sample (about 10-20 s of CPU work per pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

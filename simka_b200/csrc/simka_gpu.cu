@@ -255,9 +255,24 @@ __global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t *__restric
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (uint64_t base = 0; base < n; base += 1024) {
-        uint64_t i = base + tid;
-        uint64_t v = i < n ? in[i] : 0, inc = v;
+    constexpr int PER = 16;  // consecutive elements per thread and round
+    for (uint64_t base = 0; base < n; base += 1024 * PER) {
+        const uint64_t i0 = base + (uint64_t)tid * PER;
+        uint32_t x[PER];
+        if (i0 + PER <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < PER / 4; q++) {
+                const uint4 t4 = *reinterpret_cast<const uint4 *>(in + i0 + 4 * q);
+                x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < PER; q++) x[q] = (i0 + q < n) ? in[i0 + q] : 0;
+        }
+        uint64_t v = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) v += x[q];
+        uint64_t inc = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint64_t u = __shfl_up_sync(0xffffffffu, inc, d);
@@ -276,7 +291,12 @@ __global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t *__restric
             if (lane == 31) warp_sum[32] = winc;
         }
         __syncthreads();
-        if (i < n) out[i] = carry + warp_sum[wid] + inc - v;
+        uint64_t run = carry + warp_sum[wid] + inc - v;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            if (i0 + q < n) out[i0 + q] = run;
+            run += x[q];
+        }
         __syncthreads();
         if (tid == 0) carry += warp_sum[32];
         __syncthreads();
@@ -1131,7 +1151,9 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         uint64_t per_sample = ctx->prm.expected_kmers_per_sample ? ctx->prm.expected_kmers_per_sample : n_pos;
         uint64_t want = std::max<uint64_t>(1, (per_sample / 4) * (uint64_t)ctx->prm.nb_samples / MRG_TARGET);
         int fg = ilog2_ceil(want);
-        fg = std::min(fg, std::min(W, 22));
+        // never finer than the counting bins of a sample of the expected size (merge bins may be coarser)
+        const int bb = std::min(ilog2_ceil(std::max<uint64_t>(1, per_sample / BIN_TARGET)), 20);
+        fg = std::min(fg, std::min(W, bb));
         while (fg > 0 && ((size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4) > ((size_t)2 << 30)) fg--;
         ctx->fg_bits = fg;
         const size_t tbl = (size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4;
