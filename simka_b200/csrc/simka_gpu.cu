@@ -47,9 +47,9 @@ constexpr int L1_TILE = BLOCK * L1_KPT;      // 8192 keys
 constexpr int L2_KPT = 16;
 constexpr int L2_TILE = BLOCK * L2_KPT;      // 4096 keys
 constexpr int MAX_B = 1024;                  // max buckets per partition level
-constexpr int BIN_TARGET = 512;              // average keys per fine bin
+constexpr int BIN_TARGET = 512;              // fine bins hold BIN_TARGET..2*BIN_TARGET keys on average
 constexpr int CNT_SLOTS = 2048;              // K3 hash table slots
-constexpr int CNT_SUBPASS_KEYS = 1024;       // keys per sub-pass when a bin is oversized
+constexpr int CNT_MAXDISTINCT = 1536;        // distinct keys one table pass may hold (load 0.75)
 constexpr int CHIST = 1024;                  // dense abundance histogram bins (complex distances)
 constexpr int MRG_SLOTS = 2048;              // merge hash table slots
 constexpr int MRG_CAP = 2048;                // merge: grouped entries held in shared memory
@@ -394,77 +394,145 @@ struct CountOut {
     uint32_t *stage_c;
     uint32_t *surv;         // [nbins] survivor count per bin
     ull *totals;            // [3] distinct, sum c, sum c^2
-    ull *chist;             // [CHIST] abundance histogram of this sample (complex only) or null
-    uint32_t *big_counts;   // overflow list for counts >= CHIST
-    uint32_t *big_sample;
-    uint32_t *big_n;
-    uint32_t big_cap;
     int *error_flag;
 };
 
+// insert one key into the open-addressing table (linear probing).  Plain read first: most keys
+// are repeats of a k-mer that is already there, which then costs one LDS + one ATOMS.POPC.INC.
+// TRACK: count the distinct keys claimed (only for bins that might not fit).
+template <bool TRACK>
+__device__ __forceinline__ void table_insert(uint64_t *tk, uint32_t *tc, uint32_t *distinct, uint64_t h, uint32_t slot) {
+    volatile uint64_t *vk = tk;
+#pragma unroll 1
+    for (int probes = 0; probes < CNT_SLOTS; probes++) {
+        uint64_t cur = vk[slot];
+        if (cur == EMPTY) {
+            cur = atomicCAS(reinterpret_cast<ull *>(&tk[slot]), (ull)EMPTY, (ull)h);
+            if (cur == EMPTY) { cur = h; if (TRACK) atomicAdd(distinct, 1u); }
+        }
+        if (cur == h) { atomicAdd(&tc[slot], 1u); return; }
+        slot = (slot + 1) & (CNT_SLOTS - 1);
+    }
+    atomicAdd(distinct, (uint32_t)CNT_SLOTS);  // table full (only reachable when TRACK): force a finer retry
+}
+
+template <bool TRACK>
+__device__ __forceinline__ void bin_insert_all(uint64_t *tk, uint32_t *tc, uint32_t *distinct, const uint64_t *__restrict__ kb,
+                                               uint32_t n, uint32_t R, uint32_t r, int slot_shift) {
+    const int tid = threadIdx.x;
+    for (uint32_t base = 0; base < n; base += BLOCK * 4) {
+        uint64_t h[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = base + q * BLOCK + tid;
+            h[q] = i < n ? kb[i] : EMPTY;
+        }
+        if (TRACK && *((volatile uint32_t *)distinct) > CNT_MAXDISTINCT) return;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (h[q] == EMPTY) continue;
+            if (TRACK && R > 1 && (((uint32_t)(simka::hash2(h[q]) >> 20)) & (R - 1)) != r) continue;
+            table_insert<TRACK>(tk, tc, distinct, h[q], (uint32_t)(h[q] >> slot_shift) & (CNT_SLOTS - 1));
+        }
+    }
+}
+
+// Persistent CTAs, bins taken with a grid stride.  The table is left clean by the read-out scan, so
+// the only per-bin fixed cost is that scan (8 slots per thread, 128-bit shared loads and stores).
 __global__ void __launch_bounds__(BLOCK)
-k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine_off, int64_t amin, int64_t amax,
-            int sample, CountOut out) {
-    __shared__ uint64_t tk[CNT_SLOTS];
-    __shared__ uint32_t tc[CNT_SLOTS];
-    __shared__ uint32_t chist[CHIST];
-    __shared__ uint32_t s_cursor;
+k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine_off, uint32_t nbins, int slot_shift,
+            int64_t amin, int64_t amax, CountOut out) {
+    static_assert(CNT_SLOTS == 8 * BLOCK, "read-out: 8 slots per thread");
+    __shared__ __align__(16) uint64_t tk[CNT_SLOTS];
+    __shared__ __align__(16) uint32_t tc[CNT_SLOTS];
+    __shared__ uint32_t s_cursor, s_distinct[2];
     __shared__ ull s_tot[3];
     const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t bin = blockIdx.x;
-    const uint64_t beg = fine_off[bin], end = fine_off[bin + 1];
-    const uint64_t n = end - beg;
-    if (tid == 0) { s_cursor = 0; s_tot[0] = s_tot[1] = s_tot[2] = 0; }
-    if (n == 0) { if (tid == 0) out.surv[bin] = 0; return; }
-    const bool want_hist = out.chist != nullptr;
-    if (want_hist) for (int i = tid; i < CHIST; i += BLOCK) chist[i] = 0;
-    uint32_t R = 1;
-    if (n > 3 * CNT_SUBPASS_KEYS / 2) { while ((uint64_t)R * CNT_SUBPASS_KEYS < n) R <<= 1; }
+    for (int i = tid; i < CNT_SLOTS; i += BLOCK) { tk[i] = EMPTY; tc[i] = 0; }
+    if (tid == 0) { s_cursor = 0; s_distinct[0] = s_distinct[1] = 0; s_tot[0] = s_tot[1] = s_tot[2] = 0; }
+    __syncthreads();
     ull t_d = 0, t_s = 0, t_q = 0;
-    for (uint32_t r = 0; r < R; r++) {
-        for (int i = tid; i < CNT_SLOTS; i += BLOCK) { tk[i] = EMPTY; tc[i] = 0; }
-        __syncthreads();
-        for (uint64_t i = tid; i < n; i += BLOCK) {
-            const uint64_t h = keys[beg + i];
-            const uint64_t hh = simka::hash2(h);
-            if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
-            uint32_t slot = (uint32_t)(hh >> 40) & (CNT_SLOTS - 1);
-            int probes = 0;
-            for (;;) {
-                ull prev = atomicCAS(reinterpret_cast<ull *>(&tk[slot]), (ull)EMPTY, (ull)h);
-                if (prev == EMPTY || prev == h) { atomicAdd(&tc[slot], 1u); break; }
-                slot = (slot + 1) & (CNT_SLOTS - 1);
-                if (++probes >= CNT_SLOTS) { *out.error_flag = 1; break; }
-            }
-        }
-        __syncthreads();
-        for (int base = 0; base < CNT_SLOTS; base += BLOCK) {
-            const int slot = base + tid;
-            const uint64_t h = tk[slot];
-            const uint32_t c = tc[slot];
-            const bool keep = (h != EMPTY) && !((int64_t)c < amin || (int64_t)c > amax);
-            const uint32_t m = __ballot_sync(0xffffffffu, keep);
-            uint32_t wbase = 0;
-            if (lane == 0 && m) wbase = atomicAdd(&s_cursor, (uint32_t)__popc(m));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (keep) {
-                const uint64_t pos = beg + wbase + __popc(m & ((1u << lane) - 1));
-                out.stage_h[pos] = h;
-                out.stage_c[pos] = c;
-                t_d += 1;
-                t_s += c;
-                t_q += (ull)((double)c * (double)c);  // pow(count,2) -> u64, src/minikc/MiniKC.hpp:62
-                if (want_hist) {
-                    if (c < CHIST) atomicAdd(&chist[c], 1u);
-                    else {
-                        uint32_t q = atomicAdd(out.big_n, 1u);
-                        if (q < out.big_cap) { out.big_counts[q] = c; out.big_sample[q] = (uint32_t)sample; }
-                        else *out.error_flag = 2;
+    // keep iff amin <= c <= amax (src/minikc/MiniKC.hpp:56) with c a non-zero u32
+    const bool never = amax < 0 || amin > 0xFFFFFFFFll;
+    const uint32_t cmin = amin < 0 ? 0u : (uint32_t)amin;
+    const uint32_t cmax = amax > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)(amax < 0 ? 0 : amax);
+    uint32_t pass = 0;  // parity selects the distinct counter of the current table pass
+
+    for (uint32_t bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+        const uint64_t beg = fine_off[bin], end = fine_off[bin + 1];
+        if (end - beg >= 0xFFFFFFFFull) { if (tid == 0) { *out.error_flag = 6; out.surv[bin] = 0; } continue; }
+        const uint32_t n = (uint32_t)(end - beg);
+        if (n == 0) { if (tid == 0) out.surv[bin] = 0; continue; }
+        const uint64_t *kb = keys + beg;
+        const bool track = n > CNT_MAXDISTINCT;
+        // R sub-passes (keys selected by a second hash) only when the DISTINCT keys of the bin do not
+        // fit the table; a bin that is large because of a few heavy k-mers still takes one pass.
+        for (uint32_t R = 1;; R *= 2) {
+            if (R > 65536) { if (tid == 0) *out.error_flag = 5; break; }
+            ull b_d = 0, b_s = 0, b_q = 0;
+            bool overflow = false;
+            for (uint32_t r = 0; r < R && !overflow; r++, pass++) {
+                uint32_t *distinct = &s_distinct[pass & 1];
+                if (track) bin_insert_all<true>(tk, tc, distinct, kb, n, R, r, slot_shift);
+                else bin_insert_all<false>(tk, tc, distinct, kb, n, 1, 0, slot_shift);
+                __syncthreads();
+                overflow = track && *distinct > CNT_MAXDISTINCT;
+                if (tid == 0) s_distinct[(pass + 1) & 1] = 0;
+                // read-out + clean: thread t owns slots [8t, 8t+8)
+                uint64_t k8[8];
+                uint32_t c8[8];
+                {
+                    uint4 *pk = reinterpret_cast<uint4 *>(tk + 8 * tid);
+                    uint4 *pc = reinterpret_cast<uint4 *>(tc + 8 * tid);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint4 v = pk[q];
+                        k8[2 * q] = ((uint64_t)v.y << 32) | v.x;
+                        k8[2 * q + 1] = ((uint64_t)v.w << 32) | v.z;
+                    }
+                    const uint4 c0 = pc[0], c1 = pc[1];
+                    c8[0] = c0.x; c8[1] = c0.y; c8[2] = c0.z; c8[3] = c0.w;
+                    c8[4] = c1.x; c8[5] = c1.y; c8[6] = c1.z; c8[7] = c1.w;
+                    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) pk[q] = e;
+                    pc[0] = z; pc[1] = z;
+                }
+                uint32_t keepm = 0;
+                if (!overflow && !never) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) keepm |= (uint32_t)(c8[q] != 0 && c8[q] >= cmin && c8[q] <= cmax) << q;
+                }
+                const uint32_t nk = __popc(keepm);
+                uint32_t inc = nk;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += v;
+                }
+                uint32_t wbase = 0;
+                if (lane == 31 && inc) wbase = atomicAdd(&s_cursor, inc);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                uint64_t pos = beg + wbase + inc - nk;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (keepm & (1u << q)) {
+                        out.stage_h[pos] = k8[q];
+                        out.stage_c[pos] = c8[q];
+                        pos++;
+                        b_d += 1;
+                        b_s += c8[q];
+                        b_q += (ull)((double)c8[q] * (double)c8[q]);  // pow(count,2) -> u64, src/minikc/MiniKC.hpp:62
                     }
                 }
+                __syncthreads();
             }
+            if (!overflow) { t_d += b_d; t_s += b_s; t_q += b_q; break; }
+            if (tid == 0) s_cursor = 0;  // forget the aborted attempt (its survivors get overwritten)
+            __syncthreads();
         }
-        __syncthreads();
+        if (tid == 0) { out.surv[bin] = s_cursor; s_cursor = 0; }
+        // (s_cursor is next touched by other threads only after the next bin's first __syncthreads)
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -474,22 +542,39 @@ k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine
     }
     if (lane == 0 && t_d) { atomicAdd(&s_tot[0], t_d); atomicAdd(&s_tot[1], t_s); atomicAdd(&s_tot[2], t_q); }
     __syncthreads();
-    if (tid == 0) {
-        out.surv[bin] = s_cursor;
-        if (s_tot[0]) { atomicAdd(&out.totals[0], s_tot[0]); atomicAdd(&out.totals[1], s_tot[1]); atomicAdd(&out.totals[2], s_tot[2]); }
-    }
-    if (want_hist)
-        for (int i = tid; i < CHIST; i += BLOCK) { uint32_t c = chist[i]; if (c) atomicAdd(&out.chist[i], (ull)c); }
+    if (tid == 0 && s_tot[0]) { atomicAdd(&out.totals[0], s_tot[0]); atomicAdd(&out.totals[1], s_tot[1]); atomicAdd(&out.totals[2], s_tot[2]); }
 }
 
-// survivors staging -> exactly-sized per-sample list; one CTA per bin
+// survivors staging -> exactly-sized per-sample list; bins taken with a grid stride
 __global__ void __launch_bounds__(BLOCK)
 k_compact(const uint64_t *__restrict__ stage_h, const uint32_t *__restrict__ stage_c, const uint64_t *__restrict__ fine_off,
-          const uint64_t *__restrict__ out_off, uint64_t *__restrict__ eh, uint32_t *__restrict__ ec) {
-    const uint32_t bin = blockIdx.x;
-    const uint64_t src = fine_off[bin], dst = out_off[bin];
-    const uint32_t n = (uint32_t)(out_off[bin + 1] - dst);
-    for (uint32_t i = threadIdx.x; i < n; i += BLOCK) { eh[dst + i] = stage_h[src + i]; ec[dst + i] = stage_c[src + i]; }
+          const uint64_t *__restrict__ out_off, uint32_t nbins, uint64_t *__restrict__ eh, uint32_t *__restrict__ ec) {
+    for (uint32_t bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+        const uint64_t src = fine_off[bin], dst = out_off[bin];
+        const uint32_t n = (uint32_t)(out_off[bin + 1] - dst);
+        for (uint32_t i = threadIdx.x; i < n; i += BLOCK) { eh[dst + i] = stage_h[src + i]; ec[dst + i] = stage_c[src + i]; }
+    }
+}
+
+// per-sample abundance histogram of the solid k-mers (complex distances only): chist[c] for c < CHIST,
+// larger counts go to the (count, sample) overflow list
+__global__ void __launch_bounds__(BLOCK)
+k_abundance_hist(const uint32_t *__restrict__ ec, uint64_t n, int sample, ull *__restrict__ chist, uint32_t *__restrict__ big_counts,
+                 uint32_t *__restrict__ big_sample, uint32_t *__restrict__ big_n, uint32_t big_cap, int *__restrict__ error_flag) {
+    __shared__ uint32_t hist[CHIST];
+    for (int i = threadIdx.x; i < CHIST; i += BLOCK) hist[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * BLOCK) {
+        const uint32_t c = ec[i];
+        if (c < CHIST) atomicAdd(&hist[c], 1u);
+        else {
+            const uint32_t q = atomicAdd(big_n, 1u);
+            if (q < big_cap) { big_counts[q] = c; big_sample[q] = (uint32_t)sample; }
+            else *error_flag = 2;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CHIST; i += BLOCK) { const uint32_t c = hist[i]; if (c) atomicAdd(&chist[i], (ull)c); }
 }
 
 // off_table[fr] = out_off[fr * (nbins / FG)], fr in [0, FG]
@@ -603,6 +688,7 @@ k_merge(MergeArgs a) {
         uint32_t R = 1;
         if (n_e > MRG_CAP) { while ((uint64_t)R * (MRG_CAP / 2) < n_e) R <<= 1; }
         for (uint32_t r = 0; r < R; r++) {
+            __syncthreads();  // pair enumeration of the previous sub-pass still reads the group arrays
             for (int i = tid; i < MRG_SLOTS; i += BLOCK) { tk[i] = EMPTY; gs[i] = 0; pp[i] = 0; }
             if (tid == 0) { s_groups = 0; s_shared = 0; }
             __syncthreads();
@@ -940,6 +1026,8 @@ struct simka_ctx {
     float sample_ms = 0, merge_ms = 0;
     uint64_t kmers_in = 0, entries = 0;
     uint64_t launches = 0;
+    int nsm = 148;
+    int occ_bin_count = 0;
 
     void set_error(const std::string &s) { err = s; }
 };
@@ -956,6 +1044,7 @@ static double __attribute__((noinline)) onesided_kl_term(double c, double Nx, do
     return xi * log((2 * xY) / (xY + yX));
 }
 static int ilog2_ceil(uint64_t v) { int b = 0; while (((uint64_t)1 << b) < v) b++; return b; }
+static int ilog2_floor(uint64_t v) { int b = 0; while (b < 63 && ((uint64_t)2 << b) <= v) b++; return b; }
 
 static int reset_state(simka_ctx *ctx) {
     for (auto &s : ctx->samples) s = SampleData();
@@ -996,6 +1085,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
     ctx->kp.shard_rank = p->shard_rank;
     ctx->kp.shard_count = p->shard_count > 1 ? p->shard_count : 1;
     ctx->W = 2 * p->kmer_size;
+    cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
     ctx->samples.resize(p->nb_samples);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -1152,7 +1242,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         uint64_t want = std::max<uint64_t>(1, (per_sample / 4) * (uint64_t)ctx->prm.nb_samples / MRG_TARGET);
         int fg = ilog2_ceil(want);
         // never finer than the counting bins of a sample of the expected size (merge bins may be coarser)
-        const int bb = std::min(ilog2_ceil(std::max<uint64_t>(1, per_sample / BIN_TARGET)), 20);
+        const int bb = std::min(ilog2_floor(std::max<uint64_t>(1, per_sample / BIN_TARGET)), 20);
         fg = std::min(fg, std::min(W, bb));
         while (fg > 0 && ((size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4) > ((size_t)2 << 30)) fg--;
         ctx->fg_bits = fg;
@@ -1160,7 +1250,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         if (ctx->d_off_table.reserve(tbl)) { ctx->set_error("out of device memory (offset table)"); return SIMKA_ERR_NOMEM; }
         CK(cudaMemsetAsync(ctx->d_off_table.p, 0, tbl, st));
     }
-    int bin_bits = std::max(ilog2_ceil(std::max<uint64_t>(1, n_pos / BIN_TARGET)), ctx->fg_bits);
+    int bin_bits = std::max(ilog2_floor(std::max<uint64_t>(1, n_pos / BIN_TARGET)), ctx->fg_bits);
     bin_bits = std::min(bin_bits, std::min(W, 20));
     bin_bits = std::max(bin_bits, ctx->fg_bits);
     const int b1_bits = std::min(bin_bits, bin_bits > 16 ? 10 : 8);
@@ -1226,14 +1316,16 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         co.stage_c = ctx->d_stage_c.as<uint32_t>();
         co.surv = ctx->d_surv.as<uint32_t>();
         co.totals = d_totals;
-        co.chist = ctx->prm.complex_dist ? ctx->d_chist.as<ull>() + (size_t)sample_id * CHIST : nullptr;
-        co.big_counts = ctx->d_big_counts.as<uint32_t>();
-        co.big_sample = ctx->d_big_sample.as<uint32_t>();
-        co.big_n = d_big_n;
-        co.big_cap = ctx->big_cap;
         co.error_flag = d_error;
+        if (ctx->occ_bin_count <= 0) {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bin_count, k_bin_count, BLOCK, 0));
+            if (ctx->occ_bin_count <= 0) ctx->occ_bin_count = 1;
+        }
+        const unsigned gbin = (unsigned)std::min<uint64_t>(nbins, (uint64_t)ctx->nsm * ctx->occ_bin_count);
+        const int slot_shift = std::max(0, W - bin_bits - 11);
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
-        k_bin_count<<<nbins, BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), ctx->prm.abundance_min, ctx->prm.abundance_max, sample_id, co);
+        k_bin_count<<<gbin, BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins, slot_shift, ctx->prm.abundance_min,
+                                            ctx->prm.abundance_max, co);
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT + 1], st));
         k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins);
         ctx->launches += 9;
@@ -1252,9 +1344,15 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             sd.eh = (uint64_t *)ctx->arena.alloc(h_surv * 8);
             sd.ec = (uint32_t *)ctx->arena.alloc(h_surv * 4);
             if (!sd.eh || !sd.ec) { ctx->set_error("out of device memory (sample list)"); return SIMKA_ERR_NOMEM; }
-            k_compact<<<nbins, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(),
-                                              ctx->d_out_off.as<uint64_t>(), sd.eh, sd.ec);
+            k_compact<<<gbin, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(),
+                                             ctx->d_out_off.as<uint64_t>(), nbins, sd.eh, sd.ec);
             ctx->launches++;
+            if (ctx->prm.complex_dist) {
+                const unsigned gh = (unsigned)std::min<uint64_t>((h_surv + BLOCK * 16 - 1) / (BLOCK * 16), (uint64_t)ctx->nsm * 4);
+                k_abundance_hist<<<gh, BLOCK, 0, st>>>(sd.ec, h_surv, sample_id, ctx->d_chist.as<ull>() + (size_t)sample_id * CHIST,
+                                                      ctx->d_big_counts.as<uint32_t>(), ctx->d_big_sample.as<uint32_t>(), d_big_n, ctx->big_cap, d_error);
+                ctx->launches++;
+            }
         }
         const uint32_t fg = 1u << ctx->fg_bits;
         k_fill_offsets<<<(fg + 1 + 255) / 256, 256, 0, st>>>(ctx->d_out_off.as<uint64_t>(), sd.off, fg, nbins >> ctx->fg_bits);
@@ -1371,8 +1469,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
         a.nb_shared = ctx->a_nb_shared; a.distinct_shared = ctx->a_distinct; a.braycurtis = ctx->a_bc;
         a.chord = ctx->a_chord; a.hellinger = ctx->a_hell; a.whittaker = ctx->a_whit; a.kl = ctx->a_kl;
         a.scalars = ctx->a_scalars; a.error_flag = d_error;
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->prm.device);
+        const int nsm = ctx->nsm;
         const uint32_t MG = 1u << mg_bits;
         const unsigned grid = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * 8);
         k_merge<<<grid, BLOCK, merge_smem_bytes(N), st>>>(a);
