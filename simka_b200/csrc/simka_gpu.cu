@@ -776,6 +776,320 @@ k_merge(MergeArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K4 for N <= 32 samples: same grouping as k_merge, but the sample pairs of a bin are counting-sorted
+// by pair key (i,j) in shared memory and thread t owns pair key t for the whole kernel: all N x N
+// accumulators live in registers, no atomics on the accumulators at all (one flush per CTA at the end).
+// ---------------------------------------------------------------------------------------------
+constexpr int M32_THREADS = 512;
+constexpr int M32_SLOTS = 4096;   // table slots per pass
+constexpr int M32_ECAP = 4096;    // grouped entries held per pass
+constexpr int M32_GCAP = 2048;    // shared groups per pass (<= ECAP / 2)
+constexpr int M32_PCAP = 2048;    // sample pairs sorted per chunk
+constexpr int M32_PPT = M32_PCAP / M32_THREADS;
+constexpr uint32_t M32_SKIP = 0xFFFFFFFFu;
+
+struct M32Smem {
+    uint64_t tk[M32_SLOTS];
+    uint2 sp[M32_PCAP];            // (count of the lower sample, count of the higher sample), sorted by pair key
+    uint32_t gcnt[M32_SLOTS];      // group size -> fill cursor (end, counting down to start) / M32_SKIP
+    uint32_t cg[M32_GCAP];         // compact list of shared groups: start | size << 16
+    uint32_t cgp[M32_GCAP + 1];    // exclusive pair prefix over cg
+    uint32_t ge_c[M32_ECAP];       // grouped counts
+    uint32_t kh[M32_THREADS + 1];  // per pair key: histogram -> start
+    uint32_t kcur[M32_THREADS];    // per pair key: fill cursor -> end
+    uint32_t s_start[32], s_pre[33];
+    unsigned long long scan_tmp[M32_THREADS / 32 + 1];
+    uint16_t lut[1024];            // (i*32+j) -> pair key
+    uint8_t ge_s[M32_ECAP];        // grouped sample ids
+};
+
+__device__ __forceinline__ unsigned long long block_scan_u64(unsigned long long v, unsigned long long *tmp, unsigned long long *total) {
+    // exclusive scan over the M32_THREADS threads of the block; tmp has M32_THREADS/32+1 entries
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    __syncthreads();  // tmp may still be read from a previous scan
+    if (lane == 31) tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long w = lane < M32_THREADS / 32 ? tmp[lane] : 0, winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += u;
+        }
+        if (lane < M32_THREADS / 32) tmp[lane] = winc - w;
+        if (lane == M32_THREADS / 32 - 1) tmp[M32_THREADS / 32] = winc;
+    }
+    __syncthreads();
+    *total = tmp[M32_THREADS / 32];
+    return tmp[wid] + inc - v;
+}
+
+template <bool SIMPLE, bool COMPLEX>
+__global__ void __launch_bounds__(M32_THREADS, 1)
+k_merge32(MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    M32Smem &S = *reinterpret_cast<M32Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = a.n;
+    const int NP = N * (N - 1) / 2;
+    const uint32_t MG = 1u << a.mg_bits;
+    const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
+    const size_t ostride = ((size_t)1 << a.fg_bits) + 1;
+
+    for (int idx = tid; idx < 1024; idx += M32_THREADS) {
+        const int i = idx >> 5, j = idx & 31;
+        S.lut[idx] = (i < j && j < N) ? (uint16_t)(i * (2 * N - i - 1) / 2 + (j - i - 1)) : (uint16_t)0;
+    }
+    S.kh[tid] = 0;
+    if (tid == 0) S.kh[M32_THREADS] = 0;
+    // the pair key this thread owns
+    int my_i = 0, my_j = 0;
+    if (tid < NP) {
+        int i = 0;
+        while ((i + 1) * (2 * N - (i + 1) - 1) / 2 <= tid) i++;
+        my_i = i;
+        my_j = i + 1 + (tid - i * (2 * N - i - 1) / 2);
+    }
+    const double Ni = a.ntot[my_i], Nj = a.ntot[my_j];
+    ull r_sh_ij = 0, r_sh_ji = 0, r_dist = 0, r_bc = 0, r_chord = 0, r_hell = 0, r_whit = 0;
+    double r_kl = 0.0;
+    ull loc_groups = 0, loc_shared = 0, loc_pairs = 0;
+    __syncthreads();
+
+    for (uint32_t mb = blockIdx.x; mb < MG; mb += gridDim.x) {
+        if (tid < 32) {
+            uint32_t len = 0;
+            if (tid < N) {
+                const uint32_t b0 = a.off[(size_t)tid * ostride + (size_t)mb * q];
+                const uint32_t b1 = a.off[(size_t)tid * ostride + (size_t)(mb + 1) * q];
+                S.s_start[tid] = b0;
+                len = b1 - b0;
+            }
+            uint32_t inc = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += u;
+            }
+            S.s_pre[tid] = inc - len;
+            if (tid == 31) S.s_pre[32] = inc;
+        }
+        __syncthreads();
+        const uint32_t n_e = S.s_pre[32];
+        if (n_e == 0) { __syncthreads(); continue; }
+        uint32_t R = 1;
+        if (n_e > M32_ECAP) { while ((uint64_t)R * (M32_ECAP / 2) < n_e) R <<= 1; }
+        for (uint32_t r = 0; r < R; r++) {
+            {   // clean table
+                uint4 *pk = reinterpret_cast<uint4 *>(S.tk) + tid;
+                const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int qq = 0; qq < M32_SLOTS * 8 / 16 / M32_THREADS; qq++) pk[qq * M32_THREADS] = e;
+                uint4 *pg = reinterpret_cast<uint4 *>(S.gcnt) + tid;
+#pragma unroll
+                for (int qq = 0; qq < M32_SLOTS * 4 / 16 / M32_THREADS; qq++) pg[qq * M32_THREADS] = z;
+            }
+            __syncthreads();
+            // phase 1: insert keys, count group sizes
+            for (uint32_t i = tid; i < n_e; i += M32_THREADS) {
+                int lo = 0, hi = 32;  // s_pre[lo] <= i < s_pre[hi]   (s_pre[N..32] = n_e)
+#pragma unroll
+                for (int st = 0; st < 5; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const uint64_t h = a.eh[lo][S.s_start[lo] + (i - S.s_pre[lo])];
+                const uint64_t hh = simka::hash2(h);
+                if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (M32_SLOTS - 1);
+                volatile uint64_t *vk = S.tk;
+                int probes = 0;
+                for (;;) {
+                    uint64_t cur = vk[slot];
+                    if (cur == EMPTY) {
+                        cur = atomicCAS(reinterpret_cast<ull *>(&S.tk[slot]), (ull)EMPTY, (ull)h);
+                        if (cur == EMPTY) cur = h;
+                    }
+                    if (cur == h) { atomicAdd(&S.gcnt[slot], 1u); break; }
+                    slot = (slot + 1) & (M32_SLOTS - 1);
+                    if (++probes >= M32_SLOTS) { *a.error_flag = 3; break; }
+                }
+            }
+            __syncthreads();
+            // phase 2: group statistics + compact list of the shared groups (>= 2 samples)
+            unsigned long long packed = 0;  // groups (16 bits) | entries (16 bits) | pairs (32 bits)
+            uint32_t g8[M32_SLOTS / M32_THREADS];
+#pragma unroll
+            for (int qq = 0; qq < M32_SLOTS / M32_THREADS; qq++) {
+                const uint32_t g = S.gcnt[tid * (M32_SLOTS / M32_THREADS) + qq];
+                g8[qq] = g;
+                loc_groups += g > 0;
+                if (g > 1) packed += 1ull | ((unsigned long long)g << 16) | ((unsigned long long)(g * (g - 1) / 2) << 32);
+            }
+            unsigned long long total;
+            unsigned long long ex = block_scan_u64(packed, S.scan_tmp, &total);
+            const uint32_t n_groups = (uint32_t)(total & 0xFFFF), n_sub = (uint32_t)((total >> 16) & 0xFFFF);
+            const uint32_t P = (uint32_t)(total >> 32);
+            if ((total & 0xFFFF) != 0 && (n_groups > M32_GCAP || n_sub > M32_ECAP)) {  // cannot happen for hashed keys; reported, not silent
+                if (tid == 0) *a.error_flag = 4;
+                __syncthreads();
+                continue;
+            }
+#pragma unroll
+            for (int qq = 0; qq < M32_SLOTS / M32_THREADS; qq++) {
+                const uint32_t g = g8[qq];
+                uint32_t v = M32_SKIP;
+                if (g > 1) {
+                    const uint32_t gi = (uint32_t)(ex & 0xFFFF), st = (uint32_t)((ex >> 16) & 0xFFFF), pp = (uint32_t)(ex >> 32);
+                    S.cg[gi] = st | (g << 16);
+                    S.cgp[gi] = pp;
+                    v = st + g;  // fill cursor counts down from the end
+                    ex += 1ull | ((unsigned long long)g << 16) | ((unsigned long long)(g * (g - 1) / 2) << 32);
+                    loc_shared++;
+                }
+                S.gcnt[tid * (M32_SLOTS / M32_THREADS) + qq] = v;
+            }
+            if (tid == 0) { S.cgp[n_groups] = P; loc_pairs += P; }
+            __syncthreads();
+            if (n_groups == 0) continue;  // nothing shared in this pass: no accumulator changes
+            // phase 3: scatter the entries of shared k-mers into their groups
+            for (uint32_t i = tid; i < n_e; i += M32_THREADS) {
+                int lo = 0, hi = 32;
+#pragma unroll
+                for (int st = 0; st < 5; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const size_t idx = S.s_start[lo] + (i - S.s_pre[lo]);
+                const uint64_t h = a.eh[lo][idx];
+                const uint64_t hh = simka::hash2(h);
+                if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (M32_SLOTS - 1);
+                while (S.tk[slot] != h) slot = (slot + 1) & (M32_SLOTS - 1);
+                if (S.gcnt[slot] == M32_SKIP) continue;  // private k-mer: contributes to no pair
+                const uint32_t pos = atomicSub(&S.gcnt[slot], 1u) - 1;
+                S.ge_s[pos] = (uint8_t)lo;
+                S.ge_c[pos] = a.ec[lo][idx];
+            }
+            __syncthreads();
+            // phase 4: pairs, in chunks: counting sort by pair key, then every thread consumes its own key
+            for (uint32_t c0 = 0; c0 < P; c0 += M32_PCAP) {
+                const uint32_t c1 = min(P, c0 + M32_PCAP);
+                const uint32_t per = (c1 - c0 + M32_THREADS - 1) / M32_THREADS;
+                uint32_t l0 = c0 + tid * per, l1 = min(l0 + per, c1);
+                uint16_t pkey[M32_PPT];
+                uint32_t pa[M32_PPT], pb[M32_PPT];
+                int np = 0;
+                if (l0 < l1) {
+                    int lo = 0, hi = (int)n_groups;  // cgp[lo] <= l0 < cgp[hi]
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cgp[mid] <= l0) lo = mid; else hi = mid; }
+                    uint32_t g = (uint32_t)lo;
+                    uint32_t cgv = S.cg[g];
+                    uint32_t st = cgv & 0xFFFF, sz = cgv >> 16;
+                    const uint32_t l = l0 - S.cgp[g];
+                    // row-major strict upper triangle of sz x sz: row x starts at x(2 sz - x - 1)/2
+                    const float tg = 2.0f * (float)sz - 1.0f;
+                    int x = (int)((tg - sqrtf(tg * tg - 8.0f * (float)l)) * 0.5f);
+                    if (x < 0) x = 0;
+                    while ((uint32_t)(x + 1) * (2 * sz - (x + 1) - 1) / 2 <= l) x++;
+                    while ((uint32_t)x * (2 * sz - x - 1) / 2 > l) x--;
+                    uint32_t y = x + 1 + (l - (uint32_t)x * (2 * sz - x - 1) / 2);
+                    uint32_t sx = S.ge_s[st + x], cx = S.ge_c[st + x];
+#pragma unroll
+                    for (int k = 0; k < M32_PPT; k++) {
+                        if (l0 + k < l1) {
+                            const uint32_t sy = S.ge_s[st + y], cy = S.ge_c[st + y];
+                            const bool sw = sx > sy;
+                            pkey[k] = S.lut[sw ? (sy * 32 + sx) : (sx * 32 + sy)];
+                            pa[k] = sw ? cy : cx;
+                            pb[k] = sw ? cx : cy;
+                            atomicAdd(&S.kh[pkey[k]], 1u);
+                            np = k + 1;
+                            // advance
+                            if (++y == sz) {
+                                if (++x == (int)sz - 1) {
+                                    g++;
+                                    if (g < n_groups) { cgv = S.cg[g]; st = cgv & 0xFFFF; sz = cgv >> 16; }
+                                    x = 0;
+                                }
+                                y = x + 1;
+                                if (g < n_groups) { sx = S.ge_s[st + x]; cx = S.ge_c[st + x]; }
+                            }
+                        }
+                    }
+                }
+                // histogram -> start offsets
+                unsigned long long tot2;
+                __syncthreads();
+                const uint32_t myh = S.kh[tid];
+                const uint32_t exk = (uint32_t)block_scan_u64((unsigned long long)myh, S.scan_tmp, &tot2);
+                S.kh[tid] = exk;
+                S.kcur[tid] = exk;
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < M32_PPT; k++) {
+                    if (k < np) {
+                        const uint32_t pos = atomicAdd(&S.kcur[pkey[k]], 1u);
+                        S.sp[pos] = make_uint2(pa[k], pb[k]);
+                    }
+                }
+                __syncthreads();
+                if (tid < NP) {
+                    const uint32_t pbeg = S.kh[tid], pend = S.kcur[tid];
+                    for (uint32_t pos = pbeg; pos < pend; pos++) {
+                        const uint2 cc = S.sp[pos];
+                        const uint32_t ci = cc.x, cj = cc.y;
+                        r_sh_ij += ci;
+                        r_sh_ji += cj;
+                        r_dist += 1;
+                        r_bc += ci < cj ? ci : cj;
+                        if (SIMPLE) {
+                            const ull prod = (ull)ci * (ull)cj;
+                            r_chord += prod;
+                            r_hell += (ull)sqrt((double)prod);  // u64 += double truncates per increment
+                        }
+                        if (COMPLEX) {
+                            const double ai = (double)ci, aj = (double)cj;
+                            const double yX = aj * Ni, xY = ai * Nj;
+                            const double r1 = (2 * xY) / (xY + yX), r2 = (2 * yX) / (xY + yX);
+                            r_kl += (ai / Ni) * log(r1) + (aj / Nj) * log(r2);
+                            const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
+                            r_whit += (ull)(absint32_ext(wx - wy) - absint32_ext(wx) - absint32_ext(wy));
+                        }
+                    }
+                }
+                S.kh[tid] = 0;
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+    // flush: one set of global atomics per CTA and pair key
+    if (tid < NP && r_dist) {
+        const size_t n = (size_t)N;
+        const size_t ij = (size_t)my_i * n + my_j, ji = (size_t)my_j * n + my_i;
+        const size_t sym = (size_t)my_j + (n - 1) * my_i - ((size_t)my_i * (my_i - 1) / 2);
+        atomicAdd(&a.nb_shared[ij], r_sh_ij);
+        atomicAdd(&a.nb_shared[ji], r_sh_ji);
+        atomicAdd(&a.distinct_shared[sym], r_dist);
+        atomicAdd(&a.braycurtis[sym], r_bc);
+        if (SIMPLE) { atomicAdd(&a.chord[ij], r_chord); atomicAdd(&a.hellinger[ij], r_hell); }
+        if (COMPLEX) { atomicAdd(&a.whittaker[ij], r_whit); atomicAdd(&a.kl[ij], r_kl); }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        loc_groups += __shfl_down_sync(0xffffffffu, loc_groups, d);
+        loc_shared += __shfl_down_sync(0xffffffffu, loc_shared, d);
+        loc_pairs += __shfl_down_sync(0xffffffffu, loc_pairs, d);
+    }
+    if (lane == 0 && (loc_groups | loc_shared | loc_pairs)) {
+        atomicAdd(&a.scalars[0], loc_groups);
+        atomicAdd(&a.scalars[1], loc_shared);
+        atomicAdd(&a.scalars[2], loc_pairs);
+    }
+}
+
 // T[i][j] = sum over solid k-mers e of sample i of f((u64)(c_e * N_j)), f = abs((int)x): the value the
 // reference's Whittaker update adds for a k-mer present in i and absent from j
 // (src/core/SimkaAlgorithm.hpp:481,512).  Computed from the abundance histogram of sample i.
@@ -1472,7 +1786,17 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
         const int nsm = ctx->nsm;
         const uint32_t MG = 1u << mg_bits;
         const unsigned grid = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * 8);
-        k_merge<<<grid, BLOCK, merge_smem_bytes(N), st>>>(a);
+        if (N <= 32) {
+            void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge32<true, true> : k_merge32<true, false>)
+                                               : (a.complex_ ? k_merge32<false, true> : k_merge32<false, false>);
+            int occ = 0;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(M32Smem)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, M32_THREADS, sizeof(M32Smem)));
+            const unsigned g32 = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * std::max(1, occ));
+            kern<<<g32, M32_THREADS, sizeof(M32Smem), st>>>(a);
+        } else {
+            k_merge<<<grid, BLOCK, merge_smem_bytes(N), st>>>(a);
+        }
         ctx->launches++;
         if (ctx->prm.complex_dist) {
             big_n = std::min(big_n, ctx->big_cap);
