@@ -609,6 +609,7 @@ struct MergeArgs {
     const uint32_t *const *ec;   // [n] per-sample counts
     const uint32_t *off;         // [n][FG+1]
     const double *ntot;          // [n] global solid k-mer totals N_i as double
+    const double2 *logtab;       // [128] tab_log table
     int simple, complex_;
     ull *nb_shared, *distinct_shared, *braycurtis, *chord, *hellinger, *whittaker;
     double *kl;
@@ -776,6 +777,38 @@ k_merge(MergeArgs a) {
     }
 }
 
+// log(x) for normal x > 0 from a 128-entry table {1/c, log c} (interval centres c over [0.6875, 1.375), the two
+// intervals around 1 use c = 1 so that the result keeps its RELATIVE accuracy near x = 1 and log(1) == 0):
+// log x = k ln2 + log c + log1p(r), r = x/c - 1, |r| < 2^-7, degree-6 series.  |error| < 4e-14 relative
+// (checked against logl over 2e7 points); used for the Jensen-Shannon terms whose sum is compared at 1e-10.
+__device__ __forceinline__ double tab_log(double x, const double2 *T) {
+    const unsigned long long OFF = 0x3fe6000000000000ull;
+    const unsigned long long ix = (unsigned long long)__double_as_longlong(x);
+    const unsigned long long tmp = ix - OFF;
+    const int i = (int)(tmp >> 45) & 127;
+    const int k = (int)((long long)tmp >> 52);
+    const double z = __longlong_as_double((long long)(ix - (tmp & (0xfffull << 52))));
+    const double2 t = T[i];
+    const double r = fma(z, t.x, -1.0);
+    const double w = fma((double)k, 0.693147180559945309417232121458, t.y);
+    double p = fma(r, -1.0 / 6, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3);
+    p = fma(r, p, -0.5);
+    return w + fma(r * r, p, r);
+}
+
+// (u64)sqrt((double)prod): what the reference's u64 Hellinger accumulator gains per k-mer
+// (src/core/SimkaAlgorithm.hpp:395).  Below 2^32 the exact integer square root is the same value.
+__device__ __forceinline__ ull hellinger_term(ull prod) {
+    if (prod >> 32) return (ull)sqrt((double)prod);
+    const uint32_t p = (uint32_t)prod;
+    ull s = (ull)sqrtf((float)p);
+    if (s * s > p) s--;
+    else if ((s + 1) * (s + 1) <= p) s++;
+    return s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4 for N <= 32 samples: same grouping as k_merge, but the sample pairs of a bin are counting-sorted
 // by pair key (i,j) in shared memory and thread t owns pair key t for the whole kernel: all N x N
@@ -800,6 +833,7 @@ struct M32Smem {
     uint32_t kcur[M32_THREADS];    // per pair key: fill cursor -> end
     uint32_t s_start[32], s_pre[33];
     unsigned long long scan_tmp[M32_THREADS / 32 + 1];
+    double2 logtab[128];           // tab_log table
     uint16_t lut[1024];            // (i*32+j) -> pair key
     uint8_t ge_s[M32_ECAP];        // grouped sample ids
 };
@@ -849,6 +883,7 @@ k_merge32(MergeArgs a) {
     }
     S.kh[tid] = 0;
     if (tid == 0) S.kh[M32_THREADS] = 0;
+    if (tid < 128) S.logtab[tid] = a.logtab[tid];
     // the pair key this thread owns
     int my_i = 0, my_j = 0;
     if (tid < NP) {
@@ -858,6 +893,7 @@ k_merge32(MergeArgs a) {
         my_j = i + 1 + (tid - i * (2 * N - i - 1) / 2);
     }
     const double Ni = a.ntot[my_i], Nj = a.ntot[my_j];
+    const double invNi = 1.0 / Ni, invNj = 1.0 / Nj;
     ull r_sh_ij = 0, r_sh_ji = 0, r_dist = 0, r_bc = 0, r_chord = 0, r_hell = 0, r_whit = 0;
     double r_kl = 0.0;
     ull loc_groups = 0, loc_shared = 0, loc_pairs = 0;
@@ -1047,13 +1083,17 @@ k_merge32(MergeArgs a) {
                         if (SIMPLE) {
                             const ull prod = (ull)ci * (ull)cj;
                             r_chord += prod;
-                            r_hell += (ull)sqrt((double)prod);  // u64 += double truncates per increment
+                            r_hell += hellinger_term(prod);  // u64 += double truncates per increment
                         }
                         if (COMPLEX) {
                             const double ai = (double)ci, aj = (double)cj;
                             const double yX = aj * Ni, xY = ai * Nj;
-                            const double r1 = (2 * xY) / (xY + yX), r2 = (2 * yX) / (xY + yX);
-                            r_kl += (ai / Ni) * log(r1) + (aj / Nj) * log(r2);
+                            if (xY != yX) {  // equal: both logs are log(1) = 0 exactly
+                                // r1 = 2 xY / S, r2 = 2 yX / S = 2 - r1 (absolute error eps; harmless: the term it
+                                // feeds is weighted by aj/Nj ~ r2)
+                                const double r1 = (2 * xY) * __drcp_rn(xY + yX);
+                                r_kl += (ai * invNi) * tab_log(r1, S.logtab) + (aj * invNj) * tab_log(2.0 - r1, S.logtab);
+                            }
                             const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
                             r_whit += (ull)(absint32_ext(wx - wy) - absint32_ext(wx) - absint32_ext(wy));
                         }
@@ -1335,7 +1375,7 @@ struct simka_ctx {
     size_t acc_bytes = 0;
     ull *a_nb_shared = nullptr, *a_distinct = nullptr, *a_bc = nullptr, *a_chord = nullptr, *a_hell = nullptr, *a_whit = nullptr, *a_T = nullptr, *a_scalars = nullptr;
     double *a_kl = nullptr, *a_ntot = nullptr;
-    DevBuf d_ptrs;
+    DevBuf d_ptrs, d_logtab;
     float stage_ms[T_NSTAGE] = {};
     float sample_ms = 0, merge_ms = 0;
     uint64_t kmers_in = 0, entries = 0;
@@ -1411,6 +1451,19 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
                                     (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(p->nb_samples)) == cudaSuccess;
     ok = ok && ctx->d_small.reserve(64) == 0;
+    if (ok) {  // tab_log table
+        double tab[128][2];
+        const uint64_t OFF = 0x3fe6000000000000ull;
+        for (int i = 0; i < 128; i++) {
+            uint64_t ulo = OFF + ((uint64_t)i << 45), uhi = OFF + ((uint64_t)(i + 1) << 45);
+            double lo, hi;
+            memcpy(&lo, &ulo, 8); memcpy(&hi, &uhi, 8);
+            const double c = 0.5 * (lo + hi);
+            if (i == 79 || i == 80) { tab[i][0] = 1.0; tab[i][1] = 0.0; }
+            else { tab[i][0] = 1.0 / c; tab[i][1] = (double)(-logl((long double)tab[i][0])); }
+        }
+        ok = ctx->d_logtab.reserve(sizeof tab) == 0 && cudaMemcpy(ctx->d_logtab.p, tab, sizeof tab, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (ok && p->complex_dist)
         ok = ctx->d_chist.reserve((size_t)p->nb_samples * CHIST * 8) == 0 && ctx->d_big_counts.reserve((size_t)ctx->big_cap * 4) == 0 &&
              ctx->d_big_sample.reserve((size_t)ctx->big_cap * 4) == 0;
@@ -1437,7 +1490,7 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
                       &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
                       &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
-                      &ctx->d_small, &ctx->d_off_table, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs};
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
@@ -1779,6 +1832,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
         a.ec = reinterpret_cast<const uint32_t *const *>(ctx->d_ptrs.as<const void *>() + N);
         a.off = ctx->d_off_table.as<uint32_t>();
         a.ntot = ctx->a_ntot;
+        a.logtab = ctx->d_logtab.as<double2>();
         a.simple = ctx->prm.simple_dist; a.complex_ = ctx->prm.complex_dist;
         a.nb_shared = ctx->a_nb_shared; a.distinct_shared = ctx->a_distinct; a.braycurtis = ctx->a_bc;
         a.chord = ctx->a_chord; a.hellinger = ctx->a_hell; a.whittaker = ctx->a_whit; a.kl = ctx->a_kl;
