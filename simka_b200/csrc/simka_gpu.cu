@@ -803,9 +803,10 @@ __device__ __forceinline__ double tab_log(double x, const double2 *T) {
 __device__ __forceinline__ ull hellinger_term(ull prod) {
     if (prod >> 32) return (ull)sqrt((double)prod);
     const uint32_t p = (uint32_t)prod;
-    ull s = (ull)sqrtf((float)p);
+    const float pf = (float)p;
+    uint32_t s = min((uint32_t)(pf * rsqrtf(pf)), 65535u);  // within +-1 of the root (prod >= 1)
     if (s * s > p) s--;
-    else if ((s + 1) * (s + 1) <= p) s++;
+    else if (s < 65535u && (s + 1) * (s + 1) <= p) s++;
     return s;
 }
 
@@ -866,7 +867,7 @@ __device__ __forceinline__ unsigned long long block_scan_u64(unsigned long long 
 }
 
 template <bool SIMPLE, bool COMPLEX>
-__global__ void __launch_bounds__(M32_THREADS, 1)
+__global__ void __launch_bounds__(M32_THREADS, 2)
 k_merge32(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     M32Smem &S = *reinterpret_cast<M32Smem *>(smem_raw);
