@@ -147,6 +147,7 @@ typedef struct {
     uint64_t distinct_kmers;                    /* distinct solid k-mers over all samples                     */
     uint64_t pairs;                             /* sample pairs enumerated by the accumulate kernel           */
     uint64_t kernel_launches;
+    uint64_t exact_retries;                     /* samples redone with the exact two-pass K1 (a bucket overflowed)  */
 } simka_timings;
 int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out);
 /* the CUDA stream all of this context's kernels run on (for external CUDA-event timing) */

@@ -164,7 +164,7 @@ template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(BLOCK, 2)
 k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t n_words, KParams kp, int b1_bits,
           uint32_t *__restrict__ g_hist, const uint64_t *__restrict__ bucket_base, uint32_t *__restrict__ bucket_cursor,
-          uint64_t *__restrict__ keys_out) {
+          uint64_t bucket_cap, int *__restrict__ overflow_flag, uint64_t *__restrict__ keys_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);           // [MAX_B] counts, then tile-local starts
     uint32_t *gbase = hist + MAX_B;                                    // [MAX_B] reserved global offsets
@@ -224,7 +224,11 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
     for (int i = tid; i < nb; i += BLOCK) {
         uint32_t c = hist[i];
         cnt[i] = c;
-        gbase[i] = c ? atomicAdd(&bucket_cursor[i], c) : 0;
+        uint32_t g = c ? atomicAdd(&bucket_cursor[i], c) : 0;
+        // optimistic single pass: buckets have a fixed capacity; a tile that does not fit drops its keys of
+        // that bucket and raises the flag (the host then redoes the sample with the exact two-pass path)
+        if (c && (uint64_t)g + c > bucket_cap) { g = 0xFFFFFFFFu; *overflow_flag = 1; }
+        gbase[i] = g;
     }
     __syncthreads();
     block_exclusive_scan(hist, nb, warp_tmp);
@@ -240,8 +244,15 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
     for (uint32_t i = tid; i < total; i += BLOCK) {
         uint64_t h = sorted[i];
         uint32_t b = (uint32_t)(h >> bshift);
-        keys_out[bucket_base[b] + gbase[b] + (i - hist[b])] = h;
+        const uint32_t g = gbase[b];
+        if (g != 0xFFFFFFFFu) keys_out[bucket_base[b] + g + (i - hist[b])] = h;
     }
+}
+
+// bucket b of the optimistic single-pass layout starts at b * cap
+__global__ void k_fill_bases(uint64_t *__restrict__ base, int n, uint64_t cap) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) base[i] = (uint64_t)i * cap;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -304,6 +315,69 @@ __global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t *__restric
     if (tid == 0) out[n] = carry;
 }
 
+// Multi-block version for the large scans (fine-bin histogram, survivors): block b scans 16384 elements and
+// takes its exclusive prefix from block b-1 through a chained (epoch | running total) word.  All blocks are
+// co-resident (grid <= 128), so the spin of thread 0 cannot starve its predecessor.
+constexpr int SCAN_CHUNK = 1024 * 16;
+__global__ void __launch_bounds__(1024) k_scan_chain(const uint32_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
+                                                     unsigned long long *chain, unsigned long long epoch) {
+    __shared__ uint64_t warp_sum[33];
+    __shared__ uint64_t s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t i0 = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)tid * 16;
+    uint32_t x[16];
+    if (i0 + 16 <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 t4 = *reinterpret_cast<const uint4 *>(in + i0 + 4 * q);
+            x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) x[q] = (i0 + q < n) ? in[i0 + q] : 0;
+    }
+    uint64_t v = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) v += x[q];
+    uint64_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    if (lane == 31) warp_sum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = warp_sum[lane], winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += u;
+        }
+        warp_sum[lane] = winc - w;
+        if (lane == 31) {
+            const uint64_t total = winc;
+            uint64_t prefix = 0;
+            if (blockIdx.x > 0) {
+                volatile unsigned long long *c = chain + (blockIdx.x - 1);
+                unsigned long long pv = *c;
+                while ((pv >> 40) != epoch) pv = *c;
+                prefix = pv & ((1ull << 40) - 1);
+            }
+            *((volatile unsigned long long *)(chain + blockIdx.x)) = (epoch << 40) | (prefix + total);
+            s_prefix = prefix;
+            if (blockIdx.x == gridDim.x - 1) out[n] = prefix + total;
+        }
+    }
+    __syncthreads();
+    uint64_t run = s_prefix + warp_sum[wid] + inc - v;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        if (i0 + q < n) out[i0 + q] = run;
+        run += x[q];
+    }
+}
+
 // tiles[b] = ceil(count[b] / tile)
 __global__ void k_tiles_per_bucket(const uint32_t *__restrict__ count, uint32_t *__restrict__ tiles, int n, int tile) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -317,8 +391,8 @@ __global__ void k_tiles_per_bucket(const uint32_t *__restrict__ count, uint32_t 
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(BLOCK)
-k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ bucket_base /*[B1+1]*/,
-             const uint64_t *__restrict__ tile_start /*[B1+1]*/, int b1_bits, int b2_bits, int W,
+k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ bucket_base /*[B1] begin*/,
+             const uint32_t *__restrict__ bucket_cnt /*[B1]*/, const uint64_t *__restrict__ tile_start /*[B1+1]*/, int b1_bits, int b2_bits, int W,
              uint32_t *__restrict__ fine_hist, const uint64_t *__restrict__ fine_off, uint32_t *__restrict__ fine_cursor,
              uint64_t *__restrict__ keys_out) {
     __shared__ uint32_t hist[MAX_B], gbase[MAX_B], warp_tmp[16];
@@ -339,7 +413,7 @@ k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ 
     __syncthreads();
     const int b1 = s_bucket;
     if (b1 < 0) return;
-    const uint64_t bbeg = bucket_base[b1], bend = bucket_base[b1 + 1];
+    const uint64_t bbeg = bucket_base[b1], bend = bbeg + bucket_cnt[b1];
     const uint64_t tbeg = bbeg + (blockIdx.x - tile_start[b1]) * (uint64_t)L2_TILE;
     const int shift = W - b1_bits - b2_bits;
     const uint32_t m2 = (uint32_t)nb2 - 1;
@@ -545,14 +619,16 @@ k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine
     if (tid == 0 && s_tot[0]) { atomicAdd(&out.totals[0], s_tot[0]); atomicAdd(&out.totals[1], s_tot[1]); atomicAdd(&out.totals[2], s_tot[2]); }
 }
 
-// survivors staging -> exactly-sized per-sample list; bins taken with a grid stride
+// survivors staging -> exactly-sized per-sample list; one warp per bin, bins taken with a grid stride
 __global__ void __launch_bounds__(BLOCK)
 k_compact(const uint64_t *__restrict__ stage_h, const uint32_t *__restrict__ stage_c, const uint64_t *__restrict__ fine_off,
           const uint64_t *__restrict__ out_off, uint32_t nbins, uint64_t *__restrict__ eh, uint32_t *__restrict__ ec) {
-    for (uint32_t bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nw = gridDim.x * (BLOCK / 32);
+    for (uint32_t bin = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); bin < nbins; bin += nw) {
         const uint64_t src = fine_off[bin], dst = out_off[bin];
         const uint32_t n = (uint32_t)(out_off[bin + 1] - dst);
-        for (uint32_t i = threadIdx.x; i < n; i += BLOCK) { eh[dst + i] = stage_h[src + i]; ec[dst + i] = stage_c[src + i]; }
+        for (uint32_t i = lane; i < n; i += 32) { eh[dst + i] = stage_h[src + i]; ec[dst + i] = stage_c[src + i]; }
     }
 }
 
@@ -1376,7 +1452,10 @@ struct simka_ctx {
     size_t acc_bytes = 0;
     ull *a_nb_shared = nullptr, *a_distinct = nullptr, *a_bc = nullptr, *a_chord = nullptr, *a_hell = nullptr, *a_whit = nullptr, *a_T = nullptr, *a_scalars = nullptr;
     double *a_kl = nullptr, *a_ntot = nullptr;
-    DevBuf d_ptrs, d_logtab;
+    DevBuf d_ptrs, d_logtab, d_chain;
+    unsigned long long scan_epoch = 0;
+    bool force_exact = false;   // SIMKA_B200_EXACT_COUNT=1: always run the K1 count pass (tests of the fallback)
+    uint64_t exact_retries = 0;
     float stage_ms[T_NSTAGE] = {};
     float sample_ms = 0, merge_ms = 0;
     uint64_t kmers_in = 0, entries = 0;
@@ -1400,6 +1479,16 @@ static double __attribute__((noinline)) onesided_kl_term(double c, double Nx, do
 }
 static int ilog2_ceil(uint64_t v) { int b = 0; while (((uint64_t)1 << b) < v) b++; return b; }
 static int ilog2_floor(uint64_t v) { int b = 0; while (b < 63 && ((uint64_t)2 << b) <= v) b++; return b; }
+
+// exclusive scan u32[n] -> u64[n+1] on the context's stream
+static void launch_scan(simka_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n) {
+    if (n <= (uint64_t)SCAN_CHUNK) { k_scan_u32_u64<<<1, 1024, 0, ctx->stream>>>(in, out, n); return; }
+    const unsigned grid = (unsigned)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    if (grid > 128) { k_scan_u32_u64<<<1, 1024, 0, ctx->stream>>>(in, out, n); return; }  // co-residency bound of the chained version
+    ctx->scan_epoch = (ctx->scan_epoch + 1) & 0xFFFFFFull;
+    if (ctx->scan_epoch == 0) { cudaMemsetAsync(ctx->d_chain.p, 0, 128 * 8, ctx->stream); ctx->scan_epoch = 1; }
+    k_scan_chain<<<grid, 1024, 0, ctx->stream>>>(in, out, n, ctx->d_chain.as<unsigned long long>(), ctx->scan_epoch);
+}
 
 static int reset_state(simka_ctx *ctx) {
     for (auto &s : ctx->samples) s = SampleData();
@@ -1440,6 +1529,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
     ctx->kp.shard_rank = p->shard_rank;
     ctx->kp.shard_count = p->shard_count > 1 ? p->shard_count : 1;
     ctx->W = 2 * p->kmer_size;
+    { const char *e = getenv("SIMKA_B200_EXACT_COUNT"); ctx->force_exact = e && e[0] == '1'; }
     cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
     ctx->samples.resize(p->nb_samples);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1452,6 +1542,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
                                     (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(p->nb_samples)) == cudaSuccess;
     ok = ok && ctx->d_small.reserve(64) == 0;
+    ok = ok && ctx->d_chain.reserve(128 * 8) == 0 && cudaMemset(ctx->d_chain.p, 0, 128 * 8) == cudaSuccess;
     if (ok) {  // tab_log table
         double tab[128][2];
         const uint64_t OFF = 0x3fe6000000000000ull;
@@ -1491,7 +1582,7 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
                       &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
                       &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
-                      &ctx->d_small, &ctx->d_off_table, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab};
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
@@ -1631,6 +1722,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
     ull *d_totals = ctx->d_small.as<ull>();  // [0..2]
     int *d_error = reinterpret_cast<int *>(ctx->d_small.as<char>() + 32);
     uint32_t *d_big_n = reinterpret_cast<uint32_t *>(ctx->d_small.as<char>() + 40);
+    int *d_overflow = reinterpret_cast<int *>(ctx->d_small.as<char>() + 44);
     uint64_t h_keys = 0, h_surv = 0;
     ull h_tot[3] = {0, 0, 0};
 
@@ -1645,7 +1737,15 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         CK(cudaStreamWaitEvent(st, sl->copied, 0));
         cudaEvent_t *ev = ctx->ev;
         CK(cudaEventRecord(ev[2 * T_NSTAGE], st));  // sample start
+      for (int attempt = 0; attempt < 2; attempt++) {
+        // attempt 0: single pass over the reads into fixed-capacity L1 buckets (sizes are binomial for hashed
+        // keys); attempt 1 (only after an overflow, e.g. one k-mer repeated millions of times): exact count pass first
+        const bool exact = attempt == 1 || ctx->force_exact;
+        const uint64_t per_bucket = n_pos / nb1;
+        const uint64_t cap = per_bucket + 8 * (uint64_t)sqrt((double)per_bucket) + 1024;
+        if (!exact && ctx->d_keysA.reserve((size_t)nb1 * cap * 8)) { ctx->set_error("out of device memory (work buffers)"); return SIMKA_ERR_NOMEM; }
         CK(cudaMemsetAsync(d_totals, 0, 24, st));
+        CK(cudaMemsetAsync(d_overflow, 0, 4, st));
         CK(cudaMemsetAsync(ctx->d_hist1.p, 0, MAX_B * 4, st));
         CK(cudaMemsetAsync(ctx->d_cursor1.p, 0, MAX_B * 4, st));
         CK(cudaMemsetAsync(ctx->d_fine_hist.p, 0, (size_t)nbins * 4, st));
@@ -1654,28 +1754,33 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         const unsigned g1 = (unsigned)((n_words + BLOCK - 1) / BLOCK);
         const uint64_t *seq = sl->ext_packed ? sl->ext_packed : sl->packed.as<uint64_t>();
         const uint32_t *bad = sl->ext_bad ? sl->ext_bad : sl->bad.as<uint32_t>();
-        // K1 count / scan / scatter
+        // K1 (count / scan /) scatter
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
-        k_extract<true><<<g1, BLOCK, 3 * MAX_B * 4 + 64, st>>>(seq, bad, n_words, ctx->kp, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, nullptr);
+        if (exact) {
+            k_extract<true><<<g1, BLOCK, 3 * MAX_B * 4 + 64, st>>>(seq, bad, n_words, ctx->kp, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, 0, nullptr, nullptr);
+            ctx->launches++;
+        }
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT + 1], st));
-        k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_hist1.as<uint32_t>(), ctx->d_base1.as<uint64_t>(), nb1);
+        if (exact) launch_scan(ctx, ctx->d_hist1.as<uint32_t>(), ctx->d_base1.as<uint64_t>(), nb1);
+        else k_fill_bases<<<(nb1 + 256) / 256, 256, 0, st>>>(ctx->d_base1.as<uint64_t>(), (int)nb1, cap);
         CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER], st));
         k_extract<false><<<g1, BLOCK, 3 * MAX_B * 4 + 64 + L1_TILE * 8, st>>>(seq, bad, n_words, ctx->kp, b1_bits, nullptr, ctx->d_base1.as<uint64_t>(),
-                                                                           ctx->d_cursor1.as<uint32_t>(), ctx->d_keysA.as<uint64_t>());
+                                                                           ctx->d_cursor1.as<uint32_t>(), exact ? ~0ull : cap, d_overflow,
+                                                                           ctx->d_keysA.as<uint64_t>());
         CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER + 1], st));
-        CK(cudaEventRecord(sl->consumed, st));  // the input slot may be overwritten from here on
-        sl->consumed_valid = true;
+        // per-bucket key counts: the cursors of the scatter pass (== the histogram in exact mode)
+        const uint32_t *cnt1 = ctx->d_cursor1.as<uint32_t>();
         // K2 tiles, count / scan / scatter
-        k_tiles_per_bucket<<<(nb1 + 255) / 256, 256, 0, st>>>(ctx->d_hist1.as<uint32_t>(), ctx->d_tiles.as<uint32_t>(), nb1, L2_TILE);
-        k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_tiles.as<uint32_t>(), ctx->d_tile_start.as<uint64_t>(), nb1);
+        k_tiles_per_bucket<<<(nb1 + 255) / 256, 256, 0, st>>>(cnt1, ctx->d_tiles.as<uint32_t>(), nb1, L2_TILE);
+        launch_scan(ctx, ctx->d_tiles.as<uint32_t>(), ctx->d_tile_start.as<uint64_t>(), nb1);
         const unsigned g2 = (unsigned)(n_pos / L2_TILE + nb1 + 1);  // upper bound on the number of tiles
         CK(cudaEventRecord(ev[2 * T_PART_COUNT], st));
-        k_partition2<true><<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
+        k_partition2<true><<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), cnt1, ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
                                                  ctx->d_fine_hist.as<uint32_t>(), nullptr, nullptr, nullptr);
         CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
-        k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), nbins);
+        launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), nbins);
         CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
-        k_partition2<false><<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
+        k_partition2<false><<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), cnt1, ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
                                                   nullptr, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), ctx->d_keysB.as<uint64_t>());
         CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
         // K3 count
@@ -1695,24 +1800,30 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         k_bin_count<<<gbin, BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins, slot_shift, ctx->prm.abundance_min,
                                             ctx->prm.abundance_max, co);
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT + 1], st));
-        k_scan_u32_u64<<<1, 1024, 0, st>>>(ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins);
+        launch_scan(ctx, ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins);
         ctx->launches += 9;
         CK(cudaGetLastError());
         // the only host sync of the sample: sizes + totals
-        int h_err = 0;
+        int h_err = 0, h_overflow = 0;
         CK(cudaMemcpyAsync(&h_surv, ctx->d_out_off.as<uint64_t>() + nbins, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_keys, ctx->d_fine_off.as<uint64_t>() + nbins, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_tot, d_totals, 24, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_err, d_error, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (h_overflow && !exact) { ctx->exact_retries++; continue; }  // a bucket outgrew its capacity: redo with the exact two-pass path
         if (h_err) { ctx->set_error("on-chip table overflow in k_bin_count (code " + std::to_string(h_err) + ")"); return SIMKA_ERR_OVERFLOW; }
+        break;
+      }
+        CK(cudaEventRecord(sl->consumed, st));  // the input slot may be overwritten from here on
+        sl->consumed_valid = true;
         if (h_surv >= (1ull << 32)) { ctx->set_error("more than 2^32 solid k-mers in one sample shard"); return SIMKA_ERR_INVALID; }
         CK(cudaEventRecord(ev[2 * T_COMPACT], st));
         if (h_surv > 0) {
             sd.eh = (uint64_t *)ctx->arena.alloc(h_surv * 8);
             sd.ec = (uint32_t *)ctx->arena.alloc(h_surv * 4);
             if (!sd.eh || !sd.ec) { ctx->set_error("out of device memory (sample list)"); return SIMKA_ERR_NOMEM; }
-            k_compact<<<gbin, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(),
+            k_compact<<<(unsigned)std::min<uint64_t>((nbins + 7) / 8, (uint64_t)ctx->nsm * 8), BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(),
                                              ctx->d_out_off.as<uint64_t>(), nbins, sd.eh, sd.ec);
             ctx->launches++;
             if (ctx->prm.complex_dist) {
@@ -1949,6 +2060,7 @@ int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
     t.kmers_in = ctx->kmers_in;
     t.entries = ctx->entries;
     t.kernel_launches = ctx->launches;
+    t.exact_retries = ctx->exact_retries;
     if (ctx->merged && ctx->a_scalars) {
         ull sc[4];
         if (cudaMemcpy(sc, ctx->a_scalars, 32, cudaMemcpyDeviceToHost) == cudaSuccess) { t.distinct_kmers = sc[0]; t.pairs = sc[2]; }

@@ -129,3 +129,31 @@ def test_simkamin_distance():
     ojac, obc = oracle.simkamin_distance(hashes, counts)
     np.testing.assert_array_equal(jac, ojac)
     np.testing.assert_array_equal(bc, obc)
+
+
+def test_heavy_hitter_falls_back_to_exact_count():
+    """One k-mer repeated far beyond a bucket's capacity: the optimistic single-pass K1 overflows, the
+    sample is redone with the exact count pass, and the result is still bit-exact."""
+    from helpers import reads_to_arrays
+    rng = np.random.default_rng(11)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    g = alpha[rng.integers(0, 4, 5000)].tobytes()
+    normal = [g[i:i + 100] for i in rng.integers(0, 4900, 600)]
+    s0 = reads_to_arrays([b"A" * 150] * 3000 + normal)
+    s1 = reads_to_arrays(normal + [b"ACGT" * 30] * 10)
+    s2 = reads_to_arrays([b"T" * 120] * 50 + normal[:300])
+    samples = [s0, s1, s2]
+    run = oracle_run(samples, 31, 2)
+    st, ctx = simka_b200.run_samples(samples, 31, abundance_min=2, keep_ctx=True)
+    t = ctx.timings()
+    ctx.close()
+    assert t["exact_retries"] >= 1
+    assert_stats_equal(st, run)
+
+
+def test_forced_exact_count_path(monkeypatch):
+    monkeypatch.setenv("SIMKA_B200_EXACT_COUNT", "1")
+    samples = synthetic_samples(4, 2000)
+    run = oracle_run(samples, 31, 2)
+    st = simka_b200.run_samples(samples, 31, abundance_min=2)
+    assert_stats_equal(st, run)
