@@ -471,23 +471,33 @@ struct CountOut {
     int *error_flag;
 };
 
-// insert one key into the open-addressing table (linear probing).  Plain read first: most keys
-// are repeats of a k-mer that is already there, which then costs one LDS + one ATOMS.POPC.INC.
-// TRACK: count the distinct keys claimed (only for bins that might not fit).
+// Insert up to four keys per thread into the open-addressing table (linear probing), the four probe
+// sequences interleaved so that the shared-memory latencies overlap and the warp stays converged.
+// Plain read first: most keys repeat a k-mer that is already there (one LDS + one ATOMS.POPC.INC).
+// TRACK: count the distinct keys claimed (only for bins that might not fit the table).
 template <bool TRACK>
-__device__ __forceinline__ void table_insert(uint64_t *tk, uint32_t *tc, uint32_t *distinct, uint64_t h, uint32_t slot) {
+__device__ __forceinline__ void table_insert4(uint64_t *tk, uint32_t *tc, uint32_t *distinct, const uint64_t (&h)[4], uint32_t pending,
+                                              int slot_shift) {
     volatile uint64_t *vk = tk;
-#pragma unroll 1
-    for (int probes = 0; probes < CNT_SLOTS; probes++) {
-        uint64_t cur = vk[slot];
-        if (cur == EMPTY) {
-            cur = atomicCAS(reinterpret_cast<ull *>(&tk[slot]), (ull)EMPTY, (ull)h);
-            if (cur == EMPTY) { cur = h; if (TRACK) atomicAdd(distinct, 1u); }
+    uint32_t slot[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) slot[q] = (uint32_t)(h[q] >> slot_shift) & (CNT_SLOTS - 1);
+    int rounds = 0;
+    while (pending) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (pending & (1u << q)) {
+                uint64_t cur = vk[slot[q]];
+                if (cur == EMPTY) {
+                    cur = atomicCAS(reinterpret_cast<ull *>(&tk[slot[q]]), (ull)EMPTY, (ull)h[q]);
+                    if (cur == EMPTY) { cur = h[q]; if (TRACK) atomicAdd(distinct, 1u); }
+                }
+                if (cur == h[q]) { atomicAdd(&tc[slot[q]], 1u); pending &= ~(1u << q); }
+                else slot[q] = (slot[q] + 1) & (CNT_SLOTS - 1);
+            }
         }
-        if (cur == h) { atomicAdd(&tc[slot], 1u); return; }
-        slot = (slot + 1) & (CNT_SLOTS - 1);
+        if (++rounds > CNT_SLOTS) { atomicAdd(distinct, (uint32_t)CNT_SLOTS); return; }  // table full (TRACK only): finer retry
     }
-    atomicAdd(distinct, (uint32_t)CNT_SLOTS);  // table full (only reachable when TRACK): force a finer retry
 }
 
 template <bool TRACK>
@@ -496,18 +506,22 @@ __device__ __forceinline__ void bin_insert_all(uint64_t *tk, uint32_t *tc, uint3
     const int tid = threadIdx.x;
     for (uint32_t base = 0; base < n; base += BLOCK * 4) {
         uint64_t h[4];
+        uint32_t pending = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint32_t i = base + q * BLOCK + tid;
             h[q] = i < n ? kb[i] : EMPTY;
+            if (i < n) pending |= 1u << q;
         }
-        if (TRACK && *((volatile uint32_t *)distinct) > CNT_MAXDISTINCT) return;
+        if (TRACK) {
+            if (*((volatile uint32_t *)distinct) > CNT_MAXDISTINCT) return;
+            if (R > 1) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (h[q] == EMPTY) continue;
-            if (TRACK && R > 1 && (((uint32_t)(simka::hash2(h[q]) >> 20)) & (R - 1)) != r) continue;
-            table_insert<TRACK>(tk, tc, distinct, h[q], (uint32_t)(h[q] >> slot_shift) & (CNT_SLOTS - 1));
+                for (int q = 0; q < 4; q++)
+                    if ((((uint32_t)(simka::hash2(h[q]) >> 20)) & (R - 1)) != r) pending &= ~(1u << q);
+            }
         }
+        table_insert4<TRACK>(tk, tc, distinct, h, pending, slot_shift);
     }
 }
 
@@ -552,25 +566,25 @@ k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine
                 __syncthreads();
                 overflow = track && *distinct > CNT_MAXDISTINCT;
                 if (tid == 0) s_distinct[(pass + 1) & 1] = 0;
-                // read-out + clean: thread t owns slots [8t, 8t+8)
+                // read-out + clean: thread t owns the slot pairs {2(q*BLOCK+t), 2(q*BLOCK+t)+1}, q = 0..3, so that
+                // consecutive lanes touch consecutive 16-byte (keys) / 8-byte (counts) words: conflict-free
                 uint64_t k8[8];
                 uint32_t c8[8];
                 {
-                    uint4 *pk = reinterpret_cast<uint4 *>(tk + 8 * tid);
-                    uint4 *pc = reinterpret_cast<uint4 *>(tc + 8 * tid);
+                    uint4 *pk = reinterpret_cast<uint4 *>(tk) + tid;
+                    uint2 *pc = reinterpret_cast<uint2 *>(tc) + tid;
+                    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const uint4 v = pk[q];
+                        const uint4 v = pk[q * BLOCK];
+                        const uint2 c = pc[q * BLOCK];
                         k8[2 * q] = ((uint64_t)v.y << 32) | v.x;
                         k8[2 * q + 1] = ((uint64_t)v.w << 32) | v.z;
+                        c8[2 * q] = c.x;
+                        c8[2 * q + 1] = c.y;
+                        pk[q * BLOCK] = e;
+                        pc[q * BLOCK] = make_uint2(0, 0);
                     }
-                    const uint4 c0 = pc[0], c1 = pc[1];
-                    c8[0] = c0.x; c8[1] = c0.y; c8[2] = c0.z; c8[3] = c0.w;
-                    c8[4] = c1.x; c8[5] = c1.y; c8[6] = c1.z; c8[7] = c1.w;
-                    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int q = 0; q < 4; q++) pk[q] = e;
-                    pc[0] = z; pc[1] = z;
                 }
                 uint32_t keepm = 0;
                 if (!overflow && !never) {
