@@ -474,10 +474,10 @@ struct CountOut {
 // Insert up to four keys per thread into the open-addressing table (linear probing), the four probe
 // sequences interleaved so that the shared-memory latencies overlap and the warp stays converged.
 // Plain read first: most keys repeat a k-mer that is already there (one LDS + one ATOMS.POPC.INC).
-// TRACK: count the distinct keys claimed (only for bins that might not fit the table).
-template <bool TRACK>
-__device__ __forceinline__ void table_insert4(uint64_t *tk, uint32_t *tc, uint32_t *distinct, const uint64_t (&h)[4], uint32_t pending,
-                                              int slot_shift) {
+// A thread that claims a slot appends it to the claimed list, which is what the read-out walks
+// (the table itself is never scanned) and what counts the distinct keys of the bin.
+__device__ __forceinline__ void table_insert4(uint64_t *tk, uint32_t *tc, uint16_t *claimed, uint32_t *nclaim, const uint64_t (&h)[4],
+                                              uint32_t pending, int slot_shift) {
     volatile uint64_t *vk = tk;
     uint32_t slot[4];
 #pragma unroll
@@ -490,19 +490,20 @@ __device__ __forceinline__ void table_insert4(uint64_t *tk, uint32_t *tc, uint32
                 uint64_t cur = vk[slot[q]];
                 if (cur == EMPTY) {
                     cur = atomicCAS(reinterpret_cast<ull *>(&tk[slot[q]]), (ull)EMPTY, (ull)h[q]);
-                    if (cur == EMPTY) { cur = h[q]; if (TRACK) atomicAdd(distinct, 1u); }
+                    if (cur == EMPTY) { cur = h[q]; claimed[atomicAdd(nclaim, 1u)] = (uint16_t)slot[q]; }
                 }
                 if (cur == h[q]) { atomicAdd(&tc[slot[q]], 1u); pending &= ~(1u << q); }
                 else slot[q] = (slot[q] + 1) & (CNT_SLOTS - 1);
             }
         }
-        if (++rounds > CNT_SLOTS) { atomicAdd(distinct, (uint32_t)CNT_SLOTS); return; }  // table full (TRACK only): finer retry
+        if (++rounds > CNT_SLOTS) return;  // table full: nclaim == CNT_SLOTS > CNT_MAXDISTINCT makes the caller retry finer
     }
 }
 
-template <bool TRACK>
-__device__ __forceinline__ void bin_insert_all(uint64_t *tk, uint32_t *tc, uint32_t *distinct, const uint64_t *__restrict__ kb,
-                                               uint32_t n, uint32_t R, uint32_t r, int slot_shift) {
+// MULTI: the bin may hold more distinct keys than one table pass takes: stop early on overflow, R sub-passes
+template <bool MULTI>
+__device__ __forceinline__ void bin_insert_all(uint64_t *tk, uint32_t *tc, uint16_t *claimed, uint32_t *nclaim,
+                                               const uint64_t *__restrict__ kb, uint32_t n, uint32_t R, uint32_t r, int slot_shift) {
     const int tid = threadIdx.x;
     for (uint32_t base = 0; base < n; base += BLOCK * 4) {
         uint64_t h[4];
@@ -513,46 +514,50 @@ __device__ __forceinline__ void bin_insert_all(uint64_t *tk, uint32_t *tc, uint3
             h[q] = i < n ? kb[i] : EMPTY;
             if (i < n) pending |= 1u << q;
         }
-        if (TRACK) {
-            if (*((volatile uint32_t *)distinct) > CNT_MAXDISTINCT) return;
+        if (MULTI) {
+            if (*((volatile uint32_t *)nclaim) > CNT_MAXDISTINCT) return;
             if (R > 1) {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
                     if ((((uint32_t)(simka::hash2(h[q]) >> 20)) & (R - 1)) != r) pending &= ~(1u << q);
             }
         }
-        table_insert4<TRACK>(tk, tc, distinct, h, pending, slot_shift);
+        table_insert4(tk, tc, claimed, nclaim, h, pending, slot_shift);
     }
 }
 
-// Persistent CTAs, bins taken with a grid stride.  The table is left clean by the read-out scan, so
-// the only per-bin fixed cost is that scan (8 slots per thread, 128-bit shared loads and stores).
+// Persistent CTAs, bins taken with a grid stride.  Per-bin fixed cost: two barriers; everything else is
+// proportional to the keys (insert) and to the distinct keys (read-out of the claimed slots, which also
+// leaves the table clean for the next bin).
 __global__ void __launch_bounds__(BLOCK)
 k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine_off, uint32_t nbins, int slot_shift,
             int64_t amin, int64_t amax, CountOut out) {
-    static_assert(CNT_SLOTS == 8 * BLOCK, "read-out: 8 slots per thread");
     __shared__ __align__(16) uint64_t tk[CNT_SLOTS];
     __shared__ __align__(16) uint32_t tc[CNT_SLOTS];
-    __shared__ uint32_t s_cursor, s_distinct[2];
+    __shared__ uint16_t claimed[CNT_SLOTS];
+    __shared__ uint32_t s_cursor, s_nclaim[2];
     __shared__ ull s_tot[3];
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < CNT_SLOTS; i += BLOCK) { tk[i] = EMPTY; tc[i] = 0; }
-    if (tid == 0) { s_cursor = 0; s_distinct[0] = s_distinct[1] = 0; s_tot[0] = s_tot[1] = s_tot[2] = 0; }
+    if (tid == 0) { s_cursor = 0; s_nclaim[0] = s_nclaim[1] = 0; s_tot[0] = s_tot[1] = s_tot[2] = 0; }
     __syncthreads();
     ull t_d = 0, t_s = 0, t_q = 0;
     // keep iff amin <= c <= amax (src/minikc/MiniKC.hpp:56) with c a non-zero u32
     const bool never = amax < 0 || amin > 0xFFFFFFFFll;
     const uint32_t cmin = amin < 0 ? 0u : (uint32_t)amin;
     const uint32_t cmax = amax > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)(amax < 0 ? 0 : amax);
-    uint32_t pass = 0;  // parity selects the distinct counter of the current table pass
+    uint32_t pass = 0;  // parity selects the claim counter of the current table pass
 
+    uint64_t nbeg = 0, nend = 0;  // offsets of the next bin, loaded one bin ahead
+    if (blockIdx.x < nbins) { nbeg = fine_off[blockIdx.x]; nend = fine_off[blockIdx.x + 1]; }
     for (uint32_t bin = blockIdx.x; bin < nbins; bin += gridDim.x) {
-        const uint64_t beg = fine_off[bin], end = fine_off[bin + 1];
+        const uint64_t beg = nbeg, end = nend;
+        if (bin + gridDim.x < nbins) { nbeg = fine_off[bin + gridDim.x]; nend = fine_off[bin + gridDim.x + 1]; }
         if (end - beg >= 0xFFFFFFFFull) { if (tid == 0) { *out.error_flag = 6; out.surv[bin] = 0; } continue; }
         const uint32_t n = (uint32_t)(end - beg);
         if (n == 0) { if (tid == 0) out.surv[bin] = 0; continue; }
         const uint64_t *kb = keys + beg;
-        const bool track = n > CNT_MAXDISTINCT;
+        const bool multi = n > CNT_MAXDISTINCT;
         // R sub-passes (keys selected by a second hash) only when the DISTINCT keys of the bin do not
         // fit the table; a bin that is large because of a few heavy k-mers still takes one pass.
         for (uint32_t R = 1;; R *= 2) {
@@ -560,57 +565,40 @@ k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine
             ull b_d = 0, b_s = 0, b_q = 0;
             bool overflow = false;
             for (uint32_t r = 0; r < R && !overflow; r++, pass++) {
-                uint32_t *distinct = &s_distinct[pass & 1];
-                if (track) bin_insert_all<true>(tk, tc, distinct, kb, n, R, r, slot_shift);
-                else bin_insert_all<false>(tk, tc, distinct, kb, n, 1, 0, slot_shift);
+                uint32_t *nclaim = &s_nclaim[pass & 1];
+                if (multi) bin_insert_all<true>(tk, tc, claimed, nclaim, kb, n, R, r, slot_shift);
+                else bin_insert_all<false>(tk, tc, claimed, nclaim, kb, n, 1, 0, slot_shift);
                 __syncthreads();
-                overflow = track && *distinct > CNT_MAXDISTINCT;
-                if (tid == 0) s_distinct[(pass + 1) & 1] = 0;
-                // read-out + clean: thread t owns the slot pairs {2(q*BLOCK+t), 2(q*BLOCK+t)+1}, q = 0..3, so that
-                // consecutive lanes touch consecutive 16-byte (keys) / 8-byte (counts) words: conflict-free
-                uint64_t k8[8];
-                uint32_t c8[8];
-                {
-                    uint4 *pk = reinterpret_cast<uint4 *>(tk) + tid;
-                    uint2 *pc = reinterpret_cast<uint2 *>(tc) + tid;
-                    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint4 v = pk[q * BLOCK];
-                        const uint2 c = pc[q * BLOCK];
-                        k8[2 * q] = ((uint64_t)v.y << 32) | v.x;
-                        k8[2 * q + 1] = ((uint64_t)v.w << 32) | v.z;
-                        c8[2 * q] = c.x;
-                        c8[2 * q + 1] = c.y;
-                        pk[q * BLOCK] = e;
-                        pc[q * BLOCK] = make_uint2(0, 0);
+                const uint32_t nc = *nclaim;
+                overflow = nc > CNT_MAXDISTINCT;
+                if (tid == 0) s_nclaim[(pass + 1) & 1] = 0;
+                // read-out + clean of the claimed slots
+                for (uint32_t e0 = 0; e0 < nc; e0 += BLOCK) {
+                    const uint32_t e = e0 + tid;
+                    bool keep = false;
+                    uint64_t hk = 0;
+                    uint32_t c = 0;
+                    if (e < nc) {
+                        const uint32_t slot = claimed[e];
+                        hk = tk[slot];
+                        c = tc[slot];
+                        tk[slot] = EMPTY;
+                        tc[slot] = 0;
+                        keep = !overflow && !never && c >= cmin && c <= cmax;
                     }
-                }
-                uint32_t keepm = 0;
-                if (!overflow && !never) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) keepm |= (uint32_t)(c8[q] != 0 && c8[q] >= cmin && c8[q] <= cmax) << q;
-                }
-                const uint32_t nk = __popc(keepm);
-                uint32_t inc = nk;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += v;
-                }
-                uint32_t wbase = 0;
-                if (lane == 31 && inc) wbase = atomicAdd(&s_cursor, inc);
-                wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                uint64_t pos = beg + wbase + inc - nk;
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    if (keepm & (1u << q)) {
-                        out.stage_h[pos] = k8[q];
-                        out.stage_c[pos] = c8[q];
-                        pos++;
-                        b_d += 1;
-                        b_s += c8[q];
-                        b_q += (ull)((double)c8[q] * (double)c8[q]);  // pow(count,2) -> u64, src/minikc/MiniKC.hpp:62
+                    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                    if (m) {
+                        uint32_t wbase = 0;
+                        if (lane == 0) wbase = atomicAdd(&s_cursor, (uint32_t)__popc(m));
+                        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                        if (keep) {
+                            const uint64_t pos = beg + wbase + __popc(m & ((1u << lane) - 1));
+                            out.stage_h[pos] = hk;
+                            out.stage_c[pos] = c;
+                            b_d += 1;
+                            b_s += c;
+                            b_q += (ull)((double)c * (double)c);  // pow(count,2) -> u64, src/minikc/MiniKC.hpp:62
+                        }
                     }
                 }
                 __syncthreads();
