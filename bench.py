@@ -10,8 +10,9 @@ update and the read-out of the accumulators.  Workload at 1 GPU = BASELINE.json 
   value  : reads already 2-bit packed and resident in HBM when the timed region starts
   e2e    : the same through the C ABI with pinned HOST buffers (H2D of the packed reads and D2H of
            the accumulators inside the timed region, copy of sample s+1 overlapped with sample s)
-  --gpus N>1 (torchrun): hash buckets sharded over the ranks (every rank scans all reads, keeps its
-           buckets), two tiny all-reduces; same total workload => "scaling": "strong"
+  --gpus N>1 (torchrun): samples sharded over the ranks for counting, hash ranges sharded for the merge,
+           solid k-mer lists exchanged with one NCCL all-to-all, two tiny all-reduces; same total
+           workload => "scaling": "strong"
   --impl reference : the CPU restatement of the reference algorithm (oracle/, OpenMP, all host cores)
            on a bounded sample of the same workload.
 """
@@ -221,52 +222,38 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    # ---- synthetic input: every rank needs every sample (buckets are sharded, not reads) ---------
+    # ---- synthetic input: rank r owns samples s with s % world == r (sample-sharded counting) ----------
     N, M, L, k = a.samples, a.reads, a.read_len, a.kmer
-    shm = f"/dev/shm/simka_bench_{os.environ.get('MASTER_PORT', 'single')}_{N}x{M}"
-    if rank == 0:
-        os.makedirs(shm, exist_ok=True)
-    if world > 1:
-        dist.barrier()
     genomes = synth.make_genomes(n_genomes_for(N), 50_000)
     t_gen = time.perf_counter()
-    for s in range(rank, N, world):
+    mine = [s for s in range(N) if sdist.sample_owner(s, world) == rank]
+    host, devbuf, nwords = {}, {}, {}
+    for s in mine:
         seqs, off = synth.make_sample(genomes, s, M, L)
-        packed, bad, nw = simka_b200.pack_reads(seqs, off)
-        np.save(os.path.join(shm, f"p{s}.npy"), packed)
-        np.save(os.path.join(shm, f"b{s}.npy"), bad)
-        del seqs, off, packed, bad
+        hp, hb, nw = simka_b200.pack_reads(seqs, off, pinned=True)
+        del seqs, off
+        host[s] = (hp, hb)
+        nwords[s] = nw
+        devbuf[s] = (torch.from_numpy(hp.view(np.int64)).to(dev), torch.from_numpy(hb.view(np.int32)).to(dev))
     if world > 1:
         dist.barrier()
-    host, devbuf, nwords = [], [], []
-    for s in range(N):
-        p = np.load(os.path.join(shm, f"p{s}.npy"), mmap_mode="r")
-        b = np.load(os.path.join(shm, f"b{s}.npy"), mmap_mode="r")
-        hp = simka_b200.pinned_empty(len(p), np.uint64)
-        hb = simka_b200.pinned_empty(len(b), np.uint32)
-        hp[:] = p
-        hb[:] = b
-        host.append((hp, hb))
-        nwords.append(len(p) - 1)
-        devbuf.append((torch.from_numpy(hp.view(np.int64)).to(dev), torch.from_numpy(hb.view(np.int32)).to(dev)))
-    if world > 1:
-        dist.barrier()
-    if rank == 0:
-        shutil.rmtree(shm, ignore_errors=True)
     gen_s = time.perf_counter() - t_gen
     kmers_per_step = N * M * (L - k + 1)
-    h2d = sum((nw + 1) * 12 for nw in nwords)
+    h2d = sum((nw + 1) * 12 for nw in nwords.values())
 
-    ctx = simka_b200.SimkaGpu(N, k, a.abundance_min, simple_dist=True, complex_dist=True, device=local,
-                              shard_rank=rank, shard_count=world, expected_kmers_per_sample=M * (L - k + 1))
+    exp = M * (L - k + 1)
+    ctx = simka_b200.SimkaGpu(N, k, a.abundance_min, simple_dist=True, complex_dist=True, device=local, expected_kmers_per_sample=exp)
+    mctx = simka_b200.SimkaGpu(N, k, a.abundance_min, simple_dist=True, complex_dist=True, device=local) if world > 1 else None
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
     d2h_bytes = [0]
 
     def finish_run():
         if world > 1:
-            ctx.set_totals(sdist.allreduce_totals(ctx.get_totals()))
-        ctx.merge_and_accumulate()
-        st = ctx.stats()
+            mctx.reset()
+            st = sdist.exchange_and_merge(ctx, mctx, N, rank, world, dev)
+        else:
+            ctx.merge_and_accumulate()
+            st = ctx.stats()
         d2h_bytes[0] = sum(getattr(st, n).nbytes for n in st.U64_SYM + st.U64_SQ) + st.kullback_leibler.nbytes
         if world > 1:
             st = sdist.allreduce_stats(st)
@@ -274,7 +261,7 @@ def run_ours(a):
 
     def step_resident():
         ctx.reset()
-        for s in range(N):
+        for s in mine:
             dp, db = devbuf[s]
             ctx.push_reads_device(s, dp.data_ptr(), db.data_ptr(), nwords[s], M)
             ctx.finish_sample(s)
@@ -282,10 +269,12 @@ def run_ours(a):
 
     def step_e2e():
         ctx.reset()
-        ctx.push_reads(0, host[0][0], host[0][1], nwords[0], M)
-        for s in range(N):
-            if s + 1 < N:
-                ctx.push_reads(s + 1, host[s + 1][0], host[s + 1][1], nwords[s + 1], M)
+        if mine:
+            ctx.push_reads(mine[0], host[mine[0]][0], host[mine[0]][1], nwords[mine[0]], M)
+        for i, s in enumerate(mine):
+            if i + 1 < len(mine):
+                s2 = mine[i + 1]
+                ctx.push_reads(s2, host[s2][0], host[s2][1], nwords[s2], M)
             ctx.finish_sample(s)
         return finish_run()
 
@@ -303,6 +292,11 @@ def run_ours(a):
         for _ in range(steps):
             st = fn()
             t = ctx.timings()
+            if mctx is not None:  # stage 2 ran in the merge context
+                tm = mctx.timings()
+                for kk in ("merge_ms", "distinct_kmers", "pairs", "kernel_launches"):
+                    t[kk] += tm[kk]
+                t["total_ms"] += tm["merge_ms"]
             launches += t["kernel_launches"]
             for kk, v in t.items():
                 tims[kk] = tims.get(kk, 0) + v
@@ -325,12 +319,16 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else {}
     # sanity: both paths must produce the same accumulators
     assert np.array_equal(st.nb_shared, st2.nb_shared) and np.array_equal(st.braycurtis_num, st2.braycurtis_num)
+    if world > 1:  # whole-job byte and launch counts
+        t = torch.tensor([h2d, launches, d2h_bytes[0]], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h2d, launches, d2h_bytes[0] = (int(x) for x in t.tolist())
 
     if rank == 0:
         steps = a.steps
         per = {kk: v / steps for kk, v in tims.items()}
         Ks, D, U = per["kmers_in"], per["entries"], per["distinct_kmers"]
-        words = sum(nwords)
+        words = sum(nwords.values())
         # algorithmic bytes per launch set (summed over the samples of one step); DESIGN.md section 4
         alg = {
             "k_extract<count>": words * 12,
@@ -361,7 +359,8 @@ def run_ours(a):
             "metric": "31-mers/sec into NxN distance matrix", "value": kmers_per_step * steps / (ms_res * 1e-3),
             "unit": "kmers/s", "n_gpus": world, "steps": steps, "warmup": a.warmup, "ms_per_step": ms_res / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "sharding": f"hash buckets over {world} rank(s), every rank scans all reads",
+            "config": {"workload": workload_name(a), "sharding": (f"samples over {world} ranks for counting (rank r owns samples s % {world} == r), hash ranges over the ranks for the merge; "
+                                    "solid (k-mer,count) lists exchanged with NCCL all-to-all, 2 tiny all-reduces; kernels/roofline are rank 0's share") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (packed reads 57 MB/sample, 0.96 GB of keys per sample streamed)",
                        "generator": "BASELINE.md section 3 (G=256 x 50 kb, Dirichlet(0.3), 1% substitutions, 50% revcomp)",
                        "input_build_s": round(gen_s, 1)},
@@ -383,12 +382,17 @@ def run_ours(a):
                                     "sample": f"{N} samples x {a.ref_reads} reads x {L} bp (same generator), one pass of {secs:.1f} s"}
         print(json.dumps(line), flush=True)
     ctx.close()
+    if mctx is not None:
+        mctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    if os.environ.get("SIMKA_BENCH_WATCHDOG"):  # dump all stacks and exit if the run takes longer than this many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["SIMKA_BENCH_WATCHDOG"]), exit=True)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

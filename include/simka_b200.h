@@ -124,6 +124,23 @@ int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers,
 int simka_gpu_get_totals(simka_ctx *ctx, simka_sample_totals *out /* [N] */);
 int simka_gpu_set_totals(simka_ctx *ctx, const simka_sample_totals *in /* [N] */);
 
+/* ---- multi-GPU, sample-sharded counting: the exchange between the stages ---------------------------
+ * The reference runs one simkaCount process per SAMPLE and one simkaMerge process per PARTITION; what
+ * crosses between them is the per-sample, per-partition list of solid (k-mer, count) records
+ * (solid/part_P/__p__I.gz, src/SimkaCount.cpp:248-257 -> src/SimkaMerge.cpp:1082-1103).  Same here: a rank
+ * counts its own samples (all hash buckets), exports each sample's list -- grouped by "fine range" = the
+ * top simka_gpu_fine_bits() bits of the hashed k-mer, offsets in d_off[2^bits+1] -- and the rank that owns a
+ * contiguous block of fine ranges imports that slice of EVERY sample (any transport: NCCL all-to-all in
+ * simka_b200/dist.py) into a second context, sets the global totals and runs simka_gpu_merge_and_accumulate.
+ * Exported pointers are device memory owned by the context; imported arrays are device memory owned by the
+ * caller and must stay valid until the merge has run.  d_off of an import is re-based to the slice
+ * (d_off[0] = 0) and has 2^fine_bits+1 entries for the slice's own fine_bits. */
+int simka_gpu_fine_bits(simka_ctx *ctx);
+int simka_gpu_export_sample(simka_ctx *ctx, int sample_id, const uint64_t **d_kmers, const uint32_t **d_counts,
+                            const uint32_t **d_off, uint64_t *n);
+int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kmers, const uint32_t *d_counts, uint64_t n,
+                            const uint32_t *d_off, int fine_bits, uint64_t nb_reads);
+
 /* ---- stage 2: replaces `simkaMerge` over all of this shard's buckets ---------------------------
  * (src/SimkaMerge.cpp:1164-1326 k-way merge + insert gate, SimkaCountProcessorSimple::process /
  *  updateDistance{Default,Simple,Complex}, src/core/SimkaAlgorithm.hpp:200-516) */

@@ -218,6 +218,20 @@ class SimkaGpu:
                                                          ct.ctypes.data_as(_lib.u32p), C.byref(n)), "dump_sample_counts")
         return km[:n.value], ct[:n.value]
 
+    # ---- sample-sharded multi-GPU: the exchange between the stages (see include/simka_b200.h) ----
+    def fine_bits(self) -> int:
+        return int(self._L.simka_gpu_fine_bits(self._h))
+
+    def export_sample(self, sample: int):
+        """-> (d_kmers, d_counts, d_off, n): raw device pointers owned by this context"""
+        pk, pc, po, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        self._check(self._L.simka_gpu_export_sample(self._h, sample, C.byref(pk), C.byref(pc), C.byref(po), C.byref(n)), "export_sample")
+        return pk.value or 0, pc.value or 0, po.value or 0, int(n.value)
+
+    def import_sample(self, sample: int, d_kmers: int, d_counts: int, n: int, d_off: int, fine_bits: int, nb_reads: int):
+        self._check(self._L.simka_gpu_import_sample(self._h, sample, C.c_void_p(d_kmers), C.c_void_p(d_counts), n, C.c_void_p(d_off),
+                                                    fine_bits, nb_reads), "import_sample")
+
     def get_totals(self) -> np.ndarray:
         t = np.zeros((self.nb_samples, 4), np.uint64)
         self._check(self._L.simka_gpu_get_totals(self._h, t.ctypes.data_as(C.POINTER(SampleTotals))), "get_totals")

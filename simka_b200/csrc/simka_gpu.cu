@@ -655,6 +655,15 @@ k_abundance_hist(const uint32_t *__restrict__ ec, uint64_t n, int sample, ull *_
     for (int i = threadIdx.x; i < CHIST; i += BLOCK) { const uint32_t c = hist[i]; if (c) atomicAdd(&chist[i], (ull)c); }
 }
 
+// sum of a u32 array (solid abundances of an imported sample range)
+__global__ void __launch_bounds__(BLOCK) k_sum_u32(const uint32_t *__restrict__ v, uint64_t n, ull *__restrict__ out) {
+    ull acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * BLOCK) acc += v[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 // off_table[fr] = out_off[fr * (nbins / FG)], fr in [0, FG]
 __global__ void k_fill_offsets(const uint64_t *__restrict__ out_off, uint32_t *__restrict__ table, uint32_t fg, uint32_t bins_per_fr) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -816,7 +825,9 @@ k_merge(MergeArgs a) {
                 const uint64_t hh = simka::hash2(h);
                 if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
                 uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
-                while (tk[slot] != h) slot = (slot + 1) & (MRG_SLOTS - 1);
+                int pr = 0;
+                while (tk[slot] != h && ++pr <= MRG_SLOTS) slot = (slot + 1) & (MRG_SLOTS - 1);
+                if (pr > MRG_SLOTS) { *a.error_flag = 7; continue; }
                 if (gsz[slot] < 2) continue;  // private k-mer: contributes to no pair
                 const uint32_t pos = gs[slot] + atomicAdd(&pp[slot], 1u);
                 ge_s[pos] = (uint16_t)lo;
@@ -1081,7 +1092,9 @@ k_merge32(MergeArgs a) {
                 const uint64_t hh = simka::hash2(h);
                 if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
                 uint32_t slot = (uint32_t)(hh >> 40) & (M32_SLOTS - 1);
-                while (S.tk[slot] != h) slot = (slot + 1) & (M32_SLOTS - 1);
+                int pr = 0;
+                while (S.tk[slot] != h && ++pr <= M32_SLOTS) slot = (slot + 1) & (M32_SLOTS - 1);
+                if (pr > M32_SLOTS) { *a.error_flag = 7; continue; }  // inconsistent input (never for lists built by this library)
                 if (S.gcnt[slot] == M32_SKIP) continue;  // private k-mer: contributes to no pair
                 const uint32_t pos = atomicSub(&S.gcnt[slot], 1u) - 1;
                 S.ge_s[pos] = (uint8_t)lo;
@@ -1881,6 +1894,63 @@ int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers,
     for (uint64_t i = 0; i < sd.n; i++) order[i] = i;
     std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
     for (uint64_t i = 0; i < sd.n; i++) { kmers[i] = hk[order[i]]; counts[i] = hc[order[i]]; }
+    return SIMKA_OK;
+}
+
+int simka_gpu_fine_bits(simka_ctx *ctx) { return ctx ? ctx->fg_bits : -1; }
+
+int simka_gpu_export_sample(simka_ctx *ctx, int sample_id, const uint64_t **d_kmers, const uint32_t **d_counts, const uint32_t **d_off, uint64_t *n) {
+    if (!ctx || sample_id < 0 || sample_id >= ctx->prm.nb_samples || !ctx->samples[sample_id].done || ctx->fg_bits < 0) return SIMKA_ERR_INVALID;
+    const SampleData &sd = ctx->samples[sample_id];
+    if (d_kmers) *d_kmers = sd.eh;
+    if (d_counts) *d_counts = sd.ec;
+    if (d_off) *d_off = sd.off ? sd.off : ctx->d_off_table.as<uint32_t>() + (size_t)sample_id * (((size_t)1 << ctx->fg_bits) + 1);
+    if (n) *n = sd.n;
+    return SIMKA_OK;
+}
+
+int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kmers, const uint32_t *d_counts, uint64_t n, const uint32_t *d_off,
+                            int fine_bits, uint64_t nb_reads) {
+    if (!ctx) return SIMKA_ERR_INVALID;
+    if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done || fine_bits < 0 || fine_bits > 24 || !d_off ||
+        (n && (!d_kmers || !d_counts)) || n >= (1ull << 32)) { ctx->set_error("bad import arguments"); return SIMKA_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->prm.device));
+    cudaStream_t st = ctx->stream;
+    if (ctx->fg_bits < 0) {
+        ctx->fg_bits = fine_bits;
+        const size_t tbl = (size_t)ctx->prm.nb_samples * (((size_t)1 << fine_bits) + 1) * 4;
+        if (ctx->d_off_table.reserve(tbl)) { ctx->set_error("out of device memory (offset table)"); return SIMKA_ERR_NOMEM; }
+        CK(cudaMemsetAsync(ctx->d_off_table.p, 0, tbl, st));
+    } else if (ctx->fg_bits != fine_bits) { ctx->set_error("fine_bits differs from the context's"); return SIMKA_ERR_INVALID; }
+    SampleData &sd = ctx->samples[sample_id];
+    const size_t fgn = ((size_t)1 << fine_bits) + 1;
+    sd.off = ctx->d_off_table.as<uint32_t>() + (size_t)sample_id * fgn;
+    CK(cudaMemcpyAsync(sd.off, d_off, fgn * 4, cudaMemcpyDeviceToDevice, st));
+    sd.eh = const_cast<uint64_t *>(d_kmers);
+    sd.ec = const_cast<uint32_t *>(d_counts);
+    sd.n = n;
+    ull *d_totals = ctx->d_small.as<ull>();
+    int *d_error = reinterpret_cast<int *>(ctx->d_small.as<char>() + 32);
+    uint32_t *d_big_n = reinterpret_cast<uint32_t *>(ctx->d_small.as<char>() + 40);
+    ull h_sum = 0;
+    if (n) {
+        CK(cudaMemsetAsync(d_totals, 0, 8, st));
+        const unsigned g = (unsigned)std::min<uint64_t>((n + BLOCK * 16 - 1) / (BLOCK * 16), (uint64_t)ctx->nsm * 4);
+        k_sum_u32<<<g, BLOCK, 0, st>>>(d_counts, n, d_totals);
+        if (ctx->prm.complex_dist)
+            k_abundance_hist<<<g, BLOCK, 0, st>>>(d_counts, n, sample_id, ctx->d_chist.as<ull>() + (size_t)sample_id * CHIST,
+                                                 ctx->d_big_counts.as<uint32_t>(), ctx->d_big_sample.as<uint32_t>(), d_big_n, ctx->big_cap, d_error);
+        ctx->launches += ctx->prm.complex_dist ? 2 : 1;
+        CK(cudaMemcpyAsync(&h_sum, d_totals, 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    sd.done = true;
+    sd.local.nb_reads = nb_reads;
+    sd.local.nb_distinct = n;
+    sd.local.nb_kmers = h_sum;
+    sd.local.chord_n2 = 0;
+    if (!ctx->totals_overridden) ctx->global_totals[sample_id] = sd.local;
+    ctx->entries += n;
     return SIMKA_OK;
 }
 

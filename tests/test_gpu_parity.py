@@ -157,3 +157,77 @@ def test_forced_exact_count_path(monkeypatch):
     run = oracle_run(samples, 31, 2)
     st = simka_b200.run_samples(samples, 31, abundance_min=2)
     assert_stats_equal(st, run)
+
+
+class _FakeComm:
+    """in-process stand-in for torch.distributed over `world` threads (one virtual rank each)"""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.bar = threading.Barrier(world)
+        self.slots = [None] * world
+
+    def all_reduce_sum(self, rank):
+        def f(t):
+            self.slots[rank] = t.clone()
+            self.bar.wait()
+            out = sum(self.slots[1:], self.slots[0].clone())
+            self.bar.wait()
+            return out
+        return f
+
+    def all_to_all(self, rank):
+        import torch
+
+        def f(send, send_splits, recv_splits):
+            self.slots[rank] = torch.split(send, list(map(int, send_splits)))
+            self.bar.wait()
+            parts = [self.slots[o][rank] for o in range(self.world)]
+            assert [len(p) for p in parts] == list(map(int, recv_splits))
+            out = torch.cat(parts) if parts else send[:0]
+            self.bar.wait()
+            return out
+        return f
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sample_sharded_exchange_equals_whole(world):
+    """The multi-GPU path on one device: `world` virtual ranks each count their own samples, exchange the
+    solid k-mer lists by hash range and merge their block; the summed accumulators equal the oracle's."""
+    import threading
+    import torch
+    from simka_b200 import dist as sdist
+    samples = synthetic_samples(6, 2500)
+    run = oracle_run(samples, 31, 2)
+    N = len(samples)
+    comm = _FakeComm(world)
+    dev = torch.device("cuda", 0)
+    results, errors = [None] * world, []
+
+    def worker(rank):
+        try:
+            cc = simka_b200.SimkaGpu(N, 31, 2, simple_dist=True, complex_dist=True, expected_kmers_per_sample=2500 * 120)
+            mc = simka_b200.SimkaGpu(N, 31, 2, simple_dist=True, complex_dist=True)
+            for s, (seqs, off) in enumerate(samples):
+                if sdist.sample_owner(s, world) != rank:
+                    continue
+                p, b, nw = simka_b200.pack_reads(seqs, off)
+                cc.push_reads(s, p, b, nw, len(off) - 1)
+                cc.finish_sample(s)
+            results[rank] = sdist.exchange_and_merge(cc, mc, N, rank, world, dev, all_to_all=comm.all_to_all(rank),
+                                                     all_reduce_sum=comm.all_reduce_sum(rank))
+            cc.close()
+            mc.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            comm.bar.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    total = results[0]
+    for st in results[1:]:
+        total += st
+    assert_stats_equal(total, run)
