@@ -69,8 +69,13 @@ class _DevArray:
 
 
 def _dev_tensor(ptr: int, n: int, typestr: str, device) -> torch.Tensor:
+    dt = {"<i8": torch.int64, "<i4": torch.int32}[typestr]
     if n == 0:
-        return torch.empty(0, dtype={"<i8": torch.int64, "<i4": torch.int32}[typestr], device=device)
+        return torch.empty(0, dtype=dt, device=device)
+    if torch.device(device).type == "cpu":  # host memory (gloo tests of the exchange logic with stand-in contexts)
+        import ctypes
+        ct = {"<i8": ctypes.c_int64, "<i4": ctypes.c_int32}[typestr]
+        return torch.from_numpy(np.ctypeslib.as_array((ct * n).from_address(ptr)))
     return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
 
 
@@ -152,7 +157,7 @@ def exchange_and_merge(count_ctx, merge_ctx, nb_samples: int, rank: int, world: 
     recv_e = all_to_all(send_e, send_splits, recv_splits)
     recv_c = all_to_all(send_c, send_splits, recv_splits)
     recv_o = all_to_all(send_o, [len(mine) * fgn] * world, [len(owners[o]) * fgn for o in range(world)])
-    if device.type == "cuda":
+    if torch.device(device).type == "cuda":
         torch.cuda.current_stream(device).synchronize()  # the merge context runs on its own stream
     # stage 2 on my block of fine ranges over all samples
     pos_e, pos_o = 0, 0
