@@ -195,6 +195,17 @@ int simka_write_matrices(const simka_stats_view *stats, const char *const *ids, 
 int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *counts, uint32_t n,
                           uint32_t s, float *jaccard, float *braycurtis, float *kernel_ms);
 
+/* ---- hooks over the host-side mirror of the GATB input surface (simka_b200/csrc/host/*.hpp) ----------------
+ * Kmer<32>::ModelCanonical / ModelDirect iteration (GC/kmer/impl/Model.hpp:726-765): k-mer values + validity of
+ * every window; returns the number of windows.  ModelMinimizer::getMinimizerValue (:1144-1148).
+ * SimkaSequenceFilter::getShannonIndex (src/core/SimkaCommons.hpp:398-432).  Bank::open + Iterator<Sequence>
+ * over a fasta / fastq / gz / album uri: concatenated reads + offsets, malloc'ed (simka_host_free). */
+uint64_t simka_host_kmers(const char *seq, uint64_t len, int k, int canonical, uint64_t *out, uint8_t *valid);
+uint64_t simka_host_minimizer(uint64_t kmer, int k, int m);
+float simka_host_shannon_index(const char *seq, uint64_t len);
+int64_t simka_host_read_bank(const char *uri, char **seqs, uint64_t **read_off);
+void simka_host_free(void *p);
+
 const char *simka_b200_version(void);
 
 #ifdef __cplusplus

@@ -70,6 +70,11 @@ SYMBOLS = {
     "simka_matrix_csv": (C.c_size_t, [C.POINTER(StatsView), C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_size_t]),
     "simka_write_matrices": (C.c_int, [C.POINTER(StatsView), C.POINTER(C.c_char_p), C.c_char_p]),
     "simkamin_gpu_distance": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, f32p, f32p, f32p]),
+    "simka_host_kmers": (C.c_uint64, [C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p, C.POINTER(C.c_uint8)]),
+    "simka_host_minimizer": (C.c_uint64, [C.c_uint64, C.c_int, C.c_int]),
+    "simka_host_shannon_index": (C.c_float, [C.c_char_p, C.c_uint64]),
+    "simka_host_read_bank": (C.c_int64, [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "simka_host_free": (None, [C.c_void_p]),
     "simka_b200_version": (C.c_char_p, []),
 }
 

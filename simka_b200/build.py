@@ -41,7 +41,7 @@ def _stale(target: Path, sources) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / "simka_gpu.cu", CSRC / "simka_host.cpp"]
-    deps = srcs + [CSRC / "kmer_device.cuh", ROOT.parent / "include" / "simka_b200.h"]
+    deps = srcs + [CSRC / "kmer_device.cuh", ROOT.parent / "include" / "simka_b200.h", *sorted((CSRC / "host").glob("*.hpp"))]
     LIBDIR.mkdir(exist_ok=True)
     if force or _stale(LIB, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, srcs), "-lz"]
@@ -53,10 +53,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     cli = CSRC / "simka_main.cpp"
     if cli.exists():
         SIMKA_BIN.parent.mkdir(exist_ok=True)
-        cdeps = deps + [cli, CSRC / "bank.hpp"]
+        cdeps = deps + [cli]
         if force or _stale(SIMKA_BIN, cdeps) or _stale(SIMKA_BIN, [LIB]):
-            cmd = [_nvcc(), "-O2", "-std=c++17", "-o", str(SIMKA_BIN), str(cli), f"-L{LIBDIR}", "-lsimka_b200",
-                   "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../lib", "-lz", "-lpthread"]
+            cuda_lib = str(Path(_nvcc()).resolve().parent.parent / "lib64")
+            cmd = ["g++", "-O2", "-std=c++17", "-o", str(SIMKA_BIN), str(cli), f"-L{LIBDIR}", "-lsimka_b200",
+                   "-Wl,-rpath,$ORIGIN/../lib", f"-Wl,-rpath-link,{cuda_lib}", "-lz", "-lpthread"]
             subprocess.run(cmd, check=True)
     return LIB
 

@@ -1,0 +1,283 @@
+// bank.hpp -- read-set input surface of the Simka hot path, host side.
+//
+// Same names and calling conventions as the GATB-core classes simka uses to read its samples
+// (IBank GC/bank/api/IBank.hpp:78-146, Iterator<T> GC/tools/designpattern/api/Iterator.hpp:117-207,
+// Sequence GC/bank/api/Sequence.hpp:70-111, Bank::open GC/bank/impl/Bank.cpp:143-160, BankFasta
+// GC/bank/impl/BankFasta.cpp:391-572, BankAlbum GC/bank/impl/BankAlbum.cpp:310-348), re-implemented on
+// plain C++17 + zlib: no GATB dependency, no intrusive ref-counting (callers own what they `new`).
+// On top of the one-read-at-a-time iterator there is a batch reader (FastxParser::appendReads) that fills
+// the concatenated-ASCII + offsets layout simka_pack_reads / simka_gpu_push_ascii take.
+#pragma once
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace simka_b200 {
+namespace bank {
+
+struct Exception : std::runtime_error {
+    explicit Exception(const std::string &m) : std::runtime_error(m) {}
+};
+
+// ---- Sequence (GC/bank/api/Sequence.hpp:70-111): data is ASCII, as with Data::ASCII ----------------
+class Sequence {
+public:
+    char *getDataBuffer() { return data.empty() ? nullptr : &data[0]; }
+    const char *getDataBuffer() const { return data.data(); }
+    size_t getDataSize() const { return data.size(); }
+    const std::string &getData() const { return data; }
+    const std::string &getComment() const { return comment; }
+    const std::string &getQuality() const { return quality; }
+    size_t getIndex() const { return index; }
+    std::string toString() const { return data; }
+    std::string comment, data, quality;
+    size_t index = 0;
+};
+
+// ---- Iterator<T> (GC/tools/designpattern/api/Iterator.hpp:117-207) ----------------------------------
+template <class Item>
+class Iterator {
+public:
+    virtual ~Iterator() {}
+    virtual void first() = 0;
+    virtual void next() = 0;
+    virtual bool isDone() = 0;
+    virtual Item &item() = 0;
+    Item *operator->() { return &item(); }
+    Item &operator*() { return item(); }
+    // sub-iterators of a composite bank (album); a plain iterator is its own composition
+    virtual std::vector<Iterator<Item> *> getComposition() { return std::vector<Iterator<Item> *>(1, this); }
+    virtual void finalize() {}
+};
+
+// ---- streaming FASTA / FASTQ (+gz) parser ---------------------------------------------------------------
+// kseq-style grammar, as BankFasta: a record starts at a line beginning with '>' or '@'; sequence lines are
+// concatenated until a line starting with '>', '@' or '+'; after '+' quality characters are consumed until
+// at least as many as bases were read.  Multi-line FASTA, FASTQ, CRLF and gz are handled.
+class FastxParser {
+public:
+    explicit FastxParser(const std::string &path) : path_(path) {
+        f_ = gzopen(path.c_str(), "rb");
+        if (!f_) throw Exception("cannot open " + path);
+        gzbuffer(f_, 1 << 20);
+        buf_.resize(1 << 21);
+    }
+    ~FastxParser() { if (f_) gzclose(f_); }
+    FastxParser(const FastxParser &) = delete;
+    FastxParser &operator=(const FastxParser &) = delete;
+
+    void rewind() {
+        gzrewind(f_);
+        beg_ = end_ = 0;
+        eof_ = false;
+        last_ = 0;
+        index_ = 0;
+    }
+
+    // Appends the next read's bases to `data` (nothing else is touched).  Optionally returns header / quality.
+    // Returns false at end of file.
+    bool nextRead(std::string &data, std::string *comment = nullptr, std::string *quality = nullptr) {
+        int c;
+        if (last_ == 0) {
+            while ((c = getc_()) != -1 && c != '>' && c != '@') {}
+            if (c == -1) return false;
+            last_ = c;
+        }
+        if (comment) comment->clear();
+        while ((c = getc_()) != -1 && c != '\n') if (comment) comment->push_back((char)c);
+        if (comment && !comment->empty() && comment->back() == '\r') comment->pop_back();
+        const size_t start = data.size();
+        while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
+            if (c == '\n') continue;
+            data.push_back((char)c);
+            appendLine_(data);
+            if (data.size() - start > 1 && data.back() == '\r') data.pop_back();
+        }
+        last_ = (c == '>' || c == '@') ? c : 0;
+        if (quality) quality->clear();
+        if (c == '+') {
+            const size_t rlen = data.size() - start;
+            size_t qlen = 0;
+            while ((c = getc_()) != -1 && c != '\n') {}
+            while (c != -1) {
+                bool any = false;
+                while ((c = getc_()) != -1 && c != '\n') { qlen++; any = true; if (quality) quality->push_back((char)c); }
+                if (c == -1 && !any) break;
+                if (qlen >= rlen) break;
+            }
+            last_ = 0;
+        }
+        index_++;
+        return true;
+    }
+    size_t nbReadsSoFar() const { return index_; }
+    const std::string &path() const { return path_; }
+
+private:
+    bool fill_() {
+        if (eof_) return false;
+        int n = gzread(f_, &buf_[0], (unsigned)buf_.size());
+        if (n < 0) throw Exception("read error in " + path_);
+        beg_ = 0;
+        end_ = (size_t)n;
+        if (n == 0) eof_ = true;
+        return n > 0;
+    }
+    int getc_() {
+        if (beg_ >= end_ && !fill_()) return -1;
+        return (unsigned char)buf_[beg_++];
+    }
+    // rest of the current line (without the newline) appended to `out`
+    void appendLine_(std::string &out) {
+        for (;;) {
+            if (beg_ >= end_ && !fill_()) return;
+            const char *p = &buf_[beg_];
+            const char *nl = (const char *)memchr(p, '\n', end_ - beg_);
+            if (nl) {
+                out.append(p, nl - p);
+                beg_ += (size_t)(nl - p) + 1;
+                return;
+            }
+            out.append(p, end_ - beg_);
+            beg_ = end_;
+        }
+    }
+    std::string path_;
+    gzFile f_ = nullptr;
+    std::string buf_;
+    size_t beg_ = 0, end_ = 0;
+    bool eof_ = false;
+    int last_ = 0;
+    size_t index_ = 0;
+};
+
+// ---- IBank (GC/bank/api/IBank.hpp:78-146) ------------------------------------------------------------------
+class IBank {
+public:
+    virtual ~IBank() {}
+    virtual std::string getId() = 0;
+    virtual Iterator<Sequence> *iterator() = 0;  // caller deletes
+    virtual int64_t getNbItems() { return -1; }
+    // exact here (one pass over the file); the reference samples the head of the file (BankFasta.cpp:226-290)
+    virtual void estimate(uint64_t &number, uint64_t &totalSize, uint64_t &maxSize) = 0;
+    int64_t estimateNbItems() { uint64_t n, t, m; estimate(n, t, m); return (int64_t)n; }
+    virtual size_t getCompositionNb() { return 1; }
+    virtual void finalize() {}
+    // the files behind this bank, in iteration order
+    virtual std::vector<std::string> files() = 0;
+};
+
+class BankFasta : public IBank {
+public:
+    explicit BankFasta(const std::string &path) : path_(path) {}
+    static const char *name() { return "fasta"; }
+    std::string getId() override { return path_; }
+    std::vector<std::string> files() override { return std::vector<std::string>(1, path_); }
+    void estimate(uint64_t &number, uint64_t &totalSize, uint64_t &maxSize) override {
+        FastxParser p(path_);
+        std::string d;
+        number = totalSize = maxSize = 0;
+        for (;;) {
+            d.clear();
+            if (!p.nextRead(d)) break;
+            number++;
+            totalSize += d.size();
+            if (d.size() > maxSize) maxSize = d.size();
+        }
+    }
+    class It : public Iterator<Sequence> {
+    public:
+        explicit It(const std::string &path) : parser_(path) {}
+        void first() override { parser_.rewind(); done_ = false; next(); }
+        void next() override {
+            seq_.data.clear();
+            seq_.index = parser_.nbReadsSoFar();
+            done_ = !parser_.nextRead(seq_.data, &seq_.comment, &seq_.quality);
+        }
+        bool isDone() override { return done_; }
+        Sequence &item() override { return seq_; }
+    private:
+        FastxParser parser_;
+        Sequence seq_;
+        bool done_ = true;
+    };
+    Iterator<Sequence> *iterator() override { return new It(path_); }
+private:
+    std::string path_;
+};
+
+// ---- BankAlbum: a text file with one bank uri per line (relative to the album's directory) --------------------
+class BankAlbum : public IBank {
+public:
+    explicit BankAlbum(const std::string &path) : path_(path) {
+        std::ifstream in(path.c_str());
+        if (!in) throw Exception("cannot open album " + path);
+        std::string dir = path.find('/') == std::string::npos ? std::string(".") : path.substr(0, path.rfind('/'));
+        std::string line;
+        while (std::getline(in, line)) {
+            while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+            size_t b = 0;
+            while (b < line.size() && (line[b] == ' ' || line[b] == '\t')) b++;
+            line = line.substr(b);
+            if (line.empty() || line[0] == '#') continue;
+            files_.push_back(line[0] == '/' ? line : dir + "/" + line);
+        }
+    }
+    static const char *name() { return "album"; }
+    std::string getId() override { return path_; }
+    std::vector<std::string> files() override { return files_; }
+    size_t getCompositionNb() override { return files_.size(); }
+    void estimate(uint64_t &number, uint64_t &totalSize, uint64_t &maxSize) override {
+        number = totalSize = maxSize = 0;
+        for (const std::string &f : files_) {
+            uint64_t n, t, m;
+            BankFasta(f).estimate(n, t, m);
+            number += n; totalSize += t; if (m > maxSize) maxSize = m;
+        }
+    }
+    // composite iterator: the files one after the other; getComposition() exposes the per-file iterators
+    class It : public Iterator<Sequence> {
+    public:
+        explicit It(const std::vector<std::string> &files) { for (const std::string &f : files) its_.emplace_back(new BankFasta::It(f)); }
+        void first() override { cur_ = 0; if (!its_.empty()) its_[0]->first(); skip_(); }
+        void next() override { its_[cur_]->next(); skip_(); }
+        bool isDone() override { return cur_ >= its_.size(); }
+        Sequence &item() override { return its_[cur_]->item(); }
+        std::vector<Iterator<Sequence> *> getComposition() override {
+            std::vector<Iterator<Sequence> *> v;
+            for (auto &p : its_) v.push_back(p.get());
+            return v;
+        }
+    private:
+        void skip_() { while (cur_ < its_.size() && its_[cur_]->isDone()) { cur_++; if (cur_ < its_.size()) its_[cur_]->first(); } }
+        std::vector<std::unique_ptr<BankFasta::It>> its_;
+        size_t cur_ = 0;
+    };
+    Iterator<Sequence> *iterator() override { return new It(files_); }
+private:
+    std::string path_;
+    std::vector<std::string> files_;
+};
+
+// ---- Bank::open (GC/bank/impl/Bank.cpp:143-160): fasta/fastq if the content starts a record, else album ----------
+struct Bank {
+    static IBank *open(const std::string &uri) {
+        gzFile f = gzopen(uri.c_str(), "rb");
+        if (!f) throw Exception("Unable to open bank '" + uri + "'");
+        int c;
+        do { c = gzgetc(f); } while (c == ' ' || c == '\n' || c == '\r' || c == '\t');
+        gzclose(f);
+        if (c == '>' || c == '@') return new BankFasta(uri);
+        return new BankAlbum(uri);
+    }
+};
+
+}  // namespace bank
+}  // namespace simka_b200

@@ -1,0 +1,126 @@
+// simka_input.hpp -- the input side of `simka`: input-file grammar, read filter, per-sample read selection.
+//
+// Restates (does not port) src/core/SimkaAlgorithm.cpp:245-351 (layoutInputFilename: "ID: f1 , f2 ; g1 , g2"),
+// src/core/SimkaCommons.hpp:317-436 (SimkaSequenceFilter: minimal read size, Shannon index) and :150-314
+// (SimkaInputIterator: the files of a sample are read group by group -- a group is one ';' part -- and at most
+// `maxReads` filtered reads are taken from each group).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "bank.hpp"
+
+namespace simka_b200 {
+
+struct SampleSpec {
+    std::string id;
+    std::vector<std::vector<std::string>> groups;  // ';' separated groups of ',' separated files (absolute paths)
+    size_t nbFiles() const { size_t n = 0; for (auto &g : groups) n += g.size(); return n; }
+};
+
+inline std::string dirname_of(const std::string &p) {
+    size_t s = p.rfind('/');
+    return s == std::string::npos ? std::string(".") : (s == 0 ? std::string("/") : p.substr(0, s));
+}
+
+inline std::string real_path(const std::string &p) {
+    char buf[4096];
+    if (realpath(p.c_str(), buf)) return std::string(buf);
+    return p;
+}
+
+// src/core/SimkaAlgorithm.cpp:267-335: spaces removed, "id:groups", groups split on ';', files on ',';
+// relative file names are resolved against the directory of the input file
+inline std::vector<SampleSpec> parse_simka_input(const std::string &filename) {
+    std::ifstream in(filename.c_str());
+    if (!in) throw bank::Exception("Input filename does not exist  (" + filename + ")");
+    const std::string dir = dirname_of(real_path(filename));
+    std::vector<SampleSpec> out;
+    std::string line;
+    while (std::getline(in, line)) {
+        std::string l;
+        for (char c : line) if (c != ' ' && c != '\r' && c != '\t') l.push_back(c);
+        if (l.empty()) continue;
+        size_t colon = l.find(':');
+        if (colon == std::string::npos) throw bank::Exception("bad line in " + filename + ": " + line);
+        SampleSpec s;
+        s.id = l.substr(0, colon);
+        std::string rest = l.substr(colon + 1);
+        size_t c2 = rest.find(':');  // the reference splits on every ':' and keeps part 1
+        if (c2 != std::string::npos) rest = rest.substr(0, c2);
+        std::stringstream gs(rest);
+        std::string grp;
+        while (std::getline(gs, grp, ';')) {
+            std::vector<std::string> files;
+            std::stringstream fs(grp);
+            std::string f;
+            while (std::getline(fs, f, ',')) {
+                if (f.empty()) continue;
+                files.push_back(f[0] == '/' ? f : dir + "/" + f);
+            }
+            s.groups.push_back(files);
+        }
+        out.push_back(s);
+    }
+    return out;
+}
+
+// src/core/SimkaCommons.hpp:317-436
+struct SimkaSequenceFilter {
+    SimkaSequenceFilter(size_t minReadSize = 0, double minShannonIndex = 0) : _minReadSize(minReadSize), _minShannonIndex(minShannonIndex) {}
+    bool operator()(const char *seq, size_t len) const {
+        if (_minReadSize != 0 && len < _minReadSize) return false;
+        if (_minShannonIndex != 0 && getShannonIndex(seq, len) < _minShannonIndex) return false;
+        return true;
+    }
+    bool operator()(bank::Sequence &s) const { return (*this)(s.getDataBuffer(), s.getDataSize()); }
+    // frequencies of A, C, T, G, N (every other character, lower case included, counts as 'A': the reference's
+    // nt2binTab is indexed by the raw character), float accumulation, base-2 logarithm, absolute value
+    static float getShannonIndex(const char *seq, size_t len) {
+        float freqs[5] = {0, 0, 0, 0, 0};
+        for (size_t i = 0; i < len; i++) {
+            int b = 0;
+            switch ((unsigned char)seq[i]) { case 'C': b = 1; break; case 'T': b = 2; break; case 'G': b = 3; break; case 'N': b = 4; break; default: b = 0; }
+            freqs[b] += 1.0f;
+        }
+        float index = 0;
+        for (int i = 0; i < 5; i++) {
+            freqs[i] /= (float)len;
+            if (freqs[i] != 0) index += freqs[i] * std::log(freqs[i]) / std::log(2);  // log(float) / log(int -> double), as the reference's overloads resolve
+        }
+        return std::fabs(index);
+    }
+    size_t _minReadSize;
+    double _minShannonIndex;
+};
+
+// Reads one sample: for every group, the files in order, filtered, at most maxReads reads per group
+// (maxReads == 0: all).  `sink(ptr, len)` receives each selected read.  Returns the number of selected reads.
+template <class Sink>
+inline uint64_t read_sample(const SampleSpec &spec, const SimkaSequenceFilter &filter, uint64_t maxReads, Sink sink) {
+    uint64_t total = 0;
+    std::string data;
+    for (const auto &group : spec.groups) {
+        uint64_t taken = 0;
+        for (const std::string &file : group) {
+            if (maxReads && taken >= maxReads) break;
+            bank::FastxParser parser(file);
+            for (;;) {
+                data.clear();
+                if (!parser.nextRead(data)) break;
+                if (!filter(data.data(), data.size())) continue;
+                sink(data.data(), data.size());
+                taken++;
+                if (maxReads && taken >= maxReads) break;
+            }
+        }
+        total += taken;
+    }
+    return total;
+}
+
+}  // namespace simka_b200

@@ -13,6 +13,9 @@
 #include <vector>
 
 #include "../../include/simka_b200.h"
+#include "host/bank.hpp"
+#include "host/kmer_model.hpp"
+#include "host/simka_input.hpp"
 
 namespace {
 
@@ -300,5 +303,59 @@ uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n
     bad[n_words] = 0xFFFFFFFFu;
     return n_words;
 }
+
+
+// ---- hooks over the host-side mirror classes (tests/test_host_cpu.py compares them with the oracle) ----------
+
+uint64_t simka_host_kmers(const char *seq, uint64_t len, int k, int canonical, uint64_t *out, uint8_t *valid) {
+    using simka_b200::Kmer;
+    try {
+        if (canonical) {
+            Kmer<>::ModelCanonical model((size_t)k);
+            Kmer<>::ModelCanonical::Iterator it(model);
+            it.setData(seq, (size_t)len);
+            uint64_t n = 0;
+            for (it.first(); !it.isDone(); it.next(), n++) { out[n] = it->value().getVal(); valid[n] = it->isValid(); }
+            return n;
+        }
+        Kmer<>::ModelDirect model((size_t)k);
+        std::vector<Kmer<>::KmerDirect> v;
+        model.build(seq, (size_t)len, v);
+        for (size_t i = 0; i < v.size(); i++) { out[i] = v[i].value().getVal(); valid[i] = v[i].isValid(); }
+        return v.size();
+    } catch (...) { return 0; }
+}
+
+uint64_t simka_host_minimizer(uint64_t kmer, int k, int m) {
+    try {
+        simka_b200::Kmer<>::ModelMinimizer<> model((size_t)k, (size_t)m);
+        return model.getMinimizerValue(simka_b200::Kmer<>::Type(kmer));
+    } catch (...) { return ~0ull; }
+}
+
+float simka_host_shannon_index(const char *seq, uint64_t len) { return simka_b200::SimkaSequenceFilter::getShannonIndex(seq, (size_t)len); }
+
+// reads a bank (fasta / fastq / gz / album) through Bank::open + Iterator<Sequence>; malloc'ed outputs
+int64_t simka_host_read_bank(const char *uri, char **seqs, uint64_t **read_off) {
+    using namespace simka_b200::bank;
+    try {
+        std::unique_ptr<IBank> b(Bank::open(uri));
+        std::unique_ptr<Iterator<Sequence>> it(b->iterator());
+        std::string all;
+        std::vector<uint64_t> off(1, 0);
+        for (it->first(); !it->isDone(); it->next()) {
+            all.append(it->item().getDataBuffer() ? it->item().getDataBuffer() : "", it->item().getDataSize());
+            off.push_back(all.size());
+        }
+        *seqs = (char *)malloc(all.size() + 1);
+        *read_off = (uint64_t *)malloc(off.size() * 8);
+        if (!*seqs || !*read_off) return -1;
+        memcpy(*seqs, all.data(), all.size());
+        memcpy(*read_off, off.data(), off.size() * 8);
+        return (int64_t)off.size() - 1;
+    } catch (...) { return -1; }
+}
+
+void simka_host_free(void *p) { free(p); }
 
 }  // extern "C"

@@ -1,0 +1,319 @@
+// simka_main.cpp -- the `simka` command line on top of libsimka_b200.so.
+//
+// Same flags, input-file grammar, output file names and CSV format as the reference's `simka`
+// (src/core/Simka.cpp:25-117, src/SimkaPotara.cpp:36-53, src/core/SimkaDistance.cpp:603-699); the per-sample
+// simkaCount processes and per-partition simkaMerge processes of the reference (src/SimkaPotara.hpp:813-1124)
+// are replaced by in-process calls of the C ABI: every sample is parsed on the host (IBank surface, bank.hpp),
+// 2-bit packed into pinned chunks and streamed to the GPU while the previous chunk is being counted.
+// Errors print "EXCEPTION: <msg>" and return EXIT_FAILURE like the reference's main (src/SimkaPotara.cpp:147-163).
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/simka_b200.h"
+#include "host/bank.hpp"
+#include "host/simka_input.hpp"
+
+using namespace simka_b200;
+
+namespace {
+
+struct Options {
+    std::string in, out = "./simka_results", outTmp;
+    bool keepTmp = false, dataInfo = false, simple = false, complex_ = false;
+    int kmerSize = 21;
+    long long abundanceMin = 2, abundanceMax = 999999999;
+    long long maxReads = -1;
+    size_t minReadSize = 0;
+    double minShannon = 0;
+    int nbCores = 0, verbose = 1, device = 0;
+    long long maxMemory = 5000;
+};
+
+const char *kOneParam[] = {"-in", "-out", "-out-tmp", "-kmer-size", "-abundance-min", "-abundance-max", "-kmer-shannon-index", "-max-reads",
+                           "-min-read-size", "-min-shannon-index", "-nb-cores", "-max-memory", "-max-count", "-max-merge", "-count-cmd",
+                           "-merge-cmd", "-count-file", "-merge-file", "-verbose", "-minimizer-size", "-minimizer-type", "-repartition-type",
+                           "-solidity-kind", "-max-disk", "-storage-type", "-histo-max", "-solidity-custom", "-nb-gpus", "-device", nullptr};
+const char *kNoParam[] = {"-keep-tmp", "-data-info", "-simple-dist", "-complex-dist", "-help", "-version", nullptr};
+
+bool in_list(const char *const *l, const std::string &s) { for (; *l; l++) if (s == *l) return true; return false; }
+
+void usage() {
+    printf("\n[Simka options] (B200 build: counting and merging run in-process on the GPU)\n"
+           "       -in                 (1 arg) :    input file of samples. One sample per line: id1: filename1...\n"
+           "       -out                (1 arg) :    output directory for result files (distance matrices)  [default './simka_results']\n"
+           "       -out-tmp            (1 arg) :    output directory for temporary files\n"
+           "       -keep-tmp           (0 arg) :    keep temporary files\n"
+           "       -data-info          (0 arg) :    compute (and display) information before running Simka, such as the number of reads per dataset\n"
+           "   [distance options]\n"
+           "       -simple-dist        (0 arg) :    compute all simple distances (Chord, Hellinger...)\n"
+           "       -complex-dist       (0 arg) :    compute all complex distances (Jensen-Shannon...)\n"
+           "   [kmer options]\n"
+           "       -kmer-size          (1 arg) :    size of a kmer  [default '21']\n"
+           "       -abundance-min      (1 arg) :    min abundance a kmer need to be considered  [default '2']\n"
+           "       -abundance-max      (1 arg) :    max abundance a kmer can have to be considered  [default '999999999']\n"
+           "       -kmer-shannon-index (1 arg) :    minimal Shannon index a kmer should have to be kept (no effect, as in the reference)  [default '0']\n"
+           "   [read options]\n"
+           "       -max-reads          (1 arg) :    maximum number of reads per sample to process. Can be -1: use all reads. Can be 0: estimate it  [default '-1']\n"
+           "       -min-read-size      (1 arg) :    minimal size a read should have to be kept  [default '0']\n"
+           "       -min-shannon-index  (1 arg) :    minimal Shannon index a read should have to be kept. Float in [0,2]  [default '0']\n"
+           "   [core options]\n"
+           "       -nb-cores           (1 arg) :    number of host threads for parsing / packing  [default '0' = all]\n"
+           "       -max-memory         (1 arg) :    max memory (MB); accepted for compatibility  [default '5000']\n"
+           "       -device             (1 arg) :    CUDA device ordinal  [default '0']\n"
+           "   [cluster options] -max-count -max-merge -count-cmd -merge-cmd -count-file -merge-file : accepted and ignored\n"
+           "       -verbose            (1 arg) :    verbosity level  [default '1']\n\n");
+}
+
+Options parse_args(int argc, char **argv) {
+    Options o;
+    std::map<std::string, std::string> kv;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (in_list(kNoParam, a)) { kv[a] = "1"; continue; }
+        if (in_list(kOneParam, a)) {
+            if (i + 1 >= argc) throw bank::Exception("Option '" + a + "' needs an argument");
+            kv[a] = argv[++i];
+            continue;
+        }
+        throw bank::Exception("Unknown parameter '" + a + "'");
+    }
+    if (kv.count("-help")) { usage(); exit(EXIT_SUCCESS); }
+    if (kv.count("-version")) { printf("%s\n", simka_b200_version()); exit(EXIT_SUCCESS); }
+    if (!kv.count("-in")) throw bank::Exception("Option '-in' is mandatory");
+    if (!kv.count("-out-tmp")) throw bank::Exception("Option '-out-tmp' is mandatory");
+    o.in = kv["-in"];
+    o.outTmp = kv["-out-tmp"];
+    if (kv.count("-out")) o.out = kv["-out"];
+    o.keepTmp = kv.count("-keep-tmp");
+    o.dataInfo = kv.count("-data-info");
+    o.simple = kv.count("-simple-dist");
+    o.complex_ = kv.count("-complex-dist");
+    if (kv.count("-kmer-size")) o.kmerSize = atoi(kv["-kmer-size"].c_str());
+    if (kv.count("-abundance-min")) o.abundanceMin = atoll(kv["-abundance-min"].c_str());
+    if (kv.count("-abundance-max")) o.abundanceMax = atoll(kv["-abundance-max"].c_str());
+    if (kv.count("-max-reads")) o.maxReads = atoll(kv["-max-reads"].c_str());
+    if (kv.count("-min-read-size")) o.minReadSize = (size_t)atoll(kv["-min-read-size"].c_str());
+    if (kv.count("-min-shannon-index")) o.minShannon = atof(kv["-min-shannon-index"].c_str());
+    if (kv.count("-nb-cores")) o.nbCores = atoi(kv["-nb-cores"].c_str());
+    if (kv.count("-max-memory")) o.maxMemory = atoll(kv["-max-memory"].c_str());
+    if (kv.count("-verbose")) o.verbose = atoi(kv["-verbose"].c_str());
+    if (kv.count("-device")) o.device = atoi(kv["-device"].c_str());
+    // src/SimkaPotara.hpp:383-387
+    if (o.maxMemory < 500) throw bank::Exception("Please allocate more memory (minimum is 500 MB) with the option -max-memory");
+    o.minShannon = std::max(o.minShannon, 0.0);
+    o.minShannon = std::min(o.minShannon, 2.0);  // src/core/SimkaAlgorithm.cpp:202-204
+    if (o.kmerSize < 2 || o.kmerSize > 31)
+        throw bank::Exception("this build supports -kmer-size 2..31 (span 32); got " + std::to_string(o.kmerSize));
+    return o;
+}
+
+void mkdir_p(const std::string &d) {
+    std::string cur;
+    for (size_t i = 0; i <= d.size(); i++) {
+        if (i == d.size() || d[i] == '/') {
+            if (!cur.empty() && cur != "." && cur != "..") {
+                if (mkdir(cur.c_str(), 0755) != 0 && errno != EEXIST) throw bank::Exception("Cannot create dir " + cur);
+            }
+        }
+        if (i < d.size()) cur.push_back(d[i]);
+    }
+}
+void rm_rf(const std::string &d) {
+    if (d.empty() || d == "/") return;
+    std::string cmd = "rm -rf '" + d + "'";
+    if (system(cmd.c_str()) != 0) {}
+}
+void write_text(const std::string &path, const std::string &text) {
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) throw bank::Exception("cannot write " + path);
+    fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
+}
+
+struct PinnedChunk {
+    uint64_t *packed = nullptr;
+    uint32_t *bad = nullptr;
+    uint64_t cap_words = 0;
+    void reserve(uint64_t words) {
+        if (words + 1 <= cap_words) return;
+        release();
+        cap_words = words + words / 8 + 1024;
+        void *p = nullptr, *b = nullptr;
+        if (simka_gpu_host_alloc(&p, cap_words * 8) != SIMKA_OK || simka_gpu_host_alloc(&b, cap_words * 4) != SIMKA_OK)
+            throw bank::Exception("cannot allocate pinned host memory");
+        packed = (uint64_t *)p;
+        bad = (uint32_t *)b;
+    }
+    void release() {
+        if (packed) simka_gpu_host_free(packed);
+        if (bad) simka_gpu_host_free(bad);
+        packed = nullptr; bad = nullptr; cap_words = 0;
+    }
+};
+
+void check(simka_ctx *ctx, int rc, const char *what) {
+    if (rc != SIMKA_OK) throw bank::Exception(std::string(what) + ": " + (ctx ? simka_gpu_last_error(ctx) : "failed") + " (code " + std::to_string(rc) + ")");
+}
+
+int run(int argc, char **argv) {
+    Options o = parse_args(argc, argv);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<SampleSpec> samples = parse_simka_input(o.in);
+    if (samples.empty()) throw bank::Exception("no sample in " + o.in);
+    const size_t N = samples.size();
+    const int nthreads = o.nbCores > 0 ? o.nbCores : (int)std::thread::hardware_concurrency();
+
+    // directory layout of the reference (src/core/SimkaAlgorithm.cpp:214-239, Appendix A of SURVEY.md)
+    const std::string tmp = o.outTmp + "/simka_output_temp";
+    mkdir_p(o.out);
+    mkdir_p(tmp + "/input");
+    mkdir_p(tmp + "/count_synchro");
+    {
+        std::string ids, list;
+        for (const SampleSpec &s : samples) {
+            ids += s.id + "\n";
+            std::string album;
+            for (auto &g : s.groups) for (auto &f : g) album += f + "\n";
+            if (!album.empty()) album.pop_back();
+            write_text(tmp + "/input/" + s.id, album);
+            list += tmp + "/input//" + s.id + "\n";
+        }
+        if (!list.empty()) list.pop_back();
+        write_text(tmp + "/input/__input_simka__", list);
+        write_text(tmp + "/datasetIds", ids);
+    }
+    SimkaSequenceFilter filter(o.minReadSize, o.minShannon);
+
+    // -max-reads: -1 = all, N = at most N per group, 0 = (min + mean) / 2 over the samples
+    // (src/core/SimkaAlgorithm.cpp:377-445; the reference ESTIMATES the read counts from the head of each file,
+    //  here they are counted exactly)
+    uint64_t maxReads = 0;
+    if (o.maxReads > 0) maxReads = (uint64_t)o.maxReads;
+    if (o.maxReads == 0 || o.dataInfo) {
+        uint64_t mn = ~0ull, sum = 0;
+        for (const SampleSpec &s : samples) {
+            uint64_t n = read_sample(s, SimkaSequenceFilter(), 0, [](const char *, size_t) {});
+            if (o.dataInfo || o.verbose) printf("\t%s: %llu reads\n", s.id.c_str(), (unsigned long long)n);
+            mn = std::min(mn, n);
+            sum += n;
+        }
+        if (o.maxReads == 0) {
+            maxReads = (mn + sum / N) / 2;
+            if (o.verbose) printf("Reads per sample used up to: %llu\n\n", (unsigned long long)maxReads);
+        }
+    }
+
+    simka_params prm;
+    memset(&prm, 0, sizeof prm);
+    prm.kmer_size = o.kmerSize;
+    prm.nb_samples = (int32_t)N;
+    prm.abundance_min = o.abundanceMin;
+    prm.abundance_max = o.abundanceMax;
+    prm.simple_dist = o.simple;
+    prm.complex_dist = o.complex_;
+    prm.device = o.device;
+    simka_ctx *ctx = nullptr;
+    int rc = simka_gpu_create(&ctx, &prm);
+    if (rc != SIMKA_OK) throw bank::Exception("simka_gpu_create failed (code " + std::to_string(rc) + "): a CUDA device is required, there is no CPU path");
+
+    // stage 1: per sample, parse -> pack (pinned) -> push; chunks of <= CHUNK_BASES bases, every chunk of a sample
+    // needs its own pinned buffer until finish_sample, buffers are reused by the next sample
+    const uint64_t CHUNK_BASES = 1ull << 29;
+    std::vector<PinnedChunk> pool;
+    std::vector<simka_sample_totals> totals(N);
+    std::string seqs;
+    std::vector<uint64_t> off;
+    for (size_t i = 0; i < N; i++) {
+        size_t chunk = 0;
+        seqs.clear();
+        off.assign(1, 0);
+        uint64_t nreads_total = 0;
+        auto flush = [&]() {
+            if (off.size() <= 1) return;
+            const uint64_t nr = off.size() - 1;
+            const uint64_t words = simka_pack_words(seqs.size(), nr);
+            if (chunk >= pool.size()) pool.emplace_back();
+            pool[chunk].reserve(words);
+            simka_pack_reads(seqs.data(), off.data(), nr, pool[chunk].packed, pool[chunk].bad, nthreads);
+            check(ctx, simka_gpu_push_reads(ctx, (int)i, pool[chunk].packed, pool[chunk].bad, words, nr), "simka_gpu_push_reads");
+            chunk++;
+            seqs.clear();
+            off.assign(1, 0);
+        };
+        nreads_total = read_sample(samples[i], filter, maxReads, [&](const char *p, size_t n) {
+            seqs.append(p, n);
+            off.push_back(seqs.size());
+            if (seqs.size() >= CHUNK_BASES) flush();
+        });
+        flush();
+        check(ctx, simka_gpu_finish_sample(ctx, (int)i, &totals[i]), "simka_gpu_finish_sample");
+        totals[i].nb_reads = nreads_total;
+        // count_synchro/<id>.ok: nbReads, nbDistinct, sum c, sum c^2 (src/SimkaCount.cpp:355-368)
+        char buf[256];
+        snprintf(buf, sizeof buf, "%llu\n%llu\n%llu\n%llu\n", (unsigned long long)totals[i].nb_reads, (unsigned long long)totals[i].nb_distinct,
+                 (unsigned long long)totals[i].nb_kmers, (unsigned long long)totals[i].chord_n2);
+        write_text(tmp + "/count_synchro/" + samples[i].id + ".ok", buf);
+        if (o.verbose) printf("Counting dataset %zu (%s): %llu reads, %llu distinct solid k-mers, %llu solid k-mers\n", i, samples[i].id.c_str(),
+                              (unsigned long long)totals[i].nb_reads, (unsigned long long)totals[i].nb_distinct, (unsigned long long)totals[i].nb_kmers);
+    }
+    check(ctx, simka_gpu_set_totals(ctx, totals.data()), "simka_gpu_set_totals");
+
+    // stage 2 + final statistics
+    check(ctx, simka_gpu_merge_and_accumulate(ctx), "simka_gpu_merge_and_accumulate");
+    const size_t nn = N * N, ns = N * (N + 1) / 2;
+    std::vector<uint64_t> u(2 * ns + 6 * nn);
+    std::vector<double> kl(nn);
+    std::vector<simka_sample_totals> gt(N);
+    simka_stats_view v;
+    memset(&v, 0, sizeof v);
+    v.totals = gt.data();
+    v.distinct_shared = &u[0];
+    v.braycurtis_num = &u[ns];
+    v.nb_shared = &u[2 * ns];
+    v.chord_ninj = &u[2 * ns + nn];
+    v.hellinger = &u[2 * ns + 2 * nn];
+    v.kulczynski = &u[2 * ns + 3 * nn];
+    v.canberra = &u[2 * ns + 4 * nn];
+    v.whittaker = &u[2 * ns + 5 * nn];
+    v.kullback_leibler = kl.data();
+    check(ctx, simka_gpu_get_stats(ctx, &v), "simka_gpu_get_stats");
+    std::vector<const char *> ids;
+    for (const SampleSpec &s : samples) ids.push_back(s.id.c_str());
+    rc = simka_write_matrices(&v, ids.data(), o.out.c_str());
+    if (rc != SIMKA_OK) throw bank::Exception("cannot write the matrices to " + o.out);
+    if (o.verbose) {
+        simka_timings tm;
+        simka_gpu_get_timings(ctx, &tm);
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("\nNb distinct kmers: %llu   shared by >= 2 samples: %llu\n", (unsigned long long)v.nb_distinct_kmers, (unsigned long long)v.nb_shared_kmers);
+        printf("GPU time: %.1f ms counting + %.1f ms merging, %llu kernel launches; wall %.2f s\n", tm.samples_ms, tm.merge_ms,
+               (unsigned long long)tm.kernel_launches, wall);
+        printf("Output dir: %s\n", o.out.c_str());
+    }
+    simka_gpu_destroy(ctx);
+    for (auto &c : pool) c.release();
+    if (!o.keepTmp) rm_rf(tmp);
+    return EXIT_SUCCESS;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    try {
+        return run(argc, argv);
+    } catch (const std::exception &e) {
+        std::cout << "EXCEPTION: " << e.what() << std::endl;
+        return EXIT_FAILURE;
+    }
+}

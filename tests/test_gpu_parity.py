@@ -231,3 +231,64 @@ def test_sample_sharded_exchange_equals_whole(world):
     for st in results[1:]:
         total += st
     assert_stats_equal(total, run)
+
+
+@pytest.mark.parametrize("k,t", [(31, 2), (21, 0)])
+def test_simka_cli_reproduces_truth(tmp_path, golden_dir, k, t):
+    """The reference's end-to-end test (tests/simple_test.py:25-66,93-119) against the `simka` binary of this build:
+    same command line, gunzipped matrices byte-identical to the truth files."""
+    import gzip
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    out = tmp_path / "results"
+    cmd = [str(SIMKA_BIN), "-in", os.path.join(golden_dir, "example", "simka_input.txt"), "-out", str(out), "-out-tmp", str(tmp_path / "tmp"),
+           "-simple-dist", "-complex-dist", "-kmer-size", str(k), "-abundance-min", str(t), "-verbose", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    tdir = os.path.join(golden_dir, "truth", f"results_k{k}_t{t}")
+    checked = 0
+    for f in sorted(os.listdir(tdir)):
+        got = gzip.open(out / (f + ".gz"), "rt").read()
+        assert got == open(os.path.join(tdir, f)).read(), f
+        checked += 1
+    assert checked == 20
+    assert not (tmp_path / "tmp" / "simka_output_temp").exists()  # temp dir removed unless -keep-tmp
+
+
+def test_simka_cli_max_reads_and_filters(tmp_path, golden_dir):
+    """-max-reads / -min-read-size / -min-shannon-index through the CLI == the same selection done in Python + the oracle"""
+    import gzip
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    out = tmp_path / "results"
+    inp = os.path.join(golden_dir, "example", "simka_input.txt")
+    cmd = [str(SIMKA_BIN), "-in", inp, "-out", str(out), "-out-tmp", str(tmp_path / "tmp"), "-kmer-size", "21", "-abundance-min", "1",
+           "-max-reads", "50", "-min-read-size", "90", "-min-shannon-index", "1.5", "-keep-tmp", "-verbose", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    L = simka_b200._lib.load()
+    samples, ids = [], []
+    for ident, groups in oracle.parse_simka_input(inp):
+        ids.append(ident)
+        reads = []
+        for grp in groups:
+            taken = 0
+            for f in grp:
+                d, o = oracle.read_fastx(f)
+                for i in range(len(o) - 1):
+                    rd = bytes(d[int(o[i]):int(o[i + 1])])
+                    if taken >= 50:
+                        break
+                    if len(rd) < 90 or L.simka_host_shannon_index(rd, len(rd)) < 1.5:
+                        continue
+                    reads.append(rd)
+                    taken += 1
+        from helpers import reads_to_arrays
+        samples.append(reads_to_arrays(reads))
+    run = oracle_run(samples, 21, 1, simple=False, complex_=False)
+    names = run.matrix_names()
+    for m, name in enumerate(names):
+        got = gzip.open(out / (name + ".csv.gz"), "rt").read()
+        assert got == run.csv(m, ids), name
+    ok = (tmp_path / "tmp" / "simka_output_temp" / "count_synchro" / "A.ok").read_text().split()
+    assert [int(x) for x in ok] == run.all_totals()[0].tolist()

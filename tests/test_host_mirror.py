@@ -1,0 +1,132 @@
+"""CPU tests of the host-side mirror of the reference's input surface (simka_b200/csrc/host/*.hpp): the
+Kmer<32>::Model* iteration, the minimizer, the Shannon filter, Bank::open / Iterator<Sequence>, and the
+argument handling of the `simka` command line.  Checked against the oracle and the reference's own
+known-answer vectors."""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from simka_b200 import _lib
+from simka_b200.build import SIMKA_BIN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def host_kmers(seq: bytes, k: int, canonical=True):
+    L = _lib.load()
+    n = max(1, len(seq))
+    out = np.zeros(n, np.uint64)
+    valid = np.zeros(n, np.uint8)
+    m = L.simka_host_kmers(seq, len(seq), k, int(canonical), out.ctypes.data_as(_lib.u64p), valid.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out[:m], valid[:m].astype(bool)
+
+
+def test_testkmer_known_answers():
+    """GT/unit/src/kmer/TestKmer.cpp:141-147,178-191"""
+    seq = b"CATTGATAGTGG"
+    d, v = host_kmers(seq, 3, canonical=False)
+    assert d.tolist() == [18, 10, 43, 44, 50, 8, 35, 14, 59, 47] and v.all()
+    c, v = host_kmers(seq, 3, canonical=True)
+    assert c.tolist() == [11, 2, 16, 36, 9, 8, 24, 6, 17, 20] and v.all()
+
+
+@pytest.mark.parametrize("k", [3, 15, 21, 31])
+def test_model_matches_oracle(k):
+    rng = np.random.default_rng(k)
+    alpha = np.frombuffer(b"ACGTacgtNnX-", np.uint8)
+    p = np.array([20, 20, 20, 20, 3, 3, 3, 3, 1, 1, 1, 1], float)
+    for n in [0, k - 1, k, k + 1, 200, 1000]:
+        seq = alpha[rng.choice(len(alpha), size=n, p=p / p.sum())].tobytes()
+        for canonical in (True, False):
+            a, av = host_kmers(seq, k, canonical)
+            if n < k:
+                assert len(a) == 0
+                continue
+            b, bv = (oracle.canonical_kmers if canonical else oracle.direct_kmers)(seq, k)
+            np.testing.assert_array_equal(av, bv.astype(bool))
+            np.testing.assert_array_equal(a[av], b[av])  # values of invalid windows are unspecified in the reference too
+
+
+def test_minimizer_matches_oracle():
+    L, O = _lib.load(), oracle.lib()
+    rng = np.random.default_rng(5)
+    for k, m in [(31, 7), (21, 7), (15, 5), (11, 8)]:
+        for v in rng.integers(0, 1 << (2 * k), size=300, dtype=np.uint64).tolist() + [0, (1 << (2 * k)) - 1]:
+            assert L.simka_host_minimizer(v, k, m) == O.orc_minimizer(v, k, m)
+
+
+def test_shannon_index():
+    L = _lib.load()
+    assert L.simka_host_shannon_index(b"AAAAAAAA", 8) == 0.0
+    assert abs(L.simka_host_shannon_index(b"ACGTACGT", 8) - 2.0) < 1e-6
+    assert abs(L.simka_host_shannon_index(b"AACC", 4) - 1.0) < 1e-6
+    # lower case counts as 'A', as in the reference's table (src/core/SimkaCommons.hpp:400-411)
+    assert L.simka_host_shannon_index(b"acgt", 4) == 0.0
+
+
+def read_bank(uri):
+    L = _lib.load()
+    ps, po = C.c_void_p(), C.c_void_p()
+    n = L.simka_host_read_bank(os.fsencode(uri), C.byref(ps), C.byref(po))
+    assert n >= 0, uri
+    off = np.ctypeslib.as_array((C.c_uint64 * (n + 1)).from_address(po.value)).copy()
+    total = int(off[-1])
+    seqs = np.ctypeslib.as_array((C.c_uint8 * max(total, 1)).from_address(ps.value))[:total].copy()
+    L.simka_host_free(ps)
+    L.simka_host_free(po)
+    return seqs, off
+
+
+def test_bank_reads_like_the_oracle(tmp_path, golden_dir):
+    ex = os.path.join(golden_dir, "example")
+    files = [os.path.join(ex, f) for f in ("A.fasta", "B.fasta", "C.fasta", "D_paired_1.fasta", "D_paired_2.fasta")]
+    for f in files:
+        s, o = read_bank(f)
+        es, eo = oracle.read_fastx(f)
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(o, eo)
+    # gz, multi-line fasta, fastq (quality line starting with '@'), CRLF, a last record without newline
+    multi = tmp_path / "m.fa"
+    multi.write_bytes(b">r1 c\nACGT\nAC\n\nGG\n>r2\n\n>r3\nTTTT\r\nAA\r\n>r4\nNNNN")
+    fq = tmp_path / "q.fastq"
+    fq.write_bytes(b"@q1\nACGTAC\n+\n@IIII+\n@q2\nGGGTTT\n+q2\nIIIIII\n")
+    gz = tmp_path / "g.fa.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(open(files[0], "rb").read())
+    for f in (multi, fq, gz):
+        s, o = read_bank(str(f))
+        es, eo = oracle.read_fastx(str(f))
+        np.testing.assert_array_equal(s, es)
+        np.testing.assert_array_equal(o, eo)
+    s, o = read_bank(str(fq))
+    assert bytes(s) == b"ACGTACGGGTTT" and o.tolist() == [0, 6, 12]
+    # album: file of file names, relative to the album
+    album = tmp_path / "album.txt"
+    album.write_text("m.fa\n" + str(fq) + "\n")
+    s, o = read_bank(str(album))
+    s1, o1 = read_bank(str(multi))
+    s2, o2 = read_bank(str(fq))
+    assert bytes(s) == bytes(s1) + bytes(s2) and len(o) == len(o1) + len(o2) - 1
+
+
+def test_cli_argument_handling(tmp_path):
+    """same conventions as the reference's main: EXCEPTION: <msg> on stdout, EXIT_FAILURE (src/SimkaPotara.cpp:147-163)"""
+    exe = str(SIMKA_BIN)
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "-help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "-abundance-min" in r.stdout and "-complex-dist" in r.stdout
+    r = subprocess.run([exe, "-in", "x"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("EXCEPTION: ") and "-out-tmp" in r.stdout
+    r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-bogus"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown parameter" in r.stdout
+    r = subprocess.run([exe, "-in", "/nonexistent", "-out-tmp", str(tmp_path), "-out", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode == 1 and "does not exist" in r.stdout
+    r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-max-memory", "100"], capture_output=True, text=True)
+    assert r.returncode == 1 and "memory" in r.stdout
+    r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-kmer-size", "40"], capture_output=True, text=True)
+    assert r.returncode == 1 and "kmer-size" in r.stdout
