@@ -30,7 +30,8 @@ SIMKA_HD uint64_t revcomp(uint64_t x, int k) {
     return x >> (64 - 2 * k);
 }
 
-// Invertible mixing of a 2k-bit value: xorshift / odd multiply rounds modulo 2^(2k).
+// Invertible mixing of a 2k-bit value: xorshift, odd multiply modulo 2^(2k), xorshift (one round: the extraction
+// kernel is ALU-bound and every input bit still reaches the top bits through the carry chain of the multiply).
 // Top bits select the bucket, so canonical-k-mer skew (min(fwd,rev) favours small values) and
 // low-complexity repeats spread evenly over buckets.
 struct Mix {
@@ -45,13 +46,9 @@ SIMKA_HD uint64_t mix_fwd(uint64_t x, const Mix &p) {
     x ^= x >> p.shift;
     x = (x * p.m1) & p.mask;
     x ^= x >> p.shift;
-    x = (x * p.m2) & p.mask;
-    x ^= x >> p.shift;
     return x;
 }
 SIMKA_HD uint64_t mix_inv(uint64_t x, const Mix &p) {
-    x ^= x >> p.shift;
-    x = (x * p.i2) & p.mask;
     x ^= x >> p.shift;
     x = (x * p.i1) & p.mask;
     x ^= x >> p.shift;

@@ -160,16 +160,15 @@ __global__ void __launch_bounds__(BLOCK) k_pack_ascii(const char *__restrict__ s
 // Thread t owns packed word t = start positions 32t..32t+31; the 62-bit window slides through the
 // (word t, word t+1) register pair, the reverse strand is rolled alongside.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT_ONLY>
+template <bool COUNT_ONLY, bool SHARDED>
 __global__ void __launch_bounds__(BLOCK, 2)
 k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t n_words, KParams kp, int b1_bits,
           uint32_t *__restrict__ g_hist, const uint64_t *__restrict__ bucket_base, uint32_t *__restrict__ bucket_cursor,
           uint64_t bucket_cap, int *__restrict__ overflow_flag, uint64_t *__restrict__ keys_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);           // [MAX_B] counts, then tile-local starts
-    uint32_t *gbase = hist + MAX_B;                                    // [MAX_B] reserved global offsets
-    uint32_t *cnt = gbase + MAX_B;                                     // [MAX_B] counts copy
-    uint32_t *warp_tmp = cnt + MAX_B;                                  // [16]
+    uint64_t *dst = reinterpret_cast<uint64_t *>(smem_raw);            // [MAX_B] global destination of a bucket's run minus its tile-local start
+    uint32_t *hist = reinterpret_cast<uint32_t *>(dst + MAX_B);        // [MAX_B] counts, then tile-local starts
+    uint32_t *warp_tmp = hist + MAX_B;                                 // [16]
     uint64_t *sorted = reinterpret_cast<uint64_t *>(warp_tmp + 16);    // [L1_TILE] (scatter mode only)
 
     const int tid = threadIdx.x;
@@ -186,6 +185,16 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
         lo = seq[t + 1];
         bm = ((uint64_t)bad[t] << 32) | bad[t + 1];
     }
+    // window j (bases j..j+k-1 of the 64 in (hi,lo)) is valid iff none of its bases is bad: OR of the k left
+    // shifts of the bad mask, built by doubling; bit 63-j of the result belongs to start position j
+    uint32_t okmask;
+    {
+        uint64_t r = bm;
+        int built = 1;
+        while (built * 2 <= k) { r |= r << built; built *= 2; }
+        if (built < k) r |= r << (k - built);
+        okmask = ~(uint32_t)(r >> 32);
+    }
     uint64_t keys[L1_KPT];
     uint32_t ranks[L1_KPT / 2];
     uint32_t vmask = 0;
@@ -194,12 +203,12 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
 #pragma unroll
     for (int j = 0; j < L1_KPT; j++) {
         const uint64_t fwd = hi >> (64 - 2 * k);
-        const bool ok = ((bm << j) >> (64 - k)) == 0;
         if (j == 0) rev = simka::revcomp(fwd, k);
         else rev = (rev >> 2) | ((uint64_t)((fwd & 3) ^ 2) << (2 * k - 2));
         const uint64_t canon = fwd < rev ? fwd : rev;
         const uint64_t h = simka::mix_fwd(canon, kp.mix);
-        const bool keep = ok && shard_keep(h, kp);
+        bool keep = (okmask >> (31 - j)) & 1u;
+        if (SHARDED) keep = keep && shard_keep(h, kp);
         keys[j] = h;
         if (keep) {
             vmask |= 1u << j;
@@ -223,16 +232,19 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
     }
     for (int i = tid; i < nb; i += BLOCK) {
         uint32_t c = hist[i];
-        cnt[i] = c;
-        uint32_t g = c ? atomicAdd(&bucket_cursor[i], c) : 0;
+        uint64_t g = c ? atomicAdd(&bucket_cursor[i], c) : 0;
         // optimistic single pass: buckets have a fixed capacity; a tile that does not fit drops its keys of
         // that bucket and raises the flag (the host then redoes the sample with the exact two-pass path)
-        if (c && (uint64_t)g + c > bucket_cap) { g = 0xFFFFFFFFu; *overflow_flag = 1; }
-        gbase[i] = g;
+        if (c && g + c > bucket_cap) { g = ~0ull; *overflow_flag = 1; }
+        dst[i] = g;
     }
     __syncthreads();
     block_exclusive_scan(hist, nb, warp_tmp);
     const uint32_t total = warp_tmp[BLOCK / 32];
+    for (int i = tid; i < nb; i += BLOCK) {
+        const uint64_t g = dst[i];
+        if (g != ~0ull) dst[i] = bucket_base[i] + g - hist[i];
+    }
 #pragma unroll
     for (int j = 0; j < L1_KPT; j++) {
         if (vmask & (1u << j)) {
@@ -242,10 +254,9 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
     }
     __syncthreads();
     for (uint32_t i = tid; i < total; i += BLOCK) {
-        uint64_t h = sorted[i];
-        uint32_t b = (uint32_t)(h >> bshift);
-        const uint32_t g = gbase[b];
-        if (g != 0xFFFFFFFFu) keys_out[bucket_base[b] + g + (i - hist[b])] = h;
+        const uint64_t h = sorted[i];
+        const uint64_t d = dst[(uint32_t)(h >> bshift)];
+        if (d != ~0ull) keys_out[d + i] = h;
     }
 }
 
@@ -390,12 +401,13 @@ __global__ void k_tiles_per_bucket(const uint32_t *__restrict__ count, uint32_t 
 // (GC/kmer/impl/PartitionsCommand.cpp:1253-1378), which splits a partition into radix bins.
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ bucket_base /*[B1] begin*/,
              const uint32_t *__restrict__ bucket_cnt /*[B1]*/, const uint64_t *__restrict__ tile_start /*[B1+1]*/, int b1_bits, int b2_bits, int W,
              uint32_t *__restrict__ fine_hist, const uint64_t *__restrict__ fine_off, uint32_t *__restrict__ fine_cursor,
              uint64_t *__restrict__ keys_out) {
-    __shared__ uint32_t hist[MAX_B], gbase[MAX_B], warp_tmp[16];
+    __shared__ uint32_t hist[MAX_B], warp_tmp[16];
+    __shared__ __align__(16) uint64_t dst[COUNT_ONLY ? 1 : MAX_B];   // global destination of a bin's run minus its tile-local start
     __shared__ __align__(16) uint64_t sorted[COUNT_ONLY ? 1 : L2_TILE];
     __shared__ int s_bucket;
     const int tid = threadIdx.x;
@@ -424,11 +436,13 @@ k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ 
 #pragma unroll
     for (int j = 0; j < L2_KPT; j++) {
         uint64_t i = tbeg + (uint64_t)j * BLOCK + tid;
-        if (i < bend) {
-            uint64_t h = keys_in[i];
-            keys[j] = h;
-            vmask |= 1u << j;
-            uint32_t r = atomicAdd(&hist[(uint32_t)(h >> shift) & m2], 1u);
+        keys[j] = i < bend ? keys_in[i] : 0;
+        if (i < bend) vmask |= 1u << j;
+    }
+#pragma unroll
+    for (int j = 0; j < L2_KPT; j++) {
+        if (vmask & (1u << j)) {
+            uint32_t r = atomicAdd(&hist[(uint32_t)(keys[j] >> shift) & m2], 1u);
             if (!COUNT_ONLY) { if (j & 1) ranks[j >> 1] |= r << 16; else ranks[j >> 1] = r; }
         } else if (!COUNT_ONLY && !(j & 1)) ranks[j >> 1] = 0;
     }
@@ -438,10 +452,11 @@ k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ 
         for (int i = tid; i < nb2; i += BLOCK) { uint32_t c = hist[i]; if (c) atomicAdd(&fine_hist[fbase + i], c); }
         return;
     }
-    for (int i = tid; i < nb2; i += BLOCK) { uint32_t c = hist[i]; gbase[i] = c ? atomicAdd(&fine_cursor[fbase + i], c) : 0; }
+    for (int i = tid; i < nb2; i += BLOCK) { uint32_t c = hist[i]; dst[i] = c ? atomicAdd(&fine_cursor[fbase + i], c) : 0; }
     __syncthreads();
     block_exclusive_scan(hist, nb2, warp_tmp);
     const uint32_t total = warp_tmp[BLOCK / 32];
+    for (int i = tid; i < nb2; i += BLOCK) dst[i] = fine_off[fbase + i] + dst[i] - hist[i];
 #pragma unroll
     for (int j = 0; j < L2_KPT; j++)
         if (vmask & (1u << j)) {
@@ -450,9 +465,8 @@ k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ 
         }
     __syncthreads();
     for (uint32_t i = tid; i < total; i += BLOCK) {
-        uint64_t h = sorted[i];
-        uint32_t b = (uint32_t)(h >> shift) & m2;
-        keys_out[fine_off[fbase + b] + gbase[b] + (i - hist[b])] = h;
+        const uint64_t h = sorted[i];
+        keys_out[dst[(uint32_t)(h >> shift) & m2] + i] = h;
     }
 }
 
@@ -1553,7 +1567,9 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
         ok = ok && cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming) == cudaSuccess;
     for (auto &e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_extract<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ok = ok && cudaFuncSetAttribute(k_extract<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_extract<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(p->nb_samples)) == cudaSuccess;
     ok = ok && ctx->d_small.reserve(64) == 0;
@@ -1767,21 +1783,26 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         CK(cudaMemsetAsync(ctx->d_fine_cursor.p, 0, (size_t)nbins * 4, st));
 
         const unsigned g1 = (unsigned)((n_words + BLOCK - 1) / BLOCK);
+        const bool sharded = ctx->kp.shard_count > 1;
         const uint64_t *seq = sl->ext_packed ? sl->ext_packed : sl->packed.as<uint64_t>();
         const uint32_t *bad = sl->ext_bad ? sl->ext_bad : sl->bad.as<uint32_t>();
         // K1 (count / scan /) scatter
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
         if (exact) {
-            k_extract<true><<<g1, BLOCK, 3 * MAX_B * 4 + 64, st>>>(seq, bad, n_words, ctx->kp, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, 0, nullptr, nullptr);
+            if (sharded) k_extract<true, true><<<g1, BLOCK, 3 * MAX_B * 4 + 64, st>>>(seq, bad, n_words, ctx->kp, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, 0, nullptr, nullptr);
+            else k_extract<true, false><<<g1, BLOCK, 3 * MAX_B * 4 + 64, st>>>(seq, bad, n_words, ctx->kp, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, 0, nullptr, nullptr);
             ctx->launches++;
         }
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT + 1], st));
         if (exact) launch_scan(ctx, ctx->d_hist1.as<uint32_t>(), ctx->d_base1.as<uint64_t>(), nb1);
         else k_fill_bases<<<(nb1 + 256) / 256, 256, 0, st>>>(ctx->d_base1.as<uint64_t>(), (int)nb1, cap);
         CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER], st));
-        k_extract<false><<<g1, BLOCK, 3 * MAX_B * 4 + 64 + L1_TILE * 8, st>>>(seq, bad, n_words, ctx->kp, b1_bits, nullptr, ctx->d_base1.as<uint64_t>(),
-                                                                           ctx->d_cursor1.as<uint32_t>(), exact ? ~0ull : cap, d_overflow,
-                                                                           ctx->d_keysA.as<uint64_t>());
+        if (sharded) k_extract<false, true><<<g1, BLOCK, 3 * MAX_B * 4 + 64 + L1_TILE * 8, st>>>(seq, bad, n_words, ctx->kp, b1_bits, nullptr, ctx->d_base1.as<uint64_t>(),
+                                                                                 ctx->d_cursor1.as<uint32_t>(), exact ? ~0ull >> 1 : cap, d_overflow,
+                                                                                 ctx->d_keysA.as<uint64_t>());
+        else k_extract<false, false><<<g1, BLOCK, 3 * MAX_B * 4 + 64 + L1_TILE * 8, st>>>(seq, bad, n_words, ctx->kp, b1_bits, nullptr, ctx->d_base1.as<uint64_t>(),
+                                                                                  ctx->d_cursor1.as<uint32_t>(), exact ? ~0ull >> 1 : cap, d_overflow,
+                                                                                  ctx->d_keysA.as<uint64_t>());
         CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER + 1], st));
         // per-bucket key counts: the cursors of the scatter pass (== the histogram in exact mode)
         const uint32_t *cnt1 = ctx->d_cursor1.as<uint32_t>();
