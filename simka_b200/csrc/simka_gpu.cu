@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(BLOCK) k_pack_ascii(const char *__restrict__ s
 // Thread t owns packed word t = start positions 32t..32t+31; the 62-bit window slides through the
 // (word t, word t+1) register pair, the reverse strand is rolled alongside.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT_ONLY, bool SHARDED>
+template <bool COUNT_ONLY, bool SHARDED, bool BIGK>
 __global__ void __launch_bounds__(BLOCK, 2)
 k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t n_words, KParams kp, int b1_bits,
           uint32_t *__restrict__ g_hist, const uint64_t *__restrict__ bucket_base, uint32_t *__restrict__ bucket_cursor,
@@ -198,29 +198,83 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
     uint64_t keys[L1_KPT];
     uint32_t ranks[L1_KPT / 2];
     uint32_t vmask = 0;
-    uint64_t rev = 0;
     const int bshift = W - b1_bits;
+    if (BIGK) {
+        // 17 <= k <= 31: the k-mer straddles both 32-bit halves and every run-time shift amount is < 32, so the
+        // whole roll is written on explicit halves with funnel shifts (a 64-bit shift by a run-time amount costs
+        // the compiler 4-6 instructions, a funnel shift one).
+        const uint32_t A = (uint32_t)(hi >> 32), B = (uint32_t)hi, Cw = (uint32_t)(lo >> 32), D = (uint32_t)lo;
+        const int s1 = 64 - 2 * k;        // fwd = top 2k bits of the 64-bit window: 2..30
+        const int s2 = 2 * k - 34;        // position of the incoming reverse-strand base inside the high half: 0..28
+        const int sx = kp.mix.shift;      // k
+        const uint32_t mhi = (uint32_t)(kp.mix.mask >> 32);
+        const uint32_t m1l = (uint32_t)kp.mix.m1, m1h = (uint32_t)(kp.mix.m1 >> 32);
+        const int bs = bshift - 32;       // bucket = top bits of the high half (b1_bits <= 2k - 32)
+        uint32_t rl = 0, rh = 0;
 #pragma unroll
-    for (int j = 0; j < L1_KPT; j++) {
-        const uint64_t fwd = hi >> (64 - 2 * k);
-        if (j == 0) rev = simka::revcomp(fwd, k);
-        else rev = (rev >> 2) | ((uint64_t)((fwd & 3) ^ 2) << (2 * k - 2));
-        const uint64_t canon = fwd < rev ? fwd : rev;
-        const uint64_t h = simka::mix_fwd(canon, kp.mix);
-        bool keep = (okmask >> (31 - j)) & 1u;
-        if (SHARDED) keep = keep && shard_keep(h, kp);
-        keys[j] = h;
-        if (keep) {
-            vmask |= 1u << j;
-            uint32_t r = atomicAdd(&hist[(uint32_t)(h >> bshift)], 1u);
-            if (!COUNT_ONLY) {
-                if (j & 1) ranks[j >> 1] |= r << 16; else ranks[j >> 1] = r;
+        for (int j = 0; j < L1_KPT; j++) {
+            // 64-bit window starting at base j
+            uint32_t w1, w0;
+            if (j == 0) { w1 = A; w0 = B; }
+            else if (j < 16) { w1 = __funnelshift_l(B, A, 2 * j); w0 = __funnelshift_l(Cw, B, 2 * j); }
+            else if (j == 16) { w1 = B; w0 = Cw; }
+            else { w1 = __funnelshift_l(Cw, B, 2 * j - 32); w0 = __funnelshift_l(D, Cw, 2 * j - 32); }
+            const uint32_t fh = w1 >> s1, fl = __funnelshift_r(w0, w1, s1);
+            if (j == 0) {
+                const uint64_t r0 = simka::revcomp(((uint64_t)fh << 32) | fl, k);
+                rh = (uint32_t)(r0 >> 32); rl = (uint32_t)r0;
+            } else {
+                rl = __funnelshift_r(rl, rh, 2);
+                rh = (rh >> 2) | (((fl & 3u) ^ 2u) << s2);
             }
-        } else if (!COUNT_ONLY && !(j & 1)) {
-            ranks[j >> 1] = 0;
+            const bool fwd_smaller = fh < rh || (fh == rh && fl < rl);
+            uint32_t xh = fwd_smaller ? fh : rh, xl = fwd_smaller ? fl : rl;
+            // mix: x ^= x >> k; x = x * m1 mod 2^2k; x ^= x >> k
+            xl ^= __funnelshift_r(xl, xh, sx); xh ^= xh >> sx;
+            {
+                const uint64_t p = (uint64_t)xl * m1l;
+                const uint32_t ph = (uint32_t)(p >> 32) + xl * m1h + xh * m1l;
+                xl = (uint32_t)p; xh = ph & mhi;
+            }
+            xl ^= __funnelshift_r(xl, xh, sx); xh ^= xh >> sx;
+            const uint64_t h = ((uint64_t)xh << 32) | xl;
+            bool keep = (okmask >> (31 - j)) & 1u;
+            if (SHARDED) keep = keep && shard_keep(h, kp);
+            keys[j] = h;
+            if (keep) {
+                vmask |= 1u << j;
+                uint32_t r = atomicAdd(&hist[xh >> bs], 1u);
+                if (!COUNT_ONLY) {
+                    if (j & 1) ranks[j >> 1] |= r << 16; else ranks[j >> 1] = r;
+                }
+            } else if (!COUNT_ONLY && !(j & 1)) {
+                ranks[j >> 1] = 0;
+            }
         }
-        hi = (hi << 2) | (lo >> 62);
-        lo <<= 2;
+    } else {
+        uint64_t rev = 0;
+#pragma unroll
+        for (int j = 0; j < L1_KPT; j++) {
+            const uint64_t fwd = hi >> (64 - 2 * k);
+            if (j == 0) rev = simka::revcomp(fwd, k);
+            else rev = (rev >> 2) | ((uint64_t)((fwd & 3) ^ 2) << (2 * k - 2));
+            const uint64_t canon = fwd < rev ? fwd : rev;
+            const uint64_t h = simka::mix_fwd(canon, kp.mix);
+            bool keep = (okmask >> (31 - j)) & 1u;
+            if (SHARDED) keep = keep && shard_keep(h, kp);
+            keys[j] = h;
+            if (keep) {
+                vmask |= 1u << j;
+                uint32_t r = atomicAdd(&hist[(uint32_t)(h >> bshift)], 1u);
+                if (!COUNT_ONLY) {
+                    if (j & 1) ranks[j >> 1] |= r << 16; else ranks[j >> 1] = r;
+                }
+            } else if (!COUNT_ONLY && !(j & 1)) {
+                ranks[j >> 1] = 0;
+            }
+            hi = (hi << 2) | (lo >> 62);
+            lo <<= 2;
+        }
     }
     __syncthreads();
     if (COUNT_ONLY) {
@@ -1509,6 +1563,21 @@ static double __attribute__((noinline)) onesided_kl_term(double c, double Nx, do
 static int ilog2_ceil(uint64_t v) { int b = 0; while (((uint64_t)1 << b) < v) b++; return b; }
 static int ilog2_floor(uint64_t v) { int b = 0; while (b < 63 && ((uint64_t)2 << b) <= v) b++; return b; }
 
+// K1 launcher: picks the template instance (count-only / sharded / k >= 17 fast roll)
+typedef void (*extract_fn)(const uint64_t *, const uint32_t *, uint64_t, KParams, int, uint32_t *, const uint64_t *, uint32_t *, uint64_t, int *, uint64_t *);
+static extract_fn extract_instance(bool count_only, bool sharded, bool bigk) {
+    static const extract_fn tab[8] = {k_extract<false, false, false>, k_extract<false, false, true>, k_extract<false, true, false>, k_extract<false, true, true>,
+                                      k_extract<true, false, false>,  k_extract<true, false, true>,  k_extract<true, true, false>,  k_extract<true, true, true>};
+    return tab[(count_only ? 4 : 0) | (sharded ? 2 : 0) | (bigk ? 1 : 0)];
+}
+static void launch_extract(simka_ctx *ctx, bool count_only, unsigned grid, const uint64_t *seq, const uint32_t *bad, uint64_t n_words, int b1_bits,
+                           uint32_t *g_hist, const uint64_t *bucket_base, uint32_t *bucket_cursor, uint64_t cap, int *overflow, uint64_t *keys_out) {
+    const bool bigk = ctx->kp.k >= 17 && b1_bits <= 2 * ctx->kp.k - 32;
+    const size_t smem = 3 * MAX_B * 4 + 64 + (count_only ? 0 : L1_TILE * 8);
+    extract_instance(count_only, ctx->kp.shard_count > 1, bigk)<<<grid, BLOCK, smem, ctx->stream>>>(seq, bad, n_words, ctx->kp, b1_bits, g_hist, bucket_base,
+                                                                                                   bucket_cursor, cap, overflow, keys_out);
+}
+
 // exclusive scan u32[n] -> u64[n+1] on the context's stream
 static void launch_scan(simka_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n) {
     if (n <= (uint64_t)SCAN_CHUNK) { k_scan_u32_u64<<<1, 1024, 0, ctx->stream>>>(in, out, n); return; }
@@ -1567,10 +1636,10 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
         ok = ok && cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming) == cudaSuccess;
     for (auto &e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_extract<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_extract<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
+    for (int sh = 0; sh < 2; sh++)
+        for (int bk = 0; bk < 2; bk++)
+            ok = ok && cudaFuncSetAttribute(extract_instance(false, sh, bk), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(p->nb_samples)) == cudaSuccess;
     ok = ok && ctx->d_small.reserve(64) == 0;
     ok = ok && ctx->d_chain.reserve(128 * 8) == 0 && cudaMemset(ctx->d_chain.p, 0, 128 * 8) == cudaSuccess;
@@ -1783,26 +1852,20 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         CK(cudaMemsetAsync(ctx->d_fine_cursor.p, 0, (size_t)nbins * 4, st));
 
         const unsigned g1 = (unsigned)((n_words + BLOCK - 1) / BLOCK);
-        const bool sharded = ctx->kp.shard_count > 1;
         const uint64_t *seq = sl->ext_packed ? sl->ext_packed : sl->packed.as<uint64_t>();
         const uint32_t *bad = sl->ext_bad ? sl->ext_bad : sl->bad.as<uint32_t>();
         // K1 (count / scan /) scatter
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
         if (exact) {
-            if (sharded) k_extract<true, true><<<g1, BLOCK, 3 * MAX_B * 4 + 64, st>>>(seq, bad, n_words, ctx->kp, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, 0, nullptr, nullptr);
-            else k_extract<true, false><<<g1, BLOCK, 3 * MAX_B * 4 + 64, st>>>(seq, bad, n_words, ctx->kp, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, 0, nullptr, nullptr);
+            launch_extract(ctx, true, g1, seq, bad, n_words, b1_bits, ctx->d_hist1.as<uint32_t>(), nullptr, nullptr, 0, nullptr, nullptr);
             ctx->launches++;
         }
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT + 1], st));
         if (exact) launch_scan(ctx, ctx->d_hist1.as<uint32_t>(), ctx->d_base1.as<uint64_t>(), nb1);
         else k_fill_bases<<<(nb1 + 256) / 256, 256, 0, st>>>(ctx->d_base1.as<uint64_t>(), (int)nb1, cap);
         CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER], st));
-        if (sharded) k_extract<false, true><<<g1, BLOCK, 3 * MAX_B * 4 + 64 + L1_TILE * 8, st>>>(seq, bad, n_words, ctx->kp, b1_bits, nullptr, ctx->d_base1.as<uint64_t>(),
-                                                                                 ctx->d_cursor1.as<uint32_t>(), exact ? ~0ull >> 1 : cap, d_overflow,
-                                                                                 ctx->d_keysA.as<uint64_t>());
-        else k_extract<false, false><<<g1, BLOCK, 3 * MAX_B * 4 + 64 + L1_TILE * 8, st>>>(seq, bad, n_words, ctx->kp, b1_bits, nullptr, ctx->d_base1.as<uint64_t>(),
-                                                                                  ctx->d_cursor1.as<uint32_t>(), exact ? ~0ull >> 1 : cap, d_overflow,
-                                                                                  ctx->d_keysA.as<uint64_t>());
+        launch_extract(ctx, false, g1, seq, bad, n_words, b1_bits, nullptr, ctx->d_base1.as<uint64_t>(), ctx->d_cursor1.as<uint32_t>(),
+                       exact ? ~0ull >> 1 : cap, d_overflow, ctx->d_keysA.as<uint64_t>());
         CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER + 1], st));
         // per-bucket key counts: the cursors of the scatter pass (== the histogram in exact mode)
         const uint32_t *cnt1 = ctx->d_cursor1.as<uint32_t>();
