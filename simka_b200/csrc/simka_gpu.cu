@@ -778,6 +778,39 @@ __device__ __forceinline__ long long absint32_ext(uint64_t x) {  // abs((int)x) 
     return (long long)d;
 }
 
+// log(x) for normal x > 0 from a 128-entry table {1/c, log c} (interval centres c over [0.6875, 1.375), the two
+// intervals around 1 use c = 1 so that the result keeps its RELATIVE accuracy near x = 1 and log(1) == 0):
+// log x = k ln2 + log c + log1p(r), r = x/c - 1, |r| < 2^-7, degree-6 series.  |error| < 4e-14 relative
+// (checked against logl over 2e7 points); used for the Jensen-Shannon terms whose sum is compared at 1e-10.
+__device__ __forceinline__ double tab_log(double x, const double2 *T) {
+    const unsigned long long OFF = 0x3fe6000000000000ull;
+    const unsigned long long ix = (unsigned long long)__double_as_longlong(x);
+    const unsigned long long tmp = ix - OFF;
+    const int i = (int)(tmp >> 45) & 127;
+    const int k = (int)((long long)tmp >> 52);
+    const double z = __longlong_as_double((long long)(ix - (tmp & (0xfffull << 52))));
+    const double2 t = T[i];
+    const double r = fma(z, t.x, -1.0);
+    const double w = fma((double)k, 0.693147180559945309417232121458, t.y);
+    double p = fma(r, -1.0 / 6, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3);
+    p = fma(r, p, -0.5);
+    return w + fma(r * r, p, r);
+}
+
+// (u64)sqrt((double)prod): what the reference's u64 Hellinger accumulator gains per k-mer
+// (src/core/SimkaAlgorithm.hpp:395).  Below 2^32 the exact integer square root is the same value.
+__device__ __forceinline__ ull hellinger_term(ull prod) {
+    if (prod >> 32) return (ull)sqrt((double)prod);
+    const uint32_t p = (uint32_t)prod;
+    const float pf = (float)p;
+    uint32_t s = min((uint32_t)(pf * rsqrtf(pf)), 65535u);  // within +-1 of the root (prod >= 1)
+    if (s * s > p) s--;
+    else if (s < 65535u && (s + 1) * (s + 1) <= p) s++;
+    return s;
+}
+
 __device__ __forceinline__ void accumulate_pair(const MergeArgs &a, int i, int j, uint32_t ci, uint32_t cj) {
     // i < j
     const size_t n = (size_t)a.n;
@@ -791,14 +824,15 @@ __device__ __forceinline__ void accumulate_pair(const MergeArgs &a, int i, int j
     if (a.simple) {
         const ull prod = (ull)ci * (ull)cj;
         atomicAdd(&a.chord[ij], prod);
-        atomicAdd(&a.hellinger[ij], (ull)sqrt((double)prod));  // u64 += double truncates per increment
+        atomicAdd(&a.hellinger[ij], hellinger_term(prod));  // u64 += double truncates per increment
     }
     if (a.complex_) {
         const double ai = (double)ci, aj = (double)cj, Ni = a.ntot[i], Nj = a.ntot[j];
         const double yX = aj * Ni, xY = ai * Nj;
-        const double d1 = (ai / Ni) * log((2 * xY) / (xY + yX));
-        const double d2 = (aj / Nj) * log((2 * yX) / (xY + yX));
-        atomicAdd(&a.kl[ij], d1 + d2);
+        if (xY != yX) {  // equal: both logs are log(1) = 0 exactly (same evaluation as k_merge32)
+            const double r1 = (2 * xY) * __drcp_rn(xY + yX);
+            atomicAdd(&a.kl[ij], (ai / Ni) * tab_log(r1, a.logtab) + (aj / Nj) * tab_log(2.0 - r1, a.logtab));
+        }
         const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
         const long long two = absint32_ext(wx - wy);
         const long long sub = absint32_ext(wx) + absint32_ext(wy);  // their one-sided values, removed here
@@ -914,8 +948,9 @@ k_merge(MergeArgs a) {
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pp[mid] <= p) lo = mid; else hi = mid; }
                 const uint32_t g = gsz[lo], l = p - pp[lo], base = gs[lo];
                 // row-major strict upper triangle of a g x g matrix: row x starts at x(2g-x-1)/2
-                const double tg = 2.0 * g - 1.0;
-                int x = (int)((tg - sqrt(tg * tg - 8.0 * (double)l)) * 0.5);
+                const float tg = 2.0f * (float)g - 1.0f;  // g <= N <= 8192: exact in float up to the +-1 fix-up below
+                int x = (int)((tg - sqrtf(fmaxf(tg * tg - 8.0f * (float)l, 0.0f))) * 0.5f);
+                if (x > (int)g - 2) x = (int)g - 2;
                 if (x < 0) x = 0;
                 while ((uint32_t)(x + 1) * (2 * g - (x + 1) - 1) / 2 <= l) x++;
                 while ((uint32_t)x * (2 * g - x - 1) / 2 > l) x--;
@@ -932,39 +967,6 @@ k_merge(MergeArgs a) {
         atomicAdd(&a.scalars[0], loc_groups);
         atomicAdd(&a.scalars[1], loc_shared);
     }
-}
-
-// log(x) for normal x > 0 from a 128-entry table {1/c, log c} (interval centres c over [0.6875, 1.375), the two
-// intervals around 1 use c = 1 so that the result keeps its RELATIVE accuracy near x = 1 and log(1) == 0):
-// log x = k ln2 + log c + log1p(r), r = x/c - 1, |r| < 2^-7, degree-6 series.  |error| < 4e-14 relative
-// (checked against logl over 2e7 points); used for the Jensen-Shannon terms whose sum is compared at 1e-10.
-__device__ __forceinline__ double tab_log(double x, const double2 *T) {
-    const unsigned long long OFF = 0x3fe6000000000000ull;
-    const unsigned long long ix = (unsigned long long)__double_as_longlong(x);
-    const unsigned long long tmp = ix - OFF;
-    const int i = (int)(tmp >> 45) & 127;
-    const int k = (int)((long long)tmp >> 52);
-    const double z = __longlong_as_double((long long)(ix - (tmp & (0xfffull << 52))));
-    const double2 t = T[i];
-    const double r = fma(z, t.x, -1.0);
-    const double w = fma((double)k, 0.693147180559945309417232121458, t.y);
-    double p = fma(r, -1.0 / 6, 0.2);
-    p = fma(r, p, -0.25);
-    p = fma(r, p, 1.0 / 3);
-    p = fma(r, p, -0.5);
-    return w + fma(r * r, p, r);
-}
-
-// (u64)sqrt((double)prod): what the reference's u64 Hellinger accumulator gains per k-mer
-// (src/core/SimkaAlgorithm.hpp:395).  Below 2^32 the exact integer square root is the same value.
-__device__ __forceinline__ ull hellinger_term(ull prod) {
-    if (prod >> 32) return (ull)sqrt((double)prod);
-    const uint32_t p = (uint32_t)prod;
-    const float pf = (float)p;
-    uint32_t s = min((uint32_t)(pf * rsqrtf(pf)), 65535u);  // within +-1 of the root (prod >= 1)
-    if (s * s > p) s--;
-    else if (s < 65535u && (s + 1) * (s + 1) <= p) s++;
-    return s;
 }
 
 // ---------------------------------------------------------------------------------------------
