@@ -1492,6 +1492,7 @@ struct SampleData {
     uint64_t n = 0;
     uint32_t *off = nullptr;  // points into ctx->off_table
     bool done = false;
+    bool imported = false;    // arrays owned by the caller (simka_gpu_import_sample)
     simka_sample_totals local = {0, 0, 0, 0};
 };
 
@@ -1513,7 +1514,9 @@ struct simka_ctx {
     KParams kp;
     int W = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev[2 * T_NSTAGE + 4] = {};
+    cudaEvent_t ev[2][2 * T_NSTAGE + 4] = {};  // two sets: the timings of a sample are harvested while a later one runs
+    bool ev_pending[2] = {false, false};
+    int ev_cur = 0;
     std::string err;
     InSlot slots[2];
     DevBuf d_ascii, d_roff;
@@ -1537,7 +1540,8 @@ struct simka_ctx {
     size_t acc_bytes = 0;
     ull *a_nb_shared = nullptr, *a_distinct = nullptr, *a_bc = nullptr, *a_chord = nullptr, *a_hell = nullptr, *a_whit = nullptr, *a_T = nullptr, *a_scalars = nullptr;
     double *a_kl = nullptr, *a_ntot = nullptr;
-    DevBuf d_ptrs, d_logtab, d_chain;
+    DevBuf d_ptrs, d_logtab, d_chain, d_isum;
+    bool import_pending = false;
     unsigned long long scan_epoch = 0;
     bool force_exact = false;   // SIMKA_B200_EXACT_COUNT=1: always run the K1 count pass (tests of the fallback)
     uint64_t exact_retries = 0;
@@ -1590,12 +1594,25 @@ static void launch_scan(simka_ctx *ctx, const uint32_t *in, uint64_t *out, uint6
     k_scan_chain<<<grid, 1024, 0, ctx->stream>>>(in, out, n, ctx->d_chain.as<unsigned long long>(), ctx->scan_epoch);
 }
 
+// adds the per-kernel device times of a finished sample (event set `set`) to the context's totals
+static void harvest_timings(simka_ctx *ctx, int set) {
+    if (!ctx->ev_pending[set]) return;
+    cudaEvent_t *ev = ctx->ev[set];
+    cudaEventSynchronize(ev[2 * T_NSTAGE + 1]);
+    float ms = 0;
+    for (int t = 0; t < T_NSTAGE; t++) { if (cudaEventElapsedTime(&ms, ev[2 * t], ev[2 * t + 1]) == cudaSuccess) ctx->stage_ms[t] += ms; }
+    if (cudaEventElapsedTime(&ms, ev[2 * T_NSTAGE], ev[2 * T_NSTAGE + 1]) == cudaSuccess) ctx->sample_ms += ms;
+    ctx->ev_pending[set] = false;
+}
+
 static int reset_state(simka_ctx *ctx) {
+    harvest_timings(ctx, 0); harvest_timings(ctx, 1);
     for (auto &s : ctx->samples) s = SampleData();
     ctx->arena.reset();
     for (auto &sl : ctx->slots) { sl.sample = -1; sl.words = sl.reads = 0; sl.ext_packed = nullptr; sl.ext_bad = nullptr; }
     ctx->global_totals.assign(ctx->prm.nb_samples, simka_sample_totals{0, 0, 0, 0});
     ctx->totals_overridden = false;
+    ctx->import_pending = false;
     ctx->merged = false;
     ctx->fg_bits = -1;
     for (float &f : ctx->stage_ms) f = 0;
@@ -1637,7 +1654,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
     for (auto &sl : ctx->slots)
         ok = ok && cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming) == cudaSuccess;
-    for (auto &e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    for (auto &set : ctx->ev) for (auto &e : set) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     for (int sh = 0; sh < 2; sh++)
         for (int bk = 0; bk < 2; bk++)
             ok = ok && cudaFuncSetAttribute(extract_instance(false, sh, bk), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1684,9 +1701,9 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
                       &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
                       &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
-                      &ctx->d_small, &ctx->d_off_table, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain};
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum};
     for (DevBuf *b : bufs) b->release();
-    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &set : ctx->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1837,7 +1854,9 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
                    !ctx->d_out_off.reserve(((size_t)nbins + 1) * 8);
         if (!okm) { ctx->set_error("out of device memory (work buffers)"); return SIMKA_ERR_NOMEM; }
         CK(cudaStreamWaitEvent(st, sl->copied, 0));
-        cudaEvent_t *ev = ctx->ev;
+        const int evset = ctx->ev_cur;
+        harvest_timings(ctx, evset);  // the sample before the previous one: long finished
+        cudaEvent_t *ev = ctx->ev[evset];
         CK(cudaEventRecord(ev[2 * T_NSTAGE], st));  // sample start
       for (int attempt = 0; attempt < 2; attempt++) {
         // attempt 0: single pass over the reads into fixed-capacity L1 buckets (sizes are binomial for hashed
@@ -1938,12 +1957,9 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         k_fill_offsets<<<(fg + 1 + 255) / 256, 256, 0, st>>>(ctx->d_out_off.as<uint64_t>(), sd.off, fg, nbins >> ctx->fg_bits);
         ctx->launches++;
         CK(cudaEventRecord(ev[2 * T_COMPACT + 1], st));
-        CK(cudaEventRecord(ev[2 * T_NSTAGE + 1], st));  // sample end
-        CK(cudaEventSynchronize(ev[2 * T_NSTAGE + 1]));
-        float ms = 0;
-        for (int t = 0; t < T_NSTAGE; t++) { cudaEventElapsedTime(&ms, ev[2 * t], ev[2 * t + 1]); ctx->stage_ms[t] += ms; }
-        cudaEventElapsedTime(&ms, ev[2 * T_NSTAGE], ev[2 * T_NSTAGE + 1]);
-        ctx->sample_ms += ms;
+        CK(cudaEventRecord(ev[2 * T_NSTAGE + 1], st));  // sample end; no host wait: the next sample's kernels queue right behind
+        ctx->ev_pending[evset] = true;
+        ctx->ev_cur ^= 1;
     }
     sd.n = h_surv;
     sd.done = true;
@@ -1988,6 +2004,8 @@ int simka_gpu_fine_bits(simka_ctx *ctx) { return ctx ? ctx->fg_bits : -1; }
 int simka_gpu_export_sample(simka_ctx *ctx, int sample_id, const uint64_t **d_kmers, const uint32_t **d_counts, const uint32_t **d_off, uint64_t *n) {
     if (!ctx || sample_id < 0 || sample_id >= ctx->prm.nb_samples || !ctx->samples[sample_id].done || ctx->fg_bits < 0) return SIMKA_ERR_INVALID;
     const SampleData &sd = ctx->samples[sample_id];
+    CK(cudaSetDevice(ctx->prm.device));
+    CK(cudaStreamSynchronize(ctx->stream));  // the caller reads the arrays from its own streams
     if (d_kmers) *d_kmers = sd.eh;
     if (d_counts) *d_counts = sd.ec;
     if (d_off) *d_off = sd.off ? sd.off : ctx->d_off_table.as<uint32_t>() + (size_t)sample_id * (((size_t)1 << ctx->fg_bits) + 1);
@@ -2015,25 +2033,26 @@ int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kme
     sd.eh = const_cast<uint64_t *>(d_kmers);
     sd.ec = const_cast<uint32_t *>(d_counts);
     sd.n = n;
-    ull *d_totals = ctx->d_small.as<ull>();
     int *d_error = reinterpret_cast<int *>(ctx->d_small.as<char>() + 32);
     uint32_t *d_big_n = reinterpret_cast<uint32_t *>(ctx->d_small.as<char>() + 40);
-    ull h_sum = 0;
+    // the sum of the imported abundances is needed at read-out only: computed asynchronously into d_isum[sample]
+    // and fetched once by simka_gpu_merge_and_accumulate (no host synchronisation per imported sample)
+    if (ctx->d_isum.reserve((size_t)ctx->prm.nb_samples * 8)) { ctx->set_error("out of device memory"); return SIMKA_ERR_NOMEM; }
+    if (!ctx->import_pending) { CK(cudaMemsetAsync(ctx->d_isum.p, 0, (size_t)ctx->prm.nb_samples * 8, st)); ctx->import_pending = true; }
     if (n) {
-        CK(cudaMemsetAsync(d_totals, 0, 8, st));
         const unsigned g = (unsigned)std::min<uint64_t>((n + BLOCK * 16 - 1) / (BLOCK * 16), (uint64_t)ctx->nsm * 4);
-        k_sum_u32<<<g, BLOCK, 0, st>>>(d_counts, n, d_totals);
+        k_sum_u32<<<g, BLOCK, 0, st>>>(d_counts, n, ctx->d_isum.as<ull>() + sample_id);
         if (ctx->prm.complex_dist)
             k_abundance_hist<<<g, BLOCK, 0, st>>>(d_counts, n, sample_id, ctx->d_chist.as<ull>() + (size_t)sample_id * CHIST,
                                                  ctx->d_big_counts.as<uint32_t>(), ctx->d_big_sample.as<uint32_t>(), d_big_n, ctx->big_cap, d_error);
         ctx->launches += ctx->prm.complex_dist ? 2 : 1;
-        CK(cudaMemcpyAsync(&h_sum, d_totals, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaGetLastError());
     }
-    CK(cudaStreamSynchronize(st));
     sd.done = true;
+    sd.imported = true;
     sd.local.nb_reads = nb_reads;
     sd.local.nb_distinct = n;
-    sd.local.nb_kmers = h_sum;
+    sd.local.nb_kmers = 0;  // filled from d_isum at merge time
     sd.local.chord_n2 = 0;
     if (!ctx->totals_overridden) ctx->global_totals[sample_id] = sd.local;
     ctx->entries += n;
@@ -2060,12 +2079,24 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
     if (ctx->merged) { ctx->set_error("merge already done"); return SIMKA_ERR_INVALID; }
     CK(cudaSetDevice(ctx->prm.device));
     cudaStream_t st = ctx->stream;
+    if (ctx->import_pending) {  // abundance sums of the imported sample slices
+        std::vector<ull> sums(N);
+        CK(cudaMemcpyAsync(sums.data(), ctx->d_isum.p, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int s = 0; s < N; s++)
+            if (ctx->samples[s].imported) {
+                ctx->samples[s].local.nb_kmers = sums[s];
+                if (!ctx->totals_overridden) ctx->global_totals[s].nb_kmers = sums[s];
+            }
+        ctx->import_pending = false;
+    }
     const size_t nn = (size_t)N * N, ns = (size_t)N * (N + 1) / 2;
     // slab: nb_shared nn | distinct ns | bc ns | chord nn | hell nn | whit nn | T nn | scalars 4 | kl nn (f64) | ntot N (f64)
     const size_t words = nn + ns + ns + nn + nn + nn + nn + 4 + nn + N;
     ctx->acc_bytes = words * 8;
     if (ctx->d_acc.reserve(ctx->acc_bytes)) { ctx->set_error("out of device memory (accumulators)"); return SIMKA_ERR_NOMEM; }
-    cudaEvent_t e0 = ctx->ev[2 * T_NSTAGE + 2], e1 = ctx->ev[2 * T_NSTAGE + 3];
+    harvest_timings(ctx, 0); harvest_timings(ctx, 1);
+    cudaEvent_t e0 = ctx->ev[0][2 * T_NSTAGE + 2], e1 = ctx->ev[0][2 * T_NSTAGE + 3];
     CK(cudaEventRecord(e0, st));
     CK(cudaMemsetAsync(ctx->d_acc.p, 0, ctx->acc_bytes, st));
     ull *p = ctx->d_acc.as<ull>();
@@ -2204,6 +2235,7 @@ int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) {
 
 int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
     if (!ctx || !out) return SIMKA_ERR_INVALID;
+    harvest_timings(ctx, 0); harvest_timings(ctx, 1);
     simka_timings t;
     memset(&t, 0, sizeof t);
     t.extract_count_ms = ctx->stage_ms[T_EXTRACT_COUNT];

@@ -110,6 +110,16 @@ def exchange_and_merge(count_ctx, merge_ctx, nb_samples: int, rank: int, world: 
             return t
     N = nb_samples
     mine = [s for s in range(N) if sample_owner(s, world) == rank]
+    import os
+    import time
+    timing = os.environ.get("SIMKA_DIST_TIMING")
+    marks = [("start", time.perf_counter())]
+
+    def mark(name):
+        if timing:
+            if torch.device(device).type == "cuda":
+                torch.cuda.synchronize(device)
+            marks.append((name, time.perf_counter()))
     # C1: global per-sample totals (only the owner has non-zero rows)
     tot = count_ctx.get_totals()
     own = np.zeros_like(tot)
@@ -129,13 +139,20 @@ def exchange_and_merge(count_ctx, merge_ctx, nb_samples: int, rank: int, world: 
     # split points of my samples, sizes of every (sample, destination)
     cnt = np.zeros((N, world), np.int64)
     exports = {}
+    offs = []
     for s in mine:
         pk, pc, po, n = count_ctx.export_sample(s)
         off = _dev_tensor(po, (1 << fine_bits) + 1, "<i4", device)
-        cuts = off[:: per][: parts + 1].to(torch.int64).cpu().numpy()
-        exports[s] = (pk, pc, off, n, cuts)
-        cnt[s, :parts] = np.diff(cuts)
+        offs.append(off[:: per][: parts + 1])
+        exports[s] = [pk, pc, off, n, None]
+    if mine:  # one device->host copy for the split points of all my samples
+        all_cuts = torch.stack(offs).to(torch.int64).cpu().numpy()
+        for i, s in enumerate(mine):
+            exports[s][4] = all_cuts[i]
+            cnt[s, :parts] = np.diff(all_cuts[i])
+    mark("totals+export")
     cnt = all_reduce_sum(torch.from_numpy(cnt).to(device)).cpu().numpy()
+    mark("sizes")
     # send buffers, destination-major then sample-major
     se, sc, so = [], [], []
     for r in range(world):
@@ -151,6 +168,7 @@ def exchange_and_merge(count_ctx, merge_ctx, nb_samples: int, rank: int, world: 
     send_e = torch.cat(se) if se else torch.empty(0, dtype=torch.int64, device=device)
     send_c = torch.cat(sc) if sc else torch.empty(0, dtype=torch.int32, device=device)
     send_o = torch.cat(so) if so else torch.empty(0, dtype=torch.int32, device=device)
+    mark("pack")
     owners = [[s for s in range(N) if sample_owner(s, world) == o] for o in range(world)]
     send_splits = [int(cnt[mine, r].sum()) if mine else 0 for r in range(world)]
     recv_splits = [int(cnt[owners[o], rank].sum()) if owners[o] else 0 for o in range(world)]
@@ -159,6 +177,7 @@ def exchange_and_merge(count_ctx, merge_ctx, nb_samples: int, rank: int, world: 
     recv_o = all_to_all(send_o, [len(mine) * fgn] * world, [len(owners[o]) * fgn for o in range(world)])
     if torch.device(device).type == "cuda":
         torch.cuda.current_stream(device).synchronize()  # the merge context runs on its own stream
+    mark("all_to_all")
     # stage 2 on my block of fine ranges over all samples
     pos_e, pos_o = 0, 0
     for o in range(world):
@@ -170,7 +189,12 @@ def exchange_and_merge(count_ctx, merge_ctx, nb_samples: int, rank: int, world: 
             pos_o += fgn
     merge_ctx._keep.append((recv_e, recv_c, recv_o))
     merge_ctx.set_totals(g_tot)
+    mark("import")
     merge_ctx.merge_and_accumulate()
+    mark("merge")
     st = merge_ctx.stats()
+    mark("stats")
+    if timing and rank == 0:
+        print("[exchange_and_merge ms] " + " ".join(f"{n}={1e3 * (t - marks[i][1]):.2f}" for i, (n, t) in enumerate(marks[1:])), flush=True)
     st.totals[:] = g_tot
     return st
