@@ -292,3 +292,47 @@ def test_simka_cli_max_reads_and_filters(tmp_path, golden_dir):
         assert got == run.csv(m, ids), name
     ok = (tmp_path / "tmp" / "simka_output_temp" / "count_synchro" / "A.ok").read_text().split()
     assert [int(x) for x in ok] == run.all_totals()[0].tolist()
+
+
+def test_medium_scale_oracle_parity():
+    """8 samples x 150k reads x 150 bp, k=31 (1.4e8 k-mers): thousands of full bins per sample, merge bins with
+    sub-pass pressure; still seconds for the oracle."""
+    samples = synthetic_samples(8, 150_000, n_genomes=64, genome_len=30_000)
+    run = oracle_run(samples, 31, 2)
+    st = simka_b200.run_samples(samples, 31, abundance_min=2)
+    assert_stats_equal(st, run)
+
+
+def test_full_size_sample_properties():
+    """One sample of BASELINE config 2 (1M reads x 150 bp, k=31) through size-independent properties:
+    with abundance-min 1 every valid k-mer is counted exactly once (sum of counts == M*(L-k+1) for N-free reads),
+    chunked pushes == one push, two runs are bit-identical, and the (k-mer,count) dump is strictly increasing."""
+    from simka_b200 import synth
+    genomes = synth.make_genomes(256, 50_000)
+    seqs, off = synth.make_sample(genomes, 0, 1_000_000, 150)
+    M, L, k = 1_000_000, 150, 31
+
+    def run(chunks):
+        ctx = simka_b200.SimkaGpu(1, k, 1, simple_dist=True, complex_dist=True)
+        bounds = np.linspace(0, M, chunks + 1).astype(int)
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            p, bd, nw = simka_b200.pack_reads(seqs[int(off[a]):int(off[b])], off[a:b + 1] - off[a])
+            ctx.push_reads(0, p, bd, nw, b - a)
+        tot = ctx.finish_sample(0)
+        km, ct = ctx.dump_sample_counts(0)
+        ctx.close()
+        return tot, km, ct
+
+    tot1, km1, ct1 = run(1)
+    tot3, km3, ct3 = run(3)
+    assert int(tot1[0]) == M and int(tot1[2]) == M * (L - k + 1)
+    assert int(tot1[1]) == len(km1) and int(ct1.sum()) == int(tot1[2])
+    assert int((ct1.astype(np.uint64) ** 2).sum()) == int(tot1[3])
+    assert (np.diff(km1.astype(np.int64)) > 0).all()
+    np.testing.assert_array_equal(tot1, tot3)
+    np.testing.assert_array_equal(km1, km3)
+    np.testing.assert_array_equal(ct1, ct3)
+    # canonical: no k-mer is larger than its reverse complement
+    sub = km1[:: max(1, len(km1) // 50_000)]
+    rc = np.array([oracle.lib().orc_revcomp(int(v), k) for v in sub[:20_000]], np.uint64)
+    assert (sub[:20_000] <= rc).all()
