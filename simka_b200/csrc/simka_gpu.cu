@@ -47,7 +47,7 @@ constexpr int L1_TILE = BLOCK * L1_KPT;      // 8192 keys
 constexpr int L2_KPT = 16;
 constexpr int L2_TILE = BLOCK * L2_KPT;      // 4096 keys
 constexpr int MAX_B = 1024;                  // max buckets per partition level
-constexpr int BIN_TARGET = 512;              // fine bins hold BIN_TARGET..2*BIN_TARGET keys on average
+constexpr int BIN_TARGET = 768;              // fine bins hold BIN_TARGET..2*BIN_TARGET keys on average
 constexpr int CNT_SLOTS = 2048;              // K3 hash table slots
 constexpr int CNT_MAXDISTINCT = 1536;        // distinct keys one table pass may hold (load 0.75)
 constexpr int CHIST = 1024;                  // dense abundance histogram bins (complex distances)
