@@ -975,10 +975,10 @@ k_merge(MergeArgs a) {
 // accumulators live in registers, no atomics on the accumulators at all (one flush per CTA at the end).
 // ---------------------------------------------------------------------------------------------
 constexpr int M32_THREADS = 512;
-constexpr int M32_SLOTS = 4096;   // table slots per pass
-constexpr int M32_ECAP = 4096;    // grouped entries held per pass
-constexpr int M32_GCAP = 2048;    // shared groups per pass (<= ECAP / 2)
-constexpr int M32_PCAP = 2048;    // sample pairs sorted per chunk
+constexpr int M32_SLOTS = 2048;   // table slots per pass
+constexpr int M32_ECAP = 2048;    // grouped entries held per pass
+constexpr int M32_GCAP = 1024;    // shared groups per pass (<= ECAP / 2)
+constexpr int M32_PCAP = 4096;    // sample pairs sorted per chunk
 constexpr int M32_PPT = M32_PCAP / M32_THREADS;
 constexpr uint32_t M32_SKIP = 0xFFFFFFFFu;
 
