@@ -1292,6 +1292,280 @@ k_merge32(MergeArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K4 for N <= 64 samples, the shipped merge: same grouping as k_merge32, then the sample pairs of the
+// bin are enumerated FLAT (every thread takes a contiguous run of pairs: one search + decode per run, full
+// lane utilisation) and added to CTA-private N(N-1)/2-entry accumulators in shared memory with 32-bit
+// shared atomics (64-bit values as lo/hi words with an explicit carry).  One flush of the accumulators per
+// CTA at the end.  k_merge32's counting sort + register accumulators avoid the atomics but lose two thirds
+// of the lanes to uneven per-key list lengths; measured, this version is faster.
+// ---------------------------------------------------------------------------------------------
+constexpr int MS_THREADS = 512;
+constexpr int MS_SLOTS = 2048;
+constexpr int MS_ECAP = 2048;
+constexpr int MS_GCAP = 1024;
+constexpr int MS_MAXN = 64;
+constexpr int MS_NACC = 7;  // u64 accumulators per pair key: sh_ij, sh_ji, distinct, bc, chord, hellinger, whittaker
+
+struct MSSmem {
+    alignas(16) uint64_t tk[MS_SLOTS];
+    alignas(16) double2 logtab[128];
+    alignas(16) unsigned long long scan_tmp[MS_THREADS / 32 + 1];
+    alignas(16) uint32_t gcnt[MS_SLOTS];   // cleaned with 128-bit stores
+    uint32_t cg[MS_GCAP];
+    uint32_t cgp[MS_GCAP + 1];
+    uint32_t ge_c[MS_ECAP];
+    uint32_t s_start[MS_MAXN], s_pre[MS_MAXN + 1];
+    uint8_t ge_s[MS_ECAP];
+    // followed by: double kl[NP]; uint32_t lo[MS_NACC][NP]; uint32_t hi[MS_NACC][NP];
+};
+static size_t ms_smem_bytes(int n) {
+    const size_t np = (size_t)n * (n - 1) / 2;
+    return ((sizeof(MSSmem) + 15) & ~(size_t)15) + np * 8 + (size_t)2 * MS_NACC * np * 4 + 16;
+}
+
+__device__ __forceinline__ void ms_add64(uint32_t *lo, uint32_t *hi, uint32_t idx, unsigned long long v) {
+    const uint32_t vl = (uint32_t)v;
+    const uint32_t old = atomicAdd(&lo[idx], vl);
+    const uint32_t hv = (uint32_t)(v >> 32) + ((uint32_t)(old + vl) < old ? 1u : 0u);
+    if (hv) atomicAdd(&hi[idx], hv);
+}
+
+template <bool SIMPLE, bool COMPLEX>
+__global__ void __launch_bounds__(MS_THREADS, 2)
+k_merge_sm(MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MSSmem &S = *reinterpret_cast<MSSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = a.n;
+    const int NP = N * (N - 1) / 2;
+    double *acc_kl = reinterpret_cast<double *>(smem_raw + ((sizeof(MSSmem) + 15) & ~(size_t)15));
+    uint32_t *acc_lo = reinterpret_cast<uint32_t *>(acc_kl + NP);
+    uint32_t *acc_hi = acc_lo + (size_t)MS_NACC * NP;
+    const uint32_t MG = 1u << a.mg_bits;
+    const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
+    const size_t ostride = ((size_t)1 << a.fg_bits) + 1;
+
+    for (int i = tid; i < NP; i += MS_THREADS) acc_kl[i] = 0.0;
+    for (int i = tid; i < 2 * MS_NACC * NP; i += MS_THREADS) acc_lo[i] = 0;  // lo and hi are contiguous
+    if (tid < 128) S.logtab[tid] = a.logtab[tid];
+    ull loc_groups = 0, loc_shared = 0, loc_pairs = 0;
+    __syncthreads();
+
+    for (uint32_t mb = blockIdx.x; mb < MG; mb += gridDim.x) {
+        // segment descriptors of the N samples (warps 0 and 1 cover up to 64 samples)
+        if (tid < MS_MAXN) {
+            uint32_t len = 0;
+            if (tid < N) {
+                const uint32_t b0 = a.off[(size_t)tid * ostride + (size_t)mb * q];
+                const uint32_t b1 = a.off[(size_t)tid * ostride + (size_t)(mb + 1) * q];
+                S.s_start[tid] = b0;
+                len = b1 - b0;
+            }
+            S.s_pre[tid] = len;  // lengths first, scanned below
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t l0 = S.s_pre[tid], l1 = S.s_pre[tid + 32];
+            uint32_t inc0 = l0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc0, d); if (lane >= d) inc0 += u; }
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+            uint32_t inc1 = l1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc1, d); if (lane >= d) inc1 += u; }
+            const uint32_t tot1 = __shfl_sync(0xffffffffu, inc1, 31);
+            S.s_pre[tid] = inc0 - l0;
+            S.s_pre[tid + 32] = tot0 + inc1 - l1;
+            if (tid == 31) S.s_pre[64] = tot0 + tot1;
+        }
+        __syncthreads();
+        const uint32_t n_e = S.s_pre[64];
+        if (n_e == 0) { __syncthreads(); continue; }
+        uint32_t R = 1;
+        if (n_e > MS_ECAP) { while ((uint64_t)R * (MS_ECAP / 2) < n_e) R <<= 1; }
+        for (uint32_t r = 0; r < R; r++) {
+            {   // clean table
+                uint4 *pk = reinterpret_cast<uint4 *>(S.tk) + tid;
+                const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int qq = 0; qq < MS_SLOTS * 8 / 16 / MS_THREADS; qq++) pk[qq * MS_THREADS] = e;
+                uint4 *pg = reinterpret_cast<uint4 *>(S.gcnt) + tid;
+#pragma unroll
+                for (int qq = 0; qq < MS_SLOTS * 4 / 16 / MS_THREADS; qq++) pg[qq * MS_THREADS] = z;
+            }
+            __syncthreads();
+            // phase 1: insert keys, count group sizes
+            for (uint32_t i = tid; i < n_e; i += MS_THREADS) {
+                int lo = 0, hi = 64;  // s_pre[lo] <= i < s_pre[hi]   (s_pre[N..64] = n_e)
+#pragma unroll
+                for (int st = 0; st < 6; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const uint64_t h = a.eh[lo][S.s_start[lo] + (i - S.s_pre[lo])];
+                const uint64_t hh = simka::hash2(h);
+                if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (MS_SLOTS - 1);
+                volatile uint64_t *vk = S.tk;
+                int probes = 0;
+                for (;;) {
+                    uint64_t cur = vk[slot];
+                    if (cur == EMPTY) {
+                        cur = atomicCAS(reinterpret_cast<ull *>(&S.tk[slot]), (ull)EMPTY, (ull)h);
+                        if (cur == EMPTY) cur = h;
+                    }
+                    if (cur == h) { atomicAdd(&S.gcnt[slot], 1u); break; }
+                    slot = (slot + 1) & (MS_SLOTS - 1);
+                    if (++probes >= MS_SLOTS) { *a.error_flag = 3; break; }
+                }
+            }
+            __syncthreads();
+            // phase 2: group statistics + compact list of the shared groups (>= 2 samples)
+            unsigned long long packed = 0;  // groups (16 bits) | entries (16 bits) | pairs (32 bits)
+            uint32_t g8[MS_SLOTS / MS_THREADS];
+#pragma unroll
+            for (int qq = 0; qq < MS_SLOTS / MS_THREADS; qq++) {
+                const uint32_t g = S.gcnt[tid * (MS_SLOTS / MS_THREADS) + qq];
+                g8[qq] = g;
+                loc_groups += g > 0;
+                if (g > 1) packed += 1ull | ((unsigned long long)g << 16) | ((unsigned long long)(g * (g - 1) / 2) << 32);
+            }
+            unsigned long long total;
+            unsigned long long ex = block_scan_u64(packed, S.scan_tmp, &total);
+            const uint32_t n_groups = (uint32_t)(total & 0xFFFF), n_sub = (uint32_t)((total >> 16) & 0xFFFF);
+            const uint32_t P = (uint32_t)(total >> 32);
+            if (n_groups > MS_GCAP || n_sub > MS_ECAP) {  // cannot happen for hashed keys; reported, not silent
+                if (tid == 0) *a.error_flag = 4;
+                __syncthreads();
+                continue;
+            }
+#pragma unroll
+            for (int qq = 0; qq < MS_SLOTS / MS_THREADS; qq++) {
+                const uint32_t g = g8[qq];
+                uint32_t v = M32_SKIP;
+                if (g > 1) {
+                    const uint32_t gi = (uint32_t)(ex & 0xFFFF), st = (uint32_t)((ex >> 16) & 0xFFFF), pp = (uint32_t)(ex >> 32);
+                    S.cg[gi] = st | (g << 16);
+                    S.cgp[gi] = pp;
+                    v = st + g;  // fill cursor counts down from the end
+                    ex += 1ull | ((unsigned long long)g << 16) | ((unsigned long long)(g * (g - 1) / 2) << 32);
+                    loc_shared++;
+                }
+                S.gcnt[tid * (MS_SLOTS / MS_THREADS) + qq] = v;
+            }
+            if (tid == 0) { S.cgp[n_groups] = P; loc_pairs += P; }
+            __syncthreads();
+            if (n_groups == 0) continue;  // nothing shared in this pass: no accumulator changes
+            // phase 3: scatter the entries of shared k-mers into their groups
+            for (uint32_t i = tid; i < n_e; i += MS_THREADS) {
+                int lo = 0, hi = 64;
+#pragma unroll
+                for (int st = 0; st < 6; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const size_t idx = S.s_start[lo] + (i - S.s_pre[lo]);
+                const uint64_t h = a.eh[lo][idx];
+                const uint64_t hh = simka::hash2(h);
+                if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (MS_SLOTS - 1);
+                int pr = 0;
+                while (S.tk[slot] != h && ++pr <= MS_SLOTS) slot = (slot + 1) & (MS_SLOTS - 1);
+                if (pr > MS_SLOTS) { *a.error_flag = 7; continue; }  // inconsistent input (never for lists built by this library)
+                if (S.gcnt[slot] == M32_SKIP) continue;  // private k-mer: contributes to no pair
+                const uint32_t pos = atomicSub(&S.gcnt[slot], 1u) - 1;
+                S.ge_s[pos] = (uint8_t)lo;
+                S.ge_c[pos] = a.ec[lo][idx];
+            }
+            __syncthreads();
+            // phase 4: flat pair enumeration, one contiguous run of pairs per thread
+            {
+                const uint32_t per = (P + MS_THREADS - 1) / MS_THREADS;
+                const uint32_t l0 = min(P, tid * per), l1 = min(P, l0 + per);
+                if (l0 < l1) {
+                    int lo = 0, hi = (int)n_groups;  // cgp[lo] <= l0 < cgp[hi]
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cgp[mid] <= l0) lo = mid; else hi = mid; }
+                    uint32_t g = (uint32_t)lo;
+                    uint32_t cgv = S.cg[g];
+                    uint32_t st = cgv & 0xFFFF, sz = cgv >> 16;
+                    const uint32_t l = l0 - S.cgp[g];
+                    // row-major strict upper triangle of sz x sz: row x starts at x(2 sz - x - 1)/2
+                    const float tg = 2.0f * (float)sz - 1.0f;
+                    int x = (int)((tg - sqrtf(fmaxf(tg * tg - 8.0f * (float)l, 0.0f))) * 0.5f);
+                    if (x > (int)sz - 2) x = (int)sz - 2;
+                    if (x < 0) x = 0;
+                    while ((uint32_t)(x + 1) * (2 * sz - (x + 1) - 1) / 2 <= l) x++;
+                    while ((uint32_t)x * (2 * sz - x - 1) / 2 > l) x--;
+                    uint32_t y = x + 1 + (l - (uint32_t)x * (2 * sz - x - 1) / 2);
+                    uint32_t sx = S.ge_s[st + x], cx = S.ge_c[st + x];
+                    for (uint32_t p = l0; p < l1; p++) {
+                        const uint32_t sy = S.ge_s[st + y], cy = S.ge_c[st + y];
+                        const bool sw = sx > sy;
+                        const uint32_t si = sw ? sy : sx, sj = sw ? sx : sy;
+                        const uint32_t ci = sw ? cy : cx, cj = sw ? cx : cy;
+                        const uint32_t key = si * (2 * N - si - 1) / 2 + (sj - si - 1);
+                        ms_add64(acc_lo + 0 * NP, acc_hi + 0 * NP, key, ci);
+                        ms_add64(acc_lo + 1 * NP, acc_hi + 1 * NP, key, cj);
+                        ms_add64(acc_lo + 2 * NP, acc_hi + 2 * NP, key, 1);
+                        ms_add64(acc_lo + 3 * NP, acc_hi + 3 * NP, key, ci < cj ? ci : cj);
+                        if (SIMPLE) {
+                            const ull prod = (ull)ci * (ull)cj;
+                            ms_add64(acc_lo + 4 * NP, acc_hi + 4 * NP, key, prod);
+                            ms_add64(acc_lo + 5 * NP, acc_hi + 5 * NP, key, hellinger_term(prod));  // u64 += double truncates per increment
+                        }
+                        if (COMPLEX) {
+                            const double ai = (double)ci, aj = (double)cj, Ni = a.ntot[si], Nj = a.ntot[sj];
+                            const double yX = aj * Ni, xY = ai * Nj;
+                            if (xY != yX) {  // equal: both logs are log(1) = 0 exactly
+                                const double r1 = (2 * xY) * __drcp_rn(xY + yX);
+                                atomicAdd(&acc_kl[key], (ai / Ni) * tab_log(r1, S.logtab) + (aj / Nj) * tab_log(2.0 - r1, S.logtab));
+                            }
+                            const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
+                            ms_add64(acc_lo + 6 * NP, acc_hi + 6 * NP, key, (ull)(absint32_ext(wx - wy) - absint32_ext(wx) - absint32_ext(wy)));
+                        }
+                        // advance
+                        if (++y == sz) {
+                            if (++x == (int)sz - 1) {
+                                g++;
+                                if (g < n_groups) { cgv = S.cg[g]; st = cgv & 0xFFFF; sz = cgv >> 16; }
+                                x = 0;
+                            }
+                            y = x + 1;
+                            if (g < n_groups) { sx = S.ge_s[st + x]; cx = S.ge_c[st + x]; }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // flush: one set of global atomics per CTA and pair key
+    for (int key = tid; key < NP; key += MS_THREADS) {
+        const ull dist = ((ull)acc_hi[2 * NP + key] << 32) | acc_lo[2 * NP + key];
+        if (!dist) continue;
+        int i = 0;
+        while ((i + 1) * (2 * N - (i + 1) - 1) / 2 <= key) i++;
+        const int j = i + 1 + (key - i * (2 * N - i - 1) / 2);
+        const size_t n = (size_t)N;
+        const size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
+        const size_t sym = (size_t)j + (n - 1) * i - ((size_t)i * (i - 1) / 2);
+        auto val = [&](int w) { return ((ull)acc_hi[(size_t)w * NP + key] << 32) | acc_lo[(size_t)w * NP + key]; };
+        atomicAdd(&a.nb_shared[ij], val(0));
+        atomicAdd(&a.nb_shared[ji], val(1));
+        atomicAdd(&a.distinct_shared[sym], dist);
+        atomicAdd(&a.braycurtis[sym], val(3));
+        if (SIMPLE) { atomicAdd(&a.chord[ij], val(4)); atomicAdd(&a.hellinger[ij], val(5)); }
+        if (COMPLEX) { atomicAdd(&a.whittaker[ij], val(6)); atomicAdd(&a.kl[ij], acc_kl[key]); }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        loc_groups += __shfl_down_sync(0xffffffffu, loc_groups, d);
+        loc_shared += __shfl_down_sync(0xffffffffu, loc_shared, d);
+        loc_pairs += __shfl_down_sync(0xffffffffu, loc_pairs, d);
+    }
+    if (lane == 0 && (loc_groups | loc_shared | loc_pairs)) {
+        atomicAdd(&a.scalars[0], loc_groups);
+        atomicAdd(&a.scalars[1], loc_shared);
+        atomicAdd(&a.scalars[2], loc_pairs);
+    }
+}
+
 // T[i][j] = sum over solid k-mers e of sample i of f((u64)(c_e * N_j)), f = abs((int)x): the value the
 // reference's Whittaker update adds for a k-mer present in i and absent from j
 // (src/core/SimkaAlgorithm.hpp:481,512).  Computed from the abundance histogram of sample i.
@@ -2141,7 +2415,9 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
         const int nsm = ctx->nsm;
         const uint32_t MG = 1u << mg_bits;
         const unsigned grid = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * 8);
-        if (N <= 32) {
+        const char *mv = getenv("SIMKA_B200_MERGE");  // "sorted": the k_merge32 variant (N <= 32), "generic": k_merge
+        const bool want_generic = mv && !strcmp(mv, "generic"), want_sorted = mv && !strcmp(mv, "sorted");
+        if (N <= 32 && want_sorted) {
             void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge32<true, true> : k_merge32<true, false>)
                                                : (a.complex_ ? k_merge32<false, true> : k_merge32<false, false>);
             int occ = 0;
@@ -2149,6 +2425,15 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, M32_THREADS, sizeof(M32Smem)));
             const unsigned g32 = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * std::max(1, occ));
             kern<<<g32, M32_THREADS, sizeof(M32Smem), st>>>(a);
+        } else if (N >= 2 && N <= MS_MAXN && !want_generic) {
+            void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge_sm<true, true> : k_merge_sm<true, false>)
+                                               : (a.complex_ ? k_merge_sm<false, true> : k_merge_sm<false, false>);
+            int occ = 0;
+            const size_t smem = ms_smem_bytes(N);
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MS_THREADS, smem));
+            const unsigned gs = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * std::max(1, occ));
+            kern<<<gs, MS_THREADS, smem, st>>>(a);
         } else {
             k_merge<<<grid, BLOCK, merge_smem_bytes(N), st>>>(a);
         }
