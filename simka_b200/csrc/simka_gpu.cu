@@ -768,6 +768,7 @@ struct MergeArgs {
     int simple, complex_;
     ull *nb_shared, *distinct_shared, *braycurtis, *chord, *hellinger, *whittaker;
     double *kl;
+    ull *klfix;                  // Jensen-Shannon sums in fixed point (units of 2^-60), exact integer adds
     ull *scalars;                // [0] distinct k-mers, [1] shared k-mers, [2] pairs
     int *error_flag;
 };
@@ -1305,7 +1306,7 @@ constexpr int MS_SLOTS = 2048;
 constexpr int MS_ECAP = 2048;
 constexpr int MS_GCAP = 1024;
 constexpr int MS_MAXN = 64;
-constexpr int MS_NACC = 7;  // u64 accumulators per pair key: sh_ij, sh_ji, distinct, bc, chord, hellinger, whittaker
+constexpr int MS_NACC = 8;  // u64 accumulators per pair key: sh_ij, sh_ji, distinct, bc, chord, hellinger, whittaker (negated), JS (2^-60)
 
 struct MSSmem {
     alignas(16) uint64_t tk[MS_SLOTS];
@@ -1317,11 +1318,11 @@ struct MSSmem {
     uint32_t ge_c[MS_ECAP];
     uint32_t s_start[MS_MAXN], s_pre[MS_MAXN + 1];
     uint8_t ge_s[MS_ECAP];
-    // followed by: double kl[NP]; uint32_t lo[MS_NACC][NP]; uint32_t hi[MS_NACC][NP];
+    // followed by: uint32_t lo[MS_NACC][NP]; uint32_t hi[MS_NACC][NP];
 };
 static size_t ms_smem_bytes(int n) {
     const size_t np = (size_t)n * (n - 1) / 2;
-    return ((sizeof(MSSmem) + 15) & ~(size_t)15) + np * 8 + (size_t)2 * MS_NACC * np * 4 + 16;
+    return ((sizeof(MSSmem) + 15) & ~(size_t)15) + (size_t)2 * MS_NACC * np * 4 + 16;
 }
 
 __device__ __forceinline__ void ms_add64(uint32_t *lo, uint32_t *hi, uint32_t idx, unsigned long long v) {
@@ -1339,14 +1340,12 @@ k_merge_sm(MergeArgs a) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = a.n;
     const int NP = N * (N - 1) / 2;
-    double *acc_kl = reinterpret_cast<double *>(smem_raw + ((sizeof(MSSmem) + 15) & ~(size_t)15));
-    uint32_t *acc_lo = reinterpret_cast<uint32_t *>(acc_kl + NP);
+    uint32_t *acc_lo = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(MSSmem) + 15) & ~(size_t)15));
     uint32_t *acc_hi = acc_lo + (size_t)MS_NACC * NP;
     const uint32_t MG = 1u << a.mg_bits;
     const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
     const size_t ostride = ((size_t)1 << a.fg_bits) + 1;
 
-    for (int i = tid; i < NP; i += MS_THREADS) acc_kl[i] = 0.0;
     for (int i = tid; i < 2 * MS_NACC * NP; i += MS_THREADS) acc_lo[i] = 0;  // lo and hi are contiguous
     if (tid < 128) S.logtab[tid] = a.logtab[tid];
     ull loc_groups = 0, loc_shared = 0, loc_pairs = 0;
@@ -1513,10 +1512,14 @@ k_merge_sm(MergeArgs a) {
                             const double yX = aj * Ni, xY = ai * Nj;
                             if (xY != yX) {  // equal: both logs are log(1) = 0 exactly
                                 const double r1 = (2 * xY) * __drcp_rn(xY + yX);
-                                atomicAdd(&acc_kl[key], (ai / Ni) * tab_log(r1, S.logtab) + (aj / Nj) * tab_log(2.0 - r1, S.logtab));
+                                // the term d1 + d2 >= 0 (Jensen), |term| < 2: exact integer accumulation in units of 2^-60
+                                // (rounding 4e-19 per term, order-independent => bit-reproducible sums)
+                                const double term = (ai / Ni) * tab_log(r1, S.logtab) + (aj / Nj) * tab_log(2.0 - r1, S.logtab);
+                                ms_add64(acc_lo + 7 * NP, acc_hi + 7 * NP, key, (ull)__double2ll_rn(ldexp(term, 60)));
                             }
                             const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
-                            ms_add64(acc_lo + 6 * NP, acc_hi + 6 * NP, key, (ull)(absint32_ext(wx - wy) - absint32_ext(wx) - absint32_ext(wy)));
+                            // accumulated negated (the both-present value minus the two one-sided values is <= 0 in practice)
+                            ms_add64(acc_lo + 6 * NP, acc_hi + 6 * NP, key, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
                         }
                         // advance
                         if (++y == sz) {
@@ -1551,7 +1554,7 @@ k_merge_sm(MergeArgs a) {
         atomicAdd(&a.distinct_shared[sym], dist);
         atomicAdd(&a.braycurtis[sym], val(3));
         if (SIMPLE) { atomicAdd(&a.chord[ij], val(4)); atomicAdd(&a.hellinger[ij], val(5)); }
-        if (COMPLEX) { atomicAdd(&a.whittaker[ij], val(6)); atomicAdd(&a.kl[ij], acc_kl[key]); }
+        if (COMPLEX) { atomicAdd(&a.whittaker[ij], 0ull - val(6)); atomicAdd(&a.klfix[ij], val(7)); }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -1814,6 +1817,7 @@ struct simka_ctx {
     size_t acc_bytes = 0;
     ull *a_nb_shared = nullptr, *a_distinct = nullptr, *a_bc = nullptr, *a_chord = nullptr, *a_hell = nullptr, *a_whit = nullptr, *a_T = nullptr, *a_scalars = nullptr;
     double *a_kl = nullptr, *a_ntot = nullptr;
+    ull *a_klfix = nullptr;
     DevBuf d_ptrs, d_logtab, d_chain, d_isum;
     bool import_pending = false;
     unsigned long long scan_epoch = 0;
@@ -2365,8 +2369,8 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
         ctx->import_pending = false;
     }
     const size_t nn = (size_t)N * N, ns = (size_t)N * (N + 1) / 2;
-    // slab: nb_shared nn | distinct ns | bc ns | chord nn | hell nn | whit nn | T nn | scalars 4 | kl nn (f64) | ntot N (f64)
-    const size_t words = nn + ns + ns + nn + nn + nn + nn + 4 + nn + N;
+    // slab: nb_shared nn | distinct ns | bc ns | chord nn | hell nn | whit nn | T nn | scalars 4 | kl nn (f64) | klfix nn (i64, 2^-60 units) | ntot N (f64)
+    const size_t words = nn + ns + ns + nn + nn + nn + nn + 4 + nn + nn + N;
     ctx->acc_bytes = words * 8;
     if (ctx->d_acc.reserve(ctx->acc_bytes)) { ctx->set_error("out of device memory (accumulators)"); return SIMKA_ERR_NOMEM; }
     harvest_timings(ctx, 0); harvest_timings(ctx, 1);
@@ -2383,6 +2387,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
     ctx->a_T = p; p += nn;
     ctx->a_scalars = p; p += 4;
     ctx->a_kl = reinterpret_cast<double *>(p); p += nn;
+    ctx->a_klfix = p; p += nn;
     ctx->a_ntot = reinterpret_cast<double *>(p);
     std::vector<double> ntot(N);
     uint64_t total_entries = 0;
@@ -2410,7 +2415,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
         a.logtab = ctx->d_logtab.as<double2>();
         a.simple = ctx->prm.simple_dist; a.complex_ = ctx->prm.complex_dist;
         a.nb_shared = ctx->a_nb_shared; a.distinct_shared = ctx->a_distinct; a.braycurtis = ctx->a_bc;
-        a.chord = ctx->a_chord; a.hellinger = ctx->a_hell; a.whittaker = ctx->a_whit; a.kl = ctx->a_kl;
+        a.chord = ctx->a_chord; a.hellinger = ctx->a_hell; a.whittaker = ctx->a_whit; a.kl = ctx->a_kl; a.klfix = ctx->a_klfix;
         a.scalars = ctx->a_scalars; a.error_flag = d_error;
         const int nsm = ctx->nsm;
         const uint32_t MG = 1u << mg_bits;
@@ -2471,6 +2476,7 @@ int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) {
     const ull *distinct = nb_shared + nn, *bc = distinct + ns, *chord = bc + ns, *hell = chord + nn, *whit = hell + nn;
     const ull *scal = whit + nn + nn;
     const double *kl = reinterpret_cast<const double *>(scal + 4);
+    const long long *klfix = reinterpret_cast<const long long *>(scal + 4 + nn);
     out->nb_samples = N; out->simple_dist = ctx->prm.simple_dist; out->complex_dist = ctx->prm.complex_dist;
     out->nb_distinct_kmers = scal[0];
     out->nb_shared_kmers = scal[1];
@@ -2504,7 +2510,7 @@ int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) {
             for (int i = 0; i < N; i++)
                 for (int j = i + 1; j < N; j++) {
                     const size_t ij = (size_t)i * N + j, ji = (size_t)j * N + i;
-                    double v = kl[ij];
+                    double v = kl[ij] + ldexp((double)klfix[ij], -60);
                     const double Ni = (double)ctx->global_totals[i].nb_kmers, Nj = (double)ctx->global_totals[j].nb_kmers;
                     // k-mers present in exactly one of the two samples: (c/N_x) * log(2 c N_y / (c N_y + 0)) each
                     const ull only_i = ctx->samples[i].local.nb_kmers - nb_shared[ij];
