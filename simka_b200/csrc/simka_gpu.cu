@@ -766,6 +766,7 @@ struct MergeArgs {
     const double *ntot;          // [n] global solid k-mer totals N_i as double
     const double2 *logtab;       // [128] tab_log table
     int simple, complex_;
+    int count_only;              // k_merge: only the distinct / shared k-mer counts (the tiled merge does the pairs)
     ull *nb_shared, *distinct_shared, *braycurtis, *chord, *hellinger, *whittaker;
     double *kl;
     ull *klfix;                  // Jensen-Shannon sums in fixed point (units of 2^-60), exact integer adds
@@ -917,6 +918,7 @@ k_merge(MergeArgs a) {
             const uint32_t n_shared_groups = s_shared;
             if (tid == 0) { loc_groups += s_groups; loc_shared += s_shared; }
             __syncthreads();
+            if (a.count_only) continue;
             if (n_sub > MRG_CAP) { if (tid == 0) *a.error_flag = 4; continue; }
             if (n_shared_groups == 0) continue;  // nothing shared in this bin: no accumulator changes
             // phase 3: scatter the entries of shared k-mers into their groups
@@ -1317,11 +1319,12 @@ struct MSSmem {
     uint32_t cgp[MS_GCAP + 1];
     uint32_t ge_c[MS_ECAP];
     uint32_t s_start[MS_MAXN], s_pre[MS_MAXN + 1];
+    int s_gid[MS_MAXN];            // local sample slot -> global sample id
     uint8_t ge_s[MS_ECAP];
     // followed by: uint32_t lo[MS_NACC][NP]; uint32_t hi[MS_NACC][NP];
 };
 static size_t ms_smem_bytes(int n) {
-    const size_t np = (size_t)n * (n - 1) / 2;
+    const size_t np = n > MS_MAXN ? 1024 : (size_t)n * (n - 1) / 2;  // tiled: 32 x 32 pair keys
     return ((sizeof(MSSmem) + 15) & ~(size_t)15) + (size_t)2 * MS_NACC * np * 4 + 16;
 }
 
@@ -1332,229 +1335,270 @@ __device__ __forceinline__ void ms_add64(uint32_t *lo, uint32_t *hi, uint32_t id
     if (hv) atomicAdd(&hi[idx], hv);
 }
 
-template <bool SIMPLE, bool COMPLEX>
+// TILED (N > 64): the sample pairs are cut into tiles of 32 x 32 samples (block I x block J, I <= J); a CTA works on
+// one tile: it gathers only the <= 64 samples of its two blocks, groups them, and accumulates the pairs that belong
+// to the tile (cross pairs for I != J, all pairs for I == J) into 1024 (496) shared-memory accumulators.  Grouping
+// work is repeated once per tile a block takes part in (B+1 times for B blocks); the pair work is not.
+template <bool SIMPLE, bool COMPLEX, bool TILED>
 __global__ void __launch_bounds__(MS_THREADS, 2)
 k_merge_sm(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MSSmem &S = *reinterpret_cast<MSSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = a.n;
-    const int NP = N * (N - 1) / 2;
     uint32_t *acc_lo = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(MSSmem) + 15) & ~(size_t)15));
-    uint32_t *acc_hi = acc_lo + (size_t)MS_NACC * NP;
     const uint32_t MG = 1u << a.mg_bits;
     const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
     const size_t ostride = ((size_t)1 << a.fg_bits) + 1;
+    const uint32_t G = gridDim.x, c = blockIdx.x;
+    const uint32_t B = (uint32_t)(N + 31) / 32, T = TILED ? B * (B + 1) / 2 : 1;
+    const bool spread = G >= T;  // several CTAs per tile (each takes a stride of the merge bins) or several tiles per CTA
 
-    for (int i = tid; i < 2 * MS_NACC * NP; i += MS_THREADS) acc_lo[i] = 0;  // lo and hi are contiguous
     if (tid < 128) S.logtab[tid] = a.logtab[tid];
     ull loc_groups = 0, loc_shared = 0, loc_pairs = 0;
-    __syncthreads();
 
-    for (uint32_t mb = blockIdx.x; mb < MG; mb += gridDim.x) {
-        // segment descriptors of the N samples (warps 0 and 1 cover up to 64 samples)
-        if (tid < MS_MAXN) {
-            uint32_t len = 0;
-            if (tid < N) {
-                const uint32_t b0 = a.off[(size_t)tid * ostride + (size_t)mb * q];
-                const uint32_t b1 = a.off[(size_t)tid * ostride + (size_t)(mb + 1) * q];
-                S.s_start[tid] = b0;
-                len = b1 - b0;
-            }
-            S.s_pre[tid] = len;  // lengths first, scanned below
+    for (uint32_t tile = c % T; tile < T; tile += spread ? T : G) {
+        const uint32_t bin_first = spread ? c / T : 0, bin_stride = spread ? (G - tile + T - 1) / T : 1;
+        // tile geometry: row-major upper triangle (with diagonal) over the B sample blocks
+        uint32_t I = 0, J = 0;
+        if (TILED) {
+            uint32_t rem = tile;
+            while (rem >= B - I) { rem -= B - I; I++; }
+            J = I + rem;
+        }
+        const bool diag = !TILED || I == J;
+        const int NPk = TILED ? (diag ? 496 : 1024) : N * (N - 1) / 2;  // pair keys of this tile
+        uint32_t *acc_hi = acc_lo + (size_t)MS_NACC * NPk;
+        __syncthreads();  // the flush of the previous tile is done
+        for (int i = tid; i < 2 * MS_NACC * NPk; i += MS_THREADS) acc_lo[i] = 0;  // lo and hi are contiguous
+        if (tid < MS_MAXN) {  // local sample slot -> global sample id (-1: unused)
+            int gs = tid;
+            if (TILED) gs = tid < 32 ? (int)(32 * I) + tid : (diag ? -1 : (int)(32 * J) + tid - 32);
+            S.s_gid[tid] = (gs >= 0 && gs < N) ? gs : -1;
         }
         __syncthreads();
-        if (tid < 32) {
-            const uint32_t l0 = S.s_pre[tid], l1 = S.s_pre[tid + 32];
-            uint32_t inc0 = l0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc0, d); if (lane >= d) inc0 += u; }
-            const uint32_t tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-            uint32_t inc1 = l1;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc1, d); if (lane >= d) inc1 += u; }
-            const uint32_t tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-            S.s_pre[tid] = inc0 - l0;
-            S.s_pre[tid + 32] = tot0 + inc1 - l1;
-            if (tid == 31) S.s_pre[64] = tot0 + tot1;
-        }
-        __syncthreads();
-        const uint32_t n_e = S.s_pre[64];
-        if (n_e == 0) { __syncthreads(); continue; }
-        uint32_t R = 1;
-        if (n_e > MS_ECAP) { while ((uint64_t)R * (MS_ECAP / 2) < n_e) R <<= 1; }
-        for (uint32_t r = 0; r < R; r++) {
-            {   // clean table
-                uint4 *pk = reinterpret_cast<uint4 *>(S.tk) + tid;
-                const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int qq = 0; qq < MS_SLOTS * 8 / 16 / MS_THREADS; qq++) pk[qq * MS_THREADS] = e;
-                uint4 *pg = reinterpret_cast<uint4 *>(S.gcnt) + tid;
-#pragma unroll
-                for (int qq = 0; qq < MS_SLOTS * 4 / 16 / MS_THREADS; qq++) pg[qq * MS_THREADS] = z;
-            }
-            __syncthreads();
-            // phase 1: insert keys, count group sizes
-            for (uint32_t i = tid; i < n_e; i += MS_THREADS) {
-                int lo = 0, hi = 64;  // s_pre[lo] <= i < s_pre[hi]   (s_pre[N..64] = n_e)
-#pragma unroll
-                for (int st = 0; st < 6; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
-                const uint64_t h = a.eh[lo][S.s_start[lo] + (i - S.s_pre[lo])];
-                const uint64_t hh = simka::hash2(h);
-                if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
-                uint32_t slot = (uint32_t)(hh >> 40) & (MS_SLOTS - 1);
-                volatile uint64_t *vk = S.tk;
-                int probes = 0;
-                for (;;) {
-                    uint64_t cur = vk[slot];
-                    if (cur == EMPTY) {
-                        cur = atomicCAS(reinterpret_cast<ull *>(&S.tk[slot]), (ull)EMPTY, (ull)h);
-                        if (cur == EMPTY) cur = h;
-                    }
-                    if (cur == h) { atomicAdd(&S.gcnt[slot], 1u); break; }
-                    slot = (slot + 1) & (MS_SLOTS - 1);
-                    if (++probes >= MS_SLOTS) { *a.error_flag = 3; break; }
+
+        for (uint32_t mb = bin_first; mb < MG; mb += bin_stride) {
+            // segment descriptors of the (<= 64) samples of this tile
+            if (tid < MS_MAXN) {
+                uint32_t len = 0;
+                const int gs = S.s_gid[tid];
+                if (gs >= 0) {
+                    const uint32_t b0 = a.off[(size_t)gs * ostride + (size_t)mb * q];
+                    const uint32_t b1 = a.off[(size_t)gs * ostride + (size_t)(mb + 1) * q];
+                    S.s_start[tid] = b0;
+                    len = b1 - b0;
                 }
+                S.s_pre[tid] = len;  // lengths first, scanned below
             }
             __syncthreads();
-            // phase 2: group statistics + compact list of the shared groups (>= 2 samples)
-            unsigned long long packed = 0;  // groups (16 bits) | entries (16 bits) | pairs (32 bits)
-            uint32_t g8[MS_SLOTS / MS_THREADS];
+            if (tid < 32) {
+                const uint32_t l0 = S.s_pre[tid], l1 = S.s_pre[tid + 32];
+                uint32_t inc0 = l0;
 #pragma unroll
-            for (int qq = 0; qq < MS_SLOTS / MS_THREADS; qq++) {
-                const uint32_t g = S.gcnt[tid * (MS_SLOTS / MS_THREADS) + qq];
-                g8[qq] = g;
-                loc_groups += g > 0;
-                if (g > 1) packed += 1ull | ((unsigned long long)g << 16) | ((unsigned long long)(g * (g - 1) / 2) << 32);
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc0, d); if (lane >= d) inc0 += u; }
+                const uint32_t tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+                uint32_t inc1 = l1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc1, d); if (lane >= d) inc1 += u; }
+                const uint32_t tot1 = __shfl_sync(0xffffffffu, inc1, 31);
+                S.s_pre[tid] = inc0 - l0;
+                S.s_pre[tid + 32] = tot0 + inc1 - l1;
+                if (tid == 31) S.s_pre[64] = tot0 + tot1;
             }
-            unsigned long long total;
-            unsigned long long ex = block_scan_u64(packed, S.scan_tmp, &total);
-            const uint32_t n_groups = (uint32_t)(total & 0xFFFF), n_sub = (uint32_t)((total >> 16) & 0xFFFF);
-            const uint32_t P = (uint32_t)(total >> 32);
-            if (n_groups > MS_GCAP || n_sub > MS_ECAP) {  // cannot happen for hashed keys; reported, not silent
-                if (tid == 0) *a.error_flag = 4;
+            __syncthreads();
+            const uint32_t n_e = S.s_pre[64];
+            if (n_e == 0) { __syncthreads(); continue; }
+            uint32_t R = 1;
+            if (n_e > MS_ECAP) { while ((uint64_t)R * (MS_ECAP / 2) < n_e) R <<= 1; }
+            for (uint32_t r = 0; r < R; r++) {
+                {   // clean table
+                    uint4 *pk = reinterpret_cast<uint4 *>(S.tk) + tid;
+                    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int qq = 0; qq < MS_SLOTS * 8 / 16 / MS_THREADS; qq++) pk[qq * MS_THREADS] = e;
+                    uint4 *pg = reinterpret_cast<uint4 *>(S.gcnt) + tid;
+#pragma unroll
+                    for (int qq = 0; qq < MS_SLOTS * 4 / 16 / MS_THREADS; qq++) pg[qq * MS_THREADS] = z;
+                }
                 __syncthreads();
-                continue;
-            }
+                // phase 1: insert keys, count group sizes
+                for (uint32_t i = tid; i < n_e; i += MS_THREADS) {
+                    int lo = 0, hi = 64;  // s_pre[lo] <= i < s_pre[hi]   (empty slots repeat the next prefix)
 #pragma unroll
-            for (int qq = 0; qq < MS_SLOTS / MS_THREADS; qq++) {
-                const uint32_t g = g8[qq];
-                uint32_t v = M32_SKIP;
-                if (g > 1) {
-                    const uint32_t gi = (uint32_t)(ex & 0xFFFF), st = (uint32_t)((ex >> 16) & 0xFFFF), pp = (uint32_t)(ex >> 32);
-                    S.cg[gi] = st | (g << 16);
-                    S.cgp[gi] = pp;
-                    v = st + g;  // fill cursor counts down from the end
-                    ex += 1ull | ((unsigned long long)g << 16) | ((unsigned long long)(g * (g - 1) / 2) << 32);
-                    loc_shared++;
-                }
-                S.gcnt[tid * (MS_SLOTS / MS_THREADS) + qq] = v;
-            }
-            if (tid == 0) { S.cgp[n_groups] = P; loc_pairs += P; }
-            __syncthreads();
-            if (n_groups == 0) continue;  // nothing shared in this pass: no accumulator changes
-            // phase 3: scatter the entries of shared k-mers into their groups
-            for (uint32_t i = tid; i < n_e; i += MS_THREADS) {
-                int lo = 0, hi = 64;
-#pragma unroll
-                for (int st = 0; st < 6; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
-                const size_t idx = S.s_start[lo] + (i - S.s_pre[lo]);
-                const uint64_t h = a.eh[lo][idx];
-                const uint64_t hh = simka::hash2(h);
-                if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
-                uint32_t slot = (uint32_t)(hh >> 40) & (MS_SLOTS - 1);
-                int pr = 0;
-                while (S.tk[slot] != h && ++pr <= MS_SLOTS) slot = (slot + 1) & (MS_SLOTS - 1);
-                if (pr > MS_SLOTS) { *a.error_flag = 7; continue; }  // inconsistent input (never for lists built by this library)
-                if (S.gcnt[slot] == M32_SKIP) continue;  // private k-mer: contributes to no pair
-                const uint32_t pos = atomicSub(&S.gcnt[slot], 1u) - 1;
-                S.ge_s[pos] = (uint8_t)lo;
-                S.ge_c[pos] = a.ec[lo][idx];
-            }
-            __syncthreads();
-            // phase 4: flat pair enumeration, one contiguous run of pairs per thread
-            {
-                const uint32_t per = (P + MS_THREADS - 1) / MS_THREADS;
-                const uint32_t l0 = min(P, tid * per), l1 = min(P, l0 + per);
-                if (l0 < l1) {
-                    int lo = 0, hi = (int)n_groups;  // cgp[lo] <= l0 < cgp[hi]
-                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cgp[mid] <= l0) lo = mid; else hi = mid; }
-                    uint32_t g = (uint32_t)lo;
-                    uint32_t cgv = S.cg[g];
-                    uint32_t st = cgv & 0xFFFF, sz = cgv >> 16;
-                    const uint32_t l = l0 - S.cgp[g];
-                    // row-major strict upper triangle of sz x sz: row x starts at x(2 sz - x - 1)/2
-                    const float tg = 2.0f * (float)sz - 1.0f;
-                    int x = (int)((tg - sqrtf(fmaxf(tg * tg - 8.0f * (float)l, 0.0f))) * 0.5f);
-                    if (x > (int)sz - 2) x = (int)sz - 2;
-                    if (x < 0) x = 0;
-                    while ((uint32_t)(x + 1) * (2 * sz - (x + 1) - 1) / 2 <= l) x++;
-                    while ((uint32_t)x * (2 * sz - x - 1) / 2 > l) x--;
-                    uint32_t y = x + 1 + (l - (uint32_t)x * (2 * sz - x - 1) / 2);
-                    uint32_t sx = S.ge_s[st + x], cx = S.ge_c[st + x];
-                    for (uint32_t p = l0; p < l1; p++) {
-                        const uint32_t sy = S.ge_s[st + y], cy = S.ge_c[st + y];
-                        const bool sw = sx > sy;
-                        const uint32_t si = sw ? sy : sx, sj = sw ? sx : sy;
-                        const uint32_t ci = sw ? cy : cx, cj = sw ? cx : cy;
-                        const uint32_t key = si * (2 * N - si - 1) / 2 + (sj - si - 1);
-                        ms_add64(acc_lo + 0 * NP, acc_hi + 0 * NP, key, ci);
-                        ms_add64(acc_lo + 1 * NP, acc_hi + 1 * NP, key, cj);
-                        ms_add64(acc_lo + 2 * NP, acc_hi + 2 * NP, key, 1);
-                        ms_add64(acc_lo + 3 * NP, acc_hi + 3 * NP, key, ci < cj ? ci : cj);
-                        if (SIMPLE) {
-                            const ull prod = (ull)ci * (ull)cj;
-                            ms_add64(acc_lo + 4 * NP, acc_hi + 4 * NP, key, prod);
-                            ms_add64(acc_lo + 5 * NP, acc_hi + 5 * NP, key, hellinger_term(prod));  // u64 += double truncates per increment
+                    for (int st = 0; st < 6; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
+                    const uint64_t h = a.eh[S.s_gid[lo]][S.s_start[lo] + (i - S.s_pre[lo])];
+                    const uint64_t hh = simka::hash2(h);
+                    if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
+                    uint32_t slot = (uint32_t)(hh >> 40) & (MS_SLOTS - 1);
+                    volatile uint64_t *vk = S.tk;
+                    int probes = 0;
+                    for (;;) {
+                        uint64_t cur = vk[slot];
+                        if (cur == EMPTY) {
+                            cur = atomicCAS(reinterpret_cast<ull *>(&S.tk[slot]), (ull)EMPTY, (ull)h);
+                            if (cur == EMPTY) cur = h;
                         }
-                        if (COMPLEX) {
-                            const double ai = (double)ci, aj = (double)cj, Ni = a.ntot[si], Nj = a.ntot[sj];
-                            const double yX = aj * Ni, xY = ai * Nj;
-                            if (xY != yX) {  // equal: both logs are log(1) = 0 exactly
-                                const double r1 = (2 * xY) * __drcp_rn(xY + yX);
-                                // the term d1 + d2 >= 0 (Jensen), |term| < 2: exact integer accumulation in units of 2^-60
-                                // (rounding 4e-19 per term, order-independent => bit-reproducible sums)
-                                const double term = (ai / Ni) * tab_log(r1, S.logtab) + (aj / Nj) * tab_log(2.0 - r1, S.logtab);
-                                ms_add64(acc_lo + 7 * NP, acc_hi + 7 * NP, key, (ull)__double2ll_rn(ldexp(term, 60)));
-                            }
-                            const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
-                            // accumulated negated (the both-present value minus the two one-sided values is <= 0 in practice)
-                            ms_add64(acc_lo + 6 * NP, acc_hi + 6 * NP, key, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
-                        }
-                        // advance
-                        if (++y == sz) {
-                            if (++x == (int)sz - 1) {
-                                g++;
-                                if (g < n_groups) { cgv = S.cg[g]; st = cgv & 0xFFFF; sz = cgv >> 16; }
-                                x = 0;
-                            }
-                            y = x + 1;
-                            if (g < n_groups) { sx = S.ge_s[st + x]; cx = S.ge_c[st + x]; }
-                        }
+                        if (cur == h) { atomicAdd(&S.gcnt[slot], 1u); break; }
+                        slot = (slot + 1) & (MS_SLOTS - 1);
+                        if (++probes >= MS_SLOTS) { *a.error_flag = 3; break; }
                     }
                 }
+                __syncthreads();
+                // phase 2: group statistics + compact list of the shared groups (>= 2 samples)
+                unsigned long long packed = 0;  // groups (16 bits) | entries (16 bits) | pairs (32 bits)
+                uint32_t g8[MS_SLOTS / MS_THREADS];
+#pragma unroll
+                for (int qq = 0; qq < MS_SLOTS / MS_THREADS; qq++) {
+                    const uint32_t g = S.gcnt[tid * (MS_SLOTS / MS_THREADS) + qq];
+                    g8[qq] = g;
+                    loc_groups += g > 0;
+                    if (g > 1) packed += 1ull | ((unsigned long long)g << 16) | ((unsigned long long)(g * (g - 1) / 2) << 32);
+                }
+                unsigned long long total;
+                unsigned long long ex = block_scan_u64(packed, S.scan_tmp, &total);
+                const uint32_t n_groups = (uint32_t)(total & 0xFFFF), n_sub = (uint32_t)((total >> 16) & 0xFFFF);
+                const uint32_t P = (uint32_t)(total >> 32);
+                if (n_groups > MS_GCAP || n_sub > MS_ECAP) {  // cannot happen for hashed keys; reported, not silent
+                    if (tid == 0) *a.error_flag = 4;
+                    __syncthreads();
+                    continue;
+                }
+#pragma unroll
+                for (int qq = 0; qq < MS_SLOTS / MS_THREADS; qq++) {
+                    const uint32_t g = g8[qq];
+                    uint32_t v = M32_SKIP;
+                    if (g > 1) {
+                        const uint32_t gi = (uint32_t)(ex & 0xFFFF), st = (uint32_t)((ex >> 16) & 0xFFFF), pp = (uint32_t)(ex >> 32);
+                        S.cg[gi] = st | (g << 16);
+                        S.cgp[gi] = pp;
+                        v = st + g;  // fill cursor counts down from the end
+                        ex += 1ull | ((unsigned long long)g << 16) | ((unsigned long long)(g * (g - 1) / 2) << 32);
+                        loc_shared++;
+                    }
+                    S.gcnt[tid * (MS_SLOTS / MS_THREADS) + qq] = v;
+                }
+                if (tid == 0) S.cgp[n_groups] = P;
+                __syncthreads();
+                if (n_groups == 0) continue;  // nothing shared in this pass: no accumulator changes
+                // phase 3: scatter the entries of shared k-mers into their groups
+                for (uint32_t i = tid; i < n_e; i += MS_THREADS) {
+                    int lo = 0, hi = 64;
+#pragma unroll
+                    for (int st = 0; st < 6; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
+                    const size_t idx = S.s_start[lo] + (i - S.s_pre[lo]);
+                    const int gsid = S.s_gid[lo];
+                    const uint64_t h = a.eh[gsid][idx];
+                    const uint64_t hh = simka::hash2(h);
+                    if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
+                    uint32_t slot = (uint32_t)(hh >> 40) & (MS_SLOTS - 1);
+                    int pr = 0;
+                    while (S.tk[slot] != h && ++pr <= MS_SLOTS) slot = (slot + 1) & (MS_SLOTS - 1);
+                    if (pr > MS_SLOTS) { *a.error_flag = 7; continue; }  // inconsistent input (never for lists built by this library)
+                    if (S.gcnt[slot] == M32_SKIP) continue;  // private k-mer: contributes to no pair
+                    const uint32_t pos = atomicSub(&S.gcnt[slot], 1u) - 1;
+                    S.ge_s[pos] = (uint8_t)lo;
+                    S.ge_c[pos] = a.ec[gsid][idx];
+                }
+                __syncthreads();
+                // phase 4: flat pair enumeration, one contiguous run of pairs per thread
+                {
+                    const uint32_t per = (P + MS_THREADS - 1) / MS_THREADS;
+                    const uint32_t l0 = min(P, tid * per), l1 = min(P, l0 + per);
+                    if (l0 < l1) {
+                        int lo = 0, hi = (int)n_groups;  // cgp[lo] <= l0 < cgp[hi]
+                        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cgp[mid] <= l0) lo = mid; else hi = mid; }
+                        uint32_t g = (uint32_t)lo;
+                        uint32_t cgv = S.cg[g];
+                        uint32_t st = cgv & 0xFFFF, sz = cgv >> 16;
+                        const uint32_t l = l0 - S.cgp[g];
+                        // row-major strict upper triangle of sz x sz: row x starts at x(2 sz - x - 1)/2
+                        const float tg = 2.0f * (float)sz - 1.0f;
+                        int x = (int)((tg - sqrtf(fmaxf(tg * tg - 8.0f * (float)l, 0.0f))) * 0.5f);
+                        if (x > (int)sz - 2) x = (int)sz - 2;
+                        if (x < 0) x = 0;
+                        while ((uint32_t)(x + 1) * (2 * sz - (x + 1) - 1) / 2 <= l) x++;
+                        while ((uint32_t)x * (2 * sz - x - 1) / 2 > l) x--;
+                        uint32_t y = x + 1 + (l - (uint32_t)x * (2 * sz - x - 1) / 2);
+                        uint32_t sx = S.ge_s[st + x], cx = S.ge_c[st + x];
+                        for (uint32_t p = l0; p < l1; p++) {
+                            const uint32_t sy = S.ge_s[st + y], cy = S.ge_c[st + y];
+                            // pairs of two samples of the same block belong to the diagonal tile of that block
+                            if (!TILED || diag || ((sx < 32) != (sy < 32))) {
+                                const bool sw = sx > sy;
+                                const uint32_t si = sw ? sy : sx, sj = sw ? sx : sy;  // local slots, si < sj
+                                const uint32_t ci = sw ? cy : cx, cj = sw ? cx : cy;
+                                uint32_t key;
+                                if (!TILED) key = si * (2 * N - si - 1) / 2 + (sj - si - 1);
+                                else if (diag) key = si * (63 - si) / 2 + (sj - si - 1);
+                                else key = si * 32 + (sj - 32);
+                                if (TILED) loc_pairs++;
+                                ms_add64(acc_lo + 0 * NPk, acc_hi + 0 * NPk, key, ci);
+                                ms_add64(acc_lo + 1 * NPk, acc_hi + 1 * NPk, key, cj);
+                                ms_add64(acc_lo + 2 * NPk, acc_hi + 2 * NPk, key, 1);
+                                ms_add64(acc_lo + 3 * NPk, acc_hi + 3 * NPk, key, ci < cj ? ci : cj);
+                                if (SIMPLE) {
+                                    const ull prod = (ull)ci * (ull)cj;
+                                    ms_add64(acc_lo + 4 * NPk, acc_hi + 4 * NPk, key, prod);
+                                    ms_add64(acc_lo + 5 * NPk, acc_hi + 5 * NPk, key, hellinger_term(prod));  // u64 += double truncates per increment
+                                }
+                                if (COMPLEX) {
+                                    const double ai = (double)ci, aj = (double)cj, Ni = a.ntot[S.s_gid[si]], Nj = a.ntot[S.s_gid[sj]];
+                                    const double yX = aj * Ni, xY = ai * Nj;
+                                    if (xY != yX) {  // equal: both logs are log(1) = 0 exactly
+                                        const double r1 = (2 * xY) * __drcp_rn(xY + yX);
+                                        // the term d1 + d2 >= 0 (Jensen), |term| < 2: exact integer accumulation in units of 2^-60
+                                        // (rounding 4e-19 per term, order-independent => bit-reproducible sums)
+                                        const double term = (ai / Ni) * tab_log(r1, S.logtab) + (aj / Nj) * tab_log(2.0 - r1, S.logtab);
+                                        ms_add64(acc_lo + 7 * NPk, acc_hi + 7 * NPk, key, (ull)__double2ll_rn(ldexp(term, 60)));
+                                    }
+                                    const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
+                                    // accumulated negated (the both-present value minus the two one-sided values is <= 0 in practice)
+                                    ms_add64(acc_lo + 6 * NPk, acc_hi + 6 * NPk, key, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
+                                }
+                            }
+                            // advance
+                            if (++y == sz) {
+                                if (++x == (int)sz - 1) {
+                                    g++;
+                                    if (g < n_groups) { cgv = S.cg[g]; st = cgv & 0xFFFF; sz = cgv >> 16; }
+                                    x = 0;
+                                }
+                                y = x + 1;
+                                if (g < n_groups) { sx = S.ge_s[st + x]; cx = S.ge_c[st + x]; }
+                            }
+                        }
+                    }
+                    if (!TILED && tid == 0) loc_pairs += P;
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
-    }
-    __syncthreads();
-    // flush: one set of global atomics per CTA and pair key
-    for (int key = tid; key < NP; key += MS_THREADS) {
-        const ull dist = ((ull)acc_hi[2 * NP + key] << 32) | acc_lo[2 * NP + key];
-        if (!dist) continue;
-        int i = 0;
-        while ((i + 1) * (2 * N - (i + 1) - 1) / 2 <= key) i++;
-        const int j = i + 1 + (key - i * (2 * N - i - 1) / 2);
-        const size_t n = (size_t)N;
-        const size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
-        const size_t sym = (size_t)j + (n - 1) * i - ((size_t)i * (i - 1) / 2);
-        auto val = [&](int w) { return ((ull)acc_hi[(size_t)w * NP + key] << 32) | acc_lo[(size_t)w * NP + key]; };
-        atomicAdd(&a.nb_shared[ij], val(0));
-        atomicAdd(&a.nb_shared[ji], val(1));
-        atomicAdd(&a.distinct_shared[sym], dist);
-        atomicAdd(&a.braycurtis[sym], val(3));
-        if (SIMPLE) { atomicAdd(&a.chord[ij], val(4)); atomicAdd(&a.hellinger[ij], val(5)); }
-        if (COMPLEX) { atomicAdd(&a.whittaker[ij], 0ull - val(6)); atomicAdd(&a.klfix[ij], val(7)); }
+        __syncthreads();
+        // flush: one set of global atomics per CTA, tile and pair key
+        for (int key = tid; key < NPk; key += MS_THREADS) {
+            const ull dist = ((ull)acc_hi[2 * NPk + key] << 32) | acc_lo[2 * NPk + key];
+            if (!dist) continue;
+            int li, lj;  // local slots of the pair
+            if (TILED && !diag) { li = key >> 5; lj = 32 + (key & 31); }
+            else {
+                const int n_loc = TILED ? 32 : N;
+                li = 0;
+                while ((li + 1) * (2 * n_loc - (li + 1) - 1) / 2 <= key) li++;
+                lj = li + 1 + (key - li * (2 * n_loc - li - 1) / 2);
+            }
+            const int i = S.s_gid[li], j = S.s_gid[lj];
+            const size_t n = (size_t)N;
+            const size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
+            const size_t sym = (size_t)j + (n - 1) * i - ((size_t)i * (i - 1) / 2);
+            auto val = [&](int w) { return ((ull)acc_hi[(size_t)w * NPk + key] << 32) | acc_lo[(size_t)w * NPk + key]; };
+            atomicAdd(&a.nb_shared[ij], val(0));
+            atomicAdd(&a.nb_shared[ji], val(1));
+            atomicAdd(&a.distinct_shared[sym], dist);
+            atomicAdd(&a.braycurtis[sym], val(3));
+            if (SIMPLE) { atomicAdd(&a.chord[ij], val(4)); atomicAdd(&a.hellinger[ij], val(5)); }
+            if (COMPLEX) { atomicAdd(&a.whittaker[ij], 0ull - val(6)); atomicAdd(&a.klfix[ij], val(7)); }
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -1562,10 +1606,10 @@ k_merge_sm(MergeArgs a) {
         loc_shared += __shfl_down_sync(0xffffffffu, loc_shared, d);
         loc_pairs += __shfl_down_sync(0xffffffffu, loc_pairs, d);
     }
-    if (lane == 0 && (loc_groups | loc_shared | loc_pairs)) {
-        atomicAdd(&a.scalars[0], loc_groups);
-        atomicAdd(&a.scalars[1], loc_shared);
-        atomicAdd(&a.scalars[2], loc_pairs);
+    if (lane == 0) {
+        // a tiled run groups every k-mer once per tile: its distinct / shared k-mer counts come from the count-only pass
+        if (!TILED && (loc_groups | loc_shared)) { atomicAdd(&a.scalars[0], loc_groups); atomicAdd(&a.scalars[1], loc_shared); }
+        if (loc_pairs) atomicAdd(&a.scalars[2], loc_pairs);
     }
 }
 
@@ -2413,7 +2457,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
         a.off = ctx->d_off_table.as<uint32_t>();
         a.ntot = ctx->a_ntot;
         a.logtab = ctx->d_logtab.as<double2>();
-        a.simple = ctx->prm.simple_dist; a.complex_ = ctx->prm.complex_dist;
+        a.simple = ctx->prm.simple_dist; a.complex_ = ctx->prm.complex_dist; a.count_only = 0;
         a.nb_shared = ctx->a_nb_shared; a.distinct_shared = ctx->a_distinct; a.braycurtis = ctx->a_bc;
         a.chord = ctx->a_chord; a.hellinger = ctx->a_hell; a.whittaker = ctx->a_whit; a.kl = ctx->a_kl; a.klfix = ctx->a_klfix;
         a.scalars = ctx->a_scalars; a.error_flag = d_error;
@@ -2431,14 +2475,30 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
             const unsigned g32 = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * std::max(1, occ));
             kern<<<g32, M32_THREADS, sizeof(M32Smem), st>>>(a);
         } else if (N >= 2 && N <= MS_MAXN && !want_generic) {
-            void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge_sm<true, true> : k_merge_sm<true, false>)
-                                               : (a.complex_ ? k_merge_sm<false, true> : k_merge_sm<false, false>);
+            void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge_sm<true, true, false> : k_merge_sm<true, false, false>)
+                                               : (a.complex_ ? k_merge_sm<false, true, false> : k_merge_sm<false, false, false>);
             int occ = 0;
             const size_t smem = ms_smem_bytes(N);
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MS_THREADS, smem));
             const unsigned gs = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * std::max(1, occ));
             kern<<<gs, MS_THREADS, smem, st>>>(a);
+        } else if (N > MS_MAXN && !want_generic) {
+            // distinct / shared k-mer counts over all samples: grouping only
+            a.count_only = 1;
+            k_merge<<<grid, BLOCK, merge_smem_bytes(N), st>>>(a);
+            a.count_only = 0;
+            ctx->launches++;
+            // the pairs: tiles of 32 x 32 samples; merge bins sized for the <= 64 samples a tile gathers
+            MergeArgs t = a;
+            t.mg_bits = std::min(ctx->fg_bits, ilog2_ceil(std::max<uint64_t>(1, total_entries * 64 / (uint64_t)N / 1024)));
+            void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge_sm<true, true, true> : k_merge_sm<true, false, true>)
+                                               : (a.complex_ ? k_merge_sm<false, true, true> : k_merge_sm<false, false, true>);
+            int occ = 0;
+            const size_t smem = ms_smem_bytes(N);
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MS_THREADS, smem));
+            kern<<<(unsigned)((uint64_t)nsm * std::max(1, occ)), MS_THREADS, smem, st>>>(t);
         } else {
             k_merge<<<grid, BLOCK, merge_smem_bytes(N), st>>>(a);
         }

@@ -336,3 +336,23 @@ def test_full_size_sample_properties():
     sub = km1[:: max(1, len(km1) // 50_000)]
     rc = np.array([oracle.lib().orc_revcomp(int(v), k) for v in sub[:20_000]], np.uint64)
     assert (sub[:20_000] <= rc).all()
+
+
+@pytest.mark.parametrize("n", [64, 70, 130])
+def test_many_samples_tiled_merge(n):
+    """N = 64: largest single-tile merge; N > 64: the 32 x 32 sample-tile merge (diagonal + off-diagonal tiles,
+    a ragged last block) + the count-only pass for the distinct / shared k-mer totals."""
+    samples = synthetic_samples(n, 400, read_len=100, n_genomes=12, genome_len=2500)
+    run = oracle_run(samples, 21, 2)
+    st = simka_b200.run_samples(samples, 21, abundance_min=2)
+    assert_stats_equal(st, run)
+
+
+def test_merge_variants_agree(monkeypatch):
+    """the three merge kernels (shared-memory accumulators, register accumulators, global atomics) on the same input"""
+    samples = synthetic_samples(20, 1500, n_genomes=10, genome_len=3000)
+    run = oracle_run(samples, 31, 2)
+    for variant in ("", "sorted", "generic"):
+        monkeypatch.setenv("SIMKA_B200_MERGE", variant)
+        st = simka_b200.run_samples(samples, 31, abundance_min=2)
+        assert_stats_equal(st, run)
