@@ -46,8 +46,9 @@ def parse_args():
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--kmer", type=int, default=31)
     ap.add_argument("--abundance-min", type=int, default=2)
-    ap.add_argument("--ref-reads", type=int, default=300_000, help="reads/sample of the bounded CPU sample (about 10-20 s of CPU work per pass)")
+    ap.add_argument("--ref-reads", type=int, default=400_000, help="reads/sample of the bounded CPU sample (about 10-20 s of CPU work per pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--genomes", type=int, default=0, help="number of 50 kb genomes of the generator (0 = 256 per 32 samples)")
     return ap.parse_args()
 
 
@@ -56,7 +57,9 @@ def workload_name(a, reads=None):
             f"abundance-min={a.abundance_min}, simple+complex distances")
 
 
-def n_genomes_for(samples):
+def n_genomes_for(samples, override=0):
+    if override:
+        return override
     return 256 if samples <= 32 else 256 * ((samples + 31) // 32)  # "scale G with N" 
 
 
@@ -67,7 +70,7 @@ def cpu_port_rate(a, reads, repeats=1):
     """-> (k-mers/s, cores, seconds per pass)"""
     from oracle import oracle
     from simka_b200 import synth
-    genomes = synth.make_genomes(n_genomes_for(a.samples), 50_000)
+    genomes = synth.make_genomes(n_genomes_for(a.samples, a.genomes), 50_000)
     datas, offs, sample_off, base, nreads = [], [np.zeros(1, np.uint64)], [0], 0, 0
     for s in range(a.samples):
         seqs, off = synth.make_sample(genomes, s, reads, a.read_len)
@@ -103,7 +106,7 @@ def run_reference(a):
     kmers = a.samples * a.ref_reads * (a.read_len - a.kmer + 1)
     # build inputs once, time W + K passes
     from simka_b200 import synth
-    genomes = synth.make_genomes(n_genomes_for(a.samples), 50_000)
+    genomes = synth.make_genomes(n_genomes_for(a.samples, a.genomes), 50_000)
     datas, offs, sample_off, base, nreads = [], [np.zeros(1, np.uint64)], [0], 0, 0
     for s in range(a.samples):
         seqs, off = synth.make_sample(genomes, s, a.ref_reads, a.read_len)
@@ -224,7 +227,7 @@ def run_ours(a):
 
     # ---- synthetic input: rank r owns samples s with s % world == r (sample-sharded counting) ----------
     N, M, L, k = a.samples, a.reads, a.read_len, a.kmer
-    genomes = synth.make_genomes(n_genomes_for(N), 50_000)
+    genomes = synth.make_genomes(n_genomes_for(N, a.genomes), 50_000)
     t_gen = time.perf_counter()
     mine = [s for s in range(N) if sdist.sample_owner(s, world) == rank]
     host, devbuf, nwords = {}, {}, {}

@@ -945,7 +945,9 @@ k_merge(MergeArgs a) {
             const uint32_t P = warp_tmp[BLOCK / 32];
             if (tid == 0) pp[MRG_SLOTS] = P;
             __syncthreads();
-            // phase 4: flat pair enumeration
+            // phase 4: flat pair enumeration.  Consecutive lanes take consecutive pairs on purpose: they share the group and
+            // mostly the row, so their global atomics fall into the same few L2 lines (one run of pairs per thread was
+            // measured 2x slower at N = 128).
             for (uint32_t p = tid; p < P; p += BLOCK) {
                 int lo = 0, hi = MRG_SLOTS;  // pp[lo] <= p < pp[hi]
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pp[mid] <= p) lo = mid; else hi = mid; }
@@ -2464,8 +2466,10 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
         const int nsm = ctx->nsm;
         const uint32_t MG = 1u << mg_bits;
         const unsigned grid = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * 8);
-        const char *mv = getenv("SIMKA_B200_MERGE");  // "sorted": the k_merge32 variant (N <= 32), "generic": k_merge
-        const bool want_generic = mv && !strcmp(mv, "generic"), want_sorted = mv && !strcmp(mv, "sorted");
+        // default: k_merge_sm for N <= 64, k_merge (global atomics) above.  SIMKA_B200_MERGE selects the measured-and-kept
+        // alternatives: "sorted" = k_merge32 (N <= 32), "generic" = k_merge for any N, "tiled" = 32 x 32 sample tiles on k_merge_sm (N > 64)
+        const char *mv = getenv("SIMKA_B200_MERGE");
+        const bool want_generic = mv && !strcmp(mv, "generic"), want_sorted = mv && !strcmp(mv, "sorted"), want_tiled = mv && !strcmp(mv, "tiled");
         if (N <= 32 && want_sorted) {
             void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge32<true, true> : k_merge32<true, false>)
                                                : (a.complex_ ? k_merge32<false, true> : k_merge32<false, false>);
@@ -2483,7 +2487,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MS_THREADS, smem));
             const unsigned gs = (unsigned)std::min<uint64_t>(MG, (uint64_t)nsm * std::max(1, occ));
             kern<<<gs, MS_THREADS, smem, st>>>(a);
-        } else if (N > MS_MAXN && !want_generic) {
+        } else if (N > MS_MAXN && want_tiled) {
             // distinct / shared k-mer counts over all samples: grouping only
             a.count_only = 1;
             k_merge<<<grid, BLOCK, merge_smem_bytes(N), st>>>(a);

@@ -338,10 +338,11 @@ def test_full_size_sample_properties():
     assert (sub[:20_000] <= rc).all()
 
 
-@pytest.mark.parametrize("n", [64, 70, 130])
-def test_many_samples_tiled_merge(n):
-    """N = 64: largest single-tile merge; N > 64: the 32 x 32 sample-tile merge (diagonal + off-diagonal tiles,
-    a ragged last block) + the count-only pass for the distinct / shared k-mer totals."""
+@pytest.mark.parametrize("n,variant", [(64, ""), (70, ""), (130, ""), (70, "tiled"), (130, "tiled")])
+def test_many_samples_merge_paths(monkeypatch, n, variant):
+    """N = 64: largest shared-memory-accumulator merge; N > 64: global-atomics merge (default) and the 32 x 32 sample-tile
+    variant (diagonal + off-diagonal tiles, a ragged last block, count-only pass for the distinct / shared totals)."""
+    monkeypatch.setenv("SIMKA_B200_MERGE", variant)
     samples = synthetic_samples(n, 400, read_len=100, n_genomes=12, genome_len=2500)
     run = oracle_run(samples, 21, 2)
     st = simka_b200.run_samples(samples, 21, abundance_min=2)
