@@ -357,3 +357,31 @@ def test_merge_variants_agree(monkeypatch):
         monkeypatch.setenv("SIMKA_B200_MERGE", variant)
         st = simka_b200.run_samples(samples, 31, abundance_min=2)
         assert_stats_equal(st, run)
+
+
+@pytest.mark.parametrize("variant", ["", "chunked"])
+def test_simkamin_distance_edge_cases(monkeypatch, variant):
+    """identical sketches, disjoint sketches, heavy padding, sizes around the tile length of the tiled kernel"""
+    monkeypatch.setenv("SIMKA_B200_SIMKAMIN", variant)
+    from simka_b200 import synth
+    rng = np.random.default_rng(3)
+    for s in (1, 7, 1535, 1536, 1537, 4000):
+        n = 6
+        pool = np.unique(rng.integers(1, 2**63, size=3 * s + 10, dtype=np.uint64))
+        hashes = np.zeros((n, s), np.uint64)
+        counts = np.zeros((n, s), np.uint32)
+        for i in range(n):
+            hashes[i] = np.sort(rng.choice(pool, size=s, replace=False))
+            counts[i] = rng.integers(1, 1000, size=s, dtype=np.uint32)
+        hashes[1] = hashes[0]                                  # identical hashes, different counts
+        lo = np.sort(pool)[:s]
+        hashes[2] = lo                                         # the s smallest of the pool
+        if s > 3:
+            hashes[3, : s // 2] = 0                            # half padding
+            counts[3, : s // 2] = 0
+            hashes[4, : s - 1] = 0                             # a single element
+            counts[4, : s - 1] = 0
+        jac, bc, _ = simka_b200.simkamin_distance(hashes, counts)
+        ojac, obc = oracle.simkamin_distance(hashes, counts)
+        np.testing.assert_array_equal(jac, ojac, err_msg=f"s={s}")
+        np.testing.assert_array_equal(bc, obc, err_msg=f"s={s}")
