@@ -123,4 +123,31 @@ inline uint64_t read_sample(const SampleSpec &spec, const SimkaSequenceFilter &f
     return total;
 }
 
+// Batch variant for the ingest pipeline: reads are parsed straight into the concatenated buffer `seqs` (offsets in
+// `off`, off[0] = 0 on entry), a rejected read is rolled back; `after_read()` is called after every accepted read (the
+// caller flushes the batch there when it is large enough).
+template <class AfterRead>
+inline uint64_t read_sample_into(const SampleSpec &spec, const SimkaSequenceFilter &filter, uint64_t maxReads, std::string &seqs,
+                                 std::vector<uint64_t> &off, AfterRead after_read) {
+    uint64_t total = 0;
+    for (const auto &group : spec.groups) {
+        uint64_t taken = 0;
+        for (const std::string &file : group) {
+            if (maxReads && taken >= maxReads) break;
+            bank::FastxParser parser(file);
+            for (;;) {
+                const size_t start = seqs.size();
+                if (!parser.nextRead(seqs)) break;
+                if (!filter(seqs.data() + start, seqs.size() - start)) { seqs.resize(start); continue; }
+                off.push_back(seqs.size());
+                after_read();
+                taken++;
+                if (maxReads && taken >= maxReads) break;
+            }
+        }
+        total += taken;
+    }
+    return total;
+}
+
 }  // namespace simka_b200

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <string>
 #include <thread>
 #include <vector>
@@ -265,28 +266,43 @@ uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n
         }
         uint64_t rbeg = 0, rend = 0, o = 0;
         if (r < n_reads) { rbeg = read_off[r]; rend = read_off[r + 1]; o = p0 - (rbeg - base0 + r); }
-        for (uint64_t w = w0; w < w1; w++) {
-            uint64_t v = 0; uint32_t b = 0;
-            for (int j = 0; j < 32; j++) {
-                uint32_t code = 0, isbad = 1;
-                if (r < n_reads) {
-                    if (rbeg + o < rend) {
-                        unsigned char c = (unsigned char)seqs[rbeg + o];
-                        code = (c >> 1) & 3u;  // GC/tools/misc/api/Data.hpp:179
-                        unsigned char u = c & 0xDF;
-                        isbad = !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
-                        o++;
-                    } else {  // separator after the read
-                        r++;
-                        if (r < n_reads) { rbeg = rend; rend = read_off[r + 1]; }
-                        o = 0;
-                    }
-                }
-                v = (v << 2) | code;
-                b = (b << 1) | isbad;
+        // bad[c] = 1 for every character outside ACGTacgt (GC/tools/misc/api/Data.hpp:179-183)
+        static const struct BadTab {
+            uint8_t t[256];
+            BadTab() { for (int c = 0; c < 256; c++) { int u = c & 0xDF; t[c] = !(u == 'A' || u == 'C' || u == 'G' || u == 'T'); } }
+        } bt;
+        uint64_t w = w0, acc = 0;
+        uint32_t bacc = 0;
+        int cnt = 0;  // positions already in (acc, bacc)
+        while (w < w1) {
+            if (r >= n_reads) {  // past the last read: bad padding
+                acc <<= 2 * (32 - cnt);
+                bacc = cnt ? ((bacc << (32 - cnt)) | (0xFFFFFFFFu >> cnt)) : 0xFFFFFFFFu;
+                packed[w] = acc; bad[w] = bacc; w++;
+                acc = 0; bacc = 0; cnt = 0;
+                continue;
             }
-            packed[w] = v;
-            bad[w] = b;
+            if (rbeg + o >= rend) {  // the separator position after read r
+                acc <<= 2; bacc = (bacc << 1) | 1u; cnt++;
+                r++;
+                if (r < n_reads) { rbeg = rend; rend = read_off[r + 1]; }
+                o = 0;
+            } else {  // a run of bases of read r: up to the end of the current word
+                const unsigned char *sp = reinterpret_cast<const unsigned char *>(seqs) + rbeg + o;
+                uint64_t avail = rend - (rbeg + o);
+                if (cnt == 0 && avail >= 32) {  // fast path: a whole word inside the read
+                    uint64_t v = 0; uint32_t bb = 0;
+                    for (int j = 0; j < 32; j++) { const unsigned c = sp[j]; v = (v << 2) | ((c >> 1) & 3u); bb = (bb << 1) | bt.t[c]; }
+                    packed[w] = v; bad[w] = bb; w++;
+                    o += 32;
+                    continue;
+                }
+                const int take = (int)std::min<uint64_t>(avail, (uint64_t)(32 - cnt));
+                for (int j = 0; j < take; j++) { const unsigned c = sp[j]; acc = (acc << 2) | ((c >> 1) & 3u); bacc = (bacc << 1) | bt.t[c]; }
+                cnt += take;
+                o += take;
+            }
+            if (cnt == 32) { packed[w] = acc; bad[w] = bacc; w++; acc = 0; bacc = 0; cnt = 0; }
         }
     };
     if (nthreads == 1) work(0, n_words);

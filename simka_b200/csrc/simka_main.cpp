@@ -15,7 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -214,6 +216,77 @@ int run(int argc, char **argv) {
         }
     }
 
+    // stage 1.  Host ingest pipeline: worker threads parse + 2-bit pack whole samples into pinned chunks (one sample per
+    // worker at a time: files are independent, so the parse scales with the cores), the main thread feeds the GPU in
+    // sample order: push (async H2D) of sample i+1 overlaps the counting of sample i.  Pinned chunks come from a pool and
+    // go back to it when their sample is finished; at most `inflight` samples are parsed ahead.
+    const uint64_t CHUNK_BASES = 1ull << 29;
+    struct Parsed {
+        std::vector<PinnedChunk *> chunks;
+        std::vector<uint64_t> words, reads;
+        uint64_t nreads = 0;
+        bool ready = false;
+        std::string error;
+    };
+    std::vector<Parsed> parsed(N);
+    std::vector<PinnedChunk *> pool;
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t next_sample = 0, consumed = 0;
+    const size_t workers = std::max<size_t>(1, std::min<size_t>({(size_t)nthreads, N, (size_t)16}));
+    const size_t inflight = workers + 2;
+    auto get_chunk = [&](uint64_t words) {
+        PinnedChunk *c = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t q = 0; q < pool.size(); q++)
+                if (pool[q]->cap_words >= words + 1) { c = pool[q]; pool.erase(pool.begin() + q); break; }
+            if (!c && !pool.empty()) { c = pool.back(); pool.pop_back(); }
+        }
+        if (!c) c = new PinnedChunk();
+        c->reserve(words);
+        return c;
+    };
+    auto worker = [&]() {
+        std::string seqs;
+        std::vector<uint64_t> off;
+        for (;;) {
+            size_t i;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return next_sample >= N || next_sample < consumed + inflight; });
+                if (next_sample >= N) return;
+                i = next_sample++;
+            }
+            Parsed &P = parsed[i];
+            try {
+                seqs.clear();
+                off.assign(1, 0);
+                auto flush = [&]() {
+                    if (off.size() <= 1) return;
+                    const uint64_t nr = off.size() - 1;
+                    const uint64_t words = simka_pack_words(seqs.size(), nr);
+                    PinnedChunk *c = get_chunk(words);
+                    simka_pack_reads(seqs.data(), off.data(), nr, c->packed, c->bad, 1);
+                    P.chunks.push_back(c);
+                    P.words.push_back(words);
+                    P.reads.push_back(nr);
+                    seqs.clear();
+                    off.assign(1, 0);
+                };
+                P.nreads = read_sample_into(samples[i], filter, maxReads, seqs, off, [&]() { if (seqs.size() >= CHUNK_BASES) flush(); });
+                flush();
+            } catch (const std::exception &e) { P.error = e.what(); if (P.error.empty()) P.error = "read error"; }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                P.ready = true;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool_threads;
+    for (size_t w = 0; w < workers; w++) pool_threads.emplace_back(worker);
+    // the GPU context is created while the parser threads already work on the first samples
     simka_params prm;
     memset(&prm, 0, sizeof prm);
     prm.kmer_size = o.kmerSize;
@@ -225,40 +298,26 @@ int run(int argc, char **argv) {
     prm.device = o.device;
     simka_ctx *ctx = nullptr;
     int rc = simka_gpu_create(&ctx, &prm);
-    if (rc != SIMKA_OK) throw bank::Exception("simka_gpu_create failed (code " + std::to_string(rc) + "): a CUDA device is required, there is no CPU path");
+    const double t_create = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc != SIMKA_OK) { { std::lock_guard<std::mutex> lk(mu); next_sample = N; } cv.notify_all(); for (auto &t : pool_threads) t.join(); throw bank::Exception("simka_gpu_create failed (code " + std::to_string(rc) + "): a CUDA device is required, there is no CPU path"); }
 
-    // stage 1: per sample, parse -> pack (pinned) -> push; chunks of <= CHUNK_BASES bases, every chunk of a sample
-    // needs its own pinned buffer until finish_sample, buffers are reused by the next sample
-    const uint64_t CHUNK_BASES = 1ull << 29;
-    std::vector<PinnedChunk> pool;
     std::vector<simka_sample_totals> totals(N);
-    std::string seqs;
-    std::vector<uint64_t> off;
-    for (size_t i = 0; i < N; i++) {
-        size_t chunk = 0;
-        seqs.clear();
-        off.assign(1, 0);
-        uint64_t nreads_total = 0;
-        auto flush = [&]() {
-            if (off.size() <= 1) return;
-            const uint64_t nr = off.size() - 1;
-            const uint64_t words = simka_pack_words(seqs.size(), nr);
-            if (chunk >= pool.size()) pool.emplace_back();
-            pool[chunk].reserve(words);
-            simka_pack_reads(seqs.data(), off.data(), nr, pool[chunk].packed, pool[chunk].bad, nthreads);
-            check(ctx, simka_gpu_push_reads(ctx, (int)i, pool[chunk].packed, pool[chunk].bad, words, nr), "simka_gpu_push_reads");
-            chunk++;
-            seqs.clear();
-            off.assign(1, 0);
-        };
-        nreads_total = read_sample(samples[i], filter, maxReads, [&](const char *p, size_t n) {
-            seqs.append(p, n);
-            off.push_back(seqs.size());
-            if (seqs.size() >= CHUNK_BASES) flush();
-        });
-        flush();
-        check(ctx, simka_gpu_finish_sample(ctx, (int)i, &totals[i]), "simka_gpu_finish_sample");
-        totals[i].nb_reads = nreads_total;
+    std::string failure;
+    auto finish = [&](size_t i) {  // counts sample i (already pushed), recycles its pinned chunks, writes its .ok file
+        Parsed &P = parsed[i];
+        if (failure.empty()) {
+            const int rc2 = simka_gpu_finish_sample(ctx, (int)i, &totals[i]);
+            if (rc2 != SIMKA_OK) failure = std::string("simka_gpu_finish_sample: ") + simka_gpu_last_error(ctx) + " (code " + std::to_string(rc2) + ")";
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (PinnedChunk *c : P.chunks) pool.push_back(c);
+            P.chunks.clear();
+            consumed = i + 1;
+        }
+        cv.notify_all();
+        if (!failure.empty()) return;
+        totals[i].nb_reads = P.nreads;
         // count_synchro/<id>.ok: nbReads, nbDistinct, sum c, sum c^2 (src/SimkaCount.cpp:355-368)
         char buf[256];
         snprintf(buf, sizeof buf, "%llu\n%llu\n%llu\n%llu\n", (unsigned long long)totals[i].nb_reads, (unsigned long long)totals[i].nb_distinct,
@@ -266,7 +325,25 @@ int run(int argc, char **argv) {
         write_text(tmp + "/count_synchro/" + samples[i].id + ".ok", buf);
         if (o.verbose) printf("Counting dataset %zu (%s): %llu reads, %llu distinct solid k-mers, %llu solid k-mers\n", i, samples[i].id.c_str(),
                               (unsigned long long)totals[i].nb_reads, (unsigned long long)totals[i].nb_distinct, (unsigned long long)totals[i].nb_kmers);
+    };
+    for (size_t i = 0; i < N; i++) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return parsed[i].ready; });
+        }
+        Parsed &P = parsed[i];
+        if (failure.empty() && !P.error.empty()) failure = P.error;
+        // push sample i (asynchronous copies) BEFORE finishing sample i-1: its H2D overlaps the kernels of i-1
+        for (size_t c = 0; c < P.chunks.size() && failure.empty(); c++) {
+            const int rc2 = simka_gpu_push_reads(ctx, (int)i, P.chunks[c]->packed, P.chunks[c]->bad, P.words[c], P.reads[c]);
+            if (rc2 != SIMKA_OK) failure = std::string("simka_gpu_push_reads: ") + simka_gpu_last_error(ctx) + " (code " + std::to_string(rc2) + ")";
+        }
+        if (i > 0) finish(i - 1);
     }
+    finish(N - 1);
+    for (auto &t : pool_threads) t.join();
+    if (!failure.empty()) { simka_gpu_destroy(ctx); throw bank::Exception(failure); }
+    const double t_stage1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     check(ctx, simka_gpu_set_totals(ctx, totals.data()), "simka_gpu_set_totals");
 
     // stage 2 + final statistics
@@ -297,12 +374,12 @@ int run(int argc, char **argv) {
         simka_gpu_get_timings(ctx, &tm);
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("\nNb distinct kmers: %llu   shared by >= 2 samples: %llu\n", (unsigned long long)v.nb_distinct_kmers, (unsigned long long)v.nb_shared_kmers);
-        printf("GPU time: %.1f ms counting + %.1f ms merging, %llu kernel launches; wall %.2f s\n", tm.samples_ms, tm.merge_ms,
-               (unsigned long long)tm.kernel_launches, wall);
+        printf("GPU time: %.1f ms counting + %.1f ms merging, %llu kernel launches; wall %.2f s (GPU context ready at %.2f s, read + count done at %.2f s, %zu parser threads)\n", tm.samples_ms,
+               tm.merge_ms, (unsigned long long)tm.kernel_launches, wall, t_create, t_stage1, workers);
         printf("Output dir: %s\n", o.out.c_str());
     }
     simka_gpu_destroy(ctx);
-    for (auto &c : pool) c.release();
+    for (PinnedChunk *c : pool) { c->release(); delete c; }
     if (!o.keepTmp) rm_rf(tmp);
     return EXIT_SUCCESS;
 }
