@@ -71,9 +71,10 @@ __device__ __forceinline__ bool shard_keep(uint64_t h, const KParams &kp) {
 
 // exclusive scan of a shared array of n (<= MAX_B*?) u32 values by the whole block, in place.
 // Returns the total in *total (shared).  n need not be a multiple of the block size.
-__device__ void block_exclusive_scan(uint32_t *a, int n, uint32_t *warp_tmp /*[BLOCK/32+1]*/) {
+template <int NT = BLOCK>
+__device__ void block_exclusive_scan(uint32_t *a, int n, uint32_t *warp_tmp /*[NT/32+1]*/) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int per = (n + BLOCK - 1) / BLOCK;
+    const int per = (n + NT - 1) / NT;
     const int beg = min(tid * per, n), end = min(beg + per, n);
     uint32_t sum = 0;
     for (int i = beg; i < end; i++) sum += a[i];
@@ -86,14 +87,14 @@ __device__ void block_exclusive_scan(uint32_t *a, int n, uint32_t *warp_tmp /*[B
     if (lane == 31) warp_tmp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t w = lane < BLOCK / 32 ? warp_tmp[lane] : 0, winc = w;
+        uint32_t w = lane < NT / 32 ? warp_tmp[lane] : 0, winc = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t v = __shfl_up_sync(0xffffffffu, winc, d);
             if (lane >= d) winc += v;
         }
-        if (lane < BLOCK / 32) warp_tmp[lane] = winc - w;
-        if (lane == BLOCK / 32 - 1) warp_tmp[BLOCK / 32] = winc;
+        if (lane < NT / 32) warp_tmp[lane] = winc - w;
+        if (lane == NT / 32 - 1) warp_tmp[NT / 32] = winc;
     }
     __syncthreads();
     uint32_t run = warp_tmp[wid] + inc - sum;
@@ -310,6 +311,115 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
     for (uint32_t i = tid; i < total; i += BLOCK) {
         const uint64_t h = sorted[i];
         const uint64_t d = dst[(uint32_t)(h >> bshift)];
+        if (d != ~0ull) keys_out[d + i] = h;
+    }
+}
+
+// K1, 512 threads x 16 positions (k >= 17): two threads share a packed word, each rolls 16 start positions.  Same
+// 8192-key tile and shared-memory footprint as k_extract, but half the registers per thread, so two CTAs = 32 warps
+// per SM instead of 16: the kernel is latency-bound on its shared-memory atomics, not on issue slots.
+constexpr int K16_THREADS = 512;
+template <bool SHARDED>
+__global__ void __launch_bounds__(K16_THREADS, 2)
+k_extract16(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t n_words, KParams kp, int b1_bits,
+            const uint64_t *__restrict__ bucket_base, uint32_t *__restrict__ bucket_cursor, uint64_t bucket_cap,
+            int *__restrict__ overflow_flag, uint64_t *__restrict__ keys_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *dst = reinterpret_cast<uint64_t *>(smem_raw);            // [MAX_B]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(dst + MAX_B);        // [MAX_B]
+    uint32_t *warp_tmp = hist + MAX_B;                                 // [32]
+    uint64_t *sorted = reinterpret_cast<uint64_t *>(warp_tmp + 32);    // [L1_TILE]
+    const int tid = threadIdx.x;
+    const int nb = 1 << b1_bits;
+    const int k = kp.k;
+    for (int i = tid; i < nb; i += K16_THREADS) hist[i] = 0;
+    __syncthreads();
+
+    const uint64_t t = (uint64_t)blockIdx.x * (K16_THREADS / 2) + (tid >> 1);  // packed word of this thread pair
+    const int half = tid & 1;
+    uint64_t hi = 0, lo = 0, bm = ~0ull;
+    if (t < n_words) {
+        hi = seq[t];
+        lo = seq[t + 1];
+        bm = ((uint64_t)bad[t] << 32) | bad[t + 1];
+    }
+    uint32_t okmask;
+    {
+        uint64_t r = bm;
+        int built = 1;
+        while (built * 2 <= k) { r |= r << built; built *= 2; }
+        if (built < k) r |= r << (k - built);
+        okmask = ~(uint32_t)(r >> 32);
+        okmask = half ? (okmask << 16) : okmask;  // bit 31-j <-> local position j
+    }
+    // the 96 bits this thread's 16 windows can touch: (P,Q,R) = the words starting at its first base
+    const uint32_t A = (uint32_t)(hi >> 32), B = (uint32_t)hi, Cw = (uint32_t)(lo >> 32), D = (uint32_t)lo;
+    const uint32_t P = half ? B : A, Q = half ? Cw : B, R = half ? D : Cw;
+    const int s1 = 64 - 2 * k, s2 = 2 * k - 34, sx = kp.mix.shift;
+    const uint32_t mhi = (uint32_t)(kp.mix.mask >> 32);
+    const uint32_t m1l = (uint32_t)kp.mix.m1, m1h = (uint32_t)(kp.mix.m1 >> 32);
+    const int bs = (kp.mix.bits - b1_bits) - 32;
+    uint64_t keys[16];
+    uint32_t ranks[8];
+    uint32_t vmask = 0;
+    uint32_t rl = 0, rh = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        uint32_t w1, w0;
+        if (j == 0) { w1 = P; w0 = Q; }
+        else { w1 = __funnelshift_l(Q, P, 2 * j); w0 = __funnelshift_l(R, Q, 2 * j); }
+        const uint32_t fh = w1 >> s1, fl = __funnelshift_r(w0, w1, s1);
+        if (j == 0) {
+            const uint64_t r0 = simka::revcomp(((uint64_t)fh << 32) | fl, k);
+            rh = (uint32_t)(r0 >> 32); rl = (uint32_t)r0;
+        } else {
+            rl = __funnelshift_r(rl, rh, 2);
+            rh = (rh >> 2) | (((fl & 3u) ^ 2u) << s2);
+        }
+        const bool fwd_smaller = fh < rh || (fh == rh && fl < rl);
+        uint32_t xh = fwd_smaller ? fh : rh, xl = fwd_smaller ? fl : rl;
+        xl ^= __funnelshift_r(xl, xh, sx); xh ^= xh >> sx;
+        {
+            const uint64_t pr = (uint64_t)xl * m1l;
+            const uint32_t ph = (uint32_t)(pr >> 32) + xl * m1h + xh * m1l;
+            xl = (uint32_t)pr; xh = ph & mhi;
+        }
+        xl ^= __funnelshift_r(xl, xh, sx); xh ^= xh >> sx;
+        const uint64_t h = ((uint64_t)xh << 32) | xl;
+        bool keep = (okmask >> (31 - j)) & 1u;
+        if (SHARDED) keep = keep && shard_keep(h, kp);
+        keys[j] = h;
+        if (keep) {
+            vmask |= 1u << j;
+            const uint32_t r = atomicAdd(&hist[xh >> bs], 1u);
+            if (j & 1) ranks[j >> 1] |= r << 16; else ranks[j >> 1] = r;
+        } else if (!(j & 1)) ranks[j >> 1] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < nb; i += K16_THREADS) {
+        const uint32_t c = hist[i];
+        uint64_t g = c ? atomicAdd(&bucket_cursor[i], c) : 0;
+        if (c && g + c > bucket_cap) { g = ~0ull; *overflow_flag = 1; }
+        dst[i] = g;
+    }
+    __syncthreads();
+    block_exclusive_scan<K16_THREADS>(hist, nb, warp_tmp);
+    const uint32_t total = warp_tmp[K16_THREADS / 32];
+    for (int i = tid; i < nb; i += K16_THREADS) {
+        const uint64_t g = dst[i];
+        if (g != ~0ull) dst[i] = bucket_base[i] + g - hist[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (vmask & (1u << j)) {
+            const uint32_t r = (j & 1) ? (ranks[j >> 1] >> 16) : (ranks[j >> 1] & 0xFFFFu);
+            sorted[hist[(uint32_t)(keys[j] >> (kp.mix.bits - b1_bits))] + r] = keys[j];
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < total; i += K16_THREADS) {
+        const uint64_t h = sorted[i];
+        const uint64_t d = dst[(uint32_t)(h >> (kp.mix.bits - b1_bits))];
         if (d != ~0ull) keys_out[d + i] = h;
     }
 }
@@ -2017,6 +2127,7 @@ struct simka_ctx {
     DevBuf d_ptrs, d_logtab, d_chain, d_isum;
     bool import_pending = false;
     unsigned long long scan_epoch = 0;
+    bool use_k16 = true;        // SIMKA_B200_K1=256: the 256-thread x 32-position extraction kernel
     bool force_exact = false;   // SIMKA_B200_EXACT_COUNT=1: always run the K1 count pass (tests of the fallback)
     uint64_t exact_retries = 0;
     float stage_ms[T_NSTAGE] = {};
@@ -2053,6 +2164,13 @@ static extract_fn extract_instance(bool count_only, bool sharded, bool bigk) {
 static void launch_extract(simka_ctx *ctx, bool count_only, unsigned grid, const uint64_t *seq, const uint32_t *bad, uint64_t n_words, int b1_bits,
                            uint32_t *g_hist, const uint64_t *bucket_base, uint32_t *bucket_cursor, uint64_t cap, int *overflow, uint64_t *keys_out) {
     const bool bigk = ctx->kp.k >= 17 && b1_bits <= 2 * ctx->kp.k - 32;
+    if (bigk && !count_only && ctx->use_k16) {
+        const unsigned g16 = (unsigned)((n_words + K16_THREADS / 2 - 1) / (K16_THREADS / 2));
+        const size_t sm16 = 3 * MAX_B * 4 + 128 + L1_TILE * 8;
+        if (ctx->kp.shard_count > 1) k_extract16<true><<<g16, K16_THREADS, sm16, ctx->stream>>>(seq, bad, n_words, ctx->kp, b1_bits, bucket_base, bucket_cursor, cap, overflow, keys_out);
+        else k_extract16<false><<<g16, K16_THREADS, sm16, ctx->stream>>>(seq, bad, n_words, ctx->kp, b1_bits, bucket_base, bucket_cursor, cap, overflow, keys_out);
+        return;
+    }
     const size_t smem = 3 * MAX_B * 4 + 64 + (count_only ? 0 : L1_TILE * 8);
     extract_instance(count_only, ctx->kp.shard_count > 1, bigk)<<<grid, BLOCK, smem, ctx->stream>>>(seq, bad, n_words, ctx->kp, b1_bits, g_hist, bucket_base,
                                                                                                    bucket_cursor, cap, overflow, keys_out);
@@ -2121,6 +2239,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
     ctx->kp.shard_count = p->shard_count > 1 ? p->shard_count : 1;
     ctx->W = 2 * p->kmer_size;
     { const char *e = getenv("SIMKA_B200_EXACT_COUNT"); ctx->force_exact = e && e[0] == '1'; }
+    { const char *e = getenv("SIMKA_B200_K1"); ctx->use_k16 = !(e && !strcmp(e, "256")); }
     cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
     ctx->samples.resize(p->nb_samples);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -2129,6 +2248,8 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
         ok = ok && cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&sl.consumed, cudaEventDisableTiming) == cudaSuccess;
     for (auto &set : ctx->ev) for (auto &e : set) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_extract16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * MAX_B * 4 + 128 + L1_TILE * 8)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_extract16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * MAX_B * 4 + 128 + L1_TILE * 8)) == cudaSuccess;
     for (int sh = 0; sh < 2; sh++)
         for (int bk = 0; bk < 2; bk++)
             ok = ok && cudaFuncSetAttribute(extract_instance(false, sh, bk), cudaFuncAttributeMaxDynamicSharedMemorySize,
