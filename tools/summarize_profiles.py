@@ -69,8 +69,9 @@ with open(os.path.join(P, f"{tag}_ncu_full_summary.txt"), "w") as f:
                     f.write(f"   {w} = {row[i]} {units[i]}\n")
                     if w.startswith("dram__bytes"):
                         b += float(row[i].replace(",", "")) * UNIT.get(units[i], 1)
-            key = {"k_extract<0, 0, 1>": "k_extract<scatter>", "k_extract<0, 0, 0>": "k_extract<scatter>", "k_partition2<1>": "k_partition2<count>",
-                   "k_partition2<0>": "k_partition2<scatter>", "k_bin_count": "k_bin_count", "k_merge32<1, 1>": "k_merge", "k_merge": "k_merge"}.get(name)
+            key = {"k_extract<0, 0, 1>": "k_extract<scatter>", "k_extract<0, 0, 0>": "k_extract<scatter>", "k_extract16<0>": "k_extract<scatter>",
+                   "k_partition2<1>": "k_partition2<count>", "k_partition2<0>": "k_partition2<scatter>", "k_bin_count": "k_bin_count",
+                   "k_merge32<1, 1>": "k_merge", "k_merge_sm<1, 1, 0>": "k_merge", "k_merge": "k_merge"}.get(name)
             if key:
                 traffic[key] = b * per_step
     f.write("\ntraffic.json = dram bytes of the launch above x launches per bench step (32 samples; merge: 1)\n")
