@@ -49,6 +49,8 @@ def pack_reads(seqs: np.ndarray, read_off: np.ndarray, nthreads: int = 0, pinned
 
 
 class _PinnedOwner:
+    """frees the cudaHostAlloc'ed block when the last array viewing it is gone"""
+
     def __init__(self, ptr):
         self.ptr = ptr
 
@@ -57,6 +59,13 @@ class _PinnedOwner:
             _lib.load().simka_gpu_host_free(self.ptr)
         except Exception:
             pass
+
+
+class PinnedArray(np.ndarray):
+    """ndarray over pinned host memory; views and slices keep the owner alive"""
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
 
 
 def pinned_empty(n: int, dtype) -> np.ndarray:
@@ -68,13 +77,9 @@ def pinned_empty(n: int, dtype) -> np.ndarray:
     if rc != 0:
         raise SimkaError("cudaHostAlloc failed")
     buf = (C.c_uint8 * (max(1, n) * dt.itemsize)).from_address(ptr.value)
-    arr = np.frombuffer(buf, dtype=dt, count=n)
-    _PINNED[id(buf)] = (_PinnedOwner(ptr), buf)
-    arr = arr.view()
+    arr = np.frombuffer(buf, dtype=dt, count=n).view(PinnedArray)
+    arr._owner = _PinnedOwner(ptr)
     return arr
-
-
-_PINNED: dict = {}
 
 
 class SimkaStatistics:

@@ -41,7 +41,7 @@ def _stale(target: Path, sources) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = [CSRC / "simka_gpu.cu", CSRC / "simka_host.cpp"]
-    deps = srcs + [CSRC / "kmer_device.cuh", ROOT.parent / "include" / "simka_b200.h", *sorted((CSRC / "host").glob("*.hpp"))]
+    deps = srcs + [CSRC / "kmer_device.cuh", ROOT.parent / "include" / "simka_b200.h", *sorted((CSRC / "host").glob("*.hpp")), *sorted((CSRC / "kernels").glob("*.cuh"))]
     LIBDIR.mkdir(exist_ok=True)
     if force or _stale(LIB, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, srcs), "-lz"]

@@ -1,0 +1,192 @@
+// kernels/common.cuh -- constants, block scans, device-wide exclusive scans
+// Part of the single translation unit simka_gpu.cu (included inside its anonymous namespace).
+#pragma once
+
+
+constexpr int BLOCK = 256;
+constexpr int L1_KPT = 32;                   // K1: one packed word (32 start positions) per thread
+constexpr int L1_TILE = BLOCK * L1_KPT;      // 8192 keys
+constexpr int L2_KPT = 16;
+constexpr int L2_TILE = BLOCK * L2_KPT;      // 4096 keys
+constexpr int MAX_B = 1024;                  // max buckets per partition level
+constexpr int BIN_TARGET = 768;              // fine bins hold BIN_TARGET..2*BIN_TARGET keys on average
+constexpr int CNT_SLOTS = 2048;              // K3 hash table slots
+constexpr int CNT_MAXDISTINCT = 1536;        // distinct keys one table pass may hold (load 0.75)
+constexpr int CHIST = 1024;                  // dense abundance histogram bins (complex distances)
+constexpr int MRG_SLOTS = 2048;              // merge hash table slots
+constexpr int MRG_CAP = 2048;                // merge: grouped entries held in shared memory
+constexpr int MRG_TARGET = 768;              // average entries per merge bin
+constexpr int MRG_MAXN = 8192;               // samples supported by the shared-memory prefix arrays
+constexpr uint64_t EMPTY = ~0ull;
+
+struct KParams {
+    Mix mix;
+    int k;
+    int shard_rank, shard_count;
+};
+
+__device__ __forceinline__ bool shard_keep(uint64_t h, const KParams &kp) {
+    if (kp.shard_count <= 1) return true;
+    uint32_t x = (uint32_t)(simka::hash2(h) >> 32);
+    return (int)(((uint64_t)x * (uint32_t)kp.shard_count) >> 32) == kp.shard_rank;
+}
+
+// exclusive scan of a shared array of n (<= MAX_B*?) u32 values by the whole block, in place.
+// Returns the total in *total (shared).  n need not be a multiple of the block size.
+template <int NT = BLOCK>
+__device__ void block_exclusive_scan(uint32_t *a, int n, uint32_t *warp_tmp /*[NT/32+1]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (n + NT - 1) / NT;
+    const int beg = min(tid * per, n), end = min(beg + per, n);
+    uint32_t sum = 0;
+    for (int i = beg; i < end; i++) sum += a[i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) warp_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < NT / 32 ? warp_tmp[lane] : 0, winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += v;
+        }
+        if (lane < NT / 32) warp_tmp[lane] = winc - w;
+        if (lane == NT / 32 - 1) warp_tmp[NT / 32] = winc;
+    }
+    __syncthreads();
+    uint32_t run = warp_tmp[wid] + inc - sum;
+    for (int i = beg; i < end; i++) {
+        uint32_t v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------------------------
+
+// out[0..n] = exclusive scan of in[0..n-1] (u32 -> u64); single block, chunked.
+__global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n) {
+    __shared__ uint64_t warp_sum[33];
+    __shared__ uint64_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    constexpr int PER = 16;  // consecutive elements per thread and round
+    for (uint64_t base = 0; base < n; base += 1024 * PER) {
+        const uint64_t i0 = base + (uint64_t)tid * PER;
+        uint32_t x[PER];
+        if (i0 + PER <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < PER / 4; q++) {
+                const uint4 t4 = *reinterpret_cast<const uint4 *>(in + i0 + 4 * q);
+                x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < PER; q++) x[q] = (i0 + q < n) ? in[i0 + q] : 0;
+        }
+        uint64_t v = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) v += x[q];
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t u = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += u;
+        }
+        if (lane == 31) warp_sum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t w = warp_sum[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t u = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += u;
+            }
+            warp_sum[lane] = winc - w;
+            if (lane == 31) warp_sum[32] = winc;
+        }
+        __syncthreads();
+        uint64_t run = carry + warp_sum[wid] + inc - v;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            if (i0 + q < n) out[i0 + q] = run;
+            run += x[q];
+        }
+        __syncthreads();
+        if (tid == 0) carry += warp_sum[32];
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+// Multi-block version for the large scans (fine-bin histogram, survivors): block b scans 16384 elements and
+// takes its exclusive prefix from block b-1 through a chained (epoch | running total) word.  All blocks are
+// co-resident (grid <= 128), so the spin of thread 0 cannot starve its predecessor.
+constexpr int SCAN_CHUNK = 1024 * 16;
+__global__ void __launch_bounds__(1024) k_scan_chain(const uint32_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
+                                                     unsigned long long *chain, unsigned long long epoch) {
+    __shared__ uint64_t warp_sum[33];
+    __shared__ uint64_t s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t i0 = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)tid * 16;
+    uint32_t x[16];
+    if (i0 + 16 <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 t4 = *reinterpret_cast<const uint4 *>(in + i0 + 4 * q);
+            x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) x[q] = (i0 + q < n) ? in[i0 + q] : 0;
+    }
+    uint64_t v = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) v += x[q];
+    uint64_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    if (lane == 31) warp_sum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = warp_sum[lane], winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += u;
+        }
+        warp_sum[lane] = winc - w;
+        if (lane == 31) {
+            const uint64_t total = winc;
+            uint64_t prefix = 0;
+            if (blockIdx.x > 0) {
+                volatile unsigned long long *c = chain + (blockIdx.x - 1);
+                unsigned long long pv = *c;
+                while ((pv >> 40) != epoch) pv = *c;
+                prefix = pv & ((1ull << 40) - 1);
+            }
+            *((volatile unsigned long long *)(chain + blockIdx.x)) = (epoch << 40) | (prefix + total);
+            s_prefix = prefix;
+            if (blockIdx.x == gridDim.x - 1) out[n] = prefix + total;
+        }
+    }
+    __syncthreads();
+    uint64_t run = s_prefix + warp_sum[wid] + inc - v;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        if (i0 + q < n) out[i0 + q] = run;
+        run += x[q];
+    }
+}

@@ -1,0 +1,163 @@
+// kernels/simkamin.cuh -- SimkaMin sketch x sketch distances
+// Part of the single translation unit simka_gpu.cu (included inside its anonymous namespace).
+#pragma once
+
+// ---------------------------------------------------------------------------------------------
+// SimkaMin: all-pairs bottom-s sketch comparison.
+// Replaces ComputeDistanceManager::computeDistance_unsynch (src/simkaMin/SimkaMinDistance.hpp:190-279).  One CTA per pair streams the two sketches through shared memory in
+// tiles of SMT_TILE MERGED elements (coalesced loads, merge-path split per thread, A before B on ties), and stops at
+// the tile that holds the (S+1)-th distinct value of the union -- exactly the elements the reference's two-pointer
+// loop consumes (src/simkaMin/SimkaMinDistance.hpp:204-243): the S smallest distinct values, both copies of a shared one.
+// ---------------------------------------------------------------------------------------------
+constexpr int SMT_EPT = 6;                    // merged elements per thread and tile
+constexpr int SMT_TILE = BLOCK * SMT_EPT;     // 1536
+
+__device__ __forceinline__ void block_sum3(ull &a, ull &b, ull &c, ull *tmp /*[3*8]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, d);
+        b += __shfl_down_sync(0xffffffffu, b, d);
+        c += __shfl_down_sync(0xffffffffu, c, d);
+    }
+    __syncthreads();
+    if (lane == 0) { tmp[wid] = a; tmp[8 + wid] = b; tmp[16 + wid] = c; }
+    __syncthreads();
+    a = b = c = 0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; w++) { a += tmp[w]; b += tmp[8 + w]; c += tmp[16 + w]; }
+}
+
+__global__ void __launch_bounds__(BLOCK)
+k_simkamin_tiled(const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ start,
+                 uint32_t n, uint32_t s, ull *__restrict__ quad /*[pairs][4]: shared, distinct, sharedK, kmers*/) {
+    static_assert(BLOCK == 256, "block_sum3 assumes 8 warps");
+    const uint64_t p = blockIdx.x;
+    const double tn = 2.0 * n - 1.0;
+    int i = (int)((tn - sqrt(tn * tn - 8.0 * (double)p)) * 0.5);
+    if (i < 0) i = 0;
+    while ((uint64_t)(i + 1) * (2ull * n - (i + 1) - 1) / 2 <= p) i++;
+    while ((uint64_t)i * (2ull * n - i - 1) / 2 > p) i--;
+    const int j = i + 1 + (int)(p - (uint64_t)i * (2ull * n - i - 1) / 2);
+    const uint64_t *A = hashes + (size_t)i * s + start[i];
+    const uint64_t *B = hashes + (size_t)j * s + start[j];
+    const uint32_t *CA = counts + (size_t)i * s + start[i];
+    const uint32_t *CB = counts + (size_t)j * s + start[j];
+    const uint32_t na = s - start[i], nb = s - start[j];
+    const uint32_t S = min(na, nb);  // sketchSize = min of the two stripped sizes (:204)
+
+    __shared__ uint64_t sa[SMT_TILE], sb[SMT_TILE];
+    __shared__ uint32_t ca[SMT_TILE], cb[SMT_TILE];
+    __shared__ ull red[24];
+    __shared__ uint32_t s_scan[BLOCK / 32 + 1];
+    __shared__ uint32_t s_xs, s_tstar;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    uint32_t a0 = 0, b0 = 0;            // elements of A / B consumed so far
+    ull distinct = 0, shared = 0, sharedk = 0, kmers = 0;
+    uint64_t prevA = ~0ull;             // last A element consumed before this tile (a duplicate B may open the tile)
+    uint32_t prevCA = 0;
+    for (;;) {
+        const uint32_t ra = na - a0, rb = nb - b0;
+        const uint32_t la = min(ra, (uint32_t)SMT_TILE), lb = min(rb, (uint32_t)SMT_TILE);
+        const uint32_t tl = min((uint32_t)SMT_TILE, ra + rb);
+        if (tl == 0) break;  // (distinct == S at a tile end is NOT a stop: a duplicate B of the last A may open the next tile)
+        __syncthreads();  // previous tile fully consumed
+        for (uint32_t q = tid; q < la; q += BLOCK) { sa[q] = A[a0 + q]; ca[q] = CA[a0 + q]; }
+        for (uint32_t q = tid; q < lb; q += BLOCK) { sb[q] = B[b0 + q]; cb[q] = CB[b0 + q]; }
+        __syncthreads();
+        // merge-path split of this thread's diagonal: x = elements of A among the first d0 merged ones (A first on ties)
+        const uint32_t d0 = min(tl, (uint32_t)tid * SMT_EPT), d1 = min(tl, d0 + SMT_EPT);
+        uint32_t x;
+        {
+            uint32_t lo = d0 > lb ? d0 - lb : 0, hi = min(d0, la);
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sa[mid] <= sb[d0 - 1 - mid]) lo = mid + 1; else hi = mid; }
+            x = lo;
+        }
+        uint32_t y = d0 - x;
+        const uint32_t x0 = x, y0 = y;
+        if (tid == BLOCK - 1 || d1 == tl) {  // (several threads may write the same value)
+            uint32_t lo = tl > lb ? tl - lb : 0, hi = min(tl, la);
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sa[mid] <= sb[tl - 1 - mid]) lo = mid + 1; else hi = mid; }
+            s_xs = lo;
+        }
+        // walk: matches are detected on the B copy (the A copy of a shared value precedes it)
+        uint32_t t_match = 0;
+        ull t_k = 0, t_sk = 0;
+        for (uint32_t d = d0; d < d1; d++) {
+            const bool takeA = y >= lb || (x < la && sa[x] <= sb[y]);
+            if (takeA) { t_k += ca[x]; x++; }
+            else {
+                const uint64_t pa = x > 0 ? sa[x - 1] : prevA;
+                if (pa == sb[y]) { t_match++; const uint32_t pc = x > 0 ? ca[x - 1] : prevCA; t_sk += min(pc, cb[y]); }
+                t_k += cb[y];
+                y++;
+            }
+        }
+        const uint32_t t_dist = (d1 - d0) - t_match;
+        // distinct values of the whole tile
+        ull r_d = t_dist, r_m = t_match, r_k = t_k;
+        block_sum3(r_d, r_m, r_k, red);
+        if (distinct + r_d <= S) {  // the (S+1)-th distinct value is not in this tile: take all of it
+            ull r_sk = t_sk, z0 = 0, z1 = 0;
+            block_sum3(r_sk, z0, z1, red);
+            distinct += r_d; shared += r_m; kmers += r_k; sharedk += r_sk;
+            const uint32_t xs = s_xs;
+            if (xs > 0) { prevA = sa[xs - 1]; prevCA = ca[xs - 1]; }
+            a0 += xs;
+            b0 += tl - xs;
+            continue;
+        }
+        // cut inside this tile: first merged element that would be distinct value number S+1
+        const uint32_t need = (uint32_t)(S - distinct);  // distinct values still to take (< r_d)
+        uint32_t inc = t_dist;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += u; }
+        if (lane == 31) s_scan[wid] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < wid; w++) wbase += s_scan[w];
+        const uint32_t excl = wbase + inc - t_dist;  // distinct values before this thread's run
+        // the thread whose run contains the element that makes the count exceed `need`
+        const bool mine = excl <= need && excl + t_dist > need;
+        if (mine) s_tstar = tid;
+        __syncthreads();
+        const uint32_t tstar = s_tstar;
+        ull f_m = 0, f_k = 0, f_sk = 0;
+        if ((uint32_t)tid < tstar) { f_m = t_match; f_k = t_k; f_sk = t_sk; }
+        else if ((uint32_t)tid == tstar) {  // re-walk, stopping before distinct value number need+1
+            uint32_t xx = x0, yy = y0, dcount = excl;
+            for (uint32_t d = d0; d < d1; d++) {
+                const bool takeA = yy >= lb || (xx < la && sa[xx] <= sb[yy]);
+                bool dup = false;
+                if (!takeA) { const uint64_t pa = xx > 0 ? sa[xx - 1] : prevA; dup = pa == sb[yy]; }
+                if (!dup && dcount == need) break;
+                if (takeA) { f_k += ca[xx]; xx++; }
+                else {
+                    if (dup) { f_m++; const uint32_t pc = xx > 0 ? ca[xx - 1] : prevCA; f_sk += min(pc, cb[yy]); }
+                    f_k += cb[yy];
+                    yy++;
+                }
+                if (!dup) dcount++;
+            }
+        }
+        block_sum3(f_m, f_k, f_sk, red);
+        distinct = S; shared += f_m; kmers += f_k; sharedk += f_sk;
+        break;
+    }
+    if (tid == 0) {
+        quad[4 * p + 0] = shared;
+        quad[4 * p + 1] = distinct;
+        quad[4 * p + 2] = sharedk;
+        quad[4 * p + 3] = kmers;
+    }
+}
+
+__global__ void k_sketch_starts(const uint64_t *__restrict__ hashes, uint32_t n, uint32_t s, uint32_t *__restrict__ start) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t *h = hashes + (size_t)i * s;
+    uint32_t lo = 0, hi = s;  // first non-zero (zeros are a prefix: sketches are ascending)
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (h[mid] == 0) lo = mid + 1; else hi = mid; }
+    start[i] = lo;
+}
