@@ -231,13 +231,17 @@ def run_ours(a):
     t_gen = time.perf_counter()
     mine = [s for s in range(N) if sdist.sample_owner(s, world) == rank]
     host, devbuf, nwords = {}, {}, {}
-    for s in mine:
+
+    def gen(s):  # numpy and the packer release the GIL: the samples are generated on a few threads
         seqs, off = synth.make_sample(genomes, s, M, L)
-        hp, hb, nw = simka_b200.pack_reads(seqs, off, pinned=True)
-        del seqs, off
-        host[s] = (hp, hb)
-        nwords[s] = nw
-        devbuf[s] = (torch.from_numpy(hp.view(np.int64)).to(dev), torch.from_numpy(hb.view(np.int32)).to(dev))
+        return s, simka_b200.pack_reads(seqs, off, nthreads=1, pinned=True)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(1, min(8, (os.cpu_count() or 8) // max(1, world)))) as ex:
+        for s, (hp, hb, nw) in ex.map(gen, mine):
+            host[s] = (hp, hb)
+            nwords[s] = nw
+            devbuf[s] = (torch.from_numpy(np.asarray(hp).view(np.int64)).to(dev), torch.from_numpy(np.asarray(hb).view(np.int32)).to(dev))
     if world > 1:
         dist.barrier()
     gen_s = time.perf_counter() - t_gen
