@@ -141,6 +141,13 @@ int simka_gpu_export_sample(simka_ctx *ctx, int sample_id, const uint64_t **d_km
 int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kmers, const uint32_t *d_counts, uint64_t n,
                             const uint32_t *d_off, int fine_bits, uint64_t nb_reads);
 
+/* Registers a sample from its solid (canonical k-mer, count) list in HOST memory -- the decoded content of the
+ * reference-format files solid/part_P/__p__I.gz (src/SimkaCount.cpp:248-257, records read by
+ * src/SimkaMerge.cpp:1082-1103) -- instead of counting its reads.  Any order; counts already abundance-filtered.
+ * Used by the simkaMerge executable of this build and to resume from kept temp files. */
+int simka_gpu_import_counts(simka_ctx *ctx, int sample_id, const uint64_t *kmers, const uint32_t *counts, uint64_t n,
+                            uint64_t nb_reads);
+
 /* ---- stage 2: replaces `simkaMerge` over all of this shard's buckets ---------------------------
  * (src/SimkaMerge.cpp:1164-1326 k-way merge + insert gate, SimkaCountProcessorSimple::process /
  *  updateDistance{Default,Simple,Complex}, src/core/SimkaAlgorithm.hpp:200-516) */

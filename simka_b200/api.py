@@ -237,6 +237,14 @@ class SimkaGpu:
         self._check(self._L.simka_gpu_import_sample(self._h, sample, C.c_void_p(d_kmers), C.c_void_p(d_counts), n, C.c_void_p(d_off),
                                                     fine_bits, nb_reads), "import_sample")
 
+    def import_counts(self, sample: int, kmers: np.ndarray, counts: np.ndarray, nb_reads: int = 0):
+        """registers a sample from its solid (canonical k-mer, count) list (host arrays) instead of counting reads"""
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        counts = np.ascontiguousarray(counts, np.uint32)
+        assert len(kmers) == len(counts)
+        self._check(self._L.simka_gpu_import_counts(self._h, sample, _vp(kmers) if len(kmers) else None, _vp(counts) if len(counts) else None,
+                                                    len(kmers), nb_reads), "import_counts")
+
     def get_totals(self) -> np.ndarray:
         t = np.zeros((self.nb_samples, 4), np.uint64)
         self._check(self._L.simka_gpu_get_totals(self._h, t.ctypes.data_as(C.POINTER(SampleTotals))), "get_totals")

@@ -50,14 +50,19 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             cmd.insert(2, "-v")
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
-    cli = CSRC / "simka_main.cpp"
-    if cli.exists():
-        SIMKA_BIN.parent.mkdir(exist_ok=True)
-        cdeps = deps + [cli]
-        if force or _stale(SIMKA_BIN, cdeps) or _stale(SIMKA_BIN, [LIB]):
-            cuda_lib = str(Path(_nvcc()).resolve().parent.parent / "lib64")
-            cmd = ["g++", "-O2", "-std=c++17", "-o", str(SIMKA_BIN), str(cli), f"-L{LIBDIR}", "-lsimka_b200",
-                   "-Wl,-rpath,$ORIGIN/../lib", f"-Wl,-rpath-link,{cuda_lib}", "-lz", "-lpthread"]
+    BIN = SIMKA_BIN.parent
+    BIN.mkdir(exist_ok=True)
+    cuda_lib = str(Path(_nvcc()).resolve().parent.parent / "lib64")
+    # the command lines of the reference (g++, linked against the library): simka, simkaCount, simkaMerge, simkaCountProcess
+    for exe, src, link in (("simka", "simka_main.cpp", True), ("simkaCount", "simka_count_main.cpp", True),
+                           ("simkaMerge", "simka_merge_main.cpp", True), ("simkaCountProcess", "simka_count_process_main.cpp", False)):
+        cli, out = CSRC / src, BIN / exe
+        if not cli.exists():
+            continue
+        if force or _stale(out, deps + [cli]) or _stale(out, [LIB]):
+            cmd = ["g++", "-O2", "-std=c++17", "-o", str(out), str(cli)]
+            if link:
+                cmd += [f"-L{LIBDIR}", "-lsimka_b200", "-Wl,-rpath,$ORIGIN/../lib", f"-Wl,-rpath-link,{cuda_lib}", "-lz", "-lpthread"]
             subprocess.run(cmd, check=True)
     return LIB
 

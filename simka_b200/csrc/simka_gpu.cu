@@ -671,6 +671,81 @@ int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kme
     return SIMKA_OK;
 }
 
+// Registers a sample from its solid (canonical k-mer, count) list in HOST memory, e.g. the decoded
+// solid/part_P/__p__I.gz records of a reference-format temp dir: hashes the k-mers, groups them by fine range and
+// uploads them; after this the sample is exactly as if simka_gpu_finish_sample had produced it.
+int simka_gpu_import_counts(simka_ctx *ctx, int sample_id, const uint64_t *kmers, const uint32_t *counts, uint64_t n, uint64_t nb_reads) {
+    if (!ctx) return SIMKA_ERR_INVALID;
+    if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done || (n && (!kmers || !counts)) || n >= (1ull << 32)) {
+        ctx->set_error("bad import arguments");
+        return SIMKA_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->prm.device));
+    cudaStream_t st = ctx->stream;
+    const int W = ctx->W;
+    if (ctx->fg_bits < 0) {
+        const uint64_t per_sample = ctx->prm.expected_kmers_per_sample ? ctx->prm.expected_kmers_per_sample / 4 : n;
+        int fg = ilog2_ceil(std::max<uint64_t>(1, per_sample * (uint64_t)ctx->prm.nb_samples / MRG_TARGET));
+        fg = std::min(fg, std::min(W, 20));
+        while (fg > 0 && ((size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4) > ((size_t)2 << 30)) fg--;
+        ctx->fg_bits = fg;
+        const size_t tbl = (size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4;
+        if (ctx->d_off_table.reserve(tbl)) { ctx->set_error("out of device memory (offset table)"); return SIMKA_ERR_NOMEM; }
+        CK(cudaMemsetAsync(ctx->d_off_table.p, 0, tbl, st));
+    }
+    const int fg = ctx->fg_bits;
+    const size_t fgn = ((size_t)1 << fg) + 1;
+    // counting sort by fine range on the host
+    std::vector<uint32_t> off(fgn, 0);
+    std::vector<uint64_t> h(n);
+    const uint64_t kmask = ctx->kp.mix.mask;
+    ull sum = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (kmers[i] > kmask || counts[i] == 0) { ctx->set_error("k-mer out of range or zero count in the imported list"); return SIMKA_ERR_INVALID; }
+        h[i] = simka::mix_fwd(kmers[i], ctx->kp.mix);
+        off[(size_t)(fg ? (h[i] >> (W - fg)) : 0) + 1]++;
+        sum += counts[i];
+    }
+    for (size_t f = 0; f + 1 < fgn; f++) off[f + 1] += off[f];
+    std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+    std::vector<uint64_t> eh(n);
+    std::vector<uint32_t> ec(n);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t pos = cur[(size_t)(fg ? (h[i] >> (W - fg)) : 0)]++;
+        eh[pos] = h[i];
+        ec[pos] = counts[i];
+    }
+    SampleData &sd = ctx->samples[sample_id];
+    sd.off = ctx->d_off_table.as<uint32_t>() + (size_t)sample_id * fgn;
+    CK(cudaMemcpyAsync(sd.off, off.data(), fgn * 4, cudaMemcpyHostToDevice, st));
+    if (n) {
+        sd.eh = (uint64_t *)ctx->arena.alloc(n * 8);
+        sd.ec = (uint32_t *)ctx->arena.alloc(n * 4);
+        if (!sd.eh || !sd.ec) { ctx->set_error("out of device memory (sample list)"); return SIMKA_ERR_NOMEM; }
+        CK(cudaMemcpyAsync(sd.eh, eh.data(), n * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sd.ec, ec.data(), n * 4, cudaMemcpyHostToDevice, st));
+        if (ctx->prm.complex_dist) {
+            int *d_error = reinterpret_cast<int *>(ctx->d_small.as<char>() + 32);
+            uint32_t *d_big_n = reinterpret_cast<uint32_t *>(ctx->d_small.as<char>() + 40);
+            const unsigned g = (unsigned)std::min<uint64_t>((n + BLOCK * 16 - 1) / (BLOCK * 16), (uint64_t)ctx->nsm * 4);
+            k_abundance_hist<<<g, BLOCK, 0, st>>>(sd.ec, n, sample_id, ctx->d_chist.as<ull>() + (size_t)sample_id * CHIST,
+                                                 ctx->d_big_counts.as<uint32_t>(), ctx->d_big_sample.as<uint32_t>(), d_big_n, ctx->big_cap, d_error);
+            ctx->launches++;
+        }
+    }
+    CK(cudaStreamSynchronize(st));  // the host staging vectors go out of scope
+    sd.n = n;
+    sd.done = true;
+    sd.local.nb_reads = nb_reads;
+    sd.local.nb_distinct = n;
+    sd.local.nb_kmers = sum;
+    sd.local.chord_n2 = 0;
+    for (uint64_t i = 0; i < n; i++) sd.local.chord_n2 += (uint64_t)((double)counts[i] * (double)counts[i]);
+    if (!ctx->totals_overridden) ctx->global_totals[sample_id] = sd.local;
+    ctx->entries += n;
+    return SIMKA_OK;
+}
+
 int simka_gpu_get_totals(simka_ctx *ctx, simka_sample_totals *out) {
     if (!ctx || !out) return SIMKA_ERR_INVALID;
     for (int s = 0; s < ctx->prm.nb_samples; s++) out[s] = ctx->samples[s].local;

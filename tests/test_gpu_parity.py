@@ -383,3 +383,98 @@ def test_simkamin_distance_edge_cases():
         ojac, obc = oracle.simkamin_distance(hashes, counts)
         np.testing.assert_array_equal(jac, ojac, err_msg=f"s={s}")
         np.testing.assert_array_equal(bc, obc, err_msg=f"s={s}")
+
+
+def test_stage_binaries_reference_temp_formats(tmp_path, golden_dir):
+    """simkaCount (one process per sample) + simkaMerge (one process per partition) of this build, exchanging the
+    reference's temp files: solid/part_P/__p__I.gz records, count_synchro/*.ok, stats/part_P.gz
+    long-double streams.  The partition files decode to the oracle's per-sample counts and the per-partition
+    statistics sum to the oracle's accumulators."""
+    import gzip
+    import struct
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    bindir = os.path.dirname(str(SIMKA_BIN))
+    inp = os.path.join(golden_dir, "example", "simka_input.txt")
+    k, t, P = 31, 2, 3
+    # the orchestrator lays out input/<id> albums and datasetIds (-keep-tmp)
+    r = subprocess.run([str(SIMKA_BIN), "-in", inp, "-out", str(tmp_path / "res"), "-out-tmp", str(tmp_path), "-kmer-size", str(k),
+                        "-abundance-min", str(t), "-keep-tmp", "-verbose", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    d = str(tmp_path / "simka_output_temp")
+    import shutil
+    shutil.rmtree(os.path.join(d, "count_synchro"))
+    spec = oracle.parse_simka_input(inp)
+    ids = [s[0] for s in spec]
+    for i, (ident, groups) in enumerate(spec):
+        cmd = [os.path.join(bindir, "simkaCountProcess"), os.path.join(bindir, "simkaCount"), "-kmer-size", str(k), "-out-tmp-simka", d, "-out-tmp",
+               os.path.join(d, "temp", ident), "-bank-name", ident, "-bank-index", str(i), "-nb-datasets", str(len(groups)), "-max-memory", "2000",
+               "-nb-cores", "2", "-in", "dummy", "-abundance-min", str(t), "-abundance-max", "999999999", "-min-read-size", "0",
+               "-min-shannon-index", "0.000000", "-max-reads", "0", "-nb-partitions", str(P)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    for p in range(P):
+        r = subprocess.run([os.path.join(bindir, "simkaMerge"), "-kmer-size", str(k), "-in", inp, "-out-tmp-simka", d, "-partition-id", str(p),
+                            "-max-memory", "2000", "-nb-cores", "1", "-simple-dist", "-complex-dist"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert os.path.exists(os.path.join(d, "merge_synchro", f"{p}.ok"))
+    # oracle on the same reads
+    _, samples = load_example(golden_dir)
+    run = oracle_run(samples, k, t)
+    N = len(ids)
+    for i, ident in enumerate(ids):
+        ok = [int(x) for x in open(os.path.join(d, "count_synchro", ident + ".ok")).read().split()]
+        assert ok == run.all_totals()[i].tolist()
+        recs = []
+        for p in range(P):
+            raw = gzip.open(os.path.join(d, "solid", f"part_{p}", f"__p__{i}.gz"), "rb").read()
+            assert len(raw) % 24 == 0
+            part = [struct.unpack_from("<QIIQ", raw, o) for o in range(0, len(raw), 24)]
+            assert all(b == i for _, b, _, _ in part)
+            assert [x[0] for x in part] == sorted(x[0] for x in part)  # ascending k-mers inside a partition file
+            recs += [(x[0], x[3]) for x in part]
+        recs.sort()
+        okm, oct_ = run.sample(i)
+        assert [x[0] for x in recs] == okm.tolist() and [x[1] for x in recs] == oct_.tolist()
+    # per-partition statistics: x87 long double stream in the order of SimkaStatistics::save
+    ns, nn = N * (N + 1) // 2, N * N
+    tot = None
+    for p in range(P):
+        v = np.frombuffer(gzip.open(os.path.join(d, "stats", f"part_{p}.gz"), "rb").read(), np.longdouble)
+        assert len(v) == 7 + 3 * N + nn + 2 * ns + (N + 3 * nn) + 3 * nn
+        assert v[0] == 1 and v[1] == 1
+        tot = v.copy() if tot is None else tot + v
+    o = 7
+    assert int(tot[4]) == run.nb_distinct_kmers and int(tot[6]) == run.nb_shared_kmers
+    assert [int(x) for x in v[o:o + N]] == run.all_totals()[:, 1].tolist()             # global, not summed
+    assert [int(x) for x in v[o + 2 * N:o + 3 * N]] == run.all_totals()[:, 2].tolist()
+    o += 3 * N
+    np.testing.assert_array_equal(tot[o:o + nn].astype(np.uint64).reshape(N, N), run.u64("nb_shared"))
+    o += nn
+    np.testing.assert_array_equal(tot[o:o + 2 * ns:2].astype(np.uint64), run.u64("distinct_shared"))
+    np.testing.assert_array_equal(tot[o + 1:o + 2 * ns:2].astype(np.uint64), run.u64("braycurtis_num"))
+    o += 2 * ns + N  # + chord_sqrt_N2
+    rows = tot[o:o + 3 * nn].reshape(N, 3, N)
+    np.testing.assert_array_equal(rows[:, 0].astype(np.uint64), run.u64("chord_ninj"))
+    np.testing.assert_array_equal(rows[:, 1].astype(np.uint64), run.u64("hellinger"))
+    np.testing.assert_array_equal(rows[:, 2].astype(np.uint64), run.u64("kulczynski"))
+    o += 3 * nn
+    rows = tot[o:o + 3 * nn].reshape(N, 3, N)
+    np.testing.assert_array_equal(rows[:, 0].astype(np.uint64), run.u64("canberra"))
+    np.testing.assert_array_equal(rows[:, 1].astype(np.uint64), run.u64("whittaker"))
+    np.testing.assert_allclose(rows[:, 2].astype(np.float64), run.f64("kl"), rtol=1e-10, atol=0)
+
+
+def test_import_counts_equals_counting():
+    """a sample registered from its (k-mer, count) list behaves exactly like a counted one"""
+    samples = synthetic_samples(5, 2500)
+    run = oracle_run(samples, 31, 2)
+    ctx = simka_b200.SimkaGpu(len(samples), 31, 2, simple_dist=True, complex_dist=True)
+    for s in range(len(samples)):
+        km, ct = run.sample(s)
+        perm = np.random.default_rng(s).permutation(len(km))
+        ctx.import_counts(s, km[perm], ct[perm], nb_reads=2500)
+    ctx.merge_and_accumulate()
+    st = ctx.stats()
+    ctx.close()
+    assert_stats_equal(st, run)

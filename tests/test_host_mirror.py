@@ -130,3 +130,23 @@ def test_cli_argument_handling(tmp_path):
     assert r.returncode == 1 and "memory" in r.stdout
     r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-kmer-size", "40"], capture_output=True, text=True)
     assert r.returncode == 1 and "kmer-size" in r.stdout
+
+
+def test_stage_binaries_argument_handling(tmp_path):
+    bindir = os.path.dirname(str(SIMKA_BIN))
+    for exe in ("simkaCount", "simkaMerge", "simkaCountProcess"):
+        assert os.path.exists(os.path.join(bindir, exe))
+    r = subprocess.run([os.path.join(bindir, "simkaCount"), "-kmer-size", "31"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("EXCEPTION: ") and "mandatory" in r.stdout
+    r = subprocess.run([os.path.join(bindir, "simkaMerge"), "-kmer-size", "31", "-out-tmp-simka", str(tmp_path), "-partition-id", "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "datasetIds" in r.stdout
+    # the retry wrapper: gives up after 5 failures, succeeds at once on exit 0
+    marker = tmp_path / "n"
+    script = tmp_path / "fail.sh"
+    script.write_text(f"#!/bin/sh\necho x >> {marker}\nexit 1\n")
+    script.chmod(0o755)
+    r = subprocess.run([os.path.join(bindir, "simkaCountProcess"), str(script)])
+    assert r.returncode == 1 and len(marker.read_text().split()) == 5
+    r = subprocess.run([os.path.join(bindir, "simkaCountProcess"), "true"])
+    assert r.returncode == 0
