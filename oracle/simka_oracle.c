@@ -764,6 +764,114 @@ void orc_simkamin_distance(const uint64_t *hashes, const uint32_t *counts, int n
 }
 
 /* ------------------------------------------------------------------------------------------
+ * SimkaMin sketch: src/simkaMin/SimkaMinCount.hpp:217-266 (SelectKmersCommand::operator()), :311-338
+ * (processUnfiltered), :168-189 (heap -> ascending array, zero padding at the front), MurmurHash3_x64_128
+ * (src/simkaMin/MurmurHash3.cpp:246-330; Austin Appleby's public-domain algorithm) on the 8 bytes of the
+ * canonical k-mer value, out[0] kept.
+ * Direct simulation of the reference's containers: a max-heap of the selected hashes + a hash -> count map.
+ * Note the reference's order dependence: once the heap is full an occurrence of the CURRENT maximum is not
+ * counted (the test is `hash < top`).
+ * ---------------------------------------------------------------------------------------- */
+static uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+uint64_t orc_murmur3_x64_128_u64(uint64_t key, uint32_t seed) {
+    uint64_t h1 = seed, h2 = seed;
+    uint64_t k1 = key;  /* tail of 8 bytes, little endian */
+    k1 *= 0x87c37b91114253d5ull; k1 = rotl64(k1, 31); k1 *= 0x4cf5ad432745937full; h1 ^= k1;
+    h1 ^= 8; h2 ^= 8;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2;
+    return h1;
+}
+
+typedef struct { uint64_t *key; uint32_t *val; uint8_t *used; size_t cap, n; } u64map;
+static size_t map_slot(const u64map *m, uint64_t k) { return (size_t)((k * 0x9E3779B97F4A7C15ull) >> 20) & (m->cap - 1); }
+static long map_find(const u64map *m, uint64_t k) {
+    size_t i = map_slot(m, k);
+    while (m->used[i]) { if (m->key[i] == k) return (long)i; i = (i + 1) & (m->cap - 1); }
+    return -1;
+}
+static void map_put(u64map *m, uint64_t k, uint32_t v) {
+    size_t i = map_slot(m, k);
+    while (m->used[i]) i = (i + 1) & (m->cap - 1);
+    m->used[i] = 1; m->key[i] = k; m->val[i] = v; m->n++;
+}
+static void map_erase(u64map *m, uint64_t k) {  /* backward-shift deletion */
+    long f = map_find(m, k);
+    if (f < 0) return;
+    size_t i = (size_t)f, j = i;
+    m->used[i] = 0; m->n--;
+    for (;;) {
+        j = (j + 1) & (m->cap - 1);
+        if (!m->used[j]) break;
+        size_t h = map_slot(m, m->key[j]);
+        if ((i <= j) ? (i < h && h <= j) : (i < h || h <= j)) continue;
+        m->used[i] = 1; m->key[i] = m->key[j]; m->val[i] = m->val[j]; m->used[j] = 0;
+        i = j;
+    }
+}
+static void sk_heap_push(uint64_t *h, size_t *n, uint64_t v) {
+    size_t i = (*n)++;
+    h[i] = v;
+    while (i > 0 && h[(i - 1) / 2] < h[i]) { uint64_t t = h[i]; h[i] = h[(i - 1) / 2]; h[(i - 1) / 2] = t; i = (i - 1) / 2; }
+}
+static void sk_heap_pop(uint64_t *h, size_t *n) {
+    h[0] = h[--(*n)];
+    size_t i = 0;
+    for (;;) {
+        size_t l = 2 * i + 1, r = l + 1, b = i;
+        if (l < *n && h[l] > h[b]) b = l;
+        if (r < *n && h[r] > h[b]) b = r;
+        if (b == i) break;
+        uint64_t t = h[i]; h[i] = h[b]; h[b] = t; i = b;
+    }
+}
+
+/* hashes_out / counts_out: sketch_size entries, ascending hashes, zero padding at the FRONT when the sample has
+ * fewer distinct k-mers.  Returns the number of selected hashes. */
+uint32_t orc_simkamin_sketch(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int k, uint32_t sketch_size,
+                             uint32_t seed, uint64_t *hashes_out, uint32_t *counts_out) {
+    u64map m;
+    m.cap = 16; while (m.cap < (size_t)sketch_size * 4 + 16) m.cap <<= 1;
+    m.key = calloc(m.cap, 8); m.val = calloc(m.cap, 4); m.used = calloc(m.cap, 1); m.n = 0;
+    uint64_t *heap = malloc(((size_t)sketch_size + 1) * 8);
+    size_t hn = 0;
+    uint64_t *canon = NULL; uint8_t *valid = NULL; size_t cap = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const size_t len = (size_t)(read_off[r + 1] - read_off[r]);
+        if (len < (size_t)k) continue;
+        if (len > cap) { cap = len * 2; canon = realloc(canon, cap * 8); valid = realloc(valid, cap); }
+        const size_t nk = orc_canonical_kmers(seqs + read_off[r], len, k, canon, valid);
+        for (size_t i = 0; i < nk; i++) {
+            if (!valid[i]) continue;
+            const uint64_t h = orc_murmur3_x64_128_u64(canon[i], seed);
+            if (hn < sketch_size) {                       /* SimkaMinCount.hpp:313-322 */
+                long f = map_find(&m, h);
+                if (f < 0) { sk_heap_push(heap, &hn, h); map_put(&m, h, 1); } else m.val[f] += 1;
+            } else if (h < heap[0]) {                      /* :324-336 */
+                long f = map_find(&m, h);
+                if (f < 0) { map_erase(&m, heap[0]); sk_heap_pop(heap, &hn); sk_heap_push(heap, &hn, h); map_put(&m, h, 1); }
+                else m.val[f] += 1;
+            }
+        }
+    }
+    const uint32_t n_sel = (uint32_t)hn;
+    for (uint32_t i = 0; i < sketch_size; i++) { hashes_out[i] = 0; counts_out[i] = 0; }
+    for (size_t i = 0; i < n_sel; i++) {                   /* :174-189: pop the maximum into the last free cell */
+        const uint64_t h = heap[0];
+        hashes_out[sketch_size - 1 - i] = h;
+        counts_out[sketch_size - 1 - i] = m.val[map_find(&m, h)];
+        sk_heap_pop(heap, &hn);
+    }
+    free(heap); free(m.key); free(m.val); free(m.used); free(canon); free(valid);
+    return n_sel;
+}
+
+/* ------------------------------------------------------------------------------------------
  * FASTA / FASTQ (.gz) reader: GC/bank/impl/BankFasta.cpp:485-572 (kseq-style)
  * ---------------------------------------------------------------------------------------- */
 typedef struct { gzFile f; unsigned char buf[1 << 16]; int beg, end, eof; } gzbuf;

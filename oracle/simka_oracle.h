@@ -95,6 +95,11 @@ void orc_matrix_from_accumulators(const orc_accumulators *a, int m, float *out);
 /* ---- SimkaMin distance (src/simkaMin/SimkaMinDistance.hpp:190-279) -------------------- */
 /* sketches: n x s (hash u64, count u32) in two arrays; leading zero hashes are padding
  * (loadSketches :521-586 strips them).  Writes n*n float32 Jaccard and Bray-Curtis. */
+/* SimkaMin sketch of one sample (src/simkaMin/SimkaMinCount.hpp:217-338): ascending bottom-s MurmurHash3 values of the
+ * valid canonical k-mers with their counts, zero padding at the front.  Returns the number of selected hashes. */
+uint64_t orc_murmur3_x64_128_u64(uint64_t key, uint32_t seed);
+uint32_t orc_simkamin_sketch(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int k, uint32_t sketch_size,
+                             uint32_t seed, uint64_t *hashes_out, uint32_t *counts_out);
 void orc_simkamin_distance(const uint64_t *hashes, const uint32_t *counts, int n, uint32_t s,
                            float *jaccard, float *braycurtis, int nthreads);
 

@@ -98,27 +98,45 @@ struct SimkaSequenceFilter {
     double _minShannonIndex;
 };
 
-// Reads one sample: for every group, the files in order, filtered, at most maxReads reads per group
-// (maxReads == 0: all).  `sink(ptr, len)` receives each selected read.  Returns the number of selected reads.
+// Read selection of SimkaInputIterator (src/core/SimkaCommons.hpp:150-314), restated: the files of a sample are read group
+// by group (a group = one ';' part of the input line).  Inside a group a counter is incremented for every filtered read
+// EXCEPT the first read of each file (first() does not count); the read that makes the counter reach maxReads is dropped
+// and the group ends.  So a group yields maxReads reads, plus one for every file switch that happens before the limit
+// (maxReads == 0: everything).
+struct GroupReadCounter {
+    uint64_t maxReads, count = 0;
+    bool first_of_file = true;
+    explicit GroupReadCounter(uint64_t m) : maxReads(m) {}
+    void new_file() { first_of_file = true; }
+    // call for every filtered read; false = drop it and stop the group
+    bool take() {
+        if (first_of_file) { first_of_file = false; return true; }
+        count++;
+        return !(maxReads && count >= maxReads);
+    }
+};
+
+// Reads one sample; `sink(ptr, len)` receives each selected read.  Returns the number of selected reads.
 template <class Sink>
 inline uint64_t read_sample(const SampleSpec &spec, const SimkaSequenceFilter &filter, uint64_t maxReads, Sink sink) {
     uint64_t total = 0;
     std::string data;
     for (const auto &group : spec.groups) {
-        uint64_t taken = 0;
+        GroupReadCounter ctr(maxReads);
+        bool stop = false;
         for (const std::string &file : group) {
-            if (maxReads && taken >= maxReads) break;
+            if (stop) break;
             bank::FastxParser parser(file);
+            ctr.new_file();
             for (;;) {
                 data.clear();
                 if (!parser.nextRead(data)) break;
                 if (!filter(data.data(), data.size())) continue;
+                if (!ctr.take()) { stop = true; break; }
                 sink(data.data(), data.size());
-                taken++;
-                if (maxReads && taken >= maxReads) break;
+                total++;
             }
         }
-        total += taken;
     }
     return total;
 }
@@ -131,21 +149,22 @@ inline uint64_t read_sample_into(const SampleSpec &spec, const SimkaSequenceFilt
                                  std::vector<uint64_t> &off, AfterRead after_read) {
     uint64_t total = 0;
     for (const auto &group : spec.groups) {
-        uint64_t taken = 0;
+        GroupReadCounter ctr(maxReads);
+        bool stop = false;
         for (const std::string &file : group) {
-            if (maxReads && taken >= maxReads) break;
+            if (stop) break;
             bank::FastxParser parser(file);
+            ctr.new_file();
             for (;;) {
                 const size_t start = seqs.size();
                 if (!parser.nextRead(seqs)) break;
                 if (!filter(seqs.data() + start, seqs.size() - start)) { seqs.resize(start); continue; }
+                if (!ctr.take()) { seqs.resize(start); stop = true; break; }
                 off.push_back(seqs.size());
                 after_read();
-                taken++;
-                if (maxReads && taken >= maxReads) break;
+                total++;
             }
         }
-        total += taken;
     }
     return total;
 }

@@ -101,3 +101,29 @@ def assert_stats_equal(st, run, kl_rtol=1e-10):
             np.testing.assert_allclose(a, b, rtol=1e-6, atol=0, err_msg=name)
         else:
             np.testing.assert_array_equal(a, b, err_msg=name)
+
+
+def select_reads(groups, max_reads, keep=lambda rd: True):
+    """Read selection of the reference's SimkaInputIterator (src/core/SimkaCommons.hpp:150-314): per ';' group the counter
+    skips the first read of every file and the read that makes it reach max_reads is dropped (0 = all reads)."""
+    reads = []
+    for grp in groups:
+        count, stop = 0, False
+        for f in grp:
+            if stop:
+                break
+            d, o = oracle.read_fastx(f)
+            first = True
+            for i in range(len(o) - 1):
+                rd = bytes(d[int(o[i]):int(o[i + 1])])
+                if not keep(rd):
+                    continue
+                if first:
+                    first = False
+                else:
+                    count += 1
+                    if max_reads and count >= max_reads:
+                        stop = True
+                        break
+                reads.append(rd)
+    return reads

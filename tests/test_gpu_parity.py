@@ -270,19 +270,8 @@ def test_simka_cli_max_reads_and_filters(tmp_path, golden_dir):
     samples, ids = [], []
     for ident, groups in oracle.parse_simka_input(inp):
         ids.append(ident)
-        reads = []
-        for grp in groups:
-            taken = 0
-            for f in grp:
-                d, o = oracle.read_fastx(f)
-                for i in range(len(o) - 1):
-                    rd = bytes(d[int(o[i]):int(o[i + 1])])
-                    if taken >= 50:
-                        break
-                    if len(rd) < 90 or L.simka_host_shannon_index(rd, len(rd)) < 1.5:
-                        continue
-                    reads.append(rd)
-                    taken += 1
+        from helpers import select_reads
+        reads = select_reads(groups, 50, keep=lambda rd: len(rd) >= 90 and L.simka_host_shannon_index(rd, len(rd)) >= 1.5)
         from helpers import reads_to_arrays
         samples.append(reads_to_arrays(reads))
     run = oracle_run(samples, 21, 1, simple=False, complex_=False)
