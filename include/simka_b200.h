@@ -46,6 +46,8 @@ typedef struct {
                               /*    src/SimkaPotara.hpp:991-1058); 0 or 1 = no sharding            */
     int32_t reserved;
     uint64_t expected_kmers_per_sample; /* sizing hint for the merge granularity, 0 = derive       */
+    int32_t sketch_mode;      /* 1: count MurmurHash3_x64_128(canonical k-mer, sketch_seed) instead of    */
+    uint32_t sketch_seed;     /*    the k-mer itself (SimkaMin sketches; stage 1 only)                    */
 } simka_params;
 
 /* Replaces the 4 lines of count_synchro/<id>.ok (src/SimkaCount.cpp:303-317,355-368). */
@@ -195,6 +197,15 @@ int simka_distance_matrix(const simka_stats_view *stats, int m, float *out /* N*
 size_t simka_matrix_csv(const simka_stats_view *stats, int m, const char *const *ids, char *buf, size_t cap);
 /* writes <dir>/<name>.csv.gz for every matrix, like outputMatrix */
 int simka_write_matrices(const simka_stats_view *stats, const char *const *ids, const char *out_dir);
+
+/* ---- SimkaMin sketch of one sample: replaces SelectKmersCommand (src/simkaMin/SimkaMinCount.hpp:217-338) --------
+ * Reads in the packed layout of simka_pack_reads (host memory).  hashes_out / counts_out: sketch_size entries, the
+ * bottom-s distinct MurmurHash3_x64_128(canonical k-mer, seed) values in ascending order with their counts, zero
+ * padding at the FRONT when the sample has fewer distinct k-mers (:174-189); *n_selected = entries that are not
+ * padding.  Reproduces the reference's order dependence: occurrences of the largest selected hash are counted only
+ * until the sketch is complete (the reference tests `hash < top`). */
+int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
+                        uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected);
 
 /* ---- SimkaMin: replaces ComputeDistanceManager::computeDistance_unsynch over all pairs ------------
  * (src/simkaMin/SimkaMinDistance.hpp:190-303).  hashes/counts: n sketches of s entries, ascending,

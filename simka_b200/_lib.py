@@ -16,7 +16,8 @@ class SimkaParams(C.Structure):
     _fields_ = [("kmer_size", C.c_int32), ("nb_samples", C.c_int32), ("abundance_min", C.c_int64),
                 ("abundance_max", C.c_int64), ("simple_dist", C.c_int32), ("complex_dist", C.c_int32),
                 ("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
-                ("reserved", C.c_int32), ("expected_kmers_per_sample", C.c_uint64)]
+                ("reserved", C.c_int32), ("expected_kmers_per_sample", C.c_uint64), ("sketch_mode", C.c_int32),
+                ("sketch_seed", C.c_uint32)]
 
 
 class SampleTotals(C.Structure):
@@ -70,6 +71,8 @@ SYMBOLS = {
     "simka_distance_matrix": (C.c_int, [C.POINTER(StatsView), C.c_int, f32p]),
     "simka_matrix_csv": (C.c_size_t, [C.POINTER(StatsView), C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_size_t]),
     "simka_write_matrices": (C.c_int, [C.POINTER(StatsView), C.POINTER(C.c_char_p), C.c_char_p]),
+    "simkamin_gpu_sketch": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, u64p, u32p,
+                            C.POINTER(C.c_uint32)]),
     "simkamin_gpu_distance": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, f32p, f32p, f32p]),
     "simka_host_kmers": (C.c_uint64, [C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p, C.POINTER(C.c_uint8)]),
     "simka_host_minimizer": (C.c_uint64, [C.c_uint64, C.c_int, C.c_int]),

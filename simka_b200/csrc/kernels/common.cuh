@@ -23,6 +23,8 @@ struct KParams {
     Mix mix;
     int k;
     int shard_rank, shard_count;
+    int key_mode;        // 0: key = mix(canonical k-mer) (2k bits); 1: key = MurmurHash3(canonical k-mer) (64 bits, SimkaMin sketches)
+    uint32_t seed;       // MurmurHash3 seed
 };
 
 __device__ __forceinline__ bool shard_keep(uint64_t h, const KParams &kp) {

@@ -161,3 +161,52 @@ __global__ void k_sketch_starts(const uint64_t *__restrict__ hashes, uint32_t n,
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (h[mid] == 0) lo = mid + 1; else hi = mid; }
     start[i] = lo;
 }
+
+// ---------------------------------------------------------------------------------------------
+// SimkaMin sketch, second look at the reads (the multiset count itself runs through stage 1 with
+// key = MurmurHash3): the reference counts occurrences of the LARGEST selected hash only until the sketch is
+// complete (processUnfiltered tests `hash < top`, src/simkaMin/SimkaMinCount.hpp:324), so its count depends on the
+// processing order.  MODE 0: first occurrence position of every sketch member (the sketch is complete at the largest
+// of them).  MODE 1: occurrences of the largest member at positions <= t_star.
+// Thread = one packed word = 32 k-mer start positions, same roll as k_extract.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK)
+k_sketch_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t n_words, int k, uint32_t seed,
+              const uint64_t *__restrict__ sketch, uint32_t n_sel, ull *__restrict__ first_pos, ull t_star, ull *__restrict__ count_out) {
+    const uint64_t t = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (t >= n_words || n_sel == 0) return;
+    uint64_t hi = seq[t], lo = seq[t + 1];
+    const uint64_t bm = ((uint64_t)bad[t] << 32) | bad[t + 1];
+    uint32_t okmask;
+    {
+        uint64_t r = bm;
+        int built = 1;
+        while (built * 2 <= k) { r |= r << built; built *= 2; }
+        if (built < k) r |= r << (k - built);
+        okmask = ~(uint32_t)(r >> 32);
+    }
+    const uint64_t top = sketch[n_sel - 1];
+    uint64_t rev = 0;
+    ull local = 0;
+    for (int j = 0; j < 32; j++) {
+        const uint64_t fwd = hi >> (64 - 2 * k);
+        if (j == 0) rev = simka::revcomp(fwd, k);
+        else rev = (rev >> 2) | ((uint64_t)((fwd & 3) ^ 2) << (2 * k - 2));
+        if ((okmask >> (31 - j)) & 1u) {
+            const uint64_t h = simka::murmur3_x64_128_u64(fwd < rev ? fwd : rev, seed);
+            const ull pos = (ull)t * 32 + j;
+            if (MODE == 0) {
+                if (h <= top) {
+                    uint32_t a = 0, b = n_sel;  // lower bound
+                    while (a < b) { const uint32_t mid = (a + b) >> 1; if (sketch[mid] < h) a = mid + 1; else b = mid; }
+                    if (a < n_sel && sketch[a] == h) atomicMin(&first_pos[a], pos);
+                }
+            } else if (h == top && pos <= t_star) local++;
+        }
+        hi = (hi << 2) | (lo >> 62);
+        lo <<= 2;
+    }
+    if (MODE == 1 && local) atomicAdd(count_out, local);
+}
+

@@ -156,7 +156,7 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
             if (j == 0) rev = simka::revcomp(fwd, k);
             else rev = (rev >> 2) | ((uint64_t)((fwd & 3) ^ 2) << (2 * k - 2));
             const uint64_t canon = fwd < rev ? fwd : rev;
-            const uint64_t h = simka::mix_fwd(canon, kp.mix);
+            const uint64_t h = kp.key_mode ? simka::murmur3_x64_128_u64(canon, kp.seed) : simka::mix_fwd(canon, kp.mix);
             bool keep = (okmask >> (31 - j)) & 1u;
             if (SHARDED) keep = keep && shard_keep(h, kp);
             keys[j] = h;

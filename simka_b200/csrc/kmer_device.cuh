@@ -72,6 +72,21 @@ inline Mix make_mix(int k) {
     return p;
 }
 
+// MurmurHash3_x64_128 (Austin Appleby, public domain) of the 8 bytes of a k-mer value, first output word: the hash
+// SimkaMin sketches with (src/simkaMin/SimkaMinCount.hpp:247-250, src/simkaMin/MurmurHash3.cpp:246-330)
+SIMKA_HD uint64_t murmur3_fmix64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+SIMKA_HD uint64_t murmur3_x64_128_u64(uint64_t key, uint32_t seed) {
+    uint64_t h1 = seed, h2 = seed, k1 = key;
+    k1 *= 0x87c37b91114253d5ull; k1 = (k1 << 31) | (k1 >> 33); k1 *= 0x4cf5ad432745937full; h1 ^= k1;
+    h1 ^= 8; h2 ^= 8;
+    h1 += h2; h2 += h1;
+    h1 = murmur3_fmix64(h1); h2 = murmur3_fmix64(h2);
+    return h1 + h2;
+}
+
 // secondary hash used for table slots / sub-pass selection / GPU shard choice
 SIMKA_HD uint64_t hash2(uint64_t h) { return h * 0x9E3779B97F4A7C15ull; }
 

@@ -180,7 +180,7 @@ static extract_fn extract_instance(bool count_only, bool sharded, bool bigk) {
 }
 static void launch_extract(simka_ctx *ctx, bool count_only, unsigned grid, const uint64_t *seq, const uint32_t *bad, uint64_t n_words, int b1_bits,
                            uint32_t *g_hist, const uint64_t *bucket_base, uint32_t *bucket_cursor, uint64_t cap, int *overflow, uint64_t *keys_out) {
-    const bool bigk = ctx->kp.k >= 17 && b1_bits <= 2 * ctx->kp.k - 32;
+    const bool bigk = !ctx->kp.key_mode && ctx->kp.k >= 17 && b1_bits <= 2 * ctx->kp.k - 32;
     if (bigk && !count_only && ctx->use_k16) {
         const unsigned g16 = (unsigned)((n_words + K16_THREADS / 2 - 1) / (K16_THREADS / 2));
         const size_t sm16 = 3 * MAX_B * 4 + 128 + L1_TILE * 8;
@@ -254,7 +254,14 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
     ctx->kp.k = p->kmer_size;
     ctx->kp.shard_rank = p->shard_rank;
     ctx->kp.shard_count = p->shard_count > 1 ? p->shard_count : 1;
+    ctx->kp.key_mode = p->sketch_mode ? 1 : 0;
+    ctx->kp.seed = p->sketch_seed;
     ctx->W = 2 * p->kmer_size;
+    if (ctx->kp.key_mode) {  // keys are 64-bit MurmurHash3 values: partition on their top bits
+        ctx->W = 64;
+        ctx->kp.mix.bits = 64;
+        ctx->kp.mix.mask = ~0ull;
+    }
     { const char *e = getenv("SIMKA_B200_EXACT_COUNT"); ctx->force_exact = e && e[0] == '1'; }
     { const char *e = getenv("SIMKA_B200_K1"); ctx->use_k16 = !(e && !strcmp(e, "256")); }
     cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
@@ -597,7 +604,8 @@ int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers,
     if (sd.n == 0) return SIMKA_OK;
     uint64_t *tmp = nullptr;
     CK(cudaMalloc(&tmp, sd.n * 8));
-    k_unmix<<<(unsigned)((sd.n + 255) / 256), 256, 0, ctx->stream>>>(sd.eh, tmp, sd.n, ctx->kp.mix);
+    if (ctx->kp.key_mode) CK(cudaMemcpyAsync(tmp, sd.eh, sd.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // the keys ARE the hashes
+    else k_unmix<<<(unsigned)((sd.n + 255) / 256), 256, 0, ctx->stream>>>(sd.eh, tmp, sd.n, ctx->kp.mix);
     std::vector<uint64_t> hk(sd.n);
     std::vector<uint32_t> hc(sd.n);
     CK(cudaMemcpyAsync(hk.data(), tmp, sd.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -764,6 +772,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
     const int N = ctx->prm.nb_samples;
     for (int s = 0; s < N; s++) if (!ctx->samples[s].done) { ctx->set_error("all samples must be finished before the merge"); return SIMKA_ERR_INVALID; }
     if (ctx->merged) { ctx->set_error("merge already done"); return SIMKA_ERR_INVALID; }
+    if (ctx->kp.key_mode) { ctx->set_error("a sketch-mode context has no stage 2"); return SIMKA_ERR_INVALID; }
     CK(cudaSetDevice(ctx->prm.device));
     cudaStream_t st = ctx->stream;
     if (ctx->import_pending) {  // abundance sums of the imported sample slices
@@ -966,6 +975,70 @@ int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
         if (cudaMemcpy(sc, ctx->a_scalars, 32, cudaMemcpyDeviceToHost) == cudaSuccess) { t.distinct_kmers = sc[0]; t.pairs = sc[2]; }
     }
     *out = t;
+    return SIMKA_OK;
+}
+
+int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
+                        uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected) {
+    if (!hashes_out || !counts_out || sketch_size == 0 || (n_words && (!packed || !bad))) return SIMKA_ERR_INVALID;
+    simka_params prm;
+    memset(&prm, 0, sizeof prm);
+    prm.kmer_size = kmer_size;
+    prm.nb_samples = 1;
+    prm.abundance_min = 0;
+    prm.abundance_max = 0x7FFFFFFFFFFFFFFFll;
+    prm.device = device;
+    prm.sketch_mode = 1;
+    prm.sketch_seed = seed;
+    simka_ctx *ctx = nullptr;
+    int rc = simka_gpu_create(&ctx, &prm);
+    if (rc != SIMKA_OK) return rc;
+    std::vector<uint64_t> hk;
+    std::vector<uint32_t> hc;
+    uint64_t n = 0;
+    do {
+        // exact multiset count of the hashes: stage 1 with key = MurmurHash3(canonical k-mer)
+        if ((rc = simka_gpu_push_reads(ctx, 0, packed, bad, n_words, n_reads)) != SIMKA_OK) break;
+        if ((rc = simka_gpu_finish_sample(ctx, 0, nullptr)) != SIMKA_OK) break;
+        if ((rc = simka_gpu_dump_sample_counts(ctx, 0, nullptr, nullptr, &n)) != SIMKA_OK) break;
+        hk.resize(std::max<uint64_t>(n, 1));
+        hc.resize(std::max<uint64_t>(n, 1));
+        if ((rc = simka_gpu_dump_sample_counts(ctx, 0, hk.data(), hc.data(), &n)) != SIMKA_OK) break;  // ascending hashes
+    } while (0);
+    if (rc != SIMKA_OK) { simka_gpu_destroy(ctx); return rc; }
+    const uint32_t n_sel = (uint32_t)std::min<uint64_t>(n, sketch_size);
+    // the order-dependent count of the largest member once the sketch is complete (only when it can be complete)
+    if (n >= sketch_size && n_sel > 0) {
+        uint64_t *d_sk = nullptr; ull *d_first = nullptr, *d_cnt = nullptr;
+        uint64_t *d_packed = nullptr; uint32_t *d_bad = nullptr;
+        bool ok = cudaMalloc(&d_sk, (size_t)n_sel * 8) == cudaSuccess && cudaMalloc(&d_first, (size_t)n_sel * 8) == cudaSuccess &&
+                  cudaMalloc(&d_cnt, 8) == cudaSuccess && cudaMalloc(&d_packed, (n_words + 1) * 8) == cudaSuccess &&
+                  cudaMalloc(&d_bad, (n_words + 1) * 4) == cudaSuccess;
+        ok = ok && cudaMemcpy(d_sk, hk.data(), (size_t)n_sel * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemset(d_first, 0xFF, (size_t)n_sel * 8) == cudaSuccess && cudaMemset(d_cnt, 0, 8) == cudaSuccess &&
+             cudaMemcpy(d_packed, packed, (n_words + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(d_bad, bad, (n_words + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok) {
+            const unsigned g = (unsigned)((n_words + BLOCK - 1) / BLOCK);
+            k_sketch_scan<0><<<g, BLOCK>>>(d_packed, d_bad, n_words, kmer_size, seed, d_sk, n_sel, d_first, 0, d_cnt);
+            std::vector<ull> first(n_sel);
+            ok = cudaMemcpy(first.data(), d_first, (size_t)n_sel * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+            ull t_star = 0;
+            for (uint32_t i = 0; i < n_sel; i++) t_star = std::max(t_star, first[i]);
+            if (ok) {
+                k_sketch_scan<1><<<g, BLOCK>>>(d_packed, d_bad, n_words, kmer_size, seed, d_sk, n_sel, d_first, t_star, d_cnt);
+                ull cnt = 0;
+                ok = cudaMemcpy(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+                if (ok) hc[n_sel - 1] = (uint32_t)cnt;
+            }
+        }
+        cudaFree(d_sk); cudaFree(d_first); cudaFree(d_cnt); cudaFree(d_packed); cudaFree(d_bad);
+        if (!ok) { simka_gpu_destroy(ctx); return SIMKA_ERR_CUDA; }
+    }
+    simka_gpu_destroy(ctx);
+    for (uint32_t i = 0; i < sketch_size; i++) { hashes_out[i] = 0; counts_out[i] = 0; }
+    for (uint32_t i = 0; i < n_sel; i++) { hashes_out[sketch_size - n_sel + i] = hk[i]; counts_out[sketch_size - n_sel + i] = hc[i]; }
+    if (n_selected) *n_selected = n_sel;
     return SIMKA_OK;
 }
 
