@@ -187,6 +187,12 @@ uint64_t simka_pack_words(uint64_t total_bases, uint64_t n_reads);
  * packed/bad must hold simka_pack_words()+1 entries.  Returns the number of words used. */
 uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n_reads,
                           uint64_t *packed, uint32_t *bad, int nthreads);
+/* Same, for a given -kmer-size: with k <= 15 the reference counts with MiniKC, which does NOT skip windows containing a
+ * non-ACGT character (src/SimkaCount.cpp:283-288, src/minikc/MiniKC.hpp:219-231; the character contributes its
+ * (c>>1)&3 code), so only the read separators are marked bad.  simka_pack_reads == kmer_size 31.
+ * simka_gpu_push_ascii applies the same rule from the context's kmer_size. */
+uint64_t simka_pack_reads_k(const char *seqs, const uint64_t *read_off, uint64_t n_reads,
+                            uint64_t *packed, uint32_t *bad, int nthreads, int kmer_size);
 
 /* Replaces SimkaDistance + SimkaStatistics::outputMatrix (src/core/SimkaDistance.cpp:603-649,920-1226).
  * Matrix order = the reference's output order: 15 default, +3 if simple, +3 if complex. */

@@ -234,7 +234,10 @@ static void count_sample(orc_run *r, int s) {
         const char *seq = r->seqs + r->read_off[q];
         size_t len = r->read_off[q + 1] - r->read_off[q];
         size_t m = orc_canonical_kmers(seq, len, k, kb, vb);
-        for (size_t i = 0; i < m; i++) if (vb[i]) keys[nk++] = kb[i]; /* invalid windows are skipped */
+        /* invalid windows are skipped -- except for k <= 15, where simkaCount switches to MiniKC (src/SimkaCount.cpp:283-288),
+         * whose counting loop does not test isValid() (src/minikc/MiniKC.hpp:219-231): every window is counted, a non-ACGT
+         * character contributing its (c>>1)&3 code */
+        for (size_t i = 0; i < m; i++) if (vb[i] || k <= 15) keys[nk++] = kb[i];
     }
     free(kb); free(vb);
     radix_sort_u64(keys, tmp, nk, 2 * k);

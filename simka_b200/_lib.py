@@ -66,6 +66,7 @@ SYMBOLS = {
     "simka_gpu_stream": (C.c_void_p, [C.c_void_p]),
     "simka_pack_words": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "simka_pack_reads": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
+    "simka_pack_reads_k": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "simka_nb_matrices": (C.c_int, [C.POINTER(StatsView)]),
     "simka_matrix_name": (C.c_char_p, [C.POINTER(StatsView), C.c_int]),
     "simka_distance_matrix": (C.c_int, [C.POINTER(StatsView), C.c_int, f32p]),

@@ -26,8 +26,9 @@ def _vp(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def pack_reads(seqs: np.ndarray, read_off: np.ndarray, nthreads: int = 0, pinned: bool = False):
-    """2-bit pack + bad mask in the layout simka_gpu_push_reads expects.
+def pack_reads(seqs: np.ndarray, read_off: np.ndarray, nthreads: int = 0, pinned: bool = False, kmer_size: int = 31):
+    """2-bit pack + bad mask in the layout simka_gpu_push_reads expects (kmer_size <= 15: the MiniKC rule, only read
+    separators are bad, see simka_pack_reads_k).
     -> (packed uint64[n_words+1], bad uint32[n_words+1], n_words)"""
     L = _lib.load()
     seqs = np.ascontiguousarray(seqs, np.uint8)
@@ -43,7 +44,7 @@ def pack_reads(seqs: np.ndarray, read_off: np.ndarray, nthreads: int = 0, pinned
         bad = np.empty(nw + 1, np.uint32)
     if seqs.size == 0:
         seqs = np.zeros(1, np.uint8)
-    used = L.simka_pack_reads(_vp(seqs), _vp(read_off), n_reads, _vp(packed), _vp(bad), nthreads)
+    used = L.simka_pack_reads_k(_vp(seqs), _vp(read_off), n_reads, _vp(packed), _vp(bad), nthreads, kmer_size)
     assert used == nw
     return packed, bad, nw
 
@@ -301,7 +302,7 @@ def run_samples(samples, kmer_size: int, abundance_min: int = 2, abundance_max: 
         if ascii_path:
             ctx.push_ascii(s, seqs, off)
         else:
-            packed, bad, nw = pack_reads(seqs, off)
+            packed, bad, nw = pack_reads(seqs, off, kmer_size=kmer_size)
             ctx.push_reads(s, packed, bad, nw, len(off) - 1)
         ctx.finish_sample(s)
     ctx.merge_and_accumulate()

@@ -8,7 +8,7 @@
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLOCK) k_pack_ascii(const char *__restrict__ seqs, const uint64_t *__restrict__ read_off,
                                                       uint64_t n_reads, uint64_t n_words, uint64_t *__restrict__ packed,
-                                                      uint32_t *__restrict__ bad) {
+                                                      uint32_t *__restrict__ bad, int badchars /* 0: k <= 15, only separators are bad */) {
     uint64_t t = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (t > n_words) return;
     if (t == n_words) { packed[t] = 0; bad[t] = 0xFFFFFFFFu; return; }
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(BLOCK) k_pack_ascii(const char *__restrict__ s
                 unsigned char c = (unsigned char)seqs[rbeg + o];
                 code = (c >> 1) & 3u;
                 unsigned char u = c & 0xDF;  // upper-case
-                isbad = !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
+                isbad = badchars && !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
                 o++;
             } else {  // separator
                 r++;

@@ -47,7 +47,7 @@ static int run(int argc, char **argv) {
     const uint64_t words = simka_pack_words(seqs.size(), off.size() - 1);
     std::vector<uint64_t> packed(words + 1);
     std::vector<uint32_t> bad(words + 1);
-    simka_pack_reads(seqs.data(), off.data(), off.size() - 1, packed.data(), bad.data(), kv.count("-nb-cores") ? atoi(kv["-nb-cores"].c_str()) : 0);
+    simka_pack_reads_k(seqs.data(), off.data(), off.size() - 1, packed.data(), bad.data(), kv.count("-nb-cores") ? atoi(kv["-nb-cores"].c_str()) : 0, k);
     simka_sample_totals tot;
     if (simka_gpu_push_reads(ctx, 0, packed.data(), bad.data(), words, off.size() - 1) != SIMKA_OK || simka_gpu_finish_sample(ctx, 0, &tot) != SIMKA_OK)
         throw bank::Exception(std::string("counting failed: ") + simka_gpu_last_error(ctx));

@@ -411,7 +411,7 @@ int simka_gpu_push_ascii(simka_ctx *ctx, int sample_id, const char *seqs, const 
     if (!rel.empty()) CK(cudaStreamSynchronize(ctx->copy_stream));
     const unsigned grid = (unsigned)((n_words + 1 + BLOCK - 1) / BLOCK);
     k_pack_ascii<<<grid, BLOCK, 0, ctx->copy_stream>>>(ctx->d_ascii.as<char>(), ctx->d_roff.as<uint64_t>(), n_reads, n_words,
-                                                       sl->packed.as<uint64_t>() + w0, sl->bad.as<uint32_t>() + w0);
+                                                       sl->packed.as<uint64_t>() + w0, sl->bad.as<uint32_t>() + w0, ctx->prm.kmer_size > 15);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(sl->copied, ctx->copy_stream));

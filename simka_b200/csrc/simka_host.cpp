@@ -246,6 +246,14 @@ int simka_write_matrices(const simka_stats_view *s, const char *const *ids, cons
 uint64_t simka_pack_words(uint64_t total_bases, uint64_t n_reads) { return (total_bases + n_reads + 31) / 32; }
 
 uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n_reads, uint64_t *packed, uint32_t *bad, int nthreads) {
+    return simka_pack_reads_k(seqs, read_off, n_reads, packed, bad, nthreads, 31);
+}
+
+uint64_t simka_pack_reads_k(const char *seqs, const uint64_t *read_off, uint64_t n_reads, uint64_t *packed, uint32_t *bad, int nthreads,
+                            int kmer_size) {
+    // k <= 15: the reference counts with MiniKC, which does not skip windows that contain a non-ACGT character
+    // (src/minikc/MiniKC.hpp:219-231): only the read separators are marked bad
+    const bool badchars = kmer_size > 15;
     const uint64_t base0 = n_reads ? read_off[0] : 0;
     const uint64_t total = n_reads ? read_off[n_reads] - base0 : 0;
     const uint64_t n_words = simka_pack_words(total, n_reads);
@@ -270,7 +278,9 @@ uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n
         static const struct BadTab {
             uint8_t t[256];
             BadTab() { for (int c = 0; c < 256; c++) { int u = c & 0xDF; t[c] = !(u == 'A' || u == 'C' || u == 'G' || u == 'T'); } }
-        } bt;
+        } bt_all;
+        static const struct NoBadTab { uint8_t t[256]; NoBadTab() { memset(t, 0, sizeof t); } } bt_none;
+        const uint8_t *btt = badchars ? bt_all.t : bt_none.t;
         uint64_t w = w0, acc = 0;
         uint32_t bacc = 0;
         int cnt = 0;  // positions already in (acc, bacc)
@@ -292,13 +302,13 @@ uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n
                 uint64_t avail = rend - (rbeg + o);
                 if (cnt == 0 && avail >= 32) {  // fast path: a whole word inside the read
                     uint64_t v = 0; uint32_t bb = 0;
-                    for (int j = 0; j < 32; j++) { const unsigned c = sp[j]; v = (v << 2) | ((c >> 1) & 3u); bb = (bb << 1) | bt.t[c]; }
+                    for (int j = 0; j < 32; j++) { const unsigned c = sp[j]; v = (v << 2) | ((c >> 1) & 3u); bb = (bb << 1) | btt[c]; }
                     packed[w] = v; bad[w] = bb; w++;
                     o += 32;
                     continue;
                 }
                 const int take = (int)std::min<uint64_t>(avail, (uint64_t)(32 - cnt));
-                for (int j = 0; j < take; j++) { const unsigned c = sp[j]; acc = (acc << 2) | ((c >> 1) & 3u); bacc = (bacc << 1) | bt.t[c]; }
+                for (int j = 0; j < take; j++) { const unsigned c = sp[j]; acc = (acc << 2) | ((c >> 1) & 3u); bacc = (bacc << 1) | btt[c]; }
                 cnt += take;
                 o += take;
             }

@@ -267,7 +267,7 @@ int run(int argc, char **argv) {
                     const uint64_t nr = off.size() - 1;
                     const uint64_t words = simka_pack_words(seqs.size(), nr);
                     PinnedChunk *c = get_chunk(words);
-                    simka_pack_reads(seqs.data(), off.data(), nr, c->packed, c->bad, 1);
+                    simka_pack_reads_k(seqs.data(), off.data(), nr, c->packed, c->bad, 1, o.kmerSize);
                     P.chunks.push_back(c);
                     P.words.push_back(words);
                     P.reads.push_back(nr);

@@ -132,3 +132,18 @@ def test_statistics_iadd():
     b.kullback_leibler[0, 1] = 0.25
     a += b
     assert (a.nb_shared == 12).all() and a.nb_distinct_kmers == 5 and a.kullback_leibler[0, 1] == 0.25
+
+
+def test_pack_reads_minikc_rule():
+    """k <= 15: only the read separators are bad (the reference's MiniKC counts windows with non-ACGT characters)"""
+    from helpers import reads_to_arrays
+    seqs, off = reads_to_arrays([b"ACGTNNACGT", b"acgtxACG"])
+    p31, b31, nw = simka_b200.pack_reads(seqs, off, kmer_size=31)
+    p15, b15, nw15 = simka_b200.pack_reads(seqs, off, kmer_size=15)
+    assert nw == nw15 == 1
+    np.testing.assert_array_equal(p31, p15)  # same codes, (c>>1)&3 for every character
+    bits31 = format(int(b31[0]), "032b")
+    bits15 = format(int(b15[0]), "032b")
+    assert bits31[:20] == "00001100001" + "000010001"   # NN, separator, x, separator
+    assert bits15[:20] == "00000000001" + "000000001"   # separators only
+    assert bits31[20:] == bits15[20:] == "1" * 12        # padding
