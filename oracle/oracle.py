@@ -25,6 +25,32 @@ def build(force: bool = False) -> Path:
     return _LIB_PATH
 
 
+REF_MURMUR = _HERE / "_ref" / "libmurmur_ref.so"
+
+
+def build_ref() -> Path | None:
+    """oracle/_ref: the reference's own MurmurHash3.cpp compiled where it lies (build_ref.sh); only possible where
+    /root/reference exists (the build container).  Returns the library path, or None when it could not be built."""
+    if os.path.exists("/root/reference/src/simkaMin/MurmurHash3.cpp"):
+        subprocess.run(["make", "-C", str(_HERE), "-s", "ref"], check=True)
+    return REF_MURMUR if REF_MURMUR.exists() else None
+
+
+def ref_murmur3_x64_128_u64(keys: np.ndarray, seed: int) -> np.ndarray:
+    """out[0] of the REFERENCE's MurmurHash3_x64_128(&key, 8, seed, out) for every key (oracle/_ref/libmurmur_ref.so)"""
+    L = C.CDLL(str(REF_MURMUR))
+    f = getattr(L, "_Z19MurmurHash3_x64_128PKvijPv")  # void MurmurHash3_x64_128(const void*, int, uint32_t, void*)
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.zeros(2, dtype=np.uint64)
+    res = np.empty(len(keys), dtype=np.uint64)
+    for i in range(len(keys)):
+        f(keys[i:i + 1].ctypes.data, 8, seed, out.ctypes.data)
+        res[i] = out[0]
+    return res
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:

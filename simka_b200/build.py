@@ -53,9 +53,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     BIN = SIMKA_BIN.parent
     BIN.mkdir(exist_ok=True)
     cuda_lib = str(Path(_nvcc()).resolve().parent.parent / "lib64")
-    # the command lines of the reference (g++, linked against the library): simka, simkaCount, simkaMerge, simkaCountProcess
+    # the command lines of the reference (g++, linked against the library): simka, simkaCount, simkaMerge, simkaCountProcess, simkaMinCore
     for exe, src, link in (("simka", "simka_main.cpp", True), ("simkaCount", "simka_count_main.cpp", True),
-                           ("simkaMerge", "simka_merge_main.cpp", True), ("simkaCountProcess", "simka_count_process_main.cpp", False)):
+                           ("simkaMerge", "simka_merge_main.cpp", True), ("simkaCountProcess", "simka_count_process_main.cpp", False),
+                           ("simkaMinCore", "simkamin_main.cpp", True)):
         cli, out = CSRC / src, BIN / exe
         if not cli.exists():
             continue

@@ -28,22 +28,30 @@ __device__ __forceinline__ void block_sum3(ull &a, ull &b, ull &c, ull *tmp /*[3
     for (int w = 0; w < BLOCK / 32; w++) { a += tmp[w]; b += tmp[8 + w]; c += tmp[16 + w]; }
 }
 
+// RECT = false: pair p of the upper triangle of one set of n sketches; RECT = true: pair (p / n2, p % n2) of two sets
+// (hashes/counts/start: n sketches; hashes2/counts2/start2: n2 sketches), the rectangular blocks of simkaMinCore distance
+template <bool RECT>
 __global__ void __launch_bounds__(BLOCK)
 k_simkamin_tiled(const uint64_t *__restrict__ hashes, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ start,
-                 uint32_t n, uint32_t s, ull *__restrict__ quad /*[pairs][4]: shared, distinct, sharedK, kmers*/) {
+                 uint32_t n, const uint64_t *__restrict__ hashes2, const uint32_t *__restrict__ counts2, const uint32_t *__restrict__ start2,
+                 uint32_t n2, uint32_t s, ull *__restrict__ quad /*[pairs][4]: shared, distinct, sharedK, kmers*/) {
     static_assert(BLOCK == 256, "block_sum3 assumes 8 warps");
     const uint64_t p = blockIdx.x;
-    const double tn = 2.0 * n - 1.0;
-    int i = (int)((tn - sqrt(tn * tn - 8.0 * (double)p)) * 0.5);
-    if (i < 0) i = 0;
-    while ((uint64_t)(i + 1) * (2ull * n - (i + 1) - 1) / 2 <= p) i++;
-    while ((uint64_t)i * (2ull * n - i - 1) / 2 > p) i--;
-    const int j = i + 1 + (int)(p - (uint64_t)i * (2ull * n - i - 1) / 2);
+    int i, j;
+    if (RECT) { i = (int)(p / n2); j = (int)(p % n2); }
+    else {
+        const double tn = 2.0 * n - 1.0;
+        i = (int)((tn - sqrt(tn * tn - 8.0 * (double)p)) * 0.5);
+        if (i < 0) i = 0;
+        while ((uint64_t)(i + 1) * (2ull * n - (i + 1) - 1) / 2 <= p) i++;
+        while ((uint64_t)i * (2ull * n - i - 1) / 2 > p) i--;
+        j = i + 1 + (int)(p - (uint64_t)i * (2ull * n - i - 1) / 2);
+    }
     const uint64_t *A = hashes + (size_t)i * s + start[i];
-    const uint64_t *B = hashes + (size_t)j * s + start[j];
+    const uint64_t *B = (RECT ? hashes2 : hashes) + (size_t)j * s + (RECT ? start2 : start)[j];
     const uint32_t *CA = counts + (size_t)i * s + start[i];
-    const uint32_t *CB = counts + (size_t)j * s + start[j];
-    const uint32_t na = s - start[i], nb = s - start[j];
+    const uint32_t *CB = (RECT ? counts2 : counts) + (size_t)j * s + (RECT ? start2 : start)[j];
+    const uint32_t na = s - start[i], nb = s - (RECT ? start2 : start)[j];
     const uint32_t S = min(na, nb);  // sketchSize = min of the two stripped sizes (:204)
 
     __shared__ uint64_t sa[SMT_TILE], sb[SMT_TILE];

@@ -1058,7 +1058,7 @@ int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *co
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
         k_sketch_starts<<<(n + 255) / 256, 256>>>(dh, n, s, dstart);
-        if (pairs) k_simkamin_tiled<<<(unsigned)pairs, BLOCK>>>(dh, dc, dstart, n, s, dq);
+        if (pairs) k_simkamin_tiled<false><<<(unsigned)pairs, BLOCK>>>(dh, dc, dstart, n, nullptr, nullptr, nullptr, 0, s, dq);
         cudaEventRecord(e1);
         if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
         if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
@@ -1079,6 +1079,45 @@ int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *co
             jaccard[(size_t)i * n + j] = jaccard[(size_t)j * n + i] = ja;
             braycurtis[(size_t)i * n + j] = braycurtis[(size_t)j * n + i] = b;
         }
+    return rc;
+}
+
+// all n1 x n2 pairs between two sets of sketches (the rectangular blocks of `simkaMinCore distance`,
+// src/simkaMin/SimkaMinDistance.hpp:642-753); outputs n1*n2 float32 row-major
+int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32_t *counts1, uint32_t n1, const uint64_t *hashes2,
+                               const uint32_t *counts2, uint32_t n2, uint32_t s, float *jaccard, float *braycurtis, float *kernel_ms) {
+    if (!hashes1 || !counts1 || !hashes2 || !counts2 || !jaccard || !braycurtis || n1 == 0 || n2 == 0 || s == 0) return SIMKA_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return SIMKA_ERR_CUDA;
+    uint64_t *dh1 = nullptr, *dh2 = nullptr; uint32_t *dc1 = nullptr, *dc2 = nullptr, *ds1 = nullptr, *ds2 = nullptr; ull *dq = nullptr;
+    const size_t e1 = (size_t)n1 * s, e2 = (size_t)n2 * s;
+    const uint64_t pairs = (uint64_t)n1 * n2;
+    int rc = SIMKA_OK;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<ull> hq(4 * pairs);
+    do {
+        if (cudaMalloc(&dh1, e1 * 8) || cudaMalloc(&dc1, e1 * 4) || cudaMalloc(&ds1, (size_t)n1 * 4) || cudaMalloc(&dh2, e2 * 8) || cudaMalloc(&dc2, e2 * 4) ||
+            cudaMalloc(&ds2, (size_t)n2 * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
+        if (cudaMemcpy(dh1, hashes1, e1 * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc1, counts1, e1 * 4, cudaMemcpyHostToDevice) ||
+            cudaMemcpy(dh2, hashes2, e2 * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc2, counts2, e2 * 4, cudaMemcpyHostToDevice)) { rc = SIMKA_ERR_CUDA; break; }
+        cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+        cudaEventRecord(ev0);
+        k_sketch_starts<<<(n1 + 255) / 256, 256>>>(dh1, n1, s, ds1);
+        k_sketch_starts<<<(n2 + 255) / 256, 256>>>(dh2, n2, s, ds2);
+        k_simkamin_tiled<true><<<(unsigned)pairs, BLOCK>>>(dh1, dc1, ds1, n1, dh2, dc2, ds2, n2, s, dq);
+        cudaEventRecord(ev1);
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
+        if (kernel_ms) cudaEventElapsedTime(kernel_ms, ev0, ev1);
+        if (cudaMemcpy(hq.data(), dq, pairs * 32, cudaMemcpyDeviceToHost)) { rc = SIMKA_ERR_CUDA; break; }
+    } while (0);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    cudaFree(dh1); cudaFree(dc1); cudaFree(ds1); cudaFree(dh2); cudaFree(dc2); cudaFree(ds2); cudaFree(dq);
+    if (rc) return rc;
+    for (uint64_t p = 0; p < pairs; p++) {  // final ratios exactly as the reference: long double division, stored as float (:244-259)
+        const ull sh = hq[4 * p], di = hq[4 * p + 1], sk = hq[4 * p + 2], km = hq[4 * p + 3];
+        jaccard[p] = di == 0 ? 1.0f : (float)(1 - (long double)sh / (long double)di);
+        braycurtis[p] = km == 0 ? 1.0f : (float)(1 - (long double)(2 * sk) / (long double)km);
+    }
     return rc;
 }
 

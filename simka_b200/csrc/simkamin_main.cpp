@@ -1,0 +1,213 @@
+// simkamin_main.cpp -- `simkaMinCore sketch | distance | export` with the reference's command lines and file formats
+// (src/simkaMin/SimkaMin.cpp:30-110; sketch: SimkaMinCount.hpp:1347-1381,713-1127; distance: SimkaMinDistance.hpp:414-640,
+//  955-998; export: SimkaMinDistanceMatrixExporter.hpp:330-404), so that the reference's simkaMin.py wrapper can drive it.
+//   sketch file:  u8 kmerSize, u32 sketchSize, u32 seed, u32 nbDatasets (13 bytes, SimkaMinCommons.hpp:28), then per dataset
+//                 sketchSize x {u64 hash, u32 count, 4 pad} ascending (zero padding first), then the ids as u8 length + bytes
+//   distance:     mat_presenceAbsence_jaccard.bin / mat_abundance_braycurtis.bin, float32 at (i * nbDatasets2 + j) * 4
+//   export:       <name>.csv.gz, header ";id..." and rows "id;%f;..."
+// -filter (approximate Bloom filter, SimkaMinCount.hpp:341-380) is not supported.
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+
+#include "host/simka_input.hpp"
+#include "host/stage_files.hpp"
+
+using namespace simka_b200;
+
+namespace {
+
+struct Entry { uint64_t hash; uint32_t count; uint32_t pad; };
+static_assert(sizeof(Entry) == 16, "KmerAndCountType is 16 bytes");
+const uint64_t HEADER = 13;
+
+struct SketchHeader { uint8_t k; uint32_t s, seed, n; };
+
+SketchHeader read_header(const std::string &path) {
+    std::ifstream f(path.c_str(), std::ios::binary);
+    if (!f) throw bank::Exception("cannot open sketch file " + path);
+    SketchHeader h;
+    f.read((char *)&h.k, 1); f.read((char *)&h.s, 4); f.read((char *)&h.seed, 4); f.read((char *)&h.n, 4);
+    if (!f) throw bank::Exception("bad sketch file " + path);
+    return h;
+}
+
+std::vector<std::string> read_ids(const std::string &path, const SketchHeader &h) {
+    std::ifstream f(path.c_str(), std::ios::binary);
+    f.seekg((std::streamoff)(HEADER + (uint64_t)h.n * h.s * sizeof(Entry)));
+    std::vector<std::string> ids;
+    for (uint32_t i = 0; i < h.n; i++) {
+        uint8_t len = 0;
+        f.read((char *)&len, 1);
+        std::string s(len, ' ');
+        f.read(&s[0], len);
+        ids.push_back(s);
+    }
+    return ids;
+}
+
+long long geti(std::map<std::string, std::string> &kv, const char *k, long long def) { return kv.count(k) ? atoll(kv[k].c_str()) : def; }
+
+int do_sketch(std::map<std::string, std::string> &kv) {
+    if (!kv.count("-in")) throw bank::Exception("Option '-in' is mandatory");
+    if (kv.count("-filter")) throw bank::Exception("-filter (approximate Bloom filter) is not supported by this build");
+    const std::string out = kv.count("-out") ? kv["-out"] : "./simkaMin_kmers.bin";
+    const int k = (int)geti(kv, "-kmer-size", 21);
+    const uint32_t s = (uint32_t)geti(kv, "-nb-kmers", 100000), seed = (uint32_t)geti(kv, "-seed", 100);
+    const uint64_t max_reads = (uint64_t)std::max(0LL, geti(kv, "-max-reads", 0));
+    if (k < 2 || k > 31) throw bank::Exception("this build supports -kmer-size 2..31");
+    SimkaSequenceFilter filter((size_t)geti(kv, "-min-read-size", 0), kv.count("-min-shannon-index") ? atof(kv["-min-shannon-index"].c_str()) : 0);
+    std::vector<SampleSpec> samples = parse_simka_input(kv["-in"]);
+    FILE *f = fopen(out.c_str(), "wb");
+    if (!f) throw bank::Exception("cannot write " + out);
+    const uint8_t k8 = (uint8_t)k;
+    const uint32_t n = (uint32_t)samples.size();
+    fwrite(&k8, 1, 1, f); fwrite(&s, 4, 1, f); fwrite(&seed, 4, 1, f); fwrite(&n, 4, 1, f);
+    std::vector<uint64_t> hashes(s);
+    std::vector<uint32_t> counts(s);
+    std::vector<Entry> rec(s);
+    std::string seqs;
+    std::vector<uint64_t> off;
+    for (const SampleSpec &sp : samples) {
+        seqs.clear();
+        off.assign(1, 0);
+        read_sample_into(sp, filter, max_reads, seqs, off, [] {});
+        const uint64_t words = simka_pack_words(seqs.size(), off.size() - 1);
+        std::vector<uint64_t> packed(words + 1);
+        std::vector<uint32_t> bad(words + 1);
+        simka_pack_reads(seqs.data(), off.data(), off.size() - 1, packed.data(), bad.data(), (int)geti(kv, "-nb-cores", 0));
+        uint32_t nsel = 0;
+        const int rc = simkamin_gpu_sketch((int)geti(kv, "-device", 0), k, s, seed, packed.data(), bad.data(), words, off.size() - 1, hashes.data(),
+                                           counts.data(), &nsel);
+        if (rc != SIMKA_OK) throw bank::Exception("simkamin_gpu_sketch failed (code " + std::to_string(rc) + "): a CUDA device is required");
+        for (uint32_t i = 0; i < s; i++) { rec[i].hash = hashes[i]; rec[i].count = counts[i]; rec[i].pad = 0; }
+        fwrite(rec.data(), sizeof(Entry), s, f);
+    }
+    for (const SampleSpec &sp : samples) {
+        const uint8_t len = (uint8_t)sp.id.size();
+        fwrite(&len, 1, 1, f);
+        fwrite(sp.id.data(), 1, len, f);
+    }
+    fclose(f);
+    return EXIT_SUCCESS;
+}
+
+void load_block(const std::string &path, const SketchHeader &h, uint32_t start, uint32_t n, uint32_t s_use, std::vector<uint64_t> &hashes,
+                std::vector<uint32_t> &counts) {
+    std::ifstream f(path.c_str(), std::ios::binary);
+    hashes.assign((size_t)n * s_use, 0);
+    counts.assign((size_t)n * s_use, 0);
+    std::vector<Entry> rec(s_use);
+    for (uint32_t i = 0; i < n; i++) {
+        f.seekg((std::streamoff)(HEADER + (uint64_t)(start + i) * h.s * sizeof(Entry)));
+        f.read((char *)rec.data(), (std::streamsize)(sizeof(Entry) * s_use));  // the first min(s1,s2) entries (SimkaMinDistance.hpp:536-552)
+        if (!f) throw bank::Exception("short read in " + path);
+        for (uint32_t q = 0; q < s_use; q++) { hashes[(size_t)i * s_use + q] = rec[q].hash; counts[(size_t)i * s_use + q] = rec[q].count; }
+    }
+}
+
+int do_distance(std::map<std::string, std::string> &kv) {
+    if (!kv.count("-in1") || !kv.count("-in2")) throw bank::Exception("Options '-in1' and '-in2' are mandatory");
+    const std::string in1 = kv["-in1"], in2 = kv["-in2"], out = kv.count("-out") ? kv["-out"] : "./simkaMin_results";
+    const SketchHeader h1 = read_header(in1), h2 = read_header(in2);
+    if (h1.k != h2.k) { std::cerr << "ERROR: can't compare both sketches because of different kmer sizes (" << (int)h1.k << " and " << (int)h2.k << ")" << std::endl; return 1; }
+    if (h1.seed != h2.seed) { std::cerr << "ERROR: can't compare both sketches because of different seeds (" << h1.seed << " and " << h2.seed << ")" << std::endl; return 1; }
+    uint32_t si = (uint32_t)geti(kv, "-start-i", 0), sj = (uint32_t)geti(kv, "-start-j", 0);
+    uint32_t ni = (uint32_t)geti(kv, "-n-i", 0), nj = (uint32_t)geti(kv, "-n-j", 0);
+    if (ni == 0) ni = h1.n;
+    if (nj == 0) nj = h2.n;
+    if (si + ni > h1.n || sj + nj > h2.n) throw bank::Exception("block outside the sketch files");
+    const uint32_t s = std::min(h1.s, h2.s);
+    stage::mkdirs(out);
+    const bool symmetric = in1 == in2 && si == sj;
+    std::vector<uint64_t> ha, hb;
+    std::vector<uint32_t> ca, cb;
+    load_block(in1, h1, si, ni, s, ha, ca);
+    std::vector<float> jac, bc;
+    int rc;
+    const int device = (int)geti(kv, "-device", 0);
+    if (symmetric) {
+        jac.assign((size_t)ni * ni, 0); bc.assign((size_t)ni * ni, 0);
+        rc = simkamin_gpu_distance(device, ha.data(), ca.data(), ni, s, jac.data(), bc.data(), nullptr);
+        nj = ni;
+    } else {
+        load_block(in2, h2, sj, nj, s, hb, cb);
+        jac.assign((size_t)ni * nj, 0); bc.assign((size_t)ni * nj, 0);
+        rc = simkamin_gpu_distance_rect(device, ha.data(), ca.data(), ni, hb.data(), cb.data(), nj, s, jac.data(), bc.data(), nullptr);
+    }
+    if (rc != SIMKA_OK) throw bank::Exception("distance kernel failed (code " + std::to_string(rc) + "): a CUDA device is required");
+    // float32 at (i * nbDatasets2 + j) * 4 (and mirrored at (j * nbDatasets1 + i) * 4 for a symmetric block), :281-303,617-628
+    for (int m = 0; m < 2; m++) {
+        const std::string path = out + (m == 0 ? "/mat_presenceAbsence_jaccard.bin" : "/mat_abundance_braycurtis.bin");
+        FILE *f = fopen(path.c_str(), "r+b");
+        if (!f) f = fopen(path.c_str(), "w+b");
+        if (!f) throw bank::Exception("cannot write " + path);
+        const std::vector<float> &v = m == 0 ? jac : bc;
+        for (uint32_t i = 0; i < ni; i++)
+            for (uint32_t j = 0; j < nj; j++) {
+                if (symmetric && j < i) continue;
+                const float d = (symmetric && i == j) ? 0.0f : v[(size_t)i * nj + j];
+                fseeko(f, (off_t)(((uint64_t)(si + i) * h2.n + (sj + j)) * 4), SEEK_SET);
+                fwrite(&d, 4, 1, f);
+                if (symmetric && j > i) {
+                    fseeko(f, (off_t)(((uint64_t)(sj + j) * h1.n + (si + i)) * 4), SEEK_SET);
+                    fwrite(&d, 4, 1, f);
+                }
+            }
+        fclose(f);
+    }
+    return EXIT_SUCCESS;
+}
+
+int do_export(std::map<std::string, std::string> &kv) {
+    if (!kv.count("-in") || !kv.count("-in1") || !kv.count("-in2")) throw bank::Exception("Options '-in', '-in1' and '-in2' are mandatory");
+    const std::string dir = kv["-in"], out = kv.count("-out") ? kv["-out"] : "./simkaMin_results";
+    const SketchHeader h1 = read_header(kv["-in1"]), h2 = read_header(kv["-in2"]);
+    const std::vector<std::string> ids1 = read_ids(kv["-in1"], h1), ids2 = read_ids(kv["-in2"], h2);
+    stage::mkdirs(out);
+    for (const char *name : {"mat_abundance_braycurtis", "mat_presenceAbsence_jaccard"}) {
+        std::ifstream f((dir + "/" + name + ".bin").c_str(), std::ios::binary);
+        if (!f) continue;
+        gzFile g = gzopen((out + "/" + name + ".csv.gz").c_str(), "wb");
+        if (!g) throw bank::Exception("cannot write " + out + "/" + name + ".csv.gz");
+        std::string line;
+        for (const std::string &id : ids2) line += ";" + id;
+        line += "\n";
+        gzwrite(g, line.data(), (unsigned)line.size());
+        std::vector<float> row(ids2.size());
+        for (size_t i = 0; i < ids1.size(); i++) {
+            f.read((char *)row.data(), (std::streamsize)(row.size() * 4));
+            line = ids1[i] + ";";
+            char buf[64];
+            for (size_t j = 0; j < ids2.size(); j++) { snprintf(buf, sizeof buf, "%f", row[j]); line += buf; line += ";"; }
+            line.erase(line.size() - 1);
+            line += "\n";
+            gzwrite(g, line.data(), (unsigned)line.size());
+        }
+        gzclose(g);
+    }
+    return EXIT_SUCCESS;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    try {
+        if (argc < 2) { std::cout << "usage: simkaMinCore sketch|distance|export [options]" << std::endl; return EXIT_FAILURE; }
+        static const char *no_param[] = {"-filter", nullptr};
+        auto kv = stage::parse_flags(argc - 1, argv + 1, no_param);
+        const std::string cmd = argv[1];
+        if (cmd == "sketch") return do_sketch(kv);
+        if (cmd == "distance") return do_distance(kv);
+        if (cmd == "export") return do_export(kv);
+        throw bank::Exception("unknown command '" + cmd + "' (sketch, distance, export)");
+    } catch (const std::exception &e) {
+        std::cout << "EXCEPTION: " << e.what() << std::endl;
+        return EXIT_FAILURE;
+    }
+}

@@ -496,3 +496,42 @@ def test_simkamin_gpu_sketch_synthetic():
             assert gn == on
             np.testing.assert_array_equal(gh, oh)
             np.testing.assert_array_equal(gc, oc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,max_reads,nb_kmers", [(21, 0, 100), (31, 100, 1000)])
+def test_simkamincore_cli_reproduces_reference_truth(tmp_path, golden_dir, k, max_reads, nb_kmers):
+    """the reference's SimkaMin test (tests/simkaMin/test_simkaMin.py:141-154) against the `simkaMinCore` binary of this
+    build, driven as simkaMin.py drives it (sketch, distance, export: simkaMin/simkaMin.py:101-197): the csv files are
+    byte-identical to the truth; then the same matrix computed in rectangular -start-i/-start-j blocks."""
+    import gzip
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    exe = os.path.join(os.path.dirname(str(SIMKA_BIN)), "simkaMinCore")
+    sk = str(tmp_path / "sketch.bin")
+    r = subprocess.run([exe, "sketch", "-in", os.path.join(golden_dir, "example", "simka_input.txt"), "-out", sk, "-seed", "100", "-kmer-size", str(k),
+                        "-nb-kmers", str(nb_kmers), "-max-reads", str(max_reads), "-min-read-size", "0", "-min-shannon-index", "0",
+                        "-nb-cores", "0", "-max-memory", "8000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.path.getsize(sk) == 13 + 5 * nb_kmers * 16 + sum(1 + len(i) for i in "ABCDE")
+    dist = str(tmp_path / "distance")
+    r = subprocess.run([exe, "distance", "-in1", sk, "-in2", sk, "-out", dist, "-nb-cores", "0", "-start-i", "0", "-start-j", "0", "-n-i", "5", "-n-j", "5"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe, "export", "-in", dist, "-in1", sk, "-in2", sk, "-out", str(tmp_path / "res"), "-nb-cores", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    tdir = os.path.join(golden_dir, "truth_simkaMin", f"k{k}__{max_reads}-{nb_kmers}_n1")
+    for f in ("mat_presenceAbsence_jaccard", "mat_abundance_braycurtis"):
+        assert gzip.open(tmp_path / "res" / (f + ".csv.gz"), "rt").read() == open(os.path.join(tdir, f + ".csv")).read(), f
+    # blocks of 2 + 3 datasets as simkaMin.py would issue them with MAX_DATASETS_PROCESS = 2..3: (0,0) (0,1) (1,1)
+    dist2 = str(tmp_path / "distance_blocks")
+    for si, sj, ni, nj in ((0, 0, 2, 2), (0, 2, 2, 3), (2, 2, 3, 3)):
+        r = subprocess.run([exe, "distance", "-in1", sk, "-in2", sk, "-out", dist2, "-start-i", str(si), "-start-j", str(sj), "-n-i", str(ni), "-n-j", str(nj)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    for f in ("mat_presenceAbsence_jaccard.bin", "mat_abundance_braycurtis.bin"):
+        whole = np.fromfile(os.path.join(dist, f), dtype=np.float32).reshape(5, 5)
+        blocks = np.fromfile(os.path.join(dist2, f), dtype=np.float32).reshape(5, 5)
+        np.testing.assert_array_equal(np.triu(blocks), np.triu(whole))  # the reference does not mirror rectangular blocks
+        np.testing.assert_array_equal(blocks[2:, 2:], whole[2:, 2:])
+        np.testing.assert_array_equal(blocks[:2, :2], whole[:2, :2])

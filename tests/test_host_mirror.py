@@ -150,3 +150,57 @@ def test_stage_binaries_argument_handling(tmp_path):
     assert r.returncode == 1 and len(marker.read_text().split()) == 5
     r = subprocess.run([os.path.join(bindir, "simkaCountProcess"), "true"])
     assert r.returncode == 0
+
+
+def _write_sketch_file(path, k, s, seed, ids, hashes, counts):
+    """the reference's sketch file (SimkaMinCommons.hpp:28,42-55,80-93): 13-byte header, n x s 16-byte entries, ids"""
+    import struct
+    with open(path, "wb") as f:
+        f.write(struct.pack("<B", k) + struct.pack("<III", s, seed, len(ids)))
+        rec = np.zeros((len(ids), s), dtype=[("h", "<u8"), ("c", "<u4"), ("p", "<u4")])
+        rec["h"], rec["c"] = hashes, counts
+        f.write(rec.tobytes())
+        for i in ids:
+            f.write(bytes([len(i)]) + i.encode())
+
+
+def test_simkamincore_argument_handling_and_export(tmp_path):
+    """simkaMinCore: error conventions of the reference's main (src/simkaMin/SimkaMin.cpp:30-110), `distance` refuses
+    sketches of different k or seed before any device work (SimkaMinDistance.hpp:990-998), `export` turns the float32
+    .bin matrices into csv.gz exactly as writeMatrixASCII (SimkaMinDistanceMatrixExporter.hpp:384-404)"""
+    import gzip
+    exe = os.path.join(os.path.dirname(str(SIMKA_BIN)), "simkaMinCore")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "sketch" in r.stdout
+    r = subprocess.run([exe, "bogus"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("EXCEPTION: ")
+    r = subprocess.run([exe, "sketch", "-out", str(tmp_path / "s.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "mandatory" in r.stdout
+    r = subprocess.run([exe, "sketch", "-in", "x", "-filter"], capture_output=True, text=True)
+    assert r.returncode == 1 and "-filter" in r.stdout
+    rng = np.random.default_rng(3)
+    ids = ["A", "B2", "sample_C"]
+    h = np.sort(rng.integers(1, 2**63, (3, 8), dtype=np.uint64), axis=1)
+    c = rng.integers(1, 9, (3, 8), dtype=np.uint32)
+    _write_sketch_file(tmp_path / "a.bin", 21, 8, 100, ids, h, c)
+    _write_sketch_file(tmp_path / "b.bin", 31, 8, 100, ids, h, c)
+    _write_sketch_file(tmp_path / "c.bin", 21, 8, 7, ids, h, c)
+    r = subprocess.run([exe, "distance", "-in1", str(tmp_path / "a.bin"), "-in2", str(tmp_path / "b.bin"), "-out", str(tmp_path / "d")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "different kmer sizes" in r.stderr
+    r = subprocess.run([exe, "distance", "-in1", str(tmp_path / "a.bin"), "-in2", str(tmp_path / "c.bin"), "-out", str(tmp_path / "d")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "different seeds" in r.stderr
+    # export
+    d = tmp_path / "dist"
+    d.mkdir()
+    m = rng.random((3, 3)).astype(np.float32)
+    m.tofile(d / "mat_presenceAbsence_jaccard.bin")
+    (1 - m).astype(np.float32).tofile(d / "mat_abundance_braycurtis.bin")
+    r = subprocess.run([exe, "export", "-in", str(d), "-in1", str(tmp_path / "a.bin"), "-in2", str(tmp_path / "a.bin"), "-out", str(tmp_path / "res")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    want = ";" + ";".join(ids) + "\n" + "".join(ids[i] + ";" + ";".join("%f" % float(v) for v in m[i]) + "\n" for i in range(3))
+    assert gzip.open(tmp_path / "res" / "mat_presenceAbsence_jaccard.csv.gz", "rt").read() == want
+    assert (tmp_path / "res" / "mat_abundance_braycurtis.csv.gz").exists()

@@ -146,3 +146,18 @@ def test_murmur3_known_answer():
     b = L.orc_murmur3_x64_128_u64(1, 100)
     c = L.orc_murmur3_x64_128_u64(0, 101)
     assert len({a, b, c}) == 3
+
+
+def test_murmur3_against_the_reference_source():
+    """the oracle's MurmurHash3 restatement == the reference's own MurmurHash3.cpp (compiled unmodified into oracle/_ref by
+    oracle/build_ref.sh) on edge keys and 20000 random 64-bit keys, for the default seed and two others"""
+    import numpy as np
+    if oracle.build_ref() is None:
+        pytest.skip("oracle/_ref/libmurmur_ref.so not built (no /root/reference here and no prebuilt file)")
+    rng = np.random.default_rng(5)
+    keys = np.concatenate([np.array([0, 1, 2**62 - 1, 2**63, 2**64 - 1], dtype=np.uint64), rng.integers(0, 2**64, 20000, dtype=np.uint64)])
+    L = oracle.lib()
+    for seed in (100, 0, 4294967295):
+        ref = oracle.ref_murmur3_x64_128_u64(keys, seed)
+        got = np.array([L.orc_murmur3_x64_128_u64(int(x), seed) for x in keys], dtype=np.uint64)
+        np.testing.assert_array_equal(got, ref)
