@@ -281,6 +281,8 @@ struct MSSmem {
     alignas(16) uint64_t tk[MS_SLOTS];
     alignas(16) double2 logtab[128];
     alignas(16) unsigned long long scan_tmp[MS_THREADS / 32 + 1];
+    alignas(16) double ntot[MS_MAXN];      // N_i of the local sample slots
+    alignas(16) double ninv30[MS_MAXN];    // 2^30 / N_i: the product of two of them scales a Jensen-Shannon term to 2^-60 units
     alignas(16) uint32_t gcnt[MS_SLOTS];   // cleaned with 128-bit stores
     uint32_t cg[MS_GCAP];
     uint32_t cgp[MS_GCAP + 1];
@@ -341,7 +343,11 @@ k_merge_sm(MergeArgs a) {
         if (tid < MS_MAXN) {  // local sample slot -> global sample id (-1: unused)
             int gs = tid;
             if (TILED) gs = tid < 32 ? (int)(32 * I) + tid : (diag ? -1 : (int)(32 * J) + tid - 32);
-            S.s_gid[tid] = (gs >= 0 && gs < N) ? gs : -1;
+            const bool used = gs >= 0 && gs < N;
+            S.s_gid[tid] = used ? gs : -1;
+            const double nt = used ? a.ntot[gs] : 0.0;
+            S.ntot[tid] = nt;
+            S.ninv30[tid] = nt > 0.0 ? 1073741824.0 / nt : 0.0;
         }
         __syncthreads();
 
@@ -510,14 +516,15 @@ k_merge_sm(MergeArgs a) {
                                     ms_add64(acc_lo + 5 * NPk, acc_hi + 5 * NPk, key, hellinger_term(prod));  // u64 += double truncates per increment
                                 }
                                 if (COMPLEX) {
-                                    const double ai = (double)ci, aj = (double)cj, Ni = a.ntot[S.s_gid[si]], Nj = a.ntot[S.s_gid[sj]];
+                                    const double ai = (double)ci, aj = (double)cj, Ni = S.ntot[si], Nj = S.ntot[sj];
                                     const double yX = aj * Ni, xY = ai * Nj;
                                     if (xY != yX) {  // equal: both logs are log(1) = 0 exactly
                                         const double r1 = (2 * xY) * __drcp_rn(xY + yX);
-                                        // the term d1 + d2 >= 0 (Jensen), |term| < 2: exact integer accumulation in units of 2^-60
-                                        // (rounding 4e-19 per term, order-independent => bit-reproducible sums)
-                                        const double term = (ai / Ni) * tab_log(r1, S.logtab) + (aj / Nj) * tab_log(2.0 - r1, S.logtab);
-                                        ms_add64(acc_lo + 7 * NPk, acc_hi + 7 * NPk, key, (ull)__double2ll_rn(ldexp(term, 60)));
+                                        // d1 + d2 = (c_i/N_i) log r1 + (c_j/N_j) log r2 = (xY log r1 + yX log r2) / (N_i N_j): no division per
+                                        // pair, the reciprocals are per sample.  The term is >= 0 (Jensen) and < 2: exact integer accumulation
+                                        // in units of 2^-60 (rounding 4e-19 per term, order-independent => bit-reproducible sums)
+                                        const double num = fma(xY, tab_log(r1, S.logtab), yX * tab_log(2.0 - r1, S.logtab));
+                                        ms_add64(acc_lo + 7 * NPk, acc_hi + 7 * NPk, key, (ull)__double2ll_rn(num * (S.ninv30[si] * S.ninv30[sj])));
                                     }
                                     const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
                                     // accumulated negated (the both-present value minus the two one-sided values is <= 0 in practice)
