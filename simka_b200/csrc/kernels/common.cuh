@@ -9,9 +9,15 @@ constexpr int L1_TILE = BLOCK * L1_KPT;      // 8192 keys
 constexpr int L2_KPT = 16;
 constexpr int L2_TILE = BLOCK * L2_KPT;      // 4096 keys
 constexpr int MAX_B = 1024;                  // max buckets per partition level
-constexpr int BIN_TARGET = 768;              // fine bins hold BIN_TARGET..2*BIN_TARGET keys on average
-constexpr int CNT_SLOTS = 2048;              // K3 hash table slots
-constexpr int CNT_MAXDISTINCT = 1536;        // distinct keys one table pass may hold (load 0.75)
+#ifndef SIMKA_BIN_TARGET
+#define SIMKA_BIN_TARGET 768
+#endif
+#ifndef SIMKA_CNT_SLOTS
+#define SIMKA_CNT_SLOTS 2048
+#endif
+constexpr int BIN_TARGET = SIMKA_BIN_TARGET;              // fine bins hold BIN_TARGET..2*BIN_TARGET keys on average
+constexpr int CNT_SLOTS = SIMKA_CNT_SLOTS;    // K3 hash table slots
+constexpr int CNT_MAXDISTINCT = CNT_SLOTS * 3 / 4;  // distinct keys one table pass may hold (load 0.75)
 constexpr int CHIST = 1024;                  // dense abundance histogram bins (complex distances)
 constexpr int MRG_SLOTS = 2048;              // merge hash table slots
 constexpr int MRG_CAP = 2048;                // merge: grouped entries held in shared memory

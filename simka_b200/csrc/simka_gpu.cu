@@ -153,6 +153,7 @@ struct simka_ctx {
     uint64_t launches = 0;
     int nsm = 148;
     int occ_bin_count = 0;
+    int b1_override = 0;  // SIMKA_B200_B1BITS: level-1 bucket bits (experiments)
 
     void set_error(const std::string &s) { err = s; }
 };
@@ -264,6 +265,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
     }
     { const char *e = getenv("SIMKA_B200_EXACT_COUNT"); ctx->force_exact = e && e[0] == '1'; }
     { const char *e = getenv("SIMKA_B200_K1"); ctx->use_k16 = !(e && !strcmp(e, "256")); }
+    { const char *e = getenv("SIMKA_B200_B1BITS"); ctx->b1_override = e ? atoi(e) : 0; }
     cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
     ctx->samples.resize(p->nb_samples);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -450,7 +452,11 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
     int bin_bits = std::max(ilog2_floor(std::max<uint64_t>(1, n_pos / BIN_TARGET)), ctx->fg_bits);
     bin_bits = std::min(bin_bits, std::min(W, 20));
     bin_bits = std::max(bin_bits, ctx->fg_bits);
-    const int b1_bits = std::min(bin_bits, bin_bits > 16 ? 10 : 8);
+    // level-1 buckets: 256 for up to 2^17 bins (measured on config 2: K1 18.7 ms with 256 buckets against 23.0 ms with 1024 -- longer
+    // contiguous runs per bucket and a shorter in-kernel scan -- while K2 loses 1.9 ms on its 512 sub-bins), more only as far as
+    // the level-2 fan-out (<= 1024) requires
+    int b1_bits = std::min(bin_bits, std::min(std::max(bin_bits - 9, 8), 10));
+    if (ctx->b1_override > 0) b1_bits = std::min(bin_bits, std::max(ctx->b1_override, bin_bits - 10));
     const int b2_bits = bin_bits - b1_bits;
     if (b2_bits > 10) { ctx->set_error("sample too large for the bin geometry"); return SIMKA_ERR_INVALID; }
     const uint32_t nb1 = 1u << b1_bits, nbins = 1u << bin_bits;
@@ -534,7 +540,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             if (ctx->occ_bin_count <= 0) ctx->occ_bin_count = 1;
         }
         const unsigned gbin = (unsigned)std::min<uint64_t>(nbins, (uint64_t)ctx->nsm * ctx->occ_bin_count);
-        const int slot_shift = std::max(0, W - bin_bits - 11);
+        const int slot_shift = std::max(0, W - bin_bits - ilog2_floor(CNT_SLOTS));  // table slot: the bits just below the bin bits
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
         k_bin_count<<<gbin, BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins, slot_shift, ctx->prm.abundance_min,
                                             ctx->prm.abundance_max, co);
