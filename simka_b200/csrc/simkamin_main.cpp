@@ -1,6 +1,7 @@
-// simkamin_main.cpp -- `simkaMinCore sketch | distance | export` with the reference's command lines and file formats
-// (src/simkaMin/SimkaMin.cpp:30-110; sketch: SimkaMinCount.hpp:1347-1381,713-1127; distance: SimkaMinDistance.hpp:414-640,
-//  955-998; export: SimkaMinDistanceMatrixExporter.hpp:330-404), so that the reference's simkaMin.py wrapper can drive it.
+// simkamin_main.cpp -- `simkaMinCore sketch | distance | export | append | info` with the reference's command lines and file
+// formats (src/simkaMin/SimkaMin.cpp:30-110; sketch: SimkaMinCount.hpp:1347-1381,713-1127; distance: SimkaMinDistance.hpp:414-640,
+//  955-998; export: SimkaMinDistanceMatrixExporter.hpp:330-404; append: SimkaMinAppend.hpp:60-160; info: SimkaMinInfos.hpp:58-100),
+// so that the reference's simkaMin.py / simkaMin_update.py wrappers can drive it.
 //   sketch file:  u8 kmerSize, u32 sketchSize, u32 seed, u32 nbDatasets (13 bytes, SimkaMinCommons.hpp:28), then per dataset
 //                 sketchSize x {u64 hash, u32 count, 4 pad} ascending (zero padding first), then the ids as u8 length + bytes
 //   distance:     mat_presenceAbsence_jaccard.bin / mat_abundance_braycurtis.bin, float32 at (i * nbDatasets2 + j) * 4
@@ -194,18 +195,76 @@ int do_export(std::map<std::string, std::string> &kv) {
     return EXIT_SUCCESS;
 }
 
+// append: the sketches of -in2 are added to -in1 in place (same k, sketch size and seed required): header count updated,
+// sketches of -in2 written where the ids of -in1 began, then the ids of -in1 and of -in2
+int do_append(std::map<std::string, std::string> &kv) {
+    if (!kv.count("-in1") || !kv.count("-in2")) throw bank::Exception("Options '-in1' and '-in2' are mandatory");
+    const std::string in1 = kv["-in1"], in2 = kv["-in2"];
+    for (const std::string &f : {in1, in2}) {
+        struct stat sb;
+        if (stat(f.c_str(), &sb) != 0) { std::cerr << "Error: input does not exist (" << f << ")" << std::endl; return 1; }
+    }
+    const SketchHeader h1 = read_header(in1), h2 = read_header(in2);
+    if (h1.k != h2.k) { std::cerr << "Error: can't merge sketches with different kmer sizes (" << (int)h1.k << " vs " << (int)h2.k << ")" << std::endl; return 1; }
+    if (h1.s != h2.s) { std::cerr << "Error: can't merge sketches with different sketch sizes (" << h1.s << " vs " << h2.s << ")" << std::endl; return 1; }
+    if (h1.seed != h2.seed) { std::cerr << "Error: can't merge sketches with different seeds (" << h1.seed << " vs " << h2.seed << ")" << std::endl; return 1; }
+    const std::vector<std::string> ids1 = read_ids(in1, h1), ids2 = read_ids(in2, h2);
+    FILE *out = fopen(in1.c_str(), "r+b");
+    FILE *src = fopen(in2.c_str(), "rb");
+    if (!out || !src) throw bank::Exception("cannot open the sketch files");
+    const uint32_t n = h1.n + h2.n;
+    fseeko(out, 9, SEEK_SET);  // u8 k, u32 sketch size, u32 seed, then the dataset count
+    fwrite(&n, 4, 1, out);
+    fseeko(out, (off_t)(HEADER + (uint64_t)h1.n * h1.s * sizeof(Entry)), SEEK_SET);
+    fseeko(src, (off_t)HEADER, SEEK_SET);
+    std::vector<char> buf(1 << 20);
+    for (uint64_t left = (uint64_t)h2.n * h2.s * sizeof(Entry); left > 0;) {
+        const size_t want = (size_t)std::min<uint64_t>(left, buf.size());
+        if (fread(buf.data(), 1, want, src) != want) throw bank::Exception("short read in " + in2);
+        fwrite(buf.data(), 1, want, out);
+        left -= want;
+    }
+    for (const std::vector<std::string> *ids : {&ids1, &ids2})
+        for (const std::string &id : *ids) {
+            const uint8_t len = (uint8_t)id.size();
+            fwrite(&len, 1, 1, out);
+            fwrite(id.data(), 1, len, out);
+        }
+    fclose(src);
+    fclose(out);
+    return EXIT_SUCCESS;
+}
+
+int do_info(std::map<std::string, std::string> &kv) {
+    if (!kv.count("-in")) throw bank::Exception("Option '-in' is mandatory");
+    const std::string in = kv["-in"];
+    struct stat sb;
+    if (stat(in.c_str(), &sb) != 0) { std::cerr << "Error: input does not exist (" << in << ")" << std::endl; return 1; }
+    const SketchHeader h = read_header(in);
+    std::cout << "Sketch info: " << in << "\n\n"
+              << "k-mer size  : " << (uint32_t)h.k << "\n"
+              << "Sketch size : " << h.s << "\n"
+              << "Seed        : " << h.seed << "\n\n"
+              << "Nb Datasets: " << h.n << "\n";
+    for (const std::string &id : read_ids(in, h)) std::cout << id << "\n";
+    std::cout << std::endl;
+    return EXIT_SUCCESS;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
     try {
-        if (argc < 2) { std::cout << "usage: simkaMinCore sketch|distance|export [options]" << std::endl; return EXIT_FAILURE; }
+        if (argc < 2) { std::cout << "usage: simkaMinCore sketch|distance|export|append|info [options]" << std::endl; return EXIT_FAILURE; }
         static const char *no_param[] = {"-filter", nullptr};
         auto kv = stage::parse_flags(argc - 1, argv + 1, no_param);
         const std::string cmd = argv[1];
         if (cmd == "sketch") return do_sketch(kv);
         if (cmd == "distance") return do_distance(kv);
         if (cmd == "export") return do_export(kv);
-        throw bank::Exception("unknown command '" + cmd + "' (sketch, distance, export)");
+        if (cmd == "append") return do_append(kv);
+        if (cmd == "info") return do_info(kv);
+        throw bank::Exception("unknown command '" + cmd + "' (sketch, distance, export, append, info)");
     } catch (const std::exception &e) {
         std::cout << "EXCEPTION: " << e.what() << std::endl;
         return EXIT_FAILURE;

@@ -204,3 +204,32 @@ def test_simkamincore_argument_handling_and_export(tmp_path):
     want = ";" + ";".join(ids) + "\n" + "".join(ids[i] + ";" + ";".join("%f" % float(v) for v in m[i]) + "\n" for i in range(3))
     assert gzip.open(tmp_path / "res" / "mat_presenceAbsence_jaccard.csv.gz", "rt").read() == want
     assert (tmp_path / "res" / "mat_abundance_braycurtis.csv.gz").exists()
+
+
+def test_simkamincore_append_and_info(tmp_path):
+    """append (src/simkaMin/SimkaMinAppend.hpp:60-160): -in2 is appended to -in1 in place, header count updated, ids of both
+    files at the end; refuses different k / sketch size / seed.  info (SimkaMinInfos.hpp:58-100) lists header + ids."""
+    exe = os.path.join(os.path.dirname(str(SIMKA_BIN)), "simkaMinCore")
+    rng = np.random.default_rng(11)
+    def sk(n, s=6):
+        return np.sort(rng.integers(1, 2**63, (n, s), dtype=np.uint64), axis=1), rng.integers(1, 9, (n, s), dtype=np.uint32)
+    h1, c1 = sk(2)
+    h2, c2 = sk(3)
+    a, b, want = tmp_path / "a.bin", tmp_path / "b.bin", tmp_path / "want.bin"
+    _write_sketch_file(a, 21, 6, 100, ["A", "Bb"], h1, c1)
+    _write_sketch_file(b, 21, 6, 100, ["C", "", "Eee"], h2, c2)
+    _write_sketch_file(want, 21, 6, 100, ["A", "Bb", "C", "", "Eee"], np.concatenate([h1, h2]), np.concatenate([c1, c2]))
+    r = subprocess.run([exe, "append", "-in1", str(a), "-in2", str(b)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert a.read_bytes() == want.read_bytes()
+    r = subprocess.run([exe, "info", "-in", str(a)], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert r.stdout == f"Sketch info: {a}\n\nk-mer size  : 21\nSketch size : 6\nSeed        : 100\n\nNb Datasets: 5\nA\nBb\nC\n\nEee\n\n"
+    for k, s, seed, msg in ((31, 6, 100, "kmer sizes"), (21, 7, 100, "sketch sizes"), (21, 6, 5, "seeds")):
+        hh, cc = sk(1, s)
+        _write_sketch_file(tmp_path / "c.bin", k, s, seed, ["X"], hh, cc)
+        r = subprocess.run([exe, "append", "-in1", str(a), "-in2", str(tmp_path / "c.bin")], capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr
+    assert a.read_bytes() == want.read_bytes()
+    r = subprocess.run([exe, "info", "-in", str(tmp_path / "missing.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "does not exist" in r.stderr
