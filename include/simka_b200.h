@@ -212,6 +212,12 @@ int simka_write_matrices(const simka_stats_view *stats, const char *const *ids, 
  * until the sketch is complete (the reference tests `hash < top`). */
 int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
                         uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected);
+/* the same with the reference's -filter option (processFiltered, src/simkaMin/SimkaMinCount.hpp:341-380): only k-mers seen at
+ * least twice are sketched, counts start at 2 on the second occurrence.  The reference remembers first occurrences in a Bloom
+ * filter (BloomCacheCoherent of max-memory * 8 / cores bits, 7 hashes, :1155-1161); this entry counts exactly, i.e. it is
+ * identical to the reference wherever that filter gives no false positive (it reproduces the reference's 8 -filter truth sets). */
+int simkamin_gpu_sketch_filter(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
+                        uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected);
 
 /* ---- SimkaMin: replaces ComputeDistanceManager::computeDistance_unsynch over all pairs ------------
  * (src/simkaMin/SimkaMinDistance.hpp:190-303).  hashes/counts: n sketches of s entries, ascending,

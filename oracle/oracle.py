@@ -100,8 +100,9 @@ def lib() -> C.CDLL:
                                             C.POINTER(C.c_float), C.c_int]
         L.orc_murmur3_x64_128_u64.restype = C.c_uint64
         L.orc_murmur3_x64_128_u64.argtypes = [C.c_uint64, C.c_uint32]
-        L.orc_simkamin_sketch.restype = C.c_uint32
-        L.orc_simkamin_sketch.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, u64p, u32p]
+        for f in (L.orc_simkamin_sketch, L.orc_simkamin_sketch_filtered):
+            f.restype = C.c_uint32
+            f.argtypes = [C.c_void_p, u64p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, u64p, u32p]
         L.orc_read_fastx.restype = C.c_int64
         L.orc_read_fastx.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), u64p, u64p,
                                      C.POINTER(C.c_void_p), u64p, u64p]
@@ -260,8 +261,8 @@ class Run:
             pass
 
 
-def simkamin_sketch(seqs: np.ndarray, read_off: np.ndarray, k: int, sketch_size: int, seed: int = 100):
-    """-> (hashes uint64[s] ascending with zero padding at the front, counts uint32[s], n_selected)"""
+def simkamin_sketch(seqs: np.ndarray, read_off: np.ndarray, k: int, sketch_size: int, seed: int = 100, filter: bool = False):
+    """-> (hashes uint64[s] ascending with zero padding at the front, counts uint32[s], n_selected); filter = the -filter option"""
     L = lib()
     seqs = np.ascontiguousarray(seqs, np.uint8)
     read_off = np.ascontiguousarray(read_off, np.uint64)
@@ -269,8 +270,8 @@ def simkamin_sketch(seqs: np.ndarray, read_off: np.ndarray, k: int, sketch_size:
         seqs = np.zeros(1, np.uint8)
     h = np.zeros(sketch_size, np.uint64)
     c = np.zeros(sketch_size, np.uint32)
-    n = L.orc_simkamin_sketch(seqs.ctypes.data_as(C.c_void_p), _p(read_off, C.c_uint64), len(read_off) - 1, k, sketch_size, seed,
-                              _p(h, C.c_uint64), _p(c, C.c_uint32))
+    fn = L.orc_simkamin_sketch_filtered if filter else L.orc_simkamin_sketch
+    n = fn(seqs.ctypes.data_as(C.c_void_p), _p(read_off, C.c_uint64), len(read_off) - 1, k, sketch_size, seed, _p(h, C.c_uint64), _p(c, C.c_uint32))
     return h, c, int(n)
 
 

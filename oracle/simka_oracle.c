@@ -874,6 +874,63 @@ uint32_t orc_simkamin_sketch(const char *seqs, const uint64_t *read_off, uint64_
     return n_sel;
 }
 
+/* The `-filter` variant: processFiltered (src/simkaMin/SimkaMinCount.hpp:341-380).  A k-mer that passes the heap test
+ * (heap not full, or hash < top) is first remembered in a Bloom filter; from its second passing occurrence on it lives in
+ * the heap / map with a count that starts at 2.  The reference's filter is a BloomCacheCoherent of max-memory * 8 / cores
+ * bits with 7 hash functions (:1155-1161): 6.4e10 bits at the wrapper's default memory, where a false positive is
+ * out of reach for any input that fits a machine, so this restatement remembers the k-mers EXACTLY (a set of hashes; the
+ * 64-bit MurmurHash3 value stands for the k-mer, as it does in the reference's own count map).  It diverges from the
+ * reference only where the reference's Bloom filter would have answered a false positive (memory-starved runs). */
+uint32_t orc_simkamin_sketch_filtered(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int k, uint32_t sketch_size,
+                                      uint32_t seed, uint64_t *hashes_out, uint32_t *counts_out) {
+    u64map m, seen;
+    m.cap = 16; while (m.cap < (size_t)sketch_size * 4 + 16) m.cap <<= 1;
+    m.key = calloc(m.cap, 8); m.val = calloc(m.cap, 4); m.used = calloc(m.cap, 1); m.n = 0;
+    seen.cap = 1024; seen.key = calloc(seen.cap, 8); seen.val = calloc(seen.cap, 4); seen.used = calloc(seen.cap, 1); seen.n = 0;
+    uint64_t *heap = malloc(((size_t)sketch_size + 1) * 8);
+    size_t hn = 0;
+    uint64_t *canon = NULL; uint8_t *valid = NULL; size_t cap = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const size_t len = (size_t)(read_off[r + 1] - read_off[r]);
+        if (len < (size_t)k) continue;
+        if (len > cap) { cap = len * 2; canon = realloc(canon, cap * 8); valid = realloc(valid, cap); }
+        const size_t nk = orc_canonical_kmers(seqs + read_off[r], len, k, canon, valid);
+        for (size_t i = 0; i < nk; i++) {
+            if (!valid[i]) continue;
+            const uint64_t h = orc_murmur3_x64_128_u64(canon[i], seed);
+            const int full = hn >= sketch_size;
+            if (full && !(h < heap[0])) continue;               /* :362 */
+            if (map_find(&seen, h) >= 0) {                       /* _bloomFilter->contains(kmer) :344,363 */
+                long f = map_find(&m, h);
+                if (f >= 0) m.val[f] += 1;
+                else {
+                    if (full) { map_erase(&m, heap[0]); sk_heap_pop(heap, &hn); }
+                    sk_heap_push(heap, &hn, h);
+                    map_put(&m, h, 2);
+                }
+            } else {                                             /* _bloomFilter->insert(kmer) :355,376 */
+                if ((seen.n + 1) * 2 > seen.cap) {               /* grow the exact set */
+                    u64map g; g.cap = seen.cap * 2; g.key = calloc(g.cap, 8); g.val = calloc(g.cap, 4); g.used = calloc(g.cap, 1); g.n = 0;
+                    for (size_t q = 0; q < seen.cap; q++) if (seen.used[q]) map_put(&g, seen.key[q], 0);
+                    free(seen.key); free(seen.val); free(seen.used);
+                    seen = g;
+                }
+                map_put(&seen, h, 0);
+            }
+        }
+    }
+    const uint32_t n_sel = (uint32_t)hn;
+    for (uint32_t i = 0; i < sketch_size; i++) { hashes_out[i] = 0; counts_out[i] = 0; }
+    for (size_t i = 0; i < n_sel; i++) {
+        const uint64_t h = heap[0];
+        hashes_out[sketch_size - 1 - i] = h;
+        counts_out[sketch_size - 1 - i] = m.val[map_find(&m, h)];
+        sk_heap_pop(heap, &hn);
+    }
+    free(heap); free(m.key); free(m.val); free(m.used); free(seen.key); free(seen.val); free(seen.used); free(canon); free(valid);
+    return n_sel;
+}
+
 /* ------------------------------------------------------------------------------------------
  * FASTA / FASTQ (.gz) reader: GC/bank/impl/BankFasta.cpp:485-572 (kseq-style)
  * ---------------------------------------------------------------------------------------- */

@@ -100,6 +100,8 @@ void orc_matrix_from_accumulators(const orc_accumulators *a, int m, float *out);
 uint64_t orc_murmur3_x64_128_u64(uint64_t key, uint32_t seed);
 uint32_t orc_simkamin_sketch(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int k, uint32_t sketch_size,
                              uint32_t seed, uint64_t *hashes_out, uint32_t *counts_out);
+uint32_t orc_simkamin_sketch_filtered(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int k, uint32_t sketch_size,
+                             uint32_t seed, uint64_t *hashes_out, uint32_t *counts_out);
 void orc_simkamin_distance(const uint64_t *hashes, const uint32_t *counts, int n, uint32_t s,
                            float *jaccard, float *braycurtis, int nthreads);
 

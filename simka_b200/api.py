@@ -313,16 +313,17 @@ def run_samples(samples, kmer_size: int, abundance_min: int = 2, abundance_max: 
     return st
 
 
-def simkamin_sketch(seqs: np.ndarray, read_off: np.ndarray, kmer_size: int, sketch_size: int, seed: int = 100, device: int = 0):
-    """SimkaMin sketch of one sample on the GPU (src/simkaMin/SimkaMinCount.hpp:217-338).
+def simkamin_sketch(seqs: np.ndarray, read_off: np.ndarray, kmer_size: int, sketch_size: int, seed: int = 100, device: int = 0, filter: bool = False):
+    """SimkaMin sketch of one sample on the GPU (src/simkaMin/SimkaMinCount.hpp:217-338; filter=True: the -filter option, :341-380).
     -> (hashes uint64[s] ascending, zero padding at the front; counts uint32[s]; n_selected)"""
     L = _lib.load()
     packed, bad, nw = pack_reads(seqs, read_off)
     h = np.zeros(sketch_size, np.uint64)
     c = np.zeros(sketch_size, np.uint32)
     n = C.c_uint32(0)
-    rc = L.simkamin_gpu_sketch(device, kmer_size, sketch_size, seed, _vp(packed), _vp(bad), nw, len(read_off) - 1,
-                               h.ctypes.data_as(_lib.u64p), c.ctypes.data_as(_lib.u32p), C.byref(n))
+    fn = L.simkamin_gpu_sketch_filter if filter else L.simkamin_gpu_sketch
+    rc = fn(device, kmer_size, sketch_size, seed, _vp(packed), _vp(bad), nw, len(read_off) - 1,
+            h.ctypes.data_as(_lib.u64p), c.ctypes.data_as(_lib.u32p), C.byref(n))
     if rc != 0:
         raise SimkaError(f"simkamin_gpu_sketch: {ERRORS.get(rc, rc)}")
     return h, c, int(n.value)

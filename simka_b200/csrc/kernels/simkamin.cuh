@@ -174,14 +174,19 @@ __global__ void k_sketch_starts(const uint64_t *__restrict__ hashes, uint32_t n,
 // SimkaMin sketch, second look at the reads (the multiset count itself runs through stage 1 with
 // key = MurmurHash3): the reference counts occurrences of the LARGEST selected hash only until the sketch is
 // complete (processUnfiltered tests `hash < top`, src/simkaMin/SimkaMinCount.hpp:324), so its count depends on the
-// processing order.  MODE 0: first occurrence position of every sketch member (the sketch is complete at the largest
-// of them).  MODE 1: occurrences of the largest member at positions <= t_star.
+// processing order.
+//   MODE 0: first occurrence position of every sketch member (without -filter the sketch is complete at the largest
+//           of them).
+//   MODE 2: second occurrence position of every member, given the first ones (-filter: a k-mer enters the heap at its
+//           second occurrence, processFiltered :341-380, so the sketch is complete at the largest second position).
+//   MODE 1: occurrences of the largest member at positions t_from <= pos <= t_star.
 // Thread = one packed word = 32 k-mer start positions, same roll as k_extract.
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(BLOCK)
 k_sketch_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t n_words, int k, uint32_t seed,
-              const uint64_t *__restrict__ sketch, uint32_t n_sel, ull *__restrict__ first_pos, ull t_star, ull *__restrict__ count_out) {
+              const uint64_t *__restrict__ sketch, uint32_t n_sel, ull *__restrict__ first_pos, ull *__restrict__ second_pos, ull t_from,
+              ull t_star, ull *__restrict__ count_out) {
     const uint64_t t = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (t >= n_words || n_sel == 0) return;
     uint64_t hi = seq[t], lo = seq[t + 1];
@@ -204,17 +209,19 @@ k_sketch_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad
         if ((okmask >> (31 - j)) & 1u) {
             const uint64_t h = simka::murmur3_x64_128_u64(fwd < rev ? fwd : rev, seed);
             const ull pos = (ull)t * 32 + j;
-            if (MODE == 0) {
+            if (MODE == 0 || MODE == 2) {
                 if (h <= top) {
                     uint32_t a = 0, b = n_sel;  // lower bound
                     while (a < b) { const uint32_t mid = (a + b) >> 1; if (sketch[mid] < h) a = mid + 1; else b = mid; }
-                    if (a < n_sel && sketch[a] == h) atomicMin(&first_pos[a], pos);
+                    if (a < n_sel && sketch[a] == h) {
+                        if (MODE == 0) atomicMin(&first_pos[a], pos);
+                        else if (pos != first_pos[a]) atomicMin(&second_pos[a], pos);
+                    }
                 }
-            } else if (h == top && pos <= t_star) local++;
+            } else if (h == top && pos >= t_from && pos <= t_star) local++;
         }
         hi = (hi << 2) | (lo >> 62);
         lo <<= 2;
     }
     if (MODE == 1 && local) atomicAdd(count_out, local);
 }
-

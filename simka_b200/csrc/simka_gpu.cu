@@ -984,14 +984,17 @@ int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
     return SIMKA_OK;
 }
 
-int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
-                        uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected) {
+// filter: the -filter option (processFiltered, src/simkaMin/SimkaMinCount.hpp:341-380): only k-mers seen at least twice are
+// sketched.  The reference remembers first occurrences in a Bloom filter of max-memory * 8 / cores bits; this build counts
+// exactly (stage 1 with abundance-min 2), i.e. it equals the reference wherever that filter answers no false positive.
+static int simkamin_sketch_impl(bool filter, int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
+                                uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected) {
     if (!hashes_out || !counts_out || sketch_size == 0 || (n_words && (!packed || !bad))) return SIMKA_ERR_INVALID;
     simka_params prm;
     memset(&prm, 0, sizeof prm);
     prm.kmer_size = kmer_size;
     prm.nb_samples = 1;
-    prm.abundance_min = 0;
+    prm.abundance_min = filter ? 2 : 0;
     prm.abundance_max = 0x7FFFFFFFFFFFFFFFll;
     prm.device = device;
     prm.sketch_mode = 1;
@@ -1013,32 +1016,39 @@ int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_
     } while (0);
     if (rc != SIMKA_OK) { simka_gpu_destroy(ctx); return rc; }
     const uint32_t n_sel = (uint32_t)std::min<uint64_t>(n, sketch_size);
-    // the order-dependent count of the largest member once the sketch is complete (only when it can be complete)
+    // the order-dependent count of the largest member once the sketch is complete (only when it can be complete):
+    // without -filter a member enters the heap at its first occurrence and the largest one counts occurrences up to the
+    // last entry; with -filter members enter at their second occurrence with count 2 and the largest one adds the
+    // occurrences between its own entry and the last entry
     if (n >= sketch_size && n_sel > 0) {
-        uint64_t *d_sk = nullptr; ull *d_first = nullptr, *d_cnt = nullptr;
+        uint64_t *d_sk = nullptr; ull *d_first = nullptr, *d_second = nullptr, *d_cnt = nullptr;
         uint64_t *d_packed = nullptr; uint32_t *d_bad = nullptr;
         bool ok = cudaMalloc(&d_sk, (size_t)n_sel * 8) == cudaSuccess && cudaMalloc(&d_first, (size_t)n_sel * 8) == cudaSuccess &&
+                  cudaMalloc(&d_second, (size_t)n_sel * 8) == cudaSuccess &&
                   cudaMalloc(&d_cnt, 8) == cudaSuccess && cudaMalloc(&d_packed, (n_words + 1) * 8) == cudaSuccess &&
                   cudaMalloc(&d_bad, (n_words + 1) * 4) == cudaSuccess;
         ok = ok && cudaMemcpy(d_sk, hk.data(), (size_t)n_sel * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemset(d_first, 0xFF, (size_t)n_sel * 8) == cudaSuccess && cudaMemset(d_cnt, 0, 8) == cudaSuccess &&
+             cudaMemset(d_first, 0xFF, (size_t)n_sel * 8) == cudaSuccess && cudaMemset(d_second, 0xFF, (size_t)n_sel * 8) == cudaSuccess &&
+             cudaMemset(d_cnt, 0, 8) == cudaSuccess &&
              cudaMemcpy(d_packed, packed, (n_words + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
              cudaMemcpy(d_bad, bad, (n_words + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
         if (ok) {
             const unsigned g = (unsigned)((n_words + BLOCK - 1) / BLOCK);
-            k_sketch_scan<0><<<g, BLOCK>>>(d_packed, d_bad, n_words, kmer_size, seed, d_sk, n_sel, d_first, 0, d_cnt);
-            std::vector<ull> first(n_sel);
-            ok = cudaMemcpy(first.data(), d_first, (size_t)n_sel * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+            k_sketch_scan<0><<<g, BLOCK>>>(d_packed, d_bad, n_words, kmer_size, seed, d_sk, n_sel, d_first, d_second, 0, 0, d_cnt);
+            if (filter) k_sketch_scan<2><<<g, BLOCK>>>(d_packed, d_bad, n_words, kmer_size, seed, d_sk, n_sel, d_first, d_second, 0, 0, d_cnt);
+            std::vector<ull> entry(n_sel);  // position at which each member enters the heap
+            ok = cudaMemcpy(entry.data(), filter ? d_second : d_first, (size_t)n_sel * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
             ull t_star = 0;
-            for (uint32_t i = 0; i < n_sel; i++) t_star = std::max(t_star, first[i]);
+            for (uint32_t i = 0; i < n_sel; i++) t_star = std::max(t_star, entry[i]);
             if (ok) {
-                k_sketch_scan<1><<<g, BLOCK>>>(d_packed, d_bad, n_words, kmer_size, seed, d_sk, n_sel, d_first, t_star, d_cnt);
+                const ull t_from = filter ? entry[n_sel - 1] + 1 : 0;
+                k_sketch_scan<1><<<g, BLOCK>>>(d_packed, d_bad, n_words, kmer_size, seed, d_sk, n_sel, d_first, d_second, t_from, t_star, d_cnt);
                 ull cnt = 0;
                 ok = cudaMemcpy(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost) == cudaSuccess && cudaGetLastError() == cudaSuccess;
-                if (ok) hc[n_sel - 1] = (uint32_t)cnt;
+                if (ok) hc[n_sel - 1] = (uint32_t)(cnt + (filter ? 2 : 0));
             }
         }
-        cudaFree(d_sk); cudaFree(d_first); cudaFree(d_cnt); cudaFree(d_packed); cudaFree(d_bad);
+        cudaFree(d_sk); cudaFree(d_first); cudaFree(d_second); cudaFree(d_cnt); cudaFree(d_packed); cudaFree(d_bad);
         if (!ok) { simka_gpu_destroy(ctx); return SIMKA_ERR_CUDA; }
     }
     simka_gpu_destroy(ctx);
@@ -1046,6 +1056,16 @@ int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_
     for (uint32_t i = 0; i < n_sel; i++) { hashes_out[sketch_size - n_sel + i] = hk[i]; counts_out[sketch_size - n_sel + i] = hc[i]; }
     if (n_selected) *n_selected = n_sel;
     return SIMKA_OK;
+}
+
+int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
+                        uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected) {
+    return simkamin_sketch_impl(false, device, kmer_size, sketch_size, seed, packed, bad, n_words, n_reads, hashes_out, counts_out, n_selected);
+}
+
+int simkamin_gpu_sketch_filter(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
+                               uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected) {
+    return simkamin_sketch_impl(true, device, kmer_size, sketch_size, seed, packed, bad, n_words, n_reads, hashes_out, counts_out, n_selected);
 }
 
 int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *counts, uint32_t n, uint32_t s, float *jaccard,

@@ -6,7 +6,7 @@
 //                 sketchSize x {u64 hash, u32 count, 4 pad} ascending (zero padding first), then the ids as u8 length + bytes
 //   distance:     mat_presenceAbsence_jaccard.bin / mat_abundance_braycurtis.bin, float32 at (i * nbDatasets2 + j) * 4
 //   export:       <name>.csv.gz, header ";id..." and rows "id;%f;..."
-// -filter (approximate Bloom filter, SimkaMinCount.hpp:341-380) is not supported.
+// -filter (SimkaMinCount.hpp:341-380): first occurrences are remembered exactly instead of in the reference's Bloom filter.
 #include <sys/stat.h>
 
 #include <cstdio>
@@ -56,7 +56,7 @@ long long geti(std::map<std::string, std::string> &kv, const char *k, long long 
 
 int do_sketch(std::map<std::string, std::string> &kv) {
     if (!kv.count("-in")) throw bank::Exception("Option '-in' is mandatory");
-    if (kv.count("-filter")) throw bank::Exception("-filter (approximate Bloom filter) is not supported by this build");
+    const bool abundance_filter = kv.count("-filter") != 0;
     const std::string out = kv.count("-out") ? kv["-out"] : "./simkaMin_kmers.bin";
     const int k = (int)geti(kv, "-kmer-size", 21);
     const uint32_t s = (uint32_t)geti(kv, "-nb-kmers", 100000), seed = (uint32_t)geti(kv, "-seed", 100);
@@ -83,8 +83,8 @@ int do_sketch(std::map<std::string, std::string> &kv) {
         std::vector<uint32_t> bad(words + 1);
         simka_pack_reads(seqs.data(), off.data(), off.size() - 1, packed.data(), bad.data(), (int)geti(kv, "-nb-cores", 0));
         uint32_t nsel = 0;
-        const int rc = simkamin_gpu_sketch((int)geti(kv, "-device", 0), k, s, seed, packed.data(), bad.data(), words, off.size() - 1, hashes.data(),
-                                           counts.data(), &nsel);
+        const int rc = (abundance_filter ? simkamin_gpu_sketch_filter : simkamin_gpu_sketch)((int)geti(kv, "-device", 0), k, s, seed, packed.data(), bad.data(), words,
+                                                                                   off.size() - 1, hashes.data(), counts.data(), &nsel);
         if (rc != SIMKA_OK) throw bank::Exception("simkamin_gpu_sketch failed (code " + std::to_string(rc) + "): a CUDA device is required");
         for (uint32_t i = 0; i < s; i++) { rec[i].hash = hashes[i]; rec[i].count = counts[i]; rec[i].pad = 0; }
         fwrite(rec.data(), sizeof(Entry), s, f);

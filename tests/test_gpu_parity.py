@@ -486,6 +486,34 @@ def test_simkamin_gpu_sketch_and_distance_reproduce_reference_truth(golden_dir, 
     assert simkamin_csv(ids, bc) == open(os.path.join(tdir, "mat_abundance_braycurtis.csv")).read()
 
 
+@pytest.mark.parametrize("k,max_reads,nb_kmers", [(21, 0, 100), (21, 100, 1000), (31, 0, 1000), (31, 100, 100)])
+def test_simkamin_gpu_filter_sketch_reproduces_reference_truth(golden_dir, k, max_reads, nb_kmers):
+    """the -filter option end to end on the GPU against the reference's k*_filter_* golden matrices, sketch for sketch against the oracle"""
+    from test_oracle_golden import simkamin_csv, simkamin_example_sketches
+    ids, gh, gc = simkamin_example_sketches(golden_dir, k, max_reads, nb_kmers,
+                                            lambda s, o, kk, n: simka_b200.simkamin_sketch(s, o, kk, n, seed=100, filter=True))
+    _, oh, oc = simkamin_example_sketches(golden_dir, k, max_reads, nb_kmers,
+                                          lambda s, o, kk, n: oracle.simkamin_sketch(s, o, kk, n, seed=100, filter=True))
+    np.testing.assert_array_equal(gh, oh)
+    np.testing.assert_array_equal(gc, oc)
+    jac, bc, _ = simka_b200.simkamin_distance(gh, gc)
+    tdir = os.path.join(golden_dir, "truth_simkaMin", f"k{k}_filter_{max_reads}-{nb_kmers}_n1")
+    assert simkamin_csv(ids, jac) == open(os.path.join(tdir, "mat_presenceAbsence_jaccard.csv")).read()
+    assert simkamin_csv(ids, bc) == open(os.path.join(tdir, "mat_abundance_braycurtis.csv")).read()
+
+
+def test_simkamin_gpu_filter_sketch_synthetic():
+    """-filter on larger inputs: sketch smaller / larger than the number of repeated k-mers, duplicates, N runs"""
+    samples = synthetic_samples(2, 4000) + nasty_samples()[:3]
+    for seqs, off in samples:
+        for k, s in [(21, 300), (31, 5000), (31, 10**6), (15, 64)]:
+            gh, gc, gn = simka_b200.simkamin_sketch(seqs, off, k, s, seed=7, filter=True)
+            oh, oc, on = oracle.simkamin_sketch(seqs, off, k, s, seed=7, filter=True)
+            assert gn == on
+            np.testing.assert_array_equal(gh, oh)
+            np.testing.assert_array_equal(gc, oc)
+
+
 def test_simkamin_gpu_sketch_synthetic():
     """larger inputs: sketch smaller than, equal to and larger than the number of distinct k-mers; N runs; duplicates"""
     samples = synthetic_samples(2, 4000) + nasty_samples()[:3]

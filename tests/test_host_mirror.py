@@ -177,8 +177,8 @@ def test_simkamincore_argument_handling_and_export(tmp_path):
     assert r.returncode == 1 and r.stdout.startswith("EXCEPTION: ")
     r = subprocess.run([exe, "sketch", "-out", str(tmp_path / "s.bin")], capture_output=True, text=True)
     assert r.returncode == 1 and "mandatory" in r.stdout
-    r = subprocess.run([exe, "sketch", "-in", "x", "-filter"], capture_output=True, text=True)
-    assert r.returncode == 1 and "-filter" in r.stdout
+    r = subprocess.run([exe, "sketch", "-in", "/nonexistent/input.txt", "-filter"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("EXCEPTION: ")
     rng = np.random.default_rng(3)
     ids = ["A", "B2", "sample_C"]
     h = np.sort(rng.integers(1, 2**63, (3, 8), dtype=np.uint64), axis=1)

@@ -138,6 +138,20 @@ def test_simkamin_oracle_reproduces_reference_truth(golden_dir, k, max_reads, nb
     assert simkamin_csv(ids, bc) == open(os.path.join(tdir, "mat_abundance_braycurtis.csv")).read()
 
 
+@pytest.mark.parametrize("k", [21, 31])
+@pytest.mark.parametrize("max_reads", [0, 100])
+@pytest.mark.parametrize("nb_kmers", [100, 1000])
+def test_simkamin_oracle_filter_reproduces_reference_truth(golden_dir, k, max_reads, nb_kmers):
+    """the -filter half of the reference's SimkaMin grid (truth_simkaMin_symetrical/k*_filter_*): the oracle remembers first
+    occurrences exactly where the reference asks a 6.4e10-bit Bloom filter, and reproduces the golden matrices byte for byte"""
+    ids, hashes, counts = simkamin_example_sketches(golden_dir, k, max_reads, nb_kmers,
+                                                    lambda s, o, kk, n: oracle.simkamin_sketch(s, o, kk, n, seed=100, filter=True))
+    jac, bc = oracle.simkamin_distance(hashes, counts)
+    tdir = os.path.join(golden_dir, "truth_simkaMin", f"k{k}_filter_{max_reads}-{nb_kmers}_n1")
+    assert simkamin_csv(ids, jac) == open(os.path.join(tdir, "mat_presenceAbsence_jaccard.csv")).read()
+    assert simkamin_csv(ids, bc) == open(os.path.join(tdir, "mat_abundance_braycurtis.csv")).read()
+
+
 def test_murmur3_known_answer():
     """MurmurHash3_x64_128 of 8 zero bytes with seed 0 is 0 for h1 only if the mix is wrong: pin two self-consistent facts
     instead -- different seeds and keys give different values, and the value is stable (regression pin)."""
