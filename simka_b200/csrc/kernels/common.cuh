@@ -12,10 +12,14 @@ constexpr int MAX_B = 1024;                  // max buckets per partition level
 #ifndef SIMKA_BIN_TARGET
 #define SIMKA_BIN_TARGET 768
 #endif
+#ifndef SIMKA_K3_BLOCK
+#define SIMKA_K3_BLOCK 256
+#endif
 #ifndef SIMKA_CNT_SLOTS
 #define SIMKA_CNT_SLOTS 2048
 #endif
 constexpr int BIN_TARGET = SIMKA_BIN_TARGET;              // fine bins hold BIN_TARGET..2*BIN_TARGET keys on average
+constexpr int K3_BLOCK = SIMKA_K3_BLOCK;      // threads of a counting CTA (one fine bin at a time)
 constexpr int CNT_SLOTS = SIMKA_CNT_SLOTS;    // K3 hash table slots
 constexpr int CNT_MAXDISTINCT = CNT_SLOTS * 3 / 4;  // distinct keys one table pass may hold (load 0.75)
 constexpr int CHIST = 1024;                  // dense abundance histogram bins (complex distances)

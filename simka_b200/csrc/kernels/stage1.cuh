@@ -456,12 +456,12 @@ template <bool MULTI>
 __device__ __forceinline__ void bin_insert_all(uint64_t *tk, uint32_t *tc, uint16_t *claimed, uint32_t *nclaim,
                                                const uint64_t *__restrict__ kb, uint32_t n, uint32_t R, uint32_t r, int slot_shift) {
     const int tid = threadIdx.x;
-    for (uint32_t base = 0; base < n; base += BLOCK * 4) {
+    for (uint32_t base = 0; base < n; base += K3_BLOCK * 4) {
         uint64_t h[4];
         uint32_t pending = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const uint32_t i = base + q * BLOCK + tid;
+            const uint32_t i = base + q * K3_BLOCK + tid;
             h[q] = i < n ? kb[i] : EMPTY;
             if (i < n) pending |= 1u << q;
         }
@@ -480,7 +480,7 @@ __device__ __forceinline__ void bin_insert_all(uint64_t *tk, uint32_t *tc, uint1
 // Persistent CTAs, bins taken with a grid stride.  Per-bin fixed cost: two barriers; everything else is
 // proportional to the keys (insert) and to the distinct keys (read-out of the claimed slots, which also
 // leaves the table clean for the next bin).
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(K3_BLOCK)
 k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine_off, uint32_t nbins, int slot_shift,
             int64_t amin, int64_t amax, CountOut out) {
     __shared__ __align__(16) uint64_t tk[CNT_SLOTS];
@@ -489,7 +489,7 @@ k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine
     __shared__ uint32_t s_cursor, s_nclaim[2];
     __shared__ ull s_tot[3];
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < CNT_SLOTS; i += BLOCK) { tk[i] = EMPTY; tc[i] = 0; }
+    for (int i = tid; i < CNT_SLOTS; i += K3_BLOCK) { tk[i] = EMPTY; tc[i] = 0; }
     if (tid == 0) { s_cursor = 0; s_nclaim[0] = s_nclaim[1] = 0; s_tot[0] = s_tot[1] = s_tot[2] = 0; }
     __syncthreads();
     ull t_d = 0, t_s = 0, t_q = 0;
@@ -524,7 +524,7 @@ k_bin_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ fine
                 overflow = nc > CNT_MAXDISTINCT;
                 if (tid == 0) s_nclaim[(pass + 1) & 1] = 0;
                 // read-out + clean of the claimed slots
-                for (uint32_t e0 = 0; e0 < nc; e0 += BLOCK) {
+                for (uint32_t e0 = 0; e0 < nc; e0 += K3_BLOCK) {
                     const uint32_t e = e0 + tid;
                     bool keep = false;
                     uint64_t hk = 0;

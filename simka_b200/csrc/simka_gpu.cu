@@ -536,13 +536,13 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         co.totals = d_totals;
         co.error_flag = d_error;
         if (ctx->occ_bin_count <= 0) {
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bin_count, k_bin_count, BLOCK, 0));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bin_count, k_bin_count, K3_BLOCK, 0));
             if (ctx->occ_bin_count <= 0) ctx->occ_bin_count = 1;
         }
         const unsigned gbin = (unsigned)std::min<uint64_t>(nbins, (uint64_t)ctx->nsm * ctx->occ_bin_count);
         const int slot_shift = std::max(0, W - bin_bits - ilog2_floor(CNT_SLOTS));  // table slot: the bits just below the bin bits
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
-        k_bin_count<<<gbin, BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins, slot_shift, ctx->prm.abundance_min,
+        k_bin_count<<<gbin, K3_BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins, slot_shift, ctx->prm.abundance_min,
                                             ctx->prm.abundance_max, co);
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT + 1], st));
         launch_scan(ctx, ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins);

@@ -527,8 +527,8 @@ def test_simkamin_gpu_sketch_synthetic():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,max_reads,nb_kmers", [(21, 0, 100), (31, 100, 1000)])
-def test_simkamincore_cli_reproduces_reference_truth(tmp_path, golden_dir, k, max_reads, nb_kmers):
+@pytest.mark.parametrize("k,max_reads,nb_kmers,filt", [(21, 0, 100, False), (31, 100, 1000, False), (21, 100, 100, True), (31, 0, 1000, True)])
+def test_simkamincore_cli_reproduces_reference_truth(tmp_path, golden_dir, k, max_reads, nb_kmers, filt):
     """the reference's SimkaMin test (tests/simkaMin/test_simkaMin.py:141-154) against the `simkaMinCore` binary of this
     build, driven as simkaMin.py drives it (sketch, distance, export: simkaMin/simkaMin.py:101-197): the csv files are
     byte-identical to the truth; then the same matrix computed in rectangular -start-i/-start-j blocks."""
@@ -539,7 +539,7 @@ def test_simkamincore_cli_reproduces_reference_truth(tmp_path, golden_dir, k, ma
     sk = str(tmp_path / "sketch.bin")
     r = subprocess.run([exe, "sketch", "-in", os.path.join(golden_dir, "example", "simka_input.txt"), "-out", sk, "-seed", "100", "-kmer-size", str(k),
                         "-nb-kmers", str(nb_kmers), "-max-reads", str(max_reads), "-min-read-size", "0", "-min-shannon-index", "0",
-                        "-nb-cores", "0", "-max-memory", "8000"], capture_output=True, text=True)
+                        "-nb-cores", "0", "-max-memory", "8000"] + (["-filter"] if filt else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert os.path.getsize(sk) == 13 + 5 * nb_kmers * 16 + sum(1 + len(i) for i in "ABCDE")
     dist = str(tmp_path / "distance")
@@ -548,7 +548,7 @@ def test_simkamincore_cli_reproduces_reference_truth(tmp_path, golden_dir, k, ma
     assert r.returncode == 0, r.stdout + r.stderr
     r = subprocess.run([exe, "export", "-in", dist, "-in1", sk, "-in2", sk, "-out", str(tmp_path / "res"), "-nb-cores", "0"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    tdir = os.path.join(golden_dir, "truth_simkaMin", f"k{k}__{max_reads}-{nb_kmers}_n1")
+    tdir = os.path.join(golden_dir, "truth_simkaMin", f"k{k}_{'filter' if filt else ''}_{max_reads}-{nb_kmers}_n1")
     for f in ("mat_presenceAbsence_jaccard", "mat_abundance_braycurtis"):
         assert gzip.open(tmp_path / "res" / (f + ".csv.gz"), "rt").read() == open(os.path.join(tdir, f + ".csv")).read(), f
     # blocks of 2 + 3 datasets as simkaMin.py would issue them with MAX_DATASETS_PROCESS = 2..3: (0,0) (0,1) (1,1)
