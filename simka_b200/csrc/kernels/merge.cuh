@@ -616,3 +616,26 @@ __global__ void k_whittaker_fold(ull *__restrict__ whit, const ull *__restrict__
     int i = idx / n, j = idx % n;
     if (i < j) whit[idx] += T[idx] + T[(size_t)j * n + i];
 }
+
+// ---------------------------------------------------------------------------------------------
+// Refinement of the per-sample lists for the merge.  A list comes out of stage 1 grouped by fine range (top fg bits of h),
+// and fg cannot exceed the counting bins of a sample; with many samples a merge bin of that width holds far more entries
+// than the on-chip tables take and the merge would re-read it once per sub-pass (16-32 times at 128-512 samples).  These two
+// kernels regroup one list by the top fg2 > fg bits (a counting sort inside every fine range; the order inside a group
+// stays arbitrary, the merge regroups by key), so that merge bins can be as narrow as the total number of entries asks.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK)
+k_refine_hist(const uint64_t *__restrict__ eh, uint64_t n, int shift, uint32_t *__restrict__ hist) {
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * BLOCK) atomicAdd(&hist[eh[i] >> shift], 1u);
+}
+__global__ void __launch_bounds__(BLOCK)
+k_refine_scatter(const uint64_t *__restrict__ eh, const uint32_t *__restrict__ ec, uint64_t n, int shift, const uint64_t *__restrict__ base,
+                 uint32_t *__restrict__ cursor, uint64_t *__restrict__ out_h, uint32_t *__restrict__ out_c) {
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * BLOCK) {
+        const uint64_t h = eh[i];
+        const uint64_t b = h >> shift;
+        const uint64_t pos = base[b] + atomicAdd(&cursor[b], 1u);
+        out_h[pos] = h;
+        out_c[pos] = ec[i];
+    }
+}

@@ -129,6 +129,8 @@ struct simka_ctx {
     Arena arena;
     int fg_bits = -1;    // fine-range granularity, fixed by the first sample
     DevBuf d_off_table;  // [N][FG+1]
+    DevBuf d_off_table2; // [N][FG2+1]: offsets of the lists regrouped for the merge (many samples)
+    bool no_refine = false;  // SIMKA_B200_REFINE=0: merge on the stage-1 granularity (A/B measurements)
     std::vector<simka_sample_totals> global_totals;
     bool totals_overridden = false;
     // complex-distance helpers
@@ -266,6 +268,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
     { const char *e = getenv("SIMKA_B200_EXACT_COUNT"); ctx->force_exact = e && e[0] == '1'; }
     { const char *e = getenv("SIMKA_B200_K1"); ctx->use_k16 = !(e && !strcmp(e, "256")); }
     { const char *e = getenv("SIMKA_B200_B1BITS"); ctx->b1_override = e ? atoi(e) : 0; }
+    { const char *e = getenv("SIMKA_B200_REFINE"); ctx->no_refine = e && e[0] == '0'; }
     cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
     ctx->samples.resize(p->nb_samples);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -322,7 +325,7 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
                       &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
                       &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
-                      &ctx->d_small, &ctx->d_off_table, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum};
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum};
     for (DevBuf *b : bufs) b->release();
     for (auto &set : ctx->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
@@ -817,6 +820,57 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
     uint64_t total_entries = 0;
     for (int s = 0; s < N; s++) { ntot[s] = (double)ctx->global_totals[s].nb_kmers; total_entries += ctx->samples[s].n; }
     CK(cudaMemcpyAsync(ctx->a_ntot, ntot.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    // merge bins of about MRG_TARGET entries.  The lists are grouped by the top fg_bits of the key, which stage 1 cannot make
+    // finer than the counting bins of one sample: when that leaves more entries per merge bin than the on-chip tables hold
+    // (many samples), the lists are first regrouped by more bits (k_refine_*), once, instead of being re-read per sub-pass.
+    const int want_bits = ilog2_ceil(std::max<uint64_t>(1, total_entries / MRG_TARGET));
+    int fg_eff = ctx->fg_bits;
+    const uint32_t *off_eff = ctx->d_off_table.as<uint32_t>();
+    if (ctx->fg_bits >= 0 && (total_entries >> ctx->fg_bits) > (uint64_t)MRG_CAP && want_bits > ctx->fg_bits && !ctx->no_refine) {
+        int fg2 = std::min(want_bits, std::min(ctx->W, 24));
+        while (fg2 > ctx->fg_bits && (size_t)N * (((size_t)1 << fg2) + 1) * 4 > ((size_t)4 << 30)) fg2--;
+        if (fg2 > ctx->fg_bits) {
+            const size_t nb2 = (size_t)1 << fg2, row = nb2 + 1;
+            uint64_t max_n = 0;
+            for (int s = 0; s < N; s++) max_n = std::max<uint64_t>(max_n, ctx->samples[s].n);
+            if (ctx->d_off_table2.reserve((size_t)N * row * 4) || ctx->d_fine_hist.reserve(nb2 * 4) || ctx->d_fine_cursor.reserve(nb2 * 4) ||
+                ctx->d_fine_off.reserve(row * 8) || ctx->d_keysA.reserve(max_n * 8) || ctx->d_stage_c.reserve(max_n * 4)) {
+                ctx->set_error("out of device memory (merge refinement)");
+                return SIMKA_ERR_NOMEM;
+            }
+            CK(cudaMemsetAsync(ctx->d_off_table2.p, 0, (size_t)N * row * 4, st));
+            const int shift = ctx->W - fg2;
+            for (int s = 0; s < N; s++) {
+                SampleData &sd = ctx->samples[s];
+                if (sd.n == 0) continue;
+                const unsigned g = (unsigned)std::min<uint64_t>((sd.n + BLOCK - 1) / BLOCK, (uint64_t)ctx->nsm * 16);
+                CK(cudaMemsetAsync(ctx->d_fine_hist.p, 0, nb2 * 4, st));
+                CK(cudaMemsetAsync(ctx->d_fine_cursor.p, 0, nb2 * 4, st));
+                k_refine_hist<<<g, BLOCK, 0, st>>>(sd.eh, sd.n, shift, ctx->d_fine_hist.as<uint32_t>());
+                launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), nb2);
+                k_fill_offsets<<<(unsigned)((row + 255) / 256), 256, 0, st>>>(ctx->d_fine_off.as<uint64_t>(), ctx->d_off_table2.as<uint32_t>() + (size_t)s * row,
+                                                                          (uint32_t)nb2, 1);
+                if (sd.imported) {
+                    // an imported list lives in the caller's memory (read-only for us): the regrouped copy goes to the arena
+                    uint64_t *nh = (uint64_t *)ctx->arena.alloc(sd.n * 8);
+                    uint32_t *nc = (uint32_t *)ctx->arena.alloc(sd.n * 4);
+                    if (!nh || !nc) { ctx->set_error("out of device memory (merge refinement)"); return SIMKA_ERR_NOMEM; }
+                    k_refine_scatter<<<g, BLOCK, 0, st>>>(sd.eh, sd.ec, sd.n, shift, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), nh, nc);
+                    sd.eh = nh;
+                    sd.ec = nc;
+                } else {
+                    k_refine_scatter<<<g, BLOCK, 0, st>>>(sd.eh, sd.ec, sd.n, shift, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(),
+                                                          ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>());
+                    CK(cudaMemcpyAsync(sd.eh, ctx->d_keysA.p, sd.n * 8, cudaMemcpyDeviceToDevice, st));
+                    CK(cudaMemcpyAsync(sd.ec, ctx->d_stage_c.p, sd.n * 4, cudaMemcpyDeviceToDevice, st));
+                }
+                ctx->launches += 4;
+            }
+            CK(cudaGetLastError());
+            fg_eff = fg2;
+            off_eff = ctx->d_off_table2.as<uint32_t>();
+        }
+    }
     // pointer tables
     std::vector<const void *> ptrs(2 * (size_t)N);
     for (int s = 0; s < N; s++) { ptrs[s] = ctx->samples[s].eh; ptrs[N + s] = ctx->samples[s].ec; }
@@ -829,12 +883,12 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
     if (ctx->prm.complex_dist) CK(cudaMemcpyAsync(&big_n, d_big_n, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));  // host staging vectors are reused below / big_n needed
     if (ctx->fg_bits >= 0 && total_entries > 0) {
-        int mg_bits = std::min(ctx->fg_bits, ilog2_ceil(std::max<uint64_t>(1, total_entries / MRG_TARGET)));
+        int mg_bits = std::min(fg_eff, want_bits);
         MergeArgs a;
-        a.n = N; a.fg_bits = ctx->fg_bits; a.mg_bits = mg_bits;
+        a.n = N; a.fg_bits = fg_eff; a.mg_bits = mg_bits;
         a.eh = reinterpret_cast<const uint64_t *const *>(ctx->d_ptrs.p);
         a.ec = reinterpret_cast<const uint32_t *const *>(ctx->d_ptrs.as<const void *>() + N);
-        a.off = ctx->d_off_table.as<uint32_t>();
+        a.off = off_eff;
         a.ntot = ctx->a_ntot;
         a.logtab = ctx->d_logtab.as<double2>();
         a.simple = ctx->prm.simple_dist; a.complex_ = ctx->prm.complex_dist; a.count_only = 0;
@@ -865,7 +919,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
             ctx->launches++;
             // the pairs: tiles of 32 x 32 samples; merge bins sized for the <= 64 samples a tile gathers
             MergeArgs t = a;
-            t.mg_bits = std::min(ctx->fg_bits, ilog2_ceil(std::max<uint64_t>(1, total_entries * 64 / (uint64_t)N / 1024)));
+            t.mg_bits = std::min(fg_eff, ilog2_ceil(std::max<uint64_t>(1, total_entries * 64 / (uint64_t)N / 1024)));
             void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge_sm<true, true, true> : k_merge_sm<true, false, true>)
                                                : (a.complex_ ? k_merge_sm<false, true, true> : k_merge_sm<false, false, true>);
             int occ = 0;

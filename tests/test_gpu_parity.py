@@ -339,6 +339,17 @@ def test_many_samples_merge_paths(monkeypatch, n, variant):
     assert_stats_equal(st, run)
 
 
+@pytest.mark.parametrize("n", [40, 96])
+def test_merge_without_list_refinement(monkeypatch, n):
+    """many small samples: the merge regroups the per-sample lists by more key bits than stage 1 could (k_refine_*, the default,
+    exercised by the tests above); SIMKA_B200_REFINE=0 keeps the stage-1 granularity and re-reads each wide bin in sub-passes"""
+    monkeypatch.setenv("SIMKA_B200_REFINE", "0")
+    samples = synthetic_samples(n, 500, read_len=100, n_genomes=12, genome_len=2500)
+    run = oracle_run(samples, 21, 2)
+    st = simka_b200.run_samples(samples, 21, abundance_min=2)
+    assert_stats_equal(st, run)
+
+
 def test_merge_variants_agree(monkeypatch):
     """the two merge kernels (shared-memory accumulators, global atomics) on the same input"""
     samples = synthetic_samples(20, 1500, n_genomes=10, genome_len=3000)
