@@ -422,32 +422,44 @@ struct CountOut {
     int *error_flag;
 };
 
-// Insert up to four keys per thread into the open-addressing table (linear probing), the four probe
-// sequences interleaved so that the shared-memory latencies overlap and the warp stays converged.
-// Plain read first: most keys repeat a k-mer that is already there (one LDS + one ATOMS.POPC.INC).
-// A thread that claims a slot appends it to the claimed list, which is what the read-out walks
-// (the table itself is never scanned) and what counts the distinct keys of the bin.
+// One probe step of the open-addressing table (linear probing).  Plain read first: most keys repeat a k-mer that is
+// already there (one LDS + one ATOMS.POPC.INC); a thread that claims a free slot appends it to the claimed list, which is
+// what the read-out walks (the table itself is never scanned) and what counts the distinct keys of the bin.
+// Returns true when the key is placed.
+__device__ __forceinline__ bool table_probe(uint64_t *tk, uint32_t *tc, uint16_t *claimed, uint32_t *nclaim, uint64_t h, uint32_t slot) {
+    volatile uint64_t *vk = tk;
+    uint64_t cur = vk[slot];
+    if (cur == EMPTY) {
+        cur = atomicCAS(reinterpret_cast<ull *>(&tk[slot]), (ull)EMPTY, (ull)h);
+        if (cur == EMPTY) { cur = h; claimed[atomicAdd(nclaim, 1u)] = (uint16_t)slot; }
+    }
+    if (cur == h) { atomicAdd(&tc[slot], 1u); return true; }
+    return false;
+}
+// Insert up to four keys per thread.  Round 1 probes the home slots of the four keys one after the other with the warp
+// converged: this places 9 keys out of 10.  The leftovers -- a different k-mer sits in the home slot -- are walked one key
+// per thread in a tight loop: in the unrolled four-key form those later rounds ran with one or two active lanes per warp and
+// were 14 % of the kernel's instructions (ncu source view of the first version).
 __device__ __forceinline__ void table_insert4(uint64_t *tk, uint32_t *tc, uint16_t *claimed, uint32_t *nclaim, const uint64_t (&h)[4],
                                               uint32_t pending, int slot_shift) {
-    volatile uint64_t *vk = tk;
     uint32_t slot[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) slot[q] = (uint32_t)(h[q] >> slot_shift) & (CNT_SLOTS - 1);
-    int rounds = 0;
-    while (pending) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (pending & (1u << q)) {
-                uint64_t cur = vk[slot[q]];
-                if (cur == EMPTY) {
-                    cur = atomicCAS(reinterpret_cast<ull *>(&tk[slot[q]]), (ull)EMPTY, (ull)h[q]);
-                    if (cur == EMPTY) { cur = h[q]; claimed[atomicAdd(nclaim, 1u)] = (uint16_t)slot[q]; }
-                }
-                if (cur == h[q]) { atomicAdd(&tc[slot[q]], 1u); pending &= ~(1u << q); }
-                else slot[q] = (slot[q] + 1) & (CNT_SLOTS - 1);
-            }
+    for (int q = 0; q < 4; q++) {
+        if (pending & (1u << q)) {
+            if (table_probe(tk, tc, claimed, nclaim, h[q], slot[q])) pending &= ~(1u << q);
         }
-        if (++rounds > CNT_SLOTS) return;  // table full: nclaim == CNT_SLOTS > CNT_MAXDISTINCT makes the caller retry finer
+    }
+    while (pending) {
+        const uint64_t hk = (pending & 1u) ? h[0] : (pending & 2u) ? h[1] : (pending & 4u) ? h[2] : h[3];
+        uint32_t sl = (pending & 1u) ? slot[0] : (pending & 2u) ? slot[1] : (pending & 4u) ? slot[2] : slot[3];
+        pending &= pending - 1;
+        // a full table leaves nclaim == CNT_SLOTS > CNT_MAXDISTINCT, which makes the caller retry with finer sub-passes
+        for (int probes = 1; probes < CNT_SLOTS; probes++) {
+            sl = (sl + 1) & (CNT_SLOTS - 1);
+            if (table_probe(tk, tc, claimed, nclaim, hk, sl)) break;
+        }
     }
 }
 
