@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -243,7 +244,7 @@ const char *simka_b200_version(void) { return "simka_b200 0.1 (sm_100a)"; }
 int simka_gpu_host_alloc(void **ptr, size_t bytes) { return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? SIMKA_OK : SIMKA_ERR_NOMEM; }
 int simka_gpu_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? SIMKA_OK : SIMKA_ERR_CUDA; }
 
-int simka_gpu_create(simka_ctx **out, const simka_params *p) {
+int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
     if (!out || !p) return SIMKA_ERR_INVALID;
     *out = nullptr;
     if (p->kmer_size < 2 || p->kmer_size > 31 || p->nb_samples < 1 || p->nb_samples > MRG_MAXN) return SIMKA_ERR_INVALID;
@@ -306,6 +307,8 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) {
     if (!ok) { simka_gpu_destroy(ctx); return SIMKA_ERR_CUDA; }
     *out = ctx;
     return SIMKA_OK;
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    return SIMKA_ERR_NOMEM;
 }
 
 int simka_gpu_reset(simka_ctx *ctx) {
@@ -395,7 +398,7 @@ int simka_gpu_push_reads_device(simka_ctx *ctx, int sample_id, const uint64_t *d
     return SIMKA_OK;
 }
 
-int simka_gpu_push_ascii(simka_ctx *ctx, int sample_id, const char *seqs, const uint64_t *read_off, uint64_t n_reads) {
+int simka_gpu_push_ascii(simka_ctx *ctx, int sample_id, const char *seqs, const uint64_t *read_off, uint64_t n_reads) try {
     InSlot *sl = nullptr;
     int rc = find_slot(ctx, sample_id, &sl);
     if (rc) return rc;
@@ -423,9 +426,12 @@ int simka_gpu_push_ascii(simka_ctx *ctx, int sample_id, const char *seqs, const 
     sl->words = w0 + n_words;
     sl->reads += n_reads;
     return SIMKA_OK;
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    if (ctx) ctx->set_error("out of host memory");
+    return SIMKA_ERR_NOMEM;
 }
 
-int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *out) {
+int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *out) try {
     if (!ctx) return SIMKA_ERR_INVALID;
     if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done) { ctx->set_error("bad sample id"); return SIMKA_ERR_INVALID; }
     CK(cudaSetDevice(ctx->prm.device));
@@ -601,9 +607,12 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
     if (sl) { sl->sample = -1; sl->words = sl->reads = 0; sl->ext_packed = nullptr; sl->ext_bad = nullptr; }
     if (out) *out = sd.local;
     return SIMKA_OK;
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    if (ctx) ctx->set_error("out of host memory");
+    return SIMKA_ERR_NOMEM;
 }
 
-int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers, uint32_t *counts, uint64_t *n) {
+int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers, uint32_t *counts, uint64_t *n) try {
     if (!ctx || !n || sample_id < 0 || sample_id >= ctx->prm.nb_samples || !ctx->samples[sample_id].done) return SIMKA_ERR_INVALID;
     CK(cudaSetDevice(ctx->prm.device));
     SampleData &sd = ctx->samples[sample_id];
@@ -626,6 +635,9 @@ int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers,
     std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
     for (uint64_t i = 0; i < sd.n; i++) { kmers[i] = hk[order[i]]; counts[i] = hc[order[i]]; }
     return SIMKA_OK;
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    if (ctx) ctx->set_error("out of host memory");
+    return SIMKA_ERR_NOMEM;
 }
 
 int simka_gpu_fine_bits(simka_ctx *ctx) { return ctx ? ctx->fg_bits : -1; }
@@ -691,7 +703,7 @@ int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kme
 // Registers a sample from its solid (canonical k-mer, count) list in HOST memory, e.g. the decoded
 // solid/part_P/__p__I.gz records of a reference-format temp dir: hashes the k-mers, groups them by fine range and
 // uploads them; after this the sample is exactly as if simka_gpu_finish_sample had produced it.
-int simka_gpu_import_counts(simka_ctx *ctx, int sample_id, const uint64_t *kmers, const uint32_t *counts, uint64_t n, uint64_t nb_reads) {
+int simka_gpu_import_counts(simka_ctx *ctx, int sample_id, const uint64_t *kmers, const uint32_t *counts, uint64_t n, uint64_t nb_reads) try {
     if (!ctx) return SIMKA_ERR_INVALID;
     if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done || (n && (!kmers || !counts)) || n >= (1ull << 32)) {
         ctx->set_error("bad import arguments");
@@ -761,6 +773,9 @@ int simka_gpu_import_counts(simka_ctx *ctx, int sample_id, const uint64_t *kmers
     if (!ctx->totals_overridden) ctx->global_totals[sample_id] = sd.local;
     ctx->entries += n;
     return SIMKA_OK;
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    if (ctx) ctx->set_error("out of host memory");
+    return SIMKA_ERR_NOMEM;
 }
 
 int simka_gpu_get_totals(simka_ctx *ctx, simka_sample_totals *out) {
@@ -776,7 +791,7 @@ int simka_gpu_set_totals(simka_ctx *ctx, const simka_sample_totals *in) {
     return SIMKA_OK;
 }
 
-int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
+int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
     if (!ctx) return SIMKA_ERR_INVALID;
     const int N = ctx->prm.nb_samples;
     for (int s = 0; s < N; s++) if (!ctx->samples[s].done) { ctx->set_error("all samples must be finished before the merge"); return SIMKA_ERR_INVALID; }
@@ -950,9 +965,12 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) {
     ctx->merge_ms = ms;
     ctx->merged = true;
     return SIMKA_OK;
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    if (ctx) ctx->set_error("out of host memory");
+    return SIMKA_ERR_NOMEM;
 }
 
-int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) {
+int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) try {
     if (!ctx || !out || !ctx->merged) { if (ctx) ctx->set_error("merge_and_accumulate has not run"); return SIMKA_ERR_INVALID; }
     CK(cudaSetDevice(ctx->prm.device));
     const int N = ctx->prm.nb_samples;
@@ -1010,6 +1028,9 @@ int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) {
         }
     }
     return SIMKA_OK;
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    if (ctx) ctx->set_error("out of host memory");
+    return SIMKA_ERR_NOMEM;
 }
 
 int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
@@ -1129,9 +1150,11 @@ int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *co
     uint64_t *dh = nullptr; uint32_t *dc = nullptr, *dstart = nullptr; ull *dq = nullptr;
     const size_t ne = (size_t)n * s, nn = (size_t)n * n;
     const uint64_t pairs = (uint64_t)n * (n - 1) / 2;
+    if (pairs > 0x7FFFFFFFull) return SIMKA_ERR_INVALID;  // one CTA per pair: the grid's x limit (n <= 65536)
     int rc = SIMKA_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    std::vector<ull> hq(4 * pairs);
+    std::vector<ull> hq;
+    try { hq.resize(4 * pairs); } catch (const std::bad_alloc &) { return SIMKA_ERR_NOMEM; }  // nothing may throw across the C ABI
     do {
         if (cudaMalloc(&dh, ne * 8) || cudaMalloc(&dc, ne * 4) || cudaMalloc(&dstart, (size_t)n * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
         if (cudaMemcpy(dh, hashes, ne * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc, counts, ne * 4, cudaMemcpyHostToDevice)) { rc = SIMKA_ERR_CUDA; break; }
@@ -1171,9 +1194,11 @@ int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32
     uint64_t *dh1 = nullptr, *dh2 = nullptr; uint32_t *dc1 = nullptr, *dc2 = nullptr, *ds1 = nullptr, *ds2 = nullptr; ull *dq = nullptr;
     const size_t e1 = (size_t)n1 * s, e2 = (size_t)n2 * s;
     const uint64_t pairs = (uint64_t)n1 * n2;
+    if (pairs > 0x7FFFFFFFull) return SIMKA_ERR_INVALID;  // one CTA per pair: the grid's x limit
     int rc = SIMKA_OK;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<ull> hq(4 * pairs);
+    std::vector<ull> hq;
+    try { hq.resize(4 * pairs); } catch (const std::bad_alloc &) { return SIMKA_ERR_NOMEM; }
     do {
         if (cudaMalloc(&dh1, e1 * 8) || cudaMalloc(&dc1, e1 * 4) || cudaMalloc(&ds1, (size_t)n1 * 4) || cudaMalloc(&dh2, e2 * 8) || cudaMalloc(&dc2, e2 * 4) ||
             cudaMalloc(&ds2, (size_t)n2 * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
