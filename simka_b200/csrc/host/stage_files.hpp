@@ -9,6 +9,7 @@
 //   stats/part_<p>.gz               gzip stream of x87 long double in the order of SimkaStatistics::save (src/core/SimkaDistance.cpp:455-513)
 //   merge_synchro/<p>.ok            empty                                                       (src/SimkaMerge.cpp:1472-1476)
 #pragma once
+#include <dirent.h>
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -42,6 +43,18 @@ inline void mkdirs(const std::string &d) {
         if (i == d.size() || d[i] == '/') { if (!cur.empty()) mkdir(cur.c_str(), 0755); }
         if (i < d.size()) cur.push_back(d[i]);
     }
+}
+
+inline std::vector<std::string> listdir(const std::string &d) {  // plain entry names, "." and ".." left out
+    std::vector<std::string> out;
+    if (DIR *dp = opendir(d.c_str())) {
+        while (struct dirent *e = readdir(dp)) {
+            const std::string n = e->d_name;
+            if (n != "." && n != "..") out.push_back(n);
+        }
+        closedir(dp);
+    }
+    return out;
 }
 
 inline std::string part_file(const std::string &dir, size_t p, size_t bank) {

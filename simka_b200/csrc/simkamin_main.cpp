@@ -1,6 +1,7 @@
-// simkamin_main.cpp -- `simkaMinCore sketch | distance | export | append | info` with the reference's command lines and file
-// formats (src/simkaMin/SimkaMin.cpp:30-110; sketch: SimkaMinCount.hpp:1347-1381,713-1127; distance: SimkaMinDistance.hpp:414-640,
-//  955-998; export: SimkaMinDistanceMatrixExporter.hpp:330-404; append: SimkaMinAppend.hpp:60-160; info: SimkaMinInfos.hpp:58-100),
+// simkamin_main.cpp -- `simkaMinCore sketch | distance | export | append | info | matrix-update` with the reference's command
+// lines and file formats (src/simkaMin/SimkaMin.cpp:30-110; sketch: SimkaMinCount.hpp:1347-1381,713-1127; distance:
+//  SimkaMinDistance.hpp:414-640,955-998; export: SimkaMinDistanceMatrixExporter.hpp:330-404; append: SimkaMinAppend.hpp:60-160;
+//  info: SimkaMinInfos.hpp:58-100; matrix-update (hidden, used by simkaMin_update.py): SimkaMinDistanceMatrixMerger.hpp:87-127),
 // so that the reference's simkaMin.py / simkaMin_update.py wrappers can drive it.
 //   sketch file:  u8 kmerSize, u32 sketchSize, u32 seed, u32 nbDatasets (13 bytes, SimkaMinCommons.hpp:28), then per dataset
 //                 sketchSize x {u64 hash, u32 count, 4 pad} ascending (zero padding first), then the ids as u8 length + bytes
@@ -251,11 +252,44 @@ int do_info(std::map<std::string, std::string> &kv) {
     return EXIT_SUCCESS;
 }
 
+// matrix-update: the binary matrices of -in (E x E, E = datasets of -in1) grow to (E+N) x (E+N) (N = datasets of -in2) from
+// -in/existingVsNew/<name> (E x N) and -in/newVsNew/<name> (N x N):  [[existing, eVsN], [eVsN^T, nVsN]]
+// (SimkaMinDistanceMatrixExporter.hpp:44-121), written to <name>.temp and renamed over the existing file.
+int do_matrix_update(std::map<std::string, std::string> &kv) {
+    if (!kv.count("-in") || !kv.count("-in1") || !kv.count("-in2")) throw bank::Exception("Options '-in', '-in1' and '-in2' are mandatory");
+    const std::string dir = kv["-in"] + "/";
+    const uint64_t E = read_header(kv["-in1"]).n, N = read_header(kv["-in2"]).n, T = E + N;
+    auto load = [](const std::string &path, uint64_t rows, uint64_t cols) {
+        std::vector<float> m(rows * cols, 0.0f);  // a short file leaves zeros, like the reference's unchecked reads into zeroed rows
+        std::ifstream f(path.c_str(), std::ios::binary);
+        if (f) f.read((char *)m.data(), (std::streamsize)(m.size() * 4));
+        return m;
+    };
+    for (const std::string &name : stage::listdir(dir)) {
+        if (name.find("mat_") == std::string::npos || name.find(".bin") == std::string::npos || name.find(".temp") != std::string::npos) continue;
+        std::cout << name << std::endl;
+        const std::vector<float> ee = load(dir + name, E, E), en = load(dir + "/existingVsNew/" + name, E, N), nn = load(dir + "/newVsNew/" + name, N, N);
+        std::vector<float> out(T * T, 0.0f);
+        for (uint64_t i = 0; i < E; i++) {
+            for (uint64_t j = 0; j < E; j++) out[i * T + j] = ee[i * E + j];
+            for (uint64_t j = 0; j < N; j++) out[i * T + E + j] = out[(E + j) * T + i] = en[i * N + j];
+        }
+        for (uint64_t i = 0; i < N; i++)
+            for (uint64_t j = 0; j < N; j++) out[(E + i) * T + E + j] = nn[i * N + j];
+        const std::string tmp = dir + name + ".temp";
+        FILE *f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(out.data(), 4, out.size(), f) != out.size()) { if (f) fclose(f); throw bank::Exception("cannot write " + tmp); }
+        fclose(f);
+        if (rename(tmp.c_str(), (dir + name).c_str()) != 0) throw bank::Exception("cannot replace " + dir + name);
+    }
+    return EXIT_SUCCESS;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
     try {
-        if (argc < 2) { std::cout << "usage: simkaMinCore sketch|distance|export|append|info [options]" << std::endl; return EXIT_FAILURE; }
+        if (argc < 2) { std::cout << "usage: simkaMinCore sketch|distance|export|append|info|matrix-update [options]" << std::endl; return EXIT_FAILURE; }
         static const char *no_param[] = {"-filter", nullptr};
         auto kv = stage::parse_flags(argc - 1, argv + 1, no_param);
         const std::string cmd = argv[1];
@@ -264,7 +298,8 @@ int main(int argc, char **argv) {
         if (cmd == "export") return do_export(kv);
         if (cmd == "append") return do_append(kv);
         if (cmd == "info") return do_info(kv);
-        throw bank::Exception("unknown command '" + cmd + "' (sketch, distance, export, append, info)");
+        if (cmd == "matrix-update") return do_matrix_update(kv);
+        throw bank::Exception("unknown command '" + cmd + "' (sketch, distance, export, append, info, matrix-update)");
     } catch (const std::exception &e) {
         std::cout << "EXCEPTION: " << e.what() << std::endl;
         return EXIT_FAILURE;

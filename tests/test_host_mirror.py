@@ -233,3 +233,39 @@ def test_simkamincore_append_and_info(tmp_path):
     assert a.read_bytes() == want.read_bytes()
     r = subprocess.run([exe, "info", "-in", str(tmp_path / "missing.bin")], capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist" in r.stderr
+
+
+def test_simkamincore_matrix_update(tmp_path):
+    """matrix-update (hidden sub-command driven by simkaMin_update.py:149-152; SimkaMinDistanceMatrixMerger.hpp:87-127,
+    SimkaMinDistanceMatrixExporter.hpp:44-121): every mat_*.bin of -in grows from E x E to (E+N) x (E+N) with the blocks of
+    existingVsNew/ (E x N, also transposed into the bottom-left corner) and newVsNew/ (N x N); .temp files are skipped."""
+    exe = os.path.join(os.path.dirname(str(SIMKA_BIN)), "simkaMinCore")
+    rng = np.random.default_rng(5)
+    E, N = 3, 2
+    def sk(n, s=4):
+        return np.sort(rng.integers(1, 2**63, (n, s), dtype=np.uint64), axis=1), rng.integers(1, 9, (n, s), dtype=np.uint32)
+    _write_sketch_file(tmp_path / "old.bin", 21, 4, 100, ["a", "b", "c"], *sk(E))
+    _write_sketch_file(tmp_path / "new.bin", 21, 4, 100, ["d", "e"], *sk(N))
+    d = tmp_path / "dist"
+    (d / "existingVsNew").mkdir(parents=True)
+    (d / "newVsNew").mkdir()
+    want = {}
+    for name in ("mat_presenceAbsence_jaccard.bin", "mat_abundance_braycurtis.bin"):
+        ee, en, nn = (rng.random(sh).astype(np.float32) for sh in ((E, E), (E, N), (N, N)))
+        ee.tofile(d / name)
+        en.tofile(d / "existingVsNew" / name)
+        nn.tofile(d / "newVsNew" / name)
+        want[name] = np.block([[ee, en], [en.T, nn]])
+    (d / "mat_old.bin.temp").write_bytes(b"left alone")
+    (d / "notes.txt").write_text("left alone")
+    r = subprocess.run([exe, "matrix-update", "-in", str(d), "-in1", str(tmp_path / "old.bin"), "-in2", str(tmp_path / "new.bin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert sorted(r.stdout.split()) == sorted(want)
+    for name, m in want.items():
+        got = np.fromfile(d / name, dtype=np.float32).reshape(E + N, E + N)
+        assert np.array_equal(got, m)
+        assert not (d / (name + ".temp")).exists()
+    assert (d / "mat_old.bin.temp").read_bytes() == b"left alone"
+    r = subprocess.run([exe, "matrix-update", "-in", str(d), "-in1", str(tmp_path / "old.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "mandatory" in r.stdout
