@@ -269,3 +269,14 @@ def test_simkamincore_matrix_update(tmp_path):
     assert (d / "mat_old.bin.temp").read_bytes() == b"left alone"
     r = subprocess.run([exe, "matrix-update", "-in", str(d), "-in1", str(tmp_path / "old.bin")], capture_output=True, text=True)
     assert r.returncode == 1 and "mandatory" in r.stdout
+
+
+def test_minimizer_known_answers_testkmer():
+    """GT/unit/src/kmer/TestKmer.cpp:443-464 on the host model (ModelMinimizer<ModelCanonical>::getMinimizerValue)"""
+    from test_oracle_golden import TESTKMER_MINIMIZER3, TESTKMER_MINIMIZER3_SEQ, kmer_string
+    L = _lib.load()
+    km, valid = host_kmers(TESTKMER_MINIMIZER3_SEQ, 15)
+    assert valid.all() and len(km) == len(TESTKMER_MINIMIZER3)
+    for v, (kmer, mini) in zip(km.tolist(), TESTKMER_MINIMIZER3):
+        assert kmer_string(v, 15) == kmer
+        assert kmer_string(L.simka_host_minimizer(v, 15, 7), 7) == mini

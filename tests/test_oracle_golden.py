@@ -175,3 +175,46 @@ def test_murmur3_against_the_reference_source():
         ref = oracle.ref_murmur3_x64_128_u64(keys, seed)
         got = np.array([L.orc_murmur3_x64_128_u64(int(x), seed) for x in keys], dtype=np.uint64)
         np.testing.assert_array_equal(got, ref)
+
+
+# GT/unit/src/kmer/TestKmer.cpp:443-464 (kmer_minimizer3, ModelMinimizer<ModelCanonical>, k=15, m=7): canonical k-mer -> minimizer
+TESTKMER_MINIMIZER3_SEQ = b"ATGTCTGAAGTGACCTAACATTGCAGTGTGTT"
+TESTKMER_MINIMIZER3 = [
+    ("ATGTCTGAAGTGACC", "AAGTGAC"), ("AGGTCACTTCAGACA", "AAGTGAC"), ("TAGGTCACTTCAGAC", "AAGTGAC"), ("TCTGAAGTGACCTAA", "AAGTGAC"),
+    ("CTGAAGTGACCTAAC", "AAGTGAC"), ("TGAAGTGACCTAACA", "AAGTGAC"), ("ATGTTAGGTCACTTC", "AAGTGAC"), ("AATGTTAGGTCACTT", "AATGTTA"),
+    ("AGTGACCTAACATTG", "AACATTG"), ("GCAATGTTAGGTCAC", "AACATTG"), ("TGACCTAACATTGCA", "AACATTG"), ("CTGCAATGTTAGGTC", "AACATTG"),
+    ("ACCTAACATTGCAGT", "AACATTG"), ("CACTGCAATGTTAGG", "AACATTG"), ("ACACTGCAATGTTAG", "AACATTG"), ("CACACTGCAATGTTA", "AACATTG"),
+    ("AACATTGCAGTGTGT", "AACATTG"), ("AACACACTGCAATGT", "AACACAC"),
+]
+
+
+def kmer_string(v, k):
+    return "".join("ACTG"[(int(v) >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def test_minimizer_known_answers_testkmer():
+    """the reference's minimizer known-answer table: the canonical 15-mers of the sequence in order, and for each the minimizer
+    (smallest canonical 7-mer without an inner "AA") -- pins orc_minimizer and, through test_minimizer_matches_oracle, the host model"""
+    km, valid = oracle.canonical_kmers(TESTKMER_MINIMIZER3_SEQ, 15)
+    assert valid.all() and len(km) == len(TESTKMER_MINIMIZER3)
+    L = oracle.lib()
+    for v, (kmer, mini) in zip(km.tolist(), TESTKMER_MINIMIZER3):
+        assert kmer_string(v, 15) == kmer
+        assert kmer_string(L.orc_minimizer(v, 15, 7), 7) == mini
+
+
+def dsk_known_answers(golden_dir):
+    import json
+    d = json.load(open(os.path.join(golden_dir, "testdsk", "check1.json")))
+    return [(d["sequences"][r["seqs"]], r["k"], r["abundance_min"], r["nb_solid"]) for r in d["rows"]]
+
+
+def test_dsk_solid_counts_known_answers(golden_dir):
+    """gatb-core's DSK known answers (test/unit/src/kmer/TestDSK.cpp:147-240, 33 rows "computed with the original minia"):
+    number of distinct canonical k-mers with count >= abundance-min over a bank of literal sequences"""
+    for seqs, k, amin, want in dsk_known_answers(golden_dir):
+        run = oracle.Run.from_reads([[s.encode() for s in seqs]], k, abundance_min=amin, simple=False, complex_=False).count()
+        km, ct = run.sample(0)
+        assert len(km) == want == int(run.totals(0)[1]), (k, amin)
+        assert (ct >= amin).all()
+        run.close()
