@@ -26,3 +26,7 @@ def _built():
     b.build()
     from oracle import oracle
     oracle.build()
+    if os.environ.get("SIMKA_B200_EMU") == "1":
+        # developer switch: run the `-m gpu` tests against the kernel-logic emulator (tests/emu) on a machine without a GPU
+        from emu.emu_lib import use_emulator
+        use_emulator()

@@ -1,0 +1,220 @@
+"""Kernel LOGIC on the CPU: the CUDA sources of simka_b200/csrc compiled with g++ against tests/emu/cuda_runtime.h (CUDA threads
+stepped as cooperative fibers) and driven through the same C ABI and the same ctypes front end as the GPU tests, against
+the oracle and the reference's golden files, at sizes a CPU finishes in seconds.
+
+This is test infrastructure like the oracle -- not a CPU path of the product: the emulated library is built under
+tests/emu/_build, is loaded by this module only, and proves nothing about speed, memory ordering or races.  What it does
+catch without a GPU: index and bit arithmetic, bin geometry, the table protocols, the overflow / retry paths and their
+edge cases -- in every kernel the GPU tests launch.  The full `-m gpu` suite runs against it with `SIMKA_B200_EMU=1`
+(developer switch, tests/conftest.py); the tests here are its fast subset."""
+import os
+
+import numpy as np
+import pytest
+
+import simka_b200
+from emu.emu_lib import emulated
+from helpers import assert_stats_equal, nasty_samples, oracle_run, reads_to_arrays, synthetic_samples
+from oracle import oracle
+
+
+@pytest.fixture(autouse=True)
+def _emulated_library():
+    with emulated():
+        yield
+
+
+def small_samples(n, reads, **kw):
+    kw.setdefault("n_genomes", 6)
+    kw.setdefault("genome_len", 1500)
+    return synthetic_samples(n, reads, **kw)
+
+
+def test_emulated_library_is_not_the_product_library():
+    from simka_b200 import _lib
+    assert "tests/emu/_build" in _lib.load()._name
+    assert b"sm_100a" in _lib.load().simka_b200_version()  # same sources, same version string
+
+
+@pytest.mark.parametrize("k,t", [(21, 2), (31, 0)])
+def test_example_csv_byte_identical(golden_dir, k, t):
+    """the reference's end-to-end golden test (tests/simple_test.py:93-119) through the emulated kernels"""
+    from test_gpu_parity import load_example
+    ids, samples = load_example(golden_dir)
+    st = simka_b200.run_samples(samples, k, abundance_min=t, simple_dist=True, complex_dist=True)
+    tdir = os.path.join(golden_dir, "truth", f"results_k{k}_t{t}")
+    checked = 0
+    for m, name in enumerate(st.matrix_names()):
+        path = os.path.join(tdir, name + ".csv")
+        if os.path.exists(path):
+            assert st.csv(m, ids) == open(path).read(), name
+            checked += 1
+    assert checked == 20
+
+
+@pytest.mark.parametrize("k,amin", [(31, 2), (21, 1), (17, 2), (16, 1), (15, 2), (9, 0)])
+def test_per_sample_counts_and_stats(k, amin):
+    """k = 17 / 16 straddle the switch between the two extraction kernels, k <= 15 is the MiniKC rule"""
+    samples = small_samples(4, 250)
+    run = oracle_run(samples, k, amin)
+    st, ctx = simka_b200.run_samples(samples, k, abundance_min=amin, keep_ctx=True)
+    for s in range(len(samples)):
+        km, ct = ctx.dump_sample_counts(s)
+        okm, oct_ = run.sample(s)
+        np.testing.assert_array_equal(km, okm)
+        np.testing.assert_array_equal(ct, oct_)
+    assert ctx.timings()["kernel_launches"] > 0
+    ctx.close()
+    assert_stats_equal(st, run)
+
+
+@pytest.mark.parametrize("ascii_path", [False, True])
+def test_nasty_inputs(ascii_path):
+    samples = nasty_samples()
+    for k, amin, amax in [(31, 0, 999999999), (21, 1, 30), (15, 1, 999999999)]:
+        run = oracle_run(samples, k, amin, amax)
+        st = simka_b200.run_samples(samples, k, abundance_min=amin, abundance_max=amax, ascii_path=ascii_path)
+        assert_stats_equal(st, run)
+        assert st.matrix("mat_abundance_braycurtis")[1, 4] == 0.0
+
+
+@pytest.mark.parametrize("simple,complex_", [(False, False), (True, False), (False, True)])
+def test_distance_family_flags(simple, complex_):
+    samples = small_samples(3, 200)
+    run = oracle_run(samples, 25, 2, simple=simple, complex_=complex_)
+    st = simka_b200.run_samples(samples, 25, abundance_min=2, simple_dist=simple, complex_dist=complex_)
+    assert_stats_equal(st, run)
+
+
+def test_forced_exact_count_path(monkeypatch):
+    monkeypatch.setenv("SIMKA_B200_EXACT_COUNT", "1")
+    samples = small_samples(3, 300)
+    run = oracle_run(samples, 31, 2)
+    st = simka_b200.run_samples(samples, 31, abundance_min=2)
+    assert_stats_equal(st, run)
+
+
+def test_256_thread_extraction_kernel(monkeypatch):
+    monkeypatch.setenv("SIMKA_B200_K1", "256")
+    samples = small_samples(3, 300)
+    run = oracle_run(samples, 31, 2)
+    st = simka_b200.run_samples(samples, 31, abundance_min=2)
+    assert_stats_equal(st, run)
+
+
+def test_heavy_hitter_falls_back_to_exact_count():
+    """one k-mer far beyond a level-1 bucket's capacity: the single-pass extraction overflows and the sample is redone"""
+    rng = np.random.default_rng(11)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    g = alpha[rng.integers(0, 4, 3000)].tobytes()
+    normal = [g[i:i + 100] for i in rng.integers(0, 2900, 150)]
+    samples = [reads_to_arrays([b"A" * 150] * 1500 + normal), reads_to_arrays(normal + [b"ACGT" * 30] * 10)]
+    run = oracle_run(samples, 31, 2)
+    st, ctx = simka_b200.run_samples(samples, 31, abundance_min=2, keep_ctx=True)
+    t = ctx.timings()
+    ctx.close()
+    assert t["exact_retries"] >= 1
+    assert_stats_equal(st, run)
+
+
+def test_bin_with_more_distinct_keys_than_the_table(monkeypatch):
+    """expected_kmers_per_sample far below the truth makes few, large bins: the counting kernel's hash-selected sub-passes and
+    the merge's regrouping of the lists both run"""
+    samples = small_samples(3, 1500, n_genomes=24, genome_len=4000)
+    run = oracle_run(samples, 31, 1)
+    ctx = simka_b200.SimkaGpu(len(samples), 31, 1, simple_dist=True, complex_dist=True, expected_kmers_per_sample=3000)
+    for s, (seqs, off) in enumerate(samples):
+        p, b, nw = simka_b200.pack_reads(seqs, off)
+        ctx.push_reads(s, p, b, nw, len(off) - 1)
+        ctx.finish_sample(s)
+    ctx.merge_and_accumulate()
+    st = ctx.stats()
+    ctx.close()
+    assert_stats_equal(st, run)
+
+
+@pytest.mark.parametrize("n,variant", [(70, None), (70, "tiled"), (40, "generic"), (40, None)])
+def test_many_samples_merge_paths(monkeypatch, n, variant):
+    """N > 64 takes the global-atomics merge (or the tiled one), N <= 64 the shared-memory-accumulator merge"""
+    if variant:
+        monkeypatch.setenv("SIMKA_B200_MERGE", variant)
+    samples = synthetic_samples(n, 40, read_len=80, n_genomes=3, genome_len=600)
+    run = oracle_run(samples, 21, 2)
+    st = simka_b200.run_samples(samples, 21, abundance_min=2)
+    assert_stats_equal(st, run)
+
+
+def test_shards_sum_to_whole():
+    samples = small_samples(4, 300)
+    run = oracle_run(samples, 31, 2)
+    S = 3
+    ctxs = [simka_b200.SimkaGpu(len(samples), 31, 2, simple_dist=True, complex_dist=True, shard_rank=r, shard_count=S) for r in range(S)]
+    for c in ctxs:
+        for s, (seqs, off) in enumerate(samples):
+            p, b, nw = simka_b200.pack_reads(seqs, off)
+            c.push_reads(s, p, b, nw, len(off) - 1)
+            c.finish_sample(s)
+    tot = sum(c.get_totals() for c in ctxs)
+    tot[:, 0] = ctxs[0].get_totals()[:, 0]
+    total = None
+    for c in ctxs:
+        c.set_totals(tot)
+        c.merge_and_accumulate()
+        st = c.stats()
+        total = st if total is None else total.__iadd__(st)
+        c.close()
+    assert_stats_equal(total, run)
+
+
+def test_import_counts_equals_counting():
+    samples = small_samples(3, 300)
+    run = oracle_run(samples, 31, 2)
+    ctx = simka_b200.SimkaGpu(len(samples), 31, 2, simple_dist=True, complex_dist=True)
+    for s in range(len(samples)):
+        km, ct = run.sample(s)
+        perm = np.random.default_rng(s).permutation(len(km))
+        ctx.import_counts(s, km[perm], ct[perm], nb_reads=300)
+    ctx.merge_and_accumulate()
+    st = ctx.stats()
+    ctx.close()
+    assert_stats_equal(st, run)
+
+
+def test_dsk_known_answers(golden_dir):
+    """gatb-core's DSK known answers (test/unit/src/kmer/TestDSK.cpp:147-240) through the emulated counting kernels"""
+    from test_oracle_golden import dsk_known_answers
+    for seqs, k, amin, want in dsk_known_answers(golden_dir):
+        sample = reads_to_arrays([s.encode() for s in seqs])
+        st, ctx = simka_b200.run_samples([sample, sample], k, abundance_min=amin, keep_ctx=True)
+        for s in (0, 1):
+            km, ct = ctx.dump_sample_counts(s)
+            assert len(km) == want, (k, amin, s)
+            assert (ct >= amin).all() and (km[1:] > km[:-1]).all()
+        ctx.close()
+        assert int(st.distinct_shared[1]) == want
+
+
+def test_simkamin_distance():
+    from simka_b200 import synth
+    hashes, counts = synth.make_sketches(6, 4000)
+    hashes[3, :700] = 0  # a short sketch: zero padding at the front
+    counts[3, :700] = 0
+    jac, bc, _ = simka_b200.simkamin_distance(hashes, counts)
+    ojac, obc = oracle.simkamin_distance(hashes, counts)
+    np.testing.assert_array_equal(jac, ojac)
+    np.testing.assert_array_equal(bc, obc)
+
+
+@pytest.mark.parametrize("k,max_reads,nb_kmers,filt", [(21, 0, 100, False), (31, 100, 1000, True)])
+def test_simkamin_sketch_reproduces_reference_truth(golden_dir, k, max_reads, nb_kmers, filt):
+    from test_oracle_golden import simkamin_csv, simkamin_example_sketches
+    ids, gh, gc = simkamin_example_sketches(golden_dir, k, max_reads, nb_kmers,
+                                            lambda s, o, kk, n: simka_b200.simkamin_sketch(s, o, kk, n, seed=100, filter=filt))
+    _, oh, oc = simkamin_example_sketches(golden_dir, k, max_reads, nb_kmers,
+                                          lambda s, o, kk, n: oracle.simkamin_sketch(s, o, kk, n, seed=100, filter=filt))
+    np.testing.assert_array_equal(gh, oh)
+    np.testing.assert_array_equal(gc, oc)
+    jac, bc, _ = simka_b200.simkamin_distance(gh, gc)
+    tdir = os.path.join(golden_dir, "truth_simkaMin", f"k{k}_{'filter' if filt else ''}_{max_reads}-{nb_kmers}_n1")
+    assert simkamin_csv(ids, jac) == open(os.path.join(tdir, "mat_presenceAbsence_jaccard.csv")).read()
+    assert simkamin_csv(ids, bc) == open(os.path.join(tdir, "mat_abundance_braycurtis.csv")).read()
