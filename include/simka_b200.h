@@ -174,6 +174,9 @@ typedef struct {
     uint64_t pairs;                             /* sample pairs enumerated by the accumulate kernel           */
     uint64_t kernel_launches;
     uint64_t exact_retries;                     /* samples redone with the exact two-pass K1 (a bucket overflowed)  */
+    uint64_t superk_samples;                    /* samples counted through the experimental super-k-mer front end
+                                                 * (SIMKA_B200_SUPERK=1; 0 on the default path)                      */
+    uint64_t superk_fallbacks;                  /* ... that overflowed the record list and were redone per k-mer    */
 } simka_timings;
 int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out);
 /* the CUDA stream all of this context's kernels run on (for external CUDA-event timing) */

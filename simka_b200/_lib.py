@@ -38,7 +38,8 @@ class Timings(C.Structure):
                 ("part_scatter_ms", C.c_float), ("bin_count_ms", C.c_float), ("compact_ms", C.c_float),
                 ("merge_ms", C.c_float), ("samples_ms", C.c_float), ("total_ms", C.c_float),
                 ("kmers_in", C.c_uint64), ("entries", C.c_uint64), ("distinct_kmers", C.c_uint64),
-                ("pairs", C.c_uint64), ("kernel_launches", C.c_uint64), ("exact_retries", C.c_uint64)]
+                ("pairs", C.c_uint64), ("kernel_launches", C.c_uint64), ("exact_retries", C.c_uint64),
+                ("superk_samples", C.c_uint64), ("superk_fallbacks", C.c_uint64)]
 
 
 # every symbol include/simka_b200.h declares: (restype, argtypes)

@@ -44,6 +44,7 @@ namespace {
 
 #include "kernels/common.cuh"
 #include "kernels/stage1.cuh"
+#include "kernels/superk.cuh"
 #include "kernels/merge.cuh"
 #include "kernels/simkamin.cuh"
 
@@ -149,7 +150,10 @@ struct simka_ctx {
     unsigned long long scan_epoch = 0;
     bool use_k16 = true;        // SIMKA_B200_K1=256: the 256-thread x 32-position extraction kernel
     bool force_exact = false;   // SIMKA_B200_EXACT_COUNT=1: always run the K1 count pass (tests of the fallback)
-    uint64_t exact_retries = 0;
+    bool use_superk = false;    // SIMKA_B200_SUPERK=1: experimental super-k-mer front end of stage 1 (kernels/superk.cuh)
+    uint64_t exact_retries = 0, superk_samples = 0, superk_fallbacks = 0;
+    uint64_t superk_cap_override = 0;
+    DevBuf d_sk_tmpc;
     float stage_ms[T_NSTAGE] = {};
     float sample_ms = 0, merge_ms = 0;
     uint64_t kmers_in = 0, entries = 0;
@@ -270,6 +274,8 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
     { const char *e = getenv("SIMKA_B200_K1"); ctx->use_k16 = !(e && !strcmp(e, "256")); }
     { const char *e = getenv("SIMKA_B200_B1BITS"); ctx->b1_override = e ? atoi(e) : 0; }
     { const char *e = getenv("SIMKA_B200_REFINE"); ctx->no_refine = e && e[0] == '0'; }
+    { const char *e = getenv("SIMKA_B200_SUPERK"); ctx->use_superk = e && e[0] == '1'; }
+    { const char *e = getenv("SIMKA_B200_SUPERK_CAP"); ctx->superk_cap_override = e ? strtoull(e, nullptr, 10) : 0; }  // tests of the fallback
     cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
     ctx->samples.resize(p->nb_samples);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -328,7 +334,7 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
                       &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
                       &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
-                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum};
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum, &ctx->d_sk_tmpc};
     for (DevBuf *b : bufs) b->release();
     for (auto &set : ctx->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
@@ -478,13 +484,15 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
     int *d_overflow = reinterpret_cast<int *>(ctx->d_small.as<char>() + 44);
     uint64_t h_keys = 0, h_surv = 0;
     ull h_tot[3] = {0, 0, 0};
+    bool sk_used = false;
 
     if (n_words > 0) {
+        const size_t nres = std::max<size_t>(nbins, (size_t)1 << ctx->fg_bits);  // (super-k-mer mode reuses these for the fine ranges)
         bool okm = !ctx->d_keysA.reserve(n_pos * 8) && !ctx->d_keysB.reserve(n_pos * 8) && !ctx->d_stage_c.reserve(n_pos * 4) &&
                    !ctx->d_hist1.reserve(MAX_B * 4) && !ctx->d_base1.reserve((MAX_B + 1) * 8) && !ctx->d_cursor1.reserve(MAX_B * 4) &&
                    !ctx->d_tiles.reserve(MAX_B * 4) && !ctx->d_tile_start.reserve((MAX_B + 1) * 8) &&
-                   !ctx->d_fine_hist.reserve((size_t)nbins * 4) && !ctx->d_fine_off.reserve(((size_t)nbins + 1) * 8) &&
-                   !ctx->d_fine_cursor.reserve((size_t)nbins * 4) && !ctx->d_surv.reserve((size_t)nbins * 4) &&
+                   !ctx->d_fine_hist.reserve(nres * 4) && !ctx->d_fine_off.reserve((nres + 1) * 8) &&
+                   !ctx->d_fine_cursor.reserve(nres * 4) && !ctx->d_surv.reserve((size_t)nbins * 4) &&
                    !ctx->d_out_off.reserve(((size_t)nbins + 1) * 8);
         if (!okm) { ctx->set_error("out of device memory (work buffers)"); return SIMKA_ERR_NOMEM; }
         CK(cudaStreamWaitEvent(st, sl->copied, 0));
@@ -492,9 +500,14 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         harvest_timings(ctx, evset);  // the sample before the previous one: long finished
         cudaEvent_t *ev = ctx->ev[evset];
         CK(cudaEventRecord(ev[2 * T_NSTAGE], st));  // sample start
-      for (int attempt = 0; attempt < 2; attempt++) {
+      // experimental front end (SIMKA_B200_SUPERK=1): super-k-mer records instead of the two k-mer partition levels
+      const bool sk_eligible = ctx->use_superk && !ctx->kp.key_mode && ctx->kp.shard_count <= 1 && ctx->kp.k >= SK_MINK && ctx->kp.k <= 31 &&
+                               !ctx->force_exact;
+      for (int attempt = sk_eligible ? -1 : 0; attempt < 2; attempt++) {
+        // attempt -1 (super-k-mer mode only): records; falls back to attempt 0 when the record list overflows.
         // attempt 0: single pass over the reads into fixed-capacity L1 buckets (sizes are binomial for hashed
         // keys); attempt 1 (only after an overflow, e.g. one k-mer repeated millions of times): exact count pass first
+        const bool sk = attempt < 0;
         const bool exact = attempt == 1 || ctx->force_exact;
         const uint64_t per_bucket = n_pos / nb1;
         const uint64_t cap = per_bucket + 8 * (uint64_t)sqrt((double)per_bucket) + 1024;
@@ -509,6 +522,28 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         const unsigned g1 = (unsigned)((n_words + BLOCK - 1) / BLOCK);
         const uint64_t *seq = sl->ext_packed ? sl->ext_packed : sl->packed.as<uint64_t>();
         const uint32_t *bad = sl->ext_bad ? sl->ext_bad : sl->bad.as<uint32_t>();
+        if (sk) {
+            // K1': reads -> unsorted super-k-mer records (in d_keysA) + k-mers per bin; K2': records -> keys grouped by bin
+            ull *d_nrec = reinterpret_cast<ull *>(ctx->d_small.as<char>() + 48);
+            uint64_t rec_cap = n_pos / 2;  // d_keysA holds n_pos * 8 bytes
+            if (ctx->superk_cap_override) rec_cap = std::min<uint64_t>(rec_cap, ctx->superk_cap_override);
+            CK(cudaMemsetAsync(d_nrec, 0, 8, st));
+            CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
+            CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT + 1], st));
+            CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER], st));
+            superk_scan_instance(ctx->kp.k)<<<(unsigned)((n_words + SK_THREADS - 1) / SK_THREADS), SK_THREADS, 0, st>>>(
+                seq, bad, n_words, bin_bits, ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->d_fine_hist.as<uint32_t>(), d_overflow);
+            CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER + 1], st));
+            CK(cudaEventRecord(ev[2 * T_PART_COUNT], st));
+            CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
+            launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), nbins);
+            CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
+            k_superk_expand<<<(unsigned)std::min<uint64_t>((rec_cap + BLOCK - 1) / BLOCK, (uint64_t)ctx->nsm * 16), BLOCK, 0, st>>>(
+                ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->kp, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(),
+                ctx->d_keysB.as<uint64_t>());
+            CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
+            ctx->launches += 3;
+        } else {
         // K1 (count / scan /) scatter
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
         if (exact) {
@@ -537,6 +572,8 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         k_partition2<false><<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), cnt1, ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
                                                   nullptr, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), ctx->d_keysB.as<uint64_t>());
         CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
+        ctx->launches += 6;
+        }
         // K3 count
         CountOut co;
         co.stage_h = ctx->d_keysA.as<uint64_t>();
@@ -549,13 +586,14 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             if (ctx->occ_bin_count <= 0) ctx->occ_bin_count = 1;
         }
         const unsigned gbin = (unsigned)std::min<uint64_t>(nbins, (uint64_t)ctx->nsm * ctx->occ_bin_count);
-        const int slot_shift = std::max(0, W - bin_bits - ilog2_floor(CNT_SLOTS));  // table slot: the bits just below the bin bits
+        // table slot: the bits just below the bin bits (super-k-mer mode: bins are not key ranges, take the top bits)
+        const int slot_shift = std::max(0, W - (sk ? 0 : bin_bits) - ilog2_floor(CNT_SLOTS));
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
         k_bin_count<<<gbin, K3_BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins, slot_shift, ctx->prm.abundance_min,
                                             ctx->prm.abundance_max, co);
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT + 1], st));
         launch_scan(ctx, ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins);
-        ctx->launches += 9;
+        ctx->launches += 3;
         CK(cudaGetLastError());
         // the only host sync of the sample: sizes + totals
         int h_err = 0, h_overflow = 0;
@@ -565,7 +603,9 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         CK(cudaMemcpyAsync(&h_err, d_error, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (h_overflow && sk) { ctx->superk_fallbacks++; continue; }  // more runs than the record list holds: redo on the k-mer path
         if (h_overflow && !exact) { ctx->exact_retries++; continue; }  // a bucket outgrew its capacity: redo with the exact two-pass path
+        sk_used = sk;
         if (h_err) { ctx->set_error("on-chip table overflow in k_bin_count (code " + std::to_string(h_err) + ")"); return SIMKA_ERR_OVERFLOW; }
         break;
       }
@@ -577,9 +617,33 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             sd.eh = (uint64_t *)ctx->arena.alloc(h_surv * 8);
             sd.ec = (uint32_t *)ctx->arena.alloc(h_surv * 4);
             if (!sd.eh || !sd.ec) { ctx->set_error("out of device memory (sample list)"); return SIMKA_ERR_NOMEM; }
+            // super-k-mer mode: the bins are minimizer bins, so the survivors are first packed into scratch (the key buffer K3
+            // has finished reading) and then counting-sorted by fine range of the key into the sample's list
+            uint64_t *pack_h = sd.eh;
+            uint32_t *pack_c = sd.ec;
+            if (sk_used) {
+                if (ctx->d_sk_tmpc.reserve(h_surv * 4)) { ctx->set_error("out of device memory (work buffers)"); return SIMKA_ERR_NOMEM; }
+                pack_h = ctx->d_keysB.as<uint64_t>();
+                pack_c = ctx->d_sk_tmpc.as<uint32_t>();
+            }
             k_compact<<<(unsigned)std::min<uint64_t>((nbins + 7) / 8, (uint64_t)ctx->nsm * 8), BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(),
-                                             ctx->d_out_off.as<uint64_t>(), nbins, sd.eh, sd.ec);
+                                             ctx->d_out_off.as<uint64_t>(), nbins, pack_h, pack_c);
             ctx->launches++;
+            if (sk_used) {
+                const size_t fgn1 = (size_t)1 << ctx->fg_bits;
+                if (ctx->d_fine_hist.reserve(fgn1 * 4) || ctx->d_fine_cursor.reserve(fgn1 * 4) || ctx->d_fine_off.reserve((fgn1 + 1) * 8)) {
+                    ctx->set_error("out of device memory (work buffers)");
+                    return SIMKA_ERR_NOMEM;
+                }
+                CK(cudaMemsetAsync(ctx->d_fine_hist.p, 0, fgn1 * 4, st));
+                CK(cudaMemsetAsync(ctx->d_fine_cursor.p, 0, fgn1 * 4, st));
+                const unsigned g = (unsigned)std::min<uint64_t>((h_surv + BLOCK - 1) / BLOCK, (uint64_t)ctx->nsm * 16);
+                const int shift = W - ctx->fg_bits;
+                k_refine_hist<<<g, BLOCK, 0, st>>>(pack_h, h_surv, shift, ctx->d_fine_hist.as<uint32_t>());
+                launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), fgn1);
+                k_refine_scatter<<<g, BLOCK, 0, st>>>(pack_h, pack_c, h_surv, shift, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), sd.eh, sd.ec);
+                ctx->launches += 3;
+            }
             if (ctx->prm.complex_dist) {
                 const unsigned gh = (unsigned)std::min<uint64_t>((h_surv + BLOCK * 16 - 1) / (BLOCK * 16), (uint64_t)ctx->nsm * 4);
                 k_abundance_hist<<<gh, BLOCK, 0, st>>>(sd.ec, h_surv, sample_id, ctx->d_chist.as<ull>() + (size_t)sample_id * CHIST,
@@ -588,7 +652,14 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             }
         }
         const uint32_t fg = 1u << ctx->fg_bits;
-        k_fill_offsets<<<(fg + 1 + 255) / 256, 256, 0, st>>>(ctx->d_out_off.as<uint64_t>(), sd.off, fg, nbins >> ctx->fg_bits);
+        if (sk_used) {
+            // offsets of the fine ranges: the scan of the regrouping above (all zero for a sample without solid k-mers)
+            if (h_surv > 0) k_fill_offsets<<<(fg + 1 + 255) / 256, 256, 0, st>>>(ctx->d_fine_off.as<uint64_t>(), sd.off, fg, 1);
+            else CK(cudaMemsetAsync(sd.off, 0, ((size_t)fg + 1) * 4, st));
+            ctx->superk_samples++;
+        } else {
+            k_fill_offsets<<<(fg + 1 + 255) / 256, 256, 0, st>>>(ctx->d_out_off.as<uint64_t>(), sd.off, fg, nbins >> ctx->fg_bits);
+        }
         ctx->launches++;
         CK(cudaEventRecord(ev[2 * T_COMPACT + 1], st));
         CK(cudaEventRecord(ev[2 * T_NSTAGE + 1], st));  // sample end; no host wait: the next sample's kernels queue right behind
@@ -1051,6 +1122,8 @@ int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
     t.entries = ctx->entries;
     t.kernel_launches = ctx->launches;
     t.exact_retries = ctx->exact_retries;
+    t.superk_samples = ctx->superk_samples;
+    t.superk_fallbacks = ctx->superk_fallbacks;
     if (ctx->merged && ctx->a_scalars) {
         ull sc[4];
         if (cudaMemcpy(sc, ctx->a_scalars, 32, cudaMemcpyDeviceToHost) == cudaSuccess) { t.distinct_kmers = sc[0]; t.pairs = sc[2]; }

@@ -218,3 +218,101 @@ def test_simkamin_sketch_reproduces_reference_truth(golden_dir, k, max_reads, nb
     tdir = os.path.join(golden_dir, "truth_simkaMin", f"k{k}_{'filter' if filt else ''}_{max_reads}-{nb_kmers}_n1")
     assert simkamin_csv(ids, jac) == open(os.path.join(tdir, "mat_presenceAbsence_jaccard.csv")).read()
     assert simkamin_csv(ids, bc) == open(os.path.join(tdir, "mat_abundance_braycurtis.csv")).read()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# experimental super-k-mer front end of stage 1 (SIMKA_B200_SUPERK=1, simka_b200/csrc/kernels/superk.cuh)
+# ---------------------------------------------------------------------------------------------------------------
+def run_superk(samples, k, amin, amax=999999999, expect_fallbacks=None, **kw):
+    st, ctx = simka_b200.run_samples(samples, k, abundance_min=amin, abundance_max=amax, keep_ctx=True, **kw)
+    t = ctx.timings()
+    assert t["superk_samples"] + t["superk_fallbacks"] == sum(1 for s, o in samples if len(s) > 0)
+    if expect_fallbacks is not None:
+        assert t["superk_fallbacks"] == expect_fallbacks
+    return st, ctx
+
+
+@pytest.mark.parametrize("k,amin", [(31, 2), (30, 1), (26, 2), (21, 1), (18, 2), (17, 0)])
+def test_superk_per_sample_counts_and_stats(monkeypatch, k, amin):
+    monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
+    samples = small_samples(4, 250)
+    run = oracle_run(samples, k, amin)
+    st, ctx = run_superk(samples, k, amin, expect_fallbacks=0)
+    for s in range(len(samples)):
+        km, ct = ctx.dump_sample_counts(s)
+        okm, oct_ = run.sample(s)
+        np.testing.assert_array_equal(km, okm)
+        np.testing.assert_array_equal(ct, oct_)
+    ctx.close()
+    assert_stats_equal(st, run)
+
+
+def test_superk_is_off_by_default_and_below_k17(monkeypatch):
+    samples = small_samples(2, 100)
+    st, ctx = simka_b200.run_samples(samples, 31, abundance_min=1, keep_ctx=True)
+    assert ctx.timings()["superk_samples"] == 0
+    ctx.close()
+    monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
+    st, ctx = simka_b200.run_samples(samples, 16, abundance_min=1, keep_ctx=True)
+    assert ctx.timings()["superk_samples"] == 0
+    ctx.close()
+    assert_stats_equal(st, oracle_run(samples, 16, 1))
+
+
+@pytest.mark.parametrize("ascii_path", [False, True])
+def test_superk_nasty_inputs(monkeypatch, ascii_path):
+    """N runs, reads shorter than k, lowercase, empty reads and an empty sample, low-complexity repeats (runs at the record
+    capacity), a duplicated sample"""
+    monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
+    samples = nasty_samples()
+    for k, amin, amax in [(31, 0, 999999999), (21, 1, 30), (17, 2, 999999999)]:
+        run = oracle_run(samples, k, amin, amax)
+        st, ctx = run_superk(samples, k, amin, amax, ascii_path=ascii_path)
+        ctx.close()
+        assert_stats_equal(st, run)
+        assert st.matrix("mat_abundance_braycurtis")[1, 4] == 0.0
+
+
+def test_superk_example_csv_byte_identical(monkeypatch, golden_dir):
+    monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
+    from test_gpu_parity import load_example
+    ids, samples = load_example(golden_dir)
+    for k, t in ((21, 0), (31, 2)):
+        st, ctx = run_superk(samples, k, t, expect_fallbacks=0)
+        ctx.close()
+        tdir = os.path.join(golden_dir, "truth", f"results_k{k}_t{t}")
+        for m, name in enumerate(st.matrix_names()):
+            path = os.path.join(tdir, name + ".csv")
+            if os.path.exists(path):
+                assert st.csv(m, ids) == open(path).read(), name
+
+
+def test_superk_record_list_overflow_falls_back(monkeypatch):
+    monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
+    monkeypatch.setenv("SIMKA_B200_SUPERK_CAP", "50")
+    samples = small_samples(3, 200)
+    run = oracle_run(samples, 31, 2)
+    st, ctx = run_superk(samples, 31, 2, expect_fallbacks=3)
+    ctx.close()
+    assert_stats_equal(st, run)
+
+
+def test_superk_large_bins_and_many_samples(monkeypatch):
+    """few, large minimizer bins (sub-passes of the counting kernel) and the N > 64 merge behind the regrouped lists"""
+    monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
+    samples = small_samples(3, 1500, n_genomes=24, genome_len=4000)
+    run = oracle_run(samples, 31, 1)
+    ctx = simka_b200.SimkaGpu(len(samples), 31, 1, simple_dist=True, complex_dist=True, expected_kmers_per_sample=3000)
+    for s, (seqs, off) in enumerate(samples):
+        p, b, nw = simka_b200.pack_reads(seqs, off)
+        ctx.push_reads(s, p, b, nw, len(off) - 1)
+        ctx.finish_sample(s)
+    ctx.merge_and_accumulate()
+    st = ctx.stats()
+    assert ctx.timings()["superk_samples"] == 3
+    ctx.close()
+    assert_stats_equal(st, run)
+    samples = synthetic_samples(70, 40, read_len=80, n_genomes=3, genome_len=600)
+    st, ctx = run_superk(samples, 21, 2, expect_fallbacks=0)
+    ctx.close()
+    assert_stats_equal(st, oracle_run(samples, 21, 2))
