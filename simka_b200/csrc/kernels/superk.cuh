@@ -11,22 +11,29 @@
 //   k_superk_scan<K>   thread = one packed word = 32 start positions.  Canonical m-mers (m = 13) rolled through registers and
 //                      hashed (a bijection on 32 bits, so ties are identical m-mers); minimizer VALUE of every k-mer = sliding
 //                      minimum over its K-m+1 m-mers by block prefix / suffix minima (van Herk), all indices static.  A k-mer's
-//                      bin is a function of that value alone, hence of the canonical k-mer (both strands see the same set of
-//                      canonical m-mers): every occurrence of a k-mer lands in the same bin, which is all exact counting needs.
-//                      Runs = consecutive valid k-mers of the word with equal bin (cut at the word boundary and at the record
-//                      capacity); each run is appended to an unsorted record list (one atomic per warp round) and adds its
-//                      k-mer count to the bin histogram (one atomic per run).
-//   k_superk_expand    thread = one record: reserves its k-mers' slots in the bin (one atomic), rolls the canonical k-mers
-//                      out of the record, mixes them and writes the keys -- the layout k_bin_count reads today.
+//                      MICRO-BIN (up to 2^21 of them) is a function of that value alone, hence of the canonical k-mer (both
+//                      strands see the same set of canonical m-mers): every occurrence of a k-mer lands in the same micro-bin,
+//                      which is all exact counting needs.  Runs = consecutive valid k-mers of the word with equal micro-bin (cut
+//                      at the word boundary and at the record capacity); each run is appended to an unsorted record list (one
+//                      atomic per warp round) and adds its k-mer count to the micro-bin histogram (one atomic per run).
+//   k_superk_bins      minimizer frequencies follow the coverage of the genomes they come from (bins of a fixed hash range came
+//                      out at 916 +- 703 keys on the bench workload, tools/superk_balance.py), so the counting bins are cut
+//                      per sample from the scanned histogram, as the reference balances its partitions from sampled minimizer
+//                      frequencies (Repartitor::computeDistrib, GC/kmer/impl/PartiInfo.cpp:48-105): a bin = the consecutive
+//                      micro-bins whose first key falls into the same multiple of SK_TARGET keys.
+//   k_superk_expand    thread = one record: reserves its k-mers' slots in the micro-bin (one atomic), rolls the canonical
+//                      k-mers out of the record, mixes them and writes the keys -- the layout k_bin_count reads today.
 //
 // Record (128 bits): bases of the run, first base most significant, in the top 102 bits (<= 51 bases = k-mers + K - 1),
-// then 5 bits (k-mers - 1), then 21 bits of bin id.
+// then 5 bits (k-mers - 1), then 21 bits of micro-bin id.
 #pragma once
 
 constexpr int SK_M = 13;          // minimizer length
 constexpr int SK_MAXB = 51;       // bases a record holds
 constexpr int SK_MINK = 17;       // smallest k of this path (window of >= 5 m-mers)
 constexpr int SK_THREADS = 256;
+constexpr int SK_MAXMICRO = 21;   // micro-bin id bits a record can carry
+constexpr int SK_TARGET = 896;    // keys per counting bin (+ the micro-bin that crosses the mark)
 
 struct __align__(16) SkRecord { uint64_t hi, lo; };
 
@@ -172,10 +179,24 @@ static superk_scan_fn superk_scan_instance(int k) {
     return (k >= SK_MINK && k <= 31) ? tab[k - SK_MINK] : nullptr;
 }
 
-// records -> mixed canonical k-mers, written where k_bin_count expects the keys of the record's bin
+// fine_off[b] = first key of counting bin b = prefix[u] of the first micro-bin u with prefix[u] >= b * SK_TARGET (b <= nb; bins
+// past the last key are empty).  Thread u fills the bins that begin at micro-bin u; thread n_micro fills the tail.
+__global__ void __launch_bounds__(BLOCK)
+k_superk_bins(const uint64_t *__restrict__ prefix /*[n_micro + 1]*/, uint32_t n_micro, uint64_t *__restrict__ fine_off, uint32_t nb) {
+    const uint32_t u = blockIdx.x * BLOCK + threadIdx.x;
+    if (u > n_micro) return;
+    const uint64_t here = prefix[u];
+    // bins whose mark b * SK_TARGET lies in (prefix[u - 1], prefix[u]]  (u = 0: bin 0)
+    uint64_t b_lo = u ? prefix[u - 1] / SK_TARGET + 1 : 0;
+    uint64_t b_hi = u == n_micro ? (uint64_t)nb : here / SK_TARGET;
+    if (u == n_micro) b_lo = (n_micro ? prefix[n_micro - 1] / SK_TARGET + 1 : 0);
+    for (uint64_t b = b_lo; b <= b_hi && b <= nb; b++) fine_off[b] = here;
+}
+
+// records -> mixed canonical k-mers, written where k_bin_count expects the keys of the record's micro-bin
 __global__ void __launch_bounds__(BLOCK)
 k_superk_expand(const SkRecord *__restrict__ records, const ull *__restrict__ n_records, uint64_t cap, KParams kp,
-                const uint64_t *__restrict__ fine_off, uint32_t *__restrict__ fine_cursor, uint64_t *__restrict__ keys_out) {
+                const uint64_t *__restrict__ micro_off, uint32_t *__restrict__ micro_cursor, uint64_t *__restrict__ keys_out) {
     const ull nr = *n_records < cap ? *n_records : cap;
     const int k = kp.k;
     const uint64_t kmask = kp.mix.mask;
@@ -183,7 +204,7 @@ k_superk_expand(const SkRecord *__restrict__ records, const ull *__restrict__ n_
         const SkRecord rec = records[r];
         const uint32_t bin = (uint32_t)rec.lo & 0x1FFFFFu;
         const uint32_t n = ((uint32_t)(rec.lo >> 21) & 31u) + 1;
-        uint64_t pos = fine_off[bin] + atomicAdd(&fine_cursor[bin], n);
+        uint64_t pos = micro_off[bin] + atomicAdd(&micro_cursor[bin], n);
         uint64_t fwd = rec.hi >> (64 - 2 * k);
         uint64_t rev = simka::revcomp(fwd, k);
         keys_out[pos] = simka::mix_fwd(fwd < rev ? fwd : rev, kp.mix);

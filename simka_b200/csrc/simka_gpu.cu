@@ -153,7 +153,7 @@ struct simka_ctx {
     bool use_superk = false;    // SIMKA_B200_SUPERK=1: experimental super-k-mer front end of stage 1 (kernels/superk.cuh)
     uint64_t exact_retries = 0, superk_samples = 0, superk_fallbacks = 0;
     uint64_t superk_cap_override = 0;
-    DevBuf d_sk_tmpc;
+    DevBuf d_sk_tmpc, d_sk_prefix;
     float stage_ms[T_NSTAGE] = {};
     float sample_ms = 0, merge_ms = 0;
     uint64_t kmers_in = 0, entries = 0;
@@ -334,7 +334,7 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
                       &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
                       &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
-                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum, &ctx->d_sk_tmpc};
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum, &ctx->d_sk_tmpc, &ctx->d_sk_prefix};
     for (DevBuf *b : bufs) b->release();
     for (auto &set : ctx->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
@@ -485,15 +485,21 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
     uint64_t h_keys = 0, h_surv = 0;
     ull h_tot[3] = {0, 0, 0};
     bool sk_used = false;
+    uint32_t nbins_fin = 0;  // bins of the attempt that succeeded
 
     if (n_words > 0) {
-        const size_t nres = std::max<size_t>(nbins, (size_t)1 << ctx->fg_bits);  // (super-k-mer mode reuses these for the fine ranges)
+        // super-k-mer mode: micro-bins of ~48 positions (at most 2^21), counting bins cut from their histogram
+        const int micro_bits = std::min(SK_MAXMICRO, std::max(8, ilog2_floor(std::max<uint64_t>(1, n_pos / 48))));
+        const uint32_t n_micro = 1u << micro_bits;
+        const uint32_t nb_sk = (uint32_t)std::min<uint64_t>(n_pos / SK_TARGET + 2, 0x7FFFFFFFull);
+        const size_t nres = std::max<size_t>(std::max<size_t>(nbins, (size_t)1 << ctx->fg_bits),
+                                             ctx->use_superk ? std::max<size_t>(n_micro, (size_t)nb_sk + 1) : 0);
         bool okm = !ctx->d_keysA.reserve(n_pos * 8) && !ctx->d_keysB.reserve(n_pos * 8) && !ctx->d_stage_c.reserve(n_pos * 4) &&
                    !ctx->d_hist1.reserve(MAX_B * 4) && !ctx->d_base1.reserve((MAX_B + 1) * 8) && !ctx->d_cursor1.reserve(MAX_B * 4) &&
                    !ctx->d_tiles.reserve(MAX_B * 4) && !ctx->d_tile_start.reserve((MAX_B + 1) * 8) &&
                    !ctx->d_fine_hist.reserve(nres * 4) && !ctx->d_fine_off.reserve((nres + 1) * 8) &&
-                   !ctx->d_fine_cursor.reserve(nres * 4) && !ctx->d_surv.reserve((size_t)nbins * 4) &&
-                   !ctx->d_out_off.reserve(((size_t)nbins + 1) * 8);
+                   !ctx->d_fine_cursor.reserve(nres * 4) && !ctx->d_surv.reserve(nres * 4) &&
+                   !ctx->d_out_off.reserve((nres + 1) * 8) && (!ctx->use_superk || !ctx->d_sk_prefix.reserve(((size_t)n_micro + 1) * 8));
         if (!okm) { ctx->set_error("out of device memory (work buffers)"); return SIMKA_ERR_NOMEM; }
         CK(cudaStreamWaitEvent(st, sl->copied, 0));
         const int evset = ctx->ev_cur;
@@ -516,8 +522,9 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         CK(cudaMemsetAsync(d_overflow, 0, 4, st));
         CK(cudaMemsetAsync(ctx->d_hist1.p, 0, MAX_B * 4, st));
         CK(cudaMemsetAsync(ctx->d_cursor1.p, 0, MAX_B * 4, st));
-        CK(cudaMemsetAsync(ctx->d_fine_hist.p, 0, (size_t)nbins * 4, st));
-        CK(cudaMemsetAsync(ctx->d_fine_cursor.p, 0, (size_t)nbins * 4, st));
+        CK(cudaMemsetAsync(ctx->d_fine_hist.p, 0, (size_t)(sk ? n_micro : nbins) * 4, st));
+        CK(cudaMemsetAsync(ctx->d_fine_cursor.p, 0, (size_t)(sk ? n_micro : nbins) * 4, st));
+        const uint32_t nbins_run = sk ? nb_sk : nbins;  // bins the counting kernel walks
 
         const unsigned g1 = (unsigned)((n_words + BLOCK - 1) / BLOCK);
         const uint64_t *seq = sl->ext_packed ? sl->ext_packed : sl->packed.as<uint64_t>();
@@ -532,17 +539,18 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT + 1], st));
             CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER], st));
             superk_scan_instance(ctx->kp.k)<<<(unsigned)((n_words + SK_THREADS - 1) / SK_THREADS), SK_THREADS, 0, st>>>(
-                seq, bad, n_words, bin_bits, ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->d_fine_hist.as<uint32_t>(), d_overflow);
+                seq, bad, n_words, micro_bits, ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->d_fine_hist.as<uint32_t>(), d_overflow);
             CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER + 1], st));
             CK(cudaEventRecord(ev[2 * T_PART_COUNT], st));
+            launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_sk_prefix.as<uint64_t>(), n_micro);
+            k_superk_bins<<<(n_micro + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk);
             CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
-            launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), nbins);
             CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
             k_superk_expand<<<(unsigned)std::min<uint64_t>((rec_cap + BLOCK - 1) / BLOCK, (uint64_t)ctx->nsm * 16), BLOCK, 0, st>>>(
-                ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->kp, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(),
+                ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->kp, ctx->d_sk_prefix.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(),
                 ctx->d_keysB.as<uint64_t>());
             CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
-            ctx->launches += 3;
+            ctx->launches += 4;
         } else {
         // K1 (count / scan /) scatter
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
@@ -585,20 +593,20 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_bin_count, k_bin_count, K3_BLOCK, 0));
             if (ctx->occ_bin_count <= 0) ctx->occ_bin_count = 1;
         }
-        const unsigned gbin = (unsigned)std::min<uint64_t>(nbins, (uint64_t)ctx->nsm * ctx->occ_bin_count);
+        const unsigned gbin = (unsigned)std::min<uint64_t>(nbins_run, (uint64_t)ctx->nsm * ctx->occ_bin_count);
         // table slot: the bits just below the bin bits (super-k-mer mode: bins are not key ranges, take the top bits)
         const int slot_shift = std::max(0, W - (sk ? 0 : bin_bits) - ilog2_floor(CNT_SLOTS));
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
-        k_bin_count<<<gbin, K3_BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins, slot_shift, ctx->prm.abundance_min,
+        k_bin_count<<<gbin, K3_BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins_run, slot_shift, ctx->prm.abundance_min,
                                             ctx->prm.abundance_max, co);
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT + 1], st));
-        launch_scan(ctx, ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins);
+        launch_scan(ctx, ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins_run);
         ctx->launches += 3;
         CK(cudaGetLastError());
         // the only host sync of the sample: sizes + totals
         int h_err = 0, h_overflow = 0;
-        CK(cudaMemcpyAsync(&h_surv, ctx->d_out_off.as<uint64_t>() + nbins, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&h_keys, ctx->d_fine_off.as<uint64_t>() + nbins, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_surv, ctx->d_out_off.as<uint64_t>() + nbins_run, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_keys, ctx->d_fine_off.as<uint64_t>() + nbins_run, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_tot, d_totals, 24, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_err, d_error, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
@@ -606,6 +614,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         if (h_overflow && sk) { ctx->superk_fallbacks++; continue; }  // more runs than the record list holds: redo on the k-mer path
         if (h_overflow && !exact) { ctx->exact_retries++; continue; }  // a bucket outgrew its capacity: redo with the exact two-pass path
         sk_used = sk;
+        nbins_fin = nbins_run;
         if (h_err) { ctx->set_error("on-chip table overflow in k_bin_count (code " + std::to_string(h_err) + ")"); return SIMKA_ERR_OVERFLOW; }
         break;
       }
@@ -626,8 +635,8 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
                 pack_h = ctx->d_keysB.as<uint64_t>();
                 pack_c = ctx->d_sk_tmpc.as<uint32_t>();
             }
-            k_compact<<<(unsigned)std::min<uint64_t>((nbins + 7) / 8, (uint64_t)ctx->nsm * 8), BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(),
-                                             ctx->d_out_off.as<uint64_t>(), nbins, pack_h, pack_c);
+            k_compact<<<(unsigned)std::min<uint64_t>((nbins_fin + 7) / 8, (uint64_t)ctx->nsm * 8), BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_stage_c.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(),
+                                             ctx->d_out_off.as<uint64_t>(), nbins_fin, pack_h, pack_c);
             ctx->launches++;
             if (sk_used) {
                 const size_t fgn1 = (size_t)1 << ctx->fg_bits;
