@@ -153,6 +153,7 @@ struct simka_ctx {
     bool use_superk = false;    // SIMKA_B200_SUPERK=1: experimental super-k-mer front end of stage 1 (kernels/superk.cuh)
     uint64_t exact_retries = 0, superk_samples = 0, superk_fallbacks = 0;
     uint64_t superk_cap_override = 0;
+    bool superk_expand_thread = false;
     DevBuf d_sk_tmpc, d_sk_prefix;
     float stage_ms[T_NSTAGE] = {};
     float sample_ms = 0, merge_ms = 0;
@@ -275,6 +276,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
     { const char *e = getenv("SIMKA_B200_B1BITS"); ctx->b1_override = e ? atoi(e) : 0; }
     { const char *e = getenv("SIMKA_B200_REFINE"); ctx->no_refine = e && e[0] == '0'; }
     { const char *e = getenv("SIMKA_B200_SUPERK"); ctx->use_superk = e && e[0] == '1'; }
+    { const char *e = getenv("SIMKA_B200_SUPERK_EXPAND"); ctx->superk_expand_thread = e && !strcmp(e, "thread"); }
     { const char *e = getenv("SIMKA_B200_SUPERK_CAP"); ctx->superk_cap_override = e ? strtoull(e, nullptr, 10) : 0; }  // tests of the fallback
     cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
     ctx->samples.resize(p->nb_samples);
@@ -546,7 +548,8 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             k_superk_bins<<<(n_micro + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk);
             CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
             CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
-            k_superk_expand<<<(unsigned)std::min<uint64_t>((rec_cap + BLOCK - 1) / BLOCK, (uint64_t)ctx->nsm * 16), BLOCK, 0, st>>>(
+            // default: flat (work per k-mer); SIMKA_B200_SUPERK_EXPAND=thread: one thread rolls a whole record
+            (ctx->superk_expand_thread ? k_superk_expand : k_superk_expand_flat)<<<(unsigned)std::min<uint64_t>((rec_cap + BLOCK - 1) / BLOCK, (uint64_t)ctx->nsm * 16), BLOCK, 0, st>>>(
                 ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->kp, ctx->d_sk_prefix.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(),
                 ctx->d_keysB.as<uint64_t>());
             CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));

@@ -287,6 +287,17 @@ def test_superk_example_csv_byte_identical(monkeypatch, golden_dir):
                 assert st.csv(m, ids) == open(path).read(), name
 
 
+def test_superk_expand_one_thread_per_record(monkeypatch):
+    """the alternative expansion kernel (SIMKA_B200_SUPERK_EXPAND=thread; the default lays the k-mers out flat)"""
+    monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
+    monkeypatch.setenv("SIMKA_B200_SUPERK_EXPAND", "thread")
+    samples = nasty_samples()[:5] + small_samples(2, 300)
+    for k in (31, 22):
+        st, ctx = run_superk(samples, k, 1, expect_fallbacks=0)
+        ctx.close()
+        assert_stats_equal(st, oracle_run(samples, k, 1))
+
+
 def test_superk_record_list_overflow_falls_back(monkeypatch):
     monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
     monkeypatch.setenv("SIMKA_B200_SUPERK_CAP", "50")

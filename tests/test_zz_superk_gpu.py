@@ -75,6 +75,15 @@ def test_superk_medium_size_and_many_samples():
     assert_stats_equal(st, oracle_run(samples, 21, 2))
 
 
+def test_superk_expand_one_thread_per_record(monkeypatch):
+    monkeypatch.setenv("SIMKA_B200_SUPERK_EXPAND", "thread")
+    samples = synthetic_samples(4, 3000) + nasty_samples()[:3]
+    st, ctx = simka_b200.run_samples(samples, 31, abundance_min=2, keep_ctx=True)
+    assert counted_by_superk(ctx, samples)
+    ctx.close()
+    assert_stats_equal(st, oracle_run(samples, 31, 2))
+
+
 def test_superk_record_list_overflow_falls_back(monkeypatch):
     monkeypatch.setenv("SIMKA_B200_SUPERK_CAP", "1000")
     samples = synthetic_samples(3, 2000)
