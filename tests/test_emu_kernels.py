@@ -327,3 +327,51 @@ def test_superk_large_bins_and_many_samples(monkeypatch):
     st, ctx = run_superk(samples, 21, 2, expect_fallbacks=0)
     ctx.close()
     assert_stats_equal(st, oracle_run(samples, 21, 2))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi-GPU data path (sample-sharded counting, export -> all-to-all -> import, range-sharded merge) on virtual ranks
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,superk", [(2, False), (4, False), (2, True)])
+def test_sample_sharded_exchange_equals_whole(monkeypatch, world, superk):
+    """simka_b200.dist.exchange_and_merge with the real export / import entry points and merge kernels (emulated), one thread
+    per virtual rank: the summed accumulators equal the oracle's"""
+    import threading
+    import torch
+    from simka_b200 import dist as sdist
+    from test_gpu_parity import _FakeComm
+    if superk:
+        monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
+    samples = small_samples(5, 300)
+    run = oracle_run(samples, 31, 2)
+    N = len(samples)
+    comm = _FakeComm(world)
+    dev = torch.device("cpu")  # the emulator's "device memory" is host memory
+    results, errors = [None] * world, []
+
+    def worker(rank):
+        try:
+            cc = simka_b200.SimkaGpu(N, 31, 2, simple_dist=True, complex_dist=True, expected_kmers_per_sample=300 * 120)
+            mc = simka_b200.SimkaGpu(N, 31, 2, simple_dist=True, complex_dist=True)
+            for s, (seqs, off) in enumerate(samples):
+                if sdist.sample_owner(s, world) != rank:
+                    continue
+                p, b, nw = simka_b200.pack_reads(seqs, off)
+                cc.push_reads(s, p, b, nw, len(off) - 1)
+                cc.finish_sample(s)
+            results[rank] = sdist.exchange_and_merge(cc, mc, N, rank, world, dev, all_to_all=comm.all_to_all(rank),
+                                                     all_reduce_sum=comm.all_reduce_sum(rank))
+            cc.close()
+            mc.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            comm.bar.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    total = results[0]
+    for st in results[1:]:
+        total += st
+    assert_stats_equal(total, run)
