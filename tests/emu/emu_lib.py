@@ -26,8 +26,10 @@ def load_emulator() -> C.CDLL:
 
 
 def use_emulator():
-    """process-wide switch (developer runs with SIMKA_B200_EMU=1)"""
+    """process-wide switch (developer runs with SIMKA_B200_EMU=1): the ctypes front end and, through LD_LIBRARY_PATH, the
+    command-line binaries started by the tests"""
     _lib._lib = load_emulator()
+    os.environ["LD_LIBRARY_PATH"] = cli_env()["LD_LIBRARY_PATH"]
 
 
 @contextlib.contextmanager

@@ -375,3 +375,44 @@ def test_sample_sharded_exchange_equals_whole(monkeypatch, world, superk):
     for st in results[1:]:
         total += st
     assert_stats_equal(total, run)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the command-line binaries (simka, simkaCount / simkaMerge, simkaMinCore, the SimkaMin pipelines), linked against the
+# library through a RUNPATH: LD_LIBRARY_PATH puts the emulated library first for the processes these tests start
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def emulated_cli(monkeypatch):
+    from emu.emu_lib import cli_env
+    monkeypatch.setenv("LD_LIBRARY_PATH", cli_env()["LD_LIBRARY_PATH"])
+
+
+def test_cli_simka_reproduces_truth(emulated_cli, tmp_path, golden_dir):
+    import test_gpu_parity as G
+    for i, (k, t) in enumerate([(21, 0), (31, 2)]):
+        d = tmp_path / str(i)
+        d.mkdir()
+        G.test_simka_cli_reproduces_truth(d, golden_dir, k, t)
+    d = tmp_path / "filters"
+    d.mkdir()
+    G.test_simka_cli_max_reads_and_filters(d, golden_dir)
+
+
+def test_cli_stage_binaries_reference_temp_formats(emulated_cli, tmp_path, golden_dir):
+    import test_gpu_parity as G
+    G.test_stage_binaries_reference_temp_formats(tmp_path, golden_dir)
+
+
+def test_cli_simkamincore_and_pipelines_reproduce_truth(emulated_cli, tmp_path, golden_dir):
+    import test_gpu_parity as G
+    import test_simkamin_pipeline as P
+    for i, (k, mr, nk, filt) in enumerate([(21, 0, 100, False), (31, 0, 1000, True)]):
+        d = tmp_path / f"core{i}"
+        d.mkdir()
+        G.test_simkamincore_cli_reproduces_reference_truth(d, golden_dir, k, mr, nk, filt)
+    d = tmp_path / "py"
+    d.mkdir()
+    P.test_simkamin_py_reproduces_reference_truth(d, golden_dir, 31, 100, 100, True)
+    d = tmp_path / "update"
+    d.mkdir()
+    P.test_simkamin_update_equals_one_run(d, golden_dir)
