@@ -337,19 +337,35 @@ def run_ours(a):
         Ks, D, U = per["kmers_in"], per["entries"], per["distinct_kmers"]
         words = sum(nwords.values())
         # algorithmic bytes per launch set (summed over the samples of one step); DESIGN.md section 4
-        alg = {
-            "k_extract<count>": words * 12,
-            "k_extract<scatter>": words * 12 + 8 * Ks,
-            "k_partition2<count>": 8 * Ks,
-            "k_partition2<scatter>": 16 * Ks,
-            "k_bin_count": 8 * Ks + 12 * D,
-            "k_merge": 12 * D + 8 * U,
-        }
-        tms = {
-            "k_extract<count>": per["extract_count_ms"], "k_extract<scatter>": per["extract_scatter_ms"],
-            "k_partition2<count>": per["part_count_ms"], "k_partition2<scatter>": per["part_scatter_ms"],
-            "k_bin_count": per["bin_count_ms"], "k_merge": per["merge_ms"],
-        }
+        superk = per.get("superk_samples", 0) > 0  # SIMKA_B200_SUPERK=1: experimental super-k-mer front end of stage 1
+        if superk:
+            # the scan reads the packed reads and the expansion writes the keys: together the algorithmic bytes of the k-mer
+            # extraction; the record list in between (about 2 B per k-mer each way) is implementation traffic
+            alg = {
+                "k_superk_scan": words * 12,
+                "k_superk_bins(+scan)": 0,
+                "k_superk_expand": 8 * Ks,
+                "k_bin_count": 8 * Ks + 12 * D,
+                "k_merge": 12 * D + 8 * U,
+            }
+            tms = {
+                "k_superk_scan": per["extract_scatter_ms"], "k_superk_bins(+scan)": per["part_count_ms"],
+                "k_superk_expand": per["part_scatter_ms"], "k_bin_count": per["bin_count_ms"], "k_merge": per["merge_ms"],
+            }
+        else:
+            alg = {
+                "k_extract<count>": words * 12,
+                "k_extract<scatter>": words * 12 + 8 * Ks,
+                "k_partition2<count>": 8 * Ks,
+                "k_partition2<scatter>": 16 * Ks,
+                "k_bin_count": 8 * Ks + 12 * D,
+                "k_merge": 12 * D + 8 * U,
+            }
+            tms = {
+                "k_extract<count>": per["extract_count_ms"], "k_extract<scatter>": per["extract_scatter_ms"],
+                "k_partition2<count>": per["part_count_ms"], "k_partition2<scatter>": per["part_scatter_ms"],
+                "k_bin_count": per["bin_count_ms"], "k_merge": per["merge_ms"],
+            }
         peak, peak_src = hbm_peak()
         kernels = {n: {"ms_per_step": tms[n], "alg_bytes_per_step": alg[n],
                        "achieved_gbs": (alg[n] / (tms[n] * 1e-3) / 1e9) if tms[n] > 0 else None} for n in alg}
@@ -370,7 +386,9 @@ def run_ours(a):
                                     "solid (k-mer,count) lists exchanged with NCCL all-to-all, 2 tiny all-reduces; kernels/roofline are rank 0's share") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (packed reads 57 MB/sample, 0.96 GB of keys per sample streamed)",
                        "generator": "BASELINE.md section 3 (G=256 x 50 kb, Dirichlet(0.3), 1% substitutions, 50% revcomp)",
-                       "input_build_s": round(gen_s, 1)},
+                       "input_build_s": round(gen_s, 1),
+                       "stage1": ("super-k-mer front end (SIMKA_B200_SUPERK=1, experimental), %d fallbacks" % per.get("superk_fallbacks", 0)) if superk
+                                 else "k-mer partition (default)"},
             "e2e": {"value": kmers_per_step * steps / (ms_e2e * 1e-3), "unit": "kmers/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes[0]},
             "gpu_launches": int(launches),
