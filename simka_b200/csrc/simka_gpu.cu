@@ -155,6 +155,7 @@ struct simka_ctx {
     uint64_t superk_cap_override = 0;
     bool superk_expand_thread = false;
     DevBuf d_sk_tmpc, d_sk_prefix;
+    DevBuf d_dump;  // scratch of simka_gpu_dump_sample_counts (parity hook)
     float stage_ms[T_NSTAGE] = {};
     float sample_ms = 0, merge_ms = 0;
     uint64_t kmers_in = 0, entries = 0;
@@ -336,7 +337,7 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
                       &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
                       &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
-                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum, &ctx->d_sk_tmpc, &ctx->d_sk_prefix};
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum, &ctx->d_sk_tmpc, &ctx->d_sk_prefix, &ctx->d_dump};
     for (DevBuf *b : bufs) b->release();
     for (auto &set : ctx->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
@@ -355,7 +356,12 @@ static int grow_keep(simka_ctx *ctx, DevBuf &b, size_t bytes, size_t keep) {
     size_t want = bytes + bytes / 4 + 256;
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaMalloc(&np, want));
-    if (keep) { CK(cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, ctx->copy_stream)); CK(cudaStreamSynchronize(ctx->copy_stream)); }
+    if (keep && (cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, ctx->copy_stream) != cudaSuccess ||
+                 cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess)) {
+        cudaFree(np);
+        ctx->set_error("device copy failed while growing an input buffer");
+        return SIMKA_ERR_CUDA;
+    }
     if (b.p) cudaFree(b.p);
     b.p = np; b.cap = want;
     return SIMKA_OK;
@@ -703,16 +709,15 @@ int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers,
     if (*n < sd.n) { *n = sd.n; return SIMKA_ERR_INVALID; }
     *n = sd.n;
     if (sd.n == 0) return SIMKA_OK;
-    uint64_t *tmp = nullptr;
-    CK(cudaMalloc(&tmp, sd.n * 8));
-    if (ctx->kp.key_mode) CK(cudaMemcpyAsync(tmp, sd.eh, sd.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // the keys ARE the hashes
-    else k_unmix<<<(unsigned)((sd.n + 255) / 256), 256, 0, ctx->stream>>>(sd.eh, tmp, sd.n, ctx->kp.mix);
     std::vector<uint64_t> hk(sd.n);
     std::vector<uint32_t> hc(sd.n);
+    if (ctx->d_dump.reserve(sd.n * 8)) { ctx->set_error("out of device memory (dump)"); return SIMKA_ERR_NOMEM; }  // context-owned: no leak on an error return
+    uint64_t *tmp = ctx->d_dump.as<uint64_t>();
+    if (ctx->kp.key_mode) CK(cudaMemcpyAsync(tmp, sd.eh, sd.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // the keys ARE the hashes
+    else k_unmix<<<(unsigned)((sd.n + 255) / 256), 256, 0, ctx->stream>>>(sd.eh, tmp, sd.n, ctx->kp.mix);
     CK(cudaMemcpyAsync(hk.data(), tmp, sd.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hc.data(), sd.ec, sd.n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
     std::vector<uint64_t> order(sd.n);
     for (uint64_t i = 0; i < sd.n; i++) order[i] = i;
     std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
