@@ -8,6 +8,9 @@
 // On top of the one-read-at-a-time iterator there is a batch reader (FastxParser::appendReads) that fills
 // the concatenated-ASCII + offsets layout simka_pack_reads / simka_gpu_push_ascii take.
 #pragma once
+#include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <cstdint>
@@ -64,17 +67,30 @@ public:
 class FastxParser {
 public:
     explicit FastxParser(const std::string &path) : path_(path) {
-        f_ = gzopen(path.c_str(), "rb");
-        if (!f_) throw Exception("cannot open " + path);
-        gzbuffer(f_, 1 << 20);
+        // plain files are read with read(2) into the parse buffer; only gzip streams (magic 1f 8b) go through zlib
+        raw_ = ::open(path.c_str(), O_RDONLY);
+        if (raw_ < 0) throw Exception("cannot open " + path);
+        unsigned char magic[2] = {0, 0};
+        const bool gz = ::pread(raw_, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        if (gz) {
+            ::close(raw_);
+            raw_ = -1;
+            f_ = gzopen(path.c_str(), "rb");
+            if (!f_) throw Exception("cannot open " + path);
+            gzbuffer(f_, 1 << 20);
+        }
         buf_.resize(1 << 21);
     }
-    ~FastxParser() { if (f_) gzclose(f_); }
+    ~FastxParser() {
+        if (f_) gzclose(f_);
+        if (raw_ >= 0) ::close(raw_);
+    }
     FastxParser(const FastxParser &) = delete;
     FastxParser &operator=(const FastxParser &) = delete;
 
     void rewind() {
-        gzrewind(f_);
+        if (f_) gzrewind(f_);
+        else ::lseek(raw_, 0, SEEK_SET);
         beg_ = end_ = 0;
         eof_ = false;
         last_ = 0;
@@ -90,13 +106,19 @@ public:
             if (c == -1) return false;
             last_ = c;
         }
-        if (comment) comment->clear();
-        while ((c = getc_()) != -1 && c != '\n') if (comment) comment->push_back((char)c);
-        if (comment && !comment->empty() && comment->back() == '\r') comment->pop_back();
+        if (comment) {
+            comment->clear();
+            appendLine_(*comment);
+            if (!comment->empty() && comment->back() == '\r') comment->pop_back();
+        } else {
+            skipLine_();
+        }
         const size_t start = data.size();
-        while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
-            if (c == '\n') continue;
-            data.push_back((char)c);
+        for (;;) {  // sequence lines up to the next line that starts with '>', '+' or '@'
+            if (beg_ >= end_ && !fill_()) { c = -1; break; }
+            c = (unsigned char)buf_[beg_];
+            if (c == '>' || c == '+' || c == '@') { beg_++; break; }
+            if (c == '\n') { beg_++; continue; }
             appendLine_(data);
             if (data.size() - start > 1 && data.back() == '\r') data.pop_back();
         }
@@ -105,10 +127,12 @@ public:
         if (c == '+') {
             const size_t rlen = data.size() - start;
             size_t qlen = 0;
-            while ((c = getc_()) != -1 && c != '\n') {}
+            c = skipLine_() ? '\n' : -1;
             while (c != -1) {
-                bool any = false;
-                while ((c = getc_()) != -1 && c != '\n') { qlen++; any = true; if (quality) quality->push_back((char)c); }
+                size_t got = 0;
+                c = consumeLine_(quality, got) ? '\n' : -1;
+                qlen += got;
+                const bool any = got > 0;
                 if (c == -1 && !any) break;
                 if (qlen >= rlen) break;
             }
@@ -123,7 +147,9 @@ public:
 private:
     bool fill_() {
         if (eof_) return false;
-        int n = gzread(f_, &buf_[0], (unsigned)buf_.size());
+        long n;
+        if (f_) n = gzread(f_, &buf_[0], (unsigned)buf_.size());
+        else do { n = (long)::read(raw_, &buf_[0], buf_.size()); } while (n < 0 && errno == EINTR);
         if (n < 0) throw Exception("read error in " + path_);
         beg_ = 0;
         end_ = (size_t)n;
@@ -133,6 +159,31 @@ private:
     int getc_() {
         if (beg_ >= end_ && !fill_()) return -1;
         return (unsigned char)buf_[beg_++];
+    }
+    // drops the rest of the current line including its newline; false at end of file before a newline
+    bool skipLine_() {
+        for (;;) {
+            if (beg_ >= end_ && !fill_()) return false;
+            const char *p = &buf_[beg_];
+            const char *nl = (const char *)memchr(p, '\n', end_ - beg_);
+            if (nl) { beg_ += (size_t)(nl - p) + 1; return true; }
+            beg_ = end_;
+        }
+    }
+    // consumes the rest of the current line: `got` = its characters (newline excluded), appended to `out` if given;
+    // false at end of file before a newline
+    bool consumeLine_(std::string *out, size_t &got) {
+        got = 0;
+        for (;;) {
+            if (beg_ >= end_ && !fill_()) return false;
+            const char *p = &buf_[beg_];
+            const char *nl = (const char *)memchr(p, '\n', end_ - beg_);
+            const size_t n = nl ? (size_t)(nl - p) : end_ - beg_;
+            if (out) out->append(p, n);
+            got += n;
+            beg_ += n + (nl ? 1 : 0);
+            if (nl) return true;
+        }
     }
     // rest of the current line (without the newline) appended to `out`
     void appendLine_(std::string &out) {
@@ -151,6 +202,7 @@ private:
     }
     std::string path_;
     gzFile f_ = nullptr;
+    int raw_ = -1;
     std::string buf_;
     size_t beg_ = 0, end_ = 0;
     bool eof_ = false;

@@ -280,3 +280,51 @@ def test_minimizer_known_answers_testkmer():
     for v, (kmer, mini) in zip(km.tolist(), TESTKMER_MINIMIZER3):
         assert kmer_string(v, 15) == kmer
         assert kmer_string(L.simka_host_minimizer(v, 15, 7), 7) == mini
+
+
+def test_fastx_parser_randomised_against_the_oracle(tmp_path):
+    """FastxParser (raw read / zlib, memchr line handling) against the oracle's reader on generated FASTA / FASTQ files: multi-line
+    records, CRLF, blank lines, long headers, '+' lines with text, quality lines that begin with '@' or '>', multi-line quality,
+    missing final newline, records longer than the 2 MB parse buffer, gz"""
+    rng = np.random.default_rng(21)
+    alpha = np.frombuffer(b"ACGTacgtN", np.uint8)
+
+    def seq(n):
+        return alpha[rng.integers(0, len(alpha), n)].tobytes()
+
+    def wrap(s, width, eol):
+        if width <= 0 or len(s) == 0:
+            return s + eol
+        return b"".join(s[i:i + width] + eol for i in range(0, len(s), width))
+
+    for case in range(12):
+        eol = b"\r\n" if case % 3 == 1 else b"\n"
+        fastq = case % 2 == 1
+        recs = []
+        for r in range(int(rng.integers(1, 40))):
+            n = int(rng.integers(0, 400)) if case != 10 else int(rng.integers(2_000_000, 2_300_000))
+            s = seq(n)
+            hdr = (b"@" if fastq else b">") + b"r%d " % r + b"x" * int(rng.integers(0, 120))
+            width = int(rng.integers(0, 4)) * 37  # 0 = one line
+            if fastq:
+                q = bytes(rng.integers(33, 74, n, dtype=np.uint8))
+                if n and rng.random() < 0.3:
+                    q = (b"@" if rng.random() < 0.5 else b">") + q[1:]
+                recs.append(hdr + eol + wrap(s, width, eol) + b"+" + (b"r%d" % r if rng.random() < 0.5 else b"") + eol + wrap(q, width, eol))
+            else:
+                recs.append(hdr + eol + wrap(s, width, eol) + (eol if rng.random() < 0.2 else b""))
+            if case == 10 and r >= 1:
+                break
+        data = b"".join(recs)
+        if case % 4 == 3 and data.endswith(eol):
+            data = data[:-len(eol)]  # no final newline
+        path = tmp_path / (f"c{case}." + ("fq" if fastq else "fa") + (".gz" if case % 5 == 4 else ""))
+        if case % 5 == 4:
+            with gzip.open(path, "wb") as f:
+                f.write(data)
+        else:
+            path.write_bytes(data)
+        s, o = read_bank(str(path))
+        es, eo = oracle.read_fastx(str(path))
+        np.testing.assert_array_equal(o, eo, err_msg=str(path))
+        np.testing.assert_array_equal(s, es, err_msg=str(path))
