@@ -98,12 +98,15 @@ def transform(text: str) -> tuple[str, int]:
     return rewrite_launches(text)
 
 
-def build(force: bool = False) -> Path:
+def build(force: bool = False, asan: bool = False) -> Path:
+    """asan=True: a second library compiled with -fsanitize=address (out-of-bounds accesses of "device" and "shared" memory by
+    the kernels abort with a report); the process loading it needs LD_PRELOAD=$(gcc -print-file-name=libasan.so)."""
     srcs = [CSRC / "simka_gpu.cu", CSRC / "kmer_device.cuh", *sorted((CSRC / "kernels").glob("*.cuh"))]
     deps = srcs + [CSRC / "simka_host.cpp", *sorted((CSRC / "host").glob("*.hpp")), ROOT / "include" / "simka_b200.h",
                    HERE / "cuda_runtime.h", Path(__file__)]
-    if not force and LIB.exists() and all(d.stat().st_mtime <= LIB.stat().st_mtime for d in deps):
-        return LIB
+    lib = OUT / "libsimka_b200_emu_asan.so" if asan else LIB
+    if not force and lib.exists() and all(d.stat().st_mtime <= lib.stat().st_mtime for d in deps):
+        return lib
     gen = OUT / "csrc"
     (gen / "kernels").mkdir(parents=True, exist_ok=True)
     launches = 0
@@ -117,11 +120,12 @@ def build(force: bool = False) -> Path:
         dst.write_text(text)
     assert launches >= 30, f"only {launches} kernel launches rewritten"
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{HERE}", "-DSIMKA_CUDA_EMU=1",
-           "-o", str(LIB), str(gen / "simka_gpu_emu.cpp"), str(CSRC / "simka_host.cpp"), "-lz", "-lpthread"]
+           *(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []),
+           "-o", str(lib), str(gen / "simka_gpu_emu.cpp"), str(CSRC / "simka_host.cpp"), "-lz", "-lpthread"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))

@@ -19,3 +19,10 @@ except Exception as e:
 run default SIMKA_B200_SUPERK=0
 run superk_flat SIMKA_B200_SUPERK=1
 run superk_thread SIMKA_B200_SUPERK=1 SIMKA_B200_SUPERK_EXPAND=thread
+# tools/ab_superk.sh ncu : additionally one full ncu capture of the super-k-mer kernels and of k_bin_count behind them
+# (2 samples are enough: every sample launches each kernel once)
+if [ "$1" = "ncu" ]; then
+    SIMKA_B200_SUPERK=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_superk|k_bin_count' -c 8 \
+        -o gpurun_out/ab_superk_full python bench.py --steps 1 --warmup 0 --samples 2 --no-cpu-baseline > gpurun_out/ab_superk_ncu.log 2>&1
+    echo "ncu rc=$?"
+fi
