@@ -105,10 +105,24 @@ inline void run_block() {
         f.state = RUNNABLE;
         f.warp_gen_seen = 0;
     }
+    // order in which the runnable fibers of a pass are resumed: ascending thread index by default; SIMKA_EMU_SCHED=reverse or
+    // =random[:seed] changes it, so that code which only works because lower-numbered threads happen to run first (a missing
+    // __syncthreads, warp-synchronous assumptions) gives different -- wrong -- results
+    static const int sched_mode = [] { const char *e = getenv("SIMKA_EMU_SCHED"); return !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0)); }();
+    static uint64_t rng = [] { const char *e = getenv("SIMKA_EMU_SCHED"); const char *c = e ? strchr(e, ':') : nullptr; return (uint64_t)(c ? atoll(c + 1) : 1) * 0x9E3779B97F4A7C15ull + 1; }();
+    static unsigned order[MAX_THREADS];
+    for (unsigned t = 0; t < n; t++) order[t] = sched_mode == 1 ? n - 1 - t : t;
     for (;;) {
         bool progress = false;
         unsigned done = 0, at_block = 0;
-        for (unsigned t = 0; t < n; t++) {
+        if (sched_mode == 2)
+            for (unsigned i = n - 1; i > 0; i--) {  // Fisher-Yates with xorshift64
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                const unsigned j = (unsigned)(rng % (i + 1));
+                const unsigned tmp = order[i]; order[i] = order[j]; order[j] = tmp;
+            }
+        for (unsigned oi = 0; oi < n; oi++) {
+            const unsigned t = order[oi];
             Fiber &f = b.fib[t];
             if (f.state == AT_WARP_BARRIER && b.warp_gen[t >> 5] != f.warp_gen_seen) f.state = RUNNABLE;
             if (f.state == RUNNABLE) {
