@@ -218,47 +218,63 @@ k_superk_expand(const SkRecord *__restrict__ records, const ull *__restrict__ n_
     }
 }
 
-// Same job with the work spread evenly: a CTA takes BLOCK records, reserves their slots (one atomic per record), lays the k-mers
-// of the chunk out flat (block scan of the record lengths + an owner byte per k-mer) and every thread then computes single k-mers
-// straight from the record (shift, reverse complement, mix) instead of rolling a whole record: records hold 1 to 21 k-mers
-// (7.4 on average), so one thread per record leaves two thirds of the lanes idle, and consecutive lanes write consecutive keys.
+// Same job with the work spread evenly: a CTA takes BLOCK records, reserves their slots (one atomic per record), cuts every record
+// into items of SK_G consecutive k-mers, lays the items of the chunk out flat (block scan of the item counts + an owner byte per
+// item) and every thread then takes single items: the first k-mer of an item straight from the record (shift, reverse complement,
+// mix: 69 instructions), the following ones rolled (26).  Records hold 1 to 21 k-mers (7.4 on average), so one thread per record
+// leaves two thirds of the lanes idle; items of 4 keep the lanes busy at about 40 instructions per k-mer.
+constexpr int SK_G = 4;
 __global__ void __launch_bounds__(BLOCK)
 k_superk_expand_flat(const SkRecord *__restrict__ records, const ull *__restrict__ n_records, uint64_t cap, KParams kp,
                      const uint64_t *__restrict__ micro_off, uint32_t *__restrict__ micro_cursor, uint64_t *__restrict__ keys_out) {
     __shared__ SkRecord s_rec[BLOCK];
     __shared__ uint64_t s_pos[BLOCK];
     __shared__ uint32_t s_start[BLOCK], warp_tmp[BLOCK / 32 + 1];
-    __shared__ uint8_t s_owner[BLOCK * 32];
+    __shared__ uint8_t s_owner[BLOCK * (32 / SK_G)];
     const int tid = threadIdx.x;
     const ull nr = *n_records < cap ? *n_records : cap;
     const int k = kp.k;
+    const uint64_t kmask = kp.mix.mask;
     for (ull c0 = (ull)blockIdx.x * BLOCK; c0 < nr; c0 += (ull)gridDim.x * BLOCK) {
         const ull r = c0 + tid;
-        uint32_t n = 0;
+        uint32_t items = 0;
         if (r < nr) {
             const SkRecord rec = records[r];
             const uint32_t micro = (uint32_t)rec.lo & 0x1FFFFFu;
-            n = ((uint32_t)(rec.lo >> 21) & 31u) + 1;
+            const uint32_t n = ((uint32_t)(rec.lo >> 21) & 31u) + 1;
+            items = (n + SK_G - 1) / SK_G;
             s_rec[tid] = rec;
             s_pos[tid] = micro_off[micro] + atomicAdd(&micro_cursor[micro], n);
         }
-        s_start[tid] = n;
+        s_start[tid] = items;
         __syncthreads();
         block_exclusive_scan(s_start, BLOCK, warp_tmp);
         const uint32_t total = warp_tmp[BLOCK / 32];
         {
             const uint32_t st = s_start[tid];
-            for (uint32_t j = 0; j < n; j++) s_owner[st + j] = (uint8_t)tid;
+            for (uint32_t j = 0; j < items; j++) s_owner[st + j] = (uint8_t)tid;
         }
         __syncthreads();
         for (uint32_t i = tid; i < total; i += BLOCK) {
             const uint32_t o = s_owner[i];
-            const uint32_t j = i - s_start[o];
+            const uint32_t j0 = (i - s_start[o]) * SK_G;
             const uint64_t hi = s_rec[o].hi, lo = s_rec[o].lo;
-            const uint64_t x = j ? (hi << (2 * j)) | (lo >> (64 - 2 * j)) : hi;  // the record from base j on (j + k <= 51 bases: never the tag bits)
-            const uint64_t fwd = x >> (64 - 2 * k);
-            const uint64_t rev = simka::revcomp(fwd, k);
-            keys_out[s_pos[o] + j] = simka::mix_fwd(fwd < rev ? fwd : rev, kp.mix);
+            const uint32_t n = ((uint32_t)(lo >> 21) & 31u) + 1;
+            const uint64_t x = j0 ? (hi << (2 * j0)) | (lo >> (64 - 2 * j0)) : hi;  // the record from base j0 on (j0 + k <= 51 bases: never the tag bits)
+            uint64_t fwd = x >> (64 - 2 * k);
+            uint64_t rev = simka::revcomp(fwd, k);
+            uint64_t *out = keys_out + s_pos[o] + j0;
+            out[0] = simka::mix_fwd(fwd < rev ? fwd : rev, kp.mix);
+#pragma unroll
+            for (int g = 1; g < SK_G; g++) {
+                if (j0 + g < n) {
+                    const int b_idx = k - 1 + (int)j0 + g;  // index of the incoming base
+                    const uint64_t b = b_idx < 32 ? (hi >> (62 - 2 * b_idx)) & 3u : (lo >> (62 - 2 * (b_idx - 32))) & 3u;
+                    fwd = ((fwd << 2) | b) & kmask;
+                    rev = (rev >> 2) | ((b ^ 2u) << (2 * k - 2));
+                    out[g] = simka::mix_fwd(fwd < rev ? fwd : rev, kp.mix);
+                }
+            }
         }
         __syncthreads();
     }
