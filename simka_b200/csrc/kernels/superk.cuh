@@ -15,7 +15,7 @@
 //                      strands see the same set of canonical m-mers): every occurrence of a k-mer lands in the same micro-bin,
 //                      which is all exact counting needs.  Runs = consecutive valid k-mers of the word with equal micro-bin (cut
 //                      at the word boundary and at the record capacity); each run is appended to an unsorted record list (one
-//                      atomic per warp round) and adds its k-mer count to the micro-bin histogram (one atomic per run).
+//                      atomic per warp) and adds its k-mer count to the micro-bin histogram (one atomic per run).
 //   k_superk_bins      minimizer frequencies follow the coverage of the genomes they come from (bins of a fixed hash range came
 //                      out at 916 +- 703 keys on the bench workload, tools/superk_balance.py), so the counting bins are cut
 //                      per sample from the scanned histogram, as the reference balances its partitions from sampled minimizer
@@ -136,37 +136,34 @@ k_superk_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad
             else len = 0;
         }
     }
-    // emit the runs, one per thread and round; the list slot comes from one atomic per warp and round
-    uint32_t todo = startmask;
-    for (;;) {
-        const bool has = todo != 0;
-        const uint32_t act = __ballot_sync(0xffffffffu, has);
-        if (!act) break;
-        SkRecord rec;
-        uint32_t n = 0, b = 0;
-        if (has) {
-            const int p = __ffs((int)todo) - 1;
-            todo &= todo - 1;
-            const uint32_t stop = p < 31 ? (startmask | ~validmask) >> (p + 1) : 0u;  // bit i <-> position p + 1 + i starts a run or is invalid
-            n = stop ? (uint32_t)__ffs((int)stop) : (uint32_t)(32 - p);
-            b = s_bin[p * SK_THREADS + tid];
-            const uint64_t rh = p ? (hi << (2 * p)) | (lo >> (64 - 2 * p)) : hi;
-            const uint64_t rl = p ? lo << (2 * p) : lo;
-            rec.hi = rh;
-            rec.lo = (rl & ~((1ull << 26) - 1)) | ((uint64_t)(n - 1) << 21) | b;
-        }
-        ull base = 0;
-        const int leader = __ffs((int)act) - 1;
-        if (lane == leader) base = atomicAdd(n_records, (ull)__popc(act));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (has) {
-            const ull slot = base + (ull)__popc(act & ((1u << lane) - 1));
-            if (slot < cap) {
-                records[slot] = rec;
-                atomicAdd(&bin_hist[b], n);
-            } else {
-                *overflow_flag = 1;  // the host redoes the sample on the k-mer path
-            }
+    // emit the runs: one list reservation per warp (prefix sum of the lanes' run counts, one atomic), then every lane writes its
+    // runs to consecutive slots
+    const uint32_t mine = (uint32_t)__popc(startmask);
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
+    if (warp_total == 0) return;  // (warp-uniform)
+    ull base = 0;
+    if (lane == 31) base = atomicAdd(n_records, (ull)warp_total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    ull slot = base + (inc - mine);
+    for (uint32_t todo = startmask; todo; todo &= todo - 1, slot++) {
+        const int p = __ffs((int)todo) - 1;
+        const uint32_t stop = p < 31 ? (startmask | ~validmask) >> (p + 1) : 0u;  // bit i <-> position p + 1 + i starts a run or is invalid
+        const uint32_t n = stop ? (uint32_t)__ffs((int)stop) : (uint32_t)(32 - p);
+        const uint32_t b = s_bin[p * SK_THREADS + tid];
+        if (slot < cap) {
+            SkRecord rec;
+            rec.hi = p ? (hi << (2 * p)) | (lo >> (64 - 2 * p)) : hi;
+            rec.lo = ((p ? lo << (2 * p) : lo) & ~((1ull << 26) - 1)) | ((uint64_t)(n - 1) << 21) | b;
+            records[slot] = rec;
+            atomicAdd(&bin_hist[b], n);
+        } else {
+            *overflow_flag = 1;  // the host redoes the sample on the k-mer path
         }
     }
 }
