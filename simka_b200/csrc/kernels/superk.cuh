@@ -39,7 +39,7 @@ struct __align__(16) SkRecord { uint64_t hi, lo; };
 
 // bijections on 32 bits: the order of the m-mers (smallest hash = minimizer) and the bin of a minimizer
 __device__ __forceinline__ uint32_t sk_hash(uint32_t x) {
-    x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
+    x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u;  // (the order only needs the high bits mixed; sk_bin multiplies once more)
     return x;
 }
 __device__ __forceinline__ uint32_t sk_bin(uint32_t minv, int bin_bits) {
@@ -64,7 +64,7 @@ k_superk_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad
     constexpr int NQ = 32 + W - 1;               // m-mers the 32 k-mers of a word touch (bases 0 .. 30 + K <= 61)
     constexpr int NMAX = (SK_MAXB - K + 1) < 32 ? (SK_MAXB - K + 1) : 32;  // k-mers per record
     static_assert(K >= SK_MINK && K <= 31, "k_superk_scan: 17 <= K <= 31");
-    __shared__ uint32_t s_bin[32 * SK_THREADS];  // bin of start position p of thread t at [p * SK_THREADS + t]
+    __shared__ uint32_t s_bin[32 * SK_THREADS];  // minimizer value of start position p of thread t at [p * SK_THREADS + t]
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint64_t t = (uint64_t)blockIdx.x * SK_THREADS + tid;
@@ -123,16 +123,16 @@ k_superk_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad
         for (int q = 1; q < NQ; q++)
             if (q % W != 0) hv[q] = hv[q - 1] < hv[q] ? hv[q - 1] : hv[q];
         // runs: consecutive valid k-mers with equal bin, at most NMAX of them
-        uint32_t prevbin = 0;
+        // (compared on the minimizer value: equal values have equal bins; the bin itself is computed once per run, at emission)
+        uint32_t prevmv = 0;
         int len = 0;
 #pragma unroll
         for (int p = 0; p < 32; p++) {
             const uint32_t mv = S[p] < hv[p + W - 1] ? S[p] : hv[p + W - 1];
-            const uint32_t b = sk_bin(mv, bin_bits);
-            s_bin[p * SK_THREADS + tid] = b;
+            s_bin[p * SK_THREADS + tid] = mv;
             const bool v = (validmask >> p) & 1u;
-            if (v && len > 0 && b == prevbin && len < NMAX) len++;
-            else if (v) { startmask |= 1u << p; len = 1; prevbin = b; }
+            if (v && len > 0 && mv == prevmv && len < NMAX) len++;
+            else if (v) { startmask |= 1u << p; len = 1; prevmv = mv; }
             else len = 0;
         }
     }
@@ -155,7 +155,7 @@ k_superk_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad
         const int p = __ffs((int)todo) - 1;
         const uint32_t stop = p < 31 ? (startmask | ~validmask) >> (p + 1) : 0u;  // bit i <-> position p + 1 + i starts a run or is invalid
         const uint32_t n = stop ? (uint32_t)__ffs((int)stop) : (uint32_t)(32 - p);
-        const uint32_t b = s_bin[p * SK_THREADS + tid];
+        const uint32_t b = sk_bin(s_bin[p * SK_THREADS + tid], bin_bits);
         if (slot < cap) {
             SkRecord rec;
             rec.hi = p ? (hi << (2 * p)) | (lo >> (64 - 2 * p)) : hi;

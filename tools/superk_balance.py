@@ -28,7 +28,6 @@ def sk_hash(x):
     x = (x * np.uint32(0x9E3779B1)).astype(np.uint32)
     x ^= x >> np.uint32(15)
     x = (x * np.uint32(0x85EBCA77)).astype(np.uint32)
-    x ^= x >> np.uint32(13)
     return x
 
 

@@ -13,7 +13,7 @@ seqs, off = synth.make_sample(genomes, sample, reads, L)
 codes = ((seqs.reshape(reads, L) >> 1) & 3).astype(np.uint32)
 def sk_hash(x):
     x = (x * np.uint32(0x9E3779B1)).astype(np.uint32); x ^= x >> np.uint32(15)
-    x = (x * np.uint32(0x85EBCA77)).astype(np.uint32); x ^= x >> np.uint32(13); return x
+    x = (x * np.uint32(0x85EBCA77)).astype(np.uint32); return x
 P = np.uint64(0x9E3779B97F4A7C15)
 powers = np.ones(L + 1, np.uint64)
 for i in range(1, L + 1): powers[i] = powers[i - 1] * P

@@ -14,7 +14,7 @@ seqs, off = synth.make_sample(genomes, 0, reads, L)
 codes = ((seqs.reshape(reads, L) >> 1) & 3).astype(np.uint32)
 def sk_hash(x):
     x = (x * np.uint32(0x9E3779B1)).astype(np.uint32); x ^= x >> np.uint32(15)
-    x = (x * np.uint32(0x85EBCA77)).astype(np.uint32); x ^= x >> np.uint32(13); return x
+    x = (x * np.uint32(0x85EBCA77)).astype(np.uint32); return x
 nkm = L - K + 1
 micro_all = np.empty((reads, nkm), np.uint32)
 kh_all = np.empty((reads, nkm), np.uint64)
