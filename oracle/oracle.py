@@ -208,11 +208,11 @@ class Run:
 
     def u64(self, name):
         n = self.n
-        size = n * (n + 1) // 2 if name in ("distinct_shared", "braycurtis_num") else n * n
-        out = np.zeros(size, np.uint64)
+        packed = name in ("distinct_shared", "braycurtis_num")  # upper triangle with diagonal, N (N + 1) / 2 entries
+        out = np.zeros(n * (n + 1) // 2 if packed else n * n, np.uint64)
         if lib().orc_get_u64(self._h, name.encode(), _p(out, C.c_uint64)) != 0:
             raise KeyError(name)
-        return out if size != n * n else out.reshape(n, n)
+        return out if packed else out.reshape(n, n)
 
     def f64(self, name):
         n = self.n

@@ -416,3 +416,12 @@ def test_cli_simkamincore_and_pipelines_reproduce_truth(emulated_cli, tmp_path, 
     d = tmp_path / "update"
     d.mkdir()
     P.test_simkamin_update_equals_one_run(d, golden_dir)
+
+
+def test_single_sample_run():
+    """N = 1: no pair exists, the per-sample totals and the (1 x 1) matrices still come out like the oracle's"""
+    samples = small_samples(1, 200)
+    for k in (31, 15):
+        run = oracle_run(samples, k, 2)
+        st = simka_b200.run_samples(samples, k, abundance_min=2)
+        assert_stats_equal(st, run)
