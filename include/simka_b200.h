@@ -222,6 +222,17 @@ int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_
 int simkamin_gpu_sketch_filter(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
                         uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected);
 
+/* How the calling thread's last simkamin_gpu_sketch / simkamin_gpu_sketch_filter call got its sketch.  The bottom-s selection of
+ * the reference is a heap over every k-mer of the sample (processUnfiltered, src/simkaMin/SimkaMinCount.hpp:311-338); here only
+ * hashes below a bound are extracted and counted, the bound growing from 16 * s / positions of the hash range by factors of 8
+ * until >= s distinct hashes lie below it (exact: every occurrence of a kept hash is counted).  attempts = counting passes run,
+ * keys_counted = k-mer occurrences that passed the bound over all attempts, distinct_dumped = distinct hashes the last attempt
+ * brought back to the host.  SIMKA_B200_SKETCH_PREFILTER=0 takes the whole hash range at once. */
+typedef struct simkamin_sketch_info {
+    uint64_t attempts, keys_counted, distinct_dumped;
+} simkamin_sketch_info;
+int simkamin_gpu_last_sketch_info(simkamin_sketch_info *out);
+
 /* ---- SimkaMin: replaces ComputeDistanceManager::computeDistance_unsynch over all pairs ------------
  * (src/simkaMin/SimkaMinDistance.hpp:190-303).  hashes/counts: n sketches of s entries, ascending,
  * zero hashes at the front are padding (loadSketches :521-586).  Outputs n*n float32 row-major. */

@@ -42,6 +42,10 @@ class Timings(C.Structure):
                 ("superk_samples", C.c_uint64), ("superk_fallbacks", C.c_uint64)]
 
 
+class SketchInfo(C.Structure):
+    _fields_ = [("attempts", C.c_uint64), ("keys_counted", C.c_uint64), ("distinct_dumped", C.c_uint64)]
+
+
 # every symbol include/simka_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "simka_gpu_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(SimkaParams)]),
@@ -77,6 +81,7 @@ SYMBOLS = {
                             C.POINTER(C.c_uint32)]),
     "simkamin_gpu_sketch_filter": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, u64p, u32p,
                             C.POINTER(C.c_uint32)]),
+    "simkamin_gpu_last_sketch_info": (C.c_int, [C.POINTER(SketchInfo)]),
     "simkamin_gpu_distance": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, f32p, f32p, f32p]),
     "simka_host_kmers": (C.c_uint64, [C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p, C.POINTER(C.c_uint8)]),
     "simka_host_minimizer": (C.c_uint64, [C.c_uint64, C.c_int, C.c_int]),

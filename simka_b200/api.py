@@ -329,6 +329,17 @@ def simkamin_sketch(seqs: np.ndarray, read_off: np.ndarray, kmer_size: int, sket
     return h, c, int(n.value)
 
 
+def simkamin_last_sketch_info() -> dict:
+    """How the last simkamin_sketch call of this thread got its sketch (bottom-s pre-filter, include/simka_b200.h):
+    counting passes run, k-mer occurrences that passed the hash bound, distinct hashes brought back to the host."""
+    L = _lib.load()
+    info = _lib.SketchInfo()
+    rc = L.simkamin_gpu_last_sketch_info(C.byref(info))
+    if rc != 0:
+        raise SimkaError(f"simkamin_gpu_last_sketch_info: {ERRORS.get(rc, rc)}")
+    return {"attempts": int(info.attempts), "keys_counted": int(info.keys_counted), "distinct_dumped": int(info.distinct_dumped)}
+
+
 def simkamin_distance(hashes: np.ndarray, counts: np.ndarray, device: int = 0):
     """All-pairs SimkaMin Jaccard / Bray-Curtis (src/simkaMin/SimkaMinDistance.hpp:190-303).
     -> (jaccard float32[n,n], braycurtis float32[n,n], kernel_ms)"""

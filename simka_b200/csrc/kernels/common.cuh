@@ -35,6 +35,7 @@ struct KParams {
     int shard_rank, shard_count;
     int key_mode;        // 0: key = mix(canonical k-mer) (2k bits); 1: key = MurmurHash3(canonical k-mer) (64 bits, SimkaMin sketches)
     uint32_t seed;       // MurmurHash3 seed
+    uint64_t key_max;    // key_mode 1: hashes above this bound are dropped at extraction (bottom-s pre-filter of the sketches; ~0 = keep all)
 };
 
 __device__ __forceinline__ bool shard_keep(uint64_t h, const KParams &kp) {

@@ -159,6 +159,7 @@ k_extract(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
             const uint64_t h = kp.key_mode ? simka::murmur3_x64_128_u64(canon, kp.seed) : simka::mix_fwd(canon, kp.mix);
             bool keep = (okmask >> (31 - j)) & 1u;
             if (SHARDED) keep = keep && shard_keep(h, kp);
+            if (kp.key_mode) keep = keep && h <= kp.key_max;  // sketches: only the low end of the hash range is ever selected
             keys[j] = h;
             if (keep) {
                 vmask |= 1u << j;

@@ -266,6 +266,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
     ctx->kp.shard_count = p->shard_count > 1 ? p->shard_count : 1;
     ctx->kp.key_mode = p->sketch_mode ? 1 : 0;
     ctx->kp.seed = p->sketch_seed;
+    ctx->kp.key_max = ~0ull;
     ctx->W = 2 * p->kmer_size;
     if (ctx->kp.key_mode) {  // keys are 64-bit MurmurHash3 values: partition on their top bits
         ctx->W = 64;
@@ -1149,6 +1150,8 @@ int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
     return SIMKA_OK;
 }
 
+static thread_local simkamin_sketch_info g_sketch_info = {0, 0, 0};  // of this thread's last simkamin_gpu_sketch* call
+
 // filter: the -filter option (processFiltered, src/simkaMin/SimkaMinCount.hpp:341-380): only k-mers seen at least twice are
 // sketched.  The reference remembers first occurrences in a Bloom filter of max-memory * 8 / cores bits; this build counts
 // exactly (stage 1 with abundance-min 2), i.e. it equals the reference wherever that filter answers no false positive.
@@ -1170,15 +1173,34 @@ static int simkamin_sketch_impl(bool filter, int device, int kmer_size, uint32_t
     std::vector<uint64_t> hk;
     std::vector<uint32_t> hc;
     uint64_t n = 0;
-    do {
+    // Bottom-s pre-filter: only hashes <= key_max are extracted at all.  Every occurrence of such a hash is kept, so the counts
+    // are exact, and as soon as >= sketch_size distinct (solid) hashes lie below the bound its s smallest are the s smallest of
+    // the sample.  The bound starts at the fraction 16 * s / positions of the hash range (enough while a k-mer occurs <= 16 times
+    // on average) and grows 8-fold until the sketch fills or the whole range is taken; small samples take the whole range at once.
+    const uint64_t n_pos = n_words * 32;
+    double frac = 1.0;
+    { const char *e = getenv("SIMKA_B200_SKETCH_PREFILTER");  // =0: count every hash of the sample (the path before the pre-filter)
+      if (!(e && e[0] == '0') && n_pos > 64ull * sketch_size) frac = 16.0 * (double)sketch_size / (double)n_pos; }
+    g_sketch_info = simkamin_sketch_info{0, 0, 0};
+    for (;;) {
+        ctx->kp.key_max = frac >= 1.0 ? ~0ull : (uint64_t)(frac * 18446744073709551616.0);
         // exact multiset count of the hashes: stage 1 with key = MurmurHash3(canonical k-mer)
         if ((rc = simka_gpu_push_reads(ctx, 0, packed, bad, n_words, n_reads)) != SIMKA_OK) break;
         if ((rc = simka_gpu_finish_sample(ctx, 0, nullptr)) != SIMKA_OK) break;
         if ((rc = simka_gpu_dump_sample_counts(ctx, 0, nullptr, nullptr, &n)) != SIMKA_OK) break;
+        g_sketch_info.attempts++;
+        g_sketch_info.keys_counted += ctx->kmers_in;
+        g_sketch_info.distinct_dumped = n;
+        if (n < sketch_size && ctx->kp.key_max != ~0ull) {  // not enough distinct hashes below the bound: widen it
+            frac *= 8.0;
+            if ((rc = simka_gpu_reset(ctx)) != SIMKA_OK) break;
+            continue;
+        }
         hk.resize(std::max<uint64_t>(n, 1));
         hc.resize(std::max<uint64_t>(n, 1));
-        if ((rc = simka_gpu_dump_sample_counts(ctx, 0, hk.data(), hc.data(), &n)) != SIMKA_OK) break;  // ascending hashes
-    } while (0);
+        rc = simka_gpu_dump_sample_counts(ctx, 0, hk.data(), hc.data(), &n);  // ascending hashes
+        break;
+    }
     if (rc != SIMKA_OK) { simka_gpu_destroy(ctx); return rc; }
     const uint32_t n_sel = (uint32_t)std::min<uint64_t>(n, sketch_size);
     // the order-dependent count of the largest member once the sketch is complete (only when it can be complete):
@@ -1231,6 +1253,12 @@ int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_
 int simkamin_gpu_sketch_filter(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
                                uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected) {
     return simkamin_sketch_impl(true, device, kmer_size, sketch_size, seed, packed, bad, n_words, n_reads, hashes_out, counts_out, n_selected);
+}
+
+int simkamin_gpu_last_sketch_info(simkamin_sketch_info *out) {
+    if (!out) return SIMKA_ERR_INVALID;
+    *out = g_sketch_info;
+    return SIMKA_OK;
 }
 
 int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *counts, uint32_t n, uint32_t s, float *jaccard,

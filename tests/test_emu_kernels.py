@@ -220,6 +220,35 @@ def test_simkamin_sketch_reproduces_reference_truth(golden_dir, k, max_reads, nb
     assert simkamin_csv(ids, bc) == open(os.path.join(tdir, "mat_abundance_braycurtis.csv")).read()
 
 
+@pytest.mark.parametrize("filt", [False, True])
+def test_simkamin_sketch_prefilter_is_exact(monkeypatch, filt):
+    """bottom-s pre-filter (only hashes below a bound are extracted; the bound widens 8-fold until the sketch fills): same sketch
+    as the oracle and as the whole-range path, with fewer k-mers counted; high multiplicity forces the widening"""
+    samples = (small_samples(1, 1500, n_genomes=2, genome_len=600, err=0.0) + small_samples(1, 400, n_genomes=40, genome_len=1500) +
+               nasty_samples()[:2])  # the first one: error-free reads at 190x coverage, a k-mer occurs ~170 times
+    widened = 0
+    for seqs, off in samples:
+        for k, s in [(21, 50), (31, 200), (21, 1000)]:
+            oh, oc, on = oracle.simkamin_sketch(seqs, off, k, s, seed=11, filter=filt)
+            monkeypatch.setenv("SIMKA_B200_SKETCH_PREFILTER", "0")
+            fh, fc, fn = simka_b200.simkamin_sketch(seqs, off, k, s, seed=11, filter=filt)
+            full = simka_b200.simkamin_last_sketch_info()
+            monkeypatch.delenv("SIMKA_B200_SKETCH_PREFILTER")
+            gh, gc, gn = simka_b200.simkamin_sketch(seqs, off, k, s, seed=11, filter=filt)
+            info = simka_b200.simkamin_last_sketch_info()
+            assert gn == on == fn
+            np.testing.assert_array_equal(gh, oh)
+            np.testing.assert_array_equal(gc, oc)
+            np.testing.assert_array_equal(fh, oh)
+            np.testing.assert_array_equal(fc, oc)
+            assert full["attempts"] == 1
+            n_pos = 32 * ((len(seqs) + len(off) - 1 + 31) // 32)
+            if n_pos > 64 * s + 64 and info["attempts"] == 1 and gn == s:
+                assert info["keys_counted"] < full["keys_counted"] and info["distinct_dumped"] <= full["distinct_dumped"]
+            widened += info["attempts"] > 1
+    assert widened > 0
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # experimental super-k-mer front end of stage 1 (SIMKA_B200_SUPERK=1, simka_b200/csrc/kernels/superk.cuh)
 # ---------------------------------------------------------------------------------------------------------------
