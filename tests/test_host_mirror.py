@@ -35,6 +35,14 @@ def test_testkmer_known_answers():
     assert c.tolist() == [11, 2, 16, 36, 9, 8, 24, 6, 17, 20] and v.all()
 
 
+def test_testkmer_badchar_known_answers():
+    """GT/unit/src/kmer/TestKmer.cpp:509-569: validity and value (bad nucleotide -> G) of every window, ModelDirect k = 11"""
+    from test_oracle_golden import BADCHAR_SEQ, BADCHAR_VALID, kmer_to_string
+    d, v = host_kmers(BADCHAR_SEQ, 11, canonical=False)
+    assert v.tolist() == BADCHAR_VALID
+    assert [kmer_to_string(x, 11) for x in d] == [BADCHAR_SEQ[i:i + 11].decode().replace("N", "G") for i in range(32)]
+
+
 @pytest.mark.parametrize("k", [3, 15, 21, 31])
 def test_model_matches_oracle(k):
     rng = np.random.default_rng(k)

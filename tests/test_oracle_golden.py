@@ -27,6 +27,24 @@ def test_kmer_model_known_answers():
     assert km.tolist() == [11, 2, 16, 36, 9, 8, 24, 6, 17, 20] and va.all()
 
 
+BADCHAR_SEQ = b"ACGNCNTGCTAGCTATTTAGCTTTAGANAGTAGATGACGCNC"
+BADCHAR_VALID = [False] * 6 + [True] * 11 + [False] * 11 + [True, True, False, False]
+
+
+def kmer_to_string(v, k):
+    """Model::toString: first base most significant, A=0 C=1 T=2 G=3"""
+    return "".join("ACTG"[(int(v) >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def test_kmer_badchar_known_answers():
+    """gatb-core test/unit/src/kmer/TestKmer.cpp:509-569 (kmer_badchar): ModelDirect, k = 11, validity of the 32 windows and the
+    VALUE of every window, valid or not -- a bad nucleotide reads as G (its (c>>1)&3 code)"""
+    km, va = oracle.direct_kmers(BADCHAR_SEQ, 11)
+    assert va.astype(bool).tolist() == BADCHAR_VALID
+    for i in range(32):
+        assert kmer_to_string(km[i], 11) == BADCHAR_SEQ[i:i + 11].decode().replace("N", "G")
+
+
 def test_kmer_model_bad_chars():
     """windows containing a non-ACGT char are invalid (Model.hpp:754-758); lower case is valid"""
     km, va = oracle.canonical_kmers(b"ACGTNACGTAC", 4)
