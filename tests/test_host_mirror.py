@@ -122,6 +122,29 @@ def test_bank_reads_like_the_oracle(tmp_path, golden_dir):
     assert bytes(s) == bytes(s1) + bytes(s2) and len(o) == len(o1) + len(o2) - 1
 
 
+def test_testbank_known_answers(golden_dir):
+    """The sample banks of the reference's own bank tests (GT/unit/src/bank/TestBank.cpp:98-250, data files of gatb-core test/db
+    copied to tests/golden/bankdb): bank_checkSample1 -- 20 sequences of 20 letters, sequence i = "ARNDCQEGHILKMFPSTWYV" rotated
+    left by i, plain and gzip; bank_checkSample2 -- 20 records with a comment and no data; bank_checkSample3 -- 7 non-empty
+    fastq records, plain and gzip.  Host reader and oracle reader."""
+    db = os.path.join(golden_dir, "bankdb")
+    text = b"ARNDCQEGHILKMFPSTWYV"
+    for reader in (read_bank, oracle.read_fastx):
+        for name in ("sample1.fa", "sample1.fa.gz"):
+            s, o = reader(os.path.join(db, name))
+            assert o.tolist() == [20 * i for i in range(21)], name
+            for i in range(20):
+                assert bytes(s[20 * i:20 * i + 20]) == text[i:] + text[:i]
+        s, o = reader(os.path.join(db, "sample2.fa"))
+        assert o.tolist() == [0] * 21 and len(s) == 0
+        for name in ("sample.fastq", "sample.fastq.gz"):
+            s, o = reader(os.path.join(db, name))
+            assert len(o) == 8 and (np.diff(o.astype(np.int64)) > 0).all(), name
+    a, ao = read_bank(os.path.join(db, "sample.fastq"))
+    b, bo = read_bank(os.path.join(db, "sample.fastq.gz"))
+    assert bytes(a) == bytes(b) and ao.tolist() == bo.tolist()
+
+
 def test_cli_argument_handling(tmp_path):
     """same conventions as the reference's main: EXCEPTION: <msg> on stdout, EXIT_FAILURE (src/SimkaPotara.cpp:147-163)"""
     exe = str(SIMKA_BIN)
