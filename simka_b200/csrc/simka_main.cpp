@@ -12,6 +12,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -143,26 +144,55 @@ void write_text(const std::string &path, const std::string &text) {
     fclose(f);
 }
 
+// A chunk of packed reads on the host.  Pinned (cudaHostAlloc) once the GPU context exists; chunks filled BEFORE that -- the
+// parser threads start at once while the CUDA context takes 1-2 s to come up, and a pinned allocation would wait for it -- are
+// plain page-aligned memory, which simka_gpu_push_reads copies through the driver's staging buffers.
 struct PinnedChunk {
     uint64_t *packed = nullptr;
     uint32_t *bad = nullptr;
     uint64_t cap_words = 0;
-    void reserve(uint64_t words) {
+    bool pinned = false;
+    void reserve(uint64_t words, bool may_pin) {
         if (words + 1 <= cap_words) return;
         release();
         cap_words = words + words / 8 + 1024;
         void *p = nullptr, *b = nullptr;
-        if (simka_gpu_host_alloc(&p, cap_words * 8) != SIMKA_OK || simka_gpu_host_alloc(&b, cap_words * 4) != SIMKA_OK)
-            throw bank::Exception("cannot allocate pinned host memory");
+        if (may_pin) {
+            if (simka_gpu_host_alloc(&p, cap_words * 8) != SIMKA_OK || simka_gpu_host_alloc(&b, cap_words * 4) != SIMKA_OK)
+                throw bank::Exception("cannot allocate pinned host memory");
+        } else {
+            p = aligned_alloc(4096, (cap_words * 8 + 4095) & ~(size_t)4095);
+            b = aligned_alloc(4096, (cap_words * 4 + 4095) & ~(size_t)4095);
+            if (!p || !b) { free(p); free(b); throw bank::Exception("cannot allocate host memory"); }
+        }
+        pinned = may_pin;
         packed = (uint64_t *)p;
         bad = (uint32_t *)b;
     }
     void release() {
-        if (packed) simka_gpu_host_free(packed);
-        if (bad) simka_gpu_host_free(bad);
+        if (pinned) {
+            if (packed) simka_gpu_host_free(packed);
+            if (bad) simka_gpu_host_free(bad);
+        } else {
+            free(packed);
+            free(bad);
+        }
         packed = nullptr; bad = nullptr; cap_words = 0;
     }
 };
+
+// bytes of one sample's input files (gzip files weighted by a typical 4x expansion)
+uint64_t sample_input_bytes(const SampleSpec &s) {
+    uint64_t total = 0;
+    for (auto &g : s.groups)
+        for (auto &f : g) {
+            struct stat st;
+            if (stat(f.c_str(), &st) != 0) continue;
+            const bool gz = f.size() > 3 && f.compare(f.size() - 3, 3, ".gz") == 0;
+            total += (uint64_t)st.st_size * (gz ? 4 : 1);
+        }
+    return total;
+}
 
 void check(simka_ctx *ctx, int rc, const char *what) {
     if (rc != SIMKA_OK) throw bank::Exception(std::string(what) + ": " + (ctx ? simka_gpu_last_error(ctx) : "failed") + " (code " + std::to_string(rc) + ")");
@@ -234,7 +264,19 @@ int run(int argc, char **argv) {
     std::condition_variable cv;
     size_t next_sample = 0, consumed = 0;
     const size_t workers = std::max<size_t>(1, std::min<size_t>({(size_t)nthreads, N, (size_t)16}));
-    const size_t inflight = workers + 2;
+    // samples parsed ahead of the GPU: as many as 80 % of -max-memory holds in packed form (0.375 B per base, about 0.4 B per
+    // input byte), at least workers + 2 -- with the default 5000 MB all 32 samples of a 5 GB run are packed while CUDA starts
+    size_t inflight = workers + 2;
+    {
+        uint64_t in_bytes = 0;
+        for (const SampleSpec &sp : samples) in_bytes += sample_input_bytes(sp);
+        const double per_sample = 0.4 * (double)in_bytes / (double)N + 1.0;
+        const double fit = 0.8 * (double)o.maxMemory * 1048576.0 / per_sample;
+        inflight = std::max(inflight, (size_t)std::min<double>((double)N, fit));
+    }
+    std::atomic<bool> gpu_ready{false};
+    const bool pageable_only = getenv("SIMKA_B200_PAGEABLE_INPUT") != nullptr;  // tests: every chunk takes the before-the-context path
+    double t_packed = 0;  // when the last sample so far came out of the parser threads (under mu)
     auto get_chunk = [&](uint64_t words) {
         PinnedChunk *c = nullptr;
         {
@@ -244,7 +286,7 @@ int run(int argc, char **argv) {
             if (!c && !pool.empty()) { c = pool.back(); pool.pop_back(); }
         }
         if (!c) c = new PinnedChunk();
-        c->reserve(words);
+        c->reserve(words, gpu_ready.load() && !pageable_only);
         return c;
     };
     auto worker = [&]() {
@@ -280,6 +322,7 @@ int run(int argc, char **argv) {
             {
                 std::lock_guard<std::mutex> lk(mu);
                 P.ready = true;
+                t_packed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             }
             cv.notify_all();
         }
@@ -300,6 +343,8 @@ int run(int argc, char **argv) {
     int rc = simka_gpu_create(&ctx, &prm);
     const double t_create = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc != SIMKA_OK) { { std::lock_guard<std::mutex> lk(mu); next_sample = N; } cv.notify_all(); for (auto &t : pool_threads) t.join(); throw bank::Exception("simka_gpu_create failed (code " + std::to_string(rc) + "): a CUDA device is required, there is no CPU path"); }
+
+    gpu_ready.store(true);
 
     std::vector<simka_sample_totals> totals(N);
     std::string failure;
@@ -374,8 +419,8 @@ int run(int argc, char **argv) {
         simka_gpu_get_timings(ctx, &tm);
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("\nNb distinct kmers: %llu   shared by >= 2 samples: %llu\n", (unsigned long long)v.nb_distinct_kmers, (unsigned long long)v.nb_shared_kmers);
-        printf("GPU time: %.1f ms counting + %.1f ms merging, %llu kernel launches; wall %.2f s (GPU context ready at %.2f s, read + count done at %.2f s, %zu parser threads)\n", tm.samples_ms,
-               tm.merge_ms, (unsigned long long)tm.kernel_launches, wall, t_create, t_stage1, workers);
+        printf("GPU time: %.1f ms counting + %.1f ms merging, %llu kernel launches; wall %.2f s (GPU context ready at %.2f s, all samples parsed + packed at %.2f s, read + count done at %.2f s, %zu parser threads, %zu samples ahead)\n", tm.samples_ms,
+               tm.merge_ms, (unsigned long long)tm.kernel_launches, wall, t_create, t_packed, t_stage1, workers, inflight);
         printf("Output dir: %s\n", o.out.c_str());
     }
     simka_gpu_destroy(ctx);

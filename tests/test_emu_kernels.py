@@ -416,8 +416,12 @@ def emulated_cli(monkeypatch):
     monkeypatch.setenv("LD_LIBRARY_PATH", cli_env()["LD_LIBRARY_PATH"])
 
 
-def test_cli_simka_reproduces_truth(emulated_cli, tmp_path, golden_dir):
+@pytest.mark.parametrize("pageable", [False, True])
+def test_cli_simka_reproduces_truth(emulated_cli, monkeypatch, tmp_path, golden_dir, pageable):
+    """pageable: the chunks the parser threads fill before the GPU context exists are plain memory (simka_main.cpp); forced for all"""
     import test_gpu_parity as G
+    if pageable:
+        monkeypatch.setenv("SIMKA_B200_PAGEABLE_INPUT", "1")
     for i, (k, t) in enumerate([(21, 0), (31, 2)]):
         d = tmp_path / str(i)
         d.mkdir()
