@@ -243,6 +243,33 @@ int simka_write_matrices(const simka_stats_view *s, const char *const *ids, cons
 
 // ---- read packing ----------------------------------------------------------------------------------
 
+// 32 characters -> 32 two-bit codes (first character most significant) + 32 bad bits, with AVX2 + BMI2 when the CPU has them
+// (run-time dispatch): the bytes are reversed so that movemask / pext, which put byte 0 in the low bits, deliver the first
+// character on top; code = (c >> 1) & 3 is bits 1-2 of every byte, gathered by pext; bad = not in ACGTacgt.
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define SIMKA_PACK_SIMD 1
+__attribute__((target("avx2,bmi2"))) static inline void pack32_avx2(const unsigned char *sp, uint64_t *v, uint32_t *bb) {
+    const __m256i rev16 = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(sp));
+    x = _mm256_shuffle_epi8(x, rev16);
+    x = _mm256_permute2x128_si256(x, x, 1);  // byte i = character 31 - i
+    const __m256i u = _mm256_and_si256(x, _mm256_set1_epi8((char)0xDF));
+    const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, _mm256_set1_epi8('A')), _mm256_cmpeq_epi8(u, _mm256_set1_epi8('C'))),
+                                       _mm256_or_si256(_mm256_cmpeq_epi8(u, _mm256_set1_epi8('G')), _mm256_cmpeq_epi8(u, _mm256_set1_epi8('T'))));
+    *bb = ~(uint32_t)_mm256_movemask_epi8(ok);
+    const uint64_t m = 0x0606060606060606ull;
+    *v = _pext_u64((uint64_t)_mm256_extract_epi64(x, 0), m) | (_pext_u64((uint64_t)_mm256_extract_epi64(x, 1), m) << 16) |
+         (_pext_u64((uint64_t)_mm256_extract_epi64(x, 2), m) << 32) | (_pext_u64((uint64_t)_mm256_extract_epi64(x, 3), m) << 48);
+}
+static bool pack_simd_available() {
+    static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && !getenv("SIMKA_B200_PACK_SCALAR");
+    return ok;
+}
+#else
+#define SIMKA_PACK_SIMD 0
+#endif
+
 uint64_t simka_pack_words(uint64_t total_bases, uint64_t n_reads) { return (total_bases + n_reads + 31) / 32; }
 
 uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n_reads, uint64_t *packed, uint32_t *bad, int nthreads) {
@@ -284,6 +311,10 @@ uint64_t simka_pack_reads_k(const char *seqs, const uint64_t *read_off, uint64_t
         uint64_t w = w0, acc = 0;
         uint32_t bacc = 0;
         int cnt = 0;  // positions already in (acc, bacc)
+#if SIMKA_PACK_SIMD
+        const bool simd = pack_simd_available();
+        const unsigned char *const simd_end = reinterpret_cast<const unsigned char *>(seqs) + (n_reads ? read_off[n_reads] : 0);  // loads of 32 bytes stay below
+#endif
         while (w < w1) {
             if (r >= n_reads) {  // past the last read: bad padding
                 acc <<= 2 * (32 - cnt);
@@ -300,6 +331,20 @@ uint64_t simka_pack_reads_k(const char *seqs, const uint64_t *read_off, uint64_t
             } else {  // a run of bases of read r: up to the end of the current word
                 const unsigned char *sp = reinterpret_cast<const unsigned char *>(seqs) + rbeg + o;
                 uint64_t avail = rend - (rbeg + o);
+#if SIMKA_PACK_SIMD
+                if (simd && sp + 32 <= simd_end) {  // 32 characters at once, of which the first `take` belong to this word
+                    const int take = (int)std::min<uint64_t>(avail, (uint64_t)(32 - cnt));
+                    uint64_t v; uint32_t bb;
+                    pack32_avx2(sp, &v, &bb);
+                    if (!badchars) bb = 0;
+                    if (take == 32) { acc = v; bacc = bb; }
+                    else { acc = (acc << (2 * take)) | (v >> (2 * (32 - take))); bacc = (bacc << take) | (bb >> (32 - take)); }
+                    cnt += take;
+                    o += take;
+                    if (cnt == 32) { packed[w] = acc; bad[w] = bacc; w++; acc = 0; bacc = 0; cnt = 0; }
+                    continue;
+                }
+#endif
                 if (cnt == 0 && avail >= 32) {  // fast path: a whole word inside the read
                     uint64_t v = 0; uint32_t bb = 0;
                     for (int j = 0; j < 32; j++) { const unsigned c = sp[j]; v = (v << 2) | ((c >> 1) & 3u); bb = (bb << 1) | btt[c]; }

@@ -70,6 +70,48 @@ def test_pack_reads_layout(k):
         np.testing.assert_array_equal(got, exp)
 
 
+PACK_DIFF_SCRIPT = r"""
+import hashlib, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import numpy as np
+import simka_b200
+from helpers import nasty_samples, synthetic_samples
+h = hashlib.sha256()
+rng = np.random.default_rng(1)
+cases = nasty_samples() + synthetic_samples(2, 2000)
+alpha = np.frombuffer(b"ACGTacgtNnX-\x00\xff", np.uint8)
+for t in range(40):  # ragged reads (lengths 0..200, empty ones, odd characters), buffers that end right after the last base
+    lens = rng.integers(0, 200, size=rng.integers(1, 400))
+    off = np.zeros(len(lens) + 1, np.uint64); off[1:] = np.cumsum(lens)
+    cases.append((alpha[rng.integers(0, len(alpha), int(off[-1]))], off))
+for seqs, off in cases:
+    for k in (31, 15):
+        for nt in (1, 3):
+            p, b, nw = simka_b200.pack_reads(seqs, off, kmer_size=k, nthreads=nt)
+            h.update(np.asarray(p)[:nw + 1].tobytes()); h.update(np.asarray(b)[:nw + 1].tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_pack_reads_simd_equals_scalar():
+    """simka_pack_reads packs 32 characters at a time with AVX2 + BMI2 where the CPU has them (run-time dispatch, simka_host.cpp);
+    SIMKA_B200_PACK_SCALAR=1 keeps the portable loop: same bytes out of both on ragged / dirty inputs (the layout itself is
+    pinned by test_pack_reads_layout, which runs on whichever path this machine takes)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for scalar in (False, True):
+        env = dict(os.environ)
+        env.pop("SIMKA_B200_PACK_SCALAR", None)
+        if scalar:
+            env["SIMKA_B200_PACK_SCALAR"] = "1"
+        r = subprocess.run([sys.executable, "-c", PACK_DIFF_SCRIPT, root], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and len(outs[0]) == 64
+
+
 def stats_from_oracle(run):
     st = simka_b200.SimkaStatistics(run.n, run.simple, run.complex_)
     st.totals[:] = run.all_totals()
