@@ -10,12 +10,18 @@
 // -filter (SimkaMinCount.hpp:341-380): first occurrences are remembered exactly instead of in the reference's Bloom filter.
 #include <sys/stat.h>
 
+#include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "host/simka_input.hpp"
 #include "host/stage_files.hpp"
@@ -73,23 +79,85 @@ int do_sketch(std::map<std::string, std::string> &kv) {
     std::vector<uint64_t> hashes(s);
     std::vector<uint32_t> counts(s);
     std::vector<Entry> rec(s);
-    std::string seqs;
-    std::vector<uint64_t> off;
-    for (const SampleSpec &sp : samples) {
-        seqs.clear();
-        off.assign(1, 0);
-        read_sample_into(sp, filter, max_reads, seqs, off, [] {});
-        const uint64_t words = simka_pack_words(seqs.size(), off.size() - 1);
-        std::vector<uint64_t> packed(words + 1);
-        std::vector<uint32_t> bad(words + 1);
-        simka_pack_reads(seqs.data(), off.data(), off.size() - 1, packed.data(), bad.data(), (int)geti(kv, "-nb-cores", 0));
-        uint32_t nsel = 0;
-        const int rc = (abundance_filter ? simkamin_gpu_sketch_filter : simkamin_gpu_sketch)((int)geti(kv, "-device", 0), k, s, seed, packed.data(), bad.data(), words,
-                                                                                   off.size() - 1, hashes.data(), counts.data(), &nsel);
-        if (rc != SIMKA_OK) throw bank::Exception("simkamin_gpu_sketch failed (code " + std::to_string(rc) + "): a CUDA device is required");
-        for (uint32_t i = 0; i < s; i++) { rec[i].hash = hashes[i]; rec[i].count = counts[i]; rec[i].pad = 0; }
-        fwrite(rec.data(), sizeof(Entry), s, f);
+    // Host pipeline: worker threads parse + 2-bit pack whole datasets (files are independent, so this scales with the cores;
+    // the reference sketches its datasets in parallel the same way, SimkaMinCount.hpp:1129-1260), the main thread sketches
+    // them on the GPU in input order and writes the records; at most `window` datasets are packed ahead.
+    struct Prepared {
+        std::vector<uint64_t> packed;
+        std::vector<uint32_t> bad;
+        uint64_t words = 0, reads = 0;
+        bool ready = false;
+        std::string error;
+    };
+    std::vector<Prepared> prep(n);
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t next = 0, consumed = 0;
+    const long long cores = geti(kv, "-nb-cores", 0);
+    const size_t hw = cores > 0 ? (size_t)cores : (size_t)std::max(1u, std::thread::hardware_concurrency());
+    const size_t workers = std::max<size_t>(1, std::min<size_t>({hw, (size_t)n, (size_t)16}));
+    const size_t window = workers + 2;
+    const int pack_threads = (int)std::max<size_t>(1, hw / workers);
+    auto worker = [&]() {
+        std::string seqs;
+        std::vector<uint64_t> off;
+        for (;;) {
+            size_t i;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return next >= n || next < consumed + window; });
+                if (next >= n) return;
+                i = next++;
+            }
+            Prepared &P = prep[i];
+            try {
+                seqs.clear();
+                off.assign(1, 0);
+                read_sample_into(samples[i], filter, max_reads, seqs, off, [] {});
+                P.reads = off.size() - 1;
+                P.words = simka_pack_words(seqs.size(), P.reads);
+                P.packed.resize(P.words + 1);
+                P.bad.resize(P.words + 1);
+                simka_pack_reads(seqs.data(), off.data(), P.reads, P.packed.data(), P.bad.data(), pack_threads);
+            } catch (const std::exception &e) { P.error = e.what(); if (P.error.empty()) P.error = "read error"; }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                P.ready = true;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> threads;
+    for (size_t w = 0; w < workers; w++) threads.emplace_back(worker);
+    std::string failure;
+    for (size_t i = 0; i < n && failure.empty(); i++) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return prep[i].ready; });
+        }
+        Prepared &P = prep[i];
+        if (!P.error.empty()) failure = P.error;
+        else {
+            uint32_t nsel = 0;
+            const int rc = (abundance_filter ? simkamin_gpu_sketch_filter : simkamin_gpu_sketch)((int)geti(kv, "-device", 0), k, s, seed, P.packed.data(), P.bad.data(), P.words,
+                                                                                       P.reads, hashes.data(), counts.data(), &nsel);
+            if (rc != SIMKA_OK) failure = "simkamin_gpu_sketch failed (code " + std::to_string(rc) + "): a CUDA device is required";
+            else {
+                for (uint32_t q = 0; q < s; q++) { rec[q].hash = hashes[q]; rec[q].count = counts[q]; rec[q].pad = 0; }
+                fwrite(rec.data(), sizeof(Entry), s, f);
+            }
+        }
+        std::vector<uint64_t>().swap(P.packed);
+        std::vector<uint32_t>().swap(P.bad);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            consumed = i + 1;
+            if (!failure.empty()) next = n;  // stop the workers
+        }
+        cv.notify_all();
     }
+    for (auto &t : threads) t.join();
+    if (!failure.empty()) { fclose(f); throw bank::Exception(failure); }
     for (const SampleSpec &sp : samples) {
         const uint8_t len = (uint8_t)sp.id.size();
         fwrite(&len, 1, 1, f);
