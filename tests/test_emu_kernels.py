@@ -224,8 +224,8 @@ def test_simkamin_sketch_reproduces_reference_truth(golden_dir, k, max_reads, nb
 def test_simkamin_sketch_prefilter_is_exact(monkeypatch, filt):
     """bottom-s pre-filter (only hashes below a bound are extracted; the bound widens 8-fold until the sketch fills): same sketch
     as the oracle and as the whole-range path, with fewer k-mers counted; high multiplicity forces the widening"""
-    samples = (small_samples(1, 1500, n_genomes=2, genome_len=600, err=0.0) + small_samples(1, 400, n_genomes=40, genome_len=1500) +
-               nasty_samples()[:2])  # the first one: error-free reads at 190x coverage, a k-mer occurs ~170 times
+    samples = (small_samples(1, 800, n_genomes=2, genome_len=600, err=0.0) + small_samples(1, 300, n_genomes=40, genome_len=1500) +
+               nasty_samples()[:1])  # the first one: error-free reads at 100x coverage, a k-mer occurs ~90 times
     widened = 0
     for seqs, off in samples:
         for k, s in [(21, 50), (31, 200), (21, 1000)]:
