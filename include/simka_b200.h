@@ -232,6 +232,10 @@ typedef struct simkamin_sketch_info {
     uint64_t attempts, keys_counted, distinct_dumped;
 } simkamin_sketch_info;
 int simkamin_gpu_last_sketch_info(simkamin_sketch_info *out);
+/* The sketch entries keep one stage-1 context (streams, events, device work buffers) between calls with the same device, k, seed
+ * and filter, so that a run over many datasets does not allocate and free them per dataset (calls are serialised on it;
+ * SIMKA_B200_SKETCH_CTX_CACHE=0: a fresh context per call).  This frees it. */
+void simkamin_gpu_release_cache(void);
 
 /* ---- SimkaMin: replaces ComputeDistanceManager::computeDistance_unsynch over all pairs ------------
  * (src/simkaMin/SimkaMinDistance.hpp:190-303).  hashes/counts: n sketches of s entries, ascending,

@@ -82,6 +82,7 @@ SYMBOLS = {
     "simkamin_gpu_sketch_filter": (C.c_int, [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, u64p, u32p,
                             C.POINTER(C.c_uint32)]),
     "simkamin_gpu_last_sketch_info": (C.c_int, [C.POINTER(SketchInfo)]),
+    "simkamin_gpu_release_cache": (None, []),
     "simkamin_gpu_distance": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, f32p, f32p, f32p]),
     "simka_host_kmers": (C.c_uint64, [C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p, C.POINTER(C.c_uint8)]),
     "simka_host_minimizer": (C.c_uint64, [C.c_uint64, C.c_int, C.c_int]),

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <new>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1151,6 +1152,14 @@ int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
 }
 
 static thread_local simkamin_sketch_info g_sketch_info = {0, 0, 0};  // of this thread's last simkamin_gpu_sketch* call
+struct SketchCtxCache {
+    std::mutex mu;
+    simka_ctx *ctx = nullptr;
+    int device = -1, k = 0;
+    uint32_t seed = 0;
+    bool filter = false;
+};
+static SketchCtxCache g_sketch_cache;
 
 // filter: the -filter option (processFiltered, src/simkaMin/SimkaMinCount.hpp:341-380): only k-mers seen at least twice are
 // sketched.  The reference remembers first occurrences in a Bloom filter of max-memory * 8 / cores bits; this build counts
@@ -1167,9 +1176,25 @@ static int simkamin_sketch_impl(bool filter, int device, int kmer_size, uint32_t
     prm.device = device;
     prm.sketch_mode = 1;
     prm.sketch_seed = seed;
+    // One stage-1 context is kept between calls (same device / k / seed / filter): a sketch run calls this once per dataset and
+    // would otherwise create and free its streams, events and multi-GB work buffers every time.  Calls are serialised on it.
+    std::lock_guard<std::mutex> cache_lock(g_sketch_cache.mu);
+    SketchCtxCache &cc = g_sketch_cache;
+    const bool use_cache = !(getenv("SIMKA_B200_SKETCH_CTX_CACHE") && getenv("SIMKA_B200_SKETCH_CTX_CACHE")[0] == '0');
     simka_ctx *ctx = nullptr;
-    int rc = simka_gpu_create(&ctx, &prm);
-    if (rc != SIMKA_OK) return rc;
+    int rc = SIMKA_OK;
+    if (cc.ctx && use_cache && cc.device == device && cc.k == kmer_size && cc.seed == seed && cc.filter == filter && simka_gpu_reset(cc.ctx) == SIMKA_OK) {
+        ctx = cc.ctx;
+    } else {
+        if (cc.ctx) { simka_gpu_destroy(cc.ctx); cc.ctx = nullptr; }
+        rc = simka_gpu_create(&ctx, &prm);
+        if (rc != SIMKA_OK) return rc;
+    }
+    cc.ctx = nullptr;  // owned by this call until it ends well
+    auto keep_or_destroy = [&](bool good) {
+        if (good && use_cache) { cc.ctx = ctx; cc.device = device; cc.k = kmer_size; cc.seed = seed; cc.filter = filter; }
+        else simka_gpu_destroy(ctx);
+    };
     std::vector<uint64_t> hk;
     std::vector<uint32_t> hc;
     uint64_t n = 0;
@@ -1201,7 +1226,7 @@ static int simkamin_sketch_impl(bool filter, int device, int kmer_size, uint32_t
         rc = simka_gpu_dump_sample_counts(ctx, 0, hk.data(), hc.data(), &n);  // ascending hashes
         break;
     }
-    if (rc != SIMKA_OK) { simka_gpu_destroy(ctx); return rc; }
+    if (rc != SIMKA_OK) { keep_or_destroy(false); return rc; }
     const uint32_t n_sel = (uint32_t)std::min<uint64_t>(n, sketch_size);
     // the order-dependent count of the largest member once the sketch is complete (only when it can be complete):
     // without -filter a member enters the heap at its first occurrence and the largest one counts occurrences up to the
@@ -1236,9 +1261,9 @@ static int simkamin_sketch_impl(bool filter, int device, int kmer_size, uint32_t
             }
         }
         cudaFree(d_sk); cudaFree(d_first); cudaFree(d_second); cudaFree(d_cnt); cudaFree(d_packed); cudaFree(d_bad);
-        if (!ok) { simka_gpu_destroy(ctx); return SIMKA_ERR_CUDA; }
+        if (!ok) { keep_or_destroy(false); return SIMKA_ERR_CUDA; }
     }
-    simka_gpu_destroy(ctx);
+    keep_or_destroy(true);
     for (uint32_t i = 0; i < sketch_size; i++) { hashes_out[i] = 0; counts_out[i] = 0; }
     for (uint32_t i = 0; i < n_sel; i++) { hashes_out[sketch_size - n_sel + i] = hk[i]; counts_out[sketch_size - n_sel + i] = hc[i]; }
     if (n_selected) *n_selected = n_sel;
@@ -1253,6 +1278,11 @@ int simkamin_gpu_sketch(int device, int kmer_size, uint32_t sketch_size, uint32_
 int simkamin_gpu_sketch_filter(int device, int kmer_size, uint32_t sketch_size, uint32_t seed, const uint64_t *packed, const uint32_t *bad,
                                uint64_t n_words, uint64_t n_reads, uint64_t *hashes_out, uint32_t *counts_out, uint32_t *n_selected) {
     return simkamin_sketch_impl(true, device, kmer_size, sketch_size, seed, packed, bad, n_words, n_reads, hashes_out, counts_out, n_selected);
+}
+
+void simkamin_gpu_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_sketch_cache.mu);
+    if (g_sketch_cache.ctx) { simka_gpu_destroy(g_sketch_cache.ctx); g_sketch_cache.ctx = nullptr; }
 }
 
 int simkamin_gpu_last_sketch_info(simkamin_sketch_info *out) {

@@ -249,6 +249,25 @@ def test_simkamin_sketch_prefilter_is_exact(monkeypatch, filt):
     assert widened > 0
 
 
+def test_simkamin_sketch_context_reuse(monkeypatch):
+    """the sketch entries keep their stage-1 context between calls (same device / k / seed / filter): a larger sample after a
+    smaller one, a change of parameters and a released cache give the sketches a fresh context gives"""
+    from simka_b200 import _lib
+    small, big = small_samples(1, 60)[0], small_samples(2, 700)[1]
+    calls = [(small, 21, 50, False), (big, 21, 300, False), (small, 21, 50, False), (big, 31, 300, False), (big, 31, 300, True), (small, 31, 40, True)]
+    monkeypatch.setenv("SIMKA_B200_SKETCH_CTX_CACHE", "0")
+    fresh = [simka_b200.simkamin_sketch(sm[0], sm[1], k, s, seed=5, filter=f) for sm, k, s, f in calls]
+    monkeypatch.delenv("SIMKA_B200_SKETCH_CTX_CACHE")
+    for rnd in range(2):
+        for (sm, k, s, f), (fh, fc, fn) in zip(calls, fresh):
+            h, c, n = simka_b200.simkamin_sketch(sm[0], sm[1], k, s, seed=5, filter=f)
+            assert n == fn
+            np.testing.assert_array_equal(h, fh)
+            np.testing.assert_array_equal(c, fc)
+        _lib.load().simkamin_gpu_release_cache()
+        _lib.load().simkamin_gpu_release_cache()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # experimental super-k-mer front end of stage 1 (SIMKA_B200_SUPERK=1, simka_b200/csrc/kernels/superk.cuh)
 # ---------------------------------------------------------------------------------------------------------------
