@@ -5,6 +5,9 @@
 // (SimkaInputIterator: the files of a sample are read group by group -- a group is one ';' part -- and at most
 // `maxReads` filtered reads are taken from each group).
 #pragma once
+#include <sys/stat.h>
+
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <fstream>
@@ -148,6 +151,23 @@ template <class AfterRead>
 inline uint64_t read_sample_into(const SampleSpec &spec, const SimkaSequenceFilter &filter, uint64_t maxReads, std::string &seqs,
                                  std::vector<uint64_t> &off, AfterRead after_read) {
     uint64_t total = 0;
+    {   // room for the whole sample up front (bases < file bytes; gzip files weighted 4x; at most 1 GiB, the caller flushes in
+        // batches anyway): growing a 150 MB string by doubling re-copies it and touches twice the pages -- 0.75 -> 1.35 GB/s
+        // of FASTA per thread
+        uint64_t bytes = 0;
+        for (const auto &group : spec.groups)
+            for (const std::string &file : group) {
+                struct stat st;
+                if (::stat(file.c_str(), &st) != 0) continue;
+                const bool gz = file.size() > 3 && file.compare(file.size() - 3, 3, ".gz") == 0;
+                bytes += (uint64_t)st.st_size * (gz ? 4 : 1);
+            }
+        bytes = std::min<uint64_t>(bytes, (uint64_t)1 << 30);
+        if (maxReads == 0 && seqs.capacity() < seqs.size() + bytes) {
+            seqs.reserve(seqs.size() + bytes);
+            off.reserve(off.size() + bytes / 128);
+        }
+    }
     for (const auto &group : spec.groups) {
         GroupReadCounter ctr(maxReads);
         bool stop = false;
