@@ -286,7 +286,9 @@ int run(int argc, char **argv) {
             if (!c && !pool.empty()) { c = pool.back(); pool.pop_back(); }
         }
         if (!c) c = new PinnedChunk();
-        c->reserve(words, gpu_ready.load() && !pageable_only);
+        const bool may_pin = gpu_ready.load() && !pageable_only;
+        if (may_pin && !c->pinned) c->release();  // a recycled before-the-context chunk: replaced by a pinned one, once
+        c->reserve(words, may_pin);
         return c;
     };
     auto worker = [&]() {
