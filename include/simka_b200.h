@@ -226,8 +226,9 @@ int simkamin_gpu_sketch_filter(int device, int kmer_size, uint32_t sketch_size, 
  * the reference is a heap over every k-mer of the sample (processUnfiltered, src/simkaMin/SimkaMinCount.hpp:311-338); here only
  * hashes below a bound are extracted and counted, the bound growing from 16 * s / positions of the hash range by factors of 8
  * until >= s distinct hashes lie below it (exact: every occurrence of a kept hash is counted).  attempts = counting passes run,
- * keys_counted = k-mer occurrences that passed the bound over all attempts, distinct_dumped = distinct hashes the last attempt
- * brought back to the host.  SIMKA_B200_SKETCH_PREFILTER=0 takes the whole hash range at once. */
+ * keys_counted = k-mer occurrences that passed the bound over all attempts, distinct_dumped = entries the last attempt
+ * brought back to the host (the counted list is grouped by ranges of the hash: only the leading ranges, up to the one holding
+ * the s-th smallest hash, are copied and sorted).  SIMKA_B200_SKETCH_PREFILTER=0 takes the whole hash range at once. */
 typedef struct simkamin_sketch_info {
     uint64_t attempts, keys_counted, distinct_dumped;
 } simkamin_sketch_info;

@@ -1161,6 +1161,41 @@ struct SketchCtxCache {
 };
 static SketchCtxCache g_sketch_cache;
 
+// The smallest hashes of the (only) sample of a sketch-mode context, ascending, with their counts: its list is grouped by fine
+// range = top bits of the hash, so the `want` smallest lie in the leading ranges.  Only the ranges up to the one that holds
+// the want-th entry come to the host, and each range (a few dozen entries) is sorted by itself.
+static int sketch_fetch_lowest(simka_ctx *ctx, uint64_t want, std::vector<uint64_t> &hk, std::vector<uint32_t> &hc, uint64_t *fetched) {
+    const SampleData &sd = ctx->samples[0];
+    const uint64_t n = sd.n;
+    hk.assign(1, 0);
+    hc.assign(1, 0);
+    *fetched = 0;
+    if (n == 0) return SIMKA_OK;
+    CK(cudaSetDevice(ctx->prm.device));
+    const size_t fgn = ((size_t)1 << ctx->fg_bits) + 1;
+    std::vector<uint32_t> off(fgn);
+    CK(cudaMemcpyAsync(off.data(), sd.off, fgn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t m = n;
+    if (n > want) m = *std::lower_bound(off.begin(), off.end(), (uint32_t)want);  // end of the range holding the want-th entry (off[fg] = n > want)
+    hk.resize(m);
+    hc.resize(m);
+    CK(cudaMemcpyAsync(hk.data(), sd.eh, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hc.data(), sd.ec, m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::pair<uint64_t, uint32_t>> seg;
+    for (size_t r = 0; r + 1 < fgn && off[r] < m; r++) {
+        const uint64_t b = off[r], e = std::min<uint64_t>(off[r + 1], m);
+        if (e - b < 2) continue;
+        seg.resize(e - b);
+        for (uint64_t i = b; i < e; i++) seg[i - b] = {hk[i], hc[i]};
+        std::sort(seg.begin(), seg.end());
+        for (uint64_t i = b; i < e; i++) { hk[i] = seg[i - b].first; hc[i] = seg[i - b].second; }
+    }
+    *fetched = m;
+    return SIMKA_OK;
+}
+
 // filter: the -filter option (processFiltered, src/simkaMin/SimkaMinCount.hpp:341-380): only k-mers seen at least twice are
 // sketched.  The reference remembers first occurrences in a Bloom filter of max-memory * 8 / cores bits; this build counts
 // exactly (stage 1 with abundance-min 2), i.e. it equals the reference wherever that filter answers no false positive.
@@ -1221,9 +1256,9 @@ static int simkamin_sketch_impl(bool filter, int device, int kmer_size, uint32_t
             if ((rc = simka_gpu_reset(ctx)) != SIMKA_OK) break;
             continue;
         }
-        hk.resize(std::max<uint64_t>(n, 1));
-        hc.resize(std::max<uint64_t>(n, 1));
-        rc = simka_gpu_dump_sample_counts(ctx, 0, hk.data(), hc.data(), &n);  // ascending hashes
+        uint64_t fetched = 0;
+        rc = sketch_fetch_lowest(ctx, sketch_size, hk, hc, &fetched);  // ascending hashes, at least min(n, sketch_size) of them
+        g_sketch_info.distinct_dumped = fetched;
         break;
     }
     if (rc != SIMKA_OK) { keep_or_destroy(false); return rc; }
