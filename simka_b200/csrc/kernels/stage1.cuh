@@ -338,8 +338,10 @@ __global__ void k_tiles_per_bucket(const uint32_t *__restrict__ count, uint32_t 
 // Same role as the per-partition "read" phase of PartitionsByVectorCommand
 // (GC/kmer/impl/PartitionsCommand.cpp:1253-1378), which splits a partition into radix bins.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(BLOCK, 4)
+// MINB = CTAs per SM the register budget is cut for: 4 (64 registers; the scatter pass spills 40 bytes per thread) is what was
+// measured; 3 (85 registers, no spill) is selectable with SIMKA_B200_K2_MINB=3 for an A/B on the GPU.
+template <bool COUNT_ONLY, int MINB = 4>
+__global__ void __launch_bounds__(BLOCK, MINB)
 k_partition2(const uint64_t *__restrict__ keys_in, const uint64_t *__restrict__ bucket_base /*[B1] begin*/,
              const uint32_t *__restrict__ bucket_cnt /*[B1]*/, const uint64_t *__restrict__ tile_start /*[B1+1]*/, int b1_bits, int b2_bits, int W,
              uint32_t *__restrict__ fine_hist, const uint64_t *__restrict__ fine_off, uint32_t *__restrict__ fine_cursor,

@@ -164,6 +164,7 @@ struct simka_ctx {
     int nsm = 148;
     int occ_bin_count = 0;
     int b1_override = 0;  // SIMKA_B200_B1BITS: level-1 bucket bits (experiments)
+    bool k2_minb3 = false;  // SIMKA_B200_K2_MINB=3: scatter pass of K2 compiled for 3 CTAs per SM (no register spill; experiments)
 
     void set_error(const std::string &s) { err = s; }
 };
@@ -277,6 +278,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
     { const char *e = getenv("SIMKA_B200_EXACT_COUNT"); ctx->force_exact = e && e[0] == '1'; }
     { const char *e = getenv("SIMKA_B200_K1"); ctx->use_k16 = !(e && !strcmp(e, "256")); }
     { const char *e = getenv("SIMKA_B200_B1BITS"); ctx->b1_override = e ? atoi(e) : 0; }
+    { const char *e = getenv("SIMKA_B200_K2_MINB"); ctx->k2_minb3 = e && e[0] == '3'; }
     { const char *e = getenv("SIMKA_B200_REFINE"); ctx->no_refine = e && e[0] == '0'; }
     { const char *e = getenv("SIMKA_B200_SUPERK"); ctx->use_superk = e && e[0] == '1'; }
     { const char *e = getenv("SIMKA_B200_SUPERK_EXPAND"); ctx->superk_expand_thread = e && !strcmp(e, "thread"); }
@@ -588,7 +590,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
         launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), nbins);
         CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
-        k_partition2<false><<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), cnt1, ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
+        (ctx->k2_minb3 ? k_partition2<false, 3> : k_partition2<false, 4>)<<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), cnt1, ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
                                                   nullptr, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), ctx->d_keysB.as<uint64_t>());
         CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
         ctx->launches += 6;

@@ -19,6 +19,7 @@ except Exception as e:
 run default SIMKA_B200_SUPERK=0
 run superk_flat SIMKA_B200_SUPERK=1
 run superk_thread SIMKA_B200_SUPERK=1 SIMKA_B200_SUPERK_EXPAND=thread
+run default_k2minb3 SIMKA_B200_SUPERK=0 SIMKA_B200_K2_MINB=3   # K2 scatter compiled for 3 CTAs / SM (80 registers, no spill) against 4 (64 registers, 40 B spill)
 # tools/ab_superk.sh ncu : additionally one full ncu capture of the super-k-mer kernels and of k_bin_count behind them
 # (2 samples are enough: every sample launches each kernel once)
 if [ "$1" = "ncu" ]; then
