@@ -197,6 +197,16 @@ uint64_t simka_pack_reads(const char *seqs, const uint64_t *read_off, uint64_t n
 uint64_t simka_pack_reads_k(const char *seqs, const uint64_t *read_off, uint64_t n_reads,
                             uint64_t *packed, uint32_t *bad, int nthreads, int kmer_size);
 
+/* k <= 15 only -- the second MiniKC quirk (pinned on reference runs, tests/golden/truth_ref/example_n_results_k{12,15}_*):
+ * MiniKC::count (src/minikc/MiniKC.hpp:204-231) refills its k-mer iterator through Model::Iterator::setData -> Model::build
+ * (GC/kmer/impl/Model.hpp:603-610,499-513), which leaves the k-mer vector untouched for a read shorter than k, so the
+ * previous long-enough read of the sample is counted once more.  This returns the read set with every such short read
+ * replaced by a copy of that previous read (a short read holds no k-mer of its own): pack / push THAT for k <= 15.
+ * *seqs_out == NULL on return means "nothing to replace, use the input" (always the case for kmer_size > 15);
+ * otherwise both outputs are malloc'ed (simka_host_free).  The host readers of the command lines do the same while parsing. */
+int simka_minikc_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out,
+                        uint64_t **read_off_out);
+
 /* Replaces SimkaDistance + SimkaStatistics::outputMatrix (src/core/SimkaDistance.cpp:603-649,920-1226).
  * Matrix order = the reference's output order: 15 default, +3 if simple, +3 if complex. */
 int simka_nb_matrices(const simka_stats_view *stats);

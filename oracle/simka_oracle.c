@@ -220,23 +220,29 @@ static void count_sample(orc_run *r, int s) {
     sample_t *sm = &r->samples[s];
     const int k = r->k;
     uint64_t r0 = r->sample_read_off[s], r1 = r->sample_read_off[s + 1];
-    size_t cap = 0;
+    size_t cap = 0, last_cap = 0;
     for (uint64_t q = r0; q < r1; q++) {
         uint64_t len = r->read_off[q + 1] - r->read_off[q];
-        if (len >= (uint64_t)k) cap += len - k + 1;
+        if (len >= (uint64_t)k) { cap += len - k + 1; last_cap = len - k + 1; }
+        else if (k <= 15) cap += last_cap;  /* MiniKC replays the previous read, see below */
     }
     uint64_t *keys = malloc((cap ? cap : 1) * 8), *tmp = malloc((cap ? cap : 1) * 8);
     size_t maxlen = 0;
     for (uint64_t q = r0; q < r1; q++) { uint64_t l = r->read_off[q + 1] - r->read_off[q]; if (l > maxlen) maxlen = l; }
     uint64_t *kb = malloc((maxlen + 1) * 8); uint8_t *vb = malloc(maxlen + 1);
-    size_t nk = 0;
+    size_t nk = 0, last_m = 0;
     for (uint64_t q = r0; q < r1; q++) {
         const char *seq = r->seqs + r->read_off[q];
         size_t len = r->read_off[q + 1] - r->read_off[q];
-        size_t m = orc_canonical_kmers(seq, len, k, kb, vb);
+        size_t m;
         /* invalid windows are skipped -- except for k <= 15, where simkaCount switches to MiniKC (src/SimkaCount.cpp:283-288),
          * whose counting loop does not test isValid() (src/minikc/MiniKC.hpp:219-231): every window is counted, a non-ACGT
-         * character contributing its (c>>1)&3 code */
+         * character contributing its (c>>1)&3 code.  Second MiniKC quirk, pinned on reference runs (tests/golden/truth_ref/
+         * example_n_results_k{12,15}_*): its k-mer iterator is refilled by Model::Iterator::setData -> Model::build
+         * (GC/kmer/impl/Model.hpp:603-610,499-513), which returns early WITHOUT touching the k-mer vector when the read is
+         * shorter than k, so MiniKC::count (single-threaded, reads in bank order) walks the PREVIOUS read's k-mers again. */
+        if (k <= 15 && len < (size_t)k) m = last_m;           /* kb still holds the previous long-enough read's k-mers */
+        else { m = orc_canonical_kmers(seq, len, k, kb, vb); last_m = m; }
         for (size_t i = 0; i < m; i++) if (vb[i] || k <= 15) keys[nk++] = kb[i];
     }
     free(kb); free(vb);

@@ -26,11 +26,37 @@ def _vp(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def minikc_replay(seqs: np.ndarray, read_off: np.ndarray, kmer_size: int):
+    """k <= 15: every read shorter than k replaced by a copy of the previous long-enough read (the MiniKC iterator quirk,
+    simka_minikc_replay in include/simka_b200.h).  Returns the inputs unchanged when nothing is to be replaced."""
+    if kmer_size > 15 or len(read_off) < 2:
+        return seqs, read_off
+    L = _lib.load()
+    seqs = np.ascontiguousarray(seqs, np.uint8)
+    read_off = np.ascontiguousarray(read_off, np.uint64)
+    ps, po = C.c_void_p(), C.c_void_p()
+    src = seqs if seqs.size else np.zeros(1, np.uint8)
+    rc = L.simka_minikc_replay(_vp(src), _vp(read_off), len(read_off) - 1, kmer_size, C.byref(ps), C.byref(po))
+    if rc != 0:
+        raise SimkaError(f"simka_minikc_replay failed ({rc})")
+    if not ps.value:
+        return seqs, read_off
+    try:
+        off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(len(read_off),)).copy()
+        n = int(off[-1])
+        out = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_uint8)), shape=(max(n, 1),))[:n].copy()
+    finally:
+        L.simka_host_free(ps)
+        L.simka_host_free(po)
+    return out, off
+
+
 def pack_reads(seqs: np.ndarray, read_off: np.ndarray, nthreads: int = 0, pinned: bool = False, kmer_size: int = 31):
     """2-bit pack + bad mask in the layout simka_gpu_push_reads expects (kmer_size <= 15: the MiniKC rule, only read
     separators are bad, see simka_pack_reads_k).
     -> (packed uint64[n_words+1], bad uint32[n_words+1], n_words)"""
     L = _lib.load()
+    seqs, read_off = minikc_replay(seqs, read_off, kmer_size)
     seqs = np.ascontiguousarray(seqs, np.uint8)
     read_off = np.ascontiguousarray(read_off, np.uint64)
     n_reads = len(read_off) - 1
@@ -170,6 +196,7 @@ class SimkaGpu:
                  expected_kmers_per_sample: int = 0):
         self._L = _lib.load()
         self.nb_samples = nb_samples
+        self.kmer_size = kmer_size
         self.simple, self.complex_ = bool(simple_dist), bool(complex_dist)
         p = SimkaParams(kmer_size, nb_samples, abundance_min, abundance_max, int(simple_dist), int(complex_dist),
                         device, shard_rank, shard_count, 0, expected_kmers_per_sample)
@@ -201,6 +228,7 @@ class SimkaGpu:
         self._keep.clear()
 
     def push_ascii(self, sample: int, seqs: np.ndarray, read_off: np.ndarray):
+        seqs, read_off = minikc_replay(seqs, read_off, self.kmer_size)  # k <= 15 only
         seqs = np.ascontiguousarray(seqs, np.uint8)
         read_off = np.ascontiguousarray(read_off, np.uint64)
         if seqs.size == 0:

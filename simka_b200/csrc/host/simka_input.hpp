@@ -147,10 +147,28 @@ inline uint64_t read_sample(const SampleSpec &spec, const SimkaSequenceFilter &f
 // Batch variant for the ingest pipeline: reads are parsed straight into the concatenated buffer `seqs` (offsets in
 // `off`, off[0] = 0 on entry), a rejected read is rolled back; `after_read()` is called after every accepted read (the
 // caller flushes the batch there when it is large enough).
+// MiniKC quirk (k <= 15 only; pinned on reference runs, tests/golden/truth_ref/example_n_results_k{12,15}_*): MiniKC::count
+// (src/minikc/MiniKC.hpp:204-231) refills its k-mer iterator with Model::Iterator::setData -> Model::build
+// (GC/kmer/impl/Model.hpp:603-610,499-513), which returns early without touching the k-mer vector when the read is shorter than
+// k -- so the k-mers of the PREVIOUS long-enough read of the sample are counted once more.  A short read holds no k-mer of its
+// own, hence replacing it by a copy of that previous read gives exactly the reference's counts.
+struct MiniKCReplay {
+    size_t k = 0;  // 0: off (k > 15)
+    std::string last;
+    explicit MiniKCReplay(int kmer_size = 0) : k(kmer_size > 0 && kmer_size <= 15 ? (size_t)kmer_size : 0) {}
+    // the read just appended to `seqs` at [start, seqs.size())
+    void apply(std::string &seqs, size_t start) {
+        if (!k) return;
+        if (seqs.size() - start < k) { seqs.resize(start); seqs.append(last); }
+        else last.assign(seqs, start, std::string::npos);
+    }
+};
+
 template <class AfterRead>
 inline uint64_t read_sample_into(const SampleSpec &spec, const SimkaSequenceFilter &filter, uint64_t maxReads, std::string &seqs,
-                                 std::vector<uint64_t> &off, AfterRead after_read) {
+                                 std::vector<uint64_t> &off, AfterRead after_read, int kmer_size = 0) {
     uint64_t total = 0;
+    MiniKCReplay replay(kmer_size);
     {   // room for the whole sample up front (bases < file bytes; gzip files weighted 4x; at most 1 GiB, the caller flushes in
         // batches anyway): growing a 150 MB string by doubling re-copies it and touches twice the pages -- 0.75 -> 1.35 GB/s
         // of FASTA per thread
@@ -180,6 +198,7 @@ inline uint64_t read_sample_into(const SampleSpec &spec, const SimkaSequenceFilt
                 if (!parser.nextRead(seqs)) break;
                 if (!filter(seqs.data() + start, seqs.size() - start)) { seqs.resize(start); continue; }
                 if (!ctr.take()) { seqs.resize(start); stop = true; break; }
+                replay.apply(seqs, start);
                 off.push_back(seqs.size());
                 after_read();
                 total++;

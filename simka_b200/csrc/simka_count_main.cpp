@@ -43,7 +43,7 @@ static int run(int argc, char **argv) {
     if (simka_gpu_create(&ctx, &prm) != SIMKA_OK) throw bank::Exception("simka_gpu_create failed: a CUDA device is required, there is no CPU path");
     std::string seqs;
     std::vector<uint64_t> off(1, 0);
-    const uint64_t nreads = read_sample_into(spec, filter, max_reads, seqs, off, [] {});
+    const uint64_t nreads = read_sample_into(spec, filter, max_reads, seqs, off, [] {}, k);
     const uint64_t words = simka_pack_words(seqs.size(), off.size() - 1);
     std::vector<uint64_t> packed(words + 1);
     std::vector<uint32_t> bad(words + 1);

@@ -376,6 +376,34 @@ uint64_t simka_pack_reads_k(const char *seqs, const uint64_t *read_off, uint64_t
 }
 
 
+int simka_minikc_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out, uint64_t **read_off_out) try {
+    if (!seqs_out || !read_off_out || (n_reads && (!seqs || !read_off))) return SIMKA_ERR_INVALID;
+    *seqs_out = nullptr; *read_off_out = nullptr;
+    if (kmer_size > 15 || kmer_size < 1) return SIMKA_OK;
+    const uint64_t k = (uint64_t)kmer_size;
+    bool any = false;
+    uint64_t total = 0, last = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const uint64_t len = read_off[r + 1] - read_off[r];
+        if (len < k) { any = any || last != len; total += last; } else { last = len; total += len; }
+    }
+    if (!any) return SIMKA_OK;
+    char *out = (char *)malloc(total ? total : 1);
+    uint64_t *off = (uint64_t *)malloc((n_reads + 1) * 8);
+    if (!out || !off) { free(out); free(off); return SIMKA_ERR_NOMEM; }
+    uint64_t pos = 0, lbeg = 0, llen = 0;
+    off[0] = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const uint64_t len = read_off[r + 1] - read_off[r];
+        if (len >= k) { lbeg = read_off[r]; llen = len; }
+        memcpy(out + pos, seqs + lbeg, llen);  // a short read: the previous long-enough read again (nothing before the first one)
+        pos += llen;
+        off[r + 1] = pos;
+    }
+    *seqs_out = out; *read_off_out = off;
+    return SIMKA_OK;
+} catch (...) { return SIMKA_ERR_NOMEM; }
+
 // ---- hooks over the host-side mirror classes (tests/test_host_cpu.py compares them with the oracle) ----------
 
 uint64_t simka_host_kmers(const char *seq, uint64_t len, int k, int canonical, uint64_t *out, uint8_t *valid) {

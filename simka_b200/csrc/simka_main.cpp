@@ -318,7 +318,7 @@ int run(int argc, char **argv) {
                     seqs.clear();
                     off.assign(1, 0);
                 };
-                P.nreads = read_sample_into(samples[i], filter, maxReads, seqs, off, [&]() { if (seqs.size() >= CHUNK_BASES) flush(); });
+                P.nreads = read_sample_into(samples[i], filter, maxReads, seqs, off, [&]() { if (seqs.size() >= CHUNK_BASES) flush(); }, o.kmerSize);
                 flush();
             } catch (const std::exception &e) { P.error = e.what(); if (P.error.empty()) P.error = "read error"; }
             {

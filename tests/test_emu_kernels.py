@@ -450,6 +450,14 @@ def test_cli_simka_reproduces_truth(emulated_cli, monkeypatch, tmp_path, golden_
     G.test_simka_cli_max_reads_and_filters(d, golden_dir)
 
 
+@pytest.mark.parametrize("inp,k,t", [("example_n", 15, 0), ("example_n", 12, 2), ("example_n", 31, 2)])
+def test_reference_run_truth(emulated_cli, tmp_path, golden_dir, inp, k, t):
+    """truth produced by the reference binaries (k <= 15 MiniKC quirks, N runs, short reads): library and command line"""
+    import test_gpu_parity as G
+    G.test_reference_run_truth_byte_identical(golden_dir, inp, k, t)
+    G.test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, t)
+
+
 def test_cli_stage_binaries_reference_temp_formats(emulated_cli, tmp_path, golden_dir):
     import test_gpu_parity as G
     G.test_stage_binaries_reference_temp_formats(tmp_path, golden_dir)

@@ -11,8 +11,8 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 
-def load_example(golden_dir):
-    spec = oracle.parse_simka_input(os.path.join(golden_dir, "example", "simka_input.txt"))
+def load_example(golden_dir, inp="example"):
+    spec = oracle.parse_simka_input(os.path.join(golden_dir, inp, "simka_input.txt"))
     ids, samples = [], []
     for ident, groups in spec:
         ids.append(ident)
@@ -42,6 +42,43 @@ def test_example_csv_byte_identical(golden_dir, k, t):
         assert st.csv(m, ids) == open(path).read(), name
         checked += 1
     assert checked == 20
+
+
+@pytest.mark.parametrize("inp,k", [("example", 9), ("example", 15), ("example", 16), ("example_n", 12), ("example_n", 15), ("example_n", 21), ("example_n", 31)])
+@pytest.mark.parametrize("t", [0, 2])
+def test_reference_run_truth_byte_identical(golden_dir, inp, k, t):
+    """Truth produced by the reference binaries themselves (tools/make_ref_golden.py) for what its own truth files do not
+    cover: k <= 15 (MiniKC: N windows counted, short reads replay the previous read) and an input with N runs, lower case,
+    short reads, multi-line FASTA, FASTQ.gz and a paired sample -- through the library."""
+    import json
+    ids, samples = load_example(golden_dir, inp)
+    st = simka_b200.run_samples(samples, k, abundance_min=t, simple_dist=True, complex_dist=True)
+    tdir = os.path.join(golden_dir, "truth_ref", ("" if inp == "example" else inp + "_") + f"results_k{k}_t{t}")
+    for m, name in enumerate(st.matrix_names()):
+        assert st.csv(m, ids) == open(os.path.join(tdir, name + ".csv")).read(), name
+    sync = json.load(open(os.path.join(tdir, "count_synchro.json")))
+    for i, ident in enumerate(ids):
+        assert [int(x) for x in st.totals[i]] == sync[ident], ident
+
+
+@pytest.mark.parametrize("inp,k,t", [("example_n", 15, 0), ("example_n", 12, 2), ("example_n", 31, 2), ("example", 16, 0)])
+def test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, t):
+    """same, through the `simka` command line of this build (its own FASTA / FASTQ / gz readers)"""
+    import gzip
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    out = tmp_path / "results"
+    cmd = [str(SIMKA_BIN), "-in", os.path.join(golden_dir, inp, "simka_input.txt"), "-out", str(out), "-out-tmp", str(tmp_path / "tmp"),
+           "-simple-dist", "-complex-dist", "-kmer-size", str(k), "-abundance-min", str(t), "-verbose", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    tdir = os.path.join(golden_dir, "truth_ref", ("" if inp == "example" else inp + "_") + f"results_k{k}_t{t}")
+    checked = 0
+    for f in sorted(os.listdir(tdir)):
+        if f.endswith(".csv"):
+            assert gzip.open(out / (f + ".gz"), "rt").read() == open(os.path.join(tdir, f)).read(), f
+            checked += 1
+    assert checked == 21
 
 
 @pytest.mark.parametrize("k,amin", [(31, 2), (21, 1), (15, 2), (9, 0)])

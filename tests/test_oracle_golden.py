@@ -236,3 +236,31 @@ def test_dsk_solid_counts_known_answers(golden_dir):
         assert len(km) == want == int(run.totals(0)[1]), (k, amin)
         assert (ct >= amin).all()
         run.close()
+
+
+# (input fixture, k): truth produced by running the REFERENCE BINARIES themselves on the fixture (tools/make_ref_golden.py ->
+# tests/golden/truth_ref): the k values the reference's own truth files do not cover.  k <= 15 is the MiniKC path
+# (src/minikc/MiniKC.hpp:195-259: windows with non-ACGT characters are counted, and a read shorter than k replays the previous
+# read's k-mers); example_n holds N runs, lower case, short reads, multi-line FASTA, a FASTQ.gz and a paired sample.
+REF_TRUTH_CASES = [("example", 9), ("example", 15), ("example", 16), ("example_n", 12), ("example_n", 15), ("example_n", 21), ("example_n", 31)]
+
+
+def ref_truth_dir(golden_dir, inp, k, t):
+    return os.path.join(golden_dir, "truth_ref", ("" if inp == "example" else inp + "_") + f"results_k{k}_t{t}")
+
+
+@pytest.mark.parametrize("inp,k", REF_TRUTH_CASES)
+@pytest.mark.parametrize("t", [0, 2])
+def test_reference_run_truth_byte_identical(golden_dir, inp, k, t):
+    import json
+    run, ids = oracle.run_from_input_file(os.path.join(golden_dir, inp, "simka_input.txt"), k, abundance_min=t)
+    run.merge()
+    tdir = ref_truth_dir(golden_dir, inp, k, t)
+    names = run.matrix_names()
+    assert len(names) == 21
+    for m, name in enumerate(names):
+        assert run.csv(m, ids) == open(os.path.join(tdir, name + ".csv")).read(), name
+    sync = json.load(open(os.path.join(tdir, "count_synchro.json")))
+    tot = run.all_totals()
+    for i, ident in enumerate(ids):
+        assert [int(x) for x in tot[i]] == sync[ident], ident

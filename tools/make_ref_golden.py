@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Golden vectors produced by the REFERENCE BINARIES themselves (oracle/_ref/bin, built by oracle/build_ref.sh).
+
+The reference's own tests hold truth matrices for k = 21 and 31 only.  This script runs the reference `simka` on its
+example (tests/golden/example = /root/reference/example) for the k values its tests do not cover -- k <= 15 (the MiniKC
+path, src/minikc/MiniKC.hpp:195-259) and k > 31 (LargeInt<2>, span 64) -- and commits what came out as fixtures:
+
+  tests/golden/truth_ref/[example_n_]results_k<K>_t<AMIN>/mat_*.csv      the 21 matrices (gunzipped)
+  tests/golden/truth_ref/results_k<K>_t<AMIN>/count_synchro.json   {sample: [nbReads, nbDistinct, sum c, sum c^2]}
+
+Run from the repo root in the build container (needs oracle/_ref/bin/simka):  python tools/make_ref_golden.py
+"""
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMKA = os.path.join(ROOT, "oracle", "_ref", "bin", "simka")
+OUT = os.path.join(ROOT, "tests", "golden", "truth_ref")
+CASES = [("example", k, a) for k in (9, 15, 16, 32, 41, 63) for a in (0, 2)]
+# a second input with what the example lacks: N runs, lower case, reads shorter than k, a FASTQ and a gz sample, multi-line FASTA
+CASES += [("example_n", k, a) for k in (12, 15, 21, 31, 41) for a in (0, 2)]
+
+
+def make_example_n(dst):
+    """tests/golden/example_n: seeded; written once and committed (the reference ran on exactly these files)"""
+    import numpy as np
+    rng = np.random.default_rng(20261017)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    g = [alpha[rng.integers(0, 4, 1500)].tobytes() for _ in range(3)]
+
+    def reads(genome, n, L, p_n=0.0, lower=False):
+        out = []
+        for _ in range(n):
+            s = int(rng.integers(0, len(genome) - L))
+            r = bytearray(genome[s:s + L])
+            if p_n and rng.random() < p_n:
+                q = int(rng.integers(0, L - 6))
+                ln = int(rng.integers(1, 6))
+                r[q:q + ln] = b"N" * ln
+            if lower and rng.random() < 0.5:
+                r = bytearray(bytes(r).lower())
+            if rng.random() < 0.5:
+                r = bytearray(bytes(r).translate(bytes.maketrans(b"ACGTacgtN", b"TGCAtgcaN"))[::-1])
+            out.append(bytes(r))
+        return out
+
+    os.makedirs(dst, exist_ok=True)
+    s1 = reads(g[0], 120, 100, p_n=0.4) + [b"ACGT", b"N" * 40, b"ACGTACGTACGTAC"]
+    s2 = reads(g[0], 60, 100, lower=True) + reads(g[1], 60, 80, p_n=0.2)
+    s3 = reads(g[1], 100, 120, p_n=0.3)
+    s4 = reads(g[2], 80, 100) + reads(g[0], 40, 100, p_n=0.5, lower=True)
+    with open(os.path.join(dst, "S1.fasta"), "wb") as f:
+        for i, r in enumerate(s1):
+            f.write(b">r%d\n" % i + r + b"\n")
+    with open(os.path.join(dst, "S2.fasta"), "wb") as f:  # multi-line records
+        for i, r in enumerate(s2):
+            f.write(b">r%d some comment\n" % i + r[:37] + b"\n" + r[37:] + b"\n")
+    with gzip.open(os.path.join(dst, "S3.fastq.gz"), "wb") as f:
+        for i, r in enumerate(s3):
+            f.write(b"@q%d\n" % i + r + b"\n+\n" + b"I" * len(r) + b"\n")
+    with open(os.path.join(dst, "S4_1.fasta"), "wb") as f:
+        for i, r in enumerate(s4[:60]):
+            f.write(b">a%d\n" % i + r + b"\n")
+    with open(os.path.join(dst, "S4_2.fasta"), "wb") as f:
+        for i, r in enumerate(s4[60:]):
+            f.write(b">b%d\n" % i + r + b"\n")
+    with open(os.path.join(dst, "simka_input.txt"), "w") as f:
+        f.write("S1: S1.fasta\nS2: S2.fasta\nS3: S3.fastq.gz\nS4: S4_1.fasta ; S4_2.fasta\nS5: S1.fasta , S2.fasta\n")
+
+
+def main():
+    if not os.path.exists(SIMKA):
+        sys.exit("oracle/_ref/bin/simka missing: run oracle/build_ref.sh first")
+    exn = os.path.join(ROOT, "tests", "golden", "example_n")
+    if not os.path.exists(os.path.join(exn, "simka_input.txt")):
+        make_example_n(exn)
+    for inp, k, amin in CASES:
+        with tempfile.TemporaryDirectory() as td:
+            shutil.copytree(os.path.join(ROOT, "tests", "golden", inp), os.path.join(td, "ex"))
+            cmd = [SIMKA, "-in", os.path.join(td, "ex", "simka_input.txt"), "-out", os.path.join(td, "out"), "-out-tmp", os.path.join(td, "tmp"),
+                   "-kmer-size", str(k), "-abundance-min", str(amin), "-simple-dist", "-complex-dist", "-nb-cores", "4", "-max-memory", "4000",
+                   "-keep-tmp"]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=td)
+            if r.returncode != 0:
+                print(f"{inp} k={k} amin={amin}: reference failed rc={r.returncode}\n{r.stdout[-800:]}")
+                continue
+            dst = os.path.join(OUT, ("" if inp == "example" else inp + "_") + f"results_k{k}_t{amin}")
+            os.makedirs(dst, exist_ok=True)
+            n = 0
+            for f in sorted(os.listdir(os.path.join(td, "out"))):
+                if f.endswith(".csv.gz"):
+                    with gzip.open(os.path.join(td, "out", f), "rb") as g, open(os.path.join(dst, f[:-3]), "wb") as o:
+                        o.write(g.read())
+                    n += 1
+            sync = {}
+            sdir = os.path.join(td, "tmp", "simka_output_temp", "count_synchro")
+            for f in sorted(os.listdir(sdir)):
+                if f.endswith(".ok"):
+                    sync[f[:-3]] = [int(x) for x in open(os.path.join(sdir, f)).read().split()]
+            json.dump(sync, open(os.path.join(dst, "count_synchro.json"), "w"), indent=1, sort_keys=True)
+            print(f"{inp} k={k} amin={amin}: {n} matrices, totals {sync}")
+
+
+if __name__ == "__main__":
+    main()
