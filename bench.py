@@ -4,17 +4,24 @@
 Metric (BASELINE.json): 31-mers/sec into the N x N distance matrices.  One "step" = the whole hot
 path over one batch of synthetic input: for every sample canonical k-mer extraction -> bucket
 partition -> exact counting -> abundance filter, then the multi-sample merge + N x N accumulator
-update and the read-out of the accumulators.  Workload at 1 GPU = BASELINE.json configs[1]:
-32 samples x 1M reads x 150 bp, k=31, abundance-min 2, simple + complex distances.
+update and the read-out of the accumulators.
+
+  --config 2 (default)  BASELINE.json configs[1]: 32 samples x 1M reads x 150 bp, k=31, abundance-min 2, 1 GPU
+  --config 3            configs[2]: 128 x 5M, k=31 (meant for --gpus 8 under torchrun)
+  --config 4            configs[3]: 512 x 1M, k=21, 1 GPU (the 512 x 512 accumulator update)
+  --config 5            configs[4]: SimkaMin, 128 sketches x 1M k-mers, sketch x sketch Jaccard / Bray-Curtis on 1 GPU
+  (--samples / --reads / --kmer override the configuration's sizes)
 
   value  : reads already 2-bit packed and resident in HBM when the timed region starts
   e2e    : the same through the C ABI with pinned HOST buffers (H2D of the packed reads and D2H of
            the accumulators inside the timed region, copy of sample s+1 overlapped with sample s)
   --gpus N>1 (torchrun): samples sharded over the ranks for counting, hash ranges sharded for the merge,
-           solid k-mer lists exchanged with one NCCL all-to-all, two tiny all-reduces; same total
-           workload => "scaling": "strong"
-  --impl reference : the CPU restatement of the reference algorithm (oracle/, OpenMP, all host cores)
-           on a bounded sample of the same workload.
+           solid k-mer lists exchanged over NCCL, two tiny all-reduces; same total workload => "scaling": "strong"
+  --impl reference : the REFERENCE BINARIES (oracle/_ref/bin/simka, built from /root/reference by oracle/build_ref.sh)
+           on FASTA files in /dev/shm, all host cores, on a bounded sample of the same workload; the oracle port
+           (oracle/, OpenMP) when the binaries are absent.
+  --verify : after the timing, every accumulator of the step is compared with the CPU oracle on the same reads
+           (integers bit-exact, Jensen-Shannon sums within 1e-10 relative); N = 1 only.
 """
 from __future__ import annotations
 
@@ -24,6 +31,7 @@ import os
 import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -33,6 +41,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+CONFIGS = {2: (32, 1_000_000, 31), 3: (128, 5_000_000, 31), 4: (512, 1_000_000, 21), 5: (128, 1_000_000, 21)}
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 
 
 def parse_args():
@@ -41,20 +51,41 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--samples", type=int, default=32)
-    ap.add_argument("--reads", type=int, default=1_000_000)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--samples", type=int, default=0)
+    ap.add_argument("--reads", type=int, default=0, help="reads per sample (config 5: k-mers per sketch)")
     ap.add_argument("--read-len", type=int, default=150)
-    ap.add_argument("--kmer", type=int, default=31)
+    ap.add_argument("--kmer", type=int, default=0)
     ap.add_argument("--abundance-min", type=int, default=2)
-    ap.add_argument("--ref-reads", type=int, default=400_000, help="reads/sample of the bounded CPU sample (about 10-20 s of CPU work per pass)")
+    ap.add_argument("--ref-reads", type=int, default=0, help="reads/sample of the bounded CPU sample (0 = sized from a calibration run)")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0, help="wall-clock target of the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="compare all accumulators with the CPU oracle after the timing (N = 1)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end pass (0 = --steps)")
     ap.add_argument("--genomes", type=int, default=0, help="number of 50 kb genomes of the generator (0 = 256 per 32 samples)")
-    return ap.parse_args()
+    ap.add_argument("--out", default="", help="also write the JSON line to this file")
+    a = ap.parse_args()
+    n, m, k = CONFIGS[a.config]
+    a.samples = a.samples or n
+    a.reads = a.reads or m
+    a.kmer = a.kmer or k
+    return a
 
 
-def workload_name(a, reads=None):
-    return (f"synthetic {a.samples} samples x {reads or a.reads} reads x {a.read_len} bp, k={a.kmer}, "
+def workload_name(a):
+    if a.config == 5:
+        return f"SimkaMin distance: {a.samples} sketches x {a.reads} k-mers, all {a.samples * (a.samples - 1) // 2} pairs, Jaccard + Bray-Curtis"
+    return (f"synthetic {a.samples} samples x {a.reads} reads x {a.read_len} bp, k={a.kmer}, "
             f"abundance-min={a.abundance_min}, simple+complex distances")
+
+
+def config_dict(a):
+    """identical for both arms (the driver compares them)"""
+    if a.config == 5:
+        return {"workload": workload_name(a), "generator": "BASELINE.md section 3 sketches (pool of 4 s hashes, s drawn per sketch, counts 1..19)"}
+    return {"workload": workload_name(a),
+            "generator": f"BASELINE.md section 3 (G={n_genomes_for(a.samples, a.genomes)} x 50 kb, Dirichlet(0.3), 1% substitutions, 50% revcomp)",
+            "l2": "inputs larger than L2 (packed reads 57 MB per 1M-read sample, 0.96 GB of keys per sample streamed)"}
 
 
 def n_genomes_for(samples, override=0):
@@ -63,12 +94,26 @@ def n_genomes_for(samples, override=0):
     return 256 if samples <= 32 else 256 * ((samples + 31) // 32)  # "scale G with N" 
 
 
+def emit(a, line):
+    s = json.dumps(line)
+    print(s, flush=True)
+    if a.out:
+        os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+        with open(a.out, "w") as f:
+            f.write(s + "\n")
+
+
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm, all host threads, bounded sample
+# CPU arms
 # ----------------------------------------------------------------------------------------------
-def cpu_port_rate(a, reads, repeats=1):
-    """-> (k-mers/s, cores, seconds per pass)"""
-    from oracle import oracle
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def concat_samples(a, reads):
     from simka_b200 import synth
     genomes = synth.make_genomes(n_genomes_for(a.samples, a.genomes), 50_000)
     datas, offs, sample_off, base, nreads = [], [np.zeros(1, np.uint64)], [0], 0, 0
@@ -79,64 +124,159 @@ def cpu_port_rate(a, reads, repeats=1):
         base += len(seqs)
         nreads += reads
         sample_off.append(nreads)
-    seqs = np.concatenate(datas)
-    ro = np.concatenate(offs)
-    so = np.array(sample_off, np.uint64)
-    kmers = a.samples * reads * (a.read_len - a.kmer + 1)
-    best = None
-    for _ in range(repeats):
+    return np.concatenate(datas), np.concatenate(offs), np.array(sample_off, np.uint64)
+
+
+def oracle_pass(a, seqs, ro, so):
+    """one pass of the oracle port (all host threads; torchrun's OMP_NUM_THREADS=1 is ignored on purpose) -> seconds"""
+    from oracle import oracle
+    t0 = time.perf_counter()
+    run = oracle.Run(seqs, ro, so, a.kmer, abundance_min=a.abundance_min, simple=True, complex_=True, nthreads=host_cores())
+    run.merge()
+    for m in range(len(run.matrix_names())):
+        run.matrix(m)
+    dt = time.perf_counter() - t0
+    run.close()
+    return dt
+
+
+class RefBinaryRun:
+    """The reference's own CPU implementation: `simka` (which starts one simkaCount per sample and one simkaMerge per
+    partition) on FASTA files of the same generator, temp dir on /dev/shm (the reference is disk-bound by design)."""
+
+    def __init__(self, a):
+        self.a = a
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        self.dir = tempfile.mkdtemp(prefix="simka_bench_ref_", dir=base)
+        self.where = "/dev/shm" if base else "tmp"
+        self.cores = host_cores()
+        self.reads = 0
+
+    @staticmethod
+    def available():
+        return all(os.access(os.path.join(REF_BIN, b), os.X_OK) for b in ("simka", "simkaCount", "simkaMerge", "simkaCountProcess"))
+
+    def write_inputs(self, reads):
+        from simka_b200 import synth
+        a = self.a
+        ind = os.path.join(self.dir, f"in_{reads}")
+        if os.path.isdir(ind):
+            shutil.rmtree(ind)
+        os.makedirs(ind)
+        genomes = synth.make_genomes(n_genomes_for(a.samples, a.genomes), 50_000)
+        L = a.read_len
+        with open(os.path.join(ind, "input.txt"), "w") as f:
+            for s in range(a.samples):
+                seqs, _ = synth.make_sample(genomes, s, reads, L)
+                rec = np.empty((reads, L + 4), np.uint8)  # ">r\n" + bases + "\n"
+                rec[:, 0], rec[:, 1], rec[:, 2], rec[:, L + 3] = ord(">"), ord("r"), 10, 10
+                rec[:, 3:L + 3] = seqs.reshape(reads, L)
+                rec.tofile(os.path.join(ind, f"S{s}.fasta"))
+                f.write(f"S{s}: S{s}.fasta\n")
+        self.reads = reads
+        return ind
+
+    def run_once(self, ind):
+        a = self.a
+        out, tmp = os.path.join(self.dir, "out"), os.path.join(self.dir, "tmp")
+        for d in (out, tmp):
+            shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(tmp)
+        try:
+            ram_mb = os.sysconf("SC_PHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") // (1 << 20)
+        except Exception:
+            ram_mb = 64000
+        mem = int(max(2000, min(1000 * self.cores, ram_mb // 2)))
+        cmd = [os.path.join(REF_BIN, "simka"), "-in", os.path.join(ind, "input.txt"), "-out", out, "-out-tmp", tmp, "-kmer-size", str(a.kmer),
+               "-abundance-min", str(a.abundance_min), "-simple-dist", "-complex-dist", "-nb-cores", str(self.cores), "-max-memory", str(mem)]
         t0 = time.perf_counter()
-        run = oracle.Run(seqs, ro, so, a.kmer, abundance_min=a.abundance_min, simple=True, complex_=True, nthreads=0)
-        run.merge()
-        for m in range(len(run.matrix_names())):
-            run.matrix(m)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         dt = time.perf_counter() - t0
-        run.close()
-        best = dt if best is None else min(best, dt)
-    return kmers / best, os.cpu_count(), best
+        if r.returncode != 0 or not os.path.exists(os.path.join(out, "mat_abundance_braycurtis.csv.gz")):
+            raise RuntimeError("reference simka failed: " + r.stdout[-600:])
+        return dt
+
+    def kmers(self):
+        a = self.a
+        return a.samples * self.reads * (a.read_len - a.kmer + 1)
+
+    def sample_text(self, secs):
+        a = self.a
+        return (f"reference binaries (simka -nb-cores {self.cores}, FASTA + temp dir on {self.where}): {a.samples} samples x {self.reads} reads x "
+                f"{a.read_len} bp of the same generator, {secs:.1f} s per run")
+
+    def close(self):
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def cpu_baseline_once(a, target_s=15.0):
+    """bounded CPU baseline for our arm's line (N = 1): one run of the reference binaries (else the oracle port) of about target_s"""
+    if RefBinaryRun.available():
+        ref = RefBinaryRun(a)
+        try:
+            cal = min(a.reads, 20_000)
+            t_cal = ref.run_once(ref.write_inputs(cal))
+            reads = int(min(a.reads, max(cal, cal * target_s / max(t_cal, 1e-3) * 0.8)))
+            reads = max(1000, reads // 1000 * 1000)
+            secs = ref.run_once(ref.write_inputs(reads)) if reads != cal else t_cal
+            return {"value": ref.kmers() / secs, "unit": "kmers/s", "cores": ref.cores, "kind": "reference", "sample": ref.sample_text(secs)}
+        finally:
+            ref.close()
+    from oracle import oracle
+    oracle.build()
+    reads = min(a.reads, 400_000 * 32 // max(32, a.samples))
+    secs = oracle_pass(a, *concat_samples(a, reads))
+    return {"value": a.samples * reads * (a.read_len - a.kmer + 1) / secs, "unit": "kmers/s", "cores": host_cores(), "kind": "port",
+            "sample": f"oracle port (OpenMP): {a.samples} samples x {reads} reads x {a.read_len} bp (same generator), one pass of {secs:.1f} s"}
 
 
 def run_reference(a):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import oracle
-    oracle.build()
+    if a.config == 5:
+        return run_reference_simkamin(a)
+    nrun = a.warmup + a.steps
     times = []
-    kmers = a.samples * a.ref_reads * (a.read_len - a.kmer + 1)
-    # build inputs once, time W + K passes
-    from simka_b200 import synth
-    genomes = synth.make_genomes(n_genomes_for(a.samples, a.genomes), 50_000)
-    datas, offs, sample_off, base, nreads = [], [np.zeros(1, np.uint64)], [0], 0, 0
-    for s in range(a.samples):
-        seqs, off = synth.make_sample(genomes, s, a.ref_reads, a.read_len)
-        datas.append(seqs)
-        offs.append(off[1:] + np.uint64(base))
-        base += len(seqs)
-        nreads += a.ref_reads
-        sample_off.append(nreads)
-    seqs, ro, so = np.concatenate(datas), np.concatenate(offs), np.array(sample_off, np.uint64)
-    for it in range(a.warmup + a.steps):
-        t0 = time.perf_counter()
-        run = oracle.Run(seqs, ro, so, a.kmer, abundance_min=a.abundance_min, simple=True, complex_=True, nthreads=0)
-        run.merge()
-        for m in range(len(run.matrix_names())):
-            run.matrix(m)
-        run.close()
-        if it >= a.warmup:
-            times.append(time.perf_counter() - t0)
+    if RefBinaryRun.available():
+        ref = RefBinaryRun(a)
+        try:
+            reads = a.ref_reads
+            if not reads:  # size the sample so that warmup + steps runs fit the budget
+                cal = min(a.reads, 20_000)
+                t_cal = ref.run_once(ref.write_inputs(cal))
+                per_run = max(2.0, (a.ref_budget_s - t_cal) / nrun * 0.85)
+                reads = int(min(a.reads, max(cal, cal * per_run / max(t_cal, 1e-3))))
+                reads = max(1000, reads // 1000 * 1000)
+            ind = ref.write_inputs(reads)
+            for it in range(nrun):
+                dt = ref.run_once(ind)
+                if it >= a.warmup:
+                    times.append(dt)
+            kmers, cores, kind = ref.kmers(), ref.cores, "reference"
+            sample = ref.sample_text(sum(times) / len(times))
+        finally:
+            ref.close()
+    else:
+        from oracle import oracle
+        oracle.build()
+        reads = a.ref_reads or min(a.reads, 400_000 * 32 // max(32, a.samples))
+        seqs, ro, so = concat_samples(a, reads)
+        for it in range(nrun):
+            dt = oracle_pass(a, seqs, ro, so)
+            if it >= a.warmup:
+                times.append(dt)
+        kmers, cores, kind = a.samples * reads * (a.read_len - a.kmer + 1), host_cores(), "port"
+        sample = f"oracle port (OpenMP): {a.samples} samples x {reads} reads x {a.read_len} bp per step (same generator, reads/sample scaled down)"
     total = sum(times)
     value = kmers * a.steps / total
-    sample = f"{a.samples} samples x {a.ref_reads} reads x {a.read_len} bp per step (same generator, reads/sample scaled down)"
-    line = {
+    emit(a, {
         "impl": "reference", "metric": "31-mers/sec into NxN distance matrix", "value": value, "unit": "kmers/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "cpu_sample": sample},
-        "cpu_baseline": {"value": value, "unit": "kmers/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "config": config_dict(a),
+        "cpu_baseline": {"value": value, "unit": "kmers/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
+    })
 
 
 # ----------------------------------------------------------------------------------------------
@@ -206,6 +346,19 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s; MEASURED_PEAKS.json absent)"
 
 
+def measured_traffic(kernel, kmers_this_rank):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` per launch set, from the ncu --set full capture of
+    the shipped build: profiles/traffic.json holds bytes PER INPUT K-MER of the capture, scaled here by the k-mers this rank
+    processed (so it follows the workload, not a constant); null when the file does not list the kernel."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(tp))
+        per = d.get("bytes_per_kmer", {}).get(kernel)
+        return None if per is None else float(per) * kmers_this_rank
+    except Exception:
+        return None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -219,28 +372,35 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; simka_b200 has no CPU path")
-    sbuild.build()
+    if rank == 0:
+        sbuild.build()
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
     dev = torch.device("cuda", local)
+    if a.config == 5:
+        return run_simkamin(a, torch)
 
     # ---- synthetic input: rank r owns samples s with s % world == r (sample-sharded counting) ----------
     N, M, L, k = a.samples, a.reads, a.read_len, a.kmer
     genomes = synth.make_genomes(n_genomes_for(N, a.genomes), 50_000)
     t_gen = time.perf_counter()
     mine = [s for s in range(N) if sdist.sample_owner(s, world) == rank]
-    host, devbuf, nwords = {}, {}, {}
+    host, devbuf, nwords, ascii_keep = {}, {}, {}, {}
+    keep_ascii = a.verify and world == 1
 
     def gen(s):  # numpy and the packer release the GIL: the samples are generated on a few threads
         seqs, off = synth.make_sample(genomes, s, M, L)
-        return s, simka_b200.pack_reads(seqs, off, nthreads=1, pinned=True)
+        return s, simka_b200.pack_reads(seqs, off, nthreads=1, pinned=True), (seqs if keep_ascii else None)
 
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max(1, min(8, (os.cpu_count() or 8) // max(1, world)))) as ex:
-        for s, (hp, hb, nw) in ex.map(gen, mine):
+    with ThreadPoolExecutor(max(1, min(8, host_cores() // max(1, world)))) as ex:
+        for s, (hp, hb, nw), seqs in ex.map(gen, mine):
             host[s] = (hp, hb)
             nwords[s] = nw
+            if keep_ascii:
+                ascii_keep[s] = seqs
             devbuf[s] = (torch.from_numpy(np.asarray(hp).view(np.int64)).to(dev), torch.from_numpy(np.asarray(hb).view(np.int32)).to(dev))
     if world > 1:
         dist.barrier()
@@ -322,7 +482,8 @@ def run_ours(a):
     if rank == 0:
         sampler.start()
     ms_res, tims, launches, st = timed(step_resident, a.steps, a.warmup)
-    ms_e2e, _, _, st2 = timed(step_e2e, a.steps, max(1, a.warmup - 2))
+    e2e_steps = a.e2e_steps or a.steps
+    ms_e2e, _, _, st2 = timed(step_e2e, e2e_steps, max(1, min(a.warmup, 3) - 2))
     clocks = sampler.stop() if rank == 0 else {}
     # sanity: both paths must produce the same accumulators
     assert np.array_equal(st.nb_shared, st2.nb_shared) and np.array_equal(st.braycurtis_num, st2.braycurtis_num)
@@ -331,87 +492,159 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         h2d, launches, d2h_bytes[0] = (int(x) for x in t.tolist())
 
+    verify = None
+    if keep_ascii and rank == 0:  # outside every timed region: ALL accumulators of the full-size step against the CPU oracle
+        from oracle import oracle
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import assert_stats_equal
+        oracle.build()
+        t0 = time.perf_counter()
+        seqs = np.concatenate([ascii_keep[s] for s in range(N)])
+        ro = np.arange(N * M + 1, dtype=np.uint64) * np.uint64(L)
+        so = np.arange(N + 1, dtype=np.uint64) * np.uint64(M)
+        run = oracle.Run(seqs, ro, so, k, abundance_min=a.abundance_min, simple=True, complex_=True, nthreads=host_cores())
+        run.merge()
+        assert_stats_equal(st2, run, kl_rtol=1e-10)
+        run.close()
+        verify = {"against": "oracle port on the same reads", "checked": "all accumulators of the step (integers bit-exact, Jensen-Shannon sums rtol 1e-10) and the 21 matrices",
+                  "oracle_s": round(time.perf_counter() - t0, 1), "result": "equal"}
+
     if rank == 0:
         steps = a.steps
         per = {kk: v / steps for kk, v in tims.items()}
         Ks, D, U = per["kmers_in"], per["entries"], per["distinct_kmers"]
         words = sum(nwords.values())
         # algorithmic bytes per launch set (summed over the samples of one step); DESIGN.md section 4
-        superk = per.get("superk_samples", 0) > 0  # SIMKA_B200_SUPERK=1: experimental super-k-mer front end of stage 1
+        superk = per.get("superk_samples", 0) > 0  # super-k-mer front end of stage 1
         if superk:
-            # the scan reads the packed reads and the expansion writes the keys: together the algorithmic bytes of the k-mer
-            # extraction; the record list in between (about 2 B per k-mer each way) is implementation traffic
-            alg = {
-                "k_superk_scan": words * 12,
-                "k_superk_bins(+scan)": 0,
-                "k_superk_expand": 8 * Ks,
-                "k_bin_count": 8 * Ks + 12 * D,
-                "k_merge": 12 * D + 8 * U,
-            }
-            tms = {
-                "k_superk_scan": per["extract_scatter_ms"], "k_superk_bins(+scan)": per["part_count_ms"],
-                "k_superk_expand": per["part_scatter_ms"], "k_bin_count": per["bin_count_ms"], "k_merge": per["merge_ms"],
-            }
+            alg = {"k_superk_scan": words * 12, "k_superk_bins(+scan)": 0, "k_superk_expand": 8 * Ks, "k_bin_count": 8 * Ks + 12 * D,
+                   "k_merge": 12 * D + 8 * U}
+            tms = {"k_superk_scan": per["extract_scatter_ms"], "k_superk_bins(+scan)": per["part_count_ms"],
+                   "k_superk_expand": per["part_scatter_ms"], "k_bin_count": per["bin_count_ms"], "k_merge": per["merge_ms"]}
         else:
-            alg = {
-                "k_extract<count>": words * 12,
-                "k_extract<scatter>": words * 12 + 8 * Ks,
-                "k_partition2<count>": 8 * Ks,
-                "k_partition2<scatter>": 16 * Ks,
-                "k_bin_count": 8 * Ks + 12 * D,
-                "k_merge": 12 * D + 8 * U,
-            }
-            tms = {
-                "k_extract<count>": per["extract_count_ms"], "k_extract<scatter>": per["extract_scatter_ms"],
-                "k_partition2<count>": per["part_count_ms"], "k_partition2<scatter>": per["part_scatter_ms"],
-                "k_bin_count": per["bin_count_ms"], "k_merge": per["merge_ms"],
-            }
+            alg = {"k_extract<count>": words * 12, "k_extract<scatter>": words * 12 + 8 * Ks, "k_partition2<count>": 8 * Ks,
+                   "k_partition2<scatter>": 16 * Ks, "k_bin_count": 8 * Ks + 12 * D, "k_merge": 12 * D + 8 * U}
+            tms = {"k_extract<count>": per["extract_count_ms"], "k_extract<scatter>": per["extract_scatter_ms"],
+                   "k_partition2<count>": per["part_count_ms"], "k_partition2<scatter>": per["part_scatter_ms"],
+                   "k_bin_count": per["bin_count_ms"], "k_merge": per["merge_ms"]}
+        # a pass that did not run on this path (e.g. the exact K1 count pass) is not evidence: dropped
+        for n in [n for n in tms if tms[n] <= 1e-3 * max(tms.values())]:
+            tms.pop(n)
+            alg.pop(n)
         peak, peak_src = hbm_peak()
-        kernels = {n: {"ms_per_step": tms[n], "alg_bytes_per_step": alg[n],
-                       "achieved_gbs": (alg[n] / (tms[n] * 1e-3) / 1e9) if tms[n] > 0 else None} for n in alg}
+        kernels = {n: {"ms_per_step": tms[n], "alg_bytes_per_step": alg[n], "achieved_gbs": alg[n] / (tms[n] * 1e-3) / 1e9} for n in alg}
+        kernels["k_merge"]["pair_updates_per_s"] = per["pairs"] / (tms["k_merge"] * 1e-3) if "k_merge" in tms else None
         dom = max(tms, key=lambda n: tms[n])
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get(dom)
-            except Exception:
-                traffic = None
         achieved = kernels[dom]["achieved_gbs"] or 0.0
+        step_ms = ms_res / steps
+        # whole pipeline against the HBM roofline: SURVEY 8(d) end-to-end algorithmic bytes of THIS rank's share / step time
+        pipe_alg = words * 12 + 16 * Ks + 12 * (Ks * 0.0 + D) + 24 * D + 16 * U  # (D0 is not measured: its 12 B/entry term uses D, a lower bound)
         line = {
             "metric": "31-mers/sec into NxN distance matrix", "value": kmers_per_step * steps / (ms_res * 1e-3),
-            "unit": "kmers/s", "n_gpus": world, "steps": steps, "warmup": a.warmup, "ms_per_step": ms_res / steps,
+            "unit": "kmers/s", "n_gpus": world, "steps": steps, "warmup": a.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "sharding": (f"samples over {world} ranks for counting (rank r owns samples s % {world} == r), hash ranges over the ranks for the merge; "
-                                    "solid (k-mer,count) lists exchanged with NCCL all-to-all, 2 tiny all-reduces; kernels/roofline are rank 0's share") if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (packed reads 57 MB/sample, 0.96 GB of keys per sample streamed)",
-                       "generator": "BASELINE.md section 3 (G=256 x 50 kb, Dirichlet(0.3), 1% substitutions, 50% revcomp)",
-                       "input_build_s": round(gen_s, 1),
-                       "stage1": ("super-k-mer front end (SIMKA_B200_SUPERK=1, experimental), %d fallbacks" % per.get("superk_fallbacks", 0)) if superk
-                                 else "k-mer partition (default)"},
-            "e2e": {"value": kmers_per_step * steps / (ms_e2e * 1e-3), "unit": "kmers/s", "ms_per_step": ms_e2e / steps,
+            "config": config_dict(a),
+            "notes": {"sharding": (f"samples over {world} ranks for counting (rank r owns samples s % {world} == r), hash ranges over the ranks for the merge; "
+                                   "solid (k-mer,count) lists exchanged over NCCL, 2 tiny all-reduces; kernels/roofline are rank 0's share") if world > 1 else "single GPU",
+                      "input_build_s": round(gen_s, 1),
+                      "stage1": ("super-k-mer front end, %d fallbacks" % per.get("superk_fallbacks", 0)) if superk else "k-mer partition"},
+            "e2e": {"value": kmers_per_step * e2e_steps / (ms_e2e * 1e-3), "unit": "kmers/s", "ms_per_step": ms_e2e / e2e_steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes[0]},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "share_of_step": tms[dom] / (ms_res / steps)},
+                         "frac": achieved / peak, "traffic": measured_traffic(dom, Ks), "peak_source": peak_src,
+                         "share_of_step": tms[dom] / step_ms,
+                         "pipeline": {"alg_bytes_per_step": pipe_alg, "achieved": pipe_alg / (step_ms * 1e-3) / 1e9, "frac": pipe_alg / (step_ms * 1e-3) / 1e9 / peak}},
             "kernels": kernels,
             "counts": {"kmers_in_per_step": Ks, "solid_entries": D, "distinct_kmers": U, "pairs": per["pairs"]},
         }
+        if verify:
+            line["verify"] = verify
         if world == 1 and not a.no_cpu_baseline:
-            from oracle import oracle
-            oracle.build()
-            rate, cores, secs = cpu_port_rate(a, a.ref_reads)
-            line["cpu_baseline"] = {"value": rate, "unit": "kmers/s", "cores": cores, "kind": "port",
-                                    "sample": f"{N} samples x {a.ref_reads} reads x {L} bp (same generator), one pass of {secs:.1f} s"}
-        print(json.dumps(line), flush=True)
+            line["cpu_baseline"] = cpu_baseline_once(a)
+        emit(a, line)
     ctx.close()
     if mctx is not None:
         mctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+# config 5: SimkaMin sketch x sketch distances
+# ----------------------------------------------------------------------------------------------
+def run_simkamin(a, torch):
+    import simka_b200
+    from simka_b200 import synth
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n, s = a.samples, a.reads
+    hashes, counts = synth.make_sketches(n, s)
+    pairs = n * (n - 1) // 2
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    kms, wall = [], []
+    for it in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        jac, bc, ms = simka_b200.simkamin_distance(hashes, counts)  # host sketches in, host float matrices out
+        w = time.perf_counter() - t0
+        if it >= a.warmup:
+            kms.append(ms)
+            wall.append(w)
+    clocks = sampler.stop()
+    # algorithmic bytes: 12 B (u64 hash + u32 count) per element the two-pointer merge of a pair consumes before it has seen s
+    # distinct hashes (SURVEY 8d "per-pair streamed bytes"); counted exactly on the host from the sketches
+    consumed, sampled = 0, 0
+    for j in range(1, min(n, 17)):  # the sketches are i.i.d. draws from one pool: the mean over 16 pairs stands for all of them
+        u = np.union1d(hashes[0], hashes[j])
+        cut = u[min(s, len(u)) - 1]
+        consumed += int(np.searchsorted(hashes[0], cut, "right")) + int(np.searchsorted(hashes[j], cut, "right"))
+        sampled += 1
+    alg = consumed * pairs // max(1, sampled) * 12
+    k_ms, e_s = sum(kms) / len(kms), sum(wall) / len(wall)
+    peak, peak_src = hbm_peak()
+    line = {"metric": "SimkaMin sketch pairs/sec (Jaccard + Bray-Curtis)", "value": pairs / (k_ms * 1e-3), "unit": "pairs/s", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": k_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": config_dict(a),
+            "e2e": {"value": pairs / e_s, "unit": "pairs/s", "ms_per_step": 1e3 * e_s, "h2d_bytes_per_step": int(hashes.nbytes + counts.nbytes), "d2h_bytes_per_step": 2 * n * n * 4},
+            "gpu_launches": 2 * a.steps, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_simkamin_tiled", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_step": alg}}
+    if not a.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        m = min(32, n)
+        t0 = time.perf_counter()
+        oj, ob = oracle.simkamin_distance(hashes[:m], counts[:m])
+        dt = time.perf_counter() - t0
+        np.testing.assert_array_equal(jac[:m, :m], oj)
+        np.testing.assert_array_equal(bc[:m, :m], ob)
+        line["cpu_baseline"] = {"value": (m * (m - 1) // 2) / dt, "unit": "pairs/s", "cores": host_cores(), "kind": "port",
+                                "sample": f"oracle port of SimkaMinDistance.hpp:190-279 on {m} of the sketches, {dt:.1f} s; GPU result bit-identical on that block"}
+    emit(a, line)
+
+
+def run_reference_simkamin(a):
+    from oracle import oracle
+    from simka_b200 import synth
+    oracle.build()
+    m = min(32, a.samples)
+    hashes, counts = synth.make_sketches(m, a.reads)
+    times = []
+    for it in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        oracle.simkamin_distance(hashes, counts)
+        if it >= a.warmup:
+            times.append(time.perf_counter() - t0)
+    value = (m * (m - 1) // 2) * a.steps / sum(times)
+    sample = f"oracle port of SimkaMinDistance.hpp:190-279: {m} sketches x {a.reads} k-mers per step"
+    emit(a, {"impl": "reference", "metric": "SimkaMin sketch pairs/sec (Jaccard + Bray-Curtis)", "value": value, "unit": "pairs/s", "n_gpus": a.gpus,
+             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / a.steps, "higher_is_better": True, "scaling": "strong",
+             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config_dict(a),
+             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": host_cores(), "kind": "port", "sample": sample},
+             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def main():

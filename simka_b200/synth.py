@@ -28,8 +28,13 @@ def make_sample(genomes: np.ndarray, sample: int, n_reads: int, read_len: int = 
     g = rng.choice(G, size=n_reads, p=w)
     start = rng.integers(0, glen - read_len + 1, size=n_reads)
     flat = genomes.reshape(-1)
-    base = (g.astype(np.int64) * glen + start)[:, None] + np.arange(read_len, dtype=np.int64)[None, :]
-    reads = flat[base]  # (n_reads, read_len) ASCII
+    first = g.astype(np.int64) * glen + start
+    idx_t = np.int32 if flat.size < 2**31 else np.int64
+    ar = np.arange(read_len, dtype=idx_t)
+    reads = np.empty((n_reads, read_len), np.uint8)  # (n_reads, read_len) ASCII, gathered block-wise (same values, bounded temporaries)
+    for b0 in range(0, n_reads, 262144):
+        b1 = min(n_reads, b0 + 262144)
+        reads[b0:b1] = flat[first[b0:b1].astype(idx_t)[:, None] + ar[None, :]]
     total = n_reads * read_len
     n_err = int(rng.binomial(total, err)) if err > 0 else 0
     if n_err:

@@ -458,6 +458,14 @@ def test_reference_run_truth(emulated_cli, tmp_path, golden_dir, inp, k, t):
     G.test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, t)
 
 
+@pytest.mark.parametrize("count,merge,k,t", [("ours", "ours", 31, 2), ("ours", "ref", 21, 0), ("ref", "ours", 21, 0)])
+def test_cross_run_with_reference_binaries(emulated_cli, tmp_path, golden_dir, count, merge, k, t):
+    import test_gpu_parity as G
+    if not os.access(os.path.join(G.REF_BIN, "simka"), os.X_OK):
+        pytest.skip("oracle/_ref/bin not built")
+    G.test_cross_run_with_reference_binaries(tmp_path, golden_dir, count, merge, k, t)
+
+
 def test_cli_stage_binaries_reference_temp_formats(emulated_cli, tmp_path, golden_dir):
     import test_gpu_parity as G
     G.test_stage_binaries_reference_temp_formats(tmp_path, golden_dir)

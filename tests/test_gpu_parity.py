@@ -503,6 +503,43 @@ def test_stage_binaries_reference_temp_formats(tmp_path, golden_dir):
     np.testing.assert_allclose(rows[:, 2].astype(np.float64), run.f64("kl"), rtol=1e-10, atol=0)
 
 
+REF_BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bin")
+
+
+@pytest.mark.skipif(not os.access(os.path.join(REF_BIN, "simka"), os.X_OK), reason="oracle/_ref/bin (reference binaries, oracle/build_ref.sh) not built")
+@pytest.mark.parametrize("count,merge,k,t", [("ours", "ours", 31, 2), ("ours", "ref", 21, 0), ("ref", "ours", 21, 0), ("ref", "ours", 31, 2)])
+def test_cross_run_with_reference_binaries(tmp_path, golden_dir, count, merge, k, t):
+    """The REFERENCE's `simka` orchestrator (oracle/_ref/bin/simka, unmodified) drives the stage binaries it finds next to
+    itself (src/SimkaPotara.hpp:218-228): this build's simkaCount / simkaMerge, or one stage of each -- the temp files
+    (solid/part_P/__p__I.gz, count_synchro/*.ok, stats/part_P.gz, merge_synchro) are what crosses between them.  Every mix
+    must reproduce the reference's truth matrices byte for byte."""
+    import gzip
+    import shutil
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    ours = os.path.dirname(str(SIMKA_BIN))
+    b = tmp_path / "bin"
+    b.mkdir()
+    shutil.copy(os.path.join(REF_BIN, "simka"), b / "simka")
+    for exe, side in (("simkaCount", count), ("simkaCountProcess", count), ("simkaMerge", merge)):
+        os.symlink(os.path.join(ours if side == "ours" else REF_BIN, exe), b / exe)
+    ex = tmp_path / "ex"
+    shutil.copytree(os.path.join(golden_dir, "example"), ex)
+    out = tmp_path / "out"
+    r = subprocess.run([str(b / "simka"), "-in", str(ex / "simka_input.txt"), "-out", str(out), "-out-tmp", str(tmp_path / "tmp"), "-kmer-size", str(k),
+                        "-abundance-min", str(t), "-simple-dist", "-complex-dist", "-nb-cores", "4", "-max-memory", "4000", "-keep-tmp"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    logs = tmp_path / "tmp" / "simka_output_temp" / "log"
+    assert str(b / "simkaCount") in open(logs / "count_A.txt").read()  # the orchestrator did start the binaries of this mix
+    tdir = os.path.join(golden_dir, "truth", f"results_k{k}_t{t}")
+    checked = 0
+    for f in sorted(os.listdir(tdir)):
+        assert gzip.open(out / (f + ".gz"), "rt").read() == open(os.path.join(tdir, f)).read(), f
+        checked += 1
+    assert checked == 20
+
+
 def test_import_counts_equals_counting():
     """a sample registered from its (k-mer, count) list behaves exactly like a counted one"""
     samples = synthetic_samples(5, 2500)

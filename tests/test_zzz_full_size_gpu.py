@@ -1,0 +1,53 @@
+"""Parity at BASELINE sizes: the CUDA path against the CPU oracle on the FULL configuration 2 and on the shape of
+configuration 4 (512 samples), every accumulator compared.  Runs last (file name): a minute of host time each."""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+import simka_b200
+from helpers import assert_stats_equal
+from oracle import oracle
+from simka_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(n_samples, n_reads, k, n_genomes, read_len=150, amin=2):
+    genomes = synth.make_genomes(n_genomes, 50_000)
+    with ThreadPoolExecutor(min(8, os.cpu_count() or 1)) as ex:
+        samples = list(ex.map(lambda s: synth.make_sample(genomes, s, n_reads, read_len), range(n_samples)))
+    ctx = simka_b200.SimkaGpu(n_samples, k, amin, simple_dist=True, complex_dist=True, expected_kmers_per_sample=n_reads * (read_len - k + 1))
+    for s, (seqs, off) in enumerate(samples):
+        packed, bad, nw = simka_b200.pack_reads(seqs, off, kmer_size=k)
+        ctx.push_reads(s, packed, bad, nw, n_reads)
+        ctx.finish_sample(s)
+    ctx.merge_and_accumulate()
+    st = ctx.stats()
+    t = ctx.timings()
+    ctx.close()
+    seqs = np.concatenate([s[0] for s in samples])
+    del samples
+    ro = np.arange(n_samples * n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
+    so = np.arange(n_samples + 1, dtype=np.uint64) * np.uint64(n_reads)
+    run = oracle.Run(seqs, ro, so, k, abundance_min=amin, simple=True, complex_=True, nthreads=os.cpu_count() or 1)
+    run.merge()
+    return st, run, t
+
+
+def test_full_config2_all_accumulators_equal_the_oracle():
+    """BASELINE.json configs[1] at its stated size: 32 samples x 1M reads x 150 bp, k = 31, abundance-min 2, all distances.
+    Integers bit-exact, Jensen-Shannon sums within 1e-10 relative, the 21 matrices equal as floats."""
+    st, run, t = _run_both(32, 1_000_000, 31, 256)
+    assert int(t["kmers_in"]) == 32 * 1_000_000 * 120
+    assert_stats_equal(st, run, kl_rtol=1e-10)
+    run.close()
+
+
+def test_config4_shape_512_samples_equal_the_oracle():
+    """The shape of BASELINE.json configs[3] (512 samples, k = 21; 20 000 reads per sample so that the oracle finishes in seconds):
+    the N > 64 merge path (global 64-bit atomics, Jensen-Shannon terms added in floating point) against the oracle at 1e-10."""
+    st, run, _ = _run_both(512, 20_000, 21, 256 * 16)
+    assert_stats_equal(st, run, kl_rtol=1e-10)
+    run.close()
