@@ -141,18 +141,70 @@ __global__ void __launch_bounds__(1024) k_scan_u32_u64(const uint32_t *__restric
     if (tid == 0) out[n] = carry;
 }
 
-// Multi-block version for the large scans (fine-bin histogram, survivors): block b scans 16384 elements and
-// takes its exclusive prefix from block b-1 through a chained (epoch | running total) word.  All blocks are
-// co-resident (grid <= 128), so the spin of thread 0 cannot starve its predecessor.
+// Multi-block exclusive scan for the large arrays (micro-bin histograms, fine-bin histograms, survivors): three short launches --
+// per-block sums, a single-block scan of the sums, per-block scan with the block's prefix.  No block ever waits for another one
+// (an earlier version chained the blocks through a spin on the predecessor's word, which serialised the 128 blocks -- 0.2 ms
+// per scan -- and relied on all of them being co-resident).  `stride` reads every stride-th u32 of `in` (2: one half of a
+// packed u64 histogram).
 constexpr int SCAN_CHUNK = 1024 * 16;
-__global__ void __launch_bounds__(1024) k_scan_chain(const uint32_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n,
-                                                     unsigned long long *chain, unsigned long long epoch) {
+__global__ void __launch_bounds__(1024) k_scan_reduce(const uint32_t *__restrict__ in, uint64_t n, int stride, uint64_t *__restrict__ partial) {
+    __shared__ uint64_t warp_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t i0 = (uint64_t)blockIdx.x * SCAN_CHUNK;
+    uint64_t v = 0;
+#pragma unroll 4
+    for (int q = 0; q < 16; q++) {
+        const uint64_t i = i0 + (uint64_t)q * 1024 + tid;
+        if (i < n) v += in[i * stride];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (lane == 0) warp_sum[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = warp_sum[lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w += __shfl_down_sync(0xffffffffu, w, d);
+        if (lane == 0) partial[blockIdx.x] = w;
+    }
+}
+// in place: partial[0..m) -> exclusive prefix, partial[m] = total; single block
+__global__ void __launch_bounds__(1024) k_scan_partials(uint64_t *__restrict__ partial, uint32_t m) {
     __shared__ uint64_t warp_sum[33];
-    __shared__ uint64_t s_prefix;
+    __shared__ uint64_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < m; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint64_t v = i < m ? partial[i] : 0;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) warp_sum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t w = warp_sum[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint64_t u = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += u; }
+            warp_sum[lane] = winc - w;
+            if (lane == 31) warp_sum[32] = winc;
+        }
+        __syncthreads();
+        if (i < m) partial[i] = carry + warp_sum[wid] + inc - v;
+        __syncthreads();
+        if (tid == 0) carry += warp_sum[32];
+        __syncthreads();
+    }
+    if (tid == 0) partial[m] = carry;
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t *__restrict__ in, uint64_t n, int stride, const uint64_t *__restrict__ partial,
+                                                     uint64_t *__restrict__ out) {
+    __shared__ uint64_t warp_sum[33];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t i0 = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)tid * 16;
     uint32_t x[16];
-    if (i0 + 16 <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    if (stride == 1 && i0 + 16 <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint4 t4 = *reinterpret_cast<const uint4 *>(in + i0 + 4 * q);
@@ -160,46 +212,28 @@ __global__ void __launch_bounds__(1024) k_scan_chain(const uint32_t *__restrict_
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < 16; q++) x[q] = (i0 + q < n) ? in[i0 + q] : 0;
+        for (int q = 0; q < 16; q++) x[q] = (i0 + q < n) ? in[(i0 + q) * stride] : 0;
     }
     uint64_t v = 0;
 #pragma unroll
     for (int q = 0; q < 16; q++) v += x[q];
     uint64_t inc = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint64_t u = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += u;
-    }
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
     if (lane == 31) warp_sum[wid] = inc;
     __syncthreads();
     if (wid == 0) {
         uint64_t w = warp_sum[lane], winc = w;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t u = __shfl_up_sync(0xffffffffu, winc, d);
-            if (lane >= d) winc += u;
-        }
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t u = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += u; }
         warp_sum[lane] = winc - w;
-        if (lane == 31) {
-            const uint64_t total = winc;
-            uint64_t prefix = 0;
-            if (blockIdx.x > 0) {
-                volatile unsigned long long *c = chain + (blockIdx.x - 1);
-                unsigned long long pv = *c;
-                while ((pv >> 40) != epoch) pv = *c;
-                prefix = pv & ((1ull << 40) - 1);
-            }
-            *((volatile unsigned long long *)(chain + blockIdx.x)) = (epoch << 40) | (prefix + total);
-            s_prefix = prefix;
-            if (blockIdx.x == gridDim.x - 1) out[n] = prefix + total;
-        }
     }
     __syncthreads();
-    uint64_t run = s_prefix + warp_sum[wid] + inc - v;
+    uint64_t run = partial[blockIdx.x] + warp_sum[wid] + inc - v;
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         if (i0 + q < n) out[i0 + q] = run;
         run += x[q];
     }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) out[n] = partial[gridDim.x];
 }

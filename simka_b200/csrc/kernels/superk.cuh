@@ -58,7 +58,7 @@ template <int K>
 __global__ void __launch_bounds__(SK_THREADS, 2)
 k_superk_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t n_words, int bin_bits,
               SkRecord *__restrict__ records, ull *__restrict__ n_records, uint64_t cap, uint32_t *__restrict__ bin_hist,
-              int *__restrict__ overflow_flag) {
+              int *__restrict__ overflow_flag, ull *__restrict__ hist64 /* != null: (records << 32 | k-mers) per micro-bin instead of bin_hist */) {
     constexpr int M = SK_M;
     constexpr int W = K - M + 1;                 // m-mers per k-mer
     constexpr int NQ = 32 + W - 1;               // m-mers the 32 k-mers of a word touch (bases 0 .. 30 + K <= 61)
@@ -161,14 +161,15 @@ k_superk_scan(const uint64_t *__restrict__ seq, const uint32_t *__restrict__ bad
             rec.hi = p ? (hi << (2 * p)) | (lo >> (64 - 2 * p)) : hi;
             rec.lo = ((p ? lo << (2 * p) : lo) & ~((1ull << 26) - 1)) | ((uint64_t)(n - 1) << 21) | b;
             records[slot] = rec;
-            atomicAdd(&bin_hist[b], n);
+            if (hist64) atomicAdd(&hist64[b], (1ull << 32) | n);
+            else atomicAdd(&bin_hist[b], n);
         } else {
             *overflow_flag = 1;  // the host redoes the sample on the k-mer path
         }
     }
 }
 
-typedef void (*superk_scan_fn)(const uint64_t *, const uint32_t *, uint64_t, int, SkRecord *, ull *, uint64_t, uint32_t *, int *);
+typedef void (*superk_scan_fn)(const uint64_t *, const uint32_t *, uint64_t, int, SkRecord *, ull *, uint64_t, uint32_t *, int *, ull *);
 static superk_scan_fn superk_scan_instance(int k) {
     static const superk_scan_fn tab[15] = {k_superk_scan<17>, k_superk_scan<18>, k_superk_scan<19>, k_superk_scan<20>, k_superk_scan<21>,
                                            k_superk_scan<22>, k_superk_scan<23>, k_superk_scan<24>, k_superk_scan<25>, k_superk_scan<26>,
@@ -179,15 +180,19 @@ static superk_scan_fn superk_scan_instance(int k) {
 // fine_off[b] = first key of counting bin b = prefix[u] of the first micro-bin u with prefix[u] >= b * SK_TARGET (b <= nb; bins
 // past the last key are empty).  Thread u fills the bins that begin at micro-bin u; thread n_micro fills the tail.
 __global__ void __launch_bounds__(BLOCK)
-k_superk_bins(const uint64_t *__restrict__ prefix /*[n_micro + 1]*/, uint32_t n_micro, uint64_t *__restrict__ fine_off, uint32_t nb) {
+k_superk_bins(const uint64_t *__restrict__ prefix /*[n_micro + 1]*/, uint32_t n_micro, uint64_t *__restrict__ fine_off, uint32_t nb, uint32_t target,
+              const uint64_t *__restrict__ rec_prefix /*[n_micro + 1] or null*/, uint64_t *__restrict__ rec_off /*[nb + 1]: first record of bin b*/) {
     const uint32_t u = blockIdx.x * BLOCK + threadIdx.x;
     if (u > n_micro) return;
     const uint64_t here = prefix[u];
-    // bins whose mark b * SK_TARGET lies in (prefix[u - 1], prefix[u]]  (u = 0: bin 0)
-    uint64_t b_lo = u ? prefix[u - 1] / SK_TARGET + 1 : 0;
-    uint64_t b_hi = u == n_micro ? (uint64_t)nb : here / SK_TARGET;
-    if (u == n_micro) b_lo = (n_micro ? prefix[n_micro - 1] / SK_TARGET + 1 : 0);
-    for (uint64_t b = b_lo; b <= b_hi && b <= nb; b++) fine_off[b] = here;
+    // bins whose mark b * target lies in (prefix[u - 1], prefix[u]]  (u = 0: bin 0)
+    uint64_t b_lo = u ? prefix[u - 1] / target + 1 : 0;
+    uint64_t b_hi = u == n_micro ? (uint64_t)nb : here / target;
+    if (u == n_micro) b_lo = (n_micro ? prefix[n_micro - 1] / target + 1 : 0);
+    for (uint64_t b = b_lo; b <= b_hi && b <= nb; b++) {
+        fine_off[b] = here;
+        if (rec_prefix) rec_off[b] = rec_prefix[u];
+    }
 }
 
 // records -> mixed canonical k-mers, written where k_bin_count expects the keys of the record's micro-bin

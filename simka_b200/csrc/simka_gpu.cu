@@ -44,8 +44,10 @@ typedef unsigned long long ull;
 namespace {
 
 #include "kernels/common.cuh"
+#include "kernels/async.cuh"
 #include "kernels/stage1.cuh"
 #include "kernels/superk.cuh"
+#include "kernels/superk2.cuh"
 #include "kernels/merge.cuh"
 #include "kernels/simkamin.cuh"
 
@@ -146,23 +148,24 @@ struct simka_ctx {
     ull *a_nb_shared = nullptr, *a_distinct = nullptr, *a_bc = nullptr, *a_chord = nullptr, *a_hell = nullptr, *a_whit = nullptr, *a_T = nullptr, *a_scalars = nullptr;
     double *a_kl = nullptr, *a_ntot = nullptr;
     ull *a_klfix = nullptr;
-    DevBuf d_ptrs, d_logtab, d_chain, d_isum;
+    DevBuf d_ptrs, d_logtab, d_scan_tmp, d_isum;
     bool import_pending = false;
-    unsigned long long scan_epoch = 0;
     bool use_k16 = true;        // SIMKA_B200_K1=256: the 256-thread x 32-position extraction kernel
     bool force_exact = false;   // SIMKA_B200_EXACT_COUNT=1: always run the K1 count pass (tests of the fallback)
-    bool use_superk = false;    // SIMKA_B200_SUPERK=1: experimental super-k-mer front end of stage 1 (kernels/superk.cuh)
+    bool use_superk = false;    // SIMKA_B200_SUPERK=1|2: super-k-mer front end of stage 1 (kernels/superk.cuh; 2 = records all the way, kernels/superk2.cuh)
+    int superk_mode = 0;
+    uint32_t sk2_target = 0;    // SIMKA_B200_SK2_TARGET: k-mers per counting bin of the record path (experiments; default SK2_TARGET)
     uint64_t exact_retries = 0, superk_samples = 0, superk_fallbacks = 0;
     uint64_t superk_cap_override = 0;
     bool superk_expand_thread = false;
-    DevBuf d_sk_tmpc, d_sk_prefix;
+    DevBuf d_sk_tmpc, d_sk_prefix, d_sk_rprefix, d_sk_recoff, d_sk_hist64;
     DevBuf d_dump;  // scratch of simka_gpu_dump_sample_counts (parity hook)
     float stage_ms[T_NSTAGE] = {};
     float sample_ms = 0, merge_ms = 0;
     uint64_t kmers_in = 0, entries = 0;
     uint64_t launches = 0;
     int nsm = 148;
-    int occ_bin_count = 0;
+    int occ_bin_count = 0, occ_sk2_count = 0;
     int b1_override = 0;  // SIMKA_B200_B1BITS: level-1 bucket bits (experiments)
     bool k2_minb3 = false;  // SIMKA_B200_K2_MINB=3: scatter pass of K2 compiled for 3 CTAs per SM (no register spill; experiments)
 
@@ -205,14 +208,16 @@ static void launch_extract(simka_ctx *ctx, bool count_only, unsigned grid, const
                                                                                                    bucket_cursor, cap, overflow, keys_out);
 }
 
-// exclusive scan u32[n] -> u64[n+1] on the context's stream
-static void launch_scan(simka_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n) {
-    if (n <= (uint64_t)SCAN_CHUNK) { k_scan_u32_u64<<<1, 1024, 0, ctx->stream>>>(in, out, n); return; }
-    const unsigned grid = (unsigned)((n + SCAN_CHUNK - 1) / SCAN_CHUNK);
-    if (grid > 128) { k_scan_u32_u64<<<1, 1024, 0, ctx->stream>>>(in, out, n); return; }  // co-residency bound of the chained version
-    ctx->scan_epoch = (ctx->scan_epoch + 1) & 0xFFFFFFull;
-    if (ctx->scan_epoch == 0) { cudaMemsetAsync(ctx->d_chain.p, 0, 128 * 8, ctx->stream); ctx->scan_epoch = 1; }
-    k_scan_chain<<<grid, 1024, 0, ctx->stream>>>(in, out, n, ctx->d_chain.as<unsigned long long>(), ctx->scan_epoch);
+// exclusive scan u32[n] -> u64[n+1] on the context's stream (stride 2: one half of a packed u64 histogram)
+static int launch_scan(simka_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n, int stride = 1) {
+    if (n <= (uint64_t)SCAN_CHUNK && stride == 1) { k_scan_u32_u64<<<1, 1024, 0, ctx->stream>>>(in, out, n); ctx->launches++; return 0; }
+    const uint64_t nblk = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (ctx->d_scan_tmp.reserve((nblk + 1) * 8)) return -1;
+    k_scan_reduce<<<(unsigned)nblk, 1024, 0, ctx->stream>>>(in, n, stride, ctx->d_scan_tmp.as<uint64_t>());
+    k_scan_partials<<<1, 1024, 0, ctx->stream>>>(ctx->d_scan_tmp.as<uint64_t>(), (uint32_t)nblk);
+    k_scan_apply<<<(unsigned)nblk, 1024, 0, ctx->stream>>>(in, n, stride, ctx->d_scan_tmp.as<uint64_t>(), out);
+    ctx->launches += 3;
+    return 0;
 }
 
 // adds the per-kernel device times of a finished sample (event set `set`) to the context's totals
@@ -280,7 +285,8 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
     { const char *e = getenv("SIMKA_B200_B1BITS"); ctx->b1_override = e ? atoi(e) : 0; }
     { const char *e = getenv("SIMKA_B200_K2_MINB"); ctx->k2_minb3 = e && e[0] == '3'; }
     { const char *e = getenv("SIMKA_B200_REFINE"); ctx->no_refine = e && e[0] == '0'; }
-    { const char *e = getenv("SIMKA_B200_SUPERK"); ctx->use_superk = e && e[0] == '1'; }
+    { const char *e = getenv("SIMKA_B200_SUPERK"); ctx->superk_mode = e ? atoi(e) : 0; ctx->use_superk = ctx->superk_mode == 1 || ctx->superk_mode == 2; }
+    { const char *e = getenv("SIMKA_B200_SK2_TARGET"); ctx->sk2_target = e ? (uint32_t)std::min(std::max(atoi(e), 64), SK2_MAXD) : 0; }
     { const char *e = getenv("SIMKA_B200_SUPERK_EXPAND"); ctx->superk_expand_thread = e && !strcmp(e, "thread"); }
     { const char *e = getenv("SIMKA_B200_SUPERK_CAP"); ctx->superk_cap_override = e ? strtoull(e, nullptr, 10) : 0; }  // tests of the fallback
     cudaDeviceGetAttribute(&ctx->nsm, cudaDevAttrMultiProcessorCount, p->device);
@@ -298,8 +304,9 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
             ok = ok && cudaFuncSetAttribute(extract_instance(false, sh, bk), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(p->nb_samples)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_sk2_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sk2Smem)) == cudaSuccess;
     ok = ok && ctx->d_small.reserve(64) == 0;
-    ok = ok && ctx->d_chain.reserve(128 * 8) == 0 && cudaMemset(ctx->d_chain.p, 0, 128 * 8) == cudaSuccess;
+    ok = ok && ctx->d_scan_tmp.reserve(((size_t)1 << 17) * 8 + 64) == 0;  // block sums of the device-wide scans (up to 2^31 elements)
     if (ok) {  // tab_log table
         double tab[128][2];
         const uint64_t OFF = 0x3fe6000000000000ull;
@@ -341,7 +348,7 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->slots[0].packed, &ctx->slots[0].bad, &ctx->slots[1].packed, &ctx->slots[1].bad, &ctx->d_ascii, &ctx->d_roff,
                       &ctx->d_keysA, &ctx->d_keysB, &ctx->d_stage_c, &ctx->d_hist1, &ctx->d_base1, &ctx->d_cursor1, &ctx->d_tiles,
                       &ctx->d_tile_start, &ctx->d_fine_hist, &ctx->d_fine_off, &ctx->d_fine_cursor, &ctx->d_surv, &ctx->d_out_off,
-                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_chain, &ctx->d_isum, &ctx->d_sk_tmpc, &ctx->d_sk_prefix, &ctx->d_dump};
+                      &ctx->d_small, &ctx->d_off_table, &ctx->d_off_table2, &ctx->d_chist, &ctx->d_big_counts, &ctx->d_big_sample, &ctx->d_acc, &ctx->d_ptrs, &ctx->d_logtab, &ctx->d_scan_tmp, &ctx->d_isum, &ctx->d_sk_tmpc, &ctx->d_sk_prefix, &ctx->d_sk_rprefix, &ctx->d_sk_recoff, &ctx->d_sk_hist64, &ctx->d_dump};
     for (DevBuf *b : bufs) b->release();
     for (auto &set : ctx->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     for (auto &sl : ctx->slots) { if (sl.copied) cudaEventDestroy(sl.copied); if (sl.consumed) cudaEventDestroy(sl.consumed); }
@@ -503,7 +510,9 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         // super-k-mer mode: micro-bins of ~48 positions (at most 2^21), counting bins cut from their histogram
         const int micro_bits = std::min(SK_MAXMICRO, std::max(8, ilog2_floor(std::max<uint64_t>(1, n_pos / 48))));
         const uint32_t n_micro = 1u << micro_bits;
-        const uint32_t nb_sk = (uint32_t)std::min<uint64_t>(n_pos / SK_TARGET + 2, 0x7FFFFFFFull);
+        const bool sk2 = ctx->superk_mode == 2;  // records all the way: scatter the records, count straight from them
+        const uint32_t sk_target = sk2 ? (ctx->sk2_target ? ctx->sk2_target : SK2_TARGET) : SK_TARGET;
+        const uint32_t nb_sk = (uint32_t)std::min<uint64_t>(n_pos / sk_target + 2, 0x7FFFFFFFull);
         const size_t nres = std::max<size_t>(std::max<size_t>(nbins, (size_t)1 << ctx->fg_bits),
                                              ctx->use_superk ? std::max<size_t>(n_micro, (size_t)nb_sk + 1) : 0);
         bool okm = !ctx->d_keysA.reserve(n_pos * 8) && !ctx->d_keysB.reserve(n_pos * 8) && !ctx->d_stage_c.reserve(n_pos * 4) &&
@@ -511,7 +520,9 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
                    !ctx->d_tiles.reserve(MAX_B * 4) && !ctx->d_tile_start.reserve((MAX_B + 1) * 8) &&
                    !ctx->d_fine_hist.reserve(nres * 4) && !ctx->d_fine_off.reserve((nres + 1) * 8) &&
                    !ctx->d_fine_cursor.reserve(nres * 4) && !ctx->d_surv.reserve(nres * 4) &&
-                   !ctx->d_out_off.reserve((nres + 1) * 8) && (!ctx->use_superk || !ctx->d_sk_prefix.reserve(((size_t)n_micro + 1) * 8));
+                   !ctx->d_out_off.reserve((nres + 1) * 8) && (!ctx->use_superk || !ctx->d_sk_prefix.reserve(((size_t)n_micro + 1) * 8)) &&
+                   (!sk2 || (!ctx->d_sk_rprefix.reserve(((size_t)n_micro + 1) * 8) && !ctx->d_sk_recoff.reserve(((size_t)nb_sk + 2) * 8) &&
+                             !ctx->d_sk_hist64.reserve((size_t)n_micro * 8)));
         if (!okm) { ctx->set_error("out of device memory (work buffers)"); return SIMKA_ERR_NOMEM; }
         CK(cudaStreamWaitEvent(st, sl->copied, 0));
         const int evset = ctx->ev_cur;
@@ -550,12 +561,27 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
             CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
             CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT + 1], st));
             CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER], st));
+            if (sk2) CK(cudaMemsetAsync(ctx->d_sk_hist64.p, 0, (size_t)n_micro * 8, st));
             superk_scan_instance(ctx->kp.k)<<<(unsigned)((n_words + SK_THREADS - 1) / SK_THREADS), SK_THREADS, 0, st>>>(
-                seq, bad, n_words, micro_bits, ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->d_fine_hist.as<uint32_t>(), d_overflow);
+                seq, bad, n_words, micro_bits, ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->d_fine_hist.as<uint32_t>(), d_overflow,
+                sk2 ? ctx->d_sk_hist64.as<ull>() : nullptr);
             CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER + 1], st));
             CK(cudaEventRecord(ev[2 * T_PART_COUNT], st));
+            if (sk2) {
+                // (records | k-mers) per micro-bin -> two prefix arrays; counting bins cut on the k-mer prefix, their first records alongside
+                launch_scan(ctx, ctx->d_sk_hist64.as<uint32_t>(), ctx->d_sk_prefix.as<uint64_t>(), n_micro, 2);       // low halves: k-mers
+                launch_scan(ctx, ctx->d_sk_hist64.as<uint32_t>() + 1, ctx->d_sk_rprefix.as<uint64_t>(), n_micro, 2);  // high halves: records
+                k_superk_bins<<<(n_micro + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk, sk_target,
+                                                                                 ctx->d_sk_rprefix.as<uint64_t>(), ctx->d_sk_recoff.as<uint64_t>());
+                CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
+                CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
+                k_sk2_scatter<<<(unsigned)std::min<uint64_t>((rec_cap + BLOCK - 1) / BLOCK, (uint64_t)ctx->nsm * 16), BLOCK, 0, st>>>(
+                    ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->d_sk_rprefix.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), ctx->d_keysB.as<SkRecord>());
+                CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
+                ctx->launches += 3;
+            } else {
             launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_sk_prefix.as<uint64_t>(), n_micro);
-            k_superk_bins<<<(n_micro + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk);
+            k_superk_bins<<<(n_micro + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk, sk_target, nullptr, nullptr);
             CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
             CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
             // default: flat (work per k-mer); SIMKA_B200_SUPERK_EXPAND=thread: one thread rolls a whole record
@@ -563,7 +589,8 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
                 ctx->d_keysA.as<SkRecord>(), d_nrec, rec_cap, ctx->kp, ctx->d_sk_prefix.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(),
                 ctx->d_keysB.as<uint64_t>());
             CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
-            ctx->launches += 4;
+            ctx->launches += 3;
+            }
         } else {
         // K1 (count / scan /) scatter
         CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
@@ -593,7 +620,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         (ctx->k2_minb3 ? k_partition2<false, 3> : k_partition2<false, 4>)<<<g2, BLOCK, 0, st>>>(ctx->d_keysA.as<uint64_t>(), ctx->d_base1.as<uint64_t>(), cnt1, ctx->d_tile_start.as<uint64_t>(), b1_bits, b2_bits, W,
                                                   nullptr, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), ctx->d_keysB.as<uint64_t>());
         CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
-        ctx->launches += 6;
+        ctx->launches += exact ? 4 : 5;  // (the scans count themselves)
         }
         // K3 count
         CountOut co;
@@ -610,11 +637,22 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         // table slot: the bits just below the bin bits (super-k-mer mode: bins are not key ranges, take the top bits)
         const int slot_shift = std::max(0, W - (sk ? 0 : bin_bits) - ilog2_floor(CNT_SLOTS));
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
+        if (sk && sk2) {
+            if (ctx->occ_sk2_count <= 0) {
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sk2_count, k_sk2_count, SK2_THREADS, sizeof(Sk2Smem)));
+                if (ctx->occ_sk2_count <= 0) ctx->occ_sk2_count = 1;
+            }
+            Sk2Out so;
+            so.stage_h = co.stage_h; so.stage_c = co.stage_c; so.surv = co.surv; so.totals = co.totals; so.error_flag = co.error_flag;
+            const unsigned g2c = (unsigned)std::min<uint64_t>(nbins_run, (uint64_t)ctx->nsm * ctx->occ_sk2_count);
+            k_sk2_count<<<g2c, SK2_THREADS, sizeof(Sk2Smem), st>>>(ctx->d_keysB.as<SkRecord>(), ctx->d_sk_recoff.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins_run,
+                                                                 ctx->kp, ctx->prm.abundance_min, ctx->prm.abundance_max, so);
+        } else
         k_bin_count<<<gbin, K3_BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins_run, slot_shift, ctx->prm.abundance_min,
                                             ctx->prm.abundance_max, co);
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT + 1], st));
         launch_scan(ctx, ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins_run);
-        ctx->launches += 3;
+        ctx->launches += 1;
         CK(cudaGetLastError());
         // the only host sync of the sample: sizes + totals
         int h_err = 0, h_overflow = 0;
@@ -664,7 +702,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
                 k_refine_hist<<<g, BLOCK, 0, st>>>(pack_h, h_surv, shift, ctx->d_fine_hist.as<uint32_t>());
                 launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), fgn1);
                 k_refine_scatter<<<g, BLOCK, 0, st>>>(pack_h, pack_c, h_surv, shift, ctx->d_fine_off.as<uint64_t>(), ctx->d_fine_cursor.as<uint32_t>(), sd.eh, sd.ec);
-                ctx->launches += 3;
+                ctx->launches += 2;
             }
             if (ctx->prm.complex_dist) {
                 const unsigned gh = (unsigned)std::min<uint64_t>((h_surv + BLOCK * 16 - 1) / (BLOCK * 16), (uint64_t)ctx->nsm * 4);
@@ -971,7 +1009,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
                     CK(cudaMemcpyAsync(sd.eh, ctx->d_keysA.p, sd.n * 8, cudaMemcpyDeviceToDevice, st));
                     CK(cudaMemcpyAsync(sd.ec, ctx->d_stage_c.p, sd.n * 4, cudaMemcpyDeviceToDevice, st));
                 }
-                ctx->launches += 4;
+                ctx->launches += 3;
             }
             CK(cudaGetLastError());
             fg_eff = fg2;
