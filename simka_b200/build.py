@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     deps = srcs + [CSRC / "kmer_device.cuh", ROOT.parent / "include" / "simka_b200.h", *sorted((CSRC / "host").glob("*.hpp")), *sorted((CSRC / "kernels").glob("*.cuh"))]
     LIBDIR.mkdir(exist_ok=True)
     if force or _stale(LIB, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, srcs), "-lz"]
+        extra = os.environ.get("SIMKA_B200_NVCC_EXTRA", "").split()  # experiments: -DSIMKA_SK2_SLOTS=... etc.
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", str(LIB), *map(str, srcs), "-lz"]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

@@ -177,22 +177,22 @@ static superk_scan_fn superk_scan_instance(int k) {
     return (k >= SK_MINK && k <= 31) ? tab[k - SK_MINK] : nullptr;
 }
 
-// fine_off[b] = first key of counting bin b = prefix[u] of the first micro-bin u with prefix[u] >= b * SK_TARGET (b <= nb; bins
-// past the last key are empty).  Thread u fills the bins that begin at micro-bin u; thread n_micro fills the tail.
+// fine_off[b] = first key of counting bin b = prefix[u] of the first micro-bin u with prefix[u] >= b * target (b <= nb; bins
+// past the last key are empty).  One thread per bin: a binary search over the exclusive prefix (an earlier version let the thread
+// of the last micro-bin fill every trailing empty bin by itself: 150 us per sample).
 __global__ void __launch_bounds__(BLOCK)
 k_superk_bins(const uint64_t *__restrict__ prefix /*[n_micro + 1]*/, uint32_t n_micro, uint64_t *__restrict__ fine_off, uint32_t nb, uint32_t target,
               const uint64_t *__restrict__ rec_prefix /*[n_micro + 1] or null*/, uint64_t *__restrict__ rec_off /*[nb + 1]: first record of bin b*/) {
-    const uint32_t u = blockIdx.x * BLOCK + threadIdx.x;
-    if (u > n_micro) return;
-    const uint64_t here = prefix[u];
-    // bins whose mark b * target lies in (prefix[u - 1], prefix[u]]  (u = 0: bin 0)
-    uint64_t b_lo = u ? prefix[u - 1] / target + 1 : 0;
-    uint64_t b_hi = u == n_micro ? (uint64_t)nb : here / target;
-    if (u == n_micro) b_lo = (n_micro ? prefix[n_micro - 1] / target + 1 : 0);
-    for (uint64_t b = b_lo; b <= b_hi && b <= nb; b++) {
-        fine_off[b] = here;
-        if (rec_prefix) rec_off[b] = rec_prefix[u];
+    const uint32_t b = blockIdx.x * BLOCK + threadIdx.x;
+    if (b > nb) return;
+    const uint64_t mark = (uint64_t)b * target;
+    uint32_t lo = 0, hi = n_micro;  // smallest u in [0, n_micro] with prefix[u] >= mark (prefix[0] = 0; u = n_micro when there is none below)
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (prefix[mid] >= mark) hi = mid; else lo = mid + 1;
     }
+    fine_off[b] = prefix[lo];
+    if (rec_prefix) rec_off[b] = rec_prefix[lo];
 }
 
 // records -> mixed canonical k-mers, written where k_bin_count expects the keys of the record's micro-bin

@@ -32,10 +32,16 @@
 #define SIMKA_SK2_THREADS 256
 #endif
 constexpr int SK2_THREADS = SIMKA_SK2_THREADS;
-constexpr int SK2_SLOTS = SIMKA_SK2_SLOTS;          // table slots of a counting CTA
+constexpr int SK2_SLOTS = SIMKA_SK2_SLOTS;          // table slots of a counting CTA (a power of two)
+constexpr int sk2_log2(int v) { return v <= 1 ? 0 : 1 + sk2_log2(v >> 1); }
+constexpr int SK2_SLOTS_LOG2 = sk2_log2(SK2_SLOTS);
 constexpr int SK2_MAXD = SK2_SLOTS * 3 / 4;         // distinct k-mers one table pass may hold
 constexpr int SK2_TARGET = SIMKA_SK2_TARGET;        // k-mers per counting bin (+ the micro-bin that crosses the mark)
-constexpr int SK2_RCAP = 256;                       // records per shared-memory chunk (8 KB)
+#ifndef SIMKA_SK2_RCAP
+#define SIMKA_SK2_RCAP 256
+#endif
+constexpr int SK2_RCAP = SIMKA_SK2_RCAP;            // records per shared-memory chunk (16 B each), a multiple of SK2_THREADS
+static_assert(SK2_RCAP % SK2_THREADS == 0 && SK2_RCAP * 8 <= 8192, "record chunk: a multiple of the CTA size, at most 1024 records (13-bit owner ids)");
 constexpr int SK2_G = 4;                            // consecutive k-mers per work item
 constexpr int SK2_MAXITEMS = SK2_RCAP * (32 / SK2_G);
 
@@ -57,36 +63,55 @@ k_sk2_scatter(const SkRecord *__restrict__ records, const ull *__restrict__ n_re
     }
 }
 
+struct Sk2Item { uint64_t r0; uint32_t bin, nrec, last, pad; };  // a work item: records [r0, r0 + nrec) of counting bin `bin`; last chunk of the bin?
 struct Sk2Smem {
     alignas(16) uint64_t tk[SK2_SLOTS];
     alignas(16) SkRecord rec[2][SK2_RCAP];
     alignas(16) uint32_t tc[SK2_SLOTS];
+    alignas(16) Sk2Item item[2];
     alignas(8) uint64_t bar[2];
-    uint32_t start[SK2_RCAP];
     uint32_t warp_tmp[SK2_THREADS / 32 + 1];
     uint32_t cursor, nclaim;
     ull tot[3];
     uint16_t claimed[SK2_SLOTS];
-    uint16_t owner[SK2_MAXITEMS];
+    uint16_t owner[SK2_MAXITEMS];   // (record << 3 | item of the record) of every work item of the chunk
 };
 
-// one probe sequence of the canonical-k-mer table; a full table (more than SK2_MAXD claims) is detected by the caller
-__device__ __forceinline__ void sk2_insert(Sk2Smem &S, uint64_t key) {
-    uint32_t slot = (uint32_t)(simka::hash2(key) >> 40) & (SK2_SLOTS - 1);
+__device__ __forceinline__ uint32_t sk2_slot(uint64_t key) {
+    // 32-bit mix of both halves (the k-mers of a bin share their minimizer, i.e. a substring: multiply twice)
+    uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
+    x *= 0x85EBCA77u;
+    return x >> (32 - SK2_SLOTS_LOG2);
+}
+
+// ONE probe of the canonical-k-mer table, branches closed before returning so that the warp reconverges after every probe.
+// Plain read first: most k-mers repeat one that is already there.  Returns true when the key is placed.
+__device__ __forceinline__ bool sk2_probe(Sk2Smem &S, uint64_t key, uint32_t slot) {
     volatile uint64_t *vk = S.tk;
-    for (int probes = 0; probes < SK2_SLOTS; probes++) {
-        uint64_t cur = vk[slot];
+    uint64_t cur = vk[slot];
+    if (cur == EMPTY) {
+        cur = atomicCAS(reinterpret_cast<ull *>(&S.tk[slot]), (ull)EMPTY, (ull)key);
         if (cur == EMPTY) {
-            cur = atomicCAS(reinterpret_cast<ull *>(&S.tk[slot]), (ull)EMPTY, (ull)key);
-            if (cur == EMPTY) {
-                cur = key;
-                const uint32_t q = atomicAdd(&S.nclaim, 1u);
-                if (q < (uint32_t)SK2_SLOTS) S.claimed[q] = (uint16_t)slot;
-            }
+            cur = key;
+            const uint32_t q = atomicAdd(&S.nclaim, 1u);
+            if (q < (uint32_t)SK2_SLOTS) S.claimed[q] = (uint16_t)slot;
         }
-        if (cur == key) { atomicAdd(&S.tc[slot], 1u); return; }
-        slot = (slot + 1) & (SK2_SLOTS - 1);
     }
+    const bool hit = cur == key;
+    if (hit) atomicAdd(&S.tc[slot], 1u);
+    return hit;
+}
+// linear probing from the slot after `slot` (the leftovers of a converged first round, or the slow path); a full table (more
+// than SK2_MAXD claims) is detected by the caller
+__device__ __forceinline__ void sk2_insert_from(Sk2Smem &S, uint64_t key, uint32_t slot) {
+    for (int probes = 1; probes < SK2_SLOTS; probes++) {
+        slot = (slot + 1) & (SK2_SLOTS - 1);
+        if (sk2_probe(S, key, slot)) return;
+    }
+}
+__device__ __forceinline__ void sk2_insert(Sk2Smem &S, uint64_t key) {
+    const uint32_t slot = sk2_slot(key);
+    if (!sk2_probe(S, key, slot)) sk2_insert_from(S, key, slot);
 }
 
 // the canonical k-mers j0 .. j0+cnt-1 of a record, each handed to f
@@ -132,7 +157,7 @@ __device__ __forceinline__ void sk2_expand_item(uint64_t hi, uint64_t lo, uint32
                 rh = (rh >> 2) | (((fl & 3u) ^ 2u) << s2);
             }
             const bool fwd_smaller = fh < rh || (fh == rh && fl < rl);
-            f(((uint64_t)(fwd_smaller ? fh : rh) << 32) | (fwd_smaller ? fl : rl));
+            f(g, ((uint64_t)(fwd_smaller ? fh : rh) << 32) | (fwd_smaller ? fl : rl));
         }
     }
 }
@@ -145,6 +170,10 @@ struct Sk2Out {
     int *error_flag;
 };
 
+// SHARDED: bucket-sharded contexts (simka_params.shard_rank / shard_count: several GPUs, or several passes of one GPU when the
+// solid lists of all samples do not fit in HBM) keep the k-mers whose hash falls into their shard -- the same rule as the k-mer
+// path (shard_keep on the mixed key), so a sample that falls back to that path stays consistent with the others.
+template <bool SHARDED>
 __global__ void __launch_bounds__(SK2_THREADS, 3)
 k_sk2_count(const SkRecord *__restrict__ recs, const uint64_t *__restrict__ rec_off, const uint64_t *__restrict__ key_off, uint32_t nbins,
             KParams kp, int64_t amin, int64_t amax, Sk2Out out) {
@@ -199,56 +228,88 @@ k_sk2_count(const SkRecord *__restrict__ recs, const uint64_t *__restrict__ rec_
         }
     };
 
-    // work items of this CTA: (bin, chunk of <= SK2_RCAP records); empty bins are skipped
-    auto first_nonempty = [&](uint32_t b) {
-        while (b < nbins && rec_off[b + 1] == rec_off[b]) { if (tid == 0) out.surv[b] = 0; b += gridDim.x; }
-        return b;
+    // Work items of this CTA: (bin, chunk of <= SK2_RCAP records), bins taken with a grid stride, empty bins skipped.  Thread 0
+    // plans one item ahead: it writes the item's descriptor to shared memory, arms the buffer's mbarrier with the byte count
+    // and starts the bulk copy of the records -- the copy engine fills the buffer while all warps work on the previous one.
+    // plan(cursor state in registers of thread 0 only) -> S.item[buf]
+    uint32_t p_bin = blockIdx.x, p_chunk = 0;  // thread 0: next item to plan
+    auto plan = [&](int buf) {
+        Sk2Item it;
+        it.bin = 0xFFFFFFFFu; it.nrec = 0; it.last = 0; it.r0 = 0; it.pad = 0;
+        while (p_bin < nbins) {
+            const uint64_t b0 = rec_off[p_bin], b1 = rec_off[p_bin + 1];
+            if (b1 == b0) { out.surv[p_bin] = 0; p_bin += gridDim.x; p_chunk = 0; continue; }
+            const uint64_t r0 = b0 + (uint64_t)p_chunk * SK2_RCAP;
+            it.bin = p_bin; it.r0 = r0;
+            it.nrec = (uint32_t)min((uint64_t)SK2_RCAP, b1 - r0);
+            it.last = r0 + it.nrec == b1;
+            if (it.last) { p_bin += gridDim.x; p_chunk = 0; } else p_chunk++;
+            break;
+        }
+        S.item[buf] = it;
+        if (it.bin != 0xFFFFFFFFu) {
+            mbar_arrive_expect_tx(&S.bar[buf], it.nrec * (uint32_t)sizeof(SkRecord));
+            bulk_g2s(S.rec[buf], recs + it.r0, it.nrec * (uint32_t)sizeof(SkRecord), &S.bar[buf]);
+        }
     };
-    auto issue = [&](uint32_t b, uint32_t chunk, int buf) {  // elected thread: arm the barrier, start the bulk copy
-        const uint64_t r0 = rec_off[b] + (uint64_t)chunk * SK2_RCAP;
-        const uint32_t n = (uint32_t)min((uint64_t)SK2_RCAP, rec_off[b + 1] - r0);
-        mbar_arrive_expect_tx(&S.bar[buf], n * (uint32_t)sizeof(SkRecord));
-        bulk_g2s(S.rec[buf], recs + r0, n * (uint32_t)sizeof(SkRecord), &S.bar[buf]);
-    };
-
-    uint32_t bin = first_nonempty(blockIdx.x), chunk = 0;
+    if (tid == 0) plan(0);
+    __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
     int buf = 0;
-    if (bin < nbins && tid == 0) issue(bin, 0, 0);
-    while (bin < nbins) {
-        const uint64_t nrec_bin = rec_off[bin + 1] - rec_off[bin];
-        const uint32_t nchunks = (uint32_t)((nrec_bin + SK2_RCAP - 1) / SK2_RCAP);
-        const uint32_t nrec = (uint32_t)min((uint64_t)SK2_RCAP, nrec_bin - (uint64_t)chunk * SK2_RCAP);
-        const bool last = chunk + 1 == nchunks;
-        // the next work item; its records are fetched by the copy engine while this chunk is processed (the other buffer was
-        // released by the __syncthreads that ended the previous iteration)
-        uint32_t nbin = bin, nchunk = chunk + 1;
-        if (last) { nbin = first_nonempty(bin + gridDim.x); nchunk = 0; }
-        if (tid == 0 && nbin < nbins) issue(nbin, nchunk, buf ^ 1);
+    for (;;) {
+        const Sk2Item it = S.item[buf];
+        if (it.bin == 0xFFFFFFFFu) break;
+        if (tid == 0) plan(buf ^ 1);  // (the other buffer and its descriptor were released by the barrier that ended the previous iteration)
         if (buf == 0) { mbar_wait(&S.bar[0], phase0); phase0 ^= 1; } else { mbar_wait(&S.bar[1], phase1); phase1 ^= 1; }
         const SkRecord *sr = S.rec[buf];
-        // lay the items (SK2_G consecutive k-mers of one record) out flat
-        for (uint32_t r = tid; r < (uint32_t)SK2_RCAP; r += SK2_THREADS)
-            S.start[r] = r < nrec ? ((((uint32_t)(sr[r].lo >> 21) & 31u) + 1) + SK2_G - 1) / SK2_G : 0;
+        const uint32_t nrec = it.nrec, bin = it.bin;
+        // lay the work items (SK2_G consecutive k-mers of one record) out flat: thread t owns records t, t + THREADS, ...;
+        // exclusive prefix of its item count by warp shuffles + one pass over the warp totals
+        uint32_t my_items[SK2_RCAP / SK2_THREADS], my_sum = 0;
+#pragma unroll
+        for (int q = 0; q < SK2_RCAP / SK2_THREADS; q++) {
+            const uint32_t r = q * SK2_THREADS + tid;
+            my_items[q] = r < nrec ? ((((uint32_t)(sr[r].lo >> 21) & 31u) + 1) + SK2_G - 1) / SK2_G : 0;
+            my_sum += my_items[q];
+        }
+        uint32_t inc = my_sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+        if (lane == 31) S.warp_tmp[tid >> 5] = inc;
         __syncthreads();
-        block_exclusive_scan<SK2_THREADS>(S.start, SK2_RCAP, S.warp_tmp);
-        const uint32_t total = S.warp_tmp[SK2_THREADS / 32];
-        for (uint32_t r = tid; r < nrec; r += SK2_THREADS) {
-            const uint32_t st = S.start[r], items = ((((uint32_t)(sr[r].lo >> 21) & 31u) + 1) + SK2_G - 1) / SK2_G;
-            for (uint32_t j = 0; j < items; j++) S.owner[st + j] = (uint16_t)r;
+        uint32_t base = inc - my_sum, total = 0;
+#pragma unroll
+        for (int w = 0; w < SK2_THREADS / 32; w++) { const uint32_t v = S.warp_tmp[w]; if (w < (tid >> 5)) base += v; total += v; }
+#pragma unroll
+        for (int q = 0; q < SK2_RCAP / SK2_THREADS; q++) {
+            const uint32_t r = q * SK2_THREADS + tid;
+            for (uint32_t j = 0; j < my_items[q]; j++) S.owner[base + j] = (uint16_t)((r << 3) | j);
+            base += my_items[q];
         }
         __syncthreads();
         if (*((volatile uint32_t *)&S.nclaim) <= (uint32_t)SK2_MAXD) {  // (an overflowing bin is redone below: no point filling a full table)
             for (uint32_t i = tid; i < total; i += SK2_THREADS) {
-                const uint32_t o = S.owner[i];
-                const uint32_t j0 = (i - S.start[o]) * SK2_G;
+                const uint32_t ow = S.owner[i];
+                const uint32_t o = ow >> 3, j0 = (ow & 7u) * SK2_G;
                 const uint64_t hi = sr[o].hi, lo = sr[o].lo;
                 const uint32_t n = ((uint32_t)(lo >> 21) & 31u) + 1;
-                sk2_expand_item(hi, lo, j0, min((uint32_t)SK2_G, n - j0), k, [&](uint64_t canon) { sk2_insert(S, canon); });
+                // first probes of the item's k-mers with the warp converged; the few that find another k-mer in their home slot
+                // are walked afterwards
+                uint64_t left_key[SK2_G];
+                uint32_t left = 0;
+                sk2_expand_item(hi, lo, j0, min((uint32_t)SK2_G, n - j0), k, [&](int g, uint64_t canon) {
+                    left_key[g] = canon;
+                    if (!SHARDED || shard_keep(simka::mix_fwd(canon, kp.mix), kp)) {
+                        if (!sk2_probe(S, canon, sk2_slot(canon))) left |= 1u << g;
+                    }
+                });
+#pragma unroll
+                for (int q = 0; q < SK2_G; q++)
+                    if (left & (1u << q)) sk2_insert_from(S, left_key[q], sk2_slot(left_key[q]));
             }
         }
         __syncthreads();
-        if (last) {
+        if (it.last) {
             ull b_d = 0, b_s = 0, b_q = 0;
             const bool overflow = S.nclaim > (uint32_t)SK2_MAXD;
             read_out(bin, overflow, b_d, b_s, b_q);
@@ -257,6 +318,7 @@ k_sk2_count(const SkRecord *__restrict__ recs, const uint64_t *__restrict__ rec_
             if (overflow) {
                 // more distinct k-mers than one table pass holds (a heavy minimizer: low-complexity sequence): R hash-selected
                 // sub-passes straight from global memory, one thread per record; rare, only has to be correct
+                const uint64_t rb0 = rec_off[bin], nrec_bin = rec_off[bin + 1] - rb0;
                 for (uint32_t R = 2;; R *= 2) {
                     if (R > 65536) { if (tid == 0) *out.error_flag = 5; break; }
                     b_d = b_s = b_q = 0;
@@ -266,10 +328,13 @@ k_sk2_count(const SkRecord *__restrict__ recs, const uint64_t *__restrict__ rec_
                     for (uint32_t r = 0; r < R && !again; r++) {
                         for (uint64_t q = tid; q < nrec_bin; q += SK2_THREADS) {
                             if (*((volatile uint32_t *)&S.nclaim) > (uint32_t)SK2_MAXD) break;
-                            const SkRecord rc = recs[rec_off[bin] + q];
+                            const SkRecord rc = recs[rb0 + q];
                             const uint32_t n = ((uint32_t)(rc.lo >> 21) & 31u) + 1;
                             sk2_expand(rc.hi, rc.lo, 0, n, k, kmask, [&](uint64_t canon) {
-                                if ((((uint32_t)(simka::hash2(canon) >> 20)) & (R - 1)) == r) sk2_insert(S, canon);
+                                // (a full avalanche: the k-mers of a heavy minimizer differ in few bits, a multiply alone leaves
+                                // thousands of them with equal selector bits and the sub-passes would never split them)
+                                if (((uint32_t)(simka::murmur3_fmix64(canon) >> 20) & (R - 1)) == r && (!SHARDED || shard_keep(simka::mix_fwd(canon, kp.mix), kp)))
+                                    sk2_insert(S, canon);
                             });
                         }
                         __syncthreads();
@@ -286,7 +351,7 @@ k_sk2_count(const SkRecord *__restrict__ recs, const uint64_t *__restrict__ rec_
             if (tid == 0) { out.surv[bin] = S.cursor; S.cursor = 0; }
         }
         __syncthreads();
-        bin = nbin; chunk = nchunk; buf ^= 1;
+        buf ^= 1;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {

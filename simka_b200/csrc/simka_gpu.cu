@@ -73,17 +73,25 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-// bump allocator for the per-sample solid k-mer lists (kept across simka_gpu_reset)
+// bump allocator for the per-sample solid k-mer lists (kept across simka_gpu_reset).  Small requests share 256 MB chunks; a
+// request of 64 MB or more gets a chunk of exactly its size (512 samples x 290 MB of lists leave no room for 40 % of slack), and
+// best fit makes the next step -- same sizes -- find the same chunks again.
 struct Arena {
     struct Chunk { char *p; size_t cap, used; };
     std::vector<Chunk> chunks;
     void *alloc(size_t bytes) {
         bytes = (bytes + 255) & ~(size_t)255;
+        Chunk *best = nullptr;
         for (auto &c : chunks)
-            if (c.cap - c.used >= bytes) { void *r = c.p + c.used; c.used += bytes; return r; }
-        size_t cap = std::max<size_t>(bytes, (size_t)256 << 20);
+            if (c.cap - c.used >= bytes && (!best || c.cap - c.used < best->cap - best->used)) best = &c;
+        if (best) { void *r = best->p + best->used; best->used += bytes; return r; }
+        size_t cap = bytes >= ((size_t)64 << 20) ? bytes : std::max<size_t>(bytes, (size_t)256 << 20);
         void *p = nullptr;
-        if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&p, cap) != cudaSuccess) {
+            cudaGetLastError();
+            if (cap == bytes || cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            cap = bytes;
+        }
         chunks.push_back({(char *)p, cap, bytes});
         return p;
     }
@@ -304,7 +312,8 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
             ok = ok && cudaFuncSetAttribute(extract_instance(false, sh, bk), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(p->nb_samples)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_sk2_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sk2Smem)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_sk2_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sk2Smem)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_sk2_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sk2Smem)) == cudaSuccess;
     ok = ok && ctx->d_small.reserve(64) == 0;
     ok = ok && ctx->d_scan_tmp.reserve(((size_t)1 << 17) * 8 + 64) == 0;  // block sums of the device-wide scans (up to 2^31 elements)
     if (ok) {  // tab_log table
@@ -530,7 +539,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         cudaEvent_t *ev = ctx->ev[evset];
         CK(cudaEventRecord(ev[2 * T_NSTAGE], st));  // sample start
       // experimental front end (SIMKA_B200_SUPERK=1): super-k-mer records instead of the two k-mer partition levels
-      const bool sk_eligible = ctx->use_superk && !ctx->kp.key_mode && ctx->kp.shard_count <= 1 && ctx->kp.k >= SK_MINK && ctx->kp.k <= 31 &&
+      const bool sk_eligible = ctx->use_superk && !ctx->kp.key_mode && (ctx->kp.shard_count <= 1 || sk2) && ctx->kp.k >= SK_MINK && ctx->kp.k <= 31 &&
                                !ctx->force_exact;
       for (int attempt = sk_eligible ? -1 : 0; attempt < 2; attempt++) {
         // attempt -1 (super-k-mer mode only): records; falls back to attempt 0 when the record list overflows.
@@ -571,7 +580,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
                 // (records | k-mers) per micro-bin -> two prefix arrays; counting bins cut on the k-mer prefix, their first records alongside
                 launch_scan(ctx, ctx->d_sk_hist64.as<uint32_t>(), ctx->d_sk_prefix.as<uint64_t>(), n_micro, 2);       // low halves: k-mers
                 launch_scan(ctx, ctx->d_sk_hist64.as<uint32_t>() + 1, ctx->d_sk_rprefix.as<uint64_t>(), n_micro, 2);  // high halves: records
-                k_superk_bins<<<(n_micro + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk, sk_target,
+                k_superk_bins<<<(nb_sk + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk, sk_target,
                                                                                  ctx->d_sk_rprefix.as<uint64_t>(), ctx->d_sk_recoff.as<uint64_t>());
                 CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
                 CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
@@ -581,7 +590,7 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
                 ctx->launches += 3;
             } else {
             launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_sk_prefix.as<uint64_t>(), n_micro);
-            k_superk_bins<<<(n_micro + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk, sk_target, nullptr, nullptr);
+            k_superk_bins<<<(nb_sk + 1 + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(ctx->d_sk_prefix.as<uint64_t>(), n_micro, ctx->d_fine_off.as<uint64_t>(), nb_sk, sk_target, nullptr, nullptr);
             CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
             CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st));
             // default: flat (work per k-mer); SIMKA_B200_SUPERK_EXPAND=thread: one thread rolls a whole record
@@ -639,13 +648,13 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
         CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
         if (sk && sk2) {
             if (ctx->occ_sk2_count <= 0) {
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sk2_count, k_sk2_count, SK2_THREADS, sizeof(Sk2Smem)));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sk2_count, k_sk2_count<false>, SK2_THREADS, sizeof(Sk2Smem)));
                 if (ctx->occ_sk2_count <= 0) ctx->occ_sk2_count = 1;
             }
             Sk2Out so;
             so.stage_h = co.stage_h; so.stage_c = co.stage_c; so.surv = co.surv; so.totals = co.totals; so.error_flag = co.error_flag;
             const unsigned g2c = (unsigned)std::min<uint64_t>(nbins_run, (uint64_t)ctx->nsm * ctx->occ_sk2_count);
-            k_sk2_count<<<g2c, SK2_THREADS, sizeof(Sk2Smem), st>>>(ctx->d_keysB.as<SkRecord>(), ctx->d_sk_recoff.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins_run,
+            (ctx->kp.shard_count > 1 ? k_sk2_count<true> : k_sk2_count<false>)<<<g2c, SK2_THREADS, sizeof(Sk2Smem), st>>>(ctx->d_keysB.as<SkRecord>(), ctx->d_sk_recoff.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins_run,
                                                                  ctx->kp, ctx->prm.abundance_min, ctx->prm.abundance_max, so);
         } else
         k_bin_count<<<gbin, K3_BLOCK, 0, st>>>(ctx->d_keysB.as<uint64_t>(), ctx->d_fine_off.as<uint64_t>(), nbins_run, slot_shift, ctx->prm.abundance_min,

@@ -100,3 +100,29 @@ def test_records_many_samples(monkeypatch):
     st, ctx = run_superk(samples, 21, 2, expect_fallbacks=0)
     ctx.close()
     assert_stats_equal(st, oracle_run(samples, 21, 2))
+
+
+def test_records_shards_sum_to_whole(monkeypatch):
+    """bucket-sharded contexts on the record path (several GPUs, or several passes of one GPU over the reads): the shards'
+    statistics sum to the whole"""
+    monkeypatch.setenv("SIMKA_B200_SUPERK", MODE)
+    samples = small_samples(4, 300)
+    run = oracle_run(samples, 31, 2)
+    S = 3
+    ctxs = [simka_b200.SimkaGpu(len(samples), 31, 2, simple_dist=True, complex_dist=True, shard_rank=r, shard_count=S) for r in range(S)]
+    for c in ctxs:
+        for s, (seqs, off) in enumerate(samples):
+            p, b, nw = simka_b200.pack_reads(seqs, off)
+            c.push_reads(s, p, b, nw, len(off) - 1)
+            c.finish_sample(s)
+        assert c.timings()["superk_samples"] == len(samples)
+    tot = sum(c.get_totals() for c in ctxs)
+    tot[:, 0] = ctxs[0].get_totals()[:, 0]
+    total = None
+    for c in ctxs:
+        c.set_totals(tot)
+        c.merge_and_accumulate()
+        st = c.stats()
+        total = st if total is None else total.__iadd__(st)
+        c.close()
+    assert_stats_equal(total, run)
