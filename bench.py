@@ -410,19 +410,25 @@ def run_ours(a):
 
     exp = M * (L - k + 1)
     ctx = simka_b200.SimkaGpu(N, k, a.abundance_min, simple_dist=True, complex_dist=True, device=local, expected_kmers_per_sample=exp)
-    mctx = simka_b200.SimkaGpu(N, k, a.abundance_min, simple_dist=True, complex_dist=True, device=local) if world > 1 else None
+    mctx = simka_b200.SimkaGpu(N, k, a.abundance_min, simple_dist=True, complex_dist=True, device=local) if (world > 1 and os.environ.get("SIMKA_BENCH_EXCHANGE", "native") != "native") else None
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
     d2h_bytes = [0]
 
+    native = world > 1 and os.environ.get("SIMKA_BENCH_EXCHANGE", "native") == "native"  # "torch": the round-1 exchange in simka_b200/dist.py
+    if native:
+        sdist.native_comm_init(ctx, rank, world, dev)
+
     def finish_run():
-        if world > 1:
+        if native:  # totals all-reduce, list exchange, merge, accumulator all-reduce: all inside the library (NCCL)
+            st = sdist.exchange_and_merge_native(ctx)
+        elif world > 1:
             mctx.reset()
             st = sdist.exchange_and_merge(ctx, mctx, N, rank, world, dev)
         else:
             ctx.merge_and_accumulate()
             st = ctx.stats()
         d2h_bytes[0] = sum(getattr(st, n).nbytes for n in st.U64_SYM + st.U64_SQ) + st.kullback_leibler.nbytes
-        if world > 1:
+        if world > 1 and not native:
             st = sdist.allreduce_stats(st)
         return st
 
@@ -459,7 +465,11 @@ def run_ours(a):
         for _ in range(steps):
             st = fn()
             t = ctx.timings()
-            if mctx is not None:  # stage 2 ran in the merge context
+            if native:  # (ctx.timings() already reports stage 2 of the internal merge context; pairs / distinct k-mers are global there)
+                xt = ctx.exchange_timings()
+                for kk in ("totals_sizes_ms", "exchange_ms", "allreduce_ms"):
+                    t["x_" + kk] = xt[kk]
+            elif mctx is not None:  # stage 2 ran in the merge context
                 tm = mctx.timings()
                 for kk in ("merge_ms", "distinct_kmers", "pairs", "kernel_launches"):
                     t[kk] += tm[kk]
@@ -541,7 +551,7 @@ def run_ours(a):
         peak, peak_src = hbm_peak()
         kernels = {n: {"ms_per_step": tms[n], "alg_bytes_per_step": alg[n], "achieved_gbs": (alg[n] / (tms[n] * 1e-3) / 1e9) if tms[n] > 0 else None} for n in alg}
         kernels["other (compaction, regrouping, scans, memsets)"] = {"ms_per_step": max(0.0, per["samples_ms"] + per["merge_ms"] - sum(tms.values()))}
-        kernels["k_merge"]["pair_updates_per_s"] = per["pairs"] / (tms["k_merge"] * 1e-3) if tms["k_merge"] > 0 else None
+        kernels["k_merge"]["pair_updates_per_s"] = per["pairs"] / (tms["k_merge"] * 1e-3) if (tms["k_merge"] > 0 and world == 1) else None
         dom = max(tms, key=lambda n: tms[n])
         achieved = kernels[dom]["achieved_gbs"] or 0.0
         step_ms = ms_res / steps
@@ -567,6 +577,9 @@ def run_ours(a):
             "kernels": kernels,
             "counts": {"kmers_in_per_step": Ks, "solid_entries": D, "distinct_kmers": U, "pairs": per["pairs"]},
         }
+        if world > 1 and "x_exchange_ms" in per:
+            line["notes"]["exchange_rank0_ms_per_step"] = {"totals+sizes all-reduce": per["x_totals_sizes_ms"], "list exchange (ncclSend/ncclRecv)": per["x_exchange_ms"],
+                                                           "accumulator all-reduce": per["x_allreduce_ms"], "implementation": "simka_gpu_exchange_and_merge (C++, NCCL)"}
         if verify:
             line["verify"] = verify
         if world == 1 and not a.no_cpu_baseline:

@@ -143,6 +143,22 @@ int simka_gpu_export_sample(simka_ctx *ctx, int sample_id, const uint64_t **d_km
 int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kmers, const uint32_t *d_counts, uint64_t n,
                             const uint32_t *d_off, int fine_bits, uint64_t nb_reads);
 
+/* ---- multi-GPU inside the library: NCCL over NVLink ------------------------------------------------
+ * One context per GPU (one process per GPU under torchrun / mpirun, or one host thread per GPU in the `simka -nb-gpus` command
+ * line).  Rank r counts the samples s with s % world == r through the calls above; then ONE call does everything the reference
+ * does between and after its two stages (src/SimkaPotara.hpp:991-1058 barrier + merge jobs, :1161-1174 sum of the
+ * per-partition statistics): the per-sample totals become global (ncclAllReduce), every sample's list slice goes straight from
+ * the list it was counted into to the rank that owns that block of hash ranges (ncclSend / ncclRecv in one group, no staging
+ * copy), that rank merges its block over all samples, and the N x N accumulators are summed over the ranks (ncclAllReduce:
+ * u64 block, f64 block).  Afterwards simka_gpu_get_stats(ctx) returns the GLOBAL statistics on every rank.
+ * NCCL is loaded at run time (libnccl.so.2); without it these entries fail with SIMKA_ERR_INVALID. */
+#define SIMKA_COMM_ID_BYTES 128
+int simka_comm_unique_id(uint8_t id[SIMKA_COMM_ID_BYTES]);                       /* rank 0; hand the bytes to every rank */
+int simka_gpu_comm_init(simka_ctx *ctx, const uint8_t id[SIMKA_COMM_ID_BYTES], int rank, int world);
+int simka_gpu_exchange_and_merge(simka_ctx *ctx);
+/* device time of the last simka_gpu_exchange_and_merge, in ms: [0] totals + sizes all-reduce, [1] list exchange, [2] merge, [3] accumulator all-reduce */
+int simka_gpu_exchange_timings(simka_ctx *ctx, float ms[4]);
+
 /* Registers a sample from its solid (canonical k-mer, count) list in HOST memory -- the decoded content of the
  * reference-format files solid/part_P/__p__I.gz (src/SimkaCount.cpp:248-257, records read by
  * src/SimkaMerge.cpp:1082-1103) -- instead of counting its reads.  Any order; counts already abundance-filtered.

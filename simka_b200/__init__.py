@@ -5,8 +5,8 @@ merge -> N x N ecological-distance accumulators, behind the C ABI of include/sim
 The compute lives in lib/libsimka_b200.so (hand-written CUDA); this package is the ctypes front end
 and fails loudly if that library is missing -- there is no CPU path.
 """
-from .api import (SimkaError, SimkaGpu, SimkaStatistics, pack_reads, pinned_empty, run_samples,  # noqa: F401
+from .api import (SimkaError, SimkaGpu, SimkaStatistics, comm_unique_id, pack_reads, pinned_empty, run_samples,  # noqa: F401
                   simkamin_distance, simkamin_last_sketch_info, simkamin_sketch)
 
-__all__ = ["SimkaError", "SimkaGpu", "SimkaStatistics", "pack_reads", "pinned_empty", "run_samples",
+__all__ = ["SimkaError", "SimkaGpu", "SimkaStatistics", "comm_unique_id", "pack_reads", "pinned_empty", "run_samples",
            "simkamin_distance", "simkamin_last_sketch_info", "simkamin_sketch"]

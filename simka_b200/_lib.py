@@ -62,6 +62,10 @@ SYMBOLS = {
     "simka_gpu_fine_bits": (C.c_int, [C.c_void_p]),
     "simka_gpu_export_sample": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p]),
     "simka_gpu_import_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_uint64]),
+    "simka_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "simka_gpu_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "simka_gpu_exchange_and_merge": (C.c_int, [C.c_void_p]),
+    "simka_gpu_exchange_timings": (C.c_int, [C.c_void_p, f32p]),
     "simka_gpu_import_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "simka_gpu_get_totals": (C.c_int, [C.c_void_p, C.POINTER(SampleTotals)]),
     "simka_gpu_set_totals": (C.c_int, [C.c_void_p, C.POINTER(SampleTotals)]),

@@ -95,6 +95,15 @@ class PinnedArray(np.ndarray):
         self._owner = getattr(obj, "_owner", None)
 
 
+def comm_unique_id() -> bytes:
+    """rank 0: the NCCL unique id every rank passes to SimkaGpu.comm_init (simka_comm_unique_id)"""
+    buf = (C.c_uint8 * 128)()
+    rc = _lib.load().simka_comm_unique_id(buf)
+    if rc != 0:
+        raise SimkaError(f"simka_comm_unique_id failed ({ERRORS.get(rc, rc)}): libnccl.so.2 not loadable?")
+    return bytes(buf)
+
+
 def pinned_empty(n: int, dtype) -> np.ndarray:
     """numpy array over cudaHostAlloc'd memory (for asynchronous H2D copies)."""
     L = _lib.load()
@@ -251,6 +260,22 @@ class SimkaGpu:
         self._check(self._L.simka_gpu_dump_sample_counts(self._h, sample, km.ctypes.data_as(_lib.u64p),
                                                          ct.ctypes.data_as(_lib.u32p), C.byref(n)), "dump_sample_counts")
         return km[:n.value], ct[:n.value]
+
+    # ---- multi-GPU inside the library (NCCL): simka_gpu_comm_init / simka_gpu_exchange_and_merge ----
+    def comm_init(self, comm_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(comm_id).ljust(128, b"\0")[:128])
+        self._check(self._L.simka_gpu_comm_init(self._h, buf, rank, world), "comm_init")
+        self.comm_rank, self.comm_world = rank, world
+
+    def exchange_and_merge(self):
+        """after this rank's samples (s % world == rank) are finished: global totals, list exchange, merge of this rank's block
+        of hash ranges, accumulators summed over the ranks.  stats() then returns the GLOBAL statistics."""
+        self._check(self._L.simka_gpu_exchange_and_merge(self._h), "exchange_and_merge")
+
+    def exchange_timings(self):
+        ms = (C.c_float * 4)()
+        self._L.simka_gpu_exchange_timings(self._h, ms)
+        return {"totals_sizes_ms": ms[0], "exchange_ms": ms[1], "merge_ms": ms[2], "allreduce_ms": ms[3]}
 
     # ---- sample-sharded multi-GPU: the exchange between the stages (see include/simka_b200.h) ----
     def fine_bits(self) -> int:

@@ -135,9 +135,15 @@ k_merge(MergeArgs a) {
         if (tid == 0) s_pre[N] = n_e;
         __syncthreads();
         if (n_e == 0) continue;
-        uint32_t R = 1;
-        if (n_e > MRG_CAP) { while ((uint64_t)R * (MRG_CAP / 2) < n_e) R <<= 1; }
-        for (uint32_t r = 0; r < R; r++) {
+        uint32_t R0 = 1;
+        if (n_e > MRG_CAP) { while ((uint64_t)R0 * (MRG_CAP / 2) < n_e) R0 <<= 1; }
+        // Sub-passes select the keys with hash bits == r (mod R).  The entries of one k-mer stay together, so with hundreds of
+        // samples a sub-pass can still hold more grouped entries than fit (a few k-mers shared by everybody): such a sub-pass is
+        // split in two (R doubled) BEFORE anything of it is accumulated -- a depth-first walk over the selector tree.
+        uint32_t R = R0, r = 0;
+        bool more = true;
+        while (more) {
+            bool split = false;
             __syncthreads();  // pair enumeration of the previous sub-pass still reads the group arrays
             for (int i = tid; i < MRG_SLOTS; i += BLOCK) { tk[i] = EMPTY; gs[i] = 0; pp[i] = 0; }
             if (tid == 0) { s_groups = 0; s_shared = 0; }
@@ -155,7 +161,7 @@ k_merge(MergeArgs a) {
                     ull prev = atomicCAS(reinterpret_cast<ull *>(&tk[slot]), (ull)EMPTY, (ull)h);
                     if (prev == EMPTY || prev == h) { atomicAdd(&gs[slot], 1u); break; }
                     slot = (slot + 1) & (MRG_SLOTS - 1);
-                    if (++probes >= MRG_SLOTS) { *a.error_flag = 3; break; }
+                    if (++probes >= MRG_SLOTS) break;  // table full: this sub-pass is split below, nothing of it is kept
                 }
             }
             __syncthreads();
@@ -174,11 +180,23 @@ k_merge(MergeArgs a) {
             block_exclusive_scan(gs, MRG_SLOTS, warp_tmp);
             const uint32_t n_sub = warp_tmp[BLOCK / 32];
             const uint32_t n_shared_groups = s_shared;
-            if (tid == 0) { loc_groups += s_groups; loc_shared += s_shared; }
             __syncthreads();
-            if (a.count_only) continue;
-            if (n_sub > MRG_CAP) { if (tid == 0) *a.error_flag = 4; continue; }
-            if (n_shared_groups == 0) continue;  // nothing shared in this bin: no accumulator changes
+            // what follows the selection of the next sub-pass (the statements at the loop's end) for every way out of this one
+#define MRG_NEXT_SUBPASS()                                                                                       \
+            do {                                                                                                 \
+                if (split) { R <<= 1; }                                                                          \
+                else {                                                                                           \
+                    while (R > R0 && (r & (R >> 1))) { r -= R >> 1; R >>= 1; }                                   \
+                    if (R == R0) { r++; if (r >= R0) more = false; }                                             \
+                    else r += R >> 1;                                                                            \
+                }                                                                                                \
+            } while (0)
+            if (n_sub > MRG_CAP || s_groups > (uint32_t)(MRG_SLOTS * 7 / 8)) {
+                if (R >= (1u << 24)) { if (tid == 0) *a.error_flag = 4; }
+                else { split = true; MRG_NEXT_SUBPASS(); continue; }
+            }
+            if (tid == 0) { loc_groups += s_groups; loc_shared += s_shared; }
+            if (a.count_only || n_sub > MRG_CAP || n_shared_groups == 0) { MRG_NEXT_SUBPASS(); continue; }  // (nothing shared in this bin: no accumulator changes)
             // phase 3: scatter the entries of shared k-mers into their groups
             for (uint32_t i = tid; i < n_e; i += BLOCK) {
                 int lo = 0, hi = N;
@@ -224,7 +242,9 @@ k_merge(MergeArgs a) {
                 accumulate_pair(a, si, sj, ci, cj);
             }
             if (tid == 0) atomicAdd(&a.scalars[2], (ull)P);
+            MRG_NEXT_SUBPASS();
         }
+#undef MRG_NEXT_SUBPASS
     }
     if (tid == 0 && (loc_groups | loc_shared)) {
         atomicAdd(&a.scalars[0], loc_groups);

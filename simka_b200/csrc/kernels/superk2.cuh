@@ -173,8 +173,11 @@ struct Sk2Out {
 // SHARDED: bucket-sharded contexts (simka_params.shard_rank / shard_count: several GPUs, or several passes of one GPU when the
 // solid lists of all samples do not fit in HBM) keep the k-mers whose hash falls into their shard -- the same rule as the k-mer
 // path (shard_keep on the mixed key), so a sample that falls back to that path stays consistent with the others.
+#ifndef SIMKA_SK2_MINB
+#define SIMKA_SK2_MINB 3
+#endif
 template <bool SHARDED>
-__global__ void __launch_bounds__(SK2_THREADS, 3)
+__global__ void __launch_bounds__(SK2_THREADS, SIMKA_SK2_MINB)
 k_sk2_count(const SkRecord *__restrict__ recs, const uint64_t *__restrict__ rec_off, const uint64_t *__restrict__ key_off, uint32_t nbins,
             KParams kp, int64_t amin, int64_t amax, Sk2Out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -14,6 +14,7 @@
 //
 // What each stage replaces in the reference is cited at the kernels.  No host fallback exists.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,6 +28,15 @@
 
 #include "../../include/simka_b200.h"
 #include "kmer_device.cuh"
+
+// NCCL: types from its header at build time, the library itself is loaded at run time (dlopen) so that nothing but the multi-GPU
+// entry points depends on it
+#if !defined(SIMKA_NO_NCCL) && __has_include(<nccl.h>)
+#include <nccl.h>
+#define SIMKA_HAVE_NCCL_H 1
+#else
+#define SIMKA_HAVE_NCCL_H 0
+#endif
 
 using simka::Mix;
 
@@ -174,6 +184,14 @@ struct simka_ctx {
     uint64_t launches = 0;
     int nsm = 148;
     int occ_bin_count = 0, occ_sk2_count = 0;
+    // multi-GPU (simka_gpu_comm_init / simka_gpu_exchange_and_merge)
+    void *comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    simka_ctx *mctx = nullptr;   // merge context of this rank's block of hash ranges
+    bool reduced = false;        // accumulators already summed over the ranks: closed forms use the global totals
+    DevBuf d_xhdr;
+    cudaEvent_t xev[5] = {};
+    float xms[4] = {0, 0, 0, 0};
     int b1_override = 0;  // SIMKA_B200_B1BITS: level-1 bucket bits (experiments)
     bool k2_minb3 = false;  // SIMKA_B200_K2_MINB=3: scatter pass of K2 compiled for 3 CTAs per SM (no register spill; experiments)
 
@@ -248,6 +266,7 @@ static int reset_state(simka_ctx *ctx) {
     ctx->totals_overridden = false;
     ctx->import_pending = false;
     ctx->merged = false;
+    ctx->reduced = false;
     ctx->fg_bits = -1;
     for (float &f : ctx->stage_ms) f = 0;
     ctx->sample_ms = ctx->merge_ms = 0;
@@ -348,9 +367,15 @@ int simka_gpu_reset(simka_ctx *ctx) {
     return reset_state(ctx);
 }
 
+static void comm_release(simka_ctx *ctx);
+
 void simka_gpu_destroy(simka_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->prm.device);
+    comm_release(ctx);
+    if (ctx->mctx) { simka_gpu_destroy(ctx->mctx); ctx->mctx = nullptr; }
+    for (auto &e : ctx->xev) if (e) cudaEventDestroy(e);
+    ctx->d_xhdr.release();
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     ctx->arena.release();
@@ -1110,6 +1135,11 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
 }
 
 int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) try {
+    if (ctx && out && ctx->mctx && ctx->mctx->merged) {  // after simka_gpu_exchange_and_merge: the global statistics live in the merge context
+        const int rc = simka_gpu_get_stats(ctx->mctx, out);
+        if (rc != SIMKA_OK) ctx->set_error(ctx->mctx->err);
+        return rc;
+    }
     if (!ctx || !out || !ctx->merged) { if (ctx) ctx->set_error("merge_and_accumulate has not run"); return SIMKA_ERR_INVALID; }
     CK(cudaSetDevice(ctx->prm.device));
     const int N = ctx->prm.nb_samples;
@@ -1146,7 +1176,9 @@ int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) try {
             for (int i = 0; i < N; i++)
                 for (int j = i + 1; j < N; j++) {
                     const ull a = distinct[(size_t)j + (size_t)(N - 1) * i - ((size_t)i * (i - 1) / 2)];
-                    out->canberra[(size_t)i * N + j] = ctx->samples[i].local.nb_distinct + ctx->samples[j].local.nb_distinct - 2 * a;
+                    const simka_sample_totals &ti = ctx->reduced ? ctx->global_totals[i] : ctx->samples[i].local;
+                    const simka_sample_totals &tj = ctx->reduced ? ctx->global_totals[j] : ctx->samples[j].local;
+                    out->canberra[(size_t)i * N + j] = ti.nb_distinct + tj.nb_distinct - 2 * a;
                 }
         }
         if (out->kullback_leibler) {
@@ -1158,8 +1190,8 @@ int simka_gpu_get_stats(simka_ctx *ctx, simka_stats_view *out) try {
                     double v = kl[ij] + ldexp((double)klfix[ij], -60);
                     const double Ni = (double)ctx->global_totals[i].nb_kmers, Nj = (double)ctx->global_totals[j].nb_kmers;
                     // k-mers present in exactly one of the two samples: (c/N_x) * log(2 c N_y / (c N_y + 0)) each
-                    const ull only_i = ctx->samples[i].local.nb_kmers - nb_shared[ij];
-                    const ull only_j = ctx->samples[j].local.nb_kmers - nb_shared[ji];
+                    const ull only_i = (ctx->reduced ? ctx->global_totals[i].nb_kmers : ctx->samples[i].local.nb_kmers) - nb_shared[ij];
+                    const ull only_j = (ctx->reduced ? ctx->global_totals[j].nb_kmers : ctx->samples[j].local.nb_kmers) - nb_shared[ji];
                     if (only_i) v += (Nj > 0) ? ln2 * ((double)only_i / Ni) : onesided_kl_term(1.0, Ni, Nj);
                     if (only_j) v += (Ni > 0) ? ln2 * ((double)only_j / Nj) : onesided_kl_term(1.0, Nj, Ni);
                     out->kullback_leibler[ij] = v;
@@ -1192,9 +1224,11 @@ int simka_gpu_get_timings(simka_ctx *ctx, simka_timings *out) {
     t.exact_retries = ctx->exact_retries;
     t.superk_samples = ctx->superk_samples;
     t.superk_fallbacks = ctx->superk_fallbacks;
-    if (ctx->merged && ctx->a_scalars) {
+    const simka_ctx *mc = (ctx->mctx && ctx->mctx->merged) ? ctx->mctx : ctx;  // after simka_gpu_exchange_and_merge: stage 2 ran in the merge context
+    if (mc != ctx) { t.merge_ms = mc->merge_ms; t.total_ms = ctx->sample_ms + mc->merge_ms; t.kernel_launches += mc->launches; }
+    if (mc->merged && mc->a_scalars) {
         ull sc[4];
-        if (cudaMemcpy(sc, ctx->a_scalars, 32, cudaMemcpyDeviceToHost) == cudaSuccess) { t.distinct_kmers = sc[0]; t.pairs = sc[2]; }
+        if (cudaMemcpy(sc, mc->a_scalars, 32, cudaMemcpyDeviceToHost) == cudaSuccess) { t.distinct_kmers = sc[0]; t.pairs = sc[2]; }
     }
     *out = t;
     return SIMKA_OK;
@@ -1456,6 +1490,306 @@ int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32
         braycurtis[p] = km == 0 ? 1.0f : (float)(1 - (long double)(2 * sk) / (long double)km);
     }
     return rc;
+}
+
+// =============================================================================================
+// multi-GPU: NCCL (loaded at run time) -- totals all-reduce, list exchange, merge, accumulator all-reduce
+// =============================================================================================
+}  // extern "C" (helpers below have C++ linkage)
+
+namespace {
+
+#if SIMKA_HAVE_NCCL_H
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi &nccl() {
+    static NcclApi a = [] {
+        NcclApi n;
+        // an already loaded libnccl.so.2 (e.g. PyTorch's) is found first; else the system one
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) { n.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (n.h) break; }
+        if (!n.h) return n;
+        auto sym = [&](const char *s) { return dlsym(n.h, s); };
+        n.GetUniqueId = (decltype(n.GetUniqueId))sym("ncclGetUniqueId");
+        n.CommInitRank = (decltype(n.CommInitRank))sym("ncclCommInitRank");
+        n.CommDestroy = (decltype(n.CommDestroy))sym("ncclCommDestroy");
+        n.AllReduce = (decltype(n.AllReduce))sym("ncclAllReduce");
+        n.Send = (decltype(n.Send))sym("ncclSend");
+        n.Recv = (decltype(n.Recv))sym("ncclRecv");
+        n.GroupStart = (decltype(n.GroupStart))sym("ncclGroupStart");
+        n.GroupEnd = (decltype(n.GroupEnd))sym("ncclGroupEnd");
+        n.GetErrorString = (decltype(n.GetErrorString))sym("ncclGetErrorString");
+        n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce && n.Send && n.Recv && n.GroupStart && n.GroupEnd && n.GetErrorString;
+        return n;
+    }();
+    return a;
+}
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) {                                                                   \
+            ctx->set_error(std::string(#call) + ": " + nccl().GetErrorString(r_));                  \
+            return SIMKA_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+#endif
+
+// cnt[(s * world + r)] = entries of sample s that fall into the block of fine ranges rank r merges (u64, for the all-reduce)
+__global__ void k_xchg_counts(const uint32_t *__restrict__ off_table, size_t fgn, const int *__restrict__ sample_ids, int n_mine, int world,
+                              uint32_t per, int parts, ull *__restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mine * world) return;
+    const int s = sample_ids[i / world], r = i % world;
+    const uint32_t *off = off_table + (size_t)s * fgn;
+    cnt[(size_t)s * world + r] = r < parts ? (ull)(off[(size_t)(r + 1) * per] - off[(size_t)r * per]) : 0ull;
+}
+// received offset rows are slices of the owner's table: re-base every row to its first entry
+__global__ void k_xchg_rebase(uint32_t *__restrict__ rows, size_t fgn, int n_rows) {
+    const size_t row = blockIdx.y;
+    if ((int)row >= n_rows) return;
+    uint32_t *p = rows + row * fgn;
+    const uint32_t base = p[0];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < fgn; i += (size_t)gridDim.x * blockDim.x)
+        if (i) p[i] -= base;
+    // p[0] is reset last by the kernel below (another block may still read it as the base)
+}
+__global__ void k_xchg_zero_first(uint32_t *__restrict__ rows, size_t fgn, int n_rows) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < n_rows) rows[(size_t)row * fgn] = 0;
+}
+
+}  // namespace
+
+static void comm_release(simka_ctx *ctx) {
+#if SIMKA_HAVE_NCCL_H
+    if (ctx->comm && nccl().ok) nccl().CommDestroy((ncclComm_t)ctx->comm);
+#endif
+    ctx->comm = nullptr;
+}
+
+extern "C" {
+
+int simka_comm_unique_id(uint8_t id[SIMKA_COMM_ID_BYTES]) {
+#if SIMKA_HAVE_NCCL_H
+    static_assert(sizeof(ncclUniqueId) <= SIMKA_COMM_ID_BYTES, "ncclUniqueId grew");
+    if (!id || !nccl().ok) return SIMKA_ERR_INVALID;
+    ncclUniqueId u;
+    if (nccl().GetUniqueId(&u) != ncclSuccess) return SIMKA_ERR_CUDA;
+    memset(id, 0, SIMKA_COMM_ID_BYTES);
+    memcpy(id, &u, sizeof u);
+    return SIMKA_OK;
+#else
+    (void)id;
+    return SIMKA_ERR_INVALID;
+#endif
+}
+
+int simka_gpu_comm_init(simka_ctx *ctx, const uint8_t id[SIMKA_COMM_ID_BYTES], int rank, int world) {
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return SIMKA_ERR_INVALID;
+#if SIMKA_HAVE_NCCL_H
+    if (!nccl().ok) { ctx->set_error("libnccl.so.2 could not be loaded"); return SIMKA_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->prm.device));
+    comm_release(ctx);
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    ncclComm_t c = nullptr;
+    NK(nccl().CommInitRank(&c, world, u, rank));
+    ctx->comm = c;
+    ctx->comm_rank = rank;
+    ctx->comm_world = world;
+    for (auto &e : ctx->xev) if (!e) CK(cudaEventCreate(&e));
+    return SIMKA_OK;
+#else
+    ctx->set_error("built without nccl.h");
+    return SIMKA_ERR_INVALID;
+#endif
+}
+
+int simka_gpu_exchange_timings(simka_ctx *ctx, float ms[4]) {
+    if (!ctx || !ms) return SIMKA_ERR_INVALID;
+    for (int i = 0; i < 4; i++) ms[i] = ctx->xms[i];
+    return SIMKA_OK;
+}
+
+int simka_gpu_exchange_and_merge(simka_ctx *ctx) try {
+    if (!ctx) return SIMKA_ERR_INVALID;
+#if SIMKA_HAVE_NCCL_H
+    if (!ctx->comm) { ctx->set_error("simka_gpu_comm_init has not run"); return SIMKA_ERR_INVALID; }
+    if (ctx->kp.shard_count > 1 || ctx->kp.key_mode) { ctx->set_error("exchange needs an unsharded counting context"); return SIMKA_ERR_INVALID; }
+    const int N = ctx->prm.nb_samples, world = ctx->comm_world, rank = ctx->comm_rank;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    CK(cudaSetDevice(ctx->prm.device));
+    cudaStream_t st = ctx->stream;
+    std::vector<int> mine;
+    for (int s = rank; s < N; s += world) mine.push_back(s);
+    for (int s : mine) if (!ctx->samples[s].done) { ctx->set_error("a sample of this rank is not finished"); return SIMKA_ERR_INVALID; }
+    // ---- 1. one all-reduce: per-sample totals | entries per (sample, destination) | fine-range geometry check
+    const int fb = mine.empty() ? -1 : ctx->fg_bits;
+    int parts = 1;
+    while (fb >= 0 && parts * 2 <= world && parts * 2 <= (1 << fb)) parts *= 2;
+    int lb = fb;
+    for (int p = parts; p > 1; p >>= 1) lb--;
+    const uint32_t per = fb >= 0 ? 1u << lb : 1u;
+    const size_t n_hdr = (size_t)N * 4 + (size_t)N * world + 3;
+    std::vector<ull> hdr(n_hdr, 0);
+    for (int s : mine) {
+        const simka_sample_totals &t = ctx->samples[s].local;
+        hdr[(size_t)s * 4] = t.nb_reads; hdr[(size_t)s * 4 + 1] = t.nb_distinct; hdr[(size_t)s * 4 + 2] = t.nb_kmers; hdr[(size_t)s * 4 + 3] = t.chord_n2;
+    }
+    if (fb >= 0) { hdr[n_hdr - 3] = (ull)fb; hdr[n_hdr - 2] = 1; hdr[n_hdr - 1] = (ull)fb * fb; }
+    if (ctx->d_xhdr.reserve(n_hdr * 8 + (mine.size() + 1) * 4)) { ctx->set_error("out of device memory"); return SIMKA_ERR_NOMEM; }
+    ull *d_hdr = ctx->d_xhdr.as<ull>();
+    int *d_ids = reinterpret_cast<int *>(d_hdr + n_hdr);
+    CK(cudaEventRecord(ctx->xev[0], st));
+    CK(cudaMemcpyAsync(d_hdr, hdr.data(), n_hdr * 8, cudaMemcpyHostToDevice, st));
+    if (!mine.empty()) {
+        CK(cudaMemcpyAsync(d_ids, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice, st));
+        const int n_thr = (int)mine.size() * world;
+        k_xchg_counts<<<(n_thr + 255) / 256, 256, 0, st>>>(ctx->d_off_table.as<uint32_t>(), ((size_t)1 << fb) + 1, d_ids, (int)mine.size(), world, per, parts,
+                                                         d_hdr + (size_t)N * 4);
+        ctx->launches++;
+    }
+    NK(nccl().AllReduce(d_hdr, d_hdr, n_hdr, ncclUint64, ncclSum, comm, st));
+    CK(cudaMemcpyAsync(hdr.data(), d_hdr, n_hdr * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->xev[1], st));
+    CK(cudaStreamSynchronize(st));
+    if (hdr[n_hdr - 2] == 0) { ctx->set_error("no rank counted a sample"); return SIMKA_ERR_INVALID; }
+    if (hdr[n_hdr - 2] * hdr[n_hdr - 1] != hdr[n_hdr - 3] * hdr[n_hdr - 3]) {
+        ctx->set_error("ranks disagree on the fine-range geometry: pass the same expected_kmers_per_sample to every rank");
+        return SIMKA_ERR_INVALID;
+    }
+    const int fine_bits = (int)(hdr[n_hdr - 3] / hdr[n_hdr - 2]);
+    if (fb < 0) {  // a rank without samples: the geometry of the others
+        parts = 1;
+        while (parts * 2 <= world && parts * 2 <= (1 << fine_bits)) parts *= 2;
+        lb = fine_bits;
+        for (int p = parts; p > 1; p >>= 1) lb--;
+    }
+    const size_t fgn = ((size_t)1 << lb) + 1;
+    const ull *cnt = hdr.data() + (size_t)N * 4;  // [s * world + r]
+    std::vector<simka_sample_totals> g_tot(N);
+    for (int s = 0; s < N; s++) g_tot[s] = simka_sample_totals{hdr[(size_t)s * 4], hdr[(size_t)s * 4 + 1], hdr[(size_t)s * 4 + 2], hdr[(size_t)s * 4 + 3]};
+    // ---- 2. merge context + receive buffers (its arena keeps them across runs)
+    if (!ctx->mctx) {
+        simka_params mp = ctx->prm;
+        mp.shard_rank = 0; mp.shard_count = 1; mp.expected_kmers_per_sample = 0;
+        const int rc = simka_gpu_create(&ctx->mctx, &mp);
+        if (rc != SIMKA_OK) { ctx->set_error("could not create the merge context"); return rc; }
+    } else {
+        const int rc = simka_gpu_reset(ctx->mctx);
+        if (rc != SIMKA_OK) { ctx->set_error(ctx->mctx->err); return rc; }
+    }
+    simka_ctx *m = ctx->mctx;
+    uint64_t total_recv = 0;
+    for (int s = 0; s < N; s++) total_recv += cnt[(size_t)s * world + rank];
+    uint64_t *recv_e = (uint64_t *)m->arena.alloc(std::max<uint64_t>(total_recv, 1) * 8);
+    uint32_t *recv_c = (uint32_t *)m->arena.alloc(std::max<uint64_t>(total_recv, 1) * 4);
+    uint32_t *recv_o = (uint32_t *)m->arena.alloc((size_t)N * fgn * 4);
+    if (!recv_e || !recv_c || !recv_o) { ctx->set_error("out of device memory (exchange buffers)"); return SIMKA_ERR_NOMEM; }
+    if (rank >= parts) CK(cudaMemsetAsync(recv_o, 0, (size_t)N * fgn * 4, st));  // this rank merges nothing: empty lists
+    // ---- 3. the exchange: every slice straight from the list it was counted into (no staging copy), one NCCL group
+    NK(nccl().GroupStart());
+    for (int r = 0; r < parts; r++) {  // sends (and the local copies) of my samples, destination-major
+        for (int s : mine) {
+            const SampleData &sd = ctx->samples[s];
+            uint64_t a = 0;
+            for (int q = 0; q < r; q++) a += cnt[(size_t)s * world + q];
+            const uint64_t n = cnt[(size_t)s * world + r];
+            const uint32_t *off_src = ctx->d_off_table.as<uint32_t>() + (size_t)s * (((size_t)1 << fine_bits) + 1) + (size_t)r * per;
+            if (r == rank) continue;  // local slice: copied below, outside the group
+            if (n) {
+                NK(nccl().Send(sd.eh + a, n, ncclUint64, r, comm, st));
+                NK(nccl().Send(sd.ec + a, n, ncclUint32, r, comm, st));
+            }
+            NK(nccl().Send(off_src, fgn, ncclUint32, r, comm, st));
+        }
+    }
+    std::vector<uint64_t> pos(N, 0);  // start of sample s inside recv_e / recv_c (sample-major)
+    { uint64_t p = 0; for (int s = 0; s < N; s++) { pos[s] = p; p += cnt[(size_t)s * world + rank]; } }
+    if (rank < parts) {
+        for (int o = 0; o < world; o++) {
+            if (o == rank) continue;
+            for (int s = o; s < N; s += world) {
+                const uint64_t n = cnt[(size_t)s * world + rank];
+                if (n) {
+                    NK(nccl().Recv(recv_e + pos[s], n, ncclUint64, o, comm, st));
+                    NK(nccl().Recv(recv_c + pos[s], n, ncclUint32, o, comm, st));
+                }
+                NK(nccl().Recv(recv_o + (size_t)s * fgn, fgn, ncclUint32, o, comm, st));
+            }
+        }
+    }
+    NK(nccl().GroupEnd());
+    if (rank < parts) {
+        for (int s : mine) {
+            const SampleData &sd = ctx->samples[s];
+            uint64_t a = 0;
+            for (int q = 0; q < rank; q++) a += cnt[(size_t)s * world + q];
+            const uint64_t n = cnt[(size_t)s * world + rank];
+            if (n) {
+                CK(cudaMemcpyAsync(recv_e + pos[s], sd.eh + a, n * 8, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(recv_c + pos[s], sd.ec + a, n * 4, cudaMemcpyDeviceToDevice, st));
+            }
+            CK(cudaMemcpyAsync(recv_o + (size_t)s * fgn, ctx->d_off_table.as<uint32_t>() + (size_t)s * (((size_t)1 << fine_bits) + 1) + (size_t)rank * per, fgn * 4,
+                               cudaMemcpyDeviceToDevice, st));
+        }
+        k_xchg_rebase<<<dim3((unsigned)std::min<size_t>((fgn + 255) / 256, 64), (unsigned)N), 256, 0, st>>>(recv_o, fgn, N);
+        k_xchg_zero_first<<<(N + 255) / 256, 256, 0, st>>>(recv_o, fgn, N);
+        ctx->launches += 2;
+    }
+    CK(cudaEventRecord(ctx->xev[2], st));
+    CK(cudaStreamWaitEvent(m->stream, ctx->xev[2], 0));
+    // ---- 4. stage 2 on my block of hash ranges over all samples
+    for (int s = 0; s < N; s++) {
+        const int rc = simka_gpu_import_sample(m, s, recv_e + pos[s], recv_c + pos[s], rank < parts ? cnt[(size_t)s * world + rank] : 0, recv_o + (size_t)s * fgn, lb,
+                                               g_tot[s].nb_reads);
+        if (rc != SIMKA_OK) { ctx->set_error("import: " + m->err); return rc; }
+    }
+    simka_gpu_set_totals(m, g_tot.data());
+    {
+        const int rc = simka_gpu_merge_and_accumulate(m);
+        if (rc != SIMKA_OK) { ctx->set_error("merge: " + m->err); return rc; }
+    }
+    // ---- 5. sum of the accumulators over the ranks: u64 block | f64 block | fixed-point block
+    {
+        const size_t nn = (size_t)N * N, ns = (size_t)N * (N + 1) / 2;
+        const size_t n_u64 = nn + ns + ns + nn + nn + nn + nn + 4;  // up to and including the scalars
+        ull *acc = m->d_acc.as<ull>();
+        CK(cudaEventRecord(ctx->xev[3], m->stream));
+        NK(nccl().GroupStart());
+        NK(nccl().AllReduce(acc, acc, n_u64, ncclUint64, ncclSum, comm, m->stream));
+        NK(nccl().AllReduce(m->a_kl, m->a_kl, nn, ncclFloat64, ncclSum, comm, m->stream));
+        NK(nccl().AllReduce(m->a_klfix, m->a_klfix, nn, ncclUint64, ncclSum, comm, m->stream));
+        NK(nccl().GroupEnd());
+        CK(cudaEventRecord(ctx->xev[4], m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+    }
+    m->reduced = true;
+    ctx->global_totals = g_tot;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->xev[0], ctx->xev[1]) == cudaSuccess) ctx->xms[0] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->xev[1], ctx->xev[2]) == cudaSuccess) ctx->xms[1] = ms;
+    ctx->xms[2] = m->merge_ms;
+    if (cudaEventElapsedTime(&ms, ctx->xev[3], ctx->xev[4]) == cudaSuccess) ctx->xms[3] = ms;
+    return SIMKA_OK;
+#else
+    ctx->set_error("built without nccl.h");
+    return SIMKA_ERR_INVALID;
+#endif
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    if (ctx) ctx->set_error("out of host memory");
+    return SIMKA_ERR_NOMEM;
 }
 
 }  // extern "C"

@@ -198,3 +198,24 @@ def exchange_and_merge(count_ctx, merge_ctx, nb_samples: int, rank: int, world: 
         print("[exchange_and_merge ms] " + " ".join(f"{n}={1e3 * (t - marks[i][1]):.2f}" for i, (n, t) in enumerate(marks[1:])), flush=True)
     st.totals[:] = g_tot
     return st
+
+
+# ------------------------------------------------------------------------------------------------
+# The same, inside the library: simka_gpu_exchange_and_merge (csrc/simka_gpu.cu) does the totals all-reduce, the list
+# exchange (ncclSend / ncclRecv straight from the per-sample lists), the merge and the accumulator all-reduce in C++ on its
+# own NCCL communicator.  torch.distributed only carries the 128-byte NCCL unique id to the ranks, once per context.
+# ------------------------------------------------------------------------------------------------
+def native_comm_init(ctx, rank: int, world: int, device):
+    """creates the library's NCCL communicator for this context (collective: every rank calls it)"""
+    from .api import comm_unique_id
+    ident = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        ident = torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8).to(device)
+    dist.broadcast(ident, src=0)
+    ctx.comm_init(bytes(ident.cpu().numpy().tobytes()), rank, world)
+
+
+def exchange_and_merge_native(ctx):
+    """-> the GLOBAL SimkaStatistics (already summed over the ranks) after simka_gpu_exchange_and_merge"""
+    ctx.exchange_and_merge()
+    return ctx.stats()

@@ -119,7 +119,7 @@ def build(force: bool = False, asan: bool = False) -> Path:
             dst = dst.with_name(dst.stem + "_emu.cpp")
         dst.write_text(text)
     assert launches >= 30, f"only {launches} kernel launches rewritten"
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{HERE}", "-DSIMKA_CUDA_EMU=1",
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", f"-I{HERE}", "-DSIMKA_CUDA_EMU=1", "-DSIMKA_NO_NCCL=1",
            *(["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []),
            "-o", str(lib), str(gen / "simka_gpu_emu.cpp"), str(CSRC / "simka_host.cpp"), "-lz", "-lpthread"]
     subprocess.run(cmd, check=True)

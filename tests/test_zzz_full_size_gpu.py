@@ -51,3 +51,17 @@ def test_config4_shape_512_samples_equal_the_oracle():
     st, run, _ = _run_both(512, 20_000, 21, 256 * 16)
     assert_stats_equal(st, run, kl_rtol=1e-10)
     run.close()
+
+
+def test_merge_sub_pass_split_when_everybody_shares_the_same_kmers(monkeypatch):
+    """600 samples holding the same k-mers, lists not regrouped (one big merge bin): the hash-selected sub-passes of k_merge
+    hold whole groups of 600 entries, some of them more than fit -> those sub-passes are split in two before anything is
+    accumulated (merge.cuh).  Against the oracle."""
+    from helpers import oracle_run
+    monkeypatch.setenv("SIMKA_B200_REFINE", "0")
+    rng = np.random.default_rng(11)
+    read = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 150)]
+    one = (read.copy(), np.array([0, 150], np.uint64))
+    samples = [one] * 600
+    st = simka_b200.run_samples(samples, 31, abundance_min=1, simple_dist=True, complex_dist=True)
+    assert_stats_equal(st, oracle_run(samples, 31, 1))
