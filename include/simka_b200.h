@@ -35,7 +35,7 @@ typedef struct simka_ctx simka_ctx;
  * -kmer-size, -nb-datasets, -abundance-min/-max, -simple-dist, -complex-dist. */
 typedef struct {
     int32_t kmer_size;        /* 2..31 (span-32 k-mers, GC/kmer/impl/Model.hpp:100)                 */
-    int32_t nb_samples;       /* N, 1..65535                                                       */
+    int32_t nb_samples;       /* N, 1..8192                                                        */
     int64_t abundance_min;    /* keep a k-mer of a sample iff min <= count <= max                  */
     int64_t abundance_max;    /*   (src/minikc/MiniKC.hpp:56)                                       */
     int32_t simple_dist;      /* chord / hellinger / kulczynski accumulators                       */

@@ -13,6 +13,7 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -61,6 +62,18 @@ inline std::string part_file(const std::string &dir, size_t p, size_t bank) {
     return dir + "/solid/part_" + std::to_string(p) + "/__p__" + std::to_string(bank) + ".gz";
 }
 
+// gzwrite takes an `unsigned` length and reports errors by returning 0: write in chunks of at most 1 GiB, check every call
+// (a truncated stats/part_P.gz followed by its merge_synchro token would be read as a complete result)
+inline void gz_write_all(gzFile f, const void *data, size_t bytes, const std::string &path) {
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    while (bytes) {
+        const unsigned chunk = (unsigned)std::min<size_t>(bytes, (size_t)1 << 30);
+        if (gzwrite(f, p, chunk) != (int)chunk) { gzclose(f); throw bank::Exception("write error on " + path); }
+        p += chunk;
+        bytes -= chunk;
+    }
+}
+
 inline void write_solid_part(const std::string &path, uint32_t bank, const uint64_t *kmers, const uint32_t *counts, size_t n) {
     gzFile f = gzopen(path.c_str(), "wb1");
     if (!f) throw bank::Exception("cannot write " + path);
@@ -70,9 +83,9 @@ inline void write_solid_part(const std::string &path, uint32_t bank, const uint6
         Record r;
         r.kmer = kmers[i]; r.bank = bank; r.pad = 0; r.count = counts[i];
         buf.push_back(r);
-        if (buf.size() == 10000 || i + 1 == n) { gzwrite(f, buf.data(), (unsigned)(buf.size() * sizeof(Record))); buf.clear(); }
+        if (buf.size() == 10000 || i + 1 == n) { gz_write_all(f, buf.data(), buf.size() * sizeof(Record), path); buf.clear(); }
     }
-    gzclose(f);
+    if (gzclose(f) != Z_OK) throw bank::Exception("error closing " + path);
 }
 
 inline void read_solid_part(const std::string &path, std::vector<uint64_t> &kmers, std::vector<uint32_t> &counts) {
@@ -160,8 +173,8 @@ inline void write_stats(const std::string &path, const simka_stats_view &v) {
     for (size_t i = 0; i < s.size(); i++) memcpy(&raw[i * 16], &s[i], 10);
     gzFile f = gzopen(path.c_str(), "wb1");
     if (!f) throw bank::Exception("cannot write " + path);
-    gzwrite(f, raw.data(), (unsigned)raw.size());
-    gzclose(f);
+    gz_write_all(f, raw.data(), raw.size(), path);
+    if (gzclose(f) != Z_OK) throw bank::Exception("error closing " + path);
 }
 
 // "-flag value" / "-flag" command lines of the stage binaries

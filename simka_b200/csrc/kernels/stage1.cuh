@@ -602,6 +602,8 @@ k_compact(const uint64_t *__restrict__ stage_h, const uint32_t *__restrict__ sta
 
 // per-sample abundance histogram of the solid k-mers (complex distances only): chist[c] for c < CHIST,
 // larger counts go to the (count, sample) overflow list
+// big_n counts every large abundance, also those beyond big_cap: the merge then grows the list and rebuilds it from the
+// resident lists (chist == nullptr: only the list is filled, the dense histogram is already complete).
 __global__ void __launch_bounds__(BLOCK)
 k_abundance_hist(const uint32_t *__restrict__ ec, uint64_t n, int sample, ull *__restrict__ chist, uint32_t *__restrict__ big_counts,
                  uint32_t *__restrict__ big_sample, uint32_t *__restrict__ big_n, uint32_t big_cap, int *__restrict__ error_flag) {
@@ -610,15 +612,15 @@ k_abundance_hist(const uint32_t *__restrict__ ec, uint64_t n, int sample, ull *_
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * BLOCK) {
         const uint32_t c = ec[i];
-        if (c < CHIST) atomicAdd(&hist[c], 1u);
+        if (c < CHIST) { if (chist) atomicAdd(&hist[c], 1u); }
         else {
             const uint32_t q = atomicAdd(big_n, 1u);
             if (q < big_cap) { big_counts[q] = c; big_sample[q] = (uint32_t)sample; }
-            else *error_flag = 2;
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < CHIST; i += BLOCK) { const uint32_t c = hist[i]; if (c) atomicAdd(&chist[i], (ull)c); }
+    if (chist)
+        for (int i = threadIdx.x; i < CHIST; i += BLOCK) { const uint32_t c = hist[i]; if (c) atomicAdd(&chist[i], (ull)c); }
 }
 
 // sum of a u32 array (solid abundances of an imported sample range)

@@ -1061,6 +1061,23 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
     uint32_t big_n = 0;
     if (ctx->prm.complex_dist) CK(cudaMemcpyAsync(&big_n, d_big_n, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));  // host staging vectors are reused below / big_n needed
+    if (ctx->prm.complex_dist && big_n > ctx->big_cap) {
+        // more solid k-mers with an abundance >= CHIST than the list holds (deep or many samples): grow it and rebuild it from
+        // the resident lists (the dense part of the histograms is complete)
+        const uint32_t want = big_n + big_n / 4 + 1024;
+        if (ctx->d_big_counts.reserve((size_t)want * 4) || ctx->d_big_sample.reserve((size_t)want * 4)) { ctx->set_error("out of device memory (abundance list)"); return SIMKA_ERR_NOMEM; }
+        ctx->big_cap = want;
+        CK(cudaMemsetAsync(d_big_n, 0, 4, st));
+        for (int s = 0; s < N; s++) {
+            const SampleData &sd = ctx->samples[s];
+            if (!sd.n) continue;
+            const unsigned g = (unsigned)std::min<uint64_t>((sd.n + BLOCK * 16 - 1) / (BLOCK * 16), (uint64_t)ctx->nsm * 4);
+            k_abundance_hist<<<g, BLOCK, 0, st>>>(sd.ec, sd.n, s, nullptr, ctx->d_big_counts.as<uint32_t>(), ctx->d_big_sample.as<uint32_t>(), d_big_n, ctx->big_cap, d_error);
+            ctx->launches++;
+        }
+        CK(cudaMemcpyAsync(&big_n, d_big_n, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     if (ctx->fg_bits >= 0 && total_entries > 0) {
         int mg_bits = std::min(fg_eff, want_bits);
         MergeArgs a;

@@ -237,6 +237,7 @@ int run(int argc, char **argv) {
         for (const SampleSpec &s : samples) {
             uint64_t n = read_sample(s, SimkaSequenceFilter(), 0, [](const char *, size_t) {});
             if (o.dataInfo || o.verbose) printf("\t%s: %llu reads\n", s.id.c_str(), (unsigned long long)n);
+            n /= std::max<size_t>(1, s.groups.size());  // the limit applies per paired group (src/core/SimkaAlgorithm.cpp:405, nbReads /= _nbBankPerDataset[i])
             mn = std::min(mn, n);
             sum += n;
         }

@@ -142,11 +142,11 @@ def exchange_and_merge(count_ctx, merge_ctx, nb_samples: int, rank: int, world: 
     offs = []
     for s in mine:
         pk, pc, po, n = count_ctx.export_sample(s)
-        off = _dev_tensor(po, (1 << fine_bits) + 1, "<i4", device)
+        off = _dev_tensor(po, (1 << fine_bits) + 1, "<i4", device)  # (uint32 offsets viewed as int32: masked back below)
         offs.append(off[:: per][: parts + 1])
         exports[s] = [pk, pc, off, n, None]
     if mine:  # one device->host copy for the split points of all my samples
-        all_cuts = torch.stack(offs).to(torch.int64).cpu().numpy()
+        all_cuts = (torch.stack(offs).to(torch.int64) & 0xFFFFFFFF).cpu().numpy()  # a sample may hold >= 2^31 solid k-mers
         for i, s in enumerate(mine):
             exports[s][4] = all_cuts[i]
             cnt[s, :parts] = np.diff(all_cuts[i])
