@@ -1439,12 +1439,14 @@ int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *co
     std::vector<ull> hq;
     try { hq.resize(4 * pairs); } catch (const std::bad_alloc &) { return SIMKA_ERR_NOMEM; }  // nothing may throw across the C ABI
     do {
-        if (cudaMalloc(&dh, ne * 8) || cudaMalloc(&dc, ne * 4) || cudaMalloc(&dstart, (size_t)n * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
+        // (+64: the bulk copies of the distance kernel round their ranges outwards to 16 bytes)
+        if (cudaMalloc(&dh, ne * 8 + 64) || cudaMalloc(&dc, ne * 4 + 64) || cudaMalloc(&dstart, (size_t)n * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
+        if (cudaFuncSetAttribute(k_simkamin_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmtSmem)) != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
         if (cudaMemcpy(dh, hashes, ne * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc, counts, ne * 4, cudaMemcpyHostToDevice)) { rc = SIMKA_ERR_CUDA; break; }
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0);
         k_sketch_starts<<<(n + 255) / 256, 256>>>(dh, n, s, dstart);
-        if (pairs) k_simkamin_tiled<false><<<(unsigned)pairs, BLOCK>>>(dh, dc, dstart, n, nullptr, nullptr, nullptr, 0, s, dq);
+        if (pairs) k_simkamin_tiled<false><<<(unsigned)pairs, BLOCK, sizeof(SmtSmem)>>>(dh, dc, dstart, n, nullptr, nullptr, nullptr, 0, s, dq);
         cudaEventRecord(e1);
         if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
         if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
@@ -1483,7 +1485,8 @@ int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32
     std::vector<ull> hq;
     try { hq.resize(4 * pairs); } catch (const std::bad_alloc &) { return SIMKA_ERR_NOMEM; }
     do {
-        if (cudaMalloc(&dh1, e1 * 8) || cudaMalloc(&dc1, e1 * 4) || cudaMalloc(&ds1, (size_t)n1 * 4) || cudaMalloc(&dh2, e2 * 8) || cudaMalloc(&dc2, e2 * 4) ||
+        if (cudaFuncSetAttribute(k_simkamin_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmtSmem)) != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
+        if (cudaMalloc(&dh1, e1 * 8 + 64) || cudaMalloc(&dc1, e1 * 4 + 64) || cudaMalloc(&ds1, (size_t)n1 * 4) || cudaMalloc(&dh2, e2 * 8 + 64) || cudaMalloc(&dc2, e2 * 4 + 64) ||
             cudaMalloc(&ds2, (size_t)n2 * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
         if (cudaMemcpy(dh1, hashes1, e1 * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc1, counts1, e1 * 4, cudaMemcpyHostToDevice) ||
             cudaMemcpy(dh2, hashes2, e2 * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc2, counts2, e2 * 4, cudaMemcpyHostToDevice)) { rc = SIMKA_ERR_CUDA; break; }
@@ -1491,7 +1494,7 @@ int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32
         cudaEventRecord(ev0);
         k_sketch_starts<<<(n1 + 255) / 256, 256>>>(dh1, n1, s, ds1);
         k_sketch_starts<<<(n2 + 255) / 256, 256>>>(dh2, n2, s, ds2);
-        k_simkamin_tiled<true><<<(unsigned)pairs, BLOCK>>>(dh1, dc1, ds1, n1, dh2, dc2, ds2, n2, s, dq);
+        k_simkamin_tiled<true><<<(unsigned)pairs, BLOCK, sizeof(SmtSmem)>>>(dh1, dc1, ds1, n1, dh2, dc2, ds2, n2, s, dq);
         cudaEventRecord(ev1);
         if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
         if (kernel_ms) cudaEventElapsedTime(kernel_ms, ev0, ev1);
