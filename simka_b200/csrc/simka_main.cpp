@@ -39,7 +39,7 @@ struct Options {
     long long maxReads = -1;
     size_t minReadSize = 0;
     double minShannon = 0;
-    int nbCores = 0, verbose = 1, device = 0;
+    int nbCores = 0, verbose = 1, device = 0, nbGpus = 1;
     long long maxMemory = 5000;
 };
 
@@ -73,7 +73,9 @@ void usage() {
            "   [core options]\n"
            "       -nb-cores           (1 arg) :    number of host threads for parsing / packing  [default '0' = all]\n"
            "       -max-memory         (1 arg) :    max memory (MB); accepted for compatibility  [default '5000']\n"
-           "       -device             (1 arg) :    CUDA device ordinal  [default '0']\n"
+           "       -device             (1 arg) :    CUDA device ordinal (the first one with -nb-gpus)  [default '0']\n"
+           "       -nb-gpus            (1 arg) :    GPUs to use: sample i is counted on GPU (i mod nb-gpus), every GPU merges its block of hash ranges,\n"
+           "                                        lists and accumulators cross NVLink through NCCL  [default '1']\n"
            "   [cluster options] -max-count -max-merge -count-cmd -merge-cmd -count-file -merge-file : accepted and ignored\n"
            "       -verbose            (1 arg) :    verbosity level  [default '1']\n\n");
 }
@@ -112,6 +114,7 @@ Options parse_args(int argc, char **argv) {
     if (kv.count("-max-memory")) o.maxMemory = atoll(kv["-max-memory"].c_str());
     if (kv.count("-verbose")) o.verbose = atoi(kv["-verbose"].c_str());
     if (kv.count("-device")) o.device = atoi(kv["-device"].c_str());
+    if (kv.count("-nb-gpus")) o.nbGpus = std::max(1, atoi(kv["-nb-gpus"].c_str()));
     // src/SimkaPotara.hpp:383-387
     if (o.maxMemory < 500) throw bank::Exception("Please allocate more memory (minimum is 500 MB) with the option -max-memory");
     o.minShannon = std::max(o.minShannon, 0.0);
@@ -342,29 +345,50 @@ int run(int argc, char **argv) {
     prm.simple_dist = o.simple;
     prm.complex_dist = o.complex_;
     prm.device = o.device;
-    simka_ctx *ctx = nullptr;
-    int rc = simka_gpu_create(&ctx, &prm);
+    // one context per GPU; with -nb-gpus G > 1 sample i belongs to GPU i % G, one host thread drives each GPU
+    const size_t G = std::min<size_t>((size_t)o.nbGpus, N);
+    std::vector<simka_ctx *> ctxs(G, nullptr);
+    int rc = SIMKA_OK;
+    for (size_t g = 0; g < G && rc == SIMKA_OK; g++) {
+        simka_params pg = prm;
+        pg.device = o.device + (int)g;
+        rc = simka_gpu_create(&ctxs[g], &pg);
+    }
+    simka_ctx *ctx = ctxs[0];
     const double t_create = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (rc != SIMKA_OK) { { std::lock_guard<std::mutex> lk(mu); next_sample = N; } cv.notify_all(); for (auto &t : pool_threads) t.join(); throw bank::Exception("simka_gpu_create failed (code " + std::to_string(rc) + "): a CUDA device is required, there is no CPU path"); }
+    if (rc != SIMKA_OK) { { std::lock_guard<std::mutex> lk(mu); next_sample = N; } cv.notify_all(); for (auto &t : pool_threads) t.join(); for (simka_ctx *c : ctxs) simka_gpu_destroy(c); throw bank::Exception("simka_gpu_create failed (code " + std::to_string(rc) + "): " + std::to_string(G) + " CUDA device(s) are required, there is no CPU path"); }
+    if (G > 1) {
+        uint8_t id[SIMKA_COMM_ID_BYTES];
+        if (simka_comm_unique_id(id) != SIMKA_OK) throw bank::Exception("-nb-gpus: NCCL (libnccl.so.2) is not available");
+        std::vector<std::thread> th;
+        std::vector<int> rcs(G, SIMKA_OK);
+        for (size_t g = 0; g < G; g++) th.emplace_back([&, g] { rcs[g] = simka_gpu_comm_init(ctxs[g], id, (int)g, (int)G); });  // (collective: all ranks at once)
+        for (auto &t : th) t.join();
+        for (size_t g = 0; g < G; g++) if (rcs[g] != SIMKA_OK) throw bank::Exception(std::string("simka_gpu_comm_init: ") + simka_gpu_last_error(ctxs[g]));
+    }
 
     gpu_ready.store(true);
 
     std::vector<simka_sample_totals> totals(N);
     std::string failure;
-    auto finish = [&](size_t i) {  // counts sample i (already pushed), recycles its pinned chunks, writes its .ok file
+    std::mutex fail_mu;
+    auto failed = [&] { std::lock_guard<std::mutex> lk(fail_mu); return !failure.empty(); };
+    auto fail = [&](const std::string &m) { std::lock_guard<std::mutex> lk(fail_mu); if (failure.empty()) failure = m; };
+    size_t consumed_count = 0;  // samples whose chunks went back to the pool (under mu)
+    auto finish = [&](simka_ctx *cx, size_t i) {  // counts sample i (already pushed), recycles its pinned chunks, writes its .ok file
         Parsed &P = parsed[i];
-        if (failure.empty()) {
-            const int rc2 = simka_gpu_finish_sample(ctx, (int)i, &totals[i]);
-            if (rc2 != SIMKA_OK) failure = std::string("simka_gpu_finish_sample: ") + simka_gpu_last_error(ctx) + " (code " + std::to_string(rc2) + ")";
+        if (!failed()) {
+            const int rc2 = simka_gpu_finish_sample(cx, (int)i, &totals[i]);
+            if (rc2 != SIMKA_OK) fail(std::string("simka_gpu_finish_sample: ") + simka_gpu_last_error(cx) + " (code " + std::to_string(rc2) + ")");
         }
         {
             std::lock_guard<std::mutex> lk(mu);
             for (PinnedChunk *c : P.chunks) pool.push_back(c);
             P.chunks.clear();
-            consumed = i + 1;
+            consumed = ++consumed_count;
         }
         cv.notify_all();
-        if (!failure.empty()) return;
+        if (failed()) return;
         totals[i].nb_reads = P.nreads;
         // count_synchro/<id>.ok: nbReads, nbDistinct, sum c, sum c^2 (src/SimkaCount.cpp:355-368)
         char buf[256];
@@ -374,28 +398,48 @@ int run(int argc, char **argv) {
         if (o.verbose) printf("Counting dataset %zu (%s): %llu reads, %llu distinct solid k-mers, %llu solid k-mers\n", i, samples[i].id.c_str(),
                               (unsigned long long)totals[i].nb_reads, (unsigned long long)totals[i].nb_distinct, (unsigned long long)totals[i].nb_kmers);
     };
-    for (size_t i = 0; i < N; i++) {
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return parsed[i].ready; });
+    auto drive = [&](size_t g) {  // the samples of GPU g, in order
+        simka_ctx *cx = ctxs[g];
+        size_t prev = N;
+        for (size_t i = g; i < N; i += G) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return parsed[i].ready; });
+            }
+            Parsed &P = parsed[i];
+            if (!P.error.empty()) fail(P.error);
+            // push sample i (asynchronous copies) BEFORE finishing the previous one: its H2D overlaps those kernels
+            for (size_t c = 0; c < P.chunks.size() && !failed(); c++) {
+                const int rc2 = simka_gpu_push_reads(cx, (int)i, P.chunks[c]->packed, P.chunks[c]->bad, P.words[c], P.reads[c]);
+                if (rc2 != SIMKA_OK) fail(std::string("simka_gpu_push_reads: ") + simka_gpu_last_error(cx) + " (code " + std::to_string(rc2) + ")");
+            }
+            if (prev < N) finish(cx, prev);
+            prev = i;
         }
-        Parsed &P = parsed[i];
-        if (failure.empty() && !P.error.empty()) failure = P.error;
-        // push sample i (asynchronous copies) BEFORE finishing sample i-1: its H2D overlaps the kernels of i-1
-        for (size_t c = 0; c < P.chunks.size() && failure.empty(); c++) {
-            const int rc2 = simka_gpu_push_reads(ctx, (int)i, P.chunks[c]->packed, P.chunks[c]->bad, P.words[c], P.reads[c]);
-            if (rc2 != SIMKA_OK) failure = std::string("simka_gpu_push_reads: ") + simka_gpu_last_error(ctx) + " (code " + std::to_string(rc2) + ")";
-        }
-        if (i > 0) finish(i - 1);
+        if (prev < N) finish(cx, prev);
+    };
+    if (G == 1) drive(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; g++) th.emplace_back(drive, g);
+        for (auto &t : th) t.join();
     }
-    finish(N - 1);
     for (auto &t : pool_threads) t.join();
-    if (!failure.empty()) { simka_gpu_destroy(ctx); throw bank::Exception(failure); }
+    if (!failure.empty()) { for (simka_ctx *c : ctxs) simka_gpu_destroy(c); throw bank::Exception(failure); }
     const double t_stage1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    check(ctx, simka_gpu_set_totals(ctx, totals.data()), "simka_gpu_set_totals");
 
     // stage 2 + final statistics
-    check(ctx, simka_gpu_merge_and_accumulate(ctx), "simka_gpu_merge_and_accumulate");
+    if (G == 1) {
+        check(ctx, simka_gpu_set_totals(ctx, totals.data()), "simka_gpu_set_totals");
+        check(ctx, simka_gpu_merge_and_accumulate(ctx), "simka_gpu_merge_and_accumulate");
+    } else {
+        // totals all-reduce, list exchange, merge of every GPU's block of hash ranges, accumulator all-reduce (NCCL, one thread per GPU)
+        std::vector<std::thread> th;
+        std::vector<int> rcs(G, SIMKA_OK);
+        for (size_t g = 0; g < G; g++) th.emplace_back([&, g] { rcs[g] = simka_gpu_exchange_and_merge(ctxs[g]); });
+        for (auto &t : th) t.join();
+        for (size_t g = 0; g < G; g++) check(ctxs[g], rcs[g], "simka_gpu_exchange_and_merge");
+    }
     const size_t nn = N * N, ns = N * (N + 1) / 2;
     std::vector<uint64_t> u(2 * ns + 6 * nn);
     std::vector<double> kl(nn);
@@ -426,7 +470,7 @@ int run(int argc, char **argv) {
                tm.merge_ms, (unsigned long long)tm.kernel_launches, wall, t_create, t_packed, t_stage1, workers, inflight);
         printf("Output dir: %s\n", o.out.c_str());
     }
-    simka_gpu_destroy(ctx);
+    for (simka_ctx *c : ctxs) simka_gpu_destroy(c);
     for (PinnedChunk *c : pool) { c->release(); delete c; }
     if (!o.keepTmp) rm_rf(tmp);
     return EXIT_SUCCESS;
