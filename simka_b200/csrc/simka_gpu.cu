@@ -192,6 +192,19 @@ struct simka_ctx {
     DevBuf d_xhdr;
     cudaEvent_t xev[5] = {};
     float xms[4] = {0, 0, 0, 0};
+    // the exchange runs in ROUNDS (round t = the samples t * world .. t * world + world - 1, one per rank) on a side stream, so that
+    // the lists of round t cross NVLink while round t + 1 is being counted
+    cudaStream_t xstream = nullptr;
+    struct XRound { int state = 0; cudaEvent_t sizes_ready = nullptr; };  // 0: nothing yet, 1: sizes all-reduce enqueued, 2: data posted
+    std::vector<XRound> xr;
+    ull *xh = nullptr;           // pinned: [rounds][world * world + 3] entries per (owner, destination) + geometry check
+    DevBuf d_xcnt, d_xids;
+    std::vector<uint64_t *> x_recv_e;
+    std::vector<uint32_t *> x_recv_c;
+    std::vector<uint64_t> x_recv_n;
+    uint32_t *x_recv_o = nullptr;
+    int x_parts = 0, x_lb = 0, x_fb = -1;
+    cudaEvent_t x_sample_done = nullptr, x_all_done = nullptr;
     int b1_override = 0;  // SIMKA_B200_B1BITS: level-1 bucket bits (experiments)
     bool k2_minb3 = false;  // SIMKA_B200_K2_MINB=3: scatter pass of K2 compiled for 3 CTAs per SM (no register spill; experiments)
 
@@ -276,6 +289,8 @@ static int reset_state(simka_ctx *ctx) {
     CK(cudaMemsetAsync(ctx->d_small.p, 0, 64, ctx->stream));
     return SIMKA_OK;
 }
+
+static int xchg_after_sample(simka_ctx *ctx, int sample_id);  // multi-GPU: defined with the NCCL code at the end of the file
 
 extern "C" {
 
@@ -364,6 +379,11 @@ int simka_gpu_reset(simka_ctx *ctx) {
     CK(cudaSetDevice(ctx->prm.device));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->xstream) CK(cudaStreamSynchronize(ctx->xstream));
+    for (auto &r : ctx->xr) r.state = 0;
+    ctx->x_fb = -1;
+    ctx->x_recv_o = nullptr;
+    if (ctx->mctx) { const int rc = simka_gpu_reset(ctx->mctx); if (rc != SIMKA_OK) { ctx->set_error(ctx->mctx->err); return rc; } }
     return reset_state(ctx);
 }
 
@@ -375,7 +395,12 @@ void simka_gpu_destroy(simka_ctx *ctx) {
     comm_release(ctx);
     if (ctx->mctx) { simka_gpu_destroy(ctx->mctx); ctx->mctx = nullptr; }
     for (auto &e : ctx->xev) if (e) cudaEventDestroy(e);
-    ctx->d_xhdr.release();
+    ctx->d_xhdr.release(); ctx->d_xcnt.release(); ctx->d_xids.release();
+    for (auto &r : ctx->xr) if (r.sizes_ready) cudaEventDestroy(r.sizes_ready);
+    if (ctx->x_sample_done) cudaEventDestroy(ctx->x_sample_done);
+    if (ctx->x_all_done) cudaEventDestroy(ctx->x_all_done);
+    if (ctx->xh) cudaFreeHost(ctx->xh);
+    if (ctx->xstream) { cudaStreamSynchronize(ctx->xstream); cudaStreamDestroy(ctx->xstream); }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     ctx->arena.release();
@@ -771,6 +796,10 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
     ctx->entries += h_surv;
     if (sl) { sl->sample = -1; sl->words = sl->reads = 0; sl->ext_packed = nullptr; sl->ext_bad = nullptr; }
     if (out) *out = sd.local;
+    if (ctx->comm && ctx->comm_world > 1) {  // multi-GPU: this sample's round starts crossing NVLink while the next one is counted
+        const int rc = xchg_after_sample(ctx, sample_id);
+        if (rc != SIMKA_OK) return rc;
+    }
     return SIMKA_OK;
 } catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
     if (ctx) ctx->set_error("out of host memory");
@@ -1564,14 +1593,11 @@ static NcclApi &nccl() {
     } while (0)
 #endif
 
-// cnt[(s * world + r)] = entries of sample s that fall into the block of fine ranges rank r merges (u64, for the all-reduce)
-__global__ void k_xchg_counts(const uint32_t *__restrict__ off_table, size_t fgn, const int *__restrict__ sample_ids, int n_mine, int world,
-                              uint32_t per, int parts, ull *__restrict__ cnt) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_mine * world) return;
-    const int s = sample_ids[i / world], r = i % world;
-    const uint32_t *off = off_table + (size_t)s * fgn;
-    cnt[(size_t)s * world + r] = r < parts ? (ull)(off[(size_t)(r + 1) * per] - off[(size_t)r * per]) : 0ull;
+// one sample: row[r] = entries that fall into the block of fine ranges rank r merges; row[geo..geo+2] = geometry check (fb, 1, fb^2)
+__global__ void k_xchg_counts1(const uint32_t *__restrict__ off, int world, uint32_t per, int parts, ull *__restrict__ row, ull *__restrict__ geo, int fb) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < world) row[r] = r < parts ? (ull)(off[(size_t)(r + 1) * per] - off[(size_t)r * per]) : 0ull;
+    if (r == 0) { geo[0] = (ull)fb; geo[1] = 1ull; geo[2] = (ull)fb * (ull)fb; }
 }
 // received offset rows are slices of the owner's table: re-base every row to its first entry
 __global__ void k_xchg_rebase(uint32_t *__restrict__ rows, size_t fgn, int n_rows) {
@@ -1642,6 +1668,175 @@ int simka_gpu_exchange_timings(simka_ctx *ctx, float ms[4]) {
     return SIMKA_OK;
 }
 
+}  // extern "C"
+
+#if SIMKA_HAVE_NCCL_H
+// ---- the exchange, round by round -------------------------------------------------------------------------------------------
+// Round t = the samples t * world + r (one per rank).  After its sample is counted a rank enqueues, on the side stream, the
+// all-reduce of the round's slice sizes [owner][destination]; one sample later (the sizes have long arrived) it posts the sends
+// and receives of the round, which then overlap the counting of the following samples.  Every rank issues the NCCL operations
+// in the same order: sizes(0), data(0), sizes(1), data(1), ...  Only FULL rounds start early (every rank has a sample in them);
+// a trailing partial round is exchanged by simka_gpu_exchange_and_merge, which all ranks call.
+static int xchg_setup(simka_ctx *ctx) {
+    const int N = ctx->prm.nb_samples, world = ctx->comm_world;
+    const int T = (N + world - 1) / world;
+    CK(cudaSetDevice(ctx->prm.device));
+    if (!ctx->xstream) CK(cudaStreamCreateWithFlags(&ctx->xstream, cudaStreamNonBlocking));
+    if (!ctx->x_sample_done) CK(cudaEventCreateWithFlags(&ctx->x_sample_done, cudaEventDisableTiming));
+    if (!ctx->x_all_done) CK(cudaEventCreateWithFlags(&ctx->x_all_done, cudaEventDisableTiming));
+    const size_t row = (size_t)world * world + 3;
+    if ((int)ctx->xr.size() != T) {
+        for (auto &r : ctx->xr) if (r.sizes_ready) cudaEventDestroy(r.sizes_ready);
+        ctx->xr.assign(T, simka_ctx::XRound());
+        for (auto &r : ctx->xr) CK(cudaEventCreateWithFlags(&r.sizes_ready, cudaEventDisableTiming));
+        if (ctx->xh) { cudaFreeHost(ctx->xh); ctx->xh = nullptr; }
+        CK(cudaHostAlloc((void **)&ctx->xh, (size_t)T * row * 8, cudaHostAllocDefault));
+        if (ctx->d_xcnt.reserve((size_t)T * row * 8) || ctx->d_xids.reserve(64)) { ctx->set_error("out of device memory"); return SIMKA_ERR_NOMEM; }
+    }
+    if (!ctx->mctx) {
+        simka_params mp = ctx->prm;
+        mp.shard_rank = 0; mp.shard_count = 1; mp.expected_kmers_per_sample = 0;
+        const int rc = simka_gpu_create(&ctx->mctx, &mp);
+        if (rc != SIMKA_OK) { ctx->set_error("could not create the merge context"); return rc; }
+    }
+    ctx->x_recv_e.assign(N, nullptr);
+    ctx->x_recv_c.assign(N, nullptr);
+    ctx->x_recv_n.assign(N, 0);
+    return SIMKA_OK;
+}
+
+// geometry of the slices from this rank's fine-range bits (every rank derives the same one; checked with every round)
+static void xchg_geometry(simka_ctx *ctx, int fb) {
+    int parts = 1;
+    while (parts * 2 <= ctx->comm_world && parts * 2 <= (1 << fb)) parts *= 2;
+    int lb = fb;
+    for (int p = parts; p > 1; p >>= 1) lb--;
+    ctx->x_fb = fb; ctx->x_parts = parts; ctx->x_lb = lb;
+}
+
+// side stream: sizes of round t -> all ranks (this rank's sample of the round is `s`, or -1 when it has none)
+static int xchg_enqueue_sizes(simka_ctx *ctx, int t, int s) {
+    const int world = ctx->comm_world, rank = ctx->comm_rank;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const size_t row = (size_t)world * world + 3;
+    ull *d_row = ctx->d_xcnt.as<ull>() + (size_t)t * row;
+    CK(cudaMemsetAsync(d_row, 0, row * 8, ctx->xstream));
+    if (s >= 0) {
+        CK(cudaEventRecord(ctx->x_sample_done, ctx->stream));  // the sample's list and offsets are final behind this point
+        CK(cudaStreamWaitEvent(ctx->xstream, ctx->x_sample_done, 0));
+        const int fb = ctx->fg_bits;
+        if (ctx->x_fb < 0) xchg_geometry(ctx, fb);
+        const uint32_t per = 1u << ctx->x_lb;
+        // entries of my sample per destination = row `rank` of the [owner][destination] table
+        k_xchg_counts1<<<(world + 255) / 256, 256, 0, ctx->xstream>>>(ctx->d_off_table.as<uint32_t>() + (size_t)s * (((size_t)1 << fb) + 1), world, per, ctx->x_parts,
+                                                                    d_row + (size_t)rank * world, d_row + (size_t)world * world, fb);
+        ctx->launches++;
+    }
+    NK(nccl().AllReduce(d_row, d_row, row, ncclUint64, ncclSum, comm, ctx->xstream));
+    CK(cudaMemcpyAsync(ctx->xh + (size_t)t * row, d_row, row * 8, cudaMemcpyDeviceToHost, ctx->xstream));
+    CK(cudaEventRecord(ctx->xr[t].sizes_ready, ctx->xstream));
+    ctx->xr[t].state = 1;
+    return SIMKA_OK;
+}
+
+// side stream: sends and receives of round t (its sizes must have been enqueued); waits for the sizes on the host
+static int xchg_post_data(simka_ctx *ctx, int t) {
+    const int N = ctx->prm.nb_samples, world = ctx->comm_world, rank = ctx->comm_rank;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    simka_ctx *m = ctx->mctx;
+    const size_t row = (size_t)world * world + 3;
+    CK(cudaEventSynchronize(ctx->xr[t].sizes_ready));
+    const ull *h = ctx->xh + (size_t)t * row;  // [owner * world + destination]
+    const ull *geo = h + (size_t)world * world;
+    if (geo[1] == 0) { ctx->xr[t].state = 2; return SIMKA_OK; }  // nobody had a sample in this round
+    if (geo[1] * geo[2] != geo[0] * geo[0]) {
+        ctx->set_error("ranks disagree on the fine-range geometry: pass the same expected_kmers_per_sample to every rank");
+        return SIMKA_ERR_INVALID;
+    }
+    const int fb = (int)(geo[0] / geo[1]);
+    if (ctx->x_fb < 0) xchg_geometry(ctx, fb);
+    if (ctx->x_fb != fb) { ctx->set_error("fine-range geometry changed between rounds"); return SIMKA_ERR_INVALID; }
+    const int parts = ctx->x_parts, lb = ctx->x_lb;
+    const uint32_t per = 1u << lb;
+    const size_t fgn = ((size_t)1 << lb) + 1, fgn_src = ((size_t)1 << fb) + 1;
+    if (!ctx->x_recv_o) {
+        ctx->x_recv_o = (uint32_t *)m->arena.alloc((size_t)N * fgn * 4);
+        if (!ctx->x_recv_o) { ctx->set_error("out of device memory (exchange buffers)"); return SIMKA_ERR_NOMEM; }
+        CK(cudaMemsetAsync(ctx->x_recv_o, 0, (size_t)N * fgn * 4, ctx->xstream));
+    }
+    // receive buffers of the round's samples (this rank's block of hash ranges)
+    for (int o = 0; o < world; o++) {
+        const int s = t * world + o;
+        if (s >= N) break;
+        const uint64_t n = rank < parts ? h[(size_t)o * world + rank] : 0;
+        ctx->x_recv_n[s] = n;
+        ctx->x_recv_e[s] = (uint64_t *)m->arena.alloc(std::max<uint64_t>(n, 1) * 8);
+        ctx->x_recv_c[s] = (uint32_t *)m->arena.alloc(std::max<uint64_t>(n, 1) * 4);
+        if (!ctx->x_recv_e[s] || !ctx->x_recv_c[s]) { ctx->set_error("out of device memory (exchange buffers)"); return SIMKA_ERR_NOMEM; }
+    }
+    const int mine = t * world + rank < N ? t * world + rank : -1;
+    NK(nccl().GroupStart());
+    if (mine >= 0) {
+        const SampleData &sd = ctx->samples[mine];
+        uint64_t a = 0;
+        for (int r = 0; r < parts; r++) {
+            const uint64_t n = h[(size_t)rank * world + r];
+            if (r != rank) {
+                if (n) {
+                    NK(nccl().Send(sd.eh + a, n, ncclUint64, r, comm, ctx->xstream));
+                    NK(nccl().Send(sd.ec + a, n, ncclUint32, r, comm, ctx->xstream));
+                }
+                NK(nccl().Send(ctx->d_off_table.as<uint32_t>() + (size_t)mine * fgn_src + (size_t)r * per, fgn, ncclUint32, r, comm, ctx->xstream));
+            }
+            a += n;
+        }
+    }
+    if (rank < parts) {
+        for (int o = 0; o < world; o++) {
+            const int s = t * world + o;
+            if (s >= N) break;
+            if (o == rank) continue;
+            if (ctx->x_recv_n[s]) {
+                NK(nccl().Recv(ctx->x_recv_e[s], ctx->x_recv_n[s], ncclUint64, o, comm, ctx->xstream));
+                NK(nccl().Recv(ctx->x_recv_c[s], ctx->x_recv_n[s], ncclUint32, o, comm, ctx->xstream));
+            }
+            NK(nccl().Recv(ctx->x_recv_o + (size_t)s * fgn, fgn, ncclUint32, o, comm, ctx->xstream));
+        }
+    }
+    NK(nccl().GroupEnd());
+    if (mine >= 0 && rank < parts) {  // my own slice: a device copy
+        const SampleData &sd = ctx->samples[mine];
+        uint64_t a = 0;
+        for (int q = 0; q < rank; q++) a += h[(size_t)rank * world + q];
+        const uint64_t n = h[(size_t)rank * world + rank];
+        if (n) {
+            CK(cudaMemcpyAsync(ctx->x_recv_e[mine], sd.eh + a, n * 8, cudaMemcpyDeviceToDevice, ctx->xstream));
+            CK(cudaMemcpyAsync(ctx->x_recv_c[mine], sd.ec + a, n * 4, cudaMemcpyDeviceToDevice, ctx->xstream));
+        }
+        CK(cudaMemcpyAsync(ctx->x_recv_o + (size_t)mine * fgn, ctx->d_off_table.as<uint32_t>() + (size_t)mine * fgn_src + (size_t)rank * per, fgn * 4,
+                           cudaMemcpyDeviceToDevice, ctx->xstream));
+    }
+    ctx->xr[t].state = 2;
+    return SIMKA_OK;
+}
+
+static int xchg_after_sample(simka_ctx *ctx, int sample_id) {
+    const int N = ctx->prm.nb_samples, world = ctx->comm_world, rank = ctx->comm_rank;
+    if (sample_id % world != rank || ctx->kp.shard_count > 1 || ctx->kp.key_mode) return SIMKA_OK;
+    const int t = sample_id / world;
+    if (t >= N / world) return SIMKA_OK;  // a partial last round: exchanged by simka_gpu_exchange_and_merge (every rank is there)
+    if (ctx->xr.empty() || ctx->x_recv_e.empty()) { const int rc = xchg_setup(ctx); if (rc != SIMKA_OK) return rc; }
+    for (int q = 0; q < t; q++) if (ctx->xr[q].state == 0) return SIMKA_OK;  // samples finished out of order: leave everything to the final call
+    if (ctx->xr[t].state != 0) return SIMKA_OK;
+    if (t > 0 && ctx->xr[t - 1].state == 1) { const int rc = xchg_post_data(ctx, t - 1); if (rc != SIMKA_OK) return rc; }
+    return xchg_enqueue_sizes(ctx, t, sample_id);
+}
+#else
+static int xchg_after_sample(simka_ctx *, int) { return SIMKA_OK; }
+#endif
+
+extern "C" {
+
 int simka_gpu_exchange_and_merge(simka_ctx *ctx) try {
     if (!ctx) return SIMKA_ERR_INVALID;
 #if SIMKA_HAVE_NCCL_H
@@ -1650,130 +1845,48 @@ int simka_gpu_exchange_and_merge(simka_ctx *ctx) try {
     const int N = ctx->prm.nb_samples, world = ctx->comm_world, rank = ctx->comm_rank;
     ncclComm_t comm = (ncclComm_t)ctx->comm;
     CK(cudaSetDevice(ctx->prm.device));
-    cudaStream_t st = ctx->stream;
-    std::vector<int> mine;
-    for (int s = rank; s < N; s += world) mine.push_back(s);
-    for (int s : mine) if (!ctx->samples[s].done) { ctx->set_error("a sample of this rank is not finished"); return SIMKA_ERR_INVALID; }
-    // ---- 1. one all-reduce: per-sample totals | entries per (sample, destination) | fine-range geometry check
-    const int fb = mine.empty() ? -1 : ctx->fg_bits;
-    int parts = 1;
-    while (fb >= 0 && parts * 2 <= world && parts * 2 <= (1 << fb)) parts *= 2;
-    int lb = fb;
-    for (int p = parts; p > 1; p >>= 1) lb--;
-    const uint32_t per = fb >= 0 ? 1u << lb : 1u;
-    const size_t n_hdr = (size_t)N * 4 + (size_t)N * world + 3;
+    for (int s = rank; s < N; s += world) if (!ctx->samples[s].done) { ctx->set_error("a sample of this rank is not finished"); return SIMKA_ERR_INVALID; }
+    if (ctx->xr.empty() || ctx->x_recv_e.empty()) { const int rc = xchg_setup(ctx); if (rc != SIMKA_OK) return rc; }
+    simka_ctx *m = ctx->mctx;
+    const int T = (int)ctx->xr.size();
+    CK(cudaEventRecord(ctx->xev[0], ctx->xstream));
+    // ---- 1. the rounds that have not run yet (all of them when the samples were not finished in order; else the last ones)
+    for (int t = 0; t < T; t++) {
+        if (ctx->xr[t].state == 0) {
+            const int s = t * world + rank < N ? t * world + rank : -1;
+            const int rc = xchg_enqueue_sizes(ctx, t, s);
+            if (rc != SIMKA_OK) return rc;
+        }
+        if (ctx->xr[t].state == 1) { const int rc = xchg_post_data(ctx, t); if (rc != SIMKA_OK) return rc; }
+    }
+    const size_t fgn = ((size_t)1 << ctx->x_lb) + 1;
+    if (rank < ctx->x_parts) {
+        k_xchg_rebase<<<dim3((unsigned)std::min<size_t>((fgn + 255) / 256, 64), (unsigned)N), 256, 0, ctx->xstream>>>(ctx->x_recv_o, fgn, N);
+        k_xchg_zero_first<<<(N + 255) / 256, 256, 0, ctx->xstream>>>(ctx->x_recv_o, fgn, N);
+        ctx->launches += 2;
+    }
+    CK(cudaEventRecord(ctx->xev[1], ctx->xstream));
+    // ---- 2. global per-sample totals
+    const size_t n_hdr = (size_t)N * 4;
     std::vector<ull> hdr(n_hdr, 0);
-    for (int s : mine) {
+    for (int s = rank; s < N; s += world) {
         const simka_sample_totals &t = ctx->samples[s].local;
         hdr[(size_t)s * 4] = t.nb_reads; hdr[(size_t)s * 4 + 1] = t.nb_distinct; hdr[(size_t)s * 4 + 2] = t.nb_kmers; hdr[(size_t)s * 4 + 3] = t.chord_n2;
     }
-    if (fb >= 0) { hdr[n_hdr - 3] = (ull)fb; hdr[n_hdr - 2] = 1; hdr[n_hdr - 1] = (ull)fb * fb; }
-    if (ctx->d_xhdr.reserve(n_hdr * 8 + (mine.size() + 1) * 4)) { ctx->set_error("out of device memory"); return SIMKA_ERR_NOMEM; }
+    if (ctx->d_xhdr.reserve(n_hdr * 8)) { ctx->set_error("out of device memory"); return SIMKA_ERR_NOMEM; }
     ull *d_hdr = ctx->d_xhdr.as<ull>();
-    int *d_ids = reinterpret_cast<int *>(d_hdr + n_hdr);
-    CK(cudaEventRecord(ctx->xev[0], st));
-    CK(cudaMemcpyAsync(d_hdr, hdr.data(), n_hdr * 8, cudaMemcpyHostToDevice, st));
-    if (!mine.empty()) {
-        CK(cudaMemcpyAsync(d_ids, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice, st));
-        const int n_thr = (int)mine.size() * world;
-        k_xchg_counts<<<(n_thr + 255) / 256, 256, 0, st>>>(ctx->d_off_table.as<uint32_t>(), ((size_t)1 << fb) + 1, d_ids, (int)mine.size(), world, per, parts,
-                                                         d_hdr + (size_t)N * 4);
-        ctx->launches++;
-    }
-    NK(nccl().AllReduce(d_hdr, d_hdr, n_hdr, ncclUint64, ncclSum, comm, st));
-    CK(cudaMemcpyAsync(hdr.data(), d_hdr, n_hdr * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->xev[1], st));
-    CK(cudaStreamSynchronize(st));
-    if (hdr[n_hdr - 2] == 0) { ctx->set_error("no rank counted a sample"); return SIMKA_ERR_INVALID; }
-    if (hdr[n_hdr - 2] * hdr[n_hdr - 1] != hdr[n_hdr - 3] * hdr[n_hdr - 3]) {
-        ctx->set_error("ranks disagree on the fine-range geometry: pass the same expected_kmers_per_sample to every rank");
-        return SIMKA_ERR_INVALID;
-    }
-    const int fine_bits = (int)(hdr[n_hdr - 3] / hdr[n_hdr - 2]);
-    if (fb < 0) {  // a rank without samples: the geometry of the others
-        parts = 1;
-        while (parts * 2 <= world && parts * 2 <= (1 << fine_bits)) parts *= 2;
-        lb = fine_bits;
-        for (int p = parts; p > 1; p >>= 1) lb--;
-    }
-    const size_t fgn = ((size_t)1 << lb) + 1;
-    const ull *cnt = hdr.data() + (size_t)N * 4;  // [s * world + r]
+    CK(cudaMemcpyAsync(d_hdr, hdr.data(), n_hdr * 8, cudaMemcpyHostToDevice, ctx->xstream));
+    NK(nccl().AllReduce(d_hdr, d_hdr, n_hdr, ncclUint64, ncclSum, comm, ctx->xstream));
+    CK(cudaMemcpyAsync(hdr.data(), d_hdr, n_hdr * 8, cudaMemcpyDeviceToHost, ctx->xstream));
+    CK(cudaEventRecord(ctx->xev[2], ctx->xstream));
+    CK(cudaEventRecord(ctx->x_all_done, ctx->xstream));
+    CK(cudaStreamSynchronize(ctx->xstream));
     std::vector<simka_sample_totals> g_tot(N);
     for (int s = 0; s < N; s++) g_tot[s] = simka_sample_totals{hdr[(size_t)s * 4], hdr[(size_t)s * 4 + 1], hdr[(size_t)s * 4 + 2], hdr[(size_t)s * 4 + 3]};
-    // ---- 2. merge context + receive buffers (its arena keeps them across runs)
-    if (!ctx->mctx) {
-        simka_params mp = ctx->prm;
-        mp.shard_rank = 0; mp.shard_count = 1; mp.expected_kmers_per_sample = 0;
-        const int rc = simka_gpu_create(&ctx->mctx, &mp);
-        if (rc != SIMKA_OK) { ctx->set_error("could not create the merge context"); return rc; }
-    } else {
-        const int rc = simka_gpu_reset(ctx->mctx);
-        if (rc != SIMKA_OK) { ctx->set_error(ctx->mctx->err); return rc; }
-    }
-    simka_ctx *m = ctx->mctx;
-    uint64_t total_recv = 0;
-    for (int s = 0; s < N; s++) total_recv += cnt[(size_t)s * world + rank];
-    uint64_t *recv_e = (uint64_t *)m->arena.alloc(std::max<uint64_t>(total_recv, 1) * 8);
-    uint32_t *recv_c = (uint32_t *)m->arena.alloc(std::max<uint64_t>(total_recv, 1) * 4);
-    uint32_t *recv_o = (uint32_t *)m->arena.alloc((size_t)N * fgn * 4);
-    if (!recv_e || !recv_c || !recv_o) { ctx->set_error("out of device memory (exchange buffers)"); return SIMKA_ERR_NOMEM; }
-    if (rank >= parts) CK(cudaMemsetAsync(recv_o, 0, (size_t)N * fgn * 4, st));  // this rank merges nothing: empty lists
-    // ---- 3. the exchange: every slice straight from the list it was counted into (no staging copy), one NCCL group
-    NK(nccl().GroupStart());
-    for (int r = 0; r < parts; r++) {  // sends (and the local copies) of my samples, destination-major
-        for (int s : mine) {
-            const SampleData &sd = ctx->samples[s];
-            uint64_t a = 0;
-            for (int q = 0; q < r; q++) a += cnt[(size_t)s * world + q];
-            const uint64_t n = cnt[(size_t)s * world + r];
-            const uint32_t *off_src = ctx->d_off_table.as<uint32_t>() + (size_t)s * (((size_t)1 << fine_bits) + 1) + (size_t)r * per;
-            if (r == rank) continue;  // local slice: copied below, outside the group
-            if (n) {
-                NK(nccl().Send(sd.eh + a, n, ncclUint64, r, comm, st));
-                NK(nccl().Send(sd.ec + a, n, ncclUint32, r, comm, st));
-            }
-            NK(nccl().Send(off_src, fgn, ncclUint32, r, comm, st));
-        }
-    }
-    std::vector<uint64_t> pos(N, 0);  // start of sample s inside recv_e / recv_c (sample-major)
-    { uint64_t p = 0; for (int s = 0; s < N; s++) { pos[s] = p; p += cnt[(size_t)s * world + rank]; } }
-    if (rank < parts) {
-        for (int o = 0; o < world; o++) {
-            if (o == rank) continue;
-            for (int s = o; s < N; s += world) {
-                const uint64_t n = cnt[(size_t)s * world + rank];
-                if (n) {
-                    NK(nccl().Recv(recv_e + pos[s], n, ncclUint64, o, comm, st));
-                    NK(nccl().Recv(recv_c + pos[s], n, ncclUint32, o, comm, st));
-                }
-                NK(nccl().Recv(recv_o + (size_t)s * fgn, fgn, ncclUint32, o, comm, st));
-            }
-        }
-    }
-    NK(nccl().GroupEnd());
-    if (rank < parts) {
-        for (int s : mine) {
-            const SampleData &sd = ctx->samples[s];
-            uint64_t a = 0;
-            for (int q = 0; q < rank; q++) a += cnt[(size_t)s * world + q];
-            const uint64_t n = cnt[(size_t)s * world + rank];
-            if (n) {
-                CK(cudaMemcpyAsync(recv_e + pos[s], sd.eh + a, n * 8, cudaMemcpyDeviceToDevice, st));
-                CK(cudaMemcpyAsync(recv_c + pos[s], sd.ec + a, n * 4, cudaMemcpyDeviceToDevice, st));
-            }
-            CK(cudaMemcpyAsync(recv_o + (size_t)s * fgn, ctx->d_off_table.as<uint32_t>() + (size_t)s * (((size_t)1 << fine_bits) + 1) + (size_t)rank * per, fgn * 4,
-                               cudaMemcpyDeviceToDevice, st));
-        }
-        k_xchg_rebase<<<dim3((unsigned)std::min<size_t>((fgn + 255) / 256, 64), (unsigned)N), 256, 0, st>>>(recv_o, fgn, N);
-        k_xchg_zero_first<<<(N + 255) / 256, 256, 0, st>>>(recv_o, fgn, N);
-        ctx->launches += 2;
-    }
-    CK(cudaEventRecord(ctx->xev[2], st));
-    CK(cudaStreamWaitEvent(m->stream, ctx->xev[2], 0));
-    // ---- 4. stage 2 on my block of hash ranges over all samples
+    // ---- 3. stage 2 on my block of hash ranges over all samples
+    CK(cudaStreamWaitEvent(m->stream, ctx->x_all_done, 0));
     for (int s = 0; s < N; s++) {
-        const int rc = simka_gpu_import_sample(m, s, recv_e + pos[s], recv_c + pos[s], rank < parts ? cnt[(size_t)s * world + rank] : 0, recv_o + (size_t)s * fgn, lb,
-                                               g_tot[s].nb_reads);
+        const int rc = simka_gpu_import_sample(m, s, ctx->x_recv_e[s], ctx->x_recv_c[s], ctx->x_recv_n[s], ctx->x_recv_o + (size_t)s * fgn, ctx->x_lb, g_tot[s].nb_reads);
         if (rc != SIMKA_OK) { ctx->set_error("import: " + m->err); return rc; }
     }
     simka_gpu_set_totals(m, g_tot.data());
@@ -1781,7 +1894,7 @@ int simka_gpu_exchange_and_merge(simka_ctx *ctx) try {
         const int rc = simka_gpu_merge_and_accumulate(m);
         if (rc != SIMKA_OK) { ctx->set_error("merge: " + m->err); return rc; }
     }
-    // ---- 5. sum of the accumulators over the ranks: u64 block | f64 block | fixed-point block
+    // ---- 4. sum of the accumulators over the ranks: u64 block | f64 block | fixed-point block
     {
         const size_t nn = (size_t)N * N, ns = (size_t)N * (N + 1) / 2;
         const size_t n_u64 = nn + ns + ns + nn + nn + nn + nn + 4;  // up to and including the scalars
@@ -1798,8 +1911,8 @@ int simka_gpu_exchange_and_merge(simka_ctx *ctx) try {
     m->reduced = true;
     ctx->global_totals = g_tot;
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->xev[0], ctx->xev[1]) == cudaSuccess) ctx->xms[0] = ms;
-    if (cudaEventElapsedTime(&ms, ctx->xev[1], ctx->xev[2]) == cudaSuccess) ctx->xms[1] = ms;
+    if (cudaEventElapsedTime(&ms, ctx->xev[1], ctx->xev[2]) == cudaSuccess) ctx->xms[0] = ms;  // totals all-reduce
+    if (cudaEventElapsedTime(&ms, ctx->xev[0], ctx->xev[1]) == cudaSuccess) ctx->xms[1] = ms;  // what was left of the list exchange after the last sample
     ctx->xms[2] = m->merge_ms;
     if (cudaEventElapsedTime(&ms, ctx->xev[3], ctx->xev[4]) == cudaSuccess) ctx->xms[3] = ms;
     return SIMKA_OK;

@@ -347,6 +347,15 @@ int run(int argc, char **argv) {
     prm.device = o.device;
     // one context per GPU; with -nb-gpus G > 1 sample i belongs to GPU i % G, one host thread drives each GPU
     const size_t G = std::min<size_t>((size_t)o.nbGpus, N);
+    if (G > 1) {
+        // every context must cut the hash space into the same fine ranges: the geometry comes from the expected size of a sample,
+        // taken here from the first parsed one (a single context derives it from the first sample it counts)
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return parsed[0].ready; });
+        uint64_t w = 0;
+        for (uint64_t x : parsed[0].words) w += x;
+        prm.expected_kmers_per_sample = std::max<uint64_t>(1, w * 32);
+    }
     std::vector<simka_ctx *> ctxs(G, nullptr);
     int rc = SIMKA_OK;
     for (size_t g = 0; g < G && rc == SIMKA_OK; g++) {
