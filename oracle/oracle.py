@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         L.orc_sample_size.argtypes = [C.c_void_p, C.c_int]
         L.orc_sample_kmers.restype = u64p
         L.orc_sample_kmers.argtypes = [C.c_void_p, C.c_int]
+        L.orc_sample_kmers_hi.restype = u64p
+        L.orc_sample_kmers_hi.argtypes = [C.c_void_p, C.c_int]
         L.orc_sample_counts.restype = u32p
         L.orc_sample_counts.argtypes = [C.c_void_p, C.c_int]
         L.orc_sample_totals.restype = None
@@ -167,7 +169,7 @@ class Run:
                                    _p(self._so, C.c_uint64), self.n, k, abundance_min, abundance_max,
                                    int(simple), int(complex_), nthreads)
         if not self._h:
-            raise ValueError("orc_run_create failed (k must be 1..31)")
+            raise ValueError("orc_run_create failed (k must be 1..63)")
 
     @classmethod
     def from_reads(cls, samples, k, **kw):
@@ -196,6 +198,9 @@ class Run:
             return np.zeros(0, np.uint64), np.zeros(0, np.uint32)
         km = np.ctypeslib.as_array(L.orc_sample_kmers(self._h, s), (n,)).copy()
         ct = np.ctypeslib.as_array(L.orc_sample_counts(self._h, s), (n,)).copy()
+        if self.k > 31:  # 128-bit k-mers: (n, 2) array of [low word, high word], ascending as 128-bit integers
+            hi = np.ctypeslib.as_array(L.orc_sample_kmers_hi(self._h, s), (n,)).copy()
+            return np.stack([km, hi], axis=1), ct
         return km, ct
 
     def totals(self, s):

@@ -64,6 +64,39 @@ static size_t kmers_impl(const char *seq, size_t len, int k, uint64_t *out, uint
 size_t orc_canonical_kmers(const char *seq, size_t len, int k, uint64_t *canon, uint8_t *valid) {
     return kmers_impl(seq, len, k, canon, valid, 1);
 }
+
+/* the same for 32 <= k <= 63: Kmer<64>, Type = LargeInt<2> (GC/tools/math/LargeInt2.pri: value[1] is the high word; operator<
+ * compares value[1] first, then value[0], i.e. the order of the 128-bit integer); span dispatch KSIZE_LIST "32 64 96 128",
+ * CMakeLists.txt:66-71, Integer::apply GC/tools/math/Integer.hpp:76-85 */
+typedef unsigned __int128 u128;
+static size_t kmers_impl128(const char *seq, size_t len, int k, u128 *out, uint8_t *valid) {
+    if (len < (size_t)k) return 0;
+    const u128 mask = (((u128)1) << (2 * k)) - 1;  /* k <= 63 */
+    u128 fwd = 0, rev = 0;
+    int bad = -1;
+    size_t n = 0;
+    for (size_t i = 0; i < len; i++) {
+        unsigned c = nt_code(seq[i]);
+        fwd = ((fwd << 2) | c) & mask;
+        rev = (rev >> 2) | ((u128)(c ^ 2u) << (2 * (k - 1)));
+        if (!nt_valid(seq[i])) bad = k - 1; else bad--;
+        if (i + 1 >= (size_t)k) {
+            out[n] = fwd < rev ? fwd : rev;
+            valid[n] = (bad < 0);
+            n++;
+        }
+    }
+    return n;
+}
+/* test hook: canonical k-mers as (lo, hi) word pairs */
+size_t orc_canonical_kmers128(const char *seq, size_t len, int k, uint64_t *lo, uint64_t *hi, uint8_t *valid) {
+    if (k < 1 || k > 63 || len < (size_t)k) return 0;
+    u128 *tmp = malloc((len - k + 1) * sizeof(u128));
+    const size_t n = kmers_impl128(seq, len, k, tmp, valid);
+    for (size_t i = 0; i < n; i++) { lo[i] = (uint64_t)tmp[i]; hi[i] = (uint64_t)(tmp[i] >> 64); }
+    free(tmp);
+    return n;
+}
 size_t orc_direct_kmers(const char *seq, size_t len, int k, uint64_t *fwd, uint8_t *valid) {
     return kmers_impl(seq, len, k, fwd, valid, 0);
 }
@@ -98,7 +131,8 @@ uint32_t orc_minimizer(uint64_t kmer_fwd, int k, int m) {
  * ---------------------------------------------------------------------------------------- */
 
 typedef struct {
-    uint64_t *kmers;
+    uint64_t *kmers;      /* low words */
+    uint64_t *kmers_hi;   /* high words, k > 31 only (NULL otherwise: the high word is 0) */
     uint32_t *counts;
     size_t n;
     uint64_t nb_reads, nb_distinct, nb_kmers, chord_n2;
@@ -171,7 +205,7 @@ static void stats_add(stats_t *a, const stats_t *b, int n) {
 orc_run *orc_run_create(const char *seqs, const uint64_t *read_off, const uint64_t *sample_read_off,
                         int nsamples, int k, int64_t amin, int64_t amax, int simple, int complex_,
                         int nthreads) {
-    if (k < 1 || k > 31 || nsamples < 1) return NULL; /* span 32 only: GC/kmer/impl/Model.hpp:401-406 */
+    if (k < 1 || k > 63 || nsamples < 1) return NULL; /* spans 32 and 64 (Kmer<32>, Kmer<64>): GC/kmer/impl/Model.hpp:401-406 */
     orc_run *r = calloc(1, sizeof *r);
     if (!r) return NULL;
     r->seqs = seqs; r->read_off = read_off; r->sample_read_off = sample_read_off;
@@ -189,7 +223,7 @@ orc_run *orc_run_create(const char *seqs, const uint64_t *read_off, const uint64
 
 void orc_run_destroy(orc_run *r) {
     if (!r) return;
-    for (int s = 0; s < r->n; s++) { free(r->samples[s].kmers); free(r->samples[s].counts); }
+    for (int s = 0; s < r->n; s++) { free(r->samples[s].kmers); free(r->samples[s].kmers_hi); free(r->samples[s].counts); }
     free(r->samples);
     stats_free(&r->st);
     free(r);
@@ -216,7 +250,66 @@ static void radix_sort_u64(uint64_t *a, uint64_t *tmp, size_t n, int bits) {
     if (src != a) memcpy(a, src, n * 8);
 }
 
+static void radix_sort_u128(u128 *a, u128 *tmp, size_t n, int bits) {
+    u128 *src = a, *dst = tmp;
+    for (int shift = 0; shift < bits; shift += 11) {
+        size_t hist[2048] = {0};
+        for (size_t i = 0; i < n; i++) hist[(size_t)(src[i] >> shift) & 2047]++;
+        size_t sum = 0; int single = 0;
+        for (int d = 0; d < 2048; d++) { size_t c = hist[d]; if (c == n) single = 1; hist[d] = sum; sum += c; }
+        if (single) continue;
+        for (size_t i = 0; i < n; i++) dst[hist[(size_t)(src[i] >> shift) & 2047]++] = src[i];
+        u128 *t = src; src = dst; dst = t;
+    }
+    if (src != a) memcpy(a, src, n * sizeof(u128));
+}
+
+/* k > 31: same counting on 128-bit k-mers (the DSK path; MiniKC and its quirks are k <= 15 only) */
+static void count_sample128(orc_run *r, int s) {
+    sample_t *sm = &r->samples[s];
+    const int k = r->k;
+    uint64_t r0 = r->sample_read_off[s], r1 = r->sample_read_off[s + 1];
+    size_t cap = 0, maxlen = 0;
+    for (uint64_t q = r0; q < r1; q++) {
+        uint64_t len = r->read_off[q + 1] - r->read_off[q];
+        if (len >= (uint64_t)k) cap += len - k + 1;
+        if (len > maxlen) maxlen = len;
+    }
+    u128 *keys = malloc((cap ? cap : 1) * sizeof(u128)), *tmp = malloc((cap ? cap : 1) * sizeof(u128));
+    u128 *kb = malloc((maxlen + 1) * sizeof(u128)); uint8_t *vb = malloc(maxlen + 1);
+    size_t nk = 0;
+    for (uint64_t q = r0; q < r1; q++) {
+        const size_t len = r->read_off[q + 1] - r->read_off[q];
+        const size_t m = kmers_impl128(r->seqs + r->read_off[q], len, k, kb, vb);
+        for (size_t i = 0; i < m; i++) if (vb[i]) keys[nk++] = kb[i];
+    }
+    free(kb); free(vb);
+    radix_sort_u128(keys, tmp, nk, 2 * k);
+    free(tmp);
+    size_t nd = 0;
+    for (size_t i = 0; i < nk;) { size_t j = i + 1; while (j < nk && keys[j] == keys[i]) j++; nd++; i = j; }
+    sm->kmers = malloc((nd ? nd : 1) * 8);
+    sm->kmers_hi = malloc((nd ? nd : 1) * 8);
+    sm->counts = malloc((nd ? nd : 1) * 4);
+    size_t o = 0;
+    sm->nb_distinct = sm->nb_kmers = sm->chord_n2 = 0;
+    for (size_t i = 0; i < nk;) {
+        size_t j = i + 1; while (j < nk && keys[j] == keys[i]) j++;
+        int64_t c = (int64_t)(j - i);
+        if (!(c < r->amin || c > r->amax)) {
+            sm->kmers[o] = (uint64_t)keys[i]; sm->kmers_hi[o] = (uint64_t)(keys[i] >> 64); sm->counts[o] = (uint32_t)c; o++;
+            sm->nb_distinct += 1; sm->nb_kmers += (uint64_t)c;
+            sm->chord_n2 += (uint64_t)pow((double)c, 2);
+        }
+        i = j;
+    }
+    sm->n = o;
+    sm->nb_reads = r1 - r0;
+    free(keys);
+}
+
 static void count_sample(orc_run *r, int s) {
+    if (r->k > 31) { count_sample128(r, s); return; }
     sample_t *sm = &r->samples[s];
     const int k = r->k;
     uint64_t r0 = r->sample_read_off[s], r1 = r->sample_read_off[s + 1];
@@ -281,7 +374,8 @@ void orc_run_count(orc_run *r) {
  * stage 2: N-way merge + accumulator update
  * ---------------------------------------------------------------------------------------- */
 
-typedef struct { uint64_t kmer; int s; } heap_item;
+typedef struct { u128 kmer; int s; } heap_item;
+#define SAMPLE_KMER(sm, i) ((sm)->kmers_hi ? (((u128)(sm)->kmers_hi[i] << 64) | (sm)->kmers[i]) : (u128)(sm)->kmers[i])
 static inline int heap_less(heap_item a, heap_item b) { return a.kmer < b.kmer || (a.kmer == b.kmer && a.s < b.s); }
 static void heap_push(heap_item *h, int *n, heap_item x) {
     int i = (*n)++; h[i] = x;
@@ -366,7 +460,7 @@ static void update_distance(const orc_run *r, stats_t *st, const int32_t *counts
 }
 
 /* S/SimkaMerge.cpp:1164-1264 (k-way merge) + :1307-1326 (insert gate) over the k-mer range [lo,hi) */
-static void merge_range(const orc_run *r, stats_t *st, uint64_t lo, uint64_t hi, int last) {
+static void merge_range(const orc_run *r, stats_t *st, u128 lo, u128 hi, int last) {
     const int n = r->n;
     size_t *pos = malloc((size_t)n * sizeof(size_t)), *end = malloc((size_t)n * sizeof(size_t));
     heap_item *heap = malloc((size_t)n * sizeof(heap_item));
@@ -376,14 +470,14 @@ static void merge_range(const orc_run *r, stats_t *st, uint64_t lo, uint64_t hi,
     for (int s = 0; s < n; s++) {
         const sample_t *sm = &r->samples[s];
         size_t a = 0, b = sm->n; /* lower_bound(lo) */
-        while (a < b) { size_t m = (a + b) / 2; if (sm->kmers[m] < lo) a = m + 1; else b = m; }
+        while (a < b) { size_t m = (a + b) / 2; if (SAMPLE_KMER(sm, m) < lo) a = m + 1; else b = m; }
         pos[s] = a;
         if (last) end[s] = sm->n;
-        else { size_t c = a, d = sm->n; while (c < d) { size_t m = (c + d) / 2; if (sm->kmers[m] < hi) c = m + 1; else d = m; } end[s] = c; }
-        if (pos[s] < end[s]) heap_push(heap, &hn, (heap_item){sm->kmers[pos[s]], s});
+        else { size_t c = a, d = sm->n; while (c < d) { size_t m = (c + d) / 2; if (SAMPLE_KMER(sm, m) < hi) c = m + 1; else d = m; } end[s] = c; }
+        if (pos[s] < end[s]) heap_push(heap, &hn, (heap_item){SAMPLE_KMER(sm, pos[s]), s});
     }
     while (hn > 0) {
-        uint64_t kmer = heap[0].kmer;
+        u128 kmer = heap[0].kmer;
         int ns = 0;
         while (hn > 0 && heap[0].kmer == kmer) {
             heap_item it = heap_pop(heap, &hn);
@@ -391,7 +485,7 @@ static void merge_range(const orc_run *r, stats_t *st, uint64_t lo, uint64_t hi,
             counts[s] += (int32_t)r->samples[s].counts[pos[s]];
             shared[ns++] = (uint16_t)s; /* popped in increasing sample order for equal k-mers */
             pos[s]++;
-            if (pos[s] < end[s]) heap_push(heap, &hn, (heap_item){r->samples[s].kmers[pos[s]], s});
+            if (pos[s] < end[s]) heap_push(heap, &hn, (heap_item){SAMPLE_KMER(&r->samples[s], pos[s]), s});
         }
         st->nb_distinct_kmers += 1;
         if (r->complex_ || ns > 1) {
@@ -420,9 +514,9 @@ void orc_run_merge(orc_run *r) {
 #else
         int t = 0;
 #endif
-        uint64_t lo, hi;
-        if (kb >= 8) { lo = (uint64_t)p << (kb - 8); hi = (uint64_t)(p + 1) << (kb - 8); }
-        else { lo = (p == 0) ? 0 : ~0ull; hi = ~0ull; if (p > 0) continue; }
+        u128 lo, hi;
+        if (kb >= 8) { lo = (u128)p << (kb - 8); hi = (u128)(p + 1) << (kb - 8); }
+        else { lo = 0; hi = ~(u128)0; if (p > 0) continue; }
         merge_range(r, &part[t], lo, hi, p == nparts - 1 || kb < 8);
     }
     for (int t = 0; t < r->nthreads; t++) { stats_add(&r->st, &part[t], r->n); stats_free(&part[t]); }
@@ -432,6 +526,7 @@ void orc_run_merge(orc_run *r) {
 
 size_t orc_sample_size(const orc_run *r, int s) { return r->samples[s].n; }
 const uint64_t *orc_sample_kmers(const orc_run *r, int s) { return r->samples[s].kmers; }
+const uint64_t *orc_sample_kmers_hi(const orc_run *r, int s) { return r->samples[s].kmers_hi; }  /* NULL for k <= 31 */
 const uint32_t *orc_sample_counts(const orc_run *r, int s) { return r->samples[s].counts; }
 void orc_sample_totals(const orc_run *r, int s, uint64_t out[4]) {
     const sample_t *sm = &r->samples[s];

@@ -55,6 +55,8 @@ void orc_run_destroy(orc_run *r);
 /* stage-1 outputs (src/SimkaCount.cpp:303-317): per sample sorted (kmer,count) + 4 totals */
 size_t orc_sample_size(const orc_run *r, int s);
 const uint64_t *orc_sample_kmers(const orc_run *r, int s);
+const uint64_t *orc_sample_kmers_hi(const orc_run *r, int s);   /* high words of the k-mers, k > 31 only (else NULL) */
+size_t orc_canonical_kmers128(const char *seq, size_t len, int k, uint64_t *lo, uint64_t *hi, uint8_t *valid);
 const uint32_t *orc_sample_counts(const orc_run *r, int s);
 /* out[0..3] = nbReads, nbDistinct, sum c, sum c^2 */
 void orc_sample_totals(const orc_run *r, int s, uint64_t out[4]);

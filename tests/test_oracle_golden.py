@@ -242,7 +242,9 @@ def test_dsk_solid_counts_known_answers(golden_dir):
 # tests/golden/truth_ref): the k values the reference's own truth files do not cover.  k <= 15 is the MiniKC path
 # (src/minikc/MiniKC.hpp:195-259: windows with non-ACGT characters are counted, and a read shorter than k replays the previous
 # read's k-mers); example_n holds N runs, lower case, short reads, multi-line FASTA, a FASTQ.gz and a paired sample.
-REF_TRUTH_CASES = [("example", 9), ("example", 15), ("example", 16), ("example_n", 12), ("example_n", 15), ("example_n", 21), ("example_n", 31)]
+REF_TRUTH_CASES = [("example", 9), ("example", 15), ("example", 16), ("example_n", 12), ("example_n", 15), ("example_n", 21), ("example_n", 31),
+                   # k > 31: Kmer<64> / LargeInt<2>, 128-bit k-mers
+                   ("example", 32), ("example", 41), ("example", 63), ("example_n", 41)]
 
 
 def ref_truth_dir(golden_dir, inp, k, t):
