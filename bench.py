@@ -545,7 +545,7 @@ def run_ours(a):
                    "k_partition2<count>": per["part_count_ms"], "k_partition2<scatter>": per["part_scatter_ms"],
                    "k_bin_count": per["bin_count_ms"], "k_merge": per["merge_ms"]}
         # a pass that did not run on this path (e.g. the exact K1 count pass) is not evidence: dropped
-        for n in [n for n in tms if tms[n] <= 5e-3 * max(tms.values()) and n != "k_merge"]:
+        for n in [n for n in tms if tms[n] <= 1e-2 * max(tms.values()) and n != "k_merge"]:
             tms.pop(n)
             alg.pop(n)
         peak, peak_src = hbm_peak()

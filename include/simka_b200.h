@@ -34,7 +34,7 @@ typedef struct simka_ctx simka_ctx;
 /* Replaces the argv of simkaCount / simkaMerge (src/SimkaCount.cpp:80-98, src/SimkaMerge.cpp:1530-1544):
  * -kmer-size, -nb-datasets, -abundance-min/-max, -simple-dist, -complex-dist. */
 typedef struct {
-    int32_t kmer_size;        /* 2..31 (span-32 k-mers, GC/kmer/impl/Model.hpp:100)                 */
+    int32_t kmer_size;        /* 2..63: span 32 (k <= 31, one word) and span 64 (k <= 63, LargeInt<2>) */
     int32_t nb_samples;       /* N, 1..8192                                                        */
     int64_t abundance_min;    /* keep a k-mer of a sample iff min <= count <= max                  */
     int64_t abundance_max;    /*   (src/minikc/MiniKC.hpp:56)                                       */
@@ -118,6 +118,9 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
  * decoded content of the solid/part_P/__p__I.gz files (src/SimkaCount.cpp:248-257).  Call with kmers=NULL to
  * get the size.  Only this shard's k-mers are returned when sharded. */
 int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers, uint32_t *counts, uint64_t *n);
+/* the same for 32 <= kmer_size <= 63 (Kmer<64>, LargeInt<2>: GC/tools/math/LargeInt2.pri): k-mers as (low word, high word),
+ * ascending as 128-bit integers */
+int simka_gpu_dump_sample_counts128(simka_ctx *ctx, int sample_id, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32_t *counts, uint64_t *n);
 
 /* ---- barrier between the stages: global per-sample totals -----------------------------------
  * (SimkaStatistics ctor reads count_synchro/<id>.ok of ALL samples, src/core/SimkaDistance.cpp:116-151)

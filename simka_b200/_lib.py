@@ -59,6 +59,7 @@ SYMBOLS = {
     "simka_gpu_push_ascii": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]),
     "simka_gpu_finish_sample": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SampleTotals)]),
     "simka_gpu_dump_sample_counts": (C.c_int, [C.c_void_p, C.c_int, u64p, u32p, u64p]),
+    "simka_gpu_dump_sample_counts128": (C.c_int, [C.c_void_p, C.c_int, u64p, u64p, u32p, u64p]),
     "simka_gpu_fine_bits": (C.c_int, [C.c_void_p]),
     "simka_gpu_export_sample": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p]),
     "simka_gpu_import_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_uint64]),

@@ -253,6 +253,13 @@ class SimkaGpu:
         return np.array([t.nb_reads, t.nb_distinct, t.nb_kmers, t.chord_n2], np.uint64)
 
     def dump_sample_counts(self, sample: int):
+        if self.kmer_size > 31:  # 128-bit k-mers: (n, 2) array of [low word, high word]
+            n = C.c_uint64(0)
+            self._check(self._L.simka_gpu_dump_sample_counts128(self._h, sample, None, None, None, C.byref(n)), "dump_sample_counts128")
+            lo, hi, ct = np.zeros(max(1, n.value), np.uint64), np.zeros(max(1, n.value), np.uint64), np.zeros(max(1, n.value), np.uint32)
+            self._check(self._L.simka_gpu_dump_sample_counts128(self._h, sample, lo.ctypes.data_as(_lib.u64p), hi.ctypes.data_as(_lib.u64p),
+                                                                ct.ctypes.data_as(_lib.u32p), C.byref(n)), "dump_sample_counts128")
+            return np.stack([lo[:n.value], hi[:n.value]], axis=1), ct[:n.value]
         n = C.c_uint64(0)
         self._check(self._L.simka_gpu_dump_sample_counts(self._h, sample, None, None, C.byref(n)), "dump_sample_counts")
         km = np.zeros(max(1, n.value), np.uint64)

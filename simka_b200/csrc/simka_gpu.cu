@@ -60,6 +60,7 @@ namespace {
 #include "kernels/superk2.cuh"
 #include "kernels/merge.cuh"
 #include "kernels/simkamin.cuh"
+#include "kernels/wide.cuh"
 
 }  // namespace
 
@@ -111,6 +112,7 @@ struct Arena {
 
 struct SampleData {
     uint64_t *eh = nullptr;   // hashed solid k-mers, grouped by fine range (arena memory)
+    K128 *ehw = nullptr;      // the same for k > 31 (16-byte keys; eh is unused then)
     uint32_t *ec = nullptr;
     uint64_t n = 0;
     uint32_t *off = nullptr;  // points into ctx->off_table
@@ -172,6 +174,8 @@ struct simka_ctx {
     bool force_exact = false;   // SIMKA_B200_EXACT_COUNT=1: always run the K1 count pass (tests of the fallback)
     bool use_superk = false;    // SIMKA_B200_SUPERK=1|2: super-k-mer front end of stage 1 (kernels/superk.cuh; 2 = records all the way, kernels/superk2.cuh)
     int superk_mode = 0;
+    bool wide = false;          // k > 31: 128-bit k-mers (kernels/wide.cuh)
+    Mix128 mix128;
     uint32_t sk2_target = 0;    // SIMKA_B200_SK2_TARGET: k-mers per counting bin of the record path (experiments; default SK2_TARGET)
     uint64_t exact_retries = 0, superk_samples = 0, superk_fallbacks = 0;
     uint64_t superk_cap_override = 0;
@@ -302,14 +306,17 @@ int simka_gpu_host_free(void *ptr) { return cudaFreeHost(ptr) == cudaSuccess ? S
 int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
     if (!out || !p) return SIMKA_ERR_INVALID;
     *out = nullptr;
-    if (p->kmer_size < 2 || p->kmer_size > 31 || p->nb_samples < 1 || p->nb_samples > MRG_MAXN) return SIMKA_ERR_INVALID;
+    if (p->kmer_size < 2 || p->kmer_size > 63 || p->nb_samples < 1 || p->nb_samples > MRG_MAXN) return SIMKA_ERR_INVALID;
+    if (p->kmer_size > 31 && (p->sketch_mode || p->shard_count > 1)) return SIMKA_ERR_INVALID;  // 128-bit k-mers: plain single-context runs only
     if (p->shard_count > 1 && (p->shard_rank < 0 || p->shard_rank >= p->shard_count)) return SIMKA_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || p->device < 0 || p->device >= ndev) return SIMKA_ERR_CUDA;
     if (cudaSetDevice(p->device) != cudaSuccess) return SIMKA_ERR_CUDA;
     simka_ctx *ctx = new simka_ctx();
     ctx->prm = *p;
-    ctx->kp.mix = simka::make_mix(p->kmer_size);
+    ctx->wide = p->kmer_size > 31;
+    ctx->kp.mix = simka::make_mix(ctx->wide ? 31 : p->kmer_size);
+    ctx->mix128 = make_mix128(p->kmer_size);
     ctx->kp.k = p->kmer_size;
     ctx->kp.shard_rank = p->shard_rank;
     ctx->kp.shard_count = p->shard_count > 1 ? p->shard_count : 1;
@@ -346,6 +353,7 @@ int simka_gpu_create(simka_ctx **out, const simka_params *p) try {
             ok = ok && cudaFuncSetAttribute(extract_instance(false, sh, bk), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(3 * MAX_B * 4 + 64 + L1_TILE * 8)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem_bytes(p->nb_samples)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_wide_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_merge_smem_bytes(p->nb_samples)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_sk2_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sk2Smem)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_sk2_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Sk2Smem)) == cudaSuccess;
     ok = ok && ctx->d_small.reserve(64) == 0;
@@ -515,9 +523,12 @@ int simka_gpu_push_ascii(simka_ctx *ctx, int sample_id, const char *seqs, const 
     return SIMKA_ERR_NOMEM;
 }
 
+static int finish_sample_wide(simka_ctx *ctx, int sample_id, simka_sample_totals *out);
+
 int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *out) try {
     if (!ctx) return SIMKA_ERR_INVALID;
     if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done) { ctx->set_error("bad sample id"); return SIMKA_ERR_INVALID; }
+    if (ctx->wide) return finish_sample_wide(ctx, sample_id, out);
     CK(cudaSetDevice(ctx->prm.device));
     cudaStream_t st = ctx->stream;
     SampleData &sd = ctx->samples[sample_id];
@@ -806,7 +817,150 @@ int simka_gpu_finish_sample(simka_ctx *ctx, int sample_id, simka_sample_totals *
     return SIMKA_ERR_NOMEM;
 }
 
+// stage 1 for k > 31 (kernels/wide.cuh): count pass, scan, scatter pass, per-bin count, compaction
+static int finish_sample_wide(simka_ctx *ctx, int sample_id, simka_sample_totals *out) {
+    CK(cudaSetDevice(ctx->prm.device));
+    cudaStream_t st = ctx->stream;
+    SampleData &sd = ctx->samples[sample_id];
+    InSlot *sl = nullptr;
+    for (auto &s : ctx->slots) if (s.sample == sample_id) sl = &s;
+    const uint64_t n_words = sl ? sl->words : 0, n_reads = sl ? sl->reads : 0, n_pos = n_words * 32;
+    const int W = 2 * ctx->prm.kmer_size;
+    if (ctx->fg_bits < 0) {
+        const uint64_t per_sample = ctx->prm.expected_kmers_per_sample ? ctx->prm.expected_kmers_per_sample : n_pos;
+        int fg = ilog2_ceil(std::max<uint64_t>(1, (per_sample / 4) * (uint64_t)ctx->prm.nb_samples / MRG_TARGET));
+        fg = std::min(fg, std::min(20, ilog2_floor(std::max<uint64_t>(1, per_sample / BIN_TARGET))));
+        while (fg > 0 && ((size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4) > ((size_t)2 << 30)) fg--;
+        ctx->fg_bits = fg;
+        const size_t tbl = (size_t)ctx->prm.nb_samples * (((size_t)1 << fg) + 1) * 4;
+        if (ctx->d_off_table.reserve(tbl)) { ctx->set_error("out of device memory (offset table)"); return SIMKA_ERR_NOMEM; }
+        CK(cudaMemsetAsync(ctx->d_off_table.p, 0, tbl, st));
+    }
+    int bin_bits = std::max(ilog2_floor(std::max<uint64_t>(1, n_pos / BIN_TARGET)), ctx->fg_bits);
+    bin_bits = std::max(std::min(bin_bits, std::min(W, 20)), ctx->fg_bits);
+    const uint32_t nbins = 1u << bin_bits;
+    const size_t fgn = ((size_t)1 << ctx->fg_bits) + 1;
+    sd.off = ctx->d_off_table.as<uint32_t>() + (size_t)sample_id * fgn;
+    ull *d_totals = ctx->d_small.as<ull>();
+    int *d_error = reinterpret_cast<int *>(ctx->d_small.as<char>() + 32);
+    uint32_t *d_big_n = reinterpret_cast<uint32_t *>(ctx->d_small.as<char>() + 40);
+    uint64_t h_keys = 0, h_surv = 0;
+    ull h_tot[3] = {0, 0, 0};
+    if (n_words > 0) {
+        const size_t nres = std::max<size_t>(nbins, (size_t)1 << ctx->fg_bits);
+        if (ctx->d_keysA.reserve(n_pos * 16) || ctx->d_keysB.reserve(n_pos * 16) || ctx->d_stage_c.reserve(n_pos * 4) || ctx->d_fine_hist.reserve(nres * 4) ||
+            ctx->d_fine_off.reserve((nres + 1) * 8) || ctx->d_fine_cursor.reserve(nres * 4) || ctx->d_surv.reserve(nres * 4) || ctx->d_out_off.reserve((nres + 1) * 8)) {
+            ctx->set_error("out of device memory (work buffers)");
+            return SIMKA_ERR_NOMEM;
+        }
+        CK(cudaStreamWaitEvent(st, sl->copied, 0));
+        const int evset = ctx->ev_cur;
+        harvest_timings(ctx, evset);
+        cudaEvent_t *ev = ctx->ev[evset];
+        CK(cudaEventRecord(ev[2 * T_NSTAGE], st));
+        CK(cudaMemsetAsync(d_totals, 0, 24, st));
+        CK(cudaMemsetAsync(ctx->d_fine_hist.p, 0, (size_t)nbins * 4, st));
+        CK(cudaMemsetAsync(ctx->d_fine_cursor.p, 0, (size_t)nbins * 4, st));
+        const uint64_t *seq = sl->ext_packed ? sl->ext_packed : sl->packed.as<uint64_t>();
+        const uint32_t *bad = sl->ext_bad ? sl->ext_bad : sl->bad.as<uint32_t>();
+        const unsigned g1 = (unsigned)((n_words + BLOCK - 1) / BLOCK);
+        CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT], st));
+        k_wide_extract<true><<<g1, BLOCK, 0, st>>>(seq, bad, n_words, ctx->prm.kmer_size, ctx->mix128, bin_bits, ctx->d_fine_hist.as<uint32_t>(), nullptr, nullptr, nullptr);
+        CK(cudaEventRecord(ev[2 * T_EXTRACT_COUNT + 1], st));
+        launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), nbins);
+        CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER], st));
+        k_wide_extract<false><<<g1, BLOCK, 0, st>>>(seq, bad, n_words, ctx->prm.kmer_size, ctx->mix128, bin_bits, nullptr, ctx->d_fine_off.as<uint64_t>(),
+                                                   ctx->d_fine_cursor.as<uint32_t>(), ctx->d_keysA.as<K128>());
+        CK(cudaEventRecord(ev[2 * T_EXTRACT_SCATTER + 1], st));
+        CK(cudaEventRecord(ev[2 * T_PART_COUNT], st)); CK(cudaEventRecord(ev[2 * T_PART_COUNT + 1], st));
+        CK(cudaEventRecord(ev[2 * T_PART_SCATTER], st)); CK(cudaEventRecord(ev[2 * T_PART_SCATTER + 1], st));
+        WideOut wo;
+        wo.stage_h = ctx->d_keysB.as<K128>(); wo.stage_c = ctx->d_stage_c.as<uint32_t>(); wo.surv = ctx->d_surv.as<uint32_t>();
+        wo.totals = d_totals; wo.error_flag = d_error;
+        CK(cudaEventRecord(ev[2 * T_BIN_COUNT], st));
+        k_wide_bin_count<<<(unsigned)std::min<uint64_t>(nbins, (uint64_t)ctx->nsm * 4), BLOCK, 0, st>>>(ctx->d_keysA.as<K128>(), ctx->d_fine_off.as<uint64_t>(), nbins,
+                                                                                                   ctx->prm.abundance_min, ctx->prm.abundance_max, wo);
+        CK(cudaEventRecord(ev[2 * T_BIN_COUNT + 1], st));
+        launch_scan(ctx, ctx->d_surv.as<uint32_t>(), ctx->d_out_off.as<uint64_t>(), nbins);
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+        int h_err = 0;
+        CK(cudaMemcpyAsync(&h_surv, ctx->d_out_off.as<uint64_t>() + nbins, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_keys, ctx->d_fine_off.as<uint64_t>() + nbins, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_tot, d_totals, 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_err, d_error, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_err) { ctx->set_error("on-chip table overflow in k_wide_bin_count (code " + std::to_string(h_err) + ")"); return SIMKA_ERR_OVERFLOW; }
+        CK(cudaEventRecord(sl->consumed, st));
+        sl->consumed_valid = true;
+        if (h_surv >= (1ull << 32)) { ctx->set_error("more than 2^32 solid k-mers in one sample"); return SIMKA_ERR_INVALID; }
+        CK(cudaEventRecord(ev[2 * T_COMPACT], st));
+        if (h_surv > 0) {
+            sd.ehw = (K128 *)ctx->arena.alloc(h_surv * 16);
+            sd.ec = (uint32_t *)ctx->arena.alloc(h_surv * 4);
+            if (!sd.ehw || !sd.ec) { ctx->set_error("out of device memory (sample list)"); return SIMKA_ERR_NOMEM; }
+            k_wide_compact<<<(unsigned)std::min<uint64_t>((nbins + 7) / 8, (uint64_t)ctx->nsm * 8), BLOCK, 0, st>>>(ctx->d_keysB.as<K128>(), ctx->d_stage_c.as<uint32_t>(),
+                                                                                                              ctx->d_fine_off.as<uint64_t>(), ctx->d_out_off.as<uint64_t>(), nbins, sd.ehw, sd.ec);
+            ctx->launches++;
+            if (ctx->prm.complex_dist) {
+                const unsigned gh = (unsigned)std::min<uint64_t>((h_surv + BLOCK * 16 - 1) / (BLOCK * 16), (uint64_t)ctx->nsm * 4);
+                k_abundance_hist<<<gh, BLOCK, 0, st>>>(sd.ec, h_surv, sample_id, ctx->d_chist.as<ull>() + (size_t)sample_id * CHIST, ctx->d_big_counts.as<uint32_t>(),
+                                                      ctx->d_big_sample.as<uint32_t>(), d_big_n, ctx->big_cap, d_error);
+                ctx->launches++;
+            }
+        }
+        const uint32_t fg = 1u << ctx->fg_bits;
+        k_fill_offsets<<<(fg + 1 + 255) / 256, 256, 0, st>>>(ctx->d_out_off.as<uint64_t>(), sd.off, fg, nbins >> ctx->fg_bits);
+        ctx->launches++;
+        CK(cudaEventRecord(ev[2 * T_COMPACT + 1], st));
+        CK(cudaEventRecord(ev[2 * T_NSTAGE + 1], st));
+        ctx->ev_pending[evset] = true;
+        ctx->ev_cur ^= 1;
+    }
+    sd.n = h_surv;
+    sd.done = true;
+    sd.local.nb_reads = n_reads;
+    sd.local.nb_distinct = h_tot[0];
+    sd.local.nb_kmers = h_tot[1];
+    sd.local.chord_n2 = h_tot[2];
+    if (!ctx->totals_overridden) ctx->global_totals[sample_id] = sd.local;
+    ctx->kmers_in += h_keys;
+    ctx->entries += h_surv;
+    if (sl) { sl->sample = -1; sl->words = sl->reads = 0; sl->ext_packed = nullptr; sl->ext_bad = nullptr; }
+    if (out) *out = sd.local;
+    return SIMKA_OK;
+}
+
+// k > 31: the per-sample (canonical k-mer, count) list as (low word, high word) pairs, ascending as 128-bit integers
+int simka_gpu_dump_sample_counts128(simka_ctx *ctx, int sample_id, uint64_t *kmers_lo, uint64_t *kmers_hi, uint32_t *counts, uint64_t *n) try {
+    if (!ctx || !n || !ctx->wide || sample_id < 0 || sample_id >= ctx->prm.nb_samples || !ctx->samples[sample_id].done) return SIMKA_ERR_INVALID;
+    CK(cudaSetDevice(ctx->prm.device));
+    SampleData &sd = ctx->samples[sample_id];
+    if (!kmers_lo || !kmers_hi || !counts) { *n = sd.n; return SIMKA_OK; }
+    if (*n < sd.n) { *n = sd.n; return SIMKA_ERR_INVALID; }
+    *n = sd.n;
+    if (sd.n == 0) return SIMKA_OK;
+    std::vector<uint64_t> lo(sd.n), hi(sd.n);
+    std::vector<uint32_t> hc(sd.n);
+    if (ctx->d_dump.reserve(sd.n * 16)) { ctx->set_error("out of device memory (dump)"); return SIMKA_ERR_NOMEM; }
+    uint64_t *d_lo = ctx->d_dump.as<uint64_t>(), *d_hi = d_lo + sd.n;
+    k_wide_unmix<<<(unsigned)((sd.n + 255) / 256), 256, 0, ctx->stream>>>(sd.ehw, d_lo, d_hi, sd.n, ctx->mix128);
+    CK(cudaMemcpyAsync(lo.data(), d_lo, sd.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hi.data(), d_hi, sd.n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hc.data(), sd.ec, sd.n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint64_t> order(sd.n);
+    for (uint64_t i = 0; i < sd.n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hi[a] != hi[b] ? hi[a] < hi[b] : lo[a] < lo[b]; });
+    for (uint64_t i = 0; i < sd.n; i++) { kmers_lo[i] = lo[order[i]]; kmers_hi[i] = hi[order[i]]; counts[i] = hc[order[i]]; }
+    return SIMKA_OK;
+} catch (const std::bad_alloc &) {  // nothing may throw across the C ABI
+    if (ctx) ctx->set_error("out of host memory");
+    return SIMKA_ERR_NOMEM;
+}
+
 int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers, uint32_t *counts, uint64_t *n) try {
+    if (ctx && ctx->wide) { ctx->set_error("k > 31: use simka_gpu_dump_sample_counts128"); return SIMKA_ERR_INVALID; }
     if (!ctx || !n || sample_id < 0 || sample_id >= ctx->prm.nb_samples || !ctx->samples[sample_id].done) return SIMKA_ERR_INVALID;
     CK(cudaSetDevice(ctx->prm.device));
     SampleData &sd = ctx->samples[sample_id];
@@ -836,6 +990,7 @@ int simka_gpu_dump_sample_counts(simka_ctx *ctx, int sample_id, uint64_t *kmers,
 int simka_gpu_fine_bits(simka_ctx *ctx) { return ctx ? ctx->fg_bits : -1; }
 
 int simka_gpu_export_sample(simka_ctx *ctx, int sample_id, const uint64_t **d_kmers, const uint32_t **d_counts, const uint32_t **d_off, uint64_t *n) {
+    if (ctx && ctx->wide) { ctx->set_error("k > 31: lists of 128-bit k-mers are not exported"); return SIMKA_ERR_INVALID; }
     if (!ctx || sample_id < 0 || sample_id >= ctx->prm.nb_samples || !ctx->samples[sample_id].done || ctx->fg_bits < 0) return SIMKA_ERR_INVALID;
     const SampleData &sd = ctx->samples[sample_id];
     CK(cudaSetDevice(ctx->prm.device));
@@ -850,6 +1005,7 @@ int simka_gpu_export_sample(simka_ctx *ctx, int sample_id, const uint64_t **d_km
 int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kmers, const uint32_t *d_counts, uint64_t n, const uint32_t *d_off,
                             int fine_bits, uint64_t nb_reads) {
     if (!ctx) return SIMKA_ERR_INVALID;
+    if (ctx->wide) { ctx->set_error("k > 31: lists of 128-bit k-mers are not imported"); return SIMKA_ERR_INVALID; }
     if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done || fine_bits < 0 || fine_bits > 24 || !d_off ||
         (n && (!d_kmers || !d_counts)) || n >= (1ull << 32)) { ctx->set_error("bad import arguments"); return SIMKA_ERR_INVALID; }
     CK(cudaSetDevice(ctx->prm.device));
@@ -898,6 +1054,7 @@ int simka_gpu_import_sample(simka_ctx *ctx, int sample_id, const uint64_t *d_kme
 // uploads them; after this the sample is exactly as if simka_gpu_finish_sample had produced it.
 int simka_gpu_import_counts(simka_ctx *ctx, int sample_id, const uint64_t *kmers, const uint32_t *counts, uint64_t n, uint64_t nb_reads) try {
     if (!ctx) return SIMKA_ERR_INVALID;
+    if (ctx->wide) { ctx->set_error("k > 31: lists of 128-bit k-mers are not imported"); return SIMKA_ERR_INVALID; }
     if (sample_id < 0 || sample_id >= ctx->prm.nb_samples || ctx->samples[sample_id].done || (n && (!kmers || !counts)) || n >= (1ull << 32)) {
         ctx->set_error("bad import arguments");
         return SIMKA_ERR_INVALID;
@@ -1034,7 +1191,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
     const int want_bits = ilog2_ceil(std::max<uint64_t>(1, total_entries / MRG_TARGET));
     int fg_eff = ctx->fg_bits;
     const uint32_t *off_eff = ctx->d_off_table.as<uint32_t>();
-    if (ctx->fg_bits >= 0 && (total_entries >> ctx->fg_bits) > (uint64_t)MRG_CAP && want_bits > ctx->fg_bits && !ctx->no_refine) {
+    if (ctx->fg_bits >= 0 && (total_entries >> ctx->fg_bits) > (uint64_t)MRG_CAP && want_bits > ctx->fg_bits && !ctx->no_refine && !ctx->wide) {
         int fg2 = std::min(want_bits, std::min(ctx->W, 24));
         while (fg2 > ctx->fg_bits && (size_t)N * (((size_t)1 << fg2) + 1) * 4 > ((size_t)4 << 30)) fg2--;
         if (fg2 > ctx->fg_bits) {
@@ -1081,7 +1238,7 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
     }
     // pointer tables
     std::vector<const void *> ptrs(2 * (size_t)N);
-    for (int s = 0; s < N; s++) { ptrs[s] = ctx->samples[s].eh; ptrs[N + s] = ctx->samples[s].ec; }
+    for (int s = 0; s < N; s++) { ptrs[s] = ctx->wide ? (const void *)ctx->samples[s].ehw : (const void *)ctx->samples[s].eh; ptrs[N + s] = ctx->samples[s].ec; }
     if (ctx->d_ptrs.reserve(ptrs.size() * sizeof(void *))) { ctx->set_error("out of device memory"); return SIMKA_ERR_NOMEM; }
     CK(cudaMemcpyAsync(ctx->d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
 
@@ -1127,7 +1284,12 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
         // keep comparable: "generic" = k_merge for any N, "tiled" = 32 x 32 sample tiles on k_merge_sm (N > 64)
         const char *mv = getenv("SIMKA_B200_MERGE");
         const bool want_generic = mv && !strcmp(mv, "generic"), want_tiled = mv && !strcmp(mv, "tiled");
-        if (N >= 2 && N <= MS_MAXN && !want_generic) {
+        if (ctx->wide) {  // k > 31: the generic merge on 16-byte keys
+            WideMergeArgs wa;
+            wa.m = a;
+            wa.ehw = reinterpret_cast<const K128 *const *>(ctx->d_ptrs.p);
+            k_wide_merge<<<grid, BLOCK, wide_merge_smem_bytes(N), st>>>(wa);
+        } else if (N >= 2 && N <= MS_MAXN && !want_generic) {
             void (*kern)(MergeArgs) = a.simple ? (a.complex_ ? k_merge_sm<true, true, false> : k_merge_sm<true, false, false>)
                                                : (a.complex_ ? k_merge_sm<false, true, false> : k_merge_sm<false, false, false>);
             int occ = 0;
@@ -1822,7 +1984,7 @@ static int xchg_post_data(simka_ctx *ctx, int t) {
 
 static int xchg_after_sample(simka_ctx *ctx, int sample_id) {
     const int N = ctx->prm.nb_samples, world = ctx->comm_world, rank = ctx->comm_rank;
-    if (sample_id % world != rank || ctx->kp.shard_count > 1 || ctx->kp.key_mode) return SIMKA_OK;
+    if (sample_id % world != rank || ctx->kp.shard_count > 1 || ctx->kp.key_mode || ctx->wide) return SIMKA_OK;
     const int t = sample_id / world;
     if (t >= N / world) return SIMKA_OK;  // a partial last round: exchanged by simka_gpu_exchange_and_merge (every rank is there)
     if (ctx->xr.empty() || ctx->x_recv_e.empty()) { const int rc = xchg_setup(ctx); if (rc != SIMKA_OK) return rc; }
@@ -1841,7 +2003,7 @@ int simka_gpu_exchange_and_merge(simka_ctx *ctx) try {
     if (!ctx) return SIMKA_ERR_INVALID;
 #if SIMKA_HAVE_NCCL_H
     if (!ctx->comm) { ctx->set_error("simka_gpu_comm_init has not run"); return SIMKA_ERR_INVALID; }
-    if (ctx->kp.shard_count > 1 || ctx->kp.key_mode) { ctx->set_error("exchange needs an unsharded counting context"); return SIMKA_ERR_INVALID; }
+    if (ctx->kp.shard_count > 1 || ctx->kp.key_mode || ctx->wide) { ctx->set_error("exchange needs an unsharded counting context with k <= 31"); return SIMKA_ERR_INVALID; }
     const int N = ctx->prm.nb_samples, world = ctx->comm_world, rank = ctx->comm_rank;
     ncclComm_t comm = (ncclComm_t)ctx->comm;
     CK(cudaSetDevice(ctx->prm.device));

@@ -119,8 +119,9 @@ Options parse_args(int argc, char **argv) {
     if (o.maxMemory < 500) throw bank::Exception("Please allocate more memory (minimum is 500 MB) with the option -max-memory");
     o.minShannon = std::max(o.minShannon, 0.0);
     o.minShannon = std::min(o.minShannon, 2.0);  // src/core/SimkaAlgorithm.cpp:202-204
-    if (o.kmerSize < 2 || o.kmerSize > 31)
-        throw bank::Exception("this build supports -kmer-size 2..31 (span 32); got " + std::to_string(o.kmerSize));
+    if (o.kmerSize < 2 || o.kmerSize > 63)
+        throw bank::Exception("this build supports -kmer-size 2..63 (spans 32 and 64); got " + std::to_string(o.kmerSize));
+    if (o.kmerSize > 31 && o.nbGpus > 1) throw bank::Exception("-nb-gpus needs -kmer-size <= 31");
     return o;
 }
 

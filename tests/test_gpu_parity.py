@@ -44,7 +44,8 @@ def test_example_csv_byte_identical(golden_dir, k, t):
     assert checked == 20
 
 
-@pytest.mark.parametrize("inp,k", [("example", 9), ("example", 15), ("example", 16), ("example_n", 12), ("example_n", 15), ("example_n", 21), ("example_n", 31)])
+@pytest.mark.parametrize("inp,k", [("example", 9), ("example", 15), ("example", 16), ("example_n", 12), ("example_n", 15), ("example_n", 21), ("example_n", 31),
+                                   ("example", 32), ("example", 41), ("example", 63), ("example_n", 41)])  # k > 31: 128-bit k-mers (kernels/wide.cuh)
 @pytest.mark.parametrize("t", [0, 2])
 def test_reference_run_truth_byte_identical(golden_dir, inp, k, t):
     """Truth produced by the reference binaries themselves (tools/make_ref_golden.py) for what its own truth files do not
@@ -61,7 +62,8 @@ def test_reference_run_truth_byte_identical(golden_dir, inp, k, t):
         assert [int(x) for x in st.totals[i]] == sync[ident], ident
 
 
-@pytest.mark.parametrize("inp,k,t", [("example_n", 15, 0), ("example_n", 12, 2), ("example_n", 31, 2), ("example", 16, 0)])
+@pytest.mark.parametrize("inp,k,t", [("example_n", 15, 0), ("example_n", 12, 2), ("example_n", 31, 2), ("example", 16, 0), ("example", 41, 2), ("example_n", 41, 0),
+                                     ("example", 63, 0)])
 def test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, t):
     """same, through the `simka` command line of this build (its own FASTA / FASTQ / gz readers)"""
     import gzip
@@ -81,7 +83,7 @@ def test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, 
     assert checked == 21
 
 
-@pytest.mark.parametrize("k,amin", [(31, 2), (21, 1), (15, 2), (9, 0)])
+@pytest.mark.parametrize("k,amin", [(31, 2), (21, 1), (15, 2), (9, 0), (32, 2), (45, 1), (63, 2)])
 def test_synthetic_per_sample_counts_and_stats(k, amin):
     samples = synthetic_samples(6, 3000)
     run = oracle_run(samples, k, amin)

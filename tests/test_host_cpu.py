@@ -177,15 +177,26 @@ def test_statistics_iadd():
 
 
 def test_pack_reads_minikc_rule():
-    """k <= 15: only the read separators are bad (the reference's MiniKC counts windows with non-ACGT characters)"""
+    """k <= 15: only the read separators are bad (the reference's MiniKC counts windows with non-ACGT characters), and a read
+    shorter than k is replaced by a copy of the previous long-enough read (its k-mer iterator keeps the previous read's k-mers:
+    simka_minikc_replay, pinned on reference runs in tests/golden/truth_ref/example_n_*)"""
     from helpers import reads_to_arrays
     seqs, off = reads_to_arrays([b"ACGTNNACGT", b"acgtxACG"])
     p31, b31, nw = simka_b200.pack_reads(seqs, off, kmer_size=31)
-    p15, b15, nw15 = simka_b200.pack_reads(seqs, off, kmer_size=15)
-    assert nw == nw15 == 1
-    np.testing.assert_array_equal(p31, p15)  # same codes, (c>>1)&3 for every character
+    p9, b9, nw9 = simka_b200.pack_reads(seqs, off, kmer_size=8)   # both reads hold a k-mer: nothing is replayed
+    assert nw == nw9 == 1
+    np.testing.assert_array_equal(p31, p9)  # same codes, (c>>1)&3 for every character
     bits31 = format(int(b31[0]), "032b")
-    bits15 = format(int(b15[0]), "032b")
+    bits9 = format(int(b9[0]), "032b")
     assert bits31[:20] == "00001100001" + "000010001"   # NN, separator, x, separator
-    assert bits15[:20] == "00000000001" + "000000001"   # separators only
-    assert bits31[20:] == bits15[20:] == "1" * 12        # padding
+    assert bits9[:20] == "00000000001" + "000000001"    # separators only
+    assert bits31[20:] == bits9[20:] == "1" * 12         # padding
+    # k = 9: the second read (8 bases) is shorter than k -> the first read again
+    seqs2, off2 = simka_b200.api.minikc_replay(seqs, off, 9)
+    assert bytes(seqs2) == b"ACGTNNACGT" * 2 and off2.tolist() == [0, 10, 20]
+    # a short read with nothing before it stays empty; k > 15 never replays
+    seqs3, off3 = simka_b200.api.minikc_replay(*reads_to_arrays([b"ACG", b"ACGTACGTAC", b"AC"]), 9)
+    assert bytes(seqs3) == b"ACGTACGTAC" * 2 and off3.tolist() == [0, 0, 10, 20]
+    s4, o4 = reads_to_arrays([b"ACG", b"ACGTACGTACGTACGTACGT"])
+    s5, o5 = simka_b200.api.minikc_replay(s4, o4, 16)
+    assert s5 is s4 and o5 is o4
