@@ -425,6 +425,25 @@ def test_simkamin_distance_edge_cases():
         np.testing.assert_array_equal(bc, obc, err_msg=f"s={s}")
 
 
+def test_simkamin_distance_unbalanced_sketches():
+    """sketches whose hashes are consumed at very different rates (the tile loader sizes its requests from the previous tile's
+    split): dense low ranges against sparse ones, interleaved blocks, one sketch entirely below the other"""
+    rng = np.random.default_rng(9)
+    s = 20000
+    dense = np.sort(rng.choice(np.arange(1, 40 * s, dtype=np.uint64), size=s, replace=False))            # small values, close together
+    sparse = np.unique(rng.integers(1, 2**40, size=2 * s, dtype=np.uint64))[:s]                          # 2^25 times sparser
+    blocks = np.sort(np.concatenate([np.arange(1 + b * 10**9, 1 + b * 10**9 + 2000, dtype=np.uint64) for b in range(10)]))  # runs of 2000, far apart
+    below = np.arange(1, s + 1, dtype=np.uint64)
+    above = np.arange(10**12, 10**12 + s, dtype=np.uint64)
+    mixed = np.sort(np.unique(np.concatenate([dense[::2], sparse[::2]]))[:s])
+    hashes = np.stack([dense, sparse, blocks, below, above, mixed])
+    counts = rng.integers(1, 50, size=hashes.shape, dtype=np.uint32)
+    jac, bc, _ = simka_b200.simkamin_distance(hashes, counts)
+    ojac, obc = oracle.simkamin_distance(hashes, counts)
+    np.testing.assert_array_equal(jac, ojac)
+    np.testing.assert_array_equal(bc, obc)
+
+
 def test_stage_binaries_reference_temp_formats(tmp_path, golden_dir):
     """simkaCount (one process per sample) + simkaMerge (one process per partition) of this build, exchanging the
     reference's temp files: solid/part_P/__p__I.gz records, count_synchro/*.ok, stats/part_P.gz
