@@ -295,7 +295,14 @@ constexpr int MS_SLOTS = 2048;
 constexpr int MS_ECAP = 2048;
 constexpr int MS_GCAP = 1024;
 constexpr int MS_MAXN = 64;
-constexpr int MS_NACC = 8;  // u64 accumulators per pair key: sh_ij, sh_ji, distinct, bc, chord, hellinger, whittaker (negated), JS (2^-60)
+// 32-bit accumulator words per pair key in shared memory: sh_ij, sh_ji, distinct, bc, chord, hellinger, whittaker (negated) as
+// (low 20 bits | units of 2^20), Jensen-Shannon (2^-60 fixed point) as (low 20 bits | units of 2^20).  Every add is below 2^20 and
+// needs no return value (a 64-bit shared atomicAdd is a CAS loop, and a lo/hi pair with an explicit carry needs the old value
+// back: 16 dependent atomics per pair in the first version).  A word that reaches 2^31 is moved to the global accumulator by the
+// sweep after each pass (at most MS_GCAP pairs per key and pass: < 2^30 added per pass, so a word never wraps); the rare
+// increment of 2^20 or more (abundances in the millions) goes straight to the global accumulator.
+constexpr int MS_NACC = 10;
+constexpr uint32_t MS_FAST = 1u << 20;
 
 struct MSSmem {
     alignas(16) uint64_t tk[MS_SLOTS];
@@ -310,18 +317,30 @@ struct MSSmem {
     uint32_t s_start[MS_MAXN], s_pre[MS_MAXN + 1];
     int s_gid[MS_MAXN];            // local sample slot -> global sample id
     uint8_t ge_s[MS_ECAP];
-    // followed by: uint32_t lo[MS_NACC][NP]; uint32_t hi[MS_NACC][NP];
+    // followed by: uint32_t acc[MS_NACC][NP];
 };
 static size_t ms_smem_bytes(int n) {
     const size_t np = n > MS_MAXN ? 1024 : (size_t)n * (n - 1) / 2;  // tiled: 32 x 32 pair keys
-    return ((sizeof(MSSmem) + 15) & ~(size_t)15) + (size_t)2 * MS_NACC * np * 4 + 16;
+    return ((sizeof(MSSmem) + 15) & ~(size_t)15) + (size_t)MS_NACC * np * 4 + 16;
 }
 
-__device__ __forceinline__ void ms_add64(uint32_t *lo, uint32_t *hi, uint32_t idx, unsigned long long v) {
-    const uint32_t vl = (uint32_t)v;
-    const uint32_t old = atomicAdd(&lo[idx], vl);
-    const uint32_t hv = (uint32_t)(v >> 32) + ((uint32_t)(old + vl) < old ? 1u : 0u);
-    if (hv) atomicAdd(&hi[idx], hv);
+// word w of pair key `key` (local sample slots li < lj of the tile) -> the global accumulators, value v in the word's unit
+__device__ __forceinline__ void ms_flush_word(const MergeArgs &a, int w, int i, int j, ull v) {
+    const size_t n = (size_t)a.n;
+    const size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
+    const size_t sym = (size_t)j + (n - 1) * i - ((size_t)i * (i - 1) / 2);
+    switch (w) {
+    case 0: atomicAdd(&a.nb_shared[ij], v); break;
+    case 1: atomicAdd(&a.nb_shared[ji], v); break;
+    case 2: atomicAdd(&a.distinct_shared[sym], v); break;
+    case 3: atomicAdd(&a.braycurtis[sym], v); break;
+    case 4: atomicAdd(&a.chord[ij], v); break;
+    case 5: atomicAdd(&a.hellinger[ij], v); break;
+    case 6: atomicAdd(&a.whittaker[ij], 0ull - v); break;           // accumulated negated
+    case 7: atomicAdd(&a.whittaker[ij], 0ull - (v << 20)); break;
+    case 8: atomicAdd(&a.klfix[ij], v); break;
+    default: atomicAdd(&a.klfix[ij], v << 20); break;
+    }
 }
 
 // TILED (N > 64): the sample pairs are cut into tiles of 32 x 32 samples (block I x block J, I <= J); a CTA works on
@@ -335,7 +354,7 @@ k_merge_sm(MergeArgs a) {
     MSSmem &S = *reinterpret_cast<MSSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int N = a.n;
-    uint32_t *acc_lo = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(MSSmem) + 15) & ~(size_t)15));
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(MSSmem) + 15) & ~(size_t)15));
     const uint32_t MG = 1u << a.mg_bits;
     const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
     const size_t ostride = ((size_t)1 << a.fg_bits) + 1;
@@ -357,9 +376,18 @@ k_merge_sm(MergeArgs a) {
         }
         const bool diag = !TILED || I == J;
         const int NPk = TILED ? (diag ? 496 : 1024) : N * (N - 1) / 2;  // pair keys of this tile
-        uint32_t *acc_hi = acc_lo + (size_t)MS_NACC * NPk;
         __syncthreads();  // the flush of the previous tile is done
-        for (int i = tid; i < 2 * MS_NACC * NPk; i += MS_THREADS) acc_lo[i] = 0;  // lo and hi are contiguous
+        for (int i = tid; i < MS_NACC * NPk; i += MS_THREADS) acc[i] = 0;
+        // pair key -> local sample slots (li < lj) of the tile
+        auto key_slots = [&](int key, int &li, int &lj) {
+            if (TILED && !diag) { li = key >> 5; lj = 32 + (key & 31); }
+            else {
+                const int n_loc = TILED ? 32 : N;
+                li = 0;
+                while ((li + 1) * (2 * n_loc - (li + 1) - 1) / 2 <= key) li++;
+                lj = li + 1 + (key - li * (2 * n_loc - li - 1) / 2);
+            }
+        };
         if (tid < MS_MAXN) {  // local sample slot -> global sample id (-1: unused)
             int gs = tid;
             if (TILED) gs = tid < 32 ? (int)(32 * I) + tid : (diag ? -1 : (int)(32 * J) + tid - 32);
@@ -526,14 +554,24 @@ k_merge_sm(MergeArgs a) {
                                 else if (diag) key = si * (63 - si) / 2 + (sj - si - 1);
                                 else key = si * 32 + (sj - 32);
                                 if (TILED) loc_pairs++;
-                                ms_add64(acc_lo + 0 * NPk, acc_hi + 0 * NPk, key, ci);
-                                ms_add64(acc_lo + 1 * NPk, acc_hi + 1 * NPk, key, cj);
-                                ms_add64(acc_lo + 2 * NPk, acc_hi + 2 * NPk, key, 1);
-                                ms_add64(acc_lo + 3 * NPk, acc_hi + 3 * NPk, key, ci < cj ? ci : cj);
+                                // adds below 2^20 go to the shared-memory words (no return value); anything larger -- abundances in
+                                // the millions -- straight to the global accumulators
+                                auto add = [&](int w, ull v) {
+                                    if (v < MS_FAST) atomicAdd(&acc[w * NPk + key], (uint32_t)v);
+                                    else ms_flush_word(a, w, S.s_gid[si], S.s_gid[sj], v);
+                                };
+                                auto add2 = [&](int w, ull v) {  // 64-bit value as (low 20 bits | units of 2^20)
+                                    if (v < ((ull)MS_FAST << 20)) { atomicAdd(&acc[w * NPk + key], (uint32_t)v & (MS_FAST - 1)); atomicAdd(&acc[(w + 1) * NPk + key], (uint32_t)(v >> 20)); }
+                                    else ms_flush_word(a, w, S.s_gid[si], S.s_gid[sj], v);  // (also a term that came out negative: 64-bit modular add)
+                                };
+                                add(0, ci);
+                                add(1, cj);
+                                atomicAdd(&acc[2 * NPk + key], 1u);
+                                add(3, ci < cj ? ci : cj);
                                 if (SIMPLE) {
                                     const ull prod = (ull)ci * (ull)cj;
-                                    ms_add64(acc_lo + 4 * NPk, acc_hi + 4 * NPk, key, prod);
-                                    ms_add64(acc_lo + 5 * NPk, acc_hi + 5 * NPk, key, hellinger_term(prod));  // u64 += double truncates per increment
+                                    add(4, prod);
+                                    add(5, hellinger_term(prod));  // u64 += double truncates per increment
                                 }
                                 if (COMPLEX) {
                                     const double ai = (double)ci, aj = (double)cj, Ni = S.ntot[si], Nj = S.ntot[sj];
@@ -544,11 +582,11 @@ k_merge_sm(MergeArgs a) {
                                         // pair, the reciprocals are per sample.  The term is >= 0 (Jensen) and < 2: exact integer accumulation
                                         // in units of 2^-60 (rounding 4e-19 per term, order-independent => bit-reproducible sums)
                                         const double num = fma(xY, tab_log(r1, S.logtab), yX * tab_log(2.0 - r1, S.logtab));
-                                        ms_add64(acc_lo + 7 * NPk, acc_hi + 7 * NPk, key, (ull)__double2ll_rn(num * (S.ninv30[si] * S.ninv30[sj])));
+                                        add2(8, (ull)__double2ll_rn(num * (S.ninv30[si] * S.ninv30[sj])));
                                     }
                                     const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
                                     // accumulated negated (the both-present value minus the two one-sided values is <= 0 in practice)
-                                    ms_add64(acc_lo + 6 * NPk, acc_hi + 6 * NPk, key, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
+                                    add2(6, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
                                 }
                             }
                             // advance
@@ -566,32 +604,28 @@ k_merge_sm(MergeArgs a) {
                     if (!TILED && tid == 0) loc_pairs += P;
                 }
                 __syncthreads();
+                // sweep: a word that has reached 2^31 moves to the global accumulator (see MS_NACC)
+                for (int i = tid; i < MS_NACC * NPk; i += MS_THREADS) {
+                    const uint32_t v = acc[i];
+                    if (v & 0x80000000u) {
+                        int li, lj;
+                        key_slots(i % NPk, li, lj);
+                        ms_flush_word(a, i / NPk, S.s_gid[li], S.s_gid[lj], v);
+                        acc[i] = 0;
+                    }
+                }
             }
         }
         __syncthreads();
         // flush: one set of global atomics per CTA, tile and pair key
         for (int key = tid; key < NPk; key += MS_THREADS) {
-            const ull dist = ((ull)acc_hi[2 * NPk + key] << 32) | acc_lo[2 * NPk + key];
-            if (!dist) continue;
-            int li, lj;  // local slots of the pair
-            if (TILED && !diag) { li = key >> 5; lj = 32 + (key & 31); }
-            else {
-                const int n_loc = TILED ? 32 : N;
-                li = 0;
-                while ((li + 1) * (2 * n_loc - (li + 1) - 1) / 2 <= key) li++;
-                lj = li + 1 + (key - li * (2 * n_loc - li - 1) / 2);
+            int li = -1, lj = -1;  // local slots of the pair, decoded for the first non-zero word
+            for (int w = 0; w < MS_NACC; w++) {
+                const uint32_t v = acc[w * NPk + key];
+                if (!v) continue;
+                if (li < 0) key_slots(key, li, lj);
+                ms_flush_word(a, w, S.s_gid[li], S.s_gid[lj], v);
             }
-            const int i = S.s_gid[li], j = S.s_gid[lj];
-            const size_t n = (size_t)N;
-            const size_t ij = (size_t)i * n + j, ji = (size_t)j * n + i;
-            const size_t sym = (size_t)j + (n - 1) * i - ((size_t)i * (i - 1) / 2);
-            auto val = [&](int w) { return ((ull)acc_hi[(size_t)w * NPk + key] << 32) | acc_lo[(size_t)w * NPk + key]; };
-            atomicAdd(&a.nb_shared[ij], val(0));
-            atomicAdd(&a.nb_shared[ji], val(1));
-            atomicAdd(&a.distinct_shared[sym], dist);
-            atomicAdd(&a.braycurtis[sym], val(3));
-            if (SIMPLE) { atomicAdd(&a.chord[ij], val(4)); atomicAdd(&a.hellinger[ij], val(5)); }
-            if (COMPLEX) { atomicAdd(&a.whittaker[ij], 0ull - val(6)); atomicAdd(&a.klfix[ij], val(7)); }
         }
     }
 #pragma unroll

@@ -41,6 +41,10 @@ __device__ __forceinline__ void block_sum3(ull &a, ull &b, ull &c, ull *tmp /*[3
 // wanted one (`o*` = elements to skip in shared memory) and the arrays carry 64 bytes of padding behind their last element
 // (simkamin_gpu_distance allocates them).  The prefetch is speculative (the tile may turn out to be the last): an
 // outstanding copy is always waited for before the CTA exits.
+// Measured (config 5, B200): 75.1 ms with plain LDG->STS tile loads, 59.5 ms with the double-buffered bulk copies.  A tile still
+// loads up to SMT_TILE elements of BOTH sketches although it consumes SMT_TILE merged ones; sizing the requests from the previous
+// tile's split (8 % instead of 100 % over-read, tile length found by two more binary searches) was tried and is SLOWER (71.8 ms):
+// the kernel is bound by the per-tile dependent chain, not by HBM traffic.
 struct SmtBuf {
     alignas(16) uint64_t a[SMT_TILE + 2], b[SMT_TILE + 2];
     alignas(16) uint32_t ca[SMT_TILE + 4], cb[SMT_TILE + 4];
@@ -48,7 +52,6 @@ struct SmtBuf {
 struct SmtSmem {
     SmtBuf buf[2];
     alignas(8) uint64_t bar[2];
-    uint32_t la[2], lb[2];   // elements of A / B loaded into each buffer
     ull red[24];
     uint32_t scan[BLOCK / 32 + 1];
     uint32_t xs, tstar;
@@ -83,13 +86,9 @@ k_simkamin_tiled(const uint64_t *__restrict__ hashes, const uint32_t *__restrict
     if (tid == 0) { mbar_init(&M.bar[0], 1); mbar_init(&M.bar[1], 1); mbar_fence_init(); }
     __syncthreads();
 
-    // thread 0: start the copies of the tile that begins at (a0, b0) into buffer `bf`, at most qa / qb elements of A / B;
-    // returns false when there is nothing to load.  A tile consumes SMT_TILE MERGED elements, i.e. about half of them from each
-    // sketch: loading SMT_TILE of both (the first version) moved twice the bytes the merge consumes.  The request follows
-    // the split of the previous tile plus a margin; a tile whose margin was too small simply ends earlier (see `tl` below).
-    auto issue = [&](uint32_t a0, uint32_t b0, int bf, uint32_t qa, uint32_t qb) -> bool {
-        const uint32_t la = min(na - a0, min(qa, (uint32_t)SMT_TILE)), lb = min(nb - b0, min(qb, (uint32_t)SMT_TILE));
-        M.la[bf] = la; M.lb[bf] = lb;
+    // thread 0: start the copies of the tile that begins at (a0, b0) into buffer `bf`; returns false when there is nothing to load
+    auto issue = [&](uint32_t a0, uint32_t b0, int bf) -> bool {
+        const uint32_t la = min(na - a0, (uint32_t)SMT_TILE), lb = min(nb - b0, (uint32_t)SMT_TILE);
         if (la + lb == 0) return false;
         const uint64_t ea = ea0 + a0, eb = eb0 + b0;
         const uint32_t ba = la ? (((uint32_t)(ea & 1) + la) * 8 + 15) & ~15u : 0, bb = lb ? (((uint32_t)(eb & 1) + lb) * 8 + 15) & ~15u : 0;
@@ -107,28 +106,16 @@ k_simkamin_tiled(const uint64_t *__restrict__ hashes, const uint32_t *__restrict
     uint32_t ph0 = 0, ph1 = 0;
     int cur = 0;
     bool pending_next = false;          // (thread 0) a prefetch into buffer cur ^ 1 is in flight
-    constexpr uint32_t MARGIN = 64;
-    if (tid == 0) issue(0, 0, 0, SMT_TILE / 2 + 2 * MARGIN, SMT_TILE / 2 + 2 * MARGIN);
+    if (tid == 0) issue(0, 0, 0);
     for (;;) {
         const uint32_t ra = na - a0, rb = nb - b0;
-        if (ra + rb == 0) break;  // (distinct == S at a tile end is NOT a stop: a duplicate B of the last A may open the next tile)
+        const uint32_t la = min(ra, (uint32_t)SMT_TILE), lb = min(rb, (uint32_t)SMT_TILE);
+        const uint32_t tl = min((uint32_t)SMT_TILE, ra + rb);
+        if (tl == 0) break;  // (distinct == S at a tile end is NOT a stop: a duplicate B of the last A may open the next tile)
         if (cur == 0) { mbar_wait(&M.bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&M.bar[1], ph1); ph1 ^= 1; }
         pending_next = false;
-        const uint32_t la = M.la[cur], lb = M.lb[cur];
         const uint64_t *sa = M.buf[cur].a + ((ea0 + a0) & 1), *sb = M.buf[cur].b + ((eb0 + b0) & 1);
         const uint32_t *ca = M.buf[cur].ca + ((ea0 + a0) & 3), *cb = M.buf[cur].cb + ((eb0 + b0) & 3);
-        // merged elements this tile may consume: everything up to the smaller of the last loaded values of the sketches that
-        // still have unloaded elements (hashes are distinct inside a sketch, so whatever is not loaded is larger than that)
-        uint32_t tl;
-        if (la == ra && lb == rb) tl = min((uint32_t)SMT_TILE, la + lb);
-        else {
-            const uint64_t m = min(la < ra ? sa[la - 1] : ~0ull, lb < rb ? sb[lb - 1] : ~0ull);
-            uint32_t lo = 0, hi = la;  // elements of A <= m
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sa[mid] <= m) lo = mid + 1; else hi = mid; }
-            uint32_t lo2 = 0, hi2 = lb;  // elements of B <= m
-            while (lo2 < hi2) { const uint32_t mid = (lo2 + hi2) >> 1; if (sb[mid] <= m) lo2 = mid + 1; else hi2 = mid; }
-            tl = min((uint32_t)SMT_TILE, lo + lo2);
-        }
         // merge-path split of this thread's diagonal: x = elements of A among the first d0 merged ones (A first on ties)
         const uint32_t d0 = min(tl, (uint32_t)tid * SMT_EPT), d1 = min(tl, d0 + SMT_EPT);
         uint32_t x;
@@ -143,8 +130,7 @@ k_simkamin_tiled(const uint64_t *__restrict__ hashes, const uint32_t *__restrict
             uint32_t lo = tl > lb ? tl - lb : 0, hi = min(tl, la);
             while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sa[mid] <= sb[tl - 1 - mid]) lo = mid + 1; else hi = mid; }
             M.xs = lo;
-            // (buffer cur ^ 1 was released by the barrier that ended the previous tile)
-            pending_next = issue(a0 + lo, b0 + (tl - lo), cur ^ 1, lo + MARGIN + (tl >> 4), (tl - lo) + MARGIN + (tl >> 4));
+            pending_next = issue(a0 + lo, b0 + (tl - lo), cur ^ 1);  // (buffer cur ^ 1 was released by the barrier that ended the previous tile)
         }
         // walk: matches are detected on the B copy (the A copy of a shared value precedes it)
         uint32_t t_match = 0;

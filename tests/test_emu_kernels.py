@@ -493,3 +493,34 @@ def test_single_sample_run():
         run = oracle_run(samples, k, 2)
         st = simka_b200.run_samples(samples, k, abundance_min=2)
         assert_stats_equal(st, run)
+
+
+def test_merge_huge_abundances_shared_memory_words_against_global_atomics(monkeypatch):
+    """k_merge_sm keeps 32-bit accumulator words in shared memory: increments below 2^20 are added there, a word that reaches 2^31
+    is swept to the global accumulator, anything larger goes to it directly (merge.cuh, MS_NACC).  Solid lists with abundances
+    around every threshold (imported, no reads needed), against the generic merge kernel that only uses 64-bit global atomics."""
+    rng = np.random.default_rng(17)
+    n, nk = 6, 9000
+    pool = rng.integers(0, 4**31, size=nk, dtype=np.uint64)
+    special = np.array([1, 2, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 1 << 26, (1 << 31) - 1, 1 << 31, (1 << 32) - 1], np.uint32)
+    lists = []
+    for s in range(n):
+        keep = rng.random(nk) < 0.7
+        km = np.unique(pool[keep])
+        ct = special[rng.integers(0, len(special), size=len(km))]
+        ct[rng.random(len(km)) < 0.5] = (1 << 20) - 1  # many adds just below the fast-path bound: words cross 2^31 and are swept
+        lists.append((km, ct))
+    results = {}
+    for variant in ("", "generic"):
+        if variant:
+            monkeypatch.setenv("SIMKA_B200_MERGE", variant)
+        ctx = simka_b200.SimkaGpu(n, 31, 1, simple_dist=True, complex_dist=True)
+        for s, (km, ct) in enumerate(lists):
+            ctx.import_counts(s, km, ct, nb_reads=10)
+        ctx.merge_and_accumulate()
+        results[variant] = ctx.stats()
+        ctx.close()
+    a, b = results[""], results["generic"]
+    for name in a.U64_SYM + a.U64_SQ:
+        np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)
+    np.testing.assert_allclose(a.kullback_leibler, b.kullback_leibler, rtol=1e-10, atol=0)

@@ -159,7 +159,7 @@ def test_cli_argument_handling(tmp_path):
     assert r.returncode == 1 and "does not exist" in r.stdout
     r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-max-memory", "100"], capture_output=True, text=True)
     assert r.returncode == 1 and "memory" in r.stdout
-    r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-kmer-size", "40"], capture_output=True, text=True)
+    r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-kmer-size", "64"], capture_output=True, text=True)
     assert r.returncode == 1 and "kmer-size" in r.stdout
 
 
