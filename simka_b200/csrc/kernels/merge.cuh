@@ -252,7 +252,13 @@ k_merge(MergeArgs a) {
     }
 }
 
-constexpr int MS_THREADS = 512;
+#ifndef SIMKA_MS_THREADS
+#define SIMKA_MS_THREADS 512
+#endif
+#ifndef SIMKA_MS_MINB
+#define SIMKA_MS_MINB 2
+#endif
+constexpr int MS_THREADS = SIMKA_MS_THREADS;
 constexpr uint32_t MS_SKIP = 0xFFFFFFFFu;
 
 __device__ __forceinline__ unsigned long long block_scan_u64(unsigned long long v, unsigned long long *tmp, unsigned long long *total) {
@@ -348,7 +354,7 @@ __device__ __forceinline__ void ms_flush_word(const MergeArgs &a, int w, int i, 
 // to the tile (cross pairs for I != J, all pairs for I == J) into 1024 (496) shared-memory accumulators.  Grouping
 // work is repeated once per tile a block takes part in (B+1 times for B blocks); the pair work is not.
 template <bool SIMPLE, bool COMPLEX, bool TILED>
-__global__ void __launch_bounds__(MS_THREADS, 2)
+__global__ void __launch_bounds__(MS_THREADS, SIMKA_MS_MINB)
 k_merge_sm(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MSSmem &S = *reinterpret_cast<MSSmem *>(smem_raw);
