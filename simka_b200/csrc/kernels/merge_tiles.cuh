@@ -1,0 +1,396 @@
+// kernels/merge_tiles.cuh -- stage 2 for 64 < N <= 512 samples: group once, accumulate per sample-pair tile in shared memory.
+// Part of the single translation unit simka_gpu.cu (included inside its anonymous namespace).
+//
+// With N > 64 the N(N-1)/2 pair accumulators no longer fit the shared memory of a CTA, and k_merge adds every pair term to
+// global memory: 8 atomics per pair, 28-36 G pair-updates/s, 90 % of configuration 4's step.  Here the work is split the way
+// the data wants it:
+//   k_group_bins   (once per merge bin)  the grouping phases of k_merge; instead of enumerating pairs it writes, for every k-mer
+//                  shared by >= 2 samples, a RECORD to a scratch buffer: the bitmap of the samples that hold it (one 32-bit
+//                  word per block of 32 samples) and its abundances in sample order (the rank of a sample inside its group is
+//                  the number of set bits below it, so no sort is needed).
+//   k_merge_tiles  one CTA per (tile of 32 x 32 samples, slice of the bins): it walks the records, picks the members of its two
+//                  sample blocks out of the bitmap words (two loads per k-mer), enumerates the tile's pairs flat over the
+//                  threads and adds them to tile-private accumulators in SHARED memory exactly as k_merge_sm does; one flush
+//                  per CTA and batch.
+// The scratch is the stage-1 work buffers (idle during the merge); when the records of all bins do not fit, the bins are
+// processed in batches cut on the host from the per-bin entry counts.
+// Reference: the same src/SimkaMerge.cpp:1164-1264,1307-1326 + src/core/SimkaAlgorithm.hpp:341-516 as k_merge.
+#pragma once
+
+constexpr int TM_MAXB = 16;        // sample blocks of 32: N <= 512
+constexpr int TM_GCAP = 512;       // shared groups one sub-pass of k_group_bins may hold (their bitmaps live in shared memory)
+constexpr int TM_THREADS = 512;
+static_assert(TM_THREADS == MS_THREADS, "k_merge_tiles uses block_scan_u64 of k_merge_sm");
+constexpr int TM_MCAP = 6144;      // member entries staged per chunk of TM_THREADS records (a record has <= 64 members of a tile)
+
+struct TileArgs {
+    MergeArgs m;
+    uint32_t bin0, bin1;           // bins [bin0, bin1) of this batch
+    const uint64_t *ebin;          // [MG + 1] exclusive prefix of the entries per bin
+    uint32_t *cnt;                 // scratch: abundances, region of bin b at ebin[b] - ebin[bin0]
+    uint32_t *grp;                 // scratch: records of (1 + nblk) words [offset of the abundances inside the bin's region, bitmap words],
+                                   //          region of bin b at ((ebin[b] - ebin[bin0]) / 2) records
+    uint32_t *hdr;                 // [bin1 - bin0] records written per bin
+    int nblk;                      // ceil(N / 32)
+};
+
+static size_t group_bins_smem_bytes(int n) {
+    return (size_t)MRG_SLOTS * 8 + (size_t)MRG_SLOTS * 4 * 2 + (size_t)MRG_SLOTS * 2 + (size_t)TM_GCAP * TM_MAXB * 4 + ((size_t)2 * n + 2) * 4 + 64;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+k_bin_entries(const uint32_t *__restrict__ off, int n, uint32_t MG, uint32_t q, size_t ostride, uint32_t *__restrict__ out) {
+    const uint32_t mb = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    if (mb >= MG) return;
+    uint32_t acc = 0;
+    for (int s = threadIdx.x & 31; s < n; s += 32) acc += off[(size_t)s * ostride + (size_t)(mb + 1) * q] - off[(size_t)s * ostride + (size_t)mb * q];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) out[mb] = acc;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+k_group_bins(TileArgs t) {
+    const MergeArgs &a = t.m;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *tk = reinterpret_cast<uint64_t *>(smem_raw);        // [MRG_SLOTS] table keys
+    uint32_t *gs = reinterpret_cast<uint32_t *>(tk + MRG_SLOTS);  // [MRG_SLOTS] group size, then packed (entry start | record index << 16)
+    uint32_t *gix = gs + MRG_SLOTS;                               // [MRG_SLOTS] copy of the packed prefix
+    uint32_t *bm = gix + MRG_SLOTS;                               // [TM_GCAP][nblk] sample bitmaps of the shared groups
+    uint32_t *s_start = bm + (size_t)TM_GCAP * TM_MAXB;           // [N]
+    uint32_t *s_pre = s_start + a.n;                              // [N + 1]
+    uint16_t *gsz = reinterpret_cast<uint16_t *>(s_pre + a.n + 2); // [MRG_SLOTS]
+    __shared__ uint32_t warp_tmp[16];
+    __shared__ uint32_t s_groups, s_shared, s_subtotal, s_rec, s_ent;
+    const int tid = threadIdx.x;
+    const int N = a.n, nblk = t.nblk;
+    const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
+    const size_t ostride = ((size_t)1 << a.fg_bits) + 1;
+    ull loc_groups = 0, loc_shared = 0;
+
+    for (uint32_t mb = t.bin0 + blockIdx.x; mb < t.bin1; mb += gridDim.x) {
+        __syncthreads();
+        for (int s = tid; s < N; s += BLOCK) {
+            const uint32_t b0 = a.off[(size_t)s * ostride + (size_t)mb * q];
+            const uint32_t b1 = a.off[(size_t)s * ostride + (size_t)(mb + 1) * q];
+            s_start[s] = b0;
+            s_pre[s] = b1 - b0;
+        }
+        if (tid == 0) { s_rec = 0; s_ent = 0; }
+        __syncthreads();
+        block_exclusive_scan(s_pre, N, warp_tmp);
+        const uint32_t n_e = warp_tmp[BLOCK / 32];
+        if (tid == 0) s_pre[N] = n_e;
+        __syncthreads();
+        const uint64_t region = t.ebin[mb] - t.ebin[t.bin0];
+        uint32_t *cnt_out = t.cnt + region;
+        uint32_t *grp_out = t.grp + (region / 2) * (uint64_t)(1 + nblk);
+        if (n_e == 0) { if (tid == 0) t.hdr[mb - t.bin0] = 0; continue; }
+        uint32_t R0 = 1;
+        if (n_e > MRG_CAP) { while ((uint64_t)R0 * (MRG_CAP / 2) < n_e) R0 <<= 1; }
+        uint32_t R = R0, r = 0;  // hash-selected sub-passes, split when one does not fit (as in k_merge)
+        bool more = true;
+        while (more) {
+            bool split = false;
+            __syncthreads();
+            for (int i = tid; i < MRG_SLOTS; i += BLOCK) { tk[i] = EMPTY; gs[i] = 0; }
+            for (int i = tid; i < TM_GCAP * nblk; i += BLOCK) bm[i] = 0;
+            if (tid == 0) { s_groups = 0; s_shared = 0; s_subtotal = 0; }
+            __syncthreads();
+            for (uint32_t i = tid; i < n_e; i += BLOCK) {  // phase 1: insert keys, count group sizes
+                int lo = 0, hi = N;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const uint64_t h = a.eh[lo][s_start[lo] + (i - s_pre[lo])];
+                const uint64_t hh = simka::hash2(h);
+                if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
+                for (int probes = 0; probes < MRG_SLOTS; probes++) {
+                    ull prev = atomicCAS(reinterpret_cast<ull *>(&tk[slot]), (ull)EMPTY, (ull)h);
+                    if (prev == EMPTY || prev == h) { atomicAdd(&gs[slot], 1u); break; }
+                    slot = (slot + 1) & (MRG_SLOTS - 1);
+                }
+            }
+            __syncthreads();
+            uint32_t my_groups = 0, my_shared = 0, my_total = 0;  // phase 2: group statistics; only groups with >= 2 samples get a record
+            for (int i = tid; i < MRG_SLOTS; i += BLOCK) {
+                const uint32_t g = gs[i];
+                gsz[i] = (uint16_t)g;
+                my_groups += g > 0;
+                my_shared += g > 1;
+                my_total += g;
+                gs[i] = g > 1 ? (g | (1u << 16)) : 0;  // entries (low 16 bits) and records (high bits) scanned together
+            }
+            if (my_groups) atomicAdd(&s_groups, my_groups);
+            if (my_shared) atomicAdd(&s_shared, my_shared);
+            if (my_total) atomicAdd(&s_subtotal, my_total);
+            __syncthreads();
+            block_exclusive_scan(gs, MRG_SLOTS, warp_tmp);
+            const uint32_t tot = warp_tmp[BLOCK / 32];
+            const uint32_t n_sub = tot & 0xFFFFu, n_rec = tot >> 16;
+            const uint32_t n_groups = s_groups, n_shared_groups = s_shared;
+            for (int i = tid; i < MRG_SLOTS; i += BLOCK) gix[i] = gs[i];
+            __syncthreads();
+#define TM_NEXT()                                                                                        \
+            do {                                                                                         \
+                if (split) { R <<= 1; }                                                                  \
+                else {                                                                                   \
+                    while (R > R0 && (r & (R >> 1))) { r -= R >> 1; R >>= 1; }                           \
+                    if (R == R0) { r++; if (r >= R0) more = false; }                                     \
+                    else r += R >> 1;                                                                    \
+                }                                                                                        \
+            } while (0)
+            // split when the table is nearly full, the bitmaps of the shared groups do not fit, or the packed scan's 16 bits of entries
+            // could overflow
+            const bool too_big = n_groups > (uint32_t)(MRG_SLOTS * 7 / 8) || n_rec > (uint32_t)TM_GCAP || s_subtotal > 0xFFFFu;
+            if (too_big && R < (1u << 24)) { split = true; TM_NEXT(); continue; }
+            if (too_big) { if (tid == 0) *a.error_flag = 4; TM_NEXT(); continue; }
+            if (tid == 0) { loc_groups += n_groups; loc_shared += n_shared_groups; }
+            if (n_rec == 0) { TM_NEXT(); continue; }
+            (void)n_sub;
+            const uint32_t rec0 = s_rec, ent0 = s_ent;  // records / abundances this bin has written so far
+            // phase 3a: sample bitmaps of the shared groups
+            for (uint32_t i = tid; i < n_e; i += BLOCK) {
+                int lo = 0, hi = N;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const uint64_t h = a.eh[lo][s_start[lo] + (i - s_pre[lo])];
+                const uint64_t hh = simka::hash2(h);
+                if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
+                int pr = 0;
+                while (tk[slot] != h && ++pr <= MRG_SLOTS) slot = (slot + 1) & (MRG_SLOTS - 1);
+                if (pr > MRG_SLOTS) { *a.error_flag = 7; continue; }
+                if (gsz[slot] < 2) continue;
+                atomicOr(&bm[(gix[slot] >> 16) * nblk + (lo >> 5)], 1u << (lo & 31));
+            }
+            __syncthreads();
+            // phase 3b: abundances in sample order (rank = set bits below the sample), records
+            for (uint32_t i = tid; i < n_e; i += BLOCK) {
+                int lo = 0, hi = N;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const size_t idx = s_start[lo] + (i - s_pre[lo]);
+                const uint64_t h = a.eh[lo][idx];
+                const uint64_t hh = simka::hash2(h);
+                if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
+                uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
+                int pr = 0;
+                while (tk[slot] != h && ++pr <= MRG_SLOTS) slot = (slot + 1) & (MRG_SLOTS - 1);
+                if (pr > MRG_SLOTS || gsz[slot] < 2) continue;
+                const uint32_t pk = gix[slot];
+                const uint32_t *w = bm + (pk >> 16) * nblk;
+                uint32_t rank = __popc(w[lo >> 5] & ((1u << (lo & 31)) - 1));
+                for (int b = 0; b < (lo >> 5); b++) rank += __popc(w[b]);
+                cnt_out[ent0 + (pk & 0xFFFFu) + rank] = a.ec[lo][idx];
+            }
+            for (int i = tid; i < MRG_SLOTS; i += BLOCK) {
+                if (gsz[i] < 2) continue;
+                const uint32_t pk = gix[i];
+                uint32_t *rec = grp_out + (uint64_t)(rec0 + (pk >> 16)) * (1 + nblk);
+                rec[0] = ent0 + (pk & 0xFFFFu);
+                for (int b = 0; b < nblk; b++) rec[1 + b] = bm[(pk >> 16) * nblk + b];
+            }
+            __syncthreads();
+            if (tid == 0) { s_rec = rec0 + n_rec; s_ent = ent0 + (tot & 0xFFFFu); }
+            TM_NEXT();
+        }
+#undef TM_NEXT
+        __syncthreads();
+        if (tid == 0) t.hdr[mb - t.bin0] = s_rec;
+    }
+    if (tid == 0 && (loc_groups | loc_shared)) {
+        atomicAdd(&a.scalars[0], loc_groups);
+        atomicAdd(&a.scalars[1], loc_shared);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile accumulation
+// ---------------------------------------------------------------------------------------------
+struct TMSmem {
+    alignas(16) double2 logtab[128];
+    alignas(16) unsigned long long scan_tmp[TM_THREADS / 32 + 1];
+    alignas(16) double ntot[64];
+    alignas(16) double ninv30[64];
+    uint32_t cg[TM_THREADS];          // per record of the chunk: member start (16 bits) | members of block I (8 bits) | of block J (8 bits)
+    uint32_t cgp[TM_THREADS + 1];     // pair prefix
+    uint32_t me_c[TM_MCAP];           // staged members: abundance
+    uint8_t me_s[TM_MCAP];            //                 local sample slot (0..31 block I, 32..63 block J)
+    int s_gid[64];
+    // followed by: uint32_t acc[MS_NACC][1024]
+};
+static size_t merge_tiles_smem_bytes() { return ((sizeof(TMSmem) + 15) & ~(size_t)15) + (size_t)MS_NACC * 1024 * 4 + 16; }
+
+template <bool SIMPLE, bool COMPLEX>
+__global__ void __launch_bounds__(TM_THREADS, 2)
+k_merge_tiles(TileArgs t, uint32_t slices) {
+    const MergeArgs &a = t.m;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TMSmem &S = *reinterpret_cast<TMSmem *>(smem_raw);
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(TMSmem) + 15) & ~(size_t)15));
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int N = a.n, nblk = t.nblk;
+    const uint32_t tile = blockIdx.x / slices, slice = blockIdx.x % slices;
+    uint32_t I = 0, J = 0;
+    { uint32_t rem = tile; while (rem >= (uint32_t)nblk - I) { rem -= (uint32_t)nblk - I; I++; } J = I + rem; }
+    const bool diag = I == J;
+    const int NPk = diag ? 496 : 1024;
+    if (tid < 128) S.logtab[tid] = a.logtab[tid];
+    for (int i = tid; i < MS_NACC * NPk; i += TM_THREADS) acc[i] = 0;
+    if (tid < 64) {
+        const int gsid = tid < 32 ? (int)(32 * I) + tid : (diag ? -1 : (int)(32 * J) + tid - 32);
+        const bool used = gsid >= 0 && gsid < N;
+        S.s_gid[tid] = used ? gsid : -1;
+        const double nt = used ? a.ntot[gsid] : 0.0;
+        S.ntot[tid] = nt;
+        S.ninv30[tid] = nt > 0.0 ? 1073741824.0 / nt : 0.0;
+    }
+    __syncthreads();
+    auto key_slots = [&](int key, int &li, int &lj) {
+        if (!diag) { li = key >> 5; lj = 32 + (key & 31); }
+        else {
+            li = 0;
+            while ((li + 1) * (2 * 32 - (li + 1) - 1) / 2 <= key) li++;
+            lj = li + 1 + (key - li * (2 * 32 - li - 1) / 2);
+        }
+    };
+    ull loc_pairs = 0;
+    const uint32_t nb = t.bin1 - t.bin0;
+    const uint32_t per = (nb + slices - 1) / slices;
+    const uint32_t sb0 = min(nb, slice * per), sb1 = min(nb, sb0 + per);
+    const uint32_t stride = 1 + nblk;
+    for (uint32_t lb = sb0; lb < sb1; lb++) {
+        const uint32_t n_rec = t.hdr[lb];
+        if (n_rec == 0) continue;
+        const uint64_t region = t.ebin[t.bin0 + lb] - t.ebin[t.bin0];
+        const uint32_t *cnt_in = t.cnt + region;
+        const uint32_t *grp_in = t.grp + (region / 2) * (uint64_t)stride;
+        for (uint32_t c0 = 0, c_step = TM_THREADS; c0 < n_rec; c0 += c_step) {
+            // one record per thread: members of block I and block J from two bitmap words
+            uint32_t wI = 0, wJ = 0, offI = 0, offJ = 0, e0 = 0;
+            const uint32_t rix = c0 + tid;
+            c_step = TM_THREADS;
+            if (rix < n_rec) {
+                const uint32_t *rec = grp_in + (uint64_t)rix * stride;
+                e0 = rec[0];
+                uint32_t run = 0;
+                for (int b = 0; b < nblk; b++) {
+                    const uint32_t w = rec[1 + b];
+                    if (b == (int)I) { wI = w; offI = run; }
+                    if (b == (int)J) { wJ = w; offJ = run; }
+                    run += __popc(w);
+                }
+            }
+            uint32_t nI = __popc(wI), nJ = diag ? 0u : __popc(wJ);
+            uint32_t pairs = diag ? nI * (nI - 1) / 2 : nI * nJ;
+            uint32_t mem = pairs ? nI + nJ : 0;
+            unsigned long long total, ex;
+            for (;;) {  // a chunk stages at most TM_MCAP members (a record has up to 64 in a tile): fewer records per chunk when needed
+                const bool in = (uint32_t)tid < c_step;
+                ex = block_scan_u64((in ? ((unsigned long long)pairs << 32) | mem : 0ull), S.scan_tmp, &total);
+                if ((uint32_t)total <= (uint32_t)TM_MCAP) break;
+                c_step >>= 1;
+            }
+            if ((uint32_t)tid >= c_step) { pairs = 0; mem = 0; nI = nJ = 0; }
+            const uint32_t P = (uint32_t)(total >> 32);
+            const uint32_t m0 = (uint32_t)ex, p0 = (uint32_t)(ex >> 32);
+            S.cg[tid] = m0 | (nI << 16) | (nJ << 24);
+            S.cgp[tid] = p0;
+            if (tid == 0) S.cgp[TM_THREADS] = P;
+            if (mem) {  // stage the members: abundances are in sample order, the rank of a member is its bit's position among the set bits
+                uint32_t pos = m0, w = wI, k = 0;
+                while (w) { const int bit = __ffs((int)w) - 1; w &= w - 1; S.me_s[pos] = (uint8_t)bit; S.me_c[pos] = cnt_in[e0 + offI + k]; pos++; k++; }
+                w = wJ; k = 0;
+                while (w) { const int bit = __ffs((int)w) - 1; w &= w - 1; S.me_s[pos] = (uint8_t)(32 + bit); S.me_c[pos] = cnt_in[e0 + offJ + k]; pos++; k++; }
+            }
+            __syncthreads();
+            // flat pair enumeration, one contiguous run of pairs per thread (as k_merge_sm)
+            const uint32_t perp = (P + TM_THREADS - 1) / TM_THREADS;
+            const uint32_t l0 = min(P, tid * perp), l1 = min(P, l0 + perp);
+            if (l0 < l1) {
+                int lo = 0, hi = TM_THREADS;  // cgp[lo] <= l0 < cgp[hi]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cgp[mid] <= l0) lo = mid; else hi = mid; }
+                uint32_t g = (uint32_t)lo;
+                uint32_t cgv = S.cg[g];
+                uint32_t st = cgv & 0xFFFF, gI = (cgv >> 16) & 0xFF, gJ = cgv >> 24;
+                uint32_t l = l0 - S.cgp[g];
+                uint32_t x, y;  // indices into the record's staged members: x in block I; y in block J (or > x in block I on the diagonal)
+                if (!diag) { x = l / gJ; y = gI + l % gJ; }
+                else {
+                    const float tg = 2.0f * (float)gI - 1.0f;
+                    int xi = (int)((tg - sqrtf(fmaxf(tg * tg - 8.0f * (float)l, 0.0f))) * 0.5f);
+                    if (xi > (int)gI - 2) xi = (int)gI - 2;
+                    if (xi < 0) xi = 0;
+                    while ((uint32_t)(xi + 1) * (2 * gI - (xi + 1) - 1) / 2 <= l) xi++;
+                    while ((uint32_t)xi * (2 * gI - xi - 1) / 2 > l) xi--;
+                    x = (uint32_t)xi;
+                    y = x + 1 + (l - x * (2 * gI - x - 1) / 2);
+                }
+                for (uint32_t p = l0; p < l1; p++) {
+                    const uint32_t si = S.me_s[st + x], sj = S.me_s[st + y];  // local slots, si < sj by construction
+                    const uint32_t ci = S.me_c[st + x], cj = S.me_c[st + y];
+                    const uint32_t key = diag ? si * (63 - si) / 2 + (sj - si - 1) : si * 32 + (sj - 32);
+                    auto add = [&](int w, ull v) {
+                        if (v < MS_FAST) atomicAdd(&acc[w * NPk + key], (uint32_t)v);
+                        else ms_flush_word(a, w, S.s_gid[si], S.s_gid[sj], v);
+                    };
+                    auto add2 = [&](int w, ull v) {
+                        if (v < ((ull)MS_FAST << 20)) { atomicAdd(&acc[w * NPk + key], (uint32_t)v & (MS_FAST - 1)); atomicAdd(&acc[(w + 1) * NPk + key], (uint32_t)(v >> 20)); }
+                        else ms_flush_word(a, w, S.s_gid[si], S.s_gid[sj], v);
+                    };
+                    add(0, ci);
+                    add(1, cj);
+                    atomicAdd(&acc[2 * NPk + key], 1u);
+                    add(3, ci < cj ? ci : cj);
+                    if (SIMPLE) {
+                        const ull prod = (ull)ci * (ull)cj;
+                        add(4, prod);
+                        add(5, hellinger_term(prod));
+                    }
+                    if (COMPLEX) {
+                        const double ai = (double)ci, aj = (double)cj, Ni = S.ntot[si], Nj = S.ntot[sj];
+                        const double yX = aj * Ni, xY = ai * Nj;
+                        if (xY != yX) {
+                            const double r1 = (2 * xY) * __drcp_rn(xY + yX);
+                            const double num = fma(xY, tab_log(r1, S.logtab), yX * tab_log(2.0 - r1, S.logtab));
+                            add2(8, (ull)__double2ll_rn(num * (S.ninv30[si] * S.ninv30[sj])));
+                        }
+                        const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
+                        add2(6, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
+                    }
+                    // advance inside the record, then to the next record with pairs
+                    bool next_rec = false;
+                    if (!diag) { if (++y == gI + gJ) { y = gI; if (++x == gI) next_rec = true; } }
+                    else { if (++y == gI) { if (++x == gI - 1) next_rec = true; y = x + 1; } }
+                    if (next_rec && p + 1 < l1) {
+                        do { g++; } while (S.cgp[g + 1] == S.cgp[g]);  // records without pairs in this tile
+                        cgv = S.cg[g]; st = cgv & 0xFFFF; gI = (cgv >> 16) & 0xFF; gJ = cgv >> 24;
+                        x = 0; y = diag ? 1 : gI;
+                    }
+                }
+            }
+            if (tid == 0) loc_pairs += P;
+            __syncthreads();
+            // sweep: a word that has reached 2^31 moves to the global accumulator (see MS_NACC; <= TM_THREADS pairs per key and chunk)
+            for (int i = tid; i < MS_NACC * NPk; i += TM_THREADS) {
+                const uint32_t v = acc[i];
+                if (v & 0x80000000u) {
+                    int li, lj;
+                    key_slots(i % NPk, li, lj);
+                    ms_flush_word(a, i / NPk, S.s_gid[li], S.s_gid[lj], v);
+                    acc[i] = 0;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int key = tid; key < NPk; key += TM_THREADS) {
+        int li = -1, lj = -1;
+        for (int w = 0; w < MS_NACC; w++) {
+            const uint32_t v = acc[w * NPk + key];
+            if (!v) continue;
+            if (li < 0) key_slots(key, li, lj);
+            ms_flush_word(a, w, S.s_gid[li], S.s_gid[lj], v);
+        }
+    }
+    if (tid == 0 && loc_pairs) atomicAdd(&a.scalars[2], loc_pairs);
+    (void)lane;
+}

@@ -59,6 +59,7 @@ namespace {
 #include "kernels/superk.cuh"
 #include "kernels/superk2.cuh"
 #include "kernels/merge.cuh"
+#include "kernels/merge_tiles.cuh"
 #include "kernels/simkamin.cuh"
 #include "kernels/wide.cuh"
 
@@ -1141,6 +1142,69 @@ int simka_gpu_set_totals(simka_ctx *ctx, const simka_sample_totals *in) {
     return SIMKA_OK;
 }
 
+// stage 2 for 64 < N <= 512 (kernels/merge_tiles.cuh): records of the shared k-mers (sample bitmap + abundances in sample order) are written
+// once per merge bin into the idle stage-1 work buffers, then one CTA per tile of 32 x 32 samples accumulates its pairs in shared
+// memory.  The bins are processed in batches that fit the scratch.
+static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
+    cudaStream_t st = ctx->stream;
+    const int N = a.n, nblk = (N + 31) / 32;
+    const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
+    const size_t ostride = ((size_t)1 << a.fg_bits) + 1;
+    // entries per bin and their prefix (host copy: the batches are cut here)
+    if (ctx->d_fine_hist.reserve((size_t)MG * 4) || ctx->d_fine_off.reserve(((size_t)MG + 1) * 8)) { ctx->set_error("out of device memory (tile merge)"); return SIMKA_ERR_NOMEM; }
+    k_bin_entries<<<(MG + BLOCK / 32 - 1) / (BLOCK / 32), BLOCK, 0, st>>>(a.off, N, MG, q, ostride, ctx->d_fine_hist.as<uint32_t>());
+    ctx->launches++;
+    if (launch_scan(ctx, ctx->d_fine_hist.as<uint32_t>(), ctx->d_fine_off.as<uint64_t>(), MG)) { ctx->set_error("out of device memory (tile merge)"); return SIMKA_ERR_NOMEM; }
+    std::vector<uint64_t> ebin((size_t)MG + 1);
+    CK(cudaMemcpyAsync(ebin.data(), ctx->d_fine_off.p, ((size_t)MG + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // scratch: abundances (4 B per entry of the batch) in keysA, records ((1 + nblk) words per 2 entries at most) in keysB
+    const size_t rec_words = 1 + (size_t)nblk;
+    uint64_t max_bin = 0;
+    for (uint32_t b = 0; b < MG; b++) max_bin = std::max(max_bin, ebin[b + 1] - ebin[b]);
+    uint64_t cap_e = std::min<uint64_t>(ctx->d_keysA.cap / 4, (ctx->d_keysB.cap / (4 * rec_words)) * 2);
+    const uint64_t want = std::max<uint64_t>(std::min<uint64_t>(ebin[MG], (uint64_t)64 << 20), max_bin + 2);
+    if (cap_e < want) {
+        if (ctx->d_keysA.reserve(want * 4) || ctx->d_keysB.reserve((want / 2 + 2) * rec_words * 4)) { ctx->set_error("out of device memory (tile merge scratch)"); return SIMKA_ERR_NOMEM; }
+        cap_e = std::min<uint64_t>(ctx->d_keysA.cap / 4, (ctx->d_keysB.cap / (4 * rec_words)) * 2);
+    }
+    cap_e -= 2;
+    { const char *e = getenv("SIMKA_B200_TILE_BATCH"); if (e) cap_e = std::min<uint64_t>(cap_e, std::max<uint64_t>(max_bin, strtoull(e, nullptr, 10))); }  // tests: force several batches
+    TileArgs t;
+    t.m = a;
+    t.ebin = ctx->d_fine_off.as<uint64_t>();
+    t.cnt = ctx->d_keysA.as<uint32_t>();
+    t.grp = ctx->d_keysB.as<uint32_t>();
+    t.nblk = nblk;
+    void (*kern)(TileArgs, uint32_t) = a.simple ? (a.complex_ ? k_merge_tiles<true, true> : k_merge_tiles<true, false>)
+                                                : (a.complex_ ? k_merge_tiles<false, true> : k_merge_tiles<false, false>);
+    const size_t smem_g = group_bins_smem_bytes(N), smem_t = merge_tiles_smem_bytes();
+    CK(cudaFuncSetAttribute(k_group_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    int occ_g = 0, occ_t = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, k_group_bins, BLOCK, smem_g));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, kern, TM_THREADS, smem_t));
+    const uint32_t tiles = (uint32_t)(nblk * (nblk + 1) / 2);
+    const uint32_t slices = std::max<uint32_t>(1, (uint32_t)(ctx->nsm * std::max(1, occ_t)) / tiles);
+    for (uint32_t b0 = 0; b0 < MG;) {
+        // largest b1 with ebin[b1] - ebin[b0] <= cap_e (at least one bin: every bin fits by construction)
+        uint32_t b1 = (uint32_t)(std::upper_bound(ebin.begin() + b0, ebin.end(), ebin[b0] + cap_e) - ebin.begin()) - 1;
+        b1 = std::max(b1, b0 + 1);
+        if (ebin[b1] > ebin[b0]) {
+            t.bin0 = b0; t.bin1 = b1;
+            if (ctx->d_surv.reserve((size_t)(b1 - b0) * 4)) { ctx->set_error("out of device memory (tile merge)"); return SIMKA_ERR_NOMEM; }
+            t.hdr = ctx->d_surv.as<uint32_t>();
+            const unsigned gg = (unsigned)std::min<uint64_t>(b1 - b0, (uint64_t)ctx->nsm * std::max(1, occ_g));
+            k_group_bins<<<gg, BLOCK, smem_g, st>>>(t);
+            kern<<<tiles * slices, TM_THREADS, smem_t, st>>>(t, slices);
+            ctx->launches += 2;
+        }
+        b0 = b1;
+    }
+    CK(cudaGetLastError());
+    return SIMKA_OK;
+}
+
 int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
     if (!ctx) return SIMKA_ERR_INVALID;
     const int N = ctx->prm.nb_samples;
@@ -1284,7 +1348,11 @@ int simka_gpu_merge_and_accumulate(simka_ctx *ctx) try {
         // keep comparable: "generic" = k_merge for any N, "tiled" = 32 x 32 sample tiles on k_merge_sm (N > 64)
         const char *mv = getenv("SIMKA_B200_MERGE");
         const bool want_generic = mv && !strcmp(mv, "generic"), want_tiled = mv && !strcmp(mv, "tiled");
-        if (ctx->wide) {  // k > 31: the generic merge on 16-byte keys
+        const bool want_records = mv ? !strcmp(mv, "records") : true;  // 64 < N <= 512: group once, accumulate per sample tile in shared memory
+        if (!ctx->wide && N > MS_MAXN && N <= 32 * TM_MAXB && want_records && !want_generic && !want_tiled) {
+            const int rc = merge_by_tiles(ctx, a, MG);
+            if (rc != SIMKA_OK) return rc;
+        } else if (ctx->wide) {  // k > 31: the generic merge on 16-byte keys
             WideMergeArgs wa;
             wa.m = a;
             wa.ehw = reinterpret_cast<const K128 *const *>(ctx->d_ptrs.p);

@@ -524,3 +524,27 @@ def test_merge_huge_abundances_shared_memory_words_against_global_atomics(monkey
     for name in a.U64_SYM + a.U64_SQ:
         np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)
     np.testing.assert_allclose(a.kullback_leibler, b.kullback_leibler, rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("n,batch", [(130, None), (96, "300")])
+def test_merge_by_sample_tiles(monkeypatch, n, batch):
+    """64 < N <= 512: records of the shared k-mers (sample bitmap + abundances in sample order) written once per merge bin, pairs
+    accumulated per tile of 32 x 32 samples in shared memory (merge_tiles.cuh) -- several sample blocks incl. a partial one,
+    batches forced small, against the oracle; and the same accumulators as the generic kernel"""
+    if batch:
+        monkeypatch.setenv("SIMKA_B200_TILE_BATCH", batch)
+    samples = synthetic_samples(n, 12, read_len=70, n_genomes=4, genome_len=400)
+    st = simka_b200.run_samples(samples, 21, abundance_min=1)
+    assert_stats_equal(st, oracle_run(samples, 21, 1))
+
+
+def test_merge_by_sample_tiles_everybody_shares(monkeypatch):
+    """150 samples holding the same k-mers: groups of 150 members (sub-passes split until a group's bitmap fits), every tile busy"""
+    monkeypatch.setenv("SIMKA_B200_REFINE", "0")
+    rng = np.random.default_rng(11)
+    read = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 120)]
+    one = (read.copy(), np.array([0, 120], np.uint64))
+    two = (np.concatenate([read, read[::-1].copy()]), np.array([0, 120, 240], np.uint64))
+    samples = [one if i % 3 else two for i in range(150)]
+    st = simka_b200.run_samples(samples, 31, abundance_min=1, simple_dist=True, complex_dist=True)
+    assert_stats_equal(st, oracle_run(samples, 31, 1))

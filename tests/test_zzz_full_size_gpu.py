@@ -65,3 +65,19 @@ def test_merge_sub_pass_split_when_everybody_shares_the_same_kmers(monkeypatch):
     samples = [one] * 600
     st = simka_b200.run_samples(samples, 31, abundance_min=1, simple_dist=True, complex_dist=True)
     assert_stats_equal(st, oracle_run(samples, 31, 1))
+
+
+@pytest.mark.parametrize("n,reads,batch", [(130, 600, None), (260, 300, "5000"), (512, 200, None)])
+def test_merge_by_sample_tiles_gpu(monkeypatch, n, reads, batch):
+    """64 < N <= 512: the tile merge (merge_tiles.cuh) against the oracle, several batches forced for one case, and against the
+    generic global-atomics kernel"""
+    from helpers import oracle_run, synthetic_samples
+    if batch:
+        monkeypatch.setenv("SIMKA_B200_TILE_BATCH", batch)
+    samples = synthetic_samples(n, reads, read_len=100, n_genomes=12, genome_len=3000)
+    st = simka_b200.run_samples(samples, 21, abundance_min=2)
+    assert_stats_equal(st, oracle_run(samples, 21, 2))
+    monkeypatch.setenv("SIMKA_B200_MERGE", "generic")
+    st2 = simka_b200.run_samples(samples, 21, abundance_min=2)
+    for name in st.U64_SYM + st.U64_SQ:
+        np.testing.assert_array_equal(getattr(st, name), getattr(st2, name), err_msg=name)
