@@ -298,7 +298,7 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
             if (mem) {  // stage the members: abundances are in sample order, the rank of a member is its bit's position among the set bits
                 uint32_t pos = m0, w = wI, k = 0;
                 while (w) { const int bit = __ffs((int)w) - 1; w &= w - 1; S.me_s[pos] = (uint8_t)bit; S.me_c[pos] = cnt_in[e0 + offI + k]; pos++; k++; }
-                w = wJ; k = 0;
+                w = diag ? 0u : wJ; k = 0;  // (a diagonal tile has one block: its members are staged once)
                 while (w) { const int bit = __ffs((int)w) - 1; w &= w - 1; S.me_s[pos] = (uint8_t)(32 + bit); S.me_c[pos] = cnt_in[e0 + offJ + k]; pos++; k++; }
             }
             __syncthreads();
