@@ -209,16 +209,28 @@ class RefBinaryRun:
         shutil.rmtree(self.dir, ignore_errors=True)
 
 
+def ref_sample_size(ref, a, per_run_s):
+    """reads per sample such that one run of the reference takes about per_run_s.  The reference pays seconds of process start-up and
+    polling per run whatever the input size, so the size is fitted on TWO calibration runs (fixed cost + cost per read) -- a single
+    small run would size the sample far too small and understate the reference's rate.  -> (reads, seconds spent calibrating)"""
+    c1, c2 = min(a.reads, 8_000), min(a.reads, 32_000)
+    t1 = ref.run_once(ref.write_inputs(c1))
+    if c2 == c1:
+        return c1, t1
+    t2 = ref.run_once(ref.write_inputs(c2))
+    per_read = max((t2 - t1) / (c2 - c1), 1e-7)
+    fixed = max(0.0, t1 - per_read * c1)
+    reads = int(min(a.reads, max(c2, (per_run_s - fixed) / per_read)))
+    return max(1000, reads // 1000 * 1000), t1 + t2
+
+
 def cpu_baseline_once(a, target_s=15.0):
     """bounded CPU baseline for our arm's line (N = 1): one run of the reference binaries (else the oracle port) of about target_s"""
     if RefBinaryRun.available():
         ref = RefBinaryRun(a)
         try:
-            cal = min(a.reads, 20_000)
-            t_cal = ref.run_once(ref.write_inputs(cal))
-            reads = int(min(a.reads, max(cal, cal * target_s / max(t_cal, 1e-3) * 0.8)))
-            reads = max(1000, reads // 1000 * 1000)
-            secs = ref.run_once(ref.write_inputs(reads)) if reads != cal else t_cal
+            reads, _ = ref_sample_size(ref, a, target_s)
+            secs = ref.run_once(ref.write_inputs(reads))
             return {"value": ref.kmers() / secs, "unit": "kmers/s", "cores": ref.cores, "kind": "reference", "sample": ref.sample_text(secs)}
         finally:
             ref.close()
@@ -242,11 +254,7 @@ def run_reference(a):
         try:
             reads = a.ref_reads
             if not reads:  # size the sample so that warmup + steps runs fit the budget
-                cal = min(a.reads, 20_000)
-                t_cal = ref.run_once(ref.write_inputs(cal))
-                per_run = max(2.0, (a.ref_budget_s - t_cal) / nrun * 0.85)
-                reads = int(min(a.reads, max(cal, cal * per_run / max(t_cal, 1e-3))))
-                reads = max(1000, reads // 1000 * 1000)
+                reads, t_cal = ref_sample_size(ref, a, max(2.0, (a.ref_budget_s - 15.0) / nrun * 0.9))
             ind = ref.write_inputs(reads)
             for it in range(nrun):
                 dt = ref.run_once(ind)

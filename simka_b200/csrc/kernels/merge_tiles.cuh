@@ -21,7 +21,12 @@ constexpr int TM_MAXB = 16;        // sample blocks of 32: N <= 512
 constexpr int TM_GCAP = 512;       // shared groups one sub-pass of k_group_bins may hold (their bitmaps live in shared memory)
 constexpr int TM_THREADS = 512;
 static_assert(TM_THREADS == MS_THREADS, "k_merge_tiles uses block_scan_u64 of k_merge_sm");
-constexpr int TM_MCAP = 6144;      // member entries staged per chunk of TM_THREADS records (a record has <= 64 members of a tile)
+constexpr int TM_MCAP = 6144;      // members staged per chunk (a record has <= 64 members of a tile)
+#ifndef SIMKA_TM_SWEEP_ENTRIES
+#define SIMKA_TM_SWEEP_ENTRIES 2047  // entries between two sweeps of the shared-memory words (k_merge_tiles)
+#endif
+constexpr int TM_RPT = 4;          // records a thread looks at per chunk
+constexpr int TM_ECAP = 1024;      // entries (records with pairs in the tile) per chunk
 
 struct TileArgs {
     MergeArgs m;
@@ -210,8 +215,8 @@ struct TMSmem {
     alignas(16) unsigned long long scan_tmp[TM_THREADS / 32 + 1];
     alignas(16) double ntot[64];
     alignas(16) double ninv30[64];
-    uint32_t cg[TM_THREADS];          // per record of the chunk: member start (16 bits) | members of block I (8 bits) | of block J (8 bits)
-    uint32_t cgp[TM_THREADS + 1];     // pair prefix
+    uint32_t cg[TM_ECAP];             // per entry of the chunk: member start (16 bits) | members of block I (8 bits) | of block J (8 bits)
+    uint32_t cgp[TM_ECAP + 1];        // pair prefix
     uint32_t me_c[TM_MCAP];           // staged members: abundance
     uint8_t me_s[TM_MCAP];            //                 local sample slot (0..31 block I, 32..63 block J)
     int s_gid[64];
@@ -257,62 +262,94 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
     const uint32_t per = (nb + slices - 1) / slices;
     const uint32_t sb0 = min(nb, slice * per), sb1 = min(nb, sb0 + per);
     const uint32_t stride = 1 + nblk;
+    uint32_t rpt = TM_RPT, step = TM_THREADS, since = 0;
     for (uint32_t lb = sb0; lb < sb1; lb++) {
         const uint32_t n_rec = t.hdr[lb];
         if (n_rec == 0) continue;
         const uint64_t region = t.ebin[t.bin0 + lb] - t.ebin[t.bin0];
         const uint32_t *cnt_in = t.cnt + region;
         const uint32_t *grp_in = t.grp + (region / 2) * (uint64_t)stride;
-        for (uint32_t c0 = 0, c_step = TM_THREADS; c0 < n_rec; c0 += c_step) {
-            // one record per thread: members of block I and block J from two bitmap words
-            uint32_t wI = 0, wJ = 0, offI = 0, offJ = 0, e0 = 0;
-            const uint32_t rix = c0 + tid;
-            c_step = TM_THREADS;
-            if (rix < n_rec) {
-                const uint32_t *rec = grp_in + (uint64_t)rix * stride;
-                e0 = rec[0];
-                uint32_t run = 0;
-                for (int b = 0; b < nblk; b++) {
-                    const uint32_t w = rec[1 + b];
-                    if (b == (int)I) { wI = w; offI = run; }
-                    if (b == (int)J) { wJ = w; offJ = run; }
-                    run += __popc(w);
+        // A chunk is rpt * step consecutive records (step < TM_THREADS only with rpt == 1): every thread looks at up to TM_RPT records and
+        // only those with pairs IN THIS TILE become entries -- with many sample blocks most records have none, and a chunk of one record
+        // per thread would spend its barriers on a handful of pairs.  The shape adapts: it shrinks until the entries (<= TM_ECAP) and
+        // their members (<= TM_MCAP) fit, and grows back when a chunk filled less than half of both.
+        for (uint32_t c0 = 0; c0 < n_rec;) {
+            uint32_t pm[TM_RPT];  // per record: pairs << 8 | members of the tile (0: not an entry)
+#pragma unroll
+            for (int k = 0; k < TM_RPT; k++) {
+                pm[k] = 0;
+                const uint32_t rix = c0 + (uint32_t)k * TM_THREADS + tid;
+                if ((uint32_t)k < rpt && (uint32_t)tid < step && rix < n_rec) {
+                    const uint32_t *rec = grp_in + (uint64_t)rix * stride;
+                    const uint32_t nI = __popc(rec[1 + I]), nJ = diag ? 0u : __popc(rec[1 + J]);
+                    const uint32_t pairs = diag ? nI * (nI - 1) / 2 : nI * nJ;
+                    if (pairs) pm[k] = (pairs << 8) | (nI + nJ);
                 }
             }
-            uint32_t nI = __popc(wI), nJ = diag ? 0u : __popc(wJ);
-            uint32_t pairs = diag ? nI * (nI - 1) / 2 : nI * nJ;
-            uint32_t mem = pairs ? nI + nJ : 0;
             unsigned long long total, ex;
-            for (;;) {  // a chunk stages at most TM_MCAP members (a record has up to 64 in a tile): fewer records per chunk when needed
-                const bool in = (uint32_t)tid < c_step;
-                ex = block_scan_u64((in ? ((unsigned long long)pairs << 32) | mem : 0ull), S.scan_tmp, &total);
-                if ((uint32_t)total <= (uint32_t)TM_MCAP) break;
-                c_step >>= 1;
+            for (;;) {
+                unsigned long long v = 0;  // pairs << 32 | entries << 20 | members
+#pragma unroll
+                for (int k = 0; k < TM_RPT; k++)
+                    if ((uint32_t)k < rpt && (uint32_t)tid < step && pm[k]) v += ((unsigned long long)(pm[k] >> 8) << 32) | (1u << 20) | (pm[k] & 0xFF);
+                ex = block_scan_u64(v, S.scan_tmp, &total);
+                if (((uint32_t)total & 0xFFFFF) <= (uint32_t)TM_MCAP && (((uint32_t)total >> 20) & 0xFFF) <= (uint32_t)TM_ECAP) break;
+                if (rpt > 1) rpt >>= 1; else step >>= 1;
             }
-            if ((uint32_t)tid >= c_step) { pairs = 0; mem = 0; nI = nJ = 0; }
-            const uint32_t P = (uint32_t)(total >> 32);
-            const uint32_t m0 = (uint32_t)ex, p0 = (uint32_t)(ex >> 32);
-            S.cg[tid] = m0 | (nI << 16) | (nJ << 24);
-            S.cgp[tid] = p0;
-            if (tid == 0) S.cgp[TM_THREADS] = P;
-            if (mem) {  // stage the members: abundances are in sample order, the rank of a member is its bit's position among the set bits
-                uint32_t pos = m0, w = wI, k = 0;
-                while (w) { const int bit = __ffs((int)w) - 1; w &= w - 1; S.me_s[pos] = (uint8_t)bit; S.me_c[pos] = cnt_in[e0 + offI + k]; pos++; k++; }
-                w = diag ? 0u : wJ; k = 0;  // (a diagonal tile has one block: its members are staged once)
-                while (w) { const int bit = __ffs((int)w) - 1; w &= w - 1; S.me_s[pos] = (uint8_t)(32 + bit); S.me_c[pos] = cnt_in[e0 + offJ + k]; pos++; k++; }
+            const uint32_t P = (uint32_t)(total >> 32), E = ((uint32_t)total >> 20) & 0xFFF, M = (uint32_t)total & 0xFFFFF;
+            // sweep (CTA-uniform decision): a word holds < 2^31 after a sweep and an entry adds < 2^20 to a word of a key at most once,
+            // so 2047 entries may pass between two sweeps before a word could wrap (see MS_NACC)
+            if (since + E > (uint32_t)SIMKA_TM_SWEEP_ENTRIES) {
+                for (int i = tid; i < MS_NACC * NPk; i += TM_THREADS) {
+                    const uint32_t v = acc[i];
+                    if (v & 0x80000000u) {
+                        int li, lj;
+                        key_slots(i % NPk, li, lj);
+                        ms_flush_word(a, i / NPk, S.s_gid[li], S.s_gid[lj], v);
+                        acc[i] = 0;
+                    }
+                }
+                since = 0;
+            }
+            since += E;
+            if (tid == 0) { S.cgp[E] = P; loc_pairs += P; }
+            {  // stage the entries of this thread: abundances are in sample order, the rank of a member is its bit's position among the set bits
+                uint32_t e = ((uint32_t)ex >> 20) & 0xFFF, pos = (uint32_t)ex & 0xFFFFF, pp = (uint32_t)(ex >> 32);
+#pragma unroll
+                for (int k = 0; k < TM_RPT; k++) {
+                    if (!((uint32_t)k < rpt && (uint32_t)tid < step && pm[k])) continue;
+                    const uint32_t *rec = grp_in + (uint64_t)(c0 + (uint32_t)k * TM_THREADS + tid) * stride;
+                    const uint32_t e0 = rec[0];
+                    uint32_t wI = 0, wJ = 0, offI = 0, offJ = 0, run = 0;
+                    for (uint32_t b = 0; b <= J; b++) {
+                        const uint32_t w = rec[1 + b];
+                        if (b == I) { wI = w; offI = run; }
+                        if (b == J) { wJ = w; offJ = run; }
+                        run += __popc(w);
+                    }
+                    const uint32_t nI = __popc(wI), nJ = diag ? 0u : __popc(wJ);
+                    S.cg[e] = pos | (nI << 16) | (nJ << 24);
+                    S.cgp[e] = pp;
+                    e++;
+                    pp += pm[k] >> 8;
+                    uint32_t w = wI, q = 0;
+                    while (w) { const int bit = __ffs((int)w) - 1; w &= w - 1; S.me_s[pos] = (uint8_t)bit; S.me_c[pos] = cnt_in[e0 + offI + q]; pos++; q++; }
+                    w = diag ? 0u : wJ; q = 0;  // (a diagonal tile has one block: its members are staged once)
+                    while (w) { const int bit = __ffs((int)w) - 1; w &= w - 1; S.me_s[pos] = (uint8_t)(32 + bit); S.me_c[pos] = cnt_in[e0 + offJ + q]; pos++; q++; }
+                }
             }
             __syncthreads();
             // flat pair enumeration, one contiguous run of pairs per thread (as k_merge_sm)
             const uint32_t perp = (P + TM_THREADS - 1) / TM_THREADS;
             const uint32_t l0 = min(P, tid * perp), l1 = min(P, l0 + perp);
             if (l0 < l1) {
-                int lo = 0, hi = TM_THREADS;  // cgp[lo] <= l0 < cgp[hi]
+                int lo = 0, hi = (int)E;  // cgp[lo] <= l0 < cgp[hi]
                 while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cgp[mid] <= l0) lo = mid; else hi = mid; }
                 uint32_t g = (uint32_t)lo;
                 uint32_t cgv = S.cg[g];
                 uint32_t st = cgv & 0xFFFF, gI = (cgv >> 16) & 0xFF, gJ = cgv >> 24;
                 uint32_t l = l0 - S.cgp[g];
-                uint32_t x, y;  // indices into the record's staged members: x in block I; y in block J (or > x in block I on the diagonal)
+                uint32_t x, y;  // indices into the entry's staged members: x in block I; y in block J (or > x in block I on the diagonal)
                 if (!diag) { x = l / gJ; y = gI + l % gJ; }
                 else {
                     const float tg = 2.0f * (float)gI - 1.0f;
@@ -356,28 +393,22 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
                         const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
                         add2(6, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
                     }
-                    // advance inside the record, then to the next record with pairs
+                    // advance inside the entry, then to the next one (every entry has pairs)
                     bool next_rec = false;
                     if (!diag) { if (++y == gI + gJ) { y = gI; if (++x == gI) next_rec = true; } }
                     else { if (++y == gI) { if (++x == gI - 1) next_rec = true; y = x + 1; } }
                     if (next_rec && p + 1 < l1) {
-                        do { g++; } while (S.cgp[g + 1] == S.cgp[g]);  // records without pairs in this tile
+                        g++;
                         cgv = S.cg[g]; st = cgv & 0xFFFF; gI = (cgv >> 16) & 0xFF; gJ = cgv >> 24;
                         x = 0; y = diag ? 1 : gI;
                     }
                 }
             }
-            if (tid == 0) loc_pairs += P;
-            __syncthreads();
-            // sweep: a word that has reached 2^31 moves to the global accumulator (see MS_NACC; <= TM_THREADS pairs per key and chunk)
-            for (int i = tid; i < MS_NACC * NPk; i += TM_THREADS) {
-                const uint32_t v = acc[i];
-                if (v & 0x80000000u) {
-                    int li, lj;
-                    key_slots(i % NPk, li, lj);
-                    ms_flush_word(a, i / NPk, S.s_gid[li], S.s_gid[lj], v);
-                    acc[i] = 0;
-                }
+            // (no barrier here: the scan of the next chunk has three before anything staged is overwritten)
+            c0 += rpt * step;
+            if (2 * M <= (uint32_t)TM_MCAP && 2 * E <= (uint32_t)TM_ECAP) {
+                if (step < (uint32_t)TM_THREADS) step <<= 1;
+                else if (rpt < (uint32_t)TM_RPT) rpt <<= 1;
             }
         }
     }

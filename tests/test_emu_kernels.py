@@ -526,6 +526,40 @@ def test_merge_huge_abundances_shared_memory_words_against_global_atomics(monkey
     np.testing.assert_allclose(a.kullback_leibler, b.kullback_leibler, rtol=1e-10, atol=0)
 
 
+def test_merge_tiles_huge_abundances_and_rare_sweeps(monkeypatch):
+    """k_merge_tiles sweeps its shared-memory words only when 2047 entries have passed since the last sweep (merge_tiles.cuh): 70 samples
+    of which three hold thousands of k-mers with abundances around every threshold (so that words cross 2^31 between sweeps and
+    single adds bypass the words), the others a sprinkling of them -- against the generic kernel (64-bit global atomics only)."""
+    rng = np.random.default_rng(23)
+    n, nk = 70, 12000
+    pool = rng.integers(0, 4**31, size=nk, dtype=np.uint64)
+    special = np.array([1, 2, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 1 << 26, (1 << 31) - 1, 1 << 31, (1 << 32) - 1], np.uint32)
+    lists = []
+    for s in range(n):
+        heavy = s in (0, 1, 40)
+        km = np.unique(pool[rng.random(nk) < (0.9 if heavy else 0.02)])
+        if heavy:
+            ct = special[rng.integers(0, len(special), size=len(km))]
+            ct[rng.random(len(km)) < 0.75] = (1 << 20) - 1  # > 4096 such adds per word and pair: a word would wrap without the sweeps
+        else:
+            ct = rng.integers(1, 5, size=len(km)).astype(np.uint32)
+        lists.append((km, ct))
+    results = {}
+    for variant in ("", "generic"):
+        if variant:
+            monkeypatch.setenv("SIMKA_B200_MERGE", variant)
+        ctx = simka_b200.SimkaGpu(n, 31, 1, simple_dist=True, complex_dist=True)
+        for s, (km, ct) in enumerate(lists):
+            ctx.import_counts(s, km, ct, nb_reads=10)
+        ctx.merge_and_accumulate()
+        results[variant] = ctx.stats()
+        ctx.close()
+    a, b = results[""], results["generic"]
+    for name in a.U64_SYM + a.U64_SQ:
+        np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)
+    np.testing.assert_allclose(a.kullback_leibler, b.kullback_leibler, rtol=1e-10, atol=0)
+
+
 @pytest.mark.parametrize("n,batch", [(130, None), (96, "300")])
 def test_merge_by_sample_tiles(monkeypatch, n, batch):
     """64 < N <= 512: records of the shared k-mers (sample bitmap + abundances in sample order) written once per merge bin, pairs

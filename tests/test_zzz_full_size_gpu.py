@@ -81,3 +81,36 @@ def test_merge_by_sample_tiles_gpu(monkeypatch, n, reads, batch):
     st2 = simka_b200.run_samples(samples, 21, abundance_min=2)
     for name in st.U64_SYM + st.U64_SQ:
         np.testing.assert_array_equal(getattr(st, name), getattr(st2, name), err_msg=name)
+
+
+def test_merge_tiles_huge_abundances_gpu(monkeypatch):
+    """the tile merge's shared-memory words and their rare sweeps (merge_tiles.cuh, SIMKA_TM_SWEEP_ENTRIES) with abundances around every
+    threshold: 200 samples, eight of them heavy with hundreds of thousands of k-mers, against the generic kernel (64-bit global atomics)"""
+    rng = np.random.default_rng(29)
+    n, nk = 200, 400_000
+    pool = rng.integers(0, 4**31, size=nk, dtype=np.uint64)
+    special = np.array([1, 2, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 1 << 26, (1 << 31) - 1, 1 << 31, (1 << 32) - 1], np.uint32)
+    lists = []
+    for s in range(n):
+        heavy = s % 25 == 0
+        km = np.unique(pool[rng.random(nk) < (0.9 if heavy else 0.01)])
+        if heavy:
+            ct = special[rng.integers(0, len(special), size=len(km))]
+            ct[rng.random(len(km)) < 0.75] = (1 << 20) - 1
+        else:
+            ct = rng.integers(1, 5, size=len(km)).astype(np.uint32)
+        lists.append((km, ct))
+    results = {}
+    for variant in ("", "generic"):
+        if variant:
+            monkeypatch.setenv("SIMKA_B200_MERGE", variant)
+        ctx = simka_b200.SimkaGpu(n, 31, 1, simple_dist=True, complex_dist=True)
+        for s, (km, ct) in enumerate(lists):
+            ctx.import_counts(s, km, ct, nb_reads=10)
+        ctx.merge_and_accumulate()
+        results[variant] = ctx.stats()
+        ctx.close()
+    a, b = results[""], results["generic"]
+    for name in a.U64_SYM + a.U64_SQ:
+        np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)
+    np.testing.assert_allclose(a.kullback_leibler, b.kullback_leibler, rtol=1e-10, atol=0)
