@@ -611,6 +611,10 @@ def run_simkamin(a, torch):
         return
     n, s = a.samples, a.reads
     hashes, counts = synth.make_sketches(n, s)
+    # the sketches live in pinned host memory (as the packed reads of the k-mer configurations do): the library's cudaMemcpy of a
+    # pageable 1.5 GB would be staged through the driver's bounce buffer at a fifth of the PCIe rate
+    pin_h, pin_c = torch.from_numpy(hashes).pin_memory(), torch.from_numpy(counts).pin_memory()
+    hashes, counts = pin_h.numpy(), pin_c.numpy()
     pairs = n * (n - 1) // 2
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()

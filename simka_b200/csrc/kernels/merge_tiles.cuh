@@ -33,9 +33,11 @@ struct TileArgs {
     uint32_t bin0, bin1;           // bins [bin0, bin1) of this batch
     const uint64_t *ebin;          // [MG + 1] exclusive prefix of the entries per bin
     uint32_t *cnt;                 // scratch: abundances, region of bin b at ebin[b] - ebin[bin0]
-    uint32_t *grp;                 // scratch: records of (1 + nblk) words [offset of the abundances inside the bin's region, bitmap words],
-                                   //          region of bin b at ((ebin[b] - ebin[bin0]) / 2) records
-    uint32_t *hdr;                 // [bin1 - bin0] records written per bin
+    uint32_t *grp;                 // scratch: DENSE records of (1 + nblk) words [offset of the abundances in cnt, bitmap words]; a sub-pass of
+                                   //          k_group_bins claims the space of its records from the cursor (their order does not matter)
+    uint32_t *hdr;                 // [1] record cursor = records of the batch (zeroed before k_group_bins)
+    uint32_t rec_cap;              // records the scratch holds: word w of record r lives at grp[w * rec_cap + r] (a tile reads two of
+                                   // the words of every record: consecutive threads, consecutive addresses)
     int nblk;                      // ceil(N / 32)
 };
 
@@ -66,7 +68,7 @@ k_group_bins(TileArgs t) {
     uint32_t *s_pre = s_start + a.n;                              // [N + 1]
     uint16_t *gsz = reinterpret_cast<uint16_t *>(s_pre + a.n + 2); // [MRG_SLOTS]
     __shared__ uint32_t warp_tmp[16];
-    __shared__ uint32_t s_groups, s_shared, s_subtotal, s_rec, s_ent;
+    __shared__ uint32_t s_groups, s_shared, s_subtotal, s_base, s_ent;
     const int tid = threadIdx.x;
     const int N = a.n, nblk = t.nblk;
     const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
@@ -81,16 +83,15 @@ k_group_bins(TileArgs t) {
             s_start[s] = b0;
             s_pre[s] = b1 - b0;
         }
-        if (tid == 0) { s_rec = 0; s_ent = 0; }
+        if (tid == 0) s_ent = 0;
         __syncthreads();
         block_exclusive_scan(s_pre, N, warp_tmp);
         const uint32_t n_e = warp_tmp[BLOCK / 32];
         if (tid == 0) s_pre[N] = n_e;
         __syncthreads();
-        const uint64_t region = t.ebin[mb] - t.ebin[t.bin0];
+        const uint32_t region = (uint32_t)(t.ebin[mb] - t.ebin[t.bin0]);  // (a batch has < 2^32 entries: its abundances fit the scratch)
         uint32_t *cnt_out = t.cnt + region;
-        uint32_t *grp_out = t.grp + (region / 2) * (uint64_t)(1 + nblk);
-        if (n_e == 0) { if (tid == 0) t.hdr[mb - t.bin0] = 0; continue; }
+        if (n_e == 0) continue;
         uint32_t R0 = 1;
         if (n_e > MRG_CAP) { while ((uint64_t)R0 * (MRG_CAP / 2) < n_e) R0 <<= 1; }
         uint32_t R = R0, r = 0;  // hash-selected sub-passes, split when one does not fit (as in k_merge)
@@ -152,7 +153,8 @@ k_group_bins(TileArgs t) {
             if (tid == 0) { loc_groups += n_groups; loc_shared += n_shared_groups; }
             if (n_rec == 0) { TM_NEXT(); continue; }
             (void)n_sub;
-            const uint32_t rec0 = s_rec, ent0 = s_ent;  // records / abundances this bin has written so far
+            const uint32_t ent0 = s_ent;  // abundances this bin has written so far
+            if (tid == 0) s_base = atomicAdd(t.hdr, n_rec);  // (read after the barrier below)
             // phase 3a: sample bitmaps of the shared groups
             for (uint32_t i = tid; i < n_e; i += BLOCK) {
                 int lo = 0, hi = N;
@@ -189,17 +191,15 @@ k_group_bins(TileArgs t) {
             for (int i = tid; i < MRG_SLOTS; i += BLOCK) {
                 if (gsz[i] < 2) continue;
                 const uint32_t pk = gix[i];
-                uint32_t *rec = grp_out + (uint64_t)(rec0 + (pk >> 16)) * (1 + nblk);
-                rec[0] = ent0 + (pk & 0xFFFFu);
-                for (int b = 0; b < nblk; b++) rec[1 + b] = bm[(pk >> 16) * nblk + b];
+                uint32_t *rec = t.grp + s_base + (pk >> 16);
+                rec[0] = region + ent0 + (pk & 0xFFFFu);
+                for (int b = 0; b < nblk; b++) rec[(uint64_t)(1 + b) * t.rec_cap] = bm[(pk >> 16) * nblk + b];
             }
             __syncthreads();
-            if (tid == 0) { s_rec = rec0 + n_rec; s_ent = ent0 + (tot & 0xFFFFu); }
+            if (tid == 0) s_ent = ent0 + (tot & 0xFFFFu);
             TM_NEXT();
         }
 #undef TM_NEXT
-        __syncthreads();
-        if (tid == 0) t.hdr[mb - t.bin0] = s_rec;
     }
     if (tid == 0 && (loc_groups | loc_shared)) {
         atomicAdd(&a.scalars[0], loc_groups);
@@ -258,17 +258,14 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
         }
     };
     ull loc_pairs = 0;
-    const uint32_t nb = t.bin1 - t.bin0;
-    const uint32_t per = (nb + slices - 1) / slices;
-    const uint32_t sb0 = min(nb, slice * per), sb1 = min(nb, sb0 + per);
-    const uint32_t stride = 1 + nblk;
+    const uint32_t n_all = t.hdr[0];  // records of the batch, split evenly over the slices of the tile
+    const uint32_t per = (n_all + slices - 1) / slices;
+    const uint32_t r_lo = min(n_all, slice * per), n_rec = min(n_all, r_lo + per) - r_lo;
     uint32_t rpt = TM_RPT, step = TM_THREADS, since = 0;
-    for (uint32_t lb = sb0; lb < sb1; lb++) {
-        const uint32_t n_rec = t.hdr[lb];
-        if (n_rec == 0) continue;
-        const uint64_t region = t.ebin[t.bin0 + lb] - t.ebin[t.bin0];
-        const uint32_t *cnt_in = t.cnt + region;
-        const uint32_t *grp_in = t.grp + (region / 2) * (uint64_t)stride;
+    {
+        const uint32_t *cnt_in = t.cnt;
+        const uint32_t *grp_in = t.grp + r_lo;
+        const uint64_t wcap = t.rec_cap;
         // A chunk is rpt * step consecutive records (step < TM_THREADS only with rpt == 1): every thread looks at up to TM_RPT records and
         // only those with pairs IN THIS TILE become entries -- with many sample blocks most records have none, and a chunk of one record
         // per thread would spend its barriers on a handful of pairs.  The shape adapts: it shrinks until the entries (<= TM_ECAP) and
@@ -280,8 +277,8 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
                 pm[k] = 0;
                 const uint32_t rix = c0 + (uint32_t)k * TM_THREADS + tid;
                 if ((uint32_t)k < rpt && (uint32_t)tid < step && rix < n_rec) {
-                    const uint32_t *rec = grp_in + (uint64_t)rix * stride;
-                    const uint32_t nI = __popc(rec[1 + I]), nJ = diag ? 0u : __popc(rec[1 + J]);
+                    const uint32_t *rec = grp_in + rix;
+                    const uint32_t nI = __popc(rec[(1 + I) * wcap]), nJ = diag ? 0u : __popc(rec[(1 + J) * wcap]);
                     const uint32_t pairs = diag ? nI * (nI - 1) / 2 : nI * nJ;
                     if (pairs) pm[k] = (pairs << 8) | (nI + nJ);
                 }
@@ -318,11 +315,11 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
 #pragma unroll
                 for (int k = 0; k < TM_RPT; k++) {
                     if (!((uint32_t)k < rpt && (uint32_t)tid < step && pm[k])) continue;
-                    const uint32_t *rec = grp_in + (uint64_t)(c0 + (uint32_t)k * TM_THREADS + tid) * stride;
+                    const uint32_t *rec = grp_in + (c0 + (uint32_t)k * TM_THREADS + tid);
                     const uint32_t e0 = rec[0];
                     uint32_t wI = 0, wJ = 0, offI = 0, offJ = 0, run = 0;
                     for (uint32_t b = 0; b <= J; b++) {
-                        const uint32_t w = rec[1 + b];
+                        const uint32_t w = rec[(1 + b) * wcap];
                         if (b == I) { wI = w; offI = run; }
                         if (b == J) { wJ = w; offJ = run; }
                         run += __popc(w);

@@ -1168,7 +1168,7 @@ static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
         if (ctx->d_keysA.reserve(want * 4) || ctx->d_keysB.reserve((want / 2 + 2) * rec_words * 4)) { ctx->set_error("out of device memory (tile merge scratch)"); return SIMKA_ERR_NOMEM; }
         cap_e = std::min<uint64_t>(ctx->d_keysA.cap / 4, (ctx->d_keysB.cap / (4 * rec_words)) * 2);
     }
-    cap_e -= 2;
+    cap_e = std::min<uint64_t>(cap_e - 2, 0xFFFFFFF0ull);  // (abundance offsets inside a batch are 32-bit)
     { const char *e = getenv("SIMKA_B200_TILE_BATCH"); if (e) cap_e = std::min<uint64_t>(cap_e, std::max<uint64_t>(max_bin, strtoull(e, nullptr, 10))); }  // tests: force several batches
     TileArgs t;
     t.m = a;
@@ -1176,6 +1176,7 @@ static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
     t.cnt = ctx->d_keysA.as<uint32_t>();
     t.grp = ctx->d_keysB.as<uint32_t>();
     t.nblk = nblk;
+    t.rec_cap = (uint32_t)std::min<uint64_t>(ctx->d_keysB.cap / (4 * rec_words), 0xFFFFFFFFull);
     void (*kern)(TileArgs, uint32_t) = a.simple ? (a.complex_ ? k_merge_tiles<true, true> : k_merge_tiles<true, false>)
                                                 : (a.complex_ ? k_merge_tiles<false, true> : k_merge_tiles<false, false>);
     const size_t smem_g = group_bins_smem_bytes(N), smem_t = merge_tiles_smem_bytes();
@@ -1192,8 +1193,9 @@ static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
         b1 = std::max(b1, b0 + 1);
         if (ebin[b1] > ebin[b0]) {
             t.bin0 = b0; t.bin1 = b1;
-            if (ctx->d_surv.reserve((size_t)(b1 - b0) * 4)) { ctx->set_error("out of device memory (tile merge)"); return SIMKA_ERR_NOMEM; }
+            if (ctx->d_surv.reserve(64)) { ctx->set_error("out of device memory (tile merge)"); return SIMKA_ERR_NOMEM; }
             t.hdr = ctx->d_surv.as<uint32_t>();
+            CK(cudaMemsetAsync(t.hdr, 0, 4, st));
             const unsigned gg = (unsigned)std::min<uint64_t>(b1 - b0, (uint64_t)ctx->nsm * std::max(1, occ_g));
             k_group_bins<<<gg, BLOCK, smem_g, st>>>(t);
             kern<<<tiles * slices, TM_THREADS, smem_t, st>>>(t, slices);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Memory check of the kernels on the CPU: the emulated library (tests/emu) compiled with AddressSanitizer, every kernel family
-run once on awkward inputs (default and super-k-mer stage 1, k = 31 / 21 / 15, SimkaMin sketch with and without -filter,
+run once on awkward inputs (default, super-k-mer and record-path stage 1, k = 31 / 21 / 15 / 41, the tile merge, SimkaMin sketch with and without -filter,
 SimkaMin distance).  An out-of-bounds access of "device" or "shared" memory aborts with ASan's report.  Developer tool:
     tools/emu_asan.py            (re-executes itself with libasan preloaded)"""
 import ctypes as C
@@ -38,6 +38,21 @@ for superk in ("0", "1"):
             ctx.dump_sample_counts(s)
         ctx.close()
         print("ok: stage 1 + merge, superk", superk, "k", k, flush=True)
+os.environ["SIMKA_B200_SUPERK"] = "2"  # record path (superk2.cuh)
+samples = synthetic_samples(3, 200) + nasty_samples()
+simka_b200.run_samples(samples, 31, abundance_min=1)
+print("ok: record path", flush=True)
+os.environ.pop("SIMKA_B200_SUPERK")
+for n, reads, order in ((70, 12, ""), (150, 6, "reverse"), (100, 10, "random:3")):  # tile merge (merge_tiles.cuh), several thread orders
+    os.environ["SIMKA_EMU_SCHED"] = order
+    samples = synthetic_samples(n, reads, read_len=70, n_genomes=4, genome_len=400)
+    simka_b200.run_samples(samples, 21, abundance_min=1, simple_dist=True, complex_dist=True)
+    same = [samples[0]] * n  # every k-mer in every sample: full tiles, chunks shrink to the member capacity
+    simka_b200.run_samples(same, 31, abundance_min=1, simple_dist=True, complex_dist=True)
+    print("ok: tile merge, N =", n, order or "ascending", flush=True)
+os.environ.pop("SIMKA_EMU_SCHED")
+simka_b200.run_samples(synthetic_samples(3, 100) + nasty_samples(), 41, abundance_min=1)  # 128-bit k-mers (wide.cuh)
+print("ok: k = 41", flush=True)
 h, c = synth.make_sketches(5, 3000)
 simka_b200.simkamin_distance(h, c)
 seqs, off = synthetic_samples(1, 300)[0]
