@@ -7,11 +7,13 @@
 //   k_group_bins   (once per merge bin)  the grouping phases of k_merge; instead of enumerating pairs it writes, for every k-mer
 //                  shared by >= 2 samples, a RECORD to a scratch buffer: the bitmap of the samples that hold it (one 32-bit
 //                  word per block of 32 samples) and its abundances in sample order (the rank of a sample inside its group is
-//                  the number of set bits below it, so no sort is needed).
-//   k_merge_tiles  one CTA per (tile of 32 x 32 samples, slice of the bins): it walks the records, picks the members of its two
-//                  sample blocks out of the bitmap words (two loads per k-mer), enumerates the tile's pairs flat over the
-//                  threads and adds them to tile-private accumulators in SHARED memory exactly as k_merge_sm does; one flush
-//                  per CTA and batch.
+//                  the number of set bits below it, so no sort is needed).  The records of a batch are DENSE (a sub-pass claims
+//                  the space of its records from a cursor; their order does not matter) and stored word-major.
+//   k_merge_tiles  one CTA per (tile of 32 x 32 samples, slice of the batch's records): every thread looks at up to four records
+//                  per chunk (two coalesced loads per record: the bitmap words of the tile's two sample blocks), the records
+//                  with pairs in this tile become entries whose members are staged in shared memory, the tile's pairs are
+//                  enumerated flat over the threads and added to tile-private accumulators in SHARED memory exactly as
+//                  k_merge_sm does; the 32-bit words are swept only when 2047 entries have passed; one flush per CTA and batch.
 // The scratch is the stage-1 work buffers (idle during the merge); when the records of all bins do not fit, the bins are
 // processed in batches cut on the host from the per-bin entry counts.
 // Reference: the same src/SimkaMerge.cpp:1164-1264,1307-1326 + src/core/SimkaAlgorithm.hpp:341-516 as k_merge.

@@ -1187,6 +1187,8 @@ static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, kern, TM_THREADS, smem_t));
     const uint32_t tiles = (uint32_t)(nblk * (nblk + 1) / 2);
     const uint32_t slices = std::max<uint32_t>(1, (uint32_t)(ctx->nsm * std::max(1, occ_t)) / tiles);
+    const bool timing = getenv("SIMKA_B200_TILE_TIMING") != nullptr;
+    std::vector<cudaEvent_t> evs;
     for (uint32_t b0 = 0; b0 < MG;) {
         // largest b1 with ebin[b1] - ebin[b0] <= cap_e (at least one bin: every bin fits by construction)
         uint32_t b1 = (uint32_t)(std::upper_bound(ebin.begin() + b0, ebin.end(), ebin[b0] + cap_e) - ebin.begin()) - 1;
@@ -1197,13 +1199,27 @@ static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
             t.hdr = ctx->d_surv.as<uint32_t>();
             CK(cudaMemsetAsync(t.hdr, 0, 4, st));
             const unsigned gg = (unsigned)std::min<uint64_t>(b1 - b0, (uint64_t)ctx->nsm * std::max(1, occ_g));
+            if (timing) { evs.resize(evs.size() + 3); for (int i = 0; i < 3; i++) cudaEventCreate(&evs[evs.size() - 3 + i]); cudaEventRecord(evs[evs.size() - 3], st); }
             k_group_bins<<<gg, BLOCK, smem_g, st>>>(t);
+            if (timing) cudaEventRecord(evs[evs.size() - 2], st);
             kern<<<tiles * slices, TM_THREADS, smem_t, st>>>(t, slices);
+            if (timing) cudaEventRecord(evs[evs.size() - 1], st);
             ctx->launches += 2;
         }
         b0 = b1;
     }
     CK(cudaGetLastError());
+    if (timing) {  // developer aid (SIMKA_B200_TILE_TIMING=1): where the merge's time goes, on stderr
+        CK(cudaStreamSynchronize(st));
+        float tg = 0, tt = 0, ms = 0;
+        for (size_t i = 0; i + 2 < evs.size(); i += 3) {
+            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); tg += ms;
+            cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]); tt += ms;
+        }
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
+        fprintf(stderr, "[simka_b200] tile merge: N=%d bins=%u entries=%llu batches=%zu slices=%u k_group_bins %.1f ms, k_merge_tiles %.1f ms\n", N, MG,
+                (unsigned long long)ebin[MG], evs.size() / 3, slices, tg, tt);
+    }
     return SIMKA_OK;
 }
 
