@@ -41,10 +41,16 @@ struct TileArgs {
     uint32_t rec_cap;              // records the scratch holds: word w of record r lives at grp[w * rec_cap + r] (a tile reads two of
                                    // the words of every record: consecutive threads, consecutive addresses)
     int nblk;                      // ceil(N / 32)
+    // per-CTA scratch of k_group_bins (scr_cap entries each) for bins that need several sub-passes: the bin is partitioned by
+    // sub-pass once, so that every sub-pass reads its own entries instead of the whole bin
+    uint64_t *scr_h;               // hashed k-mer (nullptr: no scratch, every sub-pass filters the whole bin)
+    uint32_t *scr_s, *scr_c;       // sample, abundance
+    uint32_t scr_cap;
 };
+constexpr int TM_RMAX = 512;       // sub-passes a partitioned bin may start with
 
 static size_t group_bins_smem_bytes(int n) {
-    return (size_t)MRG_SLOTS * 8 + (size_t)MRG_SLOTS * 4 * 2 + (size_t)MRG_SLOTS * 2 + (size_t)TM_GCAP * TM_MAXB * 4 + ((size_t)2 * n + 2) * 4 + 64;
+    return (size_t)MRG_SLOTS * 8 + (size_t)MRG_SLOTS * 4 * 2 + (size_t)MRG_SLOTS * 2 + (size_t)TM_GCAP * ((n + 31) / 32) * 4 + ((size_t)2 * n + 2) * 4 + 64;  // (TM_RMAX + 1 static words besides)
 }
 
 __global__ void __launch_bounds__(BLOCK)
@@ -66,11 +72,15 @@ k_group_bins(TileArgs t) {
     uint32_t *gs = reinterpret_cast<uint32_t *>(tk + MRG_SLOTS);  // [MRG_SLOTS] group size, then packed (entry start | record index << 16)
     uint32_t *gix = gs + MRG_SLOTS;                               // [MRG_SLOTS] copy of the packed prefix
     uint32_t *bm = gix + MRG_SLOTS;                               // [TM_GCAP][nblk] sample bitmaps of the shared groups
-    uint32_t *s_start = bm + (size_t)TM_GCAP * TM_MAXB;           // [N]
+    uint32_t *s_start = bm + (size_t)TM_GCAP * t.nblk;            // [N]
     uint32_t *s_pre = s_start + a.n;                              // [N + 1]
     uint16_t *gsz = reinterpret_cast<uint16_t *>(s_pre + a.n + 2); // [MRG_SLOTS]
     __shared__ uint32_t warp_tmp[16];
+    __shared__ uint32_t sub_off[TM_RMAX + 1];  // partitioned bin: entries of sub-pass r0 at scratch [sub_off[r0], sub_off[r0 + 1])
     __shared__ uint32_t s_groups, s_shared, s_subtotal, s_base, s_ent;
+    uint64_t *scr_h = t.scr_h ? t.scr_h + (size_t)blockIdx.x * t.scr_cap : nullptr;
+    uint32_t *scr_s = t.scr_h ? t.scr_s + (size_t)blockIdx.x * t.scr_cap : nullptr;
+    uint32_t *scr_c = t.scr_h ? t.scr_c + (size_t)blockIdx.x * t.scr_cap : nullptr;
     const int tid = threadIdx.x;
     const int N = a.n, nblk = t.nblk;
     const uint32_t q = 1u << (a.fg_bits - a.mg_bits);
@@ -97,18 +107,53 @@ k_group_bins(TileArgs t) {
         uint32_t R0 = 1;
         if (n_e > MRG_CAP) { while ((uint64_t)R0 * (MRG_CAP / 2) < n_e) R0 <<= 1; }
         uint32_t R = R0, r = 0;  // hash-selected sub-passes, split when one does not fit (as in k_merge)
+        // With R0 sub-passes every one of them would read (and binary-search the sample of) all entries of the bin, three times.
+        // Bins that large (hundreds of samples: the offset tables cap the number of merge bins) are partitioned by their first-level
+        // sub-pass into the CTA's scratch -- a counting sort, (hash, sample, abundance) per entry -- and a sub-pass then reads its own
+        // range only; a split sub-pass filters that range by the further selector bits.
+        const bool part = R0 > 1 && R0 <= (uint32_t)TM_RMAX && scr_h != nullptr && n_e <= t.scr_cap;
+        if (part) {
+            for (uint32_t i = tid; i < R0; i += BLOCK) gs[i] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < n_e; i += BLOCK) {
+                int lo = 0, hi = N;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const uint64_t hh = simka::hash2(a.eh[lo][s_start[lo] + (i - s_pre[lo])]);
+                atomicAdd(&gs[(uint32_t)(hh >> 20) & (R0 - 1)], 1u);
+            }
+            __syncthreads();
+            block_exclusive_scan(gs, (int)R0, warp_tmp);
+            for (uint32_t i = tid; i < R0; i += BLOCK) sub_off[i] = gs[i];
+            if (tid == 0) sub_off[R0] = n_e;
+            __syncthreads();
+            for (uint32_t i = tid; i < n_e; i += BLOCK) {
+                int lo = 0, hi = N;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                const size_t idx = s_start[lo] + (i - s_pre[lo]);
+                const uint64_t h = a.eh[lo][idx];
+                const uint32_t pos = atomicAdd(&gs[(uint32_t)(simka::hash2(h) >> 20) & (R0 - 1)], 1u);
+                scr_h[pos] = h;
+                scr_s[pos] = (uint32_t)lo;
+                scr_c[pos] = a.ec[lo][idx];
+            }
+        }
         bool more = true;
         while (more) {
             bool split = false;
+            const uint32_t i0 = part ? sub_off[r & (R0 - 1)] : 0u, i1 = part ? sub_off[(r & (R0 - 1)) + 1] : n_e;
             __syncthreads();
             for (int i = tid; i < MRG_SLOTS; i += BLOCK) { tk[i] = EMPTY; gs[i] = 0; }
             for (int i = tid; i < TM_GCAP * nblk; i += BLOCK) bm[i] = 0;
             if (tid == 0) { s_groups = 0; s_shared = 0; s_subtotal = 0; }
             __syncthreads();
-            for (uint32_t i = tid; i < n_e; i += BLOCK) {  // phase 1: insert keys, count group sizes
-                int lo = 0, hi = N;
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
-                const uint64_t h = a.eh[lo][s_start[lo] + (i - s_pre[lo])];
+            for (uint32_t i = i0 + tid; i < i1; i += BLOCK) {  // phase 1: insert keys, count group sizes
+                uint64_t h;
+                if (part) h = scr_h[i];
+                else {
+                    int lo = 0, hi = N;
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                    h = a.eh[lo][s_start[lo] + (i - s_pre[lo])];
+                }
                 const uint64_t hh = simka::hash2(h);
                 if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
                 uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
@@ -158,10 +203,15 @@ k_group_bins(TileArgs t) {
             const uint32_t ent0 = s_ent;  // abundances this bin has written so far
             if (tid == 0) s_base = atomicAdd(t.hdr, n_rec);  // (read after the barrier below)
             // phase 3a: sample bitmaps of the shared groups
-            for (uint32_t i = tid; i < n_e; i += BLOCK) {
-                int lo = 0, hi = N;
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
-                const uint64_t h = a.eh[lo][s_start[lo] + (i - s_pre[lo])];
+            for (uint32_t i = i0 + tid; i < i1; i += BLOCK) {
+                uint64_t h;
+                int lo = 0;
+                if (part) { h = scr_h[i]; lo = (int)scr_s[i]; }
+                else {
+                    int hi = N;
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                    h = a.eh[lo][s_start[lo] + (i - s_pre[lo])];
+                }
                 const uint64_t hh = simka::hash2(h);
                 if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
                 uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
@@ -173,11 +223,18 @@ k_group_bins(TileArgs t) {
             }
             __syncthreads();
             // phase 3b: abundances in sample order (rank = set bits below the sample), records
-            for (uint32_t i = tid; i < n_e; i += BLOCK) {
-                int lo = 0, hi = N;
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
-                const size_t idx = s_start[lo] + (i - s_pre[lo]);
-                const uint64_t h = a.eh[lo][idx];
+            for (uint32_t i = i0 + tid; i < i1; i += BLOCK) {
+                uint64_t h;
+                uint32_t c;
+                int lo = 0;
+                if (part) { h = scr_h[i]; lo = (int)scr_s[i]; c = scr_c[i]; }
+                else {
+                    int hi = N;
+                    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_pre[mid] <= i) lo = mid; else hi = mid; }
+                    const size_t idx = s_start[lo] + (i - s_pre[lo]);
+                    h = a.eh[lo][idx];
+                    c = a.ec[lo][idx];
+                }
                 const uint64_t hh = simka::hash2(h);
                 if (((uint32_t)(hh >> 20) & (R - 1)) != r) continue;
                 uint32_t slot = (uint32_t)(hh >> 40) & (MRG_SLOTS - 1);
@@ -188,7 +245,7 @@ k_group_bins(TileArgs t) {
                 const uint32_t *w = bm + (pk >> 16) * nblk;
                 uint32_t rank = __popc(w[lo >> 5] & ((1u << (lo & 31)) - 1));
                 for (int b = 0; b < (lo >> 5); b++) rank += __popc(w[b]);
-                cnt_out[ent0 + (pk & 0xFFFFu) + rank] = a.ec[lo][idx];
+                cnt_out[ent0 + (pk & 0xFFFFu) + rank] = c;
             }
             for (int i = tid; i < MRG_SLOTS; i += BLOCK) {
                 if (gsz[i] < 2) continue;

@@ -1185,6 +1185,21 @@ static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
     int occ_g = 0, occ_t = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g, k_group_bins, BLOCK, smem_g));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, kern, TM_THREADS, smem_t));
+    // partition scratch of k_group_bins (bins of more than MRG_CAP entries): 16 bytes per entry of the largest bin and CTA, in the idle
+    // stage-1 count buffer; without it (no memory left) every sub-pass reads its whole bin
+    const unsigned gg_max = (unsigned)std::min<uint64_t>(MG, (uint64_t)ctx->nsm * std::max(1, occ_g));
+    t.scr_h = nullptr; t.scr_s = t.scr_c = nullptr; t.scr_cap = 0;
+    if (max_bin > (uint64_t)MRG_CAP && max_bin <= (uint64_t)TM_RMAX * (MRG_CAP / 2) && !getenv("SIMKA_B200_TILE_NOPART")) {
+        const size_t cap = (size_t)((max_bin + 63) & ~(uint64_t)63);
+        if (ctx->d_stage_c.reserve((size_t)gg_max * cap * 16) == 0) {
+            t.scr_h = ctx->d_stage_c.as<uint64_t>();
+            t.scr_s = reinterpret_cast<uint32_t *>(t.scr_h + (size_t)gg_max * cap);
+            t.scr_c = t.scr_s + (size_t)gg_max * cap;
+            t.scr_cap = (uint32_t)cap;
+        } else {
+            cudaGetLastError();
+        }
+    }
     const uint32_t tiles = (uint32_t)(nblk * (nblk + 1) / 2);
     const uint32_t slices = std::max<uint32_t>(1, (uint32_t)(ctx->nsm * std::max(1, occ_t)) / tiles);
     const bool timing = getenv("SIMKA_B200_TILE_TIMING") != nullptr;
@@ -1198,7 +1213,7 @@ static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
             if (ctx->d_surv.reserve(64)) { ctx->set_error("out of device memory (tile merge)"); return SIMKA_ERR_NOMEM; }
             t.hdr = ctx->d_surv.as<uint32_t>();
             CK(cudaMemsetAsync(t.hdr, 0, 4, st));
-            const unsigned gg = (unsigned)std::min<uint64_t>(b1 - b0, (uint64_t)ctx->nsm * std::max(1, occ_g));
+            const unsigned gg = (unsigned)std::min<uint64_t>(b1 - b0, gg_max);
             if (timing) { evs.resize(evs.size() + 3); for (int i = 0; i < 3; i++) cudaEventCreate(&evs[evs.size() - 3 + i]); cudaEventRecord(evs[evs.size() - 3], st); }
             k_group_bins<<<gg, BLOCK, smem_g, st>>>(t);
             if (timing) cudaEventRecord(evs[evs.size() - 2], st);
@@ -1217,8 +1232,8 @@ static int merge_by_tiles(simka_ctx *ctx, const MergeArgs &a, uint32_t MG) {
             cudaEventElapsedTime(&ms, evs[i + 1], evs[i + 2]); tt += ms;
         }
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
-        fprintf(stderr, "[simka_b200] tile merge: N=%d bins=%u entries=%llu batches=%zu slices=%u k_group_bins %.1f ms, k_merge_tiles %.1f ms\n", N, MG,
-                (unsigned long long)ebin[MG], evs.size() / 3, slices, tg, tt);
+        fprintf(stderr, "[simka_b200] tile merge: N=%d bins=%u entries=%llu largest bin=%llu (%s) batches=%zu slices=%u k_group_bins %.1f ms, k_merge_tiles %.1f ms\n", N, MG,
+                (unsigned long long)ebin[MG], (unsigned long long)max_bin, t.scr_h ? "partitioned" : "not partitioned", evs.size() / 3, slices, tg, tt);
     }
     return SIMKA_OK;
 }

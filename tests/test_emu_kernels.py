@@ -572,6 +572,18 @@ def test_merge_by_sample_tiles(monkeypatch, n, batch):
     assert_stats_equal(st, oracle_run(samples, 21, 1))
 
 
+@pytest.mark.parametrize("nopart", [False, True])
+def test_merge_by_sample_tiles_large_bins_partitioned(monkeypatch, nopart):
+    """merge bins of several thousand entries (lists not regrouped: SIMKA_B200_REFINE=0): k_group_bins partitions such a bin by sub-pass
+    into its scratch once (merge_tiles.cuh) -- against the oracle, with and without the partition"""
+    monkeypatch.setenv("SIMKA_B200_REFINE", "0")
+    if nopart:
+        monkeypatch.setenv("SIMKA_B200_TILE_NOPART", "1")
+    samples = synthetic_samples(100, 40, read_len=80, n_genomes=5, genome_len=700)
+    st = simka_b200.run_samples(samples, 21, abundance_min=1, simple_dist=True, complex_dist=True)
+    assert_stats_equal(st, oracle_run(samples, 21, 1))
+
+
 def test_merge_by_sample_tiles_everybody_shares(monkeypatch):
     """150 samples holding the same k-mers: groups of 150 members (sub-passes split until a group's bitmap fits), every tile busy"""
     monkeypatch.setenv("SIMKA_B200_REFINE", "0")

@@ -12,7 +12,8 @@ try:
 except Exception as e: print('$tag', 'FAILED', e)
 "
 }
-run n128_tiles "--samples 128 --reads 1000000 --steps 2 --warmup 1 --e2e-steps 1"
+run n128_tiles "--samples 128 --reads 1000000 --steps 2 --warmup 1 --e2e-steps 1" SIMKA_B200_TILE_TIMING=1
 true
-run config4 "--config 4 --steps 2 --warmup 1 --e2e-steps 1"
+run config4 "--config 4 --steps 2 --warmup 1 --e2e-steps 1" SIMKA_B200_TILE_TIMING=1
+grep -h "tile merge" gpurun_out/r02k_n128_tiles.log gpurun_out/r02k_config4.log | sort | uniq -c | tail -4
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_merge_tiles|k_group_bins' -c 2 -o gpurun_out/r02k_tiles python bench.py --samples 128 --reads 200000 --steps 1 --warmup 0 --e2e-steps 1 --no-cpu-baseline > gpurun_out/r02k_tiles_run.log 2>&1; echo "ncu rc=$?"
