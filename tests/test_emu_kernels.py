@@ -380,8 +380,8 @@ def test_superk_large_bins_and_many_samples(monkeypatch):
 # ---------------------------------------------------------------------------------------------------------------
 # multi-GPU data path (sample-sharded counting, export -> all-to-all -> import, range-sharded merge) on virtual ranks
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("world,superk", [(2, False), (4, False), (2, True)])
-def test_sample_sharded_exchange_equals_whole(monkeypatch, world, superk):
+@pytest.mark.parametrize("world,superk,n", [(2, False, 5), (4, False, 5), (2, True, 5), (2, False, 70)])
+def test_sample_sharded_exchange_equals_whole(monkeypatch, world, superk, n):
     """simka_b200.dist.exchange_and_merge with the real export / import entry points and merge kernels (emulated), one thread
     per virtual rank: the summed accumulators equal the oracle's"""
     import threading
@@ -390,7 +390,8 @@ def test_sample_sharded_exchange_equals_whole(monkeypatch, world, superk):
     from test_gpu_parity import _FakeComm
     if superk:
         monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
-    samples = small_samples(5, 300)
+    # (n = 70: the merge context of a rank holds imported lists of > 64 samples and merges them by sample tiles)
+    samples = small_samples(5, 300) if n == 5 else small_samples(n, 40, read_len=80, n_genomes=2, genome_len=300)
     run = oracle_run(samples, 31, 2)
     N = len(samples)
     comm = _FakeComm(world)

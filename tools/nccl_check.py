@@ -26,7 +26,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    for n_samples, n_reads, k, amin in ((7, 4000, 31, 2), (3, 2000, 21, 1), (1, 500, 31, 1)):
+    for n_samples, n_reads, k, amin in ((7, 4000, 31, 2), (3, 2000, 21, 1), (1, 500, 31, 1), (70, 300, 21, 1)):
         samples = synthetic_samples(n_samples, n_reads)
         run = oracle_run(samples, k, amin)
         exp = n_reads * (150 - k + 1)

@@ -80,6 +80,7 @@ def full_summary():
     parts = [("default stage 1 (bench --samples 2: one launch = one 1M-read sample = 120 M k-mers)", first("r02h_stage1.ncu-rep")),
              ("merge, N = 32 (whole step)", first("r02i_merge.ncu-rep", "r02_merge.ncu-rep")),
              ("SimkaMin distance kernel (config 5 shape, 48 sketches)", first("r02h_simkamin.ncu-rep")),
+             ("tile merge, 64 < N <= 512 (bench --samples 128 --reads 200000: first batch)", first("r02k_tiles.ncu-rep")),
              ("record path (SIMKA_B200_SUPERK=2, not the default): scan / scatter / regrouping", first("r02b_stage1.ncu-rep")),
              ("record path: counting kernel after the convergent-insert rewrite", first("r02c_count.ncu-rep"))]
     with open(os.path.join(P, "r02_ncu_full_summary.txt"), "w") as f:
@@ -161,8 +162,10 @@ def sass_evidence():
 def bench_lines():
     pairs = [("r02i_c2.json", "r02_bench_config2_1gpu.json"), ("r02h_c2.json", "r02_bench_config2_1gpu_verified.json"), ("r02g_bench2.json", "r02_bench_config2_2gpu.json"),
              ("r02j_c2_8gpu.json", "r02_bench_config2_8gpu.json"), ("r02f_c2_native.json", "r02_bench_config2_8gpu_before_overlap.json"),
-             ("r02f_c2_torch.json", "r02_bench_config2_8gpu_torch_exchange.json"), ("r02j_config3.json", "r02_config3.json"), ("r02f_config3.json", "r02_config3_before_overlap.json"),
-             ("r02_config4.json", "r02_config4.json"), ("r02g_config5_ept6.json", "r02_config5.json"), ("r02h_k41.json", "r02_bench_k41_1gpu.json"),
+             ("r02f_c2_torch.json", "r02_bench_config2_8gpu_torch_exchange.json"), ("r02f_config3.json", "r02_config3_before_overlap.json"),
+             ("r02_config4.json", "r02_config4_generic_merge.json"), ("r02k_config4.json", "r02_config4.json"), ("r02k_n128_tiles.json", "r02_bench_n128_tile_merge.json"),
+             ("r02k_n128_generic.json", "r02_bench_n128_generic_merge.json"), ("r02m_config3.json", "r02_config3.json"), ("r02j_config3.json", "r02_config3_generic_merge.json"),
+             ("r02m_c2.json", "r02_bench_config2_1gpu_final.json"), ("r02m_config5.json", "r02_config5.json"), ("r02g_config5_ept6.json", "r02_config5.json"), ("r02h_k41.json", "r02_bench_k41_1gpu.json"),
              ("r02j_c2_4gpu.json", "r02_bench_config2_4gpu.json")]
     for src, dst in pairs:
         p = os.path.join(G, src)
