@@ -310,18 +310,25 @@ constexpr int MS_MAXN = 64;
 constexpr int MS_NACC = 10;
 constexpr uint32_t MS_FAST = 1u << 20;
 
+// per-sample constants of the (<= 64) local sample slots of a CTA, in shared memory
+struct MSTotals {
+    alignas(16) double ntot[MS_MAXN];      // N_i of the local sample slots
+    alignas(16) double ninv30[MS_MAXN];    // 2^30 / N_i: the product of two of them scales a Jensen-Shannon term to 2^-60 units
+    uint32_t nlo[MS_MAXN];                 // N_i mod 2^32
+    int s_gid[MS_MAXN];                    // local sample slot -> global sample id (-1: unused)
+    int big_tot;                           // some N_i >= 2^32: the 32-bit Whittaker shortcut is off
+};
+
 struct MSSmem {
     alignas(16) uint64_t tk[MS_SLOTS];
     alignas(16) double2 logtab[128];
     alignas(16) unsigned long long scan_tmp[MS_THREADS / 32 + 1];
-    alignas(16) double ntot[MS_MAXN];      // N_i of the local sample slots
-    alignas(16) double ninv30[MS_MAXN];    // 2^30 / N_i: the product of two of them scales a Jensen-Shannon term to 2^-60 units
     alignas(16) uint32_t gcnt[MS_SLOTS];   // cleaned with 128-bit stores
     uint32_t cg[MS_GCAP];
     uint32_t cgp[MS_GCAP + 1];
     uint32_t ge_c[MS_ECAP];
     uint32_t s_start[MS_MAXN], s_pre[MS_MAXN + 1];
-    int s_gid[MS_MAXN];            // local sample slot -> global sample id
+    MSTotals T;
     uint8_t ge_s[MS_ECAP];
     // followed by: uint32_t acc[MS_NACC][NP];
 };
@@ -346,6 +353,69 @@ __device__ __forceinline__ void ms_flush_word(const MergeArgs &a, int w, int i, 
     case 7: atomicAdd(&a.whittaker[ij], 0ull - (v << 20)); break;
     case 8: atomicAdd(&a.klfix[ij], v); break;
     default: atomicAdd(&a.klfix[ij], v << 20); break;
+    }
+}
+
+// One sample pair (local slots si < sj, abundances ci, cj) of one k-mer into the shared-memory accumulator words of its key
+// (src/core/SimkaAlgorithm.hpp:341-516).  NPK > 0: the number of keys is a compile-time constant (the ten word addresses are
+// immediate offsets of one base).  Common case first: both abundances below 2^20, every add but the chord product is then below
+// 2^20 by construction and goes to the 32-bit words without a check.
+template <bool SIMPLE, bool COMPLEX, int NPK>
+__device__ __forceinline__ void ms_pair(const MergeArgs &a, uint32_t *acc, int npk_rt, uint32_t key, uint32_t ci, uint32_t cj, uint32_t si,
+                                        uint32_t sj, const MSTotals &T, const double2 *logtab) {
+    const int NPk = NPK > 0 ? NPK : npk_rt;
+    uint32_t *p = acc + key;
+    auto add = [&](int w, ull v) {
+        if (v < MS_FAST) atomicAdd(p + w * NPk, (uint32_t)v);
+        else ms_flush_word(a, w, T.s_gid[si], T.s_gid[sj], v);
+    };
+    auto add2 = [&](int w, ull v) {  // 64-bit value as (low 20 bits | units of 2^20); a term that came out negative: 64-bit modular add
+        if (v < ((ull)MS_FAST << 20)) { atomicAdd(p + w * NPk, (uint32_t)v & (MS_FAST - 1)); atomicAdd(p + (w + 1) * NPk, (uint32_t)(v >> 20)); }
+        else ms_flush_word(a, w, T.s_gid[si], T.s_gid[sj], v);
+    };
+    const bool small = ((ci | cj) >> 20) == 0;
+    if (small) {
+        atomicAdd(p, ci);
+        atomicAdd(p + NPk, cj);
+        atomicAdd(p + 2 * NPk, 1u);
+        atomicAdd(p + 3 * NPk, ci < cj ? ci : cj);
+        if (SIMPLE) {
+            const ull prod = (ull)ci * (ull)cj;
+            add(4, prod);
+            atomicAdd(p + 5 * NPk, (uint32_t)hellinger_term(prod));  // floor(sqrt(prod)) < 2^20; u64 += double truncates per increment
+        }
+    } else {
+        add(0, ci);
+        add(1, cj);
+        atomicAdd(p + 2 * NPk, 1u);
+        add(3, ci < cj ? ci : cj);
+        if (SIMPLE) {
+            const ull prod = (ull)ci * (ull)cj;
+            add(4, prod);
+            add(5, hellinger_term(prod));
+        }
+    }
+    if (COMPLEX) {
+        const double ai = (double)ci, aj = (double)cj, Ni = T.ntot[si], Nj = T.ntot[sj];
+        const double yX = aj * Ni, xY = ai * Nj;
+        if (xY != yX) {  // equal: both logs are log(1) = 0 exactly
+            const double r1 = (2 * xY) * __drcp_rn(xY + yX);
+            // d1 + d2 = (c_i/N_i) log r1 + (c_j/N_j) log r2 = (xY log r1 + yX log r2) / (N_i N_j): no division per pair, the reciprocals
+            // are per sample.  The term is >= 0 (Jensen) and < 2: exact integer accumulation in units of 2^-60 (rounding 4e-19 per term,
+            // order-independent => bit-reproducible sums)
+            const double num = fma(xY, tab_log(r1, logtab), yX * tab_log(2.0 - r1, logtab));
+            add2(8, (ull)__double2ll_rn(num * (T.ninv30[si] * T.ninv30[sj])));
+        }
+        // Whittaker: abs((int)(u64(xY) - u64(yX))) minus the two one-sided values, accumulated negated (<= 0 in practice).  Only the low 32
+        // bits of the u64 values enter; with abundances < 2^20 and totals < 2^32 the products are exact integers below 2^52, so
+        // their low words are one 32-bit multiply each instead of two double -> u64 conversions
+        if (small && !T.big_tot) {
+            const uint32_t wx = ci * T.nlo[sj], wy = cj * T.nlo[si];
+            add2(6, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
+        } else {
+            const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
+            add2(6, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
+        }
     }
 }
 
@@ -382,6 +452,7 @@ k_merge_sm(MergeArgs a) {
         }
         const bool diag = !TILED || I == J;
         const int NPk = TILED ? (diag ? 496 : 1024) : N * (N - 1) / 2;  // pair keys of this tile
+        if (tid == 0) S.T.big_tot = 0;  // (the flush of the previous tile does not read it)
         __syncthreads();  // the flush of the previous tile is done
         for (int i = tid; i < MS_NACC * NPk; i += MS_THREADS) acc[i] = 0;
         // pair key -> local sample slots (li < lj) of the tile
@@ -398,10 +469,12 @@ k_merge_sm(MergeArgs a) {
             int gs = tid;
             if (TILED) gs = tid < 32 ? (int)(32 * I) + tid : (diag ? -1 : (int)(32 * J) + tid - 32);
             const bool used = gs >= 0 && gs < N;
-            S.s_gid[tid] = used ? gs : -1;
+            S.T.s_gid[tid] = used ? gs : -1;
             const double nt = used ? a.ntot[gs] : 0.0;
-            S.ntot[tid] = nt;
-            S.ninv30[tid] = nt > 0.0 ? 1073741824.0 / nt : 0.0;
+            S.T.ntot[tid] = nt;
+            S.T.ninv30[tid] = nt > 0.0 ? 1073741824.0 / nt : 0.0;
+            S.T.nlo[tid] = nt < 4294967296.0 ? (uint32_t)nt : 0u;
+            if (nt >= 4294967296.0) S.T.big_tot = 1;
         }
         __syncthreads();
 
@@ -409,7 +482,7 @@ k_merge_sm(MergeArgs a) {
             // segment descriptors of the (<= 64) samples of this tile
             if (tid < MS_MAXN) {
                 uint32_t len = 0;
-                const int gs = S.s_gid[tid];
+                const int gs = S.T.s_gid[tid];
                 if (gs >= 0) {
                     const uint32_t b0 = a.off[(size_t)gs * ostride + (size_t)mb * q];
                     const uint32_t b1 = a.off[(size_t)gs * ostride + (size_t)(mb + 1) * q];
@@ -454,7 +527,7 @@ k_merge_sm(MergeArgs a) {
                     int lo = 0, hi = 64;  // s_pre[lo] <= i < s_pre[hi]   (empty slots repeat the next prefix)
 #pragma unroll
                     for (int st = 0; st < 6; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
-                    const uint64_t h = a.eh[S.s_gid[lo]][S.s_start[lo] + (i - S.s_pre[lo])];
+                    const uint64_t h = a.eh[S.T.s_gid[lo]][S.s_start[lo] + (i - S.s_pre[lo])];
                     const uint64_t hh = simka::hash2(h);
                     if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
                     uint32_t slot = (uint32_t)(hh >> 40) & (MS_SLOTS - 1);
@@ -514,7 +587,7 @@ k_merge_sm(MergeArgs a) {
 #pragma unroll
                     for (int st = 0; st < 6; st++) { const int mid = (lo + hi) >> 1; if (S.s_pre[mid] <= i) lo = mid; else hi = mid; }
                     const size_t idx = S.s_start[lo] + (i - S.s_pre[lo]);
-                    const int gsid = S.s_gid[lo];
+                    const int gsid = S.T.s_gid[lo];
                     const uint64_t h = a.eh[gsid][idx];
                     const uint64_t hh = simka::hash2(h);
                     if (R > 1 && (((uint32_t)(hh >> 20)) & (R - 1)) != r) continue;
@@ -560,40 +633,7 @@ k_merge_sm(MergeArgs a) {
                                 else if (diag) key = si * (63 - si) / 2 + (sj - si - 1);
                                 else key = si * 32 + (sj - 32);
                                 if (TILED) loc_pairs++;
-                                // adds below 2^20 go to the shared-memory words (no return value); anything larger -- abundances in
-                                // the millions -- straight to the global accumulators
-                                auto add = [&](int w, ull v) {
-                                    if (v < MS_FAST) atomicAdd(&acc[w * NPk + key], (uint32_t)v);
-                                    else ms_flush_word(a, w, S.s_gid[si], S.s_gid[sj], v);
-                                };
-                                auto add2 = [&](int w, ull v) {  // 64-bit value as (low 20 bits | units of 2^20)
-                                    if (v < ((ull)MS_FAST << 20)) { atomicAdd(&acc[w * NPk + key], (uint32_t)v & (MS_FAST - 1)); atomicAdd(&acc[(w + 1) * NPk + key], (uint32_t)(v >> 20)); }
-                                    else ms_flush_word(a, w, S.s_gid[si], S.s_gid[sj], v);  // (also a term that came out negative: 64-bit modular add)
-                                };
-                                add(0, ci);
-                                add(1, cj);
-                                atomicAdd(&acc[2 * NPk + key], 1u);
-                                add(3, ci < cj ? ci : cj);
-                                if (SIMPLE) {
-                                    const ull prod = (ull)ci * (ull)cj;
-                                    add(4, prod);
-                                    add(5, hellinger_term(prod));  // u64 += double truncates per increment
-                                }
-                                if (COMPLEX) {
-                                    const double ai = (double)ci, aj = (double)cj, Ni = S.ntot[si], Nj = S.ntot[sj];
-                                    const double yX = aj * Ni, xY = ai * Nj;
-                                    if (xY != yX) {  // equal: both logs are log(1) = 0 exactly
-                                        const double r1 = (2 * xY) * __drcp_rn(xY + yX);
-                                        // d1 + d2 = (c_i/N_i) log r1 + (c_j/N_j) log r2 = (xY log r1 + yX log r2) / (N_i N_j): no division per
-                                        // pair, the reciprocals are per sample.  The term is >= 0 (Jensen) and < 2: exact integer accumulation
-                                        // in units of 2^-60 (rounding 4e-19 per term, order-independent => bit-reproducible sums)
-                                        const double num = fma(xY, tab_log(r1, S.logtab), yX * tab_log(2.0 - r1, S.logtab));
-                                        add2(8, (ull)__double2ll_rn(num * (S.ninv30[si] * S.ninv30[sj])));
-                                    }
-                                    const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
-                                    // accumulated negated (the both-present value minus the two one-sided values is <= 0 in practice)
-                                    add2(6, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
-                                }
+                                ms_pair<SIMPLE, COMPLEX, 0>(a, acc, NPk, key, ci, cj, si, sj, S.T, S.logtab);
                             }
                             // advance
                             if (++y == sz) {
@@ -616,7 +656,7 @@ k_merge_sm(MergeArgs a) {
                     if (v & 0x80000000u) {
                         int li, lj;
                         key_slots(i % NPk, li, lj);
-                        ms_flush_word(a, i / NPk, S.s_gid[li], S.s_gid[lj], v);
+                        ms_flush_word(a, i / NPk, S.T.s_gid[li], S.T.s_gid[lj], v);
                         acc[i] = 0;
                     }
                 }
@@ -630,7 +670,7 @@ k_merge_sm(MergeArgs a) {
                 const uint32_t v = acc[w * NPk + key];
                 if (!v) continue;
                 if (li < 0) key_slots(key, li, lj);
-                ms_flush_word(a, w, S.s_gid[li], S.s_gid[lj], v);
+                ms_flush_word(a, w, S.T.s_gid[li], S.T.s_gid[lj], v);
             }
         }
     }

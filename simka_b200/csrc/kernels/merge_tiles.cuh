@@ -272,40 +272,41 @@ k_group_bins(TileArgs t) {
 struct TMSmem {
     alignas(16) double2 logtab[128];
     alignas(16) unsigned long long scan_tmp[TM_THREADS / 32 + 1];
-    alignas(16) double ntot[64];
-    alignas(16) double ninv30[64];
+    MSTotals T;                       // per-sample constants of the tile's 64 local sample slots
     uint32_t cg[TM_ECAP];             // per entry of the chunk: member start (16 bits) | members of block I (8 bits) | of block J (8 bits)
     uint32_t cgp[TM_ECAP + 1];        // pair prefix
     uint32_t me_c[TM_MCAP];           // staged members: abundance
     uint8_t me_s[TM_MCAP];            //                 local sample slot (0..31 block I, 32..63 block J)
-    int s_gid[64];
     // followed by: uint32_t acc[MS_NACC][1024]
 };
+static_assert(MS_MAXN == 64, "a tile has 2 x 32 local sample slots");
 static size_t merge_tiles_smem_bytes() { return ((sizeof(TMSmem) + 15) & ~(size_t)15) + (size_t)MS_NACC * 1024 * 4 + 16; }
 
-template <bool SIMPLE, bool COMPLEX>
-__global__ void __launch_bounds__(TM_THREADS, 2)
-k_merge_tiles(TileArgs t, uint32_t slices) {
+// the work of one CTA; DIAG (tile of a block with itself: 496 pair keys instead of 1024) is a template parameter so that the number
+// of keys -- the stride between the ten accumulator words of a key -- is a compile-time constant
+template <bool SIMPLE, bool COMPLEX, bool DIAG>
+__device__ __forceinline__ void merge_tile(const TileArgs &t, const uint32_t slices, const uint32_t I, const uint32_t J, const uint32_t slice,
+                                           unsigned char *smem_raw) {
     const MergeArgs &a = t.m;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     TMSmem &S = *reinterpret_cast<TMSmem *>(smem_raw);
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(TMSmem) + 15) & ~(size_t)15));
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int N = a.n, nblk = t.nblk;
-    const uint32_t tile = blockIdx.x / slices, slice = blockIdx.x % slices;
-    uint32_t I = 0, J = 0;
-    { uint32_t rem = tile; while (rem >= (uint32_t)nblk - I) { rem -= (uint32_t)nblk - I; I++; } J = I + rem; }
-    const bool diag = I == J;
-    const int NPk = diag ? 496 : 1024;
+    const int tid = threadIdx.x;
+    const int N = a.n;
+    constexpr bool diag = DIAG;
+    constexpr int NPk = DIAG ? 496 : 1024;
     if (tid < 128) S.logtab[tid] = a.logtab[tid];
+    if (tid == 0) S.T.big_tot = 0;
+    __syncthreads();
     for (int i = tid; i < MS_NACC * NPk; i += TM_THREADS) acc[i] = 0;
     if (tid < 64) {
         const int gsid = tid < 32 ? (int)(32 * I) + tid : (diag ? -1 : (int)(32 * J) + tid - 32);
         const bool used = gsid >= 0 && gsid < N;
-        S.s_gid[tid] = used ? gsid : -1;
+        S.T.s_gid[tid] = used ? gsid : -1;
         const double nt = used ? a.ntot[gsid] : 0.0;
-        S.ntot[tid] = nt;
-        S.ninv30[tid] = nt > 0.0 ? 1073741824.0 / nt : 0.0;
+        S.T.ntot[tid] = nt;
+        S.T.ninv30[tid] = nt > 0.0 ? 1073741824.0 / nt : 0.0;
+        S.T.nlo[tid] = nt < 4294967296.0 ? (uint32_t)nt : 0u;
+        if (nt >= 4294967296.0) S.T.big_tot = 1;
     }
     __syncthreads();
     auto key_slots = [&](int key, int &li, int &lj) {
@@ -361,7 +362,7 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
                     if (v & 0x80000000u) {
                         int li, lj;
                         key_slots(i % NPk, li, lj);
-                        ms_flush_word(a, i / NPk, S.s_gid[li], S.s_gid[lj], v);
+                        ms_flush_word(a, i / NPk, S.T.s_gid[li], S.T.s_gid[lj], v);
                         acc[i] = 0;
                     }
                 }
@@ -421,34 +422,7 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
                     const uint32_t si = S.me_s[st + x], sj = S.me_s[st + y];  // local slots, si < sj by construction
                     const uint32_t ci = S.me_c[st + x], cj = S.me_c[st + y];
                     const uint32_t key = diag ? si * (63 - si) / 2 + (sj - si - 1) : si * 32 + (sj - 32);
-                    auto add = [&](int w, ull v) {
-                        if (v < MS_FAST) atomicAdd(&acc[w * NPk + key], (uint32_t)v);
-                        else ms_flush_word(a, w, S.s_gid[si], S.s_gid[sj], v);
-                    };
-                    auto add2 = [&](int w, ull v) {
-                        if (v < ((ull)MS_FAST << 20)) { atomicAdd(&acc[w * NPk + key], (uint32_t)v & (MS_FAST - 1)); atomicAdd(&acc[(w + 1) * NPk + key], (uint32_t)(v >> 20)); }
-                        else ms_flush_word(a, w, S.s_gid[si], S.s_gid[sj], v);
-                    };
-                    add(0, ci);
-                    add(1, cj);
-                    atomicAdd(&acc[2 * NPk + key], 1u);
-                    add(3, ci < cj ? ci : cj);
-                    if (SIMPLE) {
-                        const ull prod = (ull)ci * (ull)cj;
-                        add(4, prod);
-                        add(5, hellinger_term(prod));
-                    }
-                    if (COMPLEX) {
-                        const double ai = (double)ci, aj = (double)cj, Ni = S.ntot[si], Nj = S.ntot[sj];
-                        const double yX = aj * Ni, xY = ai * Nj;
-                        if (xY != yX) {
-                            const double r1 = (2 * xY) * __drcp_rn(xY + yX);
-                            const double num = fma(xY, tab_log(r1, S.logtab), yX * tab_log(2.0 - r1, S.logtab));
-                            add2(8, (ull)__double2ll_rn(num * (S.ninv30[si] * S.ninv30[sj])));
-                        }
-                        const uint64_t wx = (uint64_t)xY, wy = (uint64_t)yX;
-                        add2(6, (ull)(absint32_ext(wx) + absint32_ext(wy) - absint32_ext(wx - wy)));
-                    }
+                    ms_pair<SIMPLE, COMPLEX, NPk>(a, acc, NPk, key, ci, cj, si, sj, S.T, S.logtab);
                     // advance inside the entry, then to the next one (every entry has pairs)
                     bool next_rec = false;
                     if (!diag) { if (++y == gI + gJ) { y = gI; if (++x == gI) next_rec = true; } }
@@ -475,9 +449,19 @@ k_merge_tiles(TileArgs t, uint32_t slices) {
             const uint32_t v = acc[w * NPk + key];
             if (!v) continue;
             if (li < 0) key_slots(key, li, lj);
-            ms_flush_word(a, w, S.s_gid[li], S.s_gid[lj], v);
+            ms_flush_word(a, w, S.T.s_gid[li], S.T.s_gid[lj], v);
         }
     }
     if (tid == 0 && loc_pairs) atomicAdd(&a.scalars[2], loc_pairs);
-    (void)lane;
+}
+
+template <bool SIMPLE, bool COMPLEX>
+__global__ void __launch_bounds__(TM_THREADS, 2)
+k_merge_tiles(TileArgs t, uint32_t slices) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t tile = blockIdx.x / slices, slice = blockIdx.x % slices, nblk = (uint32_t)t.nblk;
+    uint32_t I = 0, J = 0;
+    { uint32_t rem = tile; while (rem >= nblk - I) { rem -= nblk - I; I++; } J = I + rem; }
+    if (I == J) merge_tile<SIMPLE, COMPLEX, true>(t, slices, I, J, slice, smem_raw);
+    else merge_tile<SIMPLE, COMPLEX, false>(t, slices, I, J, slice, smem_raw);
 }
