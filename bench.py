@@ -613,8 +613,9 @@ def run_simkamin(a, torch):
     hashes, counts = synth.make_sketches(n, s)
     # the sketches live in pinned host memory (as the packed reads of the k-mer configurations do): the library's cudaMemcpy of a
     # pageable 1.5 GB would be staged through the driver's bounce buffer at a fifth of the PCIe rate
-    pin_h, pin_c = torch.from_numpy(hashes).pin_memory(), torch.from_numpy(counts).pin_memory()
-    hashes, counts = pin_h.numpy(), pin_c.numpy()
+    if os.environ.get("SIMKA_BENCH_PIN", "1") != "0":
+        pin_h, pin_c = torch.from_numpy(hashes).pin_memory(), torch.from_numpy(counts).pin_memory()
+        hashes, counts = pin_h.numpy(), pin_c.numpy()
     pairs = n * (n - 1) // 2
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
@@ -623,6 +624,8 @@ def run_simkamin(a, torch):
         t0 = time.perf_counter()
         jac, bc, ms = simka_b200.simkamin_distance(hashes, counts)  # host sketches in, host float matrices out
         w = time.perf_counter() - t0
+        if os.environ.get("SIMKA_BENCH_VERBOSE"):
+            print(f"step {it}: wall {w * 1e3:.1f} ms, kernel {ms:.1f} ms", file=sys.stderr, flush=True)
         if it >= a.warmup:
             kms.append(ms)
             wall.append(w)

@@ -284,6 +284,9 @@ float simka_host_shannon_index(const char *seq, uint64_t len);
 int64_t simka_host_read_bank(const char *uri, char **seqs, uint64_t **read_off);
 void simka_host_free(void *p);
 
+/* The two SimkaMin distance entry points keep their device buffers between calls (one call at a time); this frees them. */
+int simkamin_gpu_release(void);
+
 /* all n1 x n2 pairs between two sets of sketches: the rectangular blocks of `simkaMinCore distance -start-i/-start-j`
  * (src/simkaMin/SimkaMinDistance.hpp:642-753).  Outputs n1*n2 float32 row-major. */
 int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32_t *counts1, uint32_t n1, const uint64_t *hashes2,

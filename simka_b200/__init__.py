@@ -6,7 +6,7 @@ The compute lives in lib/libsimka_b200.so (hand-written CUDA); this package is t
 and fails loudly if that library is missing -- there is no CPU path.
 """
 from .api import (SimkaError, SimkaGpu, SimkaStatistics, comm_unique_id, pack_reads, pinned_empty, run_samples,  # noqa: F401
-                  simkamin_distance, simkamin_last_sketch_info, simkamin_sketch)
+                  simkamin_distance, simkamin_last_sketch_info, simkamin_release, simkamin_sketch)
 
 __all__ = ["SimkaError", "SimkaGpu", "SimkaStatistics", "comm_unique_id", "pack_reads", "pinned_empty", "run_samples",
-           "simkamin_distance", "simkamin_last_sketch_info", "simkamin_sketch"]
+           "simkamin_distance", "simkamin_last_sketch_info", "simkamin_release", "simkamin_sketch"]

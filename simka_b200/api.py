@@ -400,6 +400,11 @@ def simkamin_last_sketch_info() -> dict:
     return {"attempts": int(info.attempts), "keys_counted": int(info.keys_counted), "distinct_dumped": int(info.distinct_dumped)}
 
 
+def simkamin_release():
+    """frees the device buffers the SimkaMin distance entry points keep between calls"""
+    _lib.load().simkamin_gpu_release()
+
+
 def simkamin_distance(hashes: np.ndarray, counts: np.ndarray, device: int = 0):
     """All-pairs SimkaMin Jaccard / Bray-Curtis (src/simkaMin/SimkaMinDistance.hpp:190-303).
     -> (jaccard float32[n,n], braycurtis float32[n,n], kernel_ms)"""

@@ -1718,10 +1718,42 @@ int simkamin_gpu_last_sketch_info(simkamin_sketch_info *out) {
     return SIMKA_OK;
 }
 
+}  // extern "C"
+namespace {
+// Device buffers of the SimkaMin distance entry points, kept between calls (`simkaMinCore distance` walks the matrix in rectangular
+// blocks, one call each; a cudaMalloc / cudaFree pair per call also serialises against anything else that holds the driver lock).
+// One call at a time; simkamin_gpu_release() frees them.
+struct SketchBuffers {
+    std::mutex mu;
+    int device = -1;
+    DevBuf b[7];
+    void release() {
+        if (device >= 0 && cudaSetDevice(device) == cudaSuccess) for (DevBuf &x : b) x.release();
+        device = -1;
+    }
+    int use(int dev) {  // 0: the cache now belongs to device dev (which is current)
+        if (device != dev) release();
+        if (cudaSetDevice(dev) != cudaSuccess) return -1;
+        device = dev;
+        return 0;
+    }
+};
+SketchBuffers g_sketch_buffers;
+}  // namespace
+extern "C" {
+
+int simkamin_gpu_release(void) {
+    std::lock_guard<std::mutex> lock(g_sketch_buffers.mu);
+    g_sketch_buffers.release();
+    return SIMKA_OK;
+}
+
 int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *counts, uint32_t n, uint32_t s, float *jaccard,
                           float *braycurtis, float *kernel_ms) {
     if (!hashes || !counts || !jaccard || !braycurtis || n == 0 || s == 0) return SIMKA_ERR_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return SIMKA_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(g_sketch_buffers.mu);
+    if (g_sketch_buffers.use(device)) return SIMKA_ERR_CUDA;
+    DevBuf *B = g_sketch_buffers.b;
     uint64_t *dh = nullptr; uint32_t *dc = nullptr, *dstart = nullptr; ull *dq = nullptr;
     const size_t ne = (size_t)n * s, nn = (size_t)n * n;
     const uint64_t pairs = (uint64_t)n * (n - 1) / 2;
@@ -1732,7 +1764,8 @@ int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *co
     try { hq.resize(4 * pairs); } catch (const std::bad_alloc &) { return SIMKA_ERR_NOMEM; }  // nothing may throw across the C ABI
     do {
         // (+64: the bulk copies of the distance kernel round their ranges outwards to 16 bytes)
-        if (cudaMalloc(&dh, ne * 8 + 64) || cudaMalloc(&dc, ne * 4 + 64) || cudaMalloc(&dstart, (size_t)n * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
+        if (B[0].reserve(ne * 8 + 64) || B[1].reserve(ne * 4 + 64) || B[2].reserve((size_t)n * 4) || B[6].reserve((pairs + 1) * 32)) { cudaGetLastError(); rc = SIMKA_ERR_NOMEM; break; }
+        dh = B[0].as<uint64_t>(); dc = B[1].as<uint32_t>(); dstart = B[2].as<uint32_t>(); dq = B[6].as<ull>();
         if (cudaFuncSetAttribute(k_simkamin_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmtSmem)) != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
         if (cudaMemcpy(dh, hashes, ne * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc, counts, ne * 4, cudaMemcpyHostToDevice)) { rc = SIMKA_ERR_CUDA; break; }
         cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1746,7 +1779,6 @@ int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *co
     } while (0);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    cudaFree(dh); cudaFree(dc); cudaFree(dstart); cudaFree(dq);
     if (rc) return rc;
     // final ratios exactly as the reference: long double division, stored as float (:244-259)
     for (size_t q = 0; q < nn; q++) { jaccard[q] = 0; braycurtis[q] = 0; }
@@ -1767,7 +1799,9 @@ int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *co
 int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32_t *counts1, uint32_t n1, const uint64_t *hashes2,
                                const uint32_t *counts2, uint32_t n2, uint32_t s, float *jaccard, float *braycurtis, float *kernel_ms) {
     if (!hashes1 || !counts1 || !hashes2 || !counts2 || !jaccard || !braycurtis || n1 == 0 || n2 == 0 || s == 0) return SIMKA_ERR_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return SIMKA_ERR_CUDA;
+    std::lock_guard<std::mutex> lock(g_sketch_buffers.mu);
+    if (g_sketch_buffers.use(device)) return SIMKA_ERR_CUDA;
+    DevBuf *B = g_sketch_buffers.b;
     uint64_t *dh1 = nullptr, *dh2 = nullptr; uint32_t *dc1 = nullptr, *dc2 = nullptr, *ds1 = nullptr, *ds2 = nullptr; ull *dq = nullptr;
     const size_t e1 = (size_t)n1 * s, e2 = (size_t)n2 * s;
     const uint64_t pairs = (uint64_t)n1 * n2;
@@ -1778,8 +1812,10 @@ int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32
     try { hq.resize(4 * pairs); } catch (const std::bad_alloc &) { return SIMKA_ERR_NOMEM; }
     do {
         if (cudaFuncSetAttribute(k_simkamin_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmtSmem)) != cudaSuccess) { rc = SIMKA_ERR_CUDA; break; }
-        if (cudaMalloc(&dh1, e1 * 8 + 64) || cudaMalloc(&dc1, e1 * 4 + 64) || cudaMalloc(&ds1, (size_t)n1 * 4) || cudaMalloc(&dh2, e2 * 8 + 64) || cudaMalloc(&dc2, e2 * 4 + 64) ||
-            cudaMalloc(&ds2, (size_t)n2 * 4) || cudaMalloc(&dq, (pairs + 1) * 32)) { rc = SIMKA_ERR_NOMEM; break; }
+        if (B[0].reserve(e1 * 8 + 64) || B[1].reserve(e1 * 4 + 64) || B[2].reserve((size_t)n1 * 4) || B[3].reserve(e2 * 8 + 64) || B[4].reserve(e2 * 4 + 64) ||
+            B[5].reserve((size_t)n2 * 4) || B[6].reserve((pairs + 1) * 32)) { cudaGetLastError(); rc = SIMKA_ERR_NOMEM; break; }
+        dh1 = B[0].as<uint64_t>(); dc1 = B[1].as<uint32_t>(); ds1 = B[2].as<uint32_t>(); dh2 = B[3].as<uint64_t>(); dc2 = B[4].as<uint32_t>(); ds2 = B[5].as<uint32_t>();
+        dq = B[6].as<ull>();
         if (cudaMemcpy(dh1, hashes1, e1 * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc1, counts1, e1 * 4, cudaMemcpyHostToDevice) ||
             cudaMemcpy(dh2, hashes2, e2 * 8, cudaMemcpyHostToDevice) || cudaMemcpy(dc2, counts2, e2 * 4, cudaMemcpyHostToDevice)) { rc = SIMKA_ERR_CUDA; break; }
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
@@ -1794,7 +1830,6 @@ int simkamin_gpu_distance_rect(int device, const uint64_t *hashes1, const uint32
     } while (0);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    cudaFree(dh1); cudaFree(dc1); cudaFree(ds1); cudaFree(dh2); cudaFree(dc2); cudaFree(ds2); cudaFree(dq);
     if (rc) return rc;
     for (uint64_t p = 0; p < pairs; p++) {  // final ratios exactly as the reference: long double division, stored as float (:244-259)
         const ull sh = hq[4 * p], di = hq[4 * p + 1], sk = hq[4 * p + 2], km = hq[4 * p + 3];

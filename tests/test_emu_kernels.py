@@ -203,6 +203,18 @@ def test_simkamin_distance():
     ojac, obc = oracle.simkamin_distance(hashes, counts)
     np.testing.assert_array_equal(jac, ojac)
     np.testing.assert_array_equal(bc, obc)
+    # the device buffers are kept between calls: a smaller call, the first one again, then released and once more
+    h2, c2 = synth.make_sketches(3, 900, seed=5)
+    j2, b2, _ = simka_b200.simkamin_distance(h2, c2)
+    o2 = oracle.simkamin_distance(h2, c2)
+    np.testing.assert_array_equal(j2, o2[0])
+    np.testing.assert_array_equal(b2, o2[1])
+    for release in (False, True):
+        if release:
+            simka_b200.simkamin_release()
+        jac, bc, _ = simka_b200.simkamin_distance(hashes, counts)
+        np.testing.assert_array_equal(jac, ojac)
+        np.testing.assert_array_equal(bc, obc)
 
 
 @pytest.mark.parametrize("k,max_reads,nb_kmers,filt", [(21, 0, 100, False), (31, 100, 1000, True)])

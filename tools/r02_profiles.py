@@ -165,13 +165,13 @@ def bench_lines():
              ("r02f_c2_torch.json", "r02_bench_config2_8gpu_torch_exchange.json"), ("r02f_config3.json", "r02_config3_before_overlap.json"),
              ("r02_config4.json", "r02_config4_generic_merge.json"), ("r02k_config4.json", "r02_config4.json"), ("r02k_n128_tiles.json", "r02_bench_n128_tile_merge.json"),
              ("r02k_n128_generic.json", "r02_bench_n128_generic_merge.json"), ("r02m_config3.json", "r02_config3.json"), ("r02j_config3.json", "r02_config3_generic_merge.json"),
-             ("r02m_c2.json", "r02_bench_config2_1gpu_final.json"), ("r02m_config5.json", "r02_config5.json"), ("r02g_config5_ept6.json", "r02_config5.json"), ("r02h_k41.json", "r02_bench_k41_1gpu.json"),
+             ("r02q_c2.json", "r02_bench_config2_1gpu_final.json"), ("r02q_config5.json", "r02_config5.json"), ("r02q_refarm.json", "r02_bench_reference_arm.json"), ("r02g_config5_ept6.json", "r02_config5.json"), ("r02h_k41.json", "r02_bench_k41_1gpu.json"),
              ("r02j_c2_4gpu.json", "r02_bench_config2_4gpu.json")]
     for src, dst in pairs:
         p = os.path.join(G, src)
         if os.path.exists(p):
             shutil.copy(p, os.path.join(P, dst))
-    for log, dst in (("r02c_rec_default.log", "r02_bench_record_path.json"), ("r02_refarm.log", "r02_bench_reference_arm.json")):
+    for log, dst in (("r02c_rec_default.log", "r02_bench_record_path.json"), ("r02_refarm.log", "r02_bench_reference_arm_first_sizing.json")):
         p = os.path.join(G, log)
         if os.path.exists(p):
             last = [l for l in open(p) if l.startswith("{")]
