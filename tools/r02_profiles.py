@@ -81,6 +81,7 @@ def full_summary():
              ("merge, N = 32 (whole step)", first("r02i_merge.ncu-rep", "r02_merge.ncu-rep")),
              ("SimkaMin distance kernel (config 5 shape, 48 sketches)", first("r02h_simkamin.ncu-rep")),
              ("tile merge, 64 < N <= 512 (bench --samples 128 --reads 200000: first batch)", first("r02k_tiles.ncu-rep")),
+             ("tile merge, 512 samples x 150 k reads, k = 21 (sparse: few pairs per record and tile)", first("r02s_tiles512.ncu-rep")),
              ("record path (SIMKA_B200_SUPERK=2, not the default): scan / scatter / regrouping", first("r02b_stage1.ncu-rep")),
              ("record path: counting kernel after the convergent-insert rewrite", first("r02c_count.ncu-rep"))]
     with open(os.path.join(P, "r02_ncu_full_summary.txt"), "w") as f:
