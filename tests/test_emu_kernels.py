@@ -403,7 +403,7 @@ def test_sample_sharded_exchange_equals_whole(monkeypatch, world, superk, n):
     if superk:
         monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
     # (n = 70: the merge context of a rank holds imported lists of > 64 samples and merges them by sample tiles)
-    samples = small_samples(5, 300) if n == 5 else small_samples(n, 40, read_len=80, n_genomes=2, genome_len=300)
+    samples = small_samples(5, 300) if n == 5 else small_samples(n, 24, read_len=80, n_genomes=2, genome_len=300)
     run = oracle_run(samples, 31, 2)
     N = len(samples)
     comm = _FakeComm(world)
@@ -592,7 +592,7 @@ def test_merge_by_sample_tiles_large_bins_partitioned(monkeypatch, nopart):
     monkeypatch.setenv("SIMKA_B200_REFINE", "0")
     if nopart:
         monkeypatch.setenv("SIMKA_B200_TILE_NOPART", "1")
-    samples = synthetic_samples(100, 40, read_len=80, n_genomes=5, genome_len=700)
+    samples = synthetic_samples(80, 30, read_len=80, n_genomes=5, genome_len=700)
     st = simka_b200.run_samples(samples, 21, abundance_min=1, simple_dist=True, complex_dist=True)
     assert_stats_equal(st, oracle_run(samples, 21, 1))
 
