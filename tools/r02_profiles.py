@@ -166,7 +166,7 @@ def bench_lines():
              ("r02f_c2_torch.json", "r02_bench_config2_8gpu_torch_exchange.json"), ("r02f_config3.json", "r02_config3_before_overlap.json"),
              ("r02_config4.json", "r02_config4_generic_merge.json"), ("r02k_config4.json", "r02_config4.json"), ("r02k_n128_tiles.json", "r02_bench_n128_tile_merge.json"),
              ("r02k_n128_generic.json", "r02_bench_n128_generic_merge.json"), ("r02m_config3.json", "r02_config3.json"), ("r02j_config3.json", "r02_config3_generic_merge.json"),
-             ("r02q_c2.json", "r02_bench_config2_1gpu_final.json"), ("r02q_config5.json", "r02_config5.json"), ("r02q_refarm.json", "r02_bench_reference_arm.json"), ("r02g_config5_ept6.json", "r02_config5.json"), ("r02h_k41.json", "r02_bench_k41_1gpu.json"),
+             ("r02q_c2.json", "r02_bench_config2_1gpu_final.json"), ("r02q_config5.json", "r02_config5.json"), ("r02q_refarm.json", "r02_bench_reference_arm.json"), ("r02t_c2_2gpu.json", "r02_bench_config2_2gpu_final.json"), ("r02g_config5_ept6.json", "r02_config5.json"), ("r02h_k41.json", "r02_bench_k41_1gpu.json"),
              ("r02j_c2_4gpu.json", "r02_bench_config2_4gpu.json")]
     for src, dst in pairs:
         p = os.path.join(G, src)
@@ -180,10 +180,23 @@ def bench_lines():
                 open(os.path.join(P, dst), "w").write(last[-1])
 
 
+def test_logs():
+    """last lines of the GPU test runs on the shipped HEAD"""
+    with open(os.path.join(P, "r02_pytest_gpu_final.txt"), "w") as f:
+        for log, what in (("r02q_pytest.log", "python -m pytest tests -m gpu -q -x   (one B200, tools/r02_call17.sh)"),
+                          ("r02t_pytest2.log", "python -m pytest tests/test_zz_nccl_gpu.py -m gpu -q -x   (two B200s, tools/r02_call20.sh)"),
+                          ("r02m_nccl_check8.log", "torchrun --nproc-per-node 8 tools/nccl_check.py   (eight B200s, tools/r02_call13.sh)")):
+            p = os.path.join(G, log)
+            if os.path.exists(p):
+                lines = [l.rstrip() for l in open(p) if l.strip()]
+                f.write(f"$ {what}\n" + "\n".join(lines[-5:]) + "\n\n")
+
+
 if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     launch_summary()
     full_summary()
     sass_evidence()
     bench_lines()
+    test_logs()
     print("\n".join(sorted(f for f in os.listdir(P) if f.startswith("r02") or f == "traffic.json")))
