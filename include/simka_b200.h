@@ -282,6 +282,9 @@ uint64_t simka_host_kmers(const char *seq, uint64_t len, int k, int canonical, u
 uint64_t simka_host_minimizer(uint64_t kmer, int k, int m);
 float simka_host_shannon_index(const char *seq, uint64_t len);
 int64_t simka_host_read_bank(const char *uri, char **seqs, uint64_t **read_off);
+/* IBank::estimateNbItems (GC/bank/impl/BankFasta.cpp:728-775, AbstractBank.hpp:71-74): sequences at the head of every file
+ * extrapolated to the file size (a gz file = 4 x its compressed size); what `simka -max-reads 0` derives its limit from. */
+int64_t simka_host_estimate_nb_items(const char *uri);
 void simka_host_free(void *p);
 
 /* The two SimkaMin distance entry points keep their device buffers between calls (one call at a time); this frees them. */

@@ -13,6 +13,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <cctype>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -217,7 +218,7 @@ public:
     virtual std::string getId() = 0;
     virtual Iterator<Sequence> *iterator() = 0;  // caller deletes
     virtual int64_t getNbItems() { return -1; }
-    // exact here (one pass over the file); the reference samples the head of the file (BankFasta.cpp:226-290)
+    // as the reference: from the head of the file, extrapolated (BankFasta.cpp:728-775)
     virtual void estimate(uint64_t &number, uint64_t &totalSize, uint64_t &maxSize) = 0;
     int64_t estimateNbItems() { uint64_t n, t, m; estimate(n, t, m); return (int64_t)n; }
     virtual size_t getCompositionNb() { return 1; }
@@ -232,18 +233,120 @@ public:
     static const char *name() { return "fasta"; }
     std::string getId() override { return path_; }
     std::vector<std::string> files() override { return std::vector<std::string>(1, path_); }
+    // BankFasta::Iterator::estimate (GC/bank/impl/BankFasta.cpp:728-775): the sequences at the head of the file are read (until
+    // more than the threshold of 50000 have been seen) and the counts are extrapolated linearly from the position of the
+    // reader -- what gzread has delivered so far, in buffers of 256 KB -- to the size of the file, a gz file being taken for
+    // four times its compressed size (:167-188).  Exact for a plain file that ends before the threshold; NOT the number of
+    // reads of a gz file.  `simka -max-reads 0` derives its limit from these numbers (S/core/SimkaAlgorithm.cpp:397-430).
     void estimate(uint64_t &number, uint64_t &totalSize, uint64_t &maxSize) override {
-        FastxParser p(path_);
-        std::string d;
+        HeadReader r(path_);
         number = totalSize = maxSize = 0;
-        for (;;) {
-            d.clear();
-            if (!p.nextRead(d)) break;
+        uint64_t len = 0;
+        while (r.nextSequence(len) && number <= estimateThreshold_) {
             number++;
-            totalSize += d.size();
-            if (d.size() > maxSize) maxSize = d.size();
+            if (len > maxSize) maxSize = len;
+            totalSize += len;
+        }
+        const uint64_t actual = r.delivered();
+        if (actual > 0) {
+            const uint64_t size = estimatedFileSize(path_);
+            number = (number * size) / actual;
+            totalSize = (uint64_t)((float)totalSize * ((float)size / (float)actual));
         }
     }
+    void setEstimateThreshold(uint64_t n) { estimateThreshold_ = n; }
+    // file size as the reference sees it: a name whose FIRST "gz" is its last two characters counts four times its size
+    static uint64_t estimatedFileSize(const std::string &path) {
+        gzFile f = gzopen(path.c_str(), "rb");  // (existence check with the same error as the readers)
+        if (!f) throw Exception("Unable to open bank '" + path + "'");
+        gzclose(f);
+        std::ifstream in(path.c_str(), std::ios::binary | std::ios::ate);
+        const uint64_t sz = in ? (uint64_t)in.tellg() : 0;
+        const char *name = path.c_str();
+        const char *gz = strstr(name, "gz");
+        return (gz != nullptr && gz == name + strlen(name) - 2) ? sz * 4 : sz;
+    }
+    // the reference's buffered kseq-style reader (BankFasta.cpp:391-572), reduced to what estimate() needs: where records end
+    // and how many 256 KB buffers have been fetched
+    class HeadReader {
+    public:
+        explicit HeadReader(const std::string &path) : buf_(BUFFER_SIZE) {
+            f_ = gzopen(path.c_str(), "rb");
+            if (!f_) throw Exception("Unable to open bank '" + path + "'");
+        }
+        ~HeadReader() { if (f_) gzclose(f_); }
+        HeadReader(const HeadReader &) = delete;
+        HeadReader &operator=(const HeadReader &) = delete;
+        uint64_t delivered() const { return delivered_; }  // gztell of the reference's stream
+        bool nextSequence(uint64_t &length) {  // get_next_seq_from_file (:485-572); length = number of sequence characters
+            int c;
+            if (last_char_ == 0) {
+                while ((c = getc_()) != -1 && c != '>' && c != '@') {}
+                if (c == -1) return false;
+                last_char_ = c;
+            }
+            uint64_t hlen = 0;
+            char dret = 0;
+            if (gets_(hlen, &dret, false) < 0) return false;
+            if (dret != '\n') { uint64_t rest = 0; gets_(rest, nullptr, true); }
+            uint64_t rlen = 0;
+            while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
+                if (c == '\n') continue;
+                rlen++;
+                last_of_string_ = (char)c;
+                gets_(rlen, nullptr, true);
+            }
+            if (c == '>' || c == '@') last_char_ = c;
+            if (c == '+') {
+                while ((c = getc_()) != -1 && c != '\n') {}
+                uint64_t qlen = 0;
+                last_of_string_ = 0;
+                while (gets_(qlen, nullptr, true) >= 0 && qlen < rlen) {}
+                last_char_ = 0;
+            }
+            length = rlen;
+            return true;
+        }
+    private:
+        static const int BUFFER_SIZE = 256 * 1024;
+        bool rebuffer_() {
+            if (eof_) return false;
+            start_ = 0;
+            const int n = gzread(f_, buf_.data(), BUFFER_SIZE);
+            end_ = n > 0 ? (size_t)n : 0;
+            delivered_ += end_;
+            if (end_ < (size_t)BUFFER_SIZE) eof_ = true;
+            return end_ != 0;
+        }
+        int getc_() {
+            if (start_ >= end_) if (!rebuffer_()) return -1;
+            return (int)(signed char)buf_[start_++];
+        }
+        // buffered_gets (:421-475) in append mode on a string of which only the length (and last character) is kept
+        int64_t gets_(uint64_t &length, char *dret, bool allow_spaces) {
+            if (dret) *dret = 0;
+            if (start_ >= end_ && eof_) return -1;
+            for (;;) {
+                if (start_ >= end_) if (!rebuffer_()) break;
+                size_t i = start_;
+                if (allow_spaces) { while (i < end_ && buf_[i] != '\n') i++; }
+                else { while (i < end_ && !isspace((unsigned char)buf_[i])) i++; }
+                if (i > start_) last_of_string_ = (char)buf_[i - 1];
+                length += i - start_;
+                start_ = i + 1;
+                if (i < end_) { if (dret) *dret = (char)buf_[i]; break; }
+            }
+            if (allow_spaces && length > 1 && last_of_string_ == '\r') { length--; last_of_string_ = 0; }
+            return (int64_t)length;
+        }
+        gzFile f_ = nullptr;
+        std::vector<unsigned char> buf_;
+        size_t start_ = 0, end_ = 0;
+        bool eof_ = false;
+        uint64_t delivered_ = 0;
+        int last_char_ = 0;
+        char last_of_string_ = 0;
+    };
     class It : public Iterator<Sequence> {
     public:
         explicit It(const std::string &path) : parser_(path) {}
@@ -263,6 +366,7 @@ public:
     Iterator<Sequence> *iterator() override { return new It(path_); }
 private:
     std::string path_;
+    uint64_t estimateThreshold_ = 50000;  // AbstractBank.hpp:54
 };
 
 // ---- BankAlbum: a text file with one bank uri per line (relative to the album's directory) --------------------

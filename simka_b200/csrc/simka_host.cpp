@@ -455,6 +455,15 @@ int64_t simka_host_read_bank(const char *uri, char **seqs, uint64_t **read_off) 
     } catch (...) { return -1; }
 }
 
+// IBank::estimateNbItems of a bank (fasta / fastq / gz / album): the reference's head-of-file extrapolation, -1 on error
+int64_t simka_host_estimate_nb_items(const char *uri) {
+    using namespace simka_b200::bank;
+    try {
+        std::unique_ptr<IBank> b(Bank::open(uri));
+        return b->estimateNbItems();
+    } catch (...) { return -1; }
+}
+
 void simka_host_free(void *p) { free(p); }
 
 }  // extern "C"

@@ -232,15 +232,18 @@ int run(int argc, char **argv) {
     SimkaSequenceFilter filter(o.minReadSize, o.minShannon);
 
     // -max-reads: -1 = all, N = at most N per group, 0 = (min + mean) / 2 over the samples
-    // (src/core/SimkaAlgorithm.cpp:377-445; the reference ESTIMATES the read counts from the head of each file,
-    //  here they are counted exactly)
+    // (src/core/SimkaAlgorithm.cpp:377-445).  The reference takes the read counts from IBank::estimateNbItems -- the head of every
+    // file extrapolated to the file size, a gz file counted as four times its compressed size -- and so does this: the limit
+    // must be the same number for the same files (bank::BankFasta::estimate)
     uint64_t maxReads = 0;
     if (o.maxReads > 0) maxReads = (uint64_t)o.maxReads;
     if (o.maxReads == 0 || o.dataInfo) {
         uint64_t mn = ~0ull, sum = 0;
         for (const SampleSpec &s : samples) {
-            uint64_t n = read_sample(s, SimkaSequenceFilter(), 0, [](const char *, size_t) {});
-            if (o.dataInfo || o.verbose) printf("\t%s: %llu reads\n", s.id.c_str(), (unsigned long long)n);
+            uint64_t n = 0;
+            for (auto &g : s.groups)
+                for (auto &f : g) { uint64_t ni, t, m; bank::BankFasta(f).estimate(ni, t, m); n += ni; }
+            if (o.dataInfo || o.verbose) printf("\t%s: about %llu reads\n", s.id.c_str(), (unsigned long long)n);
             n /= std::max<size_t>(1, s.groups.size());  // the limit applies per paired group (src/core/SimkaAlgorithm.cpp:405, nbReads /= _nbBankPerDataset[i])
             mn = std::min(mn, n);
             sum += n;

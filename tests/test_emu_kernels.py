@@ -471,6 +471,14 @@ def test_reference_run_truth(emulated_cli, tmp_path, golden_dir, inp, k, t):
     G.test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, t)
 
 
+@pytest.mark.parametrize("tag,k,t", [("maxreads50", 21, 1), ("maxreads0", 31, 2), ("minsize90_shannon1.5", 21, 1), ("maxreads40_minsize85", 31, 2), ("amax3", 21, 1),
+                                     ("amax3", 31, 2)])
+def test_cli_options_reproduce_reference_runs(emulated_cli, tmp_path, golden_dir, tag, k, t):
+    """read limits and filters of the command line against reference runs with the same arguments"""
+    import test_gpu_parity as G
+    G.test_simka_cli_options_reproduce_reference_runs(tmp_path, golden_dir, k, t, tag)
+
+
 @pytest.mark.parametrize("count,merge,k,t", [("ours", "ours", 31, 2), ("ours", "ref", 21, 0), ("ref", "ours", 21, 0)])
 def test_cross_run_with_reference_binaries(emulated_cli, tmp_path, golden_dir, count, merge, k, t):
     import test_gpu_parity as G

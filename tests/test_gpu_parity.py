@@ -83,6 +83,38 @@ def test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, 
     assert checked == 21
 
 
+OPTION_TAGS = ["maxreads50", "maxreads0", "minsize90_shannon1.5", "maxreads40_minsize85", "amax3"]
+
+
+@pytest.mark.parametrize("tag", OPTION_TAGS)
+@pytest.mark.parametrize("k,t", [(21, 1), (31, 2)])
+def test_simka_cli_options_reproduce_reference_runs(tmp_path, golden_dir, k, t, tag):
+    """-max-reads (explicit and automatic, with a paired and a concatenated sample), -min-read-size, -min-shannon-index and
+    -abundance-max through the `simka` command line: per-sample totals and all 21 matrices equal to what the REFERENCE `simka`
+    produced with the same arguments (tests/golden/truth_ref/example_n_results_k*_t*_<tag>, tools/make_ref_golden.py)"""
+    import gzip
+    import json
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    tdir = os.path.join(golden_dir, "truth_ref", f"example_n_results_k{k}_t{t}_{tag}")
+    extra = json.load(open(os.path.join(tdir, "options.json")))
+    out = tmp_path / "results"
+    cmd = [str(SIMKA_BIN), "-in", os.path.join(golden_dir, "example_n", "simka_input.txt"), "-out", str(out), "-out-tmp", str(tmp_path / "tmp"),
+           "-simple-dist", "-complex-dist", "-kmer-size", str(k), "-abundance-min", str(t), "-verbose", "0", "-keep-tmp"] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    sync = json.load(open(os.path.join(tdir, "count_synchro.json")))
+    sdir = tmp_path / "tmp" / "simka_output_temp" / "count_synchro"
+    for ident, want in sync.items():
+        assert [int(x) for x in open(sdir / (ident + ".ok")).read().split()] == want, ident
+    checked = 0
+    for f in sorted(os.listdir(tdir)):
+        if f.endswith(".csv"):
+            assert gzip.open(out / (f + ".gz"), "rt").read() == open(os.path.join(tdir, f)).read(), f
+            checked += 1
+    assert checked == 21
+
+
 @pytest.mark.parametrize("k,amin", [(31, 2), (21, 1), (15, 2), (9, 0), (32, 2), (45, 1), (63, 2)])
 def test_synthetic_per_sample_counts_and_stats(k, amin):
     samples = synthetic_samples(6, 3000)

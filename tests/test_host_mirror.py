@@ -359,3 +359,84 @@ def test_fastx_parser_randomised_against_the_oracle(tmp_path):
         es, eo = oracle.read_fastx(str(path))
         np.testing.assert_array_equal(o, eo, err_msg=str(path))
         np.testing.assert_array_equal(s, es, err_msg=str(path))
+
+
+def test_estimate_nb_items_small_files(golden_dir):
+    """IBank::estimateNbItems (BankFasta.cpp:728-775): exact for a plain file below the threshold, 4 x compressed size / uncompressed
+    size x the reads for a gz file -- 34 for the 100 reads of example_n/S3.fastq.gz, the value behind the reference's own
+    `-max-reads 0` run (tests/golden/truth_ref/example_n_results_k*_maxreads0: limit 75 = (34 + 116) / 2)"""
+    L = _lib.load()
+    ex = os.path.join(golden_dir, "example_n")
+    want = {"S1.fasta": 123, "S2.fasta": 120, "S3.fastq.gz": 34, "S4_1.fasta": 60, "S4_2.fasta": 60}
+    for f, n in want.items():
+        assert L.simka_host_estimate_nb_items(os.fsencode(os.path.join(ex, f))) == n, f
+    assert L.simka_host_estimate_nb_items(os.fsencode(os.path.join(ex, "no_such_file"))) == -1
+
+
+def test_estimate_nb_items_matches_reference_binary_beyond_the_threshold(tmp_path):
+    """files with more than 50000 sequences (the estimate stops there and extrapolates from the reader's position, which advances
+    in buffers of 256 KB), plain / gz / multi-line / FASTQ, a paired and a concatenated sample: the numbers the REFERENCE `simka
+    -max-reads 0` prints (smallest, largest, mean, limit) against the ones derived from simka_host_estimate_nb_items"""
+    import gzip
+    import re
+    import subprocess
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bin", "simka")
+    if not os.access(ref, os.X_OK):
+        pytest.skip("oracle/_ref/bin not built")
+    rng = np.random.default_rng(5)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+
+    def write(name, n, L_, fastq=False, gz=False, multiline=False):
+        lens = L_ + rng.integers(0, 30, n)
+        bases = alpha[rng.integers(0, 4, int(lens.sum()))].tobytes()
+        out, p = [], 0
+        for i in range(n):
+            r = bases[p:p + int(lens[i])]
+            p += int(lens[i])
+            if fastq:
+                out.append(b"@q%d\n" % i + r + b"\n+\n" + b"I" * len(r) + b"\n")
+            elif multiline:
+                out.append(b">r%d c\n" % i + r[:40] + b"\n" + r[40:] + b"\n")
+            else:
+                out.append(b">r%d\n" % i + r + b"\n")
+        with (gzip.open if gz else open)(tmp_path / name, "wb") as f:
+            f.write(b"".join(out))
+
+    write("A.fasta", 130000, 60)
+    write("B.fastq.gz", 90000, 70, fastq=True, gz=True)
+    write("C.fasta", 70000, 80, multiline=True)
+    write("D.fastq", 52000, 50, fastq=True)
+    write("E.fasta.gz", 3000, 90, gz=True)
+    samples = {"A": [["A.fasta"]], "B": [["B.fastq.gz"]], "C": [["C.fasta"], ["D.fastq"]], "D": [["D.fastq"]], "E": [["E.fasta.gz", "A.fasta"]]}
+    (tmp_path / "in.txt").write_text("".join(f"{k}: " + " ; ".join(" , ".join(g) for g in v) + "\n" for k, v in samples.items()))
+    # the reference prints its estimates before it starts counting; the run itself is not needed (and is stopped: own process group)
+    import signal
+    import time
+    log = open(tmp_path / "ref.log", "w")
+    proc = subprocess.Popen([ref, "-in", str(tmp_path / "in.txt"), "-out", str(tmp_path / "out"), "-out-tmp", str(tmp_path / "tmp"), "-kmer-size", "21",
+                             "-max-reads", "0", "-nb-cores", "2", "-max-memory", "4000"], stdout=log, stderr=subprocess.STDOUT, cwd=tmp_path,
+                            start_new_session=True)
+    text = ""
+    try:
+        for _ in range(600):
+            time.sleep(0.1)
+            text = open(tmp_path / "ref.log").read()
+            if "Reads per sample used up to:" in text or proc.poll() is not None:
+                break
+    finally:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        proc.wait()
+        log.close()
+    assert "Reads per sample used up to:" in text, text[-1500:]
+    got = {k: int(re.search(pat + r"\s*(\d+)", text).group(1)) for k, pat in
+           (("min", "Smaller sample contains:"), ("max", "Larger sample contains:"), ("mean", "mean of:"), ("limit", "Reads per sample used up to:"))}
+    L = _lib.load()
+    per = []
+    for k, groups in samples.items():
+        n = sum(L.simka_host_estimate_nb_items(os.fsencode(str(tmp_path / f))) for g in groups for f in g)
+        per.append(n // len(groups))
+    mine = {"min": min(per), "max": max(per), "mean": sum(per) // len(per), "limit": (min(per) + sum(per) // len(per)) // 2}
+    assert mine == got, (per, text[-1500:])

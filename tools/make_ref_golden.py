@@ -26,6 +26,16 @@ CASES = [("example", k, a) for k in (9, 15, 16, 32, 41, 63) for a in (0, 2)]
 CASES += [("example_n", k, a) for k in (12, 15, 21, 31, 41) for a in (0, 2)]
 
 
+# option cases: the read filters and limits of the command line, run by the reference itself (tag -> extra arguments); input example_n
+OPTION_CASES = {
+    "maxreads50": ["-max-reads", "50"],
+    "maxreads0": ["-max-reads", "0"],  # automatic limit: (min + mean) / 2 of the per-group read counts (S4 is a paired sample)
+    "minsize90_shannon1.5": ["-min-read-size", "90", "-min-shannon-index", "1.5"],
+    "maxreads40_minsize85": ["-max-reads", "40", "-min-read-size", "85"],
+    "amax3": ["-abundance-max", "3"],
+}
+
+
 def make_example_n(dst):
     """tests/golden/example_n: seeded; written once and committed (the reference ran on exactly these files)"""
     import numpy as np
@@ -79,17 +89,21 @@ def main():
     exn = os.path.join(ROOT, "tests", "golden", "example_n")
     if not os.path.exists(os.path.join(exn, "simka_input.txt")):
         make_example_n(exn)
-    for inp, k, amin in CASES:
+    cases = [(inp, k, amin, "", []) for inp, k, amin in CASES]
+    cases += [("example_n", k, amin, tag, extra) for tag, extra in OPTION_CASES.items() for k, amin in ((21, 1), (31, 2))]
+    for inp, k, amin, tag, extra in cases:
         with tempfile.TemporaryDirectory() as td:
             shutil.copytree(os.path.join(ROOT, "tests", "golden", inp), os.path.join(td, "ex"))
             cmd = [SIMKA, "-in", os.path.join(td, "ex", "simka_input.txt"), "-out", os.path.join(td, "out"), "-out-tmp", os.path.join(td, "tmp"),
                    "-kmer-size", str(k), "-abundance-min", str(amin), "-simple-dist", "-complex-dist", "-nb-cores", "4", "-max-memory", "4000",
-                   "-keep-tmp"]
+                   "-keep-tmp"] + extra
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=td)
             if r.returncode != 0:
                 print(f"{inp} k={k} amin={amin}: reference failed rc={r.returncode}\n{r.stdout[-800:]}")
                 continue
-            dst = os.path.join(OUT, ("" if inp == "example" else inp + "_") + f"results_k{k}_t{amin}")
+            dst = os.path.join(OUT, ("" if inp == "example" else inp + "_") + f"results_k{k}_t{amin}" + ("_" + tag if tag else ""))
+            if os.path.exists(os.path.join(dst, "count_synchro.json")) and "--force" not in sys.argv:
+                continue
             os.makedirs(dst, exist_ok=True)
             n = 0
             for f in sorted(os.listdir(os.path.join(td, "out"))):
@@ -103,7 +117,9 @@ def main():
                 if f.endswith(".ok"):
                     sync[f[:-3]] = [int(x) for x in open(os.path.join(sdir, f)).read().split()]
             json.dump(sync, open(os.path.join(dst, "count_synchro.json"), "w"), indent=1, sort_keys=True)
-            print(f"{inp} k={k} amin={amin}: {n} matrices, totals {sync}")
+            if extra:
+                json.dump(extra, open(os.path.join(dst, "options.json"), "w"))
+            print(f"{inp} k={k} amin={amin} {tag}: {n} matrices, totals {sync}")
 
 
 if __name__ == "__main__":
