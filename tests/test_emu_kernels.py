@@ -471,8 +471,8 @@ def test_reference_run_truth(emulated_cli, tmp_path, golden_dir, inp, k, t):
     G.test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, t)
 
 
-@pytest.mark.parametrize("tag,k,t", [("maxreads50", 21, 1), ("maxreads0", 31, 2), ("minsize90_shannon1.5", 21, 1), ("maxreads40_minsize85", 31, 2), ("amax3", 21, 1),
-                                     ("amax3", 31, 2)])
+@pytest.mark.parametrize("tag,k,t", [("maxreads50", 21, 1), ("maxreads0", 31, 2), ("minsize90_shannon1.5", 21, 1), ("maxreads40_minsize85", 31, 2), ("amax3", 21, 3),
+                                     ("amax3", 31, 2), ("kshannon1.5", 21, 1)])
 def test_cli_options_reproduce_reference_runs(emulated_cli, tmp_path, golden_dir, tag, k, t):
     """read limits and filters of the command line against reference runs with the same arguments"""
     import test_gpu_parity as G
@@ -505,6 +505,12 @@ def test_cli_simkamincore_and_pipelines_reproduce_truth(emulated_cli, tmp_path, 
     d = tmp_path / "update"
     d.mkdir()
     P.test_simkamin_update_equals_one_run(d, golden_dir)
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 5])
+def test_cli_simkamincore_against_reference_binary(emulated_cli, tmp_path, golden_dir, case):
+    import test_gpu_parity as G
+    G.test_simkamincore_against_reference_binary(tmp_path, golden_dir, case)
 
 
 def test_single_sample_run():

@@ -83,15 +83,16 @@ def test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, 
     assert checked == 21
 
 
-OPTION_TAGS = ["maxreads50", "maxreads0", "minsize90_shannon1.5", "maxreads40_minsize85", "amax3"]
+OPTION_TAGS = ["maxreads50", "maxreads0", "minsize90_shannon1.5", "maxreads40_minsize85", "amax3", "kshannon1.5"]
+OPTION_CASES = [(k, t, tag) for tag in OPTION_TAGS for k, t in ((21, 1), (31, 2))] + [(21, 3, "amax3")]
 
 
-@pytest.mark.parametrize("tag", OPTION_TAGS)
-@pytest.mark.parametrize("k,t", [(21, 1), (31, 2)])
+@pytest.mark.parametrize("k,t,tag", OPTION_CASES)
 def test_simka_cli_options_reproduce_reference_runs(tmp_path, golden_dir, k, t, tag):
-    """-max-reads (explicit and automatic, with a paired and a concatenated sample), -min-read-size, -min-shannon-index and
-    -abundance-max through the `simka` command line: per-sample totals and all 21 matrices equal to what the REFERENCE `simka`
-    produced with the same arguments (tests/golden/truth_ref/example_n_results_k*_t*_<tag>, tools/make_ref_golden.py)"""
+    """-max-reads (explicit and automatic, with a paired and a concatenated sample), -min-read-size, -min-shannon-index,
+    -abundance-max and -kmer-shannon-index (accepted, without effect) through the `simka` command line: per-sample totals and all
+    21 matrices equal to what the REFERENCE `simka` produced with the same arguments
+    (tests/golden/truth_ref/example_n_results_k*_t*_<tag>, tools/make_ref_golden.py)"""
     import gzip
     import json
     import subprocess
@@ -713,3 +714,55 @@ def test_simkamincore_cli_reproduces_reference_truth(tmp_path, golden_dir, k, ma
         np.testing.assert_array_equal(np.triu(blocks), np.triu(whole))  # the reference does not mirror rectangular blocks
         np.testing.assert_array_equal(blocks[2:, 2:], whole[2:, 2:])
         np.testing.assert_array_equal(blocks[:2, :2], whole[:2, :2])
+
+
+SIMKAMIN_REF_CASES = [["-kmer-size", "21", "-nb-kmers", "500"], ["-kmer-size", "31", "-nb-kmers", "300", "-max-reads", "30"],
+                      ["-kmer-size", "21", "-nb-kmers", "400", "-filter"], ["-kmer-size", "25", "-nb-kmers", "5000"],
+                      ["-kmer-size", "21", "-nb-kmers", "200", "-min-read-size", "95", "-min-shannon-index", "1.8"],
+                      ["-kmer-size", "15", "-nb-kmers", "300"], ["-kmer-size", "31", "-nb-kmers", "100", "-seed", "7"]]
+
+
+@pytest.mark.parametrize("case", range(len(SIMKAMIN_REF_CASES)))
+def test_simkamincore_against_reference_binary(tmp_path, golden_dir, case):
+    """`simkaMinCore sketch | distance | export` of this build next to the REFERENCE simkaMinCore (oracle/_ref/bin) on the same input --
+    multi-line FASTA with lower case and N runs, FASTQ.gz, a paired and a concatenated sample -- and the same options: the sketch
+    files are equal byte for byte outside the 4 padding bytes of every 16-byte record (the reference writes them uninitialised),
+    the exported matrices byte for byte; and each build's `distance` reads the other's sketch file."""
+    import gzip
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    SIMKAMIN_BIN = SIMKA_BIN.parent / "simkaMinCore"
+    ref = os.path.join(REF_BIN, "simkaMinCore")
+    if not os.access(ref, os.X_OK):
+        pytest.skip("oracle/_ref/bin not built")
+    ex = os.path.join(golden_dir, "example_n")  # (without S1: reads shorter than k make the reference's sketch depend on its thread schedule)
+    inp = tmp_path / "in.txt"
+    inp.write_text(f"S2: {ex}/S2.fasta\nS3: {ex}/S3.fastq.gz\nS4: {ex}/S4_1.fasta ; {ex}/S4_2.fasta\nS6: {ex}/S2.fasta , {ex}/S4_1.fasta\n")
+    opts = SIMKAMIN_REF_CASES[case]
+
+    def run(exe, tag, sketch=None):
+        d = tmp_path / tag
+        (d / "dist").mkdir(parents=True)
+        sk = sketch or str(d / "sketch.bin")
+        if not sketch:
+            r = subprocess.run([exe, "sketch", "-in", str(inp), "-out", sk, "-nb-cores", "1", "-max-memory", "4000"] + opts, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+        for cmd in (["distance", "-in1", sk, "-in2", sk, "-out", str(d / "dist"), "-nb-cores", "1"],
+                    ["export", "-in", str(d / "dist"), "-in1", sk, "-in2", sk, "-out", str(d), "-nb-cores", "1"]):
+            r = subprocess.run([exe] + cmd, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+        return sk, {f: gzip.open(d / f).read() for f in sorted(os.listdir(d)) if f.startswith("mat_") and f.endswith(".csv.gz")}
+
+    sk_ref, m_ref = run(ref, "ref")
+    sk_our, m_our = run(str(SIMKAMIN_BIN), "our")
+    assert len(m_ref) == 2 and m_our == m_ref
+    a, b = np.fromfile(sk_ref, np.uint8), np.fromfile(sk_our, np.uint8)
+    assert a.size == b.size
+    differing = np.nonzero(a != b)[0]
+    # 13 header bytes (k, sketch size, seed, number of datasets), then the records {u64 hash, u32 count, 4 padding bytes}, then the identifiers
+    n_rec = 4 * int(opts[opts.index("-nb-kmers") + 1])
+    rec0 = 13
+    assert differing.size == 0 or (differing.min() >= rec0 and differing.max() < rec0 + 16 * n_rec and
+                                   set(((differing - rec0) % 16).tolist()) <= {12, 13, 14, 15})
+    assert run(ref, "ref_on_ours", sketch=sk_our)[1] == m_ref
+    assert run(str(SIMKAMIN_BIN), "ours_on_ref", sketch=sk_ref)[1] == m_ref
