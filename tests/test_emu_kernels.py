@@ -487,6 +487,15 @@ def test_cross_run_with_reference_binaries(emulated_cli, tmp_path, golden_dir, c
     G.test_cross_run_with_reference_binaries(tmp_path, golden_dir, count, merge, k, t)
 
 
+@pytest.mark.parametrize("count,merge,k,t,tag", [("ours", "ours", 21, 2, ""), ("ours", "ref", 15, 0, ""), ("ref", "ours", 12, 2, ""), ("ours", "ours", 31, 2, "maxreads50"),
+                                                 ("ours", "ref", 21, 1, "minsize90_shannon1.5"), ("ours", "ours", 21, 1, "maxreads0"), ("ref", "ours", 21, 3, "amax3")])
+def test_cross_run_with_reference_binaries_on_awkward_input(emulated_cli, tmp_path, golden_dir, count, merge, k, t, tag):
+    import test_gpu_parity as G
+    if not os.access(os.path.join(G.REF_BIN, "simka"), os.X_OK):
+        pytest.skip("oracle/_ref/bin not built")
+    G.test_cross_run_with_reference_binaries(tmp_path, golden_dir, count, merge, k, t, inp="example_n", tag=tag)
+
+
 def test_cli_stage_binaries_reference_temp_formats(emulated_cli, tmp_path, golden_dir):
     import test_gpu_parity as G
     G.test_stage_binaries_reference_temp_formats(tmp_path, golden_dir)
