@@ -83,20 +83,30 @@ void usage() {
 Options parse_args(int argc, char **argv) {
     Options o;
     std::map<std::string, std::string> kv;
+    // Command-line mistakes are handled the way the reference's GATB `Tool` does (GC/tools/misc/impl/Tool.cpp, OptionFailure): every
+    // problem is listed as "ERROR: ...", the option list follows, and the process ends with EXIT_SUCCESS -- only failures of the run
+    // itself ("EXCEPTION: ...") give EXIT_FAILURE.
+    std::vector<std::string> errs;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (in_list(kNoParam, a)) { kv[a] = "1"; continue; }
         if (in_list(kOneParam, a)) {
-            if (i + 1 >= argc) throw bank::Exception("Option '" + a + "' needs an argument");
+            if (i + 1 >= argc) { errs.push_back("Too few arguments for the " + a + " option..."); continue; }
             kv[a] = argv[++i];
             continue;
         }
-        throw bank::Exception("Unknown parameter '" + a + "'");
+        errs.push_back("Unknown parameter '" + a + "'");
     }
     if (kv.count("-help")) { usage(); exit(EXIT_SUCCESS); }
     if (kv.count("-version")) { printf("%s\n", simka_b200_version()); exit(EXIT_SUCCESS); }
-    if (!kv.count("-in")) throw bank::Exception("Option '-in' is mandatory");
-    if (!kv.count("-out-tmp")) throw bank::Exception("Option '-out-tmp' is mandatory");
+    if (!kv.count("-in")) errs.push_back("Option '-in' is mandatory");
+    if (!kv.count("-out-tmp")) errs.push_back("Option '-out-tmp' is mandatory");
+    if (!errs.empty()) {
+        for (const std::string &e : errs) printf("ERROR: %s\n", e.c_str());
+        printf("\n");
+        usage();
+        exit(EXIT_SUCCESS);
+    }
     o.in = kv["-in"];
     o.outTmp = kv["-out-tmp"];
     if (kv.count("-out")) o.out = kv["-out"];

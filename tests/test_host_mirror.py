@@ -146,15 +146,27 @@ def test_testbank_known_answers(golden_dir):
 
 
 def test_cli_argument_handling(tmp_path):
-    """same conventions as the reference's main: EXCEPTION: <msg> on stdout, EXIT_FAILURE (src/SimkaPotara.cpp:147-163)"""
+    """same conventions as the reference's main: a failing run prints EXCEPTION: <msg> on stdout and ends with EXIT_FAILURE
+    (src/SimkaPotara.cpp:147-163); a mistake on the command line prints ERROR: lines and the option list and ends with
+    EXIT_SUCCESS (GATB Tool / OptionFailure) -- checked against the reference binary where it is built"""
     exe = str(SIMKA_BIN)
     assert os.path.exists(exe)
     r = subprocess.run([exe, "-help"], capture_output=True, text=True)
     assert r.returncode == 0 and "-abundance-min" in r.stdout and "-complex-dist" in r.stdout
-    r = subprocess.run([exe, "-in", "x"], capture_output=True, text=True)
-    assert r.returncode == 1 and r.stdout.startswith("EXCEPTION: ") and "-out-tmp" in r.stdout
-    r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-bogus"], capture_output=True, text=True)
-    assert r.returncode == 1 and "Unknown parameter" in r.stdout
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bin", "simka")
+    for args, errors in ((["-in", "x"], ["ERROR: Option '-out-tmp' is mandatory"]),
+                         (["-in", "x", "-out-tmp", str(tmp_path), "-bogus"], ["ERROR: Unknown parameter '-bogus'"]),
+                         ([], ["ERROR: Option '-in' is mandatory", "ERROR: Option '-out-tmp' is mandatory"]),
+                         (["-out-tmp", str(tmp_path), "-in"], ["ERROR: Too few arguments for the -in option..."])):
+        r = subprocess.run([exe] + args, capture_output=True, text=True)
+        assert r.returncode == 0 and "-abundance-min" in r.stdout
+        for e in errors:
+            assert e in r.stdout.splitlines(), (args, r.stdout[:300])
+        if os.access(ref, os.X_OK):
+            rr = subprocess.run([ref] + args, capture_output=True, text=True)
+            assert rr.returncode == 0
+            for e in errors:
+                assert e in rr.stdout.splitlines(), (args, rr.stdout[:300])
     r = subprocess.run([exe, "-in", "/nonexistent", "-out-tmp", str(tmp_path), "-out", str(tmp_path / "o")], capture_output=True, text=True)
     assert r.returncode == 1 and "does not exist" in r.stdout
     r = subprocess.run([exe, "-in", "x", "-out-tmp", str(tmp_path), "-max-memory", "100"], capture_output=True, text=True)
