@@ -463,7 +463,7 @@ def test_cli_simka_reproduces_truth(emulated_cli, monkeypatch, tmp_path, golden_
     G.test_simka_cli_max_reads_and_filters(d, golden_dir)
 
 
-@pytest.mark.parametrize("inp,k,t", [("example_n", 15, 0), ("example_n", 12, 2), ("example_n", 31, 2)])
+@pytest.mark.parametrize("inp,k,t", [("example_n", 15, 0), ("example_n", 12, 2), ("example_n", 31, 2), ("example_fmt", 21, 0), ("example_fmt", 15, 2)])
 def test_reference_run_truth(emulated_cli, tmp_path, golden_dir, inp, k, t):
     """truth produced by the reference binaries (k <= 15 MiniKC quirks, N runs, short reads): library and command line"""
     import test_gpu_parity as G

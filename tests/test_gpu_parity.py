@@ -47,7 +47,8 @@ def test_example_csv_byte_identical(golden_dir, k, t):
 
 
 @pytest.mark.parametrize("inp,k", [("example", 9), ("example", 15), ("example", 16), ("example_n", 12), ("example_n", 15), ("example_n", 21), ("example_n", 31),
-                                   ("example", 32), ("example", 41), ("example", 63), ("example_n", 41)])  # k > 31: 128-bit k-mers (kernels/wide.cuh)
+                                   ("example", 32), ("example", 41), ("example", 63), ("example_n", 41),  # k > 31: 128-bit k-mers (kernels/wide.cuh)
+                                   ("example_fmt", 15), ("example_fmt", 31)])  # file-format corner cases
 @pytest.mark.parametrize("t", [0, 2])
 def test_reference_run_truth_byte_identical(golden_dir, inp, k, t):
     """Truth produced by the reference binaries themselves (tools/make_ref_golden.py) for what its own truth files do not
@@ -65,9 +66,11 @@ def test_reference_run_truth_byte_identical(golden_dir, inp, k, t):
 
 
 @pytest.mark.parametrize("inp,k,t", [("example_n", 15, 0), ("example_n", 12, 2), ("example_n", 31, 2), ("example", 16, 0), ("example", 41, 2), ("example_n", 41, 0),
-                                     ("example", 63, 0)])
+                                     ("example", 63, 0), ("example_fmt", 21, 0), ("example_fmt", 31, 2), ("example_fmt", 15, 2)])
 def test_simka_cli_reproduces_reference_run_truth(tmp_path, golden_dir, inp, k, t):
-    """same, through the `simka` command line of this build (its own FASTA / FASTQ / gz readers)"""
+    """same, through the `simka` command line of this build (its own FASTA / FASTQ / gz readers); example_fmt: FASTQ whose quality
+    lines start with '@' / '+' / '>', CR-LF, blank lines, header-only records, blanks inside sequence lines, no final newline,
+    IUPAC codes, a two-member gz file, long headers"""
     import gzip
     import subprocess
     from simka_b200.build import SIMKA_BIN

@@ -244,7 +244,9 @@ def test_dsk_solid_counts_known_answers(golden_dir):
 # read's k-mers); example_n holds N runs, lower case, short reads, multi-line FASTA, a FASTQ.gz and a paired sample.
 REF_TRUTH_CASES = [("example", 9), ("example", 15), ("example", 16), ("example_n", 12), ("example_n", 15), ("example_n", 21), ("example_n", 31),
                    # k > 31: Kmer<64> / LargeInt<2>, 128-bit k-mers
-                   ("example", 32), ("example", 41), ("example", 63), ("example_n", 41)]
+                   ("example", 32), ("example", 41), ("example", 63), ("example_n", 41),
+                   # file-format corner cases (tools/make_ref_golden.py, make_example_fmt)
+                   ("example_fmt", 15), ("example_fmt", 21), ("example_fmt", 31)]
 
 
 def ref_truth_dir(golden_dir, inp, k, t):

@@ -26,6 +26,8 @@ CASES = [("example", k, a) for k in (9, 15, 16, 32, 41, 63) for a in (0, 2)]
 CASES += [("example_n", k, a) for k in (12, 15, 21, 31, 41) for a in (0, 2)]
 
 
+# file-format corner cases (make_example_fmt)
+CASES += [("example_fmt", k, a) for k in (15, 21, 31) for a in (0, 2)]
 # option cases: the read filters and limits of the command line, run by the reference itself (tag -> extra arguments); input example_n
 OPTION_CASES = {
     "maxreads50": ["-max-reads", "50"],
@@ -87,12 +89,66 @@ def make_example_n(dst):
         f.write("S1: S1.fasta\nS2: S2.fasta\nS3: S3.fastq.gz\nS4: S4_1.fasta ; S4_2.fasta\nS5: S1.fasta , S2.fasta\n")
 
 
+def make_example_fmt(dst):
+    """tests/golden/example_fmt: file-format corner cases, seeded, written once and committed: FASTQ whose quality lines start with
+    '@', '+' or '>' (some records multi-line), CR-LF line ends, blank lines / header-only records / blanks inside sequence lines /
+    no final newline, IUPAC codes with dots, dashes and lower case, a gz file of two concatenated members, long headers with '>'
+    and '@' inside"""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    alpha = np.frombuffer(b"ACGT", np.uint8)
+    g = alpha[rng.integers(0, 4, 3000)].tobytes()
+    R = []
+    for _ in range(80):
+        s0 = int(rng.integers(0, len(g) - 90))
+        R.append(g[s0:s0 + 90])
+    files = {}
+    fq = b""
+    for i, r in enumerate(R):
+        q = bytes([b"@+>I"[(i + j) % 4] for j in range(len(r))])
+        if i % 3 == 0:
+            fq += b"@r%d\n" % i + r[:45] + b"\n" + r[45:] + b"\n+r%d\n" % i + q[:45] + b"\n" + q[45:] + b"\n"
+        else:
+            fq += b"@r%d desc\n" % i + r + b"\n+\n" + q + b"\n"
+    files["nastyq.fastq"] = fq
+    files["crlf.fasta"] = b"".join(b">r%d\r\n" % i + r + b"\r\n" for i, r in enumerate(R))
+    fa = b""
+    for i, r in enumerate(R):
+        if i % 10 == 0:
+            fa += b">empty%d\n" % i
+        if i % 7 == 0:
+            fa += b"\n"
+        fa += b">r%d\n" % i + r[:30] + b" " + r[30:60] + b"\t" + r[60:] + b"\n"
+    files["odd.fasta"] = fa.rstrip(b"\n")
+    fa = b""
+    for i, r in enumerate(R):
+        rr = bytearray(r)
+        for ch, pos in ((b"R", 10), (b"y", 25), (b"K", 40), (b"-", 55), (b".", 70), (b"n", 80), (b"U", 5)):
+            if (i + pos) % 3 == 0:
+                rr[pos] = ch[0]
+        if i % 2:
+            rr = bytearray(bytes(rr).lower())
+        fa += b">r%d\n" % i + bytes(rr) + b"\n"
+    files["iupac.fasta"] = fa
+    half = len(R) // 2
+    files["multi.fasta.gz"] = gzip.compress(b"".join(b">a%d\n" % i + r + b"\n" for i, r in enumerate(R[:half])), mtime=0) + \
+        gzip.compress(b"".join(b">b%d\n" % i + r + b"\n" for i, r in enumerate(R[half:])), mtime=0)
+    files["hdr.fasta"] = b"".join(b">r%d some>thing @odd " % i + b"x" * 300 + b"\n" + r + b"\n" for i, r in enumerate(R))
+    os.makedirs(dst, exist_ok=True)
+    for n, c in files.items():
+        open(os.path.join(dst, n), "wb").write(c)
+    open(os.path.join(dst, "simka_input.txt"), "w").write("".join(f"F{i}: {n}\n" for i, n in enumerate(files)))
+
+
 def main():
     if not os.path.exists(SIMKA):
         sys.exit("oracle/_ref/bin/simka missing: run oracle/build_ref.sh first")
     exn = os.path.join(ROOT, "tests", "golden", "example_n")
     if not os.path.exists(os.path.join(exn, "simka_input.txt")):
         make_example_n(exn)
+    exf = os.path.join(ROOT, "tests", "golden", "example_fmt")
+    if not os.path.exists(os.path.join(exf, "simka_input.txt")):
+        make_example_fmt(exf)
     cases = [(inp, k, amin, "", []) for inp, k, amin in CASES]
     cases += [("example_n", k, amin, tag, extra) for tag, extra in OPTION_CASES.items() for k, amin in OPTION_KT.get(tag, ((21, 1), (31, 2)))]
     for inp, k, amin, tag, extra in cases:
