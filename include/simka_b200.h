@@ -225,6 +225,13 @@ uint64_t simka_pack_reads_k(const char *seqs, const uint64_t *read_off, uint64_t
  * otherwise both outputs are malloc'ed (simka_host_free).  The host readers of the command lines do the same while parsing. */
 int simka_minikc_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out,
                         uint64_t **read_off_out);
+/* SimkaMin has the same stale-vector behaviour for EVERY k: SelectKmersCommand refills its k-mer vector with Model::build, which
+ * leaves it untouched for a read shorter than k, and then walks it again (src/simkaMin/SimkaMinCount.hpp:217-263): the previous
+ * long-enough read is counted once more.  Same contract as simka_minikc_replay, for any kmer_size; apply it to the reads of a
+ * sample before packing them for simkamin_gpu_sketch.  (The reference hands the reads to its threads in groups of 1000 and every
+ * thread keeps its own vector, so for a short read that STARTS such a group the replayed read depends on the thread schedule;
+ * this is the single-thread order, `-nb-cores 1`.) */
+int simkamin_short_read_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out, uint64_t **read_off_out);
 
 /* Replaces SimkaDistance + SimkaStatistics::outputMatrix (src/core/SimkaDistance.cpp:603-649,920-1226).
  * Matrix order = the reference's output order: 15 default, +3 if simple, +3 if complex. */

@@ -945,9 +945,14 @@ uint32_t orc_simkamin_sketch(const char *seqs, const uint64_t *read_off, uint64_
     uint64_t *heap = malloc(((size_t)sketch_size + 1) * 8);
     size_t hn = 0;
     uint64_t *canon = NULL; uint8_t *valid = NULL; size_t cap = 0;
-    for (uint64_t r = 0; r < n_reads; r++) {
+    /* A read shorter than k: SelectKmersCommand refills its k-mer vector with Model::build, which leaves it untouched, and walks
+     * it again (src/simkaMin/SimkaMinCount.hpp:217-263; GC/kmer/impl/Model.hpp:603-610) -- the previous long-enough read is counted
+     * once more.  (Single-thread order: the reference hands groups of 1000 reads to its threads, each with its own vector.) */
+    int64_t last = -1;
+    for (uint64_t r0 = 0; r0 < n_reads; r0++) {
+        uint64_t r = r0;
+        if ((size_t)(read_off[r0 + 1] - read_off[r0]) < (size_t)k) { if (last < 0) continue; r = (uint64_t)last; } else last = (int64_t)r0;
         const size_t len = (size_t)(read_off[r + 1] - read_off[r]);
-        if (len < (size_t)k) continue;
         if (len > cap) { cap = len * 2; canon = realloc(canon, cap * 8); valid = realloc(valid, cap); }
         const size_t nk = orc_canonical_kmers(seqs + read_off[r], len, k, canon, valid);
         for (size_t i = 0; i < nk; i++) {
@@ -991,9 +996,14 @@ uint32_t orc_simkamin_sketch_filtered(const char *seqs, const uint64_t *read_off
     uint64_t *heap = malloc(((size_t)sketch_size + 1) * 8);
     size_t hn = 0;
     uint64_t *canon = NULL; uint8_t *valid = NULL; size_t cap = 0;
-    for (uint64_t r = 0; r < n_reads; r++) {
+    /* A read shorter than k: SelectKmersCommand refills its k-mer vector with Model::build, which leaves it untouched, and walks
+     * it again (src/simkaMin/SimkaMinCount.hpp:217-263; GC/kmer/impl/Model.hpp:603-610) -- the previous long-enough read is counted
+     * once more.  (Single-thread order: the reference hands groups of 1000 reads to its threads, each with its own vector.) */
+    int64_t last = -1;
+    for (uint64_t r0 = 0; r0 < n_reads; r0++) {
+        uint64_t r = r0;
+        if ((size_t)(read_off[r0 + 1] - read_off[r0]) < (size_t)k) { if (last < 0) continue; r = (uint64_t)last; } else last = (int64_t)r0;
         const size_t len = (size_t)(read_off[r + 1] - read_off[r]);
-        if (len < (size_t)k) continue;
         if (len > cap) { cap = len * 2; canon = realloc(canon, cap * 8); valid = realloc(valid, cap); }
         const size_t nk = orc_canonical_kmers(seqs + read_off[r], len, k, canon, valid);
         for (size_t i = 0; i < nk; i++) {

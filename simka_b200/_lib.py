@@ -96,6 +96,7 @@ SYMBOLS = {
     "simka_host_read_bank": (C.c_int64, [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "simka_host_free": (None, [C.c_void_p]),
     "simka_minikc_replay": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "simkamin_short_read_replay": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "simkamin_gpu_release": (C.c_int, []),
     "simkamin_gpu_distance_rect": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, f32p, f32p, f32p]),
     "simka_b200_version": (C.c_char_p, []),

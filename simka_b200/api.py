@@ -26,17 +26,19 @@ def _vp(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def minikc_replay(seqs: np.ndarray, read_off: np.ndarray, kmer_size: int):
+def minikc_replay(seqs: np.ndarray, read_off: np.ndarray, kmer_size: int, any_k: bool = False):
     """k <= 15: every read shorter than k replaced by a copy of the previous long-enough read (the MiniKC iterator quirk,
-    simka_minikc_replay in include/simka_b200.h).  Returns the inputs unchanged when nothing is to be replaced."""
-    if kmer_size > 15 or len(read_off) < 2:
+    simka_minikc_replay in include/simka_b200.h).  any_k: the same for every k (SimkaMin, simkamin_short_read_replay).
+    Returns the inputs unchanged when nothing is to be replaced."""
+    if (kmer_size > 15 and not any_k) or len(read_off) < 2:
         return seqs, read_off
     L = _lib.load()
     seqs = np.ascontiguousarray(seqs, np.uint8)
     read_off = np.ascontiguousarray(read_off, np.uint64)
     ps, po = C.c_void_p(), C.c_void_p()
     src = seqs if seqs.size else np.zeros(1, np.uint8)
-    rc = L.simka_minikc_replay(_vp(src), _vp(read_off), len(read_off) - 1, kmer_size, C.byref(ps), C.byref(po))
+    fn = L.simkamin_short_read_replay if any_k else L.simka_minikc_replay
+    rc = fn(_vp(src), _vp(read_off), len(read_off) - 1, kmer_size, C.byref(ps), C.byref(po))
     if rc != 0:
         raise SimkaError(f"simka_minikc_replay failed ({rc})")
     if not ps.value:
@@ -377,6 +379,7 @@ def simkamin_sketch(seqs: np.ndarray, read_off: np.ndarray, kmer_size: int, sket
     """SimkaMin sketch of one sample on the GPU (src/simkaMin/SimkaMinCount.hpp:217-338; filter=True: the -filter option, :341-380).
     -> (hashes uint64[s] ascending, zero padding at the front; counts uint32[s]; n_selected)"""
     L = _lib.load()
+    seqs, read_off = minikc_replay(seqs, read_off, kmer_size, any_k=True)  # a read shorter than k counts the previous read again
     packed, bad, nw = pack_reads(seqs, read_off)
     h = np.zeros(sketch_size, np.uint64)
     c = np.zeros(sketch_size, np.uint32)

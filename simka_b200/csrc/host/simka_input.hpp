@@ -155,7 +155,8 @@ inline uint64_t read_sample(const SampleSpec &spec, const SimkaSequenceFilter &f
 struct MiniKCReplay {
     size_t k = 0;  // 0: off (k > 15)
     std::string last;
-    explicit MiniKCReplay(int kmer_size = 0) : k(kmer_size > 0 && kmer_size <= 15 ? (size_t)kmer_size : 0) {}
+    // any_k: SimkaMin's SelectKmersCommand has the same stale vector for every k (src/simkaMin/SimkaMinCount.hpp:217-263)
+    explicit MiniKCReplay(int kmer_size = 0, bool any_k = false) : k(kmer_size > 0 && (kmer_size <= 15 || any_k) ? (size_t)kmer_size : 0) {}
     // the read just appended to `seqs` at [start, seqs.size())
     void apply(std::string &seqs, size_t start) {
         if (!k) return;
@@ -166,9 +167,9 @@ struct MiniKCReplay {
 
 template <class AfterRead>
 inline uint64_t read_sample_into(const SampleSpec &spec, const SimkaSequenceFilter &filter, uint64_t maxReads, std::string &seqs,
-                                 std::vector<uint64_t> &off, AfterRead after_read, int kmer_size = 0) {
+                                 std::vector<uint64_t> &off, AfterRead after_read, int kmer_size = 0, bool replay_any_k = false) {
     uint64_t total = 0;
-    MiniKCReplay replay(kmer_size);
+    MiniKCReplay replay(kmer_size, replay_any_k);
     {   // room for the whole sample up front (bases < file bytes; gzip files weighted 4x; at most 1 GiB, the caller flushes in
         // batches anyway): growing a 150 MB string by doubling re-copies it and touches twice the pages -- 0.75 -> 1.35 GB/s
         // of FASTA per thread

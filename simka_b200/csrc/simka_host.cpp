@@ -376,10 +376,23 @@ uint64_t simka_pack_reads_k(const char *seqs, const uint64_t *read_off, uint64_t
 }
 
 
-int simka_minikc_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out, uint64_t **read_off_out) try {
+static int short_read_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out, uint64_t **read_off_out);
+
+int simka_minikc_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out, uint64_t **read_off_out) {
     if (!seqs_out || !read_off_out || (n_reads && (!seqs || !read_off))) return SIMKA_ERR_INVALID;
     *seqs_out = nullptr; *read_off_out = nullptr;
     if (kmer_size > 15 || kmer_size < 1) return SIMKA_OK;
+    return short_read_replay(seqs, read_off, n_reads, kmer_size, seqs_out, read_off_out);
+}
+
+int simkamin_short_read_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out, uint64_t **read_off_out) {
+    if (!seqs_out || !read_off_out || (n_reads && (!seqs || !read_off))) return SIMKA_ERR_INVALID;
+    *seqs_out = nullptr; *read_off_out = nullptr;
+    if (kmer_size < 1) return SIMKA_OK;
+    return short_read_replay(seqs, read_off, n_reads, kmer_size, seqs_out, read_off_out);
+}
+
+static int short_read_replay(const char *seqs, const uint64_t *read_off, uint64_t n_reads, int kmer_size, char **seqs_out, uint64_t **read_off_out) try {
     const uint64_t k = (uint64_t)kmer_size;
     bool any = false;
     uint64_t total = 0, last = 0;

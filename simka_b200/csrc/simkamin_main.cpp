@@ -113,7 +113,7 @@ int do_sketch(std::map<std::string, std::string> &kv) {
             try {
                 seqs.clear();
                 off.assign(1, 0);
-                read_sample_into(samples[i], filter, max_reads, seqs, off, [] {});
+                read_sample_into(samples[i], filter, max_reads, seqs, off, [] {}, k, true);  // (short reads replay the previous read)
                 P.reads = off.size() - 1;
                 P.words = simka_pack_words(seqs.size(), P.reads);
                 P.packed.resize(P.words + 1);

@@ -752,7 +752,8 @@ SIMKAMIN_REF_CASES = [["-kmer-size", "21", "-nb-kmers", "500"], ["-kmer-size", "
 @pytest.mark.parametrize("case", range(len(SIMKAMIN_REF_CASES)))
 def test_simkamincore_against_reference_binary(tmp_path, golden_dir, case):
     """`simkaMinCore sketch | distance | export` of this build next to the REFERENCE simkaMinCore (oracle/_ref/bin) on the same input --
-    multi-line FASTA with lower case and N runs, FASTQ.gz, a paired and a concatenated sample -- and the same options: the sketch
+    multi-line FASTA with lower case and N runs, reads shorter than k, FASTQ.gz, a paired and a concatenated sample, the file-format
+    corner cases of example_fmt -- and the same options: the sketch
     files are equal byte for byte outside the 4 padding bytes of every 16-byte record (the reference writes them uninitialised),
     the exported matrices byte for byte; and each build's `distance` reads the other's sketch file."""
     import gzip
@@ -762,9 +763,12 @@ def test_simkamincore_against_reference_binary(tmp_path, golden_dir, case):
     ref = os.path.join(REF_BIN, "simkaMinCore")
     if not os.access(ref, os.X_OK):
         pytest.skip("oracle/_ref/bin not built")
-    ex = os.path.join(golden_dir, "example_n")  # (without S1: reads shorter than k make the reference's sketch depend on its thread schedule)
+    # S1 and F2 hold reads shorter than k / header-only records: SelectKmersCommand then counts the previous read again
+    # (simkamin_short_read_replay; deterministic in the reference with one core, which is what both are run with)
+    ex, fm = os.path.join(golden_dir, "example_n"), os.path.join(golden_dir, "example_fmt")
     inp = tmp_path / "in.txt"
-    inp.write_text(f"S2: {ex}/S2.fasta\nS3: {ex}/S3.fastq.gz\nS4: {ex}/S4_1.fasta ; {ex}/S4_2.fasta\nS6: {ex}/S2.fasta , {ex}/S4_1.fasta\n")
+    inp.write_text(f"S1: {ex}/S1.fasta\nS2: {ex}/S2.fasta\nS3: {ex}/S3.fastq.gz\nS4: {ex}/S4_1.fasta ; {ex}/S4_2.fasta\nS6: {ex}/S2.fasta , {ex}/S4_1.fasta\n"
+                   f"F0: {fm}/nastyq.fastq\nF2: {fm}/odd.fasta\nF3: {fm}/iupac.fasta\nF4: {fm}/multi.fasta.gz\n")
     opts = SIMKAMIN_REF_CASES[case]
 
     def run(exe, tag, sketch=None):
@@ -787,7 +791,7 @@ def test_simkamincore_against_reference_binary(tmp_path, golden_dir, case):
     assert a.size == b.size
     differing = np.nonzero(a != b)[0]
     # 13 header bytes (k, sketch size, seed, number of datasets), then the records {u64 hash, u32 count, 4 padding bytes}, then the identifiers
-    n_rec = 4 * int(opts[opts.index("-nb-kmers") + 1])
+    n_rec = 9 * int(opts[opts.index("-nb-kmers") + 1])
     rec0 = 13
     assert differing.size == 0 or (differing.min() >= rec0 and differing.max() < rec0 + 16 * n_rec and
                                    set(((differing - rec0) % 16).tolist()) <= {12, 13, 14, 15})
