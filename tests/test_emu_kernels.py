@@ -403,7 +403,7 @@ def test_sample_sharded_exchange_equals_whole(monkeypatch, world, superk, n):
     if superk:
         monkeypatch.setenv("SIMKA_B200_SUPERK", "1")
     # (n = 70: the merge context of a rank holds imported lists of > 64 samples and merges them by sample tiles)
-    samples = small_samples(5, 300) if n == 5 else small_samples(n, 24, read_len=80, n_genomes=2, genome_len=300)
+    samples = small_samples(5, 300) if n == 5 else small_samples(n, 14, read_len=80, n_genomes=2, genome_len=200)
     run = oracle_run(samples, 31, 2)
     N = len(samples)
     comm = _FakeComm(world)
@@ -594,7 +594,7 @@ def test_merge_tiles_huge_abundances_and_rare_sweeps(monkeypatch):
     np.testing.assert_allclose(a.kullback_leibler, b.kullback_leibler, rtol=1e-10, atol=0)
 
 
-@pytest.mark.parametrize("n,batch", [(130, None), (96, "300")])
+@pytest.mark.parametrize("n,batch", [(100, None), (96, "1500")])
 def test_merge_by_sample_tiles(monkeypatch, n, batch):
     """64 < N <= 512: records of the shared k-mers (sample bitmap + abundances in sample order) written once per merge bin, pairs
     accumulated per tile of 32 x 32 samples in shared memory (merge_tiles.cuh) -- several sample blocks incl. a partial one,
