@@ -797,3 +797,55 @@ def test_simkamincore_against_reference_binary(tmp_path, golden_dir, case):
                                    set(((differing - rec0) % 16).tolist()) <= {12, 13, 14, 15})
     assert run(ref, "ref_on_ours", sketch=sk_our)[1] == m_ref
     assert run(str(SIMKAMIN_BIN), "ours_on_ref", sketch=sk_ref)[1] == m_ref
+
+
+def test_simkamincore_file_tools_against_reference_binary(tmp_path, golden_dir):
+    """`simkaMinCore info | distance (blocks into an existing result directory) | matrix-update | append | export` next to the REFERENCE
+    binary on the same two sketch files: same texts, binary matrices, appended sketch file (outside the reference's uninitialised
+    padding bytes) and exported matrices"""
+    import gzip
+    import shutil
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    ours = str(SIMKA_BIN.parent / "simkaMinCore")
+    ref = os.path.join(REF_BIN, "simkaMinCore")
+    if not os.access(ref, os.X_OK):
+        pytest.skip("oracle/_ref/bin not built")
+    ex = os.path.join(golden_dir, "example_n")
+    (tmp_path / "a.txt").write_text(f"S2: {ex}/S2.fasta\nS3: {ex}/S3.fastq.gz\n")
+    (tmp_path / "b.txt").write_text(f"S4: {ex}/S4_1.fasta ; {ex}/S4_2.fasta\nS6: {ex}/S2.fasta , {ex}/S4_1.fasta\nS1: {ex}/S1.fasta\n")
+
+    def masked(path):  # 13 header bytes, n x s records {u64, u32, 4 padding bytes}, identifiers
+        raw = np.fromfile(path, np.uint8).copy()
+        s, n = int(raw[1:5].view(np.uint32)[0]), int(raw[9:13].view(np.uint32)[0])
+        raw[13:13 + 16 * n * s].reshape(-1, 16)[:, 12:] = 0
+        return raw.tobytes()
+
+    res = {}
+    for tag, exe in (("ref", ref), ("our", ours)):
+        d = tmp_path / tag
+        (d / "dist").mkdir(parents=True)
+
+        def run(*a):
+            r = subprocess.run([exe] + [str(x) for x in a], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, (tag, a, r.stdout + r.stderr)
+            return r.stdout.replace(str(d), "<dir>")
+
+        o = {}
+        for name in ("a", "b"):
+            run("sketch", "-in", tmp_path / f"{name}.txt", "-out", d / f"{name}.bin", "-kmer-size", "21", "-nb-kmers", "300", "-nb-cores", "1", "-max-memory", "4000")
+        o["info"] = run("info", "-in", d / "a.bin")
+        run("distance", "-in1", d / "a.bin", "-in2", d / "a.bin", "-out", d / "dist", "-nb-cores", "1")
+        run("distance", "-in1", d / "a.bin", "-in2", d / "b.bin", "-out", d / "dist", "-nb-cores", "1")
+        run("distance", "-in1", d / "b.bin", "-in2", d / "b.bin", "-out", d / "dist", "-nb-cores", "1")
+        o["update"] = run("matrix-update", "-in", d / "dist", "-in1", d / "a.bin", "-in2", d / "b.bin")
+        o["append"] = run("append", "-in1", d / "a.bin", "-in2", d / "b.bin")
+        o["info2"] = run("info", "-in", d / "a.bin")
+        run("export", "-in", d / "dist", "-in1", d / "a.bin", "-in2", d / "a.bin", "-out", d, "-nb-cores", "1")
+        o["sketch"] = masked(d / "a.bin")
+        o["bins"] = {f: open(d / "dist" / f, "rb").read() for f in sorted(os.listdir(d / "dist"))}
+        o["csv"] = {f: gzip.open(d / f).read() for f in sorted(os.listdir(d)) if f.endswith(".csv.gz")}
+        res[tag] = o
+    assert len(res["ref"]["bins"]) == 2 and len(res["ref"]["csv"]) == 2 and "Nb Datasets: 5" in res["ref"]["info2"]
+    for key in ("info", "update", "append", "info2", "sketch", "bins", "csv"):
+        assert res["our"][key] == res["ref"][key], key
