@@ -288,6 +288,9 @@ int simkamin_gpu_distance(int device, const uint64_t *hashes, const uint32_t *co
 uint64_t simka_host_kmers(const char *seq, uint64_t len, int k, int canonical, uint64_t *out, uint8_t *valid);
 uint64_t simka_host_minimizer(uint64_t kmer, int k, int m);
 float simka_host_shannon_index(const char *seq, uint64_t len);
+/* Repartitor (GC/kmer/impl/PartiInfo.cpp:228-261) of a reference run, read from its config.h5 (S/SimkaPotara.hpp:573-606,767): the
+ * partition table[minimizer(kmer)] of n canonical k-mers.  Returns the number of partitions, -1 if the file cannot be read. */
+int simka_host_repartition(const char *config_h5, const uint64_t *kmers, uint64_t n, int k, uint16_t *parts_out);
 int64_t simka_host_read_bank(const char *uri, char **seqs, uint64_t **read_off);
 /* IBank::estimateNbItems (GC/bank/impl/BankFasta.cpp:728-775, AbstractBank.hpp:71-74): sequences at the head of every file
  * extrapolated to the file size (a gz file = 4 x its compressed size); what `simka -max-reads 0` derives its limit from. */

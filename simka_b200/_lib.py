@@ -92,6 +92,7 @@ SYMBOLS = {
     "simka_host_kmers": (C.c_uint64, [C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p, C.POINTER(C.c_uint8)]),
     "simka_host_minimizer": (C.c_uint64, [C.c_uint64, C.c_int, C.c_int]),
     "simka_host_shannon_index": (C.c_float, [C.c_char_p, C.c_uint64]),
+    "simka_host_repartition": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "simka_host_estimate_nb_items": (C.c_int64, [C.c_char_p]),
     "simka_host_read_bank": (C.c_int64, [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "simka_host_free": (None, [C.c_void_p]),

@@ -1,12 +1,17 @@
 // simka_count_main.cpp -- `simkaCount`: stage 1 for ONE sample, with the reference's command line and temp files
 // (src/SimkaCount.cpp:80-98,174-368): reads <out-tmp-simka>/input/<bank-name>, counts on the GPU, writes
 // solid/part_<p>/__p__<bank-index>.gz, kmercount_per_partition/<bank-name>.txt and count_synchro/<bank-name>.ok.
-// config.h5 is not read: the partition of a k-mer is a fixed hash (any partition function merges correctly).
+// When the temp directory holds the config.h5 of a reference orchestrator, the k-mers go to the partitions ITS simkaCount would
+// send them to (repartition table of minimizers, host/repartitor.hpp), so samples counted here and by the reference can share one
+// temp directory; without it the partition is a fixed hash (any function merges correctly as long as every sample uses it).
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <iostream>
 #include <thread>
 
+#include "host/kmer_model.hpp"
+#include "host/repartitor.hpp"
 #include "host/simka_input.hpp"
 #include "host/stage_files.hpp"
 
@@ -61,7 +66,25 @@ static int run(int argc, char **argv) {
     // split the ascending list into the P partition files (each stays ascending)
     std::vector<std::vector<uint64_t>> pk(P);
     std::vector<std::vector<uint32_t>> pc(P);
-    for (uint64_t i = 0; i < n; i++) { const size_t p = stage::partition_of(kmers[i], P); pk[p].push_back(kmers[i]); pc[p].push_back(counts[i]); }
+    Repartitor rep;
+    {
+        std::ifstream probe((dir + "/config.h5").c_str(), std::ios::binary);
+        if (probe) {
+            probe.close();
+            rep = Repartitor::load(dir + "/config.h5");  // (a damaged file is an error, not a reason to fall back silently)
+            if (rep.nbpart != P) throw bank::Exception("config.h5 holds " + std::to_string(rep.nbpart) + " partitions, -nb-partitions says " + std::to_string(P));
+        }
+    }
+    if (rep.nbpart) {
+        Kmer<>::ModelMinimizer<> model((size_t)k, (size_t)rep.minimizer_size);
+        for (uint64_t i = 0; i < n; i++) {
+            const size_t p = rep.table[(size_t)model.getMinimizerValue(Kmer<>::Type(kmers[i]))];
+            pk[p].push_back(kmers[i]);
+            pc[p].push_back(counts[i]);
+        }
+    } else {
+        for (uint64_t i = 0; i < n; i++) { const size_t p = stage::partition_of(kmers[i], P); pk[p].push_back(kmers[i]); pc[p].push_back(counts[i]); }
+    }
     std::string per_part;
     for (size_t p = 0; p < P; p++) {
         stage::mkdirs(dir + "/solid/part_" + std::to_string(p));

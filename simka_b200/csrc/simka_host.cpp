@@ -15,6 +15,7 @@
 
 #include "../../include/simka_b200.h"
 #include "host/bank.hpp"
+#include "host/repartitor.hpp"
 #include "host/kmer_model.hpp"
 #include "host/simka_input.hpp"
 
@@ -443,6 +444,17 @@ uint64_t simka_host_minimizer(uint64_t kmer, int k, int m) {
         simka_b200::Kmer<>::ModelMinimizer<> model((size_t)k, (size_t)m);
         return model.getMinimizerValue(simka_b200::Kmer<>::Type(kmer));
     } catch (...) { return ~0ull; }
+}
+
+// partitions of canonical k-mers under the repartition table of a reference run's config.h5 (host/repartitor.hpp); returns the
+// number of partitions, -1 when the file cannot be read as one
+int simka_host_repartition(const char *config_h5, const uint64_t *kmers, uint64_t n, int k, uint16_t *parts_out) {
+    try {
+        const simka_b200::Repartitor r = simka_b200::Repartitor::load(config_h5);
+        simka_b200::Kmer<>::ModelMinimizer<> model((size_t)k, (size_t)r.minimizer_size);
+        for (uint64_t i = 0; i < n; i++) parts_out[i] = r.table[(size_t)model.getMinimizerValue(simka_b200::Kmer<>::Type(kmers[i]))];
+        return (int)r.nbpart;
+    } catch (...) { return -1; }
 }
 
 float simka_host_shannon_index(const char *seq, uint64_t len) { return simka_b200::SimkaSequenceFilter::getShannonIndex(seq, (size_t)len); }

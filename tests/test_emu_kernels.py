@@ -494,6 +494,14 @@ def test_cross_run_with_reference_binaries_on_awkward_input(emulated_cli, tmp_pa
     G.test_cross_run_with_reference_binaries(tmp_path, golden_dir, count, merge, k, t, inp="example_n", tag=tag)
 
 
+@pytest.mark.parametrize("inp,k,t,mine", [("example", 21, 2, ("B", "D")), ("example_n", 15, 0, ("S2", "S4", "S5"))])
+def test_mixed_per_sample_counting_with_the_reference(emulated_cli, tmp_path, golden_dir, inp, k, t, mine):
+    import test_gpu_parity as G
+    if not os.access(os.path.join(G.REF_BIN, "simka"), os.X_OK):
+        pytest.skip("oracle/_ref/bin not built")
+    G.test_mixed_per_sample_counting_with_the_reference(tmp_path, golden_dir, inp, k, t, mine)
+
+
 def test_cli_stage_binaries_reference_temp_formats(emulated_cli, tmp_path, golden_dir):
     import test_gpu_parity as G
     G.test_stage_binaries_reference_temp_formats(tmp_path, golden_dir)

@@ -849,3 +849,66 @@ def test_simkamincore_file_tools_against_reference_binary(tmp_path, golden_dir):
     assert len(res["ref"]["bins"]) == 2 and len(res["ref"]["csv"]) == 2 and "Nb Datasets: 5" in res["ref"]["info2"]
     for key in ("info", "update", "append", "info2", "sketch", "bins", "csv"):
         assert res["our"][key] == res["ref"][key], key
+
+
+@pytest.mark.skipif(not os.access(os.path.join(REF_BIN, "simka"), os.X_OK), reason="oracle/_ref/bin (reference binaries, oracle/build_ref.sh) not built")
+@pytest.mark.parametrize("inp,k,t,mine", [("example", 21, 2, ("B", "D")), ("example_n", 15, 0, ("S2", "S4", "S5")), ("example", 31, 0, ("A", "B", "C", "D", "E"))])
+def test_mixed_per_sample_counting_with_the_reference(tmp_path, golden_dir, inp, k, t, mine):
+    """ONE run of the reference orchestrator in which some samples are counted by this build's simkaCount and the others by the
+    reference's: this build reads the run's config.h5 (host/repartitor.hpp: minimal HDF5 reader + Repartitor table) and sends every
+    solid k-mer to the partition the reference would -- the matrices equal the truth, and the partition files written here hold
+    exactly the records the reference's simkaCount writes for the same sample."""
+    import gzip
+    import shutil
+    import subprocess
+    from simka_b200.build import SIMKA_BIN
+    ours = os.path.dirname(str(SIMKA_BIN))
+
+    def run(tag, mine_ids):
+        b = tmp_path / ("bin_" + tag)
+        b.mkdir()
+        shutil.copy(os.path.join(REF_BIN, "simka"), b / "simka")
+        os.symlink(os.path.join(REF_BIN, "simkaCountProcess"), b / "simkaCountProcess")
+        os.symlink(os.path.join(REF_BIN, "simkaMerge"), b / "simkaMerge")
+        pick = "|".join(mine_ids) if mine_ids else "__none__"
+        (b / "simkaCount").write_text("#!/bin/bash\nname=\"\"; prev=\"\"\nfor a in \"$@\"; do if [ \"$prev\" = \"-bank-name\" ]; then name=\"$a\"; fi; prev=\"$a\"; done\n"
+                                      f"case \"$name\" in {pick}) exec {ours}/simkaCount \"$@\";; *) exec {REF_BIN}/simkaCount \"$@\";; esac\n")
+        (b / "simkaCount").chmod(0o755)
+        ex = tmp_path / ("ex_" + tag)
+        shutil.copytree(os.path.join(golden_dir, inp), ex)
+        proc = subprocess.Popen([str(b / "simka"), "-in", str(ex / "simka_input.txt"), "-out", str(tmp_path / ("out_" + tag)), "-out-tmp", str(tmp_path / ("tmp_" + tag)),
+                                 "-kmer-size", str(k), "-abundance-min", str(t), "-simple-dist", "-complex-dist", "-nb-cores", "4", "-max-memory", "4000", "-keep-tmp"],
+                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+        try:
+            stdout, _ = proc.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            os.killpg(proc.pid, signal.SIGKILL)
+            stdout, _ = proc.communicate()
+            pytest.fail("the orchestrator did not finish\n" + stdout[-1500:])
+        assert proc.returncode == 0, stdout[-2000:]
+        d = tmp_path / ("tmp_" + tag) / "simka_output_temp"
+        parts = {}
+        for p in sorted(os.listdir(d / "solid")):
+            for f in sorted(os.listdir(d / "solid" / p)):
+                parts[(p, f)] = gzip.open(d / "solid" / p / f).read()
+        counts = {f: open(d / "kmercount_per_partition" / f).read() for f in sorted(os.listdir(d / "kmercount_per_partition"))}
+        mats = {f: gzip.open(tmp_path / ("out_" + tag) / f).read() for f in sorted(os.listdir(tmp_path / ("out_" + tag)))}
+        logs = {f: open(d / "log" / f, errors="replace").read() for f in os.listdir(d / "log") if f.startswith("count_")}
+        return parts, counts, mats, logs
+
+    parts, counts, mats, logs = run("mixed", mine)
+    first = mine[0]
+    assert "simkaCount" in logs[f"count_{first}.txt"] and "DSK" not in logs[f"count_{first}.txt"]  # (this build's binary did count that sample)
+    tdir = os.path.join(golden_dir, "truth", f"results_k{k}_t{t}") if inp == "example" else os.path.join(golden_dir, "truth_ref", f"{inp}_results_k{k}_t{t}")
+    checked = 0
+    for f in sorted(os.listdir(tdir)):
+        if f.endswith(".csv"):
+            assert mats[f + ".gz"].decode() == open(os.path.join(tdir, f)).read(), f
+            checked += 1
+    assert checked >= 20
+    ref_parts, ref_counts, _, _ = run("ref", ())
+    assert sorted(parts) == sorted(ref_parts) and counts == ref_counts
+    rec = np.dtype([("k", "<u8"), ("b", "<u4"), ("pad", "<u4"), ("c", "<u8")])
+    for key in parts:  # the 4 padding bytes of a record are not compared
+        a, b = np.frombuffer(parts[key], rec), np.frombuffer(ref_parts[key], rec)
+        assert len(a) == len(b) and all(np.array_equal(a[x], b[x]) for x in ("k", "b", "c")), key

@@ -452,3 +452,24 @@ def test_estimate_nb_items_matches_reference_binary_beyond_the_threshold(tmp_pat
         per.append(n // len(groups))
     mine = {"min": min(per), "max": max(per), "mean": sum(per) // len(per), "limit": (min(per) + sum(per) // len(per)) // 2}
     assert mine == got, (per, text[-1500:])
+
+
+def test_repartitor_from_reference_config_h5(tmp_path, golden_dir):
+    """host/repartitor.hpp: the minimal HDF5 reader + Repartitor table on the config.h5 of a reference run (tests/golden/config_h5,
+    tools/make_ref_golden.py): every sampled solid k-mer goes to the partition the reference's simkaCount wrote it to; damaged or
+    foreign files are refused"""
+    import json
+    L = _lib.load()
+    fx = os.path.join(golden_dir, "config_h5")
+    want = json.load(open(os.path.join(fx, "kmer_partition.json")))
+    km = np.array([p[0] for p in want["kmer_partition"]], np.uint64)
+    part = np.array([p[1] for p in want["kmer_partition"]], np.uint16)
+    out = np.zeros(len(km), np.uint16)
+    nb = L.simka_host_repartition(os.fsencode(os.path.join(fx, "config.h5")), km.ctypes.data_as(C.c_void_p), len(km), want["kmer_size"], out.ctypes.data_as(C.c_void_p))
+    assert nb == want["nb_partitions"] and len(km) > 1000 and len(set(part.tolist())) == nb
+    np.testing.assert_array_equal(out, part)
+    raw = open(os.path.join(fx, "config.h5"), "rb").read()
+    for name, data in (("truncated.h5", raw[:3000]), ("not_hdf5.h5", b"x" * 5000), ("empty.h5", b""), ("bad_magic.h5", raw.replace(b"\x78\x56\x34\x12", b"\x00\x00\x00\x00"))):
+        (tmp_path / name).write_bytes(data)
+        assert L.simka_host_repartition(os.fsencode(str(tmp_path / name)), km.ctypes.data_as(C.c_void_p), 4, 21, out.ctypes.data_as(C.c_void_p)) == -1, name
+    assert L.simka_host_repartition(os.fsencode(str(tmp_path / "missing.h5")), km.ctypes.data_as(C.c_void_p), 4, 21, out.ctypes.data_as(C.c_void_p)) == -1

@@ -140,12 +140,37 @@ def make_example_fmt(dst):
     open(os.path.join(dst, "simka_input.txt"), "w").write("".join(f"F{i}: {n}\n" for i, n in enumerate(files)))
 
 
+def make_config_fixture(dst):
+    """tests/golden/config_h5: the config.h5 of a reference run on the example (k = 21) and, for 60 solid k-mers of every partition
+    file, the partition the reference's simkaCount put them in -- what host/repartitor.hpp must reproduce"""
+    import numpy as np
+    with tempfile.TemporaryDirectory() as td:
+        shutil.copytree(os.path.join(ROOT, "tests", "golden", "example"), os.path.join(td, "ex"))
+        subprocess.run([SIMKA, "-in", os.path.join(td, "ex", "simka_input.txt"), "-out", os.path.join(td, "out"), "-out-tmp", os.path.join(td, "tmp"), "-kmer-size", "21",
+                        "-abundance-min", "2", "-nb-cores", "4", "-max-memory", "4000", "-keep-tmp"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, check=True, cwd=td)
+        d = os.path.join(td, "tmp", "simka_output_temp")
+        os.makedirs(dst, exist_ok=True)
+        shutil.copy(os.path.join(d, "config.h5"), os.path.join(dst, "config.h5"))
+        pairs = []
+        rec = np.dtype([("k", "<u8"), ("b", "<u4"), ("pad", "<u4"), ("c", "<u8")])
+        for p in sorted(os.listdir(os.path.join(d, "solid"))):
+            for f in sorted(os.listdir(os.path.join(d, "solid", p))):
+                r = np.frombuffer(gzip.open(os.path.join(d, "solid", p, f)).read(), rec)
+                step = max(1, len(r) // 60)
+                pairs += [[int(x), int(p.split("_")[1])] for x in r["k"][::step][:60]]
+        json.dump({"kmer_size": 21, "nb_partitions": len(os.listdir(os.path.join(d, "solid"))), "kmer_partition": pairs}, open(os.path.join(dst, "kmer_partition.json"), "w"))
+        print(f"config fixture: {len(pairs)} (k-mer, partition) pairs")
+
+
 def main():
     if not os.path.exists(SIMKA):
         sys.exit("oracle/_ref/bin/simka missing: run oracle/build_ref.sh first")
     exn = os.path.join(ROOT, "tests", "golden", "example_n")
     if not os.path.exists(os.path.join(exn, "simka_input.txt")):
         make_example_n(exn)
+    cfg = os.path.join(ROOT, "tests", "golden", "config_h5")
+    if not os.path.exists(os.path.join(cfg, "config.h5")):
+        make_config_fixture(cfg)
     exf = os.path.join(ROOT, "tests", "golden", "example_fmt")
     if not os.path.exists(os.path.join(exf, "simka_input.txt")):
         make_example_fmt(exf)
